@@ -1,0 +1,25 @@
+# Build of the B200-native hot-path library.  sm_100a only (tcgen05 / TMEM / bulk-copy engine).
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+CSRC      := monocularsfm_b200/csrc
+LIB       := monocularsfm_b200/libmsfm_b200.so
+OBJDIR    := build/obj
+
+CU_SRCS   := $(wildcard $(CSRC)/*.cu)
+CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
+HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) include/msfm_b200.h
+
+all: $(LIB)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
+
+$(LIB): $(CU_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $^
+
+clean:
+	rm -rf build/obj $(LIB)
+
+.PHONY: all clean

@@ -1,0 +1,131 @@
+/*
+ * msfm_b200.h — C-ABI of the B200-native hot path of MonocularSfM.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status codes, no C++ or
+ * torch types.  The reference (nebula-beta/MonocularSfM) has no FFI layer of its own — its boundary is
+ * the C++ class API — so every entry point below cites the reference symbol whose arithmetic it
+ * replaces.  The C++ classes that keep the reference's names (FeatureUtils, FeatureMatcher,
+ * CeresBundelOptimizer, BundleData) live in monocularsfm_b200/host/ and call only these functions.
+ *
+ * Conventions
+ *   - return 0 (MSFM_OK) on success, a negative MSFM_E_* code otherwise; msfm_last_error() gives text.
+ *   - one msfm_ctx per (process, device).  A ctx is not thread-safe (the reference is single-threaded,
+ *     Database.cpp:297 opens SQLite NOMUTEX); different ctx objects are independent.
+ *   - "host" pointers are ordinary (pageable or pinned) CPU memory; "_dev" entry points take CUDA
+ *     device pointers valid on the ctx's device.  Nothing allocated by the library crosses the boundary
+ *     except the opaque ctx.
+ *   - there is NO CPU fallback: without a CUDA device msfm_init fails with MSFM_E_NO_DEVICE.
+ */
+#ifndef MSFM_B200_H_
+#define MSFM_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSFM_OK             0
+#define MSFM_E_INVALID     -1   /* bad argument */
+#define MSFM_E_NO_DEVICE   -2   /* no CUDA device / wrong architecture (needs sm_100) */
+#define MSFM_E_CUDA        -3   /* a CUDA call or kernel failed; see msfm_last_error */
+#define MSFM_E_CAPACITY    -4   /* caller's output buffer too small; needed size reported */
+#define MSFM_E_NOT_FOUND   -5   /* unknown image id / handle */
+#define MSFM_E_NUMERIC     -6   /* BA: linear solve failed (non-SPD reduced system) */
+
+#define MSFM_DESC_DIM 128       /* SIFT descriptor length (reference: cv::SIFT, FeatureUtils.cpp:27) */
+
+typedef struct msfm_ctx msfm_ctx;
+
+/* ---------------------------------------------------------------------------------------------
+ * Context
+ * ------------------------------------------------------------------------------------------- */
+int  msfm_init(msfm_ctx** ctx, int device_id);
+void msfm_destroy(msfm_ctx* ctx);
+/* ctx may be NULL: returns the last error of a failed msfm_init in this thread. */
+const char* msfm_last_error(const msfm_ctx* ctx);
+/* "major.minor.patch" of this library */
+const char* msfm_version(void);
+/* Blocks until all work queued on the ctx's stream has finished. */
+int  msfm_sync(msfm_ctx* ctx);
+/* The cudaStream_t (as void*) the ctx launches on — for callers that time with CUDA events. */
+void* msfm_stream(msfm_ctx* ctx);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+int64_t msfm_launch_count(const msfm_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * M-path: brute-force 2-NN descriptor matching
+ *
+ * Replaces the arithmetic behind
+ *   FeatureUtils::ComputeMatches        src/Feature/FeatureUtils.cpp:141-157  (OpenCV knnMatch k=2 + ratio test)
+ *   FeatureUtils::ComputeCrossMatches   src/Feature/FeatureUtils.cpp:160-174
+ *   FeatureUtils::CrossCheck            src/Feature/FeatureUtils.cpp:281-310
+ *   FeatureUtils::FilterMatchesByDistance src/Feature/FeatureUtils.cpp:208-218
+ * as driven by FeatureMatcher::MatchImagePairs, src/Feature/FeatureMatching.cpp:10-73.
+ *
+ * Descriptors are n x 128 uint8, row-major (the BASELINE.json contract; the reference's CV_32F
+ * blobs are bridged in the C++ shim).  Results are bit-exact with OpenCV's
+ * BFMatcher(NORM_L2) on the same uint8 inputs: distances are sqrtf of the exact integer squared
+ * distance, neighbours are ordered by (float distance, index), the ratio test is
+ * `d0 < (float)ratio * d1` in float.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Upload (or replace) the descriptor set of one image and keep it resident on the device.
+ * Replaces the per-pair Database::ReadDescriptors of FeatureMatching.cpp:32-33 (TODO "cache" at :31).
+ * n may be 0.  image_id >= 0 (image_t, Common/Types.h:9). */
+int msfm_desc_upload_u8(msfm_ctx* ctx, int32_t image_id, const uint8_t* desc_host, int32_t n);
+/* Same, source already in device memory (synthetic-data benchmarks; inputs resident in HBM). */
+int msfm_desc_upload_u8_dev(msfm_ctx* ctx, int32_t image_id, const uint8_t* desc_dev, int32_t n);
+/* Number of descriptors of a resident image, or MSFM_E_NOT_FOUND. */
+int msfm_desc_count(msfm_ctx* ctx, int32_t image_id);
+int msfm_desc_release(msfm_ctx* ctx, int32_t image_id);
+int msfm_desc_release_all(msfm_ctx* ctx);
+
+typedef struct {
+    double  max_distance;    /* FilterMatchesByDistance threshold (a double in the reference, FeatureMatching.h:30) on the
+                                u8 scale; < 0 disables (FeatureMatching.cpp:49) */
+    float   distance_ratio;  /* FeatureMatcher::distance_ratio_, narrowed to float as FeatureUtils.h:95 does (default 0.8f) */
+    int32_t cross_check;     /* FeatureMatcher::cross_check_ (default 1) */
+    int32_t opencv_quirks;   /* 1: reproduce CrossCheck's unordered_map default-0 behaviour (FeatureUtils.cpp:302) */
+    int32_t reserved;        /* must be 0 */
+} msfm_match_options;
+
+/* Match P image pairs.  pairs[p] = (image_id1, image_id2): image 1 is the query side (queryIdx),
+ * image 2 the train side (trainIdx), exactly as ComputeCrossMatches(desc1, desc2) at
+ * FeatureMatching.cpp:39.  Output is CSR: pair p's matches are rows
+ * out_offsets[p] .. out_offsets[p+1]-1 of out_matches, each (queryIdx, trainIdx), ascending queryIdx
+ * (the order of FeatureUtils.cpp:150-156).  out_dist (optional, may be NULL) receives the float
+ * DMatch::distance of each match.  capacity = number of rows out_matches/out_dist can hold; when too
+ * small the call returns MSFM_E_CAPACITY and *total_out holds the needed row count (offsets are
+ * still filled).  All output pointers are HOST memory. */
+int msfm_match_pairs(msfm_ctx* ctx, const int32_t* pairs /*[P][2]*/, int32_t P,
+                     const msfm_match_options* opt,
+                     int64_t* out_offsets /*[P+1]*/, int32_t* out_matches /*[capacity][2]*/,
+                     float* out_dist /*[capacity] or NULL*/, int64_t capacity, int64_t* total_out);
+
+/* Same computation, outputs left in DEVICE memory (no D2H; kernel-only timing, multi-GPU sharding).
+ * pairs_dev may be NULL when pairs_host is given. */
+int msfm_match_pairs_dev(msfm_ctx* ctx, const int32_t* pairs_host /*[P][2]*/, int32_t P,
+                         const msfm_match_options* opt,
+                         int64_t* out_offsets_dev /*[P+1]*/, int32_t* out_matches_dev /*[capacity][2]*/,
+                         float* out_dist_dev /*[capacity] or NULL*/, int64_t capacity, int64_t* total_out);
+
+/* Raw 2-NN of every row of A in B (host pointers) — the knnMatch(desc1, desc2, k=2) of
+ * FeatureUtils.cpp:149, exposed for parity tests.
+ *   mode 0: tensor-core path (tcgen05 distance tiles + fused top-2).  idx[i][1] is -1 unless the row
+ *           took the exact slow path: the production path only needs the runner-up's DISTANCE.
+ *   mode 1: exact CUDA-core scan of every row (also yields idx[i][1]).
+ * idx [nA][2] int32 (-1 = none), dist [nA][2] float (inf = none), d2 [nA][2] int32 exact squared
+ * distances (optional, may be NULL; -1 = none). */
+int msfm_match_knn2_u8(msfm_ctx* ctx, const uint8_t* A, int32_t nA, const uint8_t* B, int32_t nB,
+                       int32_t mode, int32_t* idx, float* dist, int32_t* d2);
+
+/* Counters of the last msfm_match_pairs / msfm_match_knn2_u8 call: [0] rows processed, [1] rows that needed the
+ * in-group rescan, [2] rows that took the exact slow path, [3] tensor-kernel work units.  */
+int msfm_match_stats(msfm_ctx* ctx, int64_t stats[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSFM_B200_H_ */

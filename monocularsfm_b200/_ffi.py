@@ -1,0 +1,190 @@
+"""ctypes binding of include/msfm_b200.h.  Fails loudly when the CUDA library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MSFM_OK = 0
+MSFM_E_CAPACITY = -4
+
+
+class MsfmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"msfm error {code}: {msg}")
+        self.code = code
+
+
+class MatchOptions(C.Structure):
+    """msfm_match_options (defaults = the reference's effective defaults, FeatureMatching.h:93-101,
+    except max_distance which is off on the u8 scale)."""
+    _fields_ = [("max_distance", C.c_double), ("distance_ratio", C.c_float), ("cross_check", C.c_int32),
+                ("opencv_quirks", C.c_int32), ("reserved", C.c_int32)]
+
+    def __init__(self, distance_ratio=0.8, max_distance=-1.0, cross_check=True, opencv_quirks=True):
+        super().__init__(float(max_distance), float(distance_ratio), int(bool(cross_check)),
+                         int(bool(opencv_quirks)), 0)
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libmsfm_b200.so")
+
+
+def header_path() -> str:
+    return os.path.join(_HERE, "..", "include", "msfm_b200.h")
+
+
+def exported_symbols():
+    """Names of all functions include/msfm_b200.h declares."""
+    with open(header_path()) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(msfm_[a-z0-9_]+)\s*\(", src)))
+
+
+def load_library():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise ImportError(
+            f"{p} is missing: build it with `make` (or __graft_entry__.build()).  There is no CPU fallback.")
+    lib = C.CDLL(p)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    P = C.POINTER
+    sig = {
+        "msfm_init": (C.c_int, [P(vp), C.c_int]),
+        "msfm_destroy": (None, [vp]),
+        "msfm_last_error": (C.c_char_p, [vp]),
+        "msfm_version": (C.c_char_p, []),
+        "msfm_sync": (C.c_int, [vp]),
+        "msfm_stream": (vp, [vp]),
+        "msfm_launch_count": (i64, [vp]),
+        "msfm_desc_upload_u8": (C.c_int, [vp, i32, vp, i32]),
+        "msfm_desc_upload_u8_dev": (C.c_int, [vp, i32, vp, i32]),
+        "msfm_desc_count": (C.c_int, [vp, i32]),
+        "msfm_desc_release": (C.c_int, [vp, i32]),
+        "msfm_desc_release_all": (C.c_int, [vp]),
+        "msfm_match_pairs": (C.c_int, [vp, vp, i32, P(MatchOptions), vp, vp, vp, i64, P(i64)]),
+        "msfm_match_pairs_dev": (C.c_int, [vp, vp, i32, P(MatchOptions), vp, vp, vp, i64, P(i64)]),
+        "msfm_match_knn2_u8": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, vp]),
+        "msfm_match_stats": (C.c_int, [vp, P(i64)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One msfm_ctx (one per process and device)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.msfm_init(C.byref(h), int(device))
+        if rc != MSFM_OK:
+            raise MsfmError(rc, (self.lib.msfm_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.msfm_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, allow=()):
+        if rc != MSFM_OK and rc not in allow:
+            raise MsfmError(rc, (self.lib.msfm_last_error(self.h) or b"").decode())
+        return rc
+
+    # ---- context
+    def sync(self):
+        self._check(self.lib.msfm_sync(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.msfm_stream(self.h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.msfm_launch_count(self.h))
+
+    # ---- M-path
+    def upload(self, image_id: int, desc: np.ndarray):
+        desc = np.ascontiguousarray(desc, dtype=np.uint8)
+        assert desc.ndim == 2 and desc.shape[1] == 128, desc.shape
+        self._check(self.lib.msfm_desc_upload_u8(self.h, image_id, _ptr(desc), desc.shape[0]))
+
+    def upload_dev(self, image_id: int, dev_ptr: int, n: int):
+        self._check(self.lib.msfm_desc_upload_u8_dev(self.h, image_id, C.c_void_p(dev_ptr), n))
+
+    def desc_count(self, image_id: int) -> int:
+        return self._check(self.lib.msfm_desc_count(self.h, image_id), allow=range(0, 1 << 30))
+
+    def release(self, image_id: int):
+        self._check(self.lib.msfm_desc_release(self.h, image_id))
+
+    def release_all(self):
+        self._check(self.lib.msfm_desc_release_all(self.h))
+
+    def match_pairs(self, pairs, opt: MatchOptions | None = None, capacity: int | None = None, want_dist=True):
+        """Returns (offsets int64 [P+1], matches int32 [total,2], dist float32 [total] | None)."""
+        opt = opt or MatchOptions()
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        npairs = pairs.shape[0]
+        if capacity is None:
+            capacity = max(1, sum(self.desc_count(int(p[0])) for p in pairs))
+        offsets = np.zeros(npairs + 1, np.int64)
+        matches = np.zeros((capacity, 2), np.int32)
+        dist = np.zeros(capacity, np.float32) if want_dist else None
+        total = C.c_int64(0)
+        self._check(self.lib.msfm_match_pairs(self.h, _ptr(pairs), npairs, C.byref(opt), _ptr(offsets), _ptr(matches),
+                                              _ptr(dist), capacity, C.byref(total)))
+        t = int(total.value)
+        return offsets, matches[:t], (dist[:t] if want_dist else None)
+
+    def match_pairs_dev(self, pairs, opt, offsets_ptr: int, matches_ptr: int, dist_ptr: int, capacity: int) -> int:
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        total = C.c_int64(0)
+        self._check(self.lib.msfm_match_pairs_dev(self.h, _ptr(pairs), pairs.shape[0], C.byref(opt),
+                                                  C.c_void_p(offsets_ptr), C.c_void_p(matches_ptr),
+                                                  C.c_void_p(dist_ptr) if dist_ptr else None, capacity,
+                                                  C.byref(total)))
+        return int(total.value)
+
+    def knn2(self, a: np.ndarray, b: np.ndarray, mode: int = 0):
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        b = np.ascontiguousarray(b, dtype=np.uint8)
+        na = a.shape[0]
+        idx = np.full((na, 2), -1, np.int32)
+        dist = np.full((na, 2), np.inf, np.float32)
+        d2 = np.full((na, 2), -1, np.int32)
+        self._check(self.lib.msfm_match_knn2_u8(self.h, _ptr(a), na, _ptr(b), b.shape[0], mode, _ptr(idx),
+                                                _ptr(dist), _ptr(d2)))
+        return idx, dist, d2
+
+    def match_stats(self):
+        s = (C.c_int64 * 4)()
+        self._check(self.lib.msfm_match_stats(self.h, s))
+        return {"rows": s[0], "rescans": s[1], "exact_rows": s[2], "units": s[3]}

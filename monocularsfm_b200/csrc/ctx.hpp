@@ -1,0 +1,86 @@
+// msfm_ctx — host-side state of one (process, device): stream, resident descriptor sets, scratch.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/msfm_b200.h"
+#include "match_types.cuh"
+
+namespace msfm {
+
+// A device (or pinned-host) buffer that only ever grows.
+struct GrowBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned_host = false;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) {
+            cudaError_t e = pinned_host ? cudaFreeHost(p) : cudaFree(p);
+            p = nullptr; cap = 0;
+            if (e != cudaSuccess) return e;
+        }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = pinned_host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) { if (pinned_host) cudaFreeHost(p); else cudaFree(p); }
+        p = nullptr; cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct ImgHost {
+    void* block = nullptr;     // one allocation: sw [n_pad*128] then cj [n_pad]
+    int32_t n = 0, n_pad = 0;
+    bool live = false;
+};
+
+}  // namespace msfm
+
+struct msfm_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // ---- M-path
+    std::unordered_map<int32_t, int> slot_of;      // image_id -> slot
+    std::vector<msfm::ImgHost> imgs;               // slot -> allocation
+    std::vector<int> free_slots;
+    msfm::GrowBuf d_imgs;                          // ImgDev[slots]
+    bool imgs_dirty = true;
+    msfm::GrowBuf d_raw;                           // upload staging (device)
+    msfm::GrowBuf h_stage;                         // pinned host staging (segments, offsets readback)
+    msfm::GrowBuf d_segs, d_units, d_res, d_m, d_exact, d_counts, d_misc;
+    msfm::GrowBuf d_out_offsets, d_out_matches, d_out_dist;
+    int64_t stats[4] = {0, 0, 0, 0};
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char* what) {
+        return fail(MSFM_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+};
+
+#define MSFM_CUDA(ctx, call)                                            \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return (ctx)->cuda_fail(e__, #call);    \
+    } while (0)

@@ -1,0 +1,420 @@
+// C-ABI entry points (include/msfm_b200.h): context + M-path orchestration.
+// The product path has no CPU fallback: every entry point needs a live CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "ctx.hpp"
+
+namespace msfm {
+cudaError_t launch_match_tile_kernel(const ImgDev*, const UnitDev*, int, int32_t*, int32_t*, int32_t*, int, cudaStream_t);
+cudaError_t launch_desc_format(const uint8_t*, int, int, uint8_t*, int32_t*, cudaStream_t);
+cudaError_t launch_build_units(const SegDev*, int, int, UnitDev*, cudaStream_t);
+cudaError_t launch_resolve_rows(const ImgDev*, const UnitDev*, int, const int32_t*, const int32_t*, const int32_t*,
+                                MatchOpts, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, unsigned int*, cudaStream_t);
+cudaError_t launch_exact_rows(const ImgDev*, const UnitDev*, const int32_t*, const unsigned int*, int, MatchOpts,
+                              int32_t*, int32_t*, int32_t*, int32_t*, int, cudaStream_t);
+cudaError_t launch_count_scan_write(const ImgDev*, const SegDev*, int, MatchOpts, const int32_t*, const int32_t*,
+                                    int32_t*, long long*, long long*, long long, int32_t*, float*, cudaStream_t);
+}  // namespace msfm
+
+using namespace msfm;
+
+static thread_local std::string g_init_error;
+static constexpr int kMaxUnitsPerBatch = 1 << 17;     // 131072 units = 16.7 M rows of scratch per batch
+static constexpr int32_t kTmpIdA = -1000001, kTmpIdB = -1000002;
+
+extern "C" {
+
+const char* msfm_version(void) { return "0.1.0"; }
+
+int msfm_init(msfm_ctx** out, int device_id) {
+    if (!out) return MSFM_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_init_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return MSFM_E_NO_DEVICE;
+    }
+    if (device_id < 0 || device_id >= ndev) {
+        g_init_error = "device_id out of range";
+        return MSFM_E_INVALID;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) {
+        g_init_error = cudaGetErrorString(e);
+        return MSFM_E_CUDA;
+    }
+    if (prop.major != 10) {
+        g_init_error = "this library contains sm_100a code only (tcgen05/TMEM); device is sm_" +
+                       std::to_string(prop.major) + std::to_string(prop.minor);
+        return MSFM_E_NO_DEVICE;
+    }
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) {
+        g_init_error = cudaGetErrorString(e);
+        return MSFM_E_CUDA;
+    }
+    msfm_ctx* c = new (std::nothrow) msfm_ctx();
+    if (!c) return MSFM_E_CUDA;
+    c->device = device_id;
+    c->num_sms = prop.multiProcessorCount;
+    c->h_stage.pinned_host = true;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_init_error = cudaGetErrorString(e);
+        delete c;
+        return MSFM_E_CUDA;
+    }
+    *out = c;
+    return MSFM_OK;
+}
+
+void msfm_destroy(msfm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& im : c->imgs)
+        if (im.block) cudaFree(im.block);
+    GrowBuf* bufs[] = {&c->d_imgs, &c->d_raw, &c->h_stage, &c->d_segs, &c->d_units, &c->d_res, &c->d_m, &c->d_exact,
+                       &c->d_counts, &c->d_misc, &c->d_out_offsets, &c->d_out_matches, &c->d_out_dist};
+    for (GrowBuf* b : bufs) b->release();
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* msfm_last_error(const msfm_ctx* c) { return c ? c->err.c_str() : g_init_error.c_str(); }
+
+int msfm_sync(msfm_ctx* c) {
+    if (!c) return MSFM_E_INVALID;
+    MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MSFM_OK;
+}
+void* msfm_stream(msfm_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
+int64_t msfm_launch_count(const msfm_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ uploads
+static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int32_t n, bool src_on_device) {
+    if (!c || n < 0 || (n > 0 && !src)) return c ? c->fail(MSFM_E_INVALID, "msfm_desc_upload: bad arguments") : MSFM_E_INVALID;
+    MSFM_CUDA(c, cudaSetDevice(c->device));
+    const int32_t n_pad = (n + 255) / 256 * 256;
+    int slot;
+    auto it = c->slot_of.find(image_id);
+    if (it != c->slot_of.end()) {
+        slot = it->second;
+    } else if (!c->free_slots.empty()) {
+        slot = c->free_slots.back();
+        c->free_slots.pop_back();
+        c->slot_of[image_id] = slot;
+    } else {
+        slot = static_cast<int>(c->imgs.size());
+        c->imgs.emplace_back();
+        c->slot_of[image_id] = slot;
+    }
+    ImgHost& im = c->imgs[slot];
+    if (im.block && im.n_pad != n_pad) {
+        // a kernel of an earlier call may still read the old block
+        MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
+        MSFM_CUDA(c, cudaFree(im.block));
+        im.block = nullptr;
+    }
+    if (!im.block && n_pad > 0) MSFM_CUDA(c, cudaMalloc(&im.block, static_cast<size_t>(n_pad) * (128 + 4)));
+    im.n = n;
+    im.n_pad = n_pad;
+    im.live = true;
+    c->imgs_dirty = true;
+    if (n_pad == 0) return MSFM_OK;
+    const uint8_t* raw = src;
+    if (!src_on_device) {
+        MSFM_CUDA(c, c->d_raw.reserve(static_cast<size_t>(n) * 128));
+        MSFM_CUDA(c, cudaMemcpyAsync(c->d_raw.p, src, static_cast<size_t>(n) * 128, cudaMemcpyHostToDevice, c->stream));
+        raw = c->d_raw.as<uint8_t>();
+    }
+    uint8_t* sw = static_cast<uint8_t*>(im.block);
+    int32_t* cj = reinterpret_cast<int32_t*>(sw + static_cast<size_t>(n_pad) * 128);
+    MSFM_CUDA(c, launch_desc_format(raw, n, n_pad, sw, cj, c->stream));
+    c->launches += 1;
+    return MSFM_OK;
+}
+
+int msfm_desc_upload_u8(msfm_ctx* c, int32_t image_id, const uint8_t* desc_host, int32_t n) {
+    if (c && image_id < 0) return c->fail(MSFM_E_INVALID, "image_id must be >= 0");
+    return upload_common(c, image_id, desc_host, n, false);
+}
+int msfm_desc_upload_u8_dev(msfm_ctx* c, int32_t image_id, const uint8_t* desc_dev, int32_t n) {
+    if (c && image_id < 0) return c->fail(MSFM_E_INVALID, "image_id must be >= 0");
+    return upload_common(c, image_id, desc_dev, n, true);
+}
+int msfm_desc_count(msfm_ctx* c, int32_t image_id) {
+    if (!c) return MSFM_E_INVALID;
+    auto it = c->slot_of.find(image_id);
+    if (it == c->slot_of.end()) return c->fail(MSFM_E_NOT_FOUND, "image %d not resident", image_id);
+    return c->imgs[it->second].n;
+}
+int msfm_desc_release(msfm_ctx* c, int32_t image_id) {
+    if (!c) return MSFM_E_INVALID;
+    auto it = c->slot_of.find(image_id);
+    if (it == c->slot_of.end()) return c->fail(MSFM_E_NOT_FOUND, "image %d not resident", image_id);
+    MSFM_CUDA(c, cudaSetDevice(c->device));
+    MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
+    ImgHost& im = c->imgs[it->second];
+    if (im.block) MSFM_CUDA(c, cudaFree(im.block));
+    im = ImgHost();
+    c->free_slots.push_back(it->second);
+    c->slot_of.erase(it);
+    c->imgs_dirty = true;
+    return MSFM_OK;
+}
+int msfm_desc_release_all(msfm_ctx* c) {
+    if (!c) return MSFM_E_INVALID;
+    MSFM_CUDA(c, cudaSetDevice(c->device));
+    MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (auto& im : c->imgs)
+        if (im.block) cudaFree(im.block);
+    c->imgs.clear();
+    c->free_slots.clear();
+    c->slot_of.clear();
+    c->imgs_dirty = true;
+    return MSFM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ matching core
+static int sync_img_table(msfm_ctx* c) {
+    if (!c->imgs_dirty) return MSFM_OK;
+    std::vector<ImgDev> tab(c->imgs.size());
+    for (size_t i = 0; i < c->imgs.size(); ++i) {
+        const ImgHost& im = c->imgs[i];
+        uint8_t* sw = static_cast<uint8_t*>(im.block);
+        tab[i].sw = sw;
+        tab[i].cj = sw ? reinterpret_cast<const int32_t*>(sw + static_cast<size_t>(im.n_pad) * 128) : nullptr;
+        tab[i].n = im.n;
+        tab[i].n_pad = im.n_pad;
+    }
+    MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
+    MSFM_CUDA(c, c->d_imgs.reserve(std::max<size_t>(1, tab.size()) * sizeof(ImgDev)));
+    if (!tab.empty())
+        MSFM_CUDA(c, cudaMemcpy(c->d_imgs.p, tab.data(), tab.size() * sizeof(ImgDev), cudaMemcpyHostToDevice));
+    c->imgs_dirty = false;
+    return MSFM_OK;
+}
+
+struct RowDump {          // optional per-row readback for the knn2 API (single pair, direction 0)
+    int32_t* j0 = nullptr;    // [n][2]
+    int32_t* d1 = nullptr;
+    int32_t* d2 = nullptr;
+    int32_t n = 0;
+};
+
+// mode: 0 tensor path, 1 exact scan of every row.
+static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_match_options* uopt, int exact_second,
+                      int mode, long long* out_offsets_dev, int32_t* out_matches_dev, float* out_dist_dev,
+                      long long capacity, long long* total_out, RowDump* dump) {
+    if (!c) return MSFM_E_INVALID;
+    if (P < 0 || (P > 0 && !pairs) || !uopt) return c->fail(MSFM_E_INVALID, "msfm_match_pairs: bad arguments");
+    if (!(uopt->distance_ratio >= 0.0f) || uopt->reserved != 0) return c->fail(MSFM_E_INVALID, "bad match options");
+    MSFM_CUDA(c, cudaSetDevice(c->device));
+    MatchOpts opt;
+    opt.max_distance = uopt->max_distance;
+    opt.ratio = uopt->distance_ratio;
+    opt.cross_check = uopt->cross_check ? 1 : 0;
+    opt.quirks = uopt->opencv_quirks ? 1 : 0;
+    opt.exact_second = exact_second;
+    const int spp = opt.cross_check ? 2 : 1;   // segments per pair
+
+    // ---- segments + batches (host)
+    std::vector<SegDev> segs(static_cast<size_t>(P) * spp);
+    struct Batch { int first_pair, npairs, nunits; };
+    std::vector<Batch> batches;
+    {
+        Batch cur{0, 0, 0};
+        for (int p = 0; p < P; ++p) {
+            auto i1 = c->slot_of.find(pairs[2 * p]), i2 = c->slot_of.find(pairs[2 * p + 1]);
+            if (i1 == c->slot_of.end() || i2 == c->slot_of.end())
+                return c->fail(MSFM_E_NOT_FOUND, "pair %d: image %d or %d not resident", p, pairs[2 * p], pairs[2 * p + 1]);
+            const int s1 = i1->second, s2 = i2->second;
+            const int u12 = (c->imgs[s1].n + 127) / 128, u21 = opt.cross_check ? (c->imgs[s2].n + 127) / 128 : 0;
+            if (cur.npairs > 0 && cur.nunits + u12 + u21 > kMaxUnitsPerBatch) {
+                batches.push_back(cur);
+                cur = Batch{p, 0, 0};
+            }
+            SegDev& a = segs[static_cast<size_t>(p) * spp];
+            a.q_slot = s1; a.t_slot = s2; a.unit_base = cur.nunits; a.n_units = u12;
+            cur.nunits += u12;
+            if (opt.cross_check) {
+                SegDev& b = segs[static_cast<size_t>(p) * spp + 1];
+                b.q_slot = s2; b.t_slot = s1; b.unit_base = cur.nunits; b.n_units = u21;
+                cur.nunits += u21;
+            }
+            cur.npairs += 1;
+        }
+        if (cur.npairs > 0) batches.push_back(cur);
+    }
+    int rc = sync_img_table(c);
+    if (rc) return rc;
+    MSFM_CUDA(c, cudaStreamSynchronize(c->stream));   // scratch of an earlier call is free now
+
+    int max_units = 1, max_pairs = 1;
+    for (const Batch& b : batches) { max_units = std::max(max_units, b.nunits); max_pairs = std::max(max_pairs, b.npairs); }
+    const size_t rows = static_cast<size_t>(max_units) * 128;
+    const size_t nb = std::max<size_t>(1, batches.size());
+    MSFM_CUDA(c, c->d_segs.reserve(std::max<size_t>(1, segs.size()) * sizeof(SegDev)));
+    MSFM_CUDA(c, c->d_units.reserve(static_cast<size_t>(max_units) * sizeof(UnitDev)));
+    MSFM_CUDA(c, c->d_res.reserve(rows * 3 * sizeof(int32_t)));
+    MSFM_CUDA(c, c->d_m.reserve(rows * 5 * sizeof(int32_t)));
+    MSFM_CUDA(c, c->d_exact.reserve(rows * sizeof(int32_t)));
+    MSFM_CUDA(c, c->d_counts.reserve(static_cast<size_t>(max_pairs) * sizeof(int32_t)));
+    MSFM_CUDA(c, c->d_misc.reserve(16 + nb * 2 * sizeof(unsigned int)));
+    if (!segs.empty())
+        MSFM_CUDA(c, cudaMemcpy(c->d_segs.p, segs.data(), segs.size() * sizeof(SegDev), cudaMemcpyHostToDevice));
+    MSFM_CUDA(c, cudaMemsetAsync(c->d_misc.p, 0, 16 + nb * 2 * sizeof(unsigned int), c->stream));
+
+    long long* running_total = c->d_misc.as<long long>();
+    unsigned int* counters = reinterpret_cast<unsigned int*>(c->d_misc.as<uint8_t>() + 16);
+    const ImgDev* d_imgs = c->d_imgs.as<ImgDev>();
+    int32_t* res_j = c->d_res.as<int32_t>();
+    int32_t* res_d1 = res_j + rows;
+    int32_t* res_u = res_d1 + rows;
+    int32_t* m_j = c->d_m.as<int32_t>();
+    int32_t* m_d1 = m_j + rows;
+    int32_t* m_d2 = m_d1 + rows;
+    int32_t* m_j0 = m_d2 + rows;
+    if (P == 0) MSFM_CUDA(c, cudaMemsetAsync(out_offsets_dev, 0, sizeof(long long), c->stream));
+
+    int64_t total_units = 0, total_rows = 0;
+    for (size_t bi = 0; bi < batches.size(); ++bi) {
+        const Batch& b = batches[bi];
+        const SegDev* bsegs = c->d_segs.as<SegDev>() + static_cast<size_t>(b.first_pair) * spp;
+        UnitDev* units = c->d_units.as<UnitDev>();
+        unsigned int* bcnt = counters + 2 * bi;
+        MSFM_CUDA(c, launch_build_units(bsegs, b.npairs * spp, b.nunits, units, c->stream));
+        if (mode == 0) {
+            MSFM_CUDA(c, launch_match_tile_kernel(d_imgs, units, b.nunits, res_j, res_d1, res_u, c->num_sms, c->stream));
+            MSFM_CUDA(c, launch_resolve_rows(d_imgs, units, b.nunits, res_j, res_d1, res_u, opt, m_j, m_d1, m_d2, m_j0,
+                                             c->d_exact.as<int32_t>(), bcnt, c->stream));
+            MSFM_CUDA(c, launch_exact_rows(d_imgs, units, c->d_exact.as<int32_t>(), bcnt, -1, opt, m_j, m_d1, m_d2, m_j0,
+                                           c->num_sms, c->stream));
+            c->launches += (b.nunits > 0 ? 4 : 1);
+        } else {
+            MSFM_CUDA(c, launch_exact_rows(d_imgs, units, nullptr, nullptr, b.nunits * 128, opt, m_j, m_d1, m_d2, m_j0,
+                                           c->num_sms, c->stream));
+            c->launches += 2;
+        }
+        MSFM_CUDA(c, launch_count_scan_write(d_imgs, bsegs, b.npairs, opt, m_j, m_d1, c->d_counts.as<int32_t>(),
+                                             out_offsets_dev + b.first_pair, running_total, capacity, out_matches_dev,
+                                             out_dist_dev, c->stream));
+        c->launches += 3;
+        total_units += b.nunits;
+        total_rows += static_cast<int64_t>(b.nunits) * 128;
+        if (dump && bi == 0 && dump->n > 0) {
+            MSFM_CUDA(c, cudaMemcpyAsync(dump->j0, m_j0, static_cast<size_t>(dump->n) * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+            MSFM_CUDA(c, cudaMemcpyAsync(dump->d1, m_d1, static_cast<size_t>(dump->n) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+            MSFM_CUDA(c, cudaMemcpyAsync(dump->d2, m_d2, static_cast<size_t>(dump->n) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    // ---- totals (one small readback; this is the call's only host<->device sync besides the entry one)
+    MSFM_CUDA(c, c->h_stage.reserve(16 + nb * 2 * sizeof(unsigned int)));
+    MSFM_CUDA(c, cudaMemcpyAsync(c->h_stage.p, c->d_misc.p, 16 + nb * 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
+    const long long total = *c->h_stage.as<long long>();
+    const unsigned int* hc = reinterpret_cast<const unsigned int*>(c->h_stage.as<uint8_t>() + 16);
+    int64_t n_exact = 0, n_rescan = 0;
+    for (size_t bi = 0; bi < batches.size(); ++bi) { n_exact += hc[2 * bi]; n_rescan += hc[2 * bi + 1]; }
+    c->stats[0] = total_rows; c->stats[1] = n_rescan; c->stats[2] = n_exact; c->stats[3] = total_units;
+    if (total_out) *total_out = total;
+    if (total > capacity) return c->fail(MSFM_E_CAPACITY, "output capacity %lld < %lld matches", capacity, total);
+    return MSFM_OK;
+}
+
+int msfm_match_pairs_dev(msfm_ctx* c, const int32_t* pairs_host, int32_t P, const msfm_match_options* opt,
+                         int64_t* out_offsets_dev, int32_t* out_matches_dev, float* out_dist_dev, int64_t capacity,
+                         int64_t* total_out) {
+    if (!c) return MSFM_E_INVALID;
+    if (!out_offsets_dev || capacity < 0 || (capacity > 0 && !out_matches_dev))
+        return c->fail(MSFM_E_INVALID, "msfm_match_pairs_dev: bad output arguments");
+    long long total = 0;
+    int rc = match_core(c, pairs_host, P, opt, 0, 0, reinterpret_cast<long long*>(out_offsets_dev), out_matches_dev,
+                        out_dist_dev, capacity, &total, nullptr);
+    if (total_out) *total_out = total;
+    return rc;
+}
+
+int msfm_match_pairs(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_match_options* opt, int64_t* out_offsets,
+                     int32_t* out_matches, float* out_dist, int64_t capacity, int64_t* total_out) {
+    if (!c) return MSFM_E_INVALID;
+    if (!out_offsets || capacity < 0 || (capacity > 0 && !out_matches) || P < 0 || (P > 0 && !pairs))
+        return c->fail(MSFM_E_INVALID, "msfm_match_pairs: bad arguments");
+    MSFM_CUDA(c, cudaSetDevice(c->device));
+    // device capacity: never more than one match per query row
+    long long bound = 0;
+    for (int p = 0; p < P; ++p) {
+        auto it = c->slot_of.find(pairs[2 * p]);
+        if (it == c->slot_of.end()) return c->fail(MSFM_E_NOT_FOUND, "pair %d: image %d not resident", p, pairs[2 * p]);
+        bound += c->imgs[it->second].n;
+    }
+    const long long devcap = std::min<long long>(capacity, bound);
+    MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
+    MSFM_CUDA(c, c->d_out_offsets.reserve((static_cast<size_t>(P) + 1) * sizeof(long long)));
+    MSFM_CUDA(c, c->d_out_matches.reserve(std::max<size_t>(1, static_cast<size_t>(devcap)) * 2 * sizeof(int32_t)));
+    if (out_dist) MSFM_CUDA(c, c->d_out_dist.reserve(std::max<size_t>(1, static_cast<size_t>(devcap)) * sizeof(float)));
+    long long total = 0;
+    int rc = match_core(c, pairs, P, opt, 0, 0, c->d_out_offsets.as<long long>(), c->d_out_matches.as<int32_t>(),
+                        out_dist ? c->d_out_dist.as<float>() : nullptr, devcap, &total, nullptr);
+    if (total_out) *total_out = total;
+    if (rc != MSFM_OK && rc != MSFM_E_CAPACITY) return rc;
+    MSFM_CUDA(c, cudaMemcpyAsync(out_offsets, c->d_out_offsets.p, (static_cast<size_t>(P) + 1) * sizeof(long long),
+                                 cudaMemcpyDeviceToHost, c->stream));
+    if (rc == MSFM_OK && total > 0) {
+        MSFM_CUDA(c, cudaMemcpyAsync(out_matches, c->d_out_matches.p, static_cast<size_t>(total) * 2 * sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, c->stream));
+        if (out_dist)
+            MSFM_CUDA(c, cudaMemcpyAsync(out_dist, c->d_out_dist.p, static_cast<size_t>(total) * sizeof(float),
+                                         cudaMemcpyDeviceToHost, c->stream));
+    }
+    MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return rc;
+}
+
+int msfm_match_knn2_u8(msfm_ctx* c, const uint8_t* A, int32_t nA, const uint8_t* B, int32_t nB, int32_t mode,
+                       int32_t* idx, float* dist, int32_t* d2) {
+    if (!c) return MSFM_E_INVALID;
+    if (nA < 0 || nB < 0 || (nA > 0 && (!A || !idx || !dist)) || (nB > 0 && !B) || (mode != 0 && mode != 1))
+        return c->fail(MSFM_E_INVALID, "msfm_match_knn2_u8: bad arguments");
+    if (nA == 0) return MSFM_OK;
+    int rc;
+    if ((rc = upload_common(c, kTmpIdA, A, nA, false))) return rc;
+    MSFM_CUDA(c, cudaStreamSynchronize(c->stream));       // d_raw staging is reused by the next upload
+    if ((rc = upload_common(c, kTmpIdB, B, nB, false))) return rc;
+    msfm_match_options o;
+    o.max_distance = -1.0; o.distance_ratio = 0.8f; o.cross_check = 0; o.opencv_quirks = 0; o.reserved = 0;
+    const int32_t pair[2] = {kTmpIdA, kTmpIdB};
+    std::vector<int32_t> hj(static_cast<size_t>(nA) * 2), hd1(nA), hd2(nA);
+    RowDump dump; dump.j0 = hj.data(); dump.d1 = hd1.data(); dump.d2 = hd2.data(); dump.n = nA;
+    MSFM_CUDA(c, c->d_out_offsets.reserve(2 * sizeof(long long)));
+    MSFM_CUDA(c, c->d_out_matches.reserve(std::max<size_t>(1, nA) * 2 * sizeof(int32_t)));
+    long long total = 0;
+    rc = match_core(c, pair, 1, &o, 1, mode, c->d_out_offsets.as<long long>(), c->d_out_matches.as<int32_t>(), nullptr, nA,
+                    &total, &dump);
+    int rc2 = msfm_desc_release(c, kTmpIdA);
+    int rc3 = msfm_desc_release(c, kTmpIdB);
+    if (rc) return rc;
+    if (rc2) return rc2;
+    if (rc3) return rc3;
+    for (int i = 0; i < nA; ++i) {
+        const int32_t a = hd1[i], b = hd2[i];
+        const bool h0 = hj[2 * i] >= 0 && a != kIntInf, h1 = h0 && b != kIntInf;
+        idx[2 * i] = h0 ? hj[2 * i] : -1;
+        idx[2 * i + 1] = h1 ? hj[2 * i + 1] : -1;
+        dist[2 * i] = h0 ? sqrtf(static_cast<float>(a)) : INFINITY;
+        dist[2 * i + 1] = h1 ? sqrtf(static_cast<float>(b)) : INFINITY;
+        if (d2) { d2[2 * i] = h0 ? a : -1; d2[2 * i + 1] = h1 ? b : -1; }
+    }
+    return MSFM_OK;
+}
+
+int msfm_match_stats(msfm_ctx* c, int64_t stats[4]) {
+    if (!c || !stats) return MSFM_E_INVALID;
+    for (int i = 0; i < 4; ++i) stats[i] = c->stats[i];
+    return MSFM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+@pytest.fixture(scope="session")
+def golden_match():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "match_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    import monocularsfm_b200 as m
+    c = m.Context(0)
+    yield c
+    c.close()

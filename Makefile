@@ -23,3 +23,8 @@ clean:
 	rm -rf build/obj $(LIB)
 
 .PHONY: all clean
+
+microbench: build/microbench
+build/microbench: tools/microbench.cu $(CSRC)/ptx.cuh
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ $<

@@ -54,6 +54,24 @@ void* msfm_stream(msfm_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t msfm_launch_count(const msfm_ctx* ctx);
 
+/* Optional per-kernel-class device timing (CUDA events on the ctx stream, recorded around every launch
+ * while enabled).  msfm_prof_read synchronises the stream, then returns the accumulated milliseconds and
+ * launch counts per class since the last msfm_prof_reset.  Replaces nothing in the reference (its only
+ * instrumentation is Common/Timer.cpp wall clocks, FeatureMatching.cpp:16-17,65). */
+#define MSFM_PROF_DESC_FORMAT  0   /* descriptor upload formatting */
+#define MSFM_PROF_BUILD_UNITS  1
+#define MSFM_PROF_MATCH_TILE   2   /* K1: tcgen05 distance tiles + fused top-2 */
+#define MSFM_PROF_RESOLVE      3   /* ratio test + in-group rescan */
+#define MSFM_PROF_EXACT        4   /* exact slow-path rows */
+#define MSFM_PROF_COMPACT      5   /* cross-check + compaction (3 launches per batch, timed together) */
+#define MSFM_PROF_BA_EVAL      6   /* K2: residual + Jacobian + normal-equation blocks */
+#define MSFM_PROF_BA_SCHUR     7   /* K2: Schur reduction onto the camera system */
+#define MSFM_PROF_BA_OTHER     8
+#define MSFM_PROF_NCAT         9
+int msfm_prof_enable(msfm_ctx* ctx, int on);
+int msfm_prof_reset(msfm_ctx* ctx);
+int msfm_prof_read(msfm_ctx* ctx, double ms[MSFM_PROF_NCAT], int64_t launches[MSFM_PROF_NCAT]);
+
 /* ---------------------------------------------------------------------------------------------
  * M-path: brute-force 2-NN descriptor matching
  *

@@ -66,6 +66,9 @@ def load_library():
         "msfm_sync": (C.c_int, [vp]),
         "msfm_stream": (vp, [vp]),
         "msfm_launch_count": (i64, [vp]),
+        "msfm_prof_enable": (C.c_int, [vp, C.c_int]),
+        "msfm_prof_reset": (C.c_int, [vp]),
+        "msfm_prof_read": (C.c_int, [vp, P(C.c_double), P(i64)]),
         "msfm_desc_upload_u8": (C.c_int, [vp, i32, vp, i32]),
         "msfm_desc_upload_u8_dev": (C.c_int, [vp, i32, vp, i32]),
         "msfm_desc_count": (C.c_int, [vp, i32]),
@@ -129,6 +132,22 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.msfm_launch_count(self.h))
+
+    PROF_NAMES = ["desc_format", "build_units", "match_tile", "resolve", "exact", "compact", "ba_eval", "ba_schur",
+                  "ba_other"]
+
+    def prof_enable(self, on=True):
+        self._check(self.lib.msfm_prof_enable(self.h, int(on)))
+
+    def prof_reset(self):
+        self._check(self.lib.msfm_prof_reset(self.h))
+
+    def prof_read(self):
+        n = len(self.PROF_NAMES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        self._check(self.lib.msfm_prof_read(self.h, ms, cnt))
+        return {k: {"ms": ms[i], "launches": int(cnt[i])} for i, k in enumerate(self.PROF_NAMES)}
 
     # ---- M-path
     def upload(self, image_id: int, desc: np.ndarray):

@@ -65,6 +65,39 @@ struct msfm_ctx {
     msfm::GrowBuf d_out_offsets, d_out_matches, d_out_dist;
     int64_t stats[4] = {0, 0, 0, 0};
 
+    // ---- optional per-kernel-class timing with CUDA events on the ctx stream (bench.py roofline)
+    struct ProfRec { int cat; cudaEvent_t a, b; };
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_pool;
+    std::vector<ProfRec> prof_recs;
+    double prof_ms[MSFM_PROF_NCAT] = {0};
+    int64_t prof_n[MSFM_PROF_NCAT] = {0};
+    cudaEvent_t prof_event() {
+        if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void prof_begin(int cat) {
+        if (!prof_on) return;
+        ProfRec r{cat, prof_event(), prof_event()};
+        cudaEventRecord(r.a, stream);
+        prof_recs.push_back(r);
+    }
+    void prof_end() {
+        if (!prof_on || prof_recs.empty()) return;
+        cudaEventRecord(prof_recs.back().b, stream);
+    }
+    void prof_collect() {      // stream must be idle
+        for (ProfRec& r : prof_recs) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { prof_ms[r.cat] += ms; prof_n[r.cat] += 1; }
+            prof_pool.push_back(r.a);
+            prof_pool.push_back(r.b);
+        }
+        prof_recs.clear();
+    }
+
     int fail(int code, const char* fmt, ...) {
         char buf[512];
         va_list ap;

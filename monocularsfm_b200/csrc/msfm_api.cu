@@ -74,6 +74,8 @@ void msfm_destroy(msfm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    c->prof_collect();
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (auto& im : c->imgs)
         if (im.block) cudaFree(im.block);
     GrowBuf* bufs[] = {&c->d_imgs, &c->d_raw, &c->h_stage, &c->d_segs, &c->d_units, &c->d_res, &c->d_m, &c->d_exact,
@@ -92,6 +94,28 @@ int msfm_sync(msfm_ctx* c) {
 }
 void* msfm_stream(msfm_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
 int64_t msfm_launch_count(const msfm_ctx* c) { return c ? c->launches : 0; }
+
+int msfm_prof_enable(msfm_ctx* c, int on) {
+    if (!c) return MSFM_E_INVALID;
+    c->prof_on = on != 0;
+    return MSFM_OK;
+}
+int msfm_prof_reset(msfm_ctx* c) {
+    if (!c) return MSFM_E_INVALID;
+    MSFM_CUDA(c, cudaSetDevice(c->device));
+    MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->prof_collect();
+    for (int i = 0; i < MSFM_PROF_NCAT; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    return MSFM_OK;
+}
+int msfm_prof_read(msfm_ctx* c, double ms[MSFM_PROF_NCAT], int64_t n[MSFM_PROF_NCAT]) {
+    if (!c || !ms || !n) return MSFM_E_INVALID;
+    MSFM_CUDA(c, cudaSetDevice(c->device));
+    MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->prof_collect();
+    for (int i = 0; i < MSFM_PROF_NCAT; ++i) { ms[i] = c->prof_ms[i]; n[i] = c->prof_n[i]; }
+    return MSFM_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ uploads
 static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int32_t n, bool src_on_device) {
@@ -132,7 +156,9 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
     }
     uint8_t* sw = static_cast<uint8_t*>(im.block);
     int32_t* cj = reinterpret_cast<int32_t*>(sw + static_cast<size_t>(n_pad) * 128);
+    c->prof_begin(MSFM_PROF_DESC_FORMAT);
     MSFM_CUDA(c, launch_desc_format(raw, n, n_pad, sw, cj, c->stream));
+    c->prof_end();
     c->launches += 1;
     return MSFM_OK;
 }
@@ -286,22 +312,34 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
         const SegDev* bsegs = c->d_segs.as<SegDev>() + static_cast<size_t>(b.first_pair) * spp;
         UnitDev* units = c->d_units.as<UnitDev>();
         unsigned int* bcnt = counters + 2 * bi;
+        c->prof_begin(MSFM_PROF_BUILD_UNITS);
         MSFM_CUDA(c, launch_build_units(bsegs, b.npairs * spp, b.nunits, units, c->stream));
+        c->prof_end();
         if (mode == 0) {
+            c->prof_begin(MSFM_PROF_MATCH_TILE);
             MSFM_CUDA(c, launch_match_tile_kernel(d_imgs, units, b.nunits, res_j, res_d1, res_u, c->num_sms, c->stream));
+            c->prof_end();
+            c->prof_begin(MSFM_PROF_RESOLVE);
             MSFM_CUDA(c, launch_resolve_rows(d_imgs, units, b.nunits, res_j, res_d1, res_u, opt, m_j, m_d1, m_d2, m_j0,
                                              c->d_exact.as<int32_t>(), bcnt, c->stream));
+            c->prof_end();
+            c->prof_begin(MSFM_PROF_EXACT);
             MSFM_CUDA(c, launch_exact_rows(d_imgs, units, c->d_exact.as<int32_t>(), bcnt, -1, opt, m_j, m_d1, m_d2, m_j0,
                                            c->num_sms, c->stream));
+            c->prof_end();
             c->launches += (b.nunits > 0 ? 4 : 1);
         } else {
+            c->prof_begin(MSFM_PROF_EXACT);
             MSFM_CUDA(c, launch_exact_rows(d_imgs, units, nullptr, nullptr, b.nunits * 128, opt, m_j, m_d1, m_d2, m_j0,
                                            c->num_sms, c->stream));
+            c->prof_end();
             c->launches += 2;
         }
+        c->prof_begin(MSFM_PROF_COMPACT);
         MSFM_CUDA(c, launch_count_scan_write(d_imgs, bsegs, b.npairs, opt, m_j, m_d1, c->d_counts.as<int32_t>(),
                                              out_offsets_dev + b.first_pair, running_total, capacity, out_matches_dev,
                                              out_dist_dev, c->stream));
+        c->prof_end();
         c->launches += 3;
         total_units += b.nunits;
         total_rows += static_cast<int64_t>(b.nunits) * 128;

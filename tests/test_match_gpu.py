@@ -1,0 +1,137 @@
+"""GPU parity tests of the M-path, through the C-ABI (ctypes), against the OpenCV golden vectors and the oracle."""
+import numpy as np
+import pytest
+
+import monocularsfm_b200 as m
+from oracle import match_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["cfg1", "ragged", "sift_planted", "ties", "sqrt_collapse", "quirk_q0", "n2_is_1", "n2_is_2", "n1_is_1",
+         "preempt100", "all_equal", "extremes"]
+
+
+def _check_knn(idx, dist, d2, gi, gd, mode):
+    np.testing.assert_array_equal(idx[:, 0], gi[:, 0])
+    np.testing.assert_array_equal(dist, gd)                     # both distances, bit-exact floats
+    if mode == 1:
+        np.testing.assert_array_equal(idx[:, 1], gi[:, 1])
+    else:
+        known = idx[:, 1] >= 0                                 # only rows that took the exact path report it
+        np.testing.assert_array_equal(idx[known, 1], gi[known, 1])
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name", CASES)
+def test_knn2_golden(ctx, golden_match, name, mode):
+    g = golden_match
+    a, b = g[f"{name}/a"], g[f"{name}/b"]
+    idx, dist, d2 = ctx.knn2(a, b, mode)
+    _check_knn(idx, dist, d2, g[f"{name}/knn12_idx"], g[f"{name}/knn12_dist"], mode)
+    idx, dist, d2 = ctx.knn2(b, a, mode)
+    _check_knn(idx, dist, d2, g[f"{name}/knn21_idx"], g[f"{name}/knn21_dist"], mode)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("ratio", [0.8, 0.95])
+def test_match_pairs_golden(ctx, golden_match, name, ratio):
+    g = golden_match
+    a, b = g[f"{name}/a"], g[f"{name}/b"]
+    tag = f"{name}/r{int(ratio * 100)}"
+    ctx.upload(1, a)
+    ctx.upload(2, b)
+    off, mt, d = ctx.match_pairs([[1, 2]], m.MatchOptions(ratio, -1.0, False, False))
+    np.testing.assert_array_equal(mt, g[f"{tag}/m12"])
+    np.testing.assert_array_equal(d, g[f"{tag}/d12"])
+    for quirk in (1, 0):
+        off, mt, d = ctx.match_pairs([[1, 2]], m.MatchOptions(ratio, -1.0, True, bool(quirk)))
+        assert off.tolist() == [0, len(g[f"{tag}/cross_q{quirk}"])]
+        np.testing.assert_array_equal(mt, g[f"{tag}/cross_q{quirk}"])
+        np.testing.assert_array_equal(d, g[f"{tag}/cross_q{quirk}_d"])
+
+
+def _sift_like(rng, n):
+    x = np.abs(rng.standard_normal((n, 128)))
+    x = x / np.linalg.norm(x, axis=1, keepdims=True) * 512.0
+    return np.clip(np.rint(x), 0, 255).astype(np.uint8)
+
+
+def _planted_set(rng, n_img, n):
+    base = _sift_like(rng, n)
+    imgs = [base]
+    for k in range(1, n_img):
+        x = _sift_like(rng, n)
+        m_ = int(0.3 * n)
+        dst = rng.permutation(n)[:m_]
+        src = rng.permutation(n)[:m_]
+        x[dst] = np.clip(base[src].astype(np.int64) + rng.integers(-2, 3, (m_, 128)), 0, 255).astype(np.uint8)
+        imgs.append(x)
+    return imgs
+
+
+@pytest.mark.parametrize("n1,n2", [(2000, 3000), (1, 257), (129, 31), (8192, 8192)])
+def test_knn2_vs_oracle_random(ctx, n1, n2):
+    rng = np.random.default_rng(n1 * 7 + n2)
+    a = rng.integers(0, 256, (n1, 128), dtype=np.uint8)
+    b = rng.integers(0, 256, (n2, 128), dtype=np.uint8)
+    oi, od, _ = mo.knn2(a, b)
+    idx, dist, d2 = ctx.knn2(a, b, 0)
+    _check_knn(idx, dist, d2, oi, od, 0)
+
+
+def test_multi_pair_batch_vs_oracle(ctx):
+    """Several ragged images, all pairs in one call, cross-check + distance filter, vs the oracle."""
+    rng = np.random.default_rng(7)
+    sizes = [700, 333, 1024, 50, 2, 0, 1500]
+    imgs = _planted_set(rng, len(sizes), 1500)
+    imgs = [im[:s] for im, s in zip(imgs, sizes)]
+    for i, im in enumerate(imgs):
+        ctx.upload(10 + i, im)
+    pairs = [(10 + i, 10 + j) for i in range(len(sizes)) for j in range(i)]
+    for opt in (m.MatchOptions(0.8, -1.0, True, True), m.MatchOptions(0.9, 60.0, True, False),
+                m.MatchOptions(0.8, -1.0, False, True)):
+        off, mt, d = ctx.match_pairs(pairs, opt)
+        assert off[0] == 0 and off[-1] == len(mt)
+        for p, (i1, i2) in enumerate(pairs):
+            em, ed = mo.match_image_pair(imgs[i1 - 10], imgs[i2 - 10], opt.distance_ratio, opt.max_distance,
+                                         bool(opt.cross_check), bool(opt.opencv_quirks))
+            np.testing.assert_array_equal(mt[off[p]:off[p + 1]], em, err_msg=f"pair {p} {i1}-{i2}")
+            np.testing.assert_array_equal(d[off[p]:off[p + 1]], ed)
+    st = ctx.match_stats()
+    assert st["units"] > 0
+
+
+def test_full_size_pair_properties(ctx):
+    """BASELINE cfg-2 shape (8192 x 8192): planted correspondences must be recovered; symmetric under swap."""
+    rng = np.random.default_rng(11)
+    a, b = _planted_set(rng, 2, 8192)
+    ctx.upload(1, a)
+    ctx.upload(2, b)
+    opt = m.MatchOptions(0.8, -1.0, True, False)
+    off, m12, d12 = ctx.match_pairs([[1, 2]], opt)
+    off, m21, d21 = ctx.match_pairs([[2, 1]], opt)
+    assert len(m12) > 2000
+    # mutual matching is symmetric: (i, j) in m12  <=>  (j, i) in m21
+    s12 = set(map(tuple, m12.tolist()))
+    s21 = set((j, i) for i, j in m21.tolist())
+    assert s12 == s21
+    assert (np.diff(m12[:, 0]) > 0).all()                     # ascending queryIdx
+    em, ed = mo.match_image_pair(a, b, 0.8, -1.0, True, False)
+    np.testing.assert_array_equal(m12, em)
+    np.testing.assert_array_equal(d12, ed)
+
+
+def test_capacity_error(ctx):
+    rng = np.random.default_rng(3)
+    a, b = _planted_set(rng, 2, 512)
+    ctx.upload(1, a)
+    ctx.upload(2, b)
+    with pytest.raises(m.MsfmError) as ei:
+        ctx.match_pairs([[1, 2]], m.MatchOptions(), capacity=3)
+    assert ei.value.code == -4
+
+
+def test_unknown_image_is_an_error(ctx):
+    with pytest.raises(m.MsfmError) as ei:
+        ctx.match_pairs([[12345, 1]], m.MatchOptions())
+    assert ei.value.code == -5

@@ -17,7 +17,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
 
 $(LIB): $(CU_OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $^
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lcusolver -ldl -Xlinker -rpath=/usr/local/cuda/lib64
 
 clean:
 	rm -rf build/obj $(LIB)

@@ -85,6 +85,116 @@ def all_pairs(n_img, base_id=0):
     return np.array([(base_id + i, base_id + j) for i in range(n_img) for j in range(i)], np.int32).reshape(-1, 2)
 
 
+# ----------------------------------------------------------------------------------------------- synthetic BA graph
+def _rodrigues_batch(rvec):
+    th = np.linalg.norm(rvec, axis=1, keepdims=True)
+    k = rvec / np.maximum(th, 1e-300)
+    K = np.zeros((len(rvec), 3, 3))
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -k[:, 2], k[:, 1], k[:, 2], -k[:, 0], -k[:, 1], k[:, 0]
+    return np.eye(3)[None] + np.sin(th)[:, :, None] * K + (1 - np.cos(th))[:, :, None] * (K @ K)
+
+
+def make_ba_problem(n_cams, n_pts, mean_track, seed, noise_px=0.5):
+    """Synthetic BA graph of SURVEY.md section 8d (vectorised): cameras on a ring of radius 10 looking inward, camera 0 =
+    identity rotation and constant, points uniform in [-3,3]^3, each point seen by its k ~ clip(Geometric(mean_track), 2, .)
+    nearest-angle cameras, observations = projection + N(0, 0.5 px), NEU intrinsics, then points / poses perturbed."""
+    rng = np.random.default_rng(seed)
+    fx = fy = 1449.2752980237
+    ang = np.linspace(0, 2 * np.pi, n_cams, endpoint=False)
+    centers = np.stack([10 * np.sin(ang), np.zeros(n_cams), -10 * np.cos(ang)], 1)
+    rvec = np.stack([np.zeros(n_cams), ang, np.zeros(n_cams)], 1)
+    rvec[1:] += rng.normal(0, 0.02, (n_cams - 1, 3))
+    R = _rodrigues_batch(rvec)
+    tvec = -(R @ centers[:, :, None])[:, :, 0]
+    cams = np.concatenate([rvec, tvec], 1)
+    pts = rng.uniform(-3, 3, (n_pts, 3))
+    k = np.clip(rng.geometric(1.0 / mean_track, n_pts), 2, min(n_cams, 64)).astype(np.int64)
+    pang = np.arctan2(pts[:, 0], -pts[:, 2]) % (2 * np.pi)
+    c0 = np.rint(pang / (2 * np.pi) * n_cams).astype(np.int64)
+    obs_pt = np.repeat(np.arange(n_pts), k)
+    within = np.arange(len(obs_pt)) - np.repeat(np.cumsum(k) - k, k)
+    off = ((within + 1) // 2) * np.where(within % 2 == 1, 1, -1)          # 0, +1, -1, +2, -2, ...
+    obs_cam = (np.repeat(c0, k) + off) % n_cams
+    order = np.lexsort((obs_cam, obs_pt))
+    obs_cam, obs_pt = obs_cam[order].astype(np.int32), obs_pt[order].astype(np.int32)
+    p = (R[obs_cam] @ pts[obs_pt][:, :, None])[:, :, 0] + tvec[obs_cam]
+    uv = np.stack([fx * p[:, 0] / p[:, 2], fy * p[:, 1] / p[:, 2]], 1) + rng.normal(0, noise_px, (len(obs_cam), 2))
+    cam_const = np.zeros(n_cams, np.uint8)
+    cam_const[0] = 1
+    pts = pts + rng.normal(0, 0.01, pts.shape)
+    cams = cams.copy()
+    cams[1:] += rng.normal(0, 0.005, (n_cams - 1, 6))
+    return {"cams": cams, "pts": pts, "obs_uv": uv, "obs_cam": obs_cam, "obs_pt": obs_pt, "cam_const": cam_const,
+            "fx": fx, "fy": fy}
+
+
+def bench_ba(ctx, args, rank, world, dist, dev, peaks):
+    """BASELINE configs[3]: 128 cams / 50k points / ~500k observations.  One "BA iteration" = evaluate all residual
+    blocks + Jacobians + Schur-eliminate onto the camera system (+ the all-reduce when world > 1).  Returns a dict."""
+    import torch
+    from monocularsfm_b200.sharding import shard_ba_problem
+    P = make_ba_problem(args.ba_cams, args.ba_pts * world, args.ba_track, 4321)          # weak scaling: points grow with N
+    L = shard_ba_problem(P, rank, world) if world > 1 else P
+    ba = ctx.ba_create(L["cams"], L["pts"], L["obs_uv"], L["obs_cam"], L["obs_pt"], L["cam_const"], L["fx"], L["fy"])
+    n_obs_total = len(P["obs_cam"])
+    iters = max(10, args.steps * 4)
+    for _ in range(3):
+        ba.linearize(1e-4, want_S=False)
+    ctx.prof_enable(True)
+    ctx.prof_reset()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        ba.linearize(1e-4, want_S=False)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    prof = ctx.prof_read()
+    ctx.prof_enable(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    k_ms = prof["ba_schur"]["ms"] / max(1, prof["ba_schur"]["launches"])
+    n6 = 6 * ba.n_free
+    # algorithmic bytes of one launch on this rank (fp64 storage): 24 B/obs stream-in + parameters + reduced system write
+    alg_bytes = 24.0 * len(L["obs_cam"]) + 48.0 * len(L["cams"]) + 24.0 * len(L["pts"]) + 8.0 * (n6 * n6 + 3 * n6)
+    out = {"workload": f"BA {len(P['cams'])} cams / {len(P['pts'])} points / {n_obs_total} observations (all ranks)",
+           "metric": "observations/s per BA iteration (evaluate + Jacobians + Schur reduction" + (" + all-reduce)" if world > 1 else ")"),
+           "value": n_obs_total / (ms * 1e-3), "unit": "observations/s", "ms_per_iteration": ms,
+           "kernel_ms": k_ms, "dtype": "f64 geometry / f32 block products / f64 accumulation",
+           "roofline": {"bound": "hbm", "kernel": "linearize_schur_kernel", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None,
+                        "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": (alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if k_ms else None, "traffic": None,
+                        "algorithmic_bytes": alg_bytes,
+                        "note": "atomic-throughput bound, far from the HBM roof: see DESIGN.md B-path"}}
+    # full LM solve (the call CeresBundelOptimizer::Optimize makes)
+    t0 = time.perf_counter()
+    summ = ba.solve()
+    out["lm"] = {"iterations": summ["iterations"], "termination": summ["termination"], "initial_cost": summ["initial_cost"],
+                 "final_cost": summ["final_cost"], "wall_s": time.perf_counter() - t0,
+                 "rmse_px": float(np.sqrt(2 * summ["final_cost"] / max(1, summ["num_residuals"])))}
+    if rank == 0 and world == 1 and args.cpu_pairs > 0:
+        from oracle import ba_oracle as bo
+        lib = bo.c_oracle()
+        if lib is not None:
+            reps, tt = 0, 0.0
+            while tt < 5.0 and reps < 20:
+                _, _, _, dt = bo.c_linearize(P, 1e-4, lib)
+                tt += dt
+                reps += 1
+            out["cpu_baseline"] = {"value": n_obs_total * reps / tt, "unit": "observations/s", "cores": 1, "kind": "port",
+                                   "sample": f"{reps} full evaluate+Schur passes of oracle/ba_oracle.c (float64 Jets + dense Schur, "
+                                             "1 thread like the reference's Ceres call, which never sets num_threads); Ceres "
+                                             "itself is not installed in this image"}
+    ba.close()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -209,6 +319,12 @@ def run_ours(args, rank, world, local_rank):
 
     n_img, n = args.images, args.ndesc
     ctx = m.Context(local_rank)
+    if dist:
+        # the library's own NCCL communicator (ncclAllReduce of the reduced camera system); id travels over the
+        # torch.distributed store
+        uid = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
     descs = make_descriptors_torch(n_img, n, 1234 + rank, dev)           # [n_img, n, 128] u8, resident in HBM
     torch.cuda.synchronize()
     pairs = all_pairs(n_img)
@@ -298,8 +414,14 @@ def run_ours(args, rank, world, local_rank):
     value = work_per_step * args.steps / (ms_total_max * 1e-3)
     e2e_value = work_per_step * e2e_steps / (e2e_ms_max * 1e-3)
 
+    peaks = load_peaks()
+    ba_out = None
+    if not args.no_ba:
+        try:
+            ba_out = bench_ba(ctx, args, rank, world, dist, dev, peaks)
+        except Exception as ex:                      # the matching headline must survive a BA failure
+            ba_out = {"error": repr(ex)}
     if rank == 0:
-        peaks = load_peaks()
         k1 = prof["match_tile"]
         k1_avg_s = (k1["ms"] / max(1, k1["launches"])) * 1e-3
         steps_launches = max(1, k1["launches"])
@@ -340,7 +462,7 @@ def run_ours(args, rank, world, local_rank):
                         "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items() if v["launches"]},
-                "match_stats": stats}
+                "match_stats": stats, "ba": ba_out}
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist:
@@ -356,6 +478,10 @@ def main():
     ap.add_argument("--images", type=int, default=128)
     ap.add_argument("--ndesc", type=int, default=8192)
     ap.add_argument("--cpu-pairs", type=int, default=6, help="image pairs in the CPU-baseline sample")
+    ap.add_argument("--no-ba", action="store_true", help="skip the secondary BA measurement")
+    ap.add_argument("--ba-cams", type=int, default=128)
+    ap.add_argument("--ba-pts", type=int, default=50000)
+    ap.add_argument("--ba-track", type=float, default=10.0)
     args = ap.parse_args()
     rank = env_int("RANK", 0)
     world = env_int("WORLD_SIZE", 1)

@@ -143,6 +143,90 @@ int msfm_match_knn2_u8(msfm_ctx* ctx, const uint8_t* A, int32_t nA, const uint8_
  * in-group rescan, [2] rows that took the exact slow path, [3] tensor-kernel work units.  */
 int msfm_match_stats(msfm_ctx* ctx, int64_t stats[4]);
 
+/* ---------------------------------------------------------------------------------------------
+ * B-path: bundle-adjustment inner loop
+ *
+ * Replaces what CeresBundelOptimizer::Optimize (src/Optimizer/CeresBundleOptimizer.cpp:188-328) delegates to
+ * Ceres: residual + Jacobian of BundleAutoDiffConstantFocalCostFunction (:29-53, autodiff <2,3,3,3> at :65) for
+ * every Measurement of every Landmark (:213-247), the Schur elimination of the points onto the non-constant
+ * cameras (solver choice :264-273) and the Levenberg-Marquardt loop with the option block of :262-291.
+ * The problem is the flattened BundleData (include/Optimizer/BundleData.h:19-65); the C++ shim
+ * monocularsfm_b200/host flattens/unflattens it.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct msfm_ba msfm_ba;
+
+typedef struct {
+    int32_t n_cams, n_pts, n_obs;
+    int32_t reserved;             /* must be 0 */
+    double  fx, fy;               /* K(0,0), K(1,1) (:197-198) */
+    const double*  cams;          /* [n_cams][6]  rvec | tvec  (BundleData::CameraPose, cv::Mat 3x1 f64 each) */
+    const double*  pts;           /* [n_pts][3]   Landmark::point3D */
+    const double*  obs_uv;        /* [n_obs][2]   Measurement::point2D already centred: (x - cx, y - cy) as :221-222 */
+    const int32_t* obs_cam;       /* [n_obs]      index into cams */
+    const int32_t* obs_pt;        /* [n_obs]      index into pts, NON-DECREASING (observations grouped by landmark) */
+    const uint8_t* cam_const;     /* [n_cams]     1 = BundleData::constant_camera_pose (:256-260) */
+} msfm_ba_problem;
+
+typedef struct {
+    int32_t max_num_iterations;           /* 100 (:276), doubled below 10 cameras (:289) */
+    int32_t verbose;                      /* 1: one line per iteration on stdout */
+    double  function_tolerance;           /* Ceres default 1e-6, /10 below 10 cameras (:285) */
+    double  gradient_tolerance;           /* Ceres default 1e-10, /10 below 10 cameras (:286) */
+    double  parameter_tolerance;          /* Ceres default 1e-8, /10 below 10 cameras (:287) */
+    double  initial_trust_region_radius;  /* Ceres default 1e4 */
+} msfm_ba_options;
+
+#define MSFM_BA_CONVERGENCE     0   /* ceres::CONVERGENCE: Optimize returns true (:296) */
+#define MSFM_BA_NO_CONVERGENCE  1   /* iteration limit: the reference prints "Bundle Adjustment failed." and returns false */
+#define MSFM_BA_FAILURE         2
+
+typedef struct {
+    int32_t iterations;          /* LM iterations (linearisations) */
+    int32_t successful_steps;
+    int32_t termination;         /* MSFM_BA_* */
+    int32_t num_residuals;       /* 2 * n_obs summed over all ranks (summary.num_residuals, :305) */
+    double  initial_cost, final_cost;     /* 1/2 sum r^2, as Ceres (:306-307 print sqrt(2 cost / #res)) */
+    double  total_time_s, linearize_time_s, solve_time_s;
+} msfm_ba_summary;
+
+/* The option block the reference sets for a problem with n_cams camera poses (:262-291). */
+void msfm_ba_default_options(msfm_ba_options* opt, int32_t n_cams);
+
+/* Copy a problem to the device (all pointers HOST).  With a communicator attached to the ctx
+ * (msfm_comm_init) every rank passes ALL cameras and its own share of the points/observations. */
+int  msfm_ba_create(msfm_ctx* ctx, const msfm_ba_problem* prob, msfm_ba** out);
+void msfm_ba_destroy(msfm_ba* ba);
+/* Current parameters -> host ([n_cams][6], [n_pts][3]; either may be NULL). */
+int  msfm_ba_get_params(msfm_ba* ba, double* cams, double* pts);
+int  msfm_ba_set_params(msfm_ba* ba, const double* cams, const double* pts);
+
+/* Residuals (fp64) and Jacobians (fp32, [n_obs][2][9], columns rvec|tvec|point — the layout of the
+ * autodiff cost function's three parameter blocks) of the local observations; cost = 1/2 sum r^2 (local).
+ * r, J may be NULL. */
+int  msfm_ba_evaluate(msfm_ba* ba, double* r /*[n_obs][2]*/, float* J /*[n_obs][2][9]*/, double* cost);
+
+/* One linearisation at the current parameters: the reduced camera system of the free cameras with Marquardt
+ * damping diag(J^T J) / radius (inv_radius = 1/radius; 0 = undamped), summed over all ranks.
+ * S [6F][6F] (symmetric, fully filled), rhs [6F] (S dc = rhs), gc [6F] (gradient of the camera blocks); any may
+ * be NULL.  *n_free_out = F. */
+int  msfm_ba_linearize(msfm_ba* ba, double inv_radius, double* S, double* rhs, double* gc, double* cost,
+                       int32_t* n_free_out);
+
+/* The whole Levenberg-Marquardt solve; parameters stay on the device (msfm_ba_get_params to read). */
+int  msfm_ba_solve(msfm_ba* ba, const msfm_ba_options* opt, msfm_ba_summary* summary);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU; the reduced camera system is summed with ONE ncclAllReduce per
+ * linearisation over NVLink.  The unique id is created on rank 0 and distributed by the host program
+ * (torch.distributed / MPI / a file) — see INTEGRATION.md.
+ * ------------------------------------------------------------------------------------------- */
+#define MSFM_COMM_ID_BYTES 128
+int  msfm_comm_unique_id(void* id_out /*[128]*/);
+int  msfm_comm_init(msfm_ctx* ctx, int32_t n_ranks, int32_t rank, const void* id /*[128]*/);
+int  msfm_comm_destroy(msfm_ctx* ctx);
+/* sum (op 0) or max (op 1) of a DEVICE fp64 buffer across ranks, in place, on the ctx stream */
+int  msfm_comm_allreduce_f64(msfm_ctx* ctx, double* buf_dev, int64_t count, int32_t op);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,8 @@ names.  This Python package is only the ctypes binding used by the tests, ``benc
 ``torch.distributed`` plumbing; it contains no compute and no CPU fallback.
 """
 from ._ffi import (  # noqa: F401
+    BAOptions,
+    BAProblem,
     Context,
     MatchOptions,
     MsfmError,
@@ -14,4 +16,4 @@ from ._ffi import (  # noqa: F401
     exported_symbols,
 )
 
-__all__ = ["Context", "MatchOptions", "MsfmError", "lib_path", "load_library", "exported_symbols"]
+__all__ = ["BAOptions", "BAProblem", "Context", "MatchOptions", "MsfmError", "lib_path", "load_library", "exported_symbols"]

@@ -31,6 +31,27 @@ class MatchOptions(C.Structure):
                          int(bool(opencv_quirks)), 0)
 
 
+class BAProblemC(C.Structure):
+    _fields_ = [("n_cams", C.c_int32), ("n_pts", C.c_int32), ("n_obs", C.c_int32), ("reserved", C.c_int32),
+                ("fx", C.c_double), ("fy", C.c_double), ("cams", C.c_void_p), ("pts", C.c_void_p),
+                ("obs_uv", C.c_void_p), ("obs_cam", C.c_void_p), ("obs_pt", C.c_void_p), ("cam_const", C.c_void_p)]
+
+
+class BAOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int32), ("verbose", C.c_int32), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+                ("initial_trust_region_radius", C.c_double)]
+
+
+class BASummary(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("successful_steps", C.c_int32), ("termination", C.c_int32),
+                ("num_residuals", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("total_time_s", C.c_double), ("linearize_time_s", C.c_double), ("solve_time_s", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 def lib_path() -> str:
     return os.path.join(_HERE, "libmsfm_b200.so")
 
@@ -78,6 +99,18 @@ def load_library():
         "msfm_match_pairs_dev": (C.c_int, [vp, vp, i32, P(MatchOptions), vp, vp, vp, i64, P(i64)]),
         "msfm_match_knn2_u8": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, vp]),
         "msfm_match_stats": (C.c_int, [vp, P(i64)]),
+        "msfm_ba_default_options": (None, [P(BAOptions), i32]),
+        "msfm_ba_create": (C.c_int, [vp, P(BAProblemC), P(vp)]),
+        "msfm_ba_destroy": (None, [vp]),
+        "msfm_ba_get_params": (C.c_int, [vp, vp, vp]),
+        "msfm_ba_set_params": (C.c_int, [vp, vp, vp]),
+        "msfm_ba_evaluate": (C.c_int, [vp, vp, vp, P(C.c_double)]),
+        "msfm_ba_linearize": (C.c_int, [vp, C.c_double, vp, vp, vp, P(C.c_double), P(i32)]),
+        "msfm_ba_solve": (C.c_int, [vp, P(BAOptions), P(BASummary)]),
+        "msfm_comm_unique_id": (C.c_int, [vp]),
+        "msfm_comm_init": (C.c_int, [vp, i32, i32, vp]),
+        "msfm_comm_destroy": (C.c_int, [vp]),
+        "msfm_comm_allreduce_f64": (C.c_int, [vp, vp, i64, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -203,7 +236,95 @@ class Context:
                                                 _ptr(dist), _ptr(d2)))
         return idx, dist, d2
 
+    # ---- B-path
+    def ba_create(self, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy):
+        return BAProblem(self, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy)
+
+    # ---- multi-GPU
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_char * 128)()
+        self._check(self.lib.msfm_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, n_ranks: int, rank: int, uid: bytes):
+        buf = (C.c_char * 128).from_buffer_copy(uid)
+        self._check(self.lib.msfm_comm_init(self.h, n_ranks, rank, buf))
+
+    def comm_destroy(self):
+        self._check(self.lib.msfm_comm_destroy(self.h))
+
+    def comm_allreduce_f64(self, dev_ptr: int, count: int, op: int = 0):
+        self._check(self.lib.msfm_comm_allreduce_f64(self.h, C.c_void_p(dev_ptr), count, op))
+
     def match_stats(self):
         s = (C.c_int64 * 4)()
         self._check(self.lib.msfm_match_stats(self.h, s))
         return {"rows": s[0], "rescans": s[1], "exact_rows": s[2], "units": s[3]}
+
+
+class BAProblem:
+    """msfm_ba: a flattened BundleData resident on the device."""
+
+    def __init__(self, ctx: Context, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        cams = np.ascontiguousarray(cams, np.float64).reshape(-1, 6)
+        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+        obs_uv = np.ascontiguousarray(obs_uv, np.float64).reshape(-1, 2)
+        obs_cam = np.ascontiguousarray(obs_cam, np.int32)
+        obs_pt = np.ascontiguousarray(obs_pt, np.int32)
+        cam_const = np.ascontiguousarray(cam_const, np.uint8)
+        self.n_cams, self.n_pts, self.n_obs = len(cams), len(pts), len(obs_cam)
+        self.n_free = int((cam_const == 0).sum())
+        pr = BAProblemC(self.n_cams, self.n_pts, self.n_obs, 0, float(fx), float(fy), _ptr(cams), _ptr(pts),
+                        _ptr(obs_uv), _ptr(obs_cam), _ptr(obs_pt), _ptr(cam_const))
+        h = C.c_void_p()
+        ctx._check(self.lib.msfm_ba_create(ctx.h, C.byref(pr), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.lib.msfm_ba_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def get_params(self):
+        cams = np.zeros((self.n_cams, 6))
+        pts = np.zeros((self.n_pts, 3))
+        self.ctx._check(self.lib.msfm_ba_get_params(self.h, _ptr(cams), _ptr(pts)))
+        return cams, pts
+
+    def set_params(self, cams=None, pts=None):
+        cams = None if cams is None else np.ascontiguousarray(cams, np.float64)
+        pts = None if pts is None else np.ascontiguousarray(pts, np.float64)
+        self.ctx._check(self.lib.msfm_ba_set_params(self.h, _ptr(cams), _ptr(pts)))
+
+    def evaluate(self, want_r=True, want_J=True):
+        r = np.zeros((self.n_obs, 2)) if want_r else None
+        J = np.zeros((self.n_obs, 2, 9), np.float32) if want_J else None
+        cost = C.c_double(0)
+        self.ctx._check(self.lib.msfm_ba_evaluate(self.h, _ptr(r), _ptr(J), C.byref(cost)))
+        return r, J, cost.value
+
+    def linearize(self, inv_radius=0.0, want_S=True):
+        n6 = 6 * self.n_free
+        S = np.zeros((n6, n6)) if want_S else None
+        rhs = np.zeros(n6)
+        gc = np.zeros(n6)
+        cost = C.c_double(0)
+        nf = C.c_int32(0)
+        self.ctx._check(self.lib.msfm_ba_linearize(self.h, float(inv_radius), _ptr(S), _ptr(rhs), _ptr(gc),
+                                                   C.byref(cost), C.byref(nf)))
+        return S, rhs, gc, cost.value
+
+    def default_options(self):
+        o = BAOptions()
+        self.lib.msfm_ba_default_options(C.byref(o), self.n_cams)
+        return o
+
+    def solve(self, opt: BAOptions | None = None):
+        opt = opt or self.default_options()
+        s = BASummary()
+        self.ctx._check(self.lib.msfm_ba_solve(self.h, C.byref(opt), C.byref(s)))
+        return s.as_dict()

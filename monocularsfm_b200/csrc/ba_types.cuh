@@ -1,0 +1,33 @@
+// Device-side data layout of the B-path (bundle adjustment).  See DESIGN.md §"B-path layout".
+#pragma once
+#include <cstdint>
+
+namespace msfm {
+namespace ba {
+
+// Per-camera quantities recomputed once per parameter update (fp64): rotation matrix of Ceres'
+// AngleAxisRotatePoint and the four scalar coefficients of its derivative.
+struct CamPre {
+    double R[9];
+    double w[3];
+    double t[3];
+    double a, b, a1, b1;
+    double pad;
+};
+
+// SoA view of a BundleData (include/Optimizer/BundleData.h:19-65) flattened for the device.
+struct Problem {
+    int32_t n_cams, n_pts, n_obs, n_free;
+    double fx, fy;
+    const CamPre* pre;          // [n_cams]
+    const double* pts;          // [n_pts][3]
+    const double* obs_uv;       // [n_obs][2], centred by (cx, cy)
+    const int32_t* obs_cam;     // [n_obs]
+    const int32_t* obs_pt;      // [n_obs], non-decreasing
+    const int32_t* pt_start;    // [n_pts+1] CSR over observations
+    const int32_t* cam_free;    // [n_cams] index among the free cameras or -1 (constant pose)
+    unsigned long long* gpmax_bits;   // max |g_p| as the bit pattern of a non-negative double
+};
+
+}  // namespace ba
+}  // namespace msfm

@@ -65,6 +65,11 @@ struct msfm_ctx {
     msfm::GrowBuf d_out_offsets, d_out_matches, d_out_dist;
     int64_t stats[4] = {0, 0, 0, 0};
 
+    // ---- B-path / multi-GPU
+    void* cusolver = nullptr;      // cusolverDnHandle_t (reduced camera system Cholesky)
+    void* comm = nullptr;          // ncclComm_t
+    int comm_ranks = 1, comm_rank = 0;
+
     // ---- optional per-kernel-class timing with CUDA events on the ctx stream (bench.py roofline)
     struct ProfRec { int cat; cudaEvent_t a, b; };
     bool prof_on = false;

@@ -19,6 +19,7 @@ cudaError_t launch_count_scan_write(const ImgDev*, const SegDev*, int, MatchOpts
                                     int32_t*, long long*, long long*, long long, int32_t*, float*, cudaStream_t);
 }  // namespace msfm
 
+namespace msfm { void ctx_destroy_solver(msfm_ctx* c); }
 using namespace msfm;
 
 static thread_local std::string g_init_error;
@@ -74,6 +75,8 @@ void msfm_destroy(msfm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    msfm_comm_destroy(c);
+    msfm::ctx_destroy_solver(c);
     c->prof_collect();
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (auto& im : c->imgs)

@@ -1,0 +1,107 @@
+"""GPU parity tests of the B-path through the C-ABI against the float64 oracle / golden vectors.
+
+Tolerances (north_star: "Ceres residual/Jacobian values within 1e-5 relative fp32"):
+  residuals  fp64 on the device          |dr| <= 1e-9 px
+  Jacobians  fp32 storage                |dJ| <= 1e-5 * max(|J_row|)  per observation row
+  S, rhs     fp32 block products, fp64 accumulation   relative to the largest entry: 1e-5
+"""
+import os
+
+import numpy as np
+import pytest
+
+import monocularsfm_b200 as m
+from oracle import ba_oracle as bo
+
+pytestmark = pytest.mark.gpu
+NAMES = ["small", "special", "ring16"]
+
+
+@pytest.fixture(scope="module")
+def golden_ba():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "ba_golden.npz"))
+
+
+def _prob(g, name):
+    return {k: g[f"{name}/{k}"] for k in ("cams", "pts", "obs_uv", "obs_cam", "obs_pt", "cam_const")} | {
+        "fx": float(g[f"{name}/fx"]), "fy": float(g[f"{name}/fy"])}
+
+
+def _create(ctx, P):
+    return ctx.ba_create(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_residuals_and_jacobians(ctx, golden_ba, name):
+    g = golden_ba
+    ba = _create(ctx, _prob(g, name))
+    r, J, cost = ba.evaluate()
+    np.testing.assert_allclose(r, g[f"{name}/r"], rtol=0, atol=1e-9)
+    assert abs(cost - float(g[f"{name}/cost"])) <= 1e-9 * float(g[f"{name}/cost"])
+    Jo = g[f"{name}/J"]
+    scale = np.abs(Jo).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(J - Jo) <= 1e-5 * scale).all(), float((np.abs(J - Jo) / scale).max())
+    ba.close()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_schur_system(ctx, golden_ba, name):
+    g = golden_ba
+    ba = _create(ctx, _prob(g, name))
+    S, rhs, gc, cost = ba.linearize(1e-4)
+    So, ro = g[f"{name}/S"], g[f"{name}/rhs"]
+    assert np.abs(S - So).max() <= 1e-5 * np.abs(So).max(), np.abs(S - So).max() / np.abs(So).max()
+    assert np.abs(rhs - ro).max() <= 1e-5 * np.abs(ro).max()
+    assert np.abs(gc - g[f"{name}/gc_free"]).max() <= 1e-5 * np.abs(g[f"{name}/gc_free"]).max()
+    # the step it implies agrees with the oracle's step
+    d, do = np.linalg.solve(S, rhs), np.linalg.solve(So, ro)
+    assert np.abs(d - do).max() <= 1e-4 * np.abs(do).max()
+    ba.close()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_lm_solve_matches_oracle(ctx, golden_ba, name):
+    g = golden_ba
+    P = _prob(g, name)
+    ba = _create(ctx, P)
+    opt = ba.default_options()
+    opt.max_num_iterations = 100
+    opt.function_tolerance = 1e-6
+    opt.gradient_tolerance = 1e-10
+    opt.parameter_tolerance = 1e-8
+    s = ba.solve(opt)
+    costs = g[f"{name}/lm_costs"]
+    assert s["termination"] == 0
+    assert abs(s["initial_cost"] - costs[0]) <= 1e-9 * costs[0]
+    assert abs(s["final_cost"] - costs[-1]) <= 1e-5 * costs[-1], (s, costs[-1])
+    cams, pts = ba.get_params()
+    const = P["cam_const"] == 1
+    np.testing.assert_array_equal(cams[const], P["cams"][const])
+    # same optimum (the problem is well conditioned once gauge-fixed by the constant camera)
+    r = bo.residuals_only(cams, pts, P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
+    assert abs(bo.cost_of(r) - s["final_cost"]) <= 1e-9 * s["final_cost"]
+    ba.close()
+
+
+def test_medium_problem_vs_oracle(ctx):
+    """128 cameras / 5 000 points (1/10 of BASELINE configs[3]): per-observation parity + LM progress."""
+    P = bo.make_problem(128, 5000, 10, 42)
+    ba = _create(ctx, P)
+    r, J, cost = ba.evaluate()
+    ro, Jo = bo.residual_jacobian_jets(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
+    np.testing.assert_allclose(r, ro, rtol=0, atol=1e-9)
+    scale = np.abs(Jo).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(J - Jo) <= 1e-5 * scale).all()
+    s = ba.solve()
+    assert s["termination"] == 0 and s["final_cost"] < 0.1 * s["initial_cost"]
+    rms = np.sqrt(2 * s["final_cost"] / s["num_residuals"])
+    assert 0.3 < rms < 0.6            # observation noise is 0.5 px per coordinate
+    ba.close()
+
+
+def test_bad_problem_is_rejected(ctx):
+    P = bo.make_problem(4, 10, 3, 0)
+    bad = P["obs_pt"].copy()
+    bad[0], bad[-1] = bad[-1], bad[0]
+    with pytest.raises(m.MsfmError):
+        ctx.ba_create(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], bad, P["cam_const"], P["fx"], P["fy"])

@@ -10,7 +10,14 @@ CU_SRCS   := $(wildcard $(CSRC)/*.cu)
 CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) include/msfm_b200.h
 
-all: $(LIB)
+HOSTDIR   := monocularsfm_b200/host
+HOSTLIB   := monocularsfm_b200/libmsfm_host.so
+HOST_SRCS := $(wildcard $(HOSTDIR)/src/*.cpp)
+HOST_HDRS := $(wildcard $(HOSTDIR)/include/*/*.h) $(wildcard $(HOSTDIR)/src/*.h) include/msfm_b200.h
+CXX       ?= g++
+CXXFLAGS  := -O2 -std=c++14 -fPIC -Wall -Wno-sign-compare -I$(HOSTDIR)/include -Iinclude
+
+all: $(LIB) $(HOSTLIB) build/host_test
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -19,8 +26,16 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 $(LIB): $(CU_OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcusolver -ldl -Xlinker -rpath=/usr/local/cuda/lib64
 
+# C++ classes with the reference's names (FeatureUtils, FeatureMatcher, Database, BundleData, CeresBundelOptimizer)
+$(HOSTLIB): $(HOST_SRCS) $(HOST_HDRS) $(LIB)
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) -Lmonocularsfm_b200 -lmsfm_b200 -ldl -Wl,-rpath,'$$ORIGIN'
+
+build/host_test: $(HOSTDIR)/test/host_test.cpp $(HOSTLIB)
+	@mkdir -p build
+	$(CXX) $(CXXFLAGS) -o $@ $< -Lmonocularsfm_b200 -lmsfm_host -lmsfm_b200 -Wl,-rpath,'$$ORIGIN/../monocularsfm_b200'
+
 clean:
-	rm -rf build/obj $(LIB)
+	rm -rf build/obj $(LIB) $(HOSTLIB) build/host_test
 
 .PHONY: all clean
 

@@ -1,0 +1,147 @@
+// BundleData::Debug and CeresBundelOptimizer::Optimize on top of the C-ABI B-path.
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <iostream>
+#include <vector>
+
+#include "DeviceContext.h"
+#include "Optimizer/BundleData.h"
+#include "Optimizer/CeresBundleOptimizer.h"
+
+using namespace MonocularSfM;
+
+void initLogging() {}
+
+namespace {
+// AoS hash maps -> SoA arrays.  Landmarks are visited in id order so the flattening is deterministic
+// (the reference iterates in hash order, CeresBundleOptimizer.cpp:213; the optimum does not depend on it).
+struct Flat {
+    std::vector<image_t> cam_ids;
+    std::vector<point3D_t> pt_ids;
+    std::vector<double> cams, pts, uv;
+    std::vector<int32_t> obs_cam, obs_pt;
+    std::vector<uint8_t> cam_const;
+    double fx, fy, cx, cy;
+};
+
+Flat Flatten(BundleData& bd) {
+    assert(bd.K.type() == CV_64F);                                           // :190
+    Flat f;
+    f.fx = bd.K.at<double>(0, 0); f.fy = bd.K.at<double>(1, 1);              // :197-200
+    f.cx = bd.K.at<double>(0, 2); f.cy = bd.K.at<double>(1, 2);
+    for (auto& el : bd.camera_poses) f.cam_ids.push_back(el.first);
+    std::sort(f.cam_ids.begin(), f.cam_ids.end());
+    std::unordered_map<image_t, int> cam_index;
+    for (size_t i = 0; i < f.cam_ids.size(); ++i) cam_index[f.cam_ids[i]] = static_cast<int>(i);
+    f.cams.resize(f.cam_ids.size() * 6);
+    f.cam_const.assign(f.cam_ids.size(), 0);
+    for (size_t i = 0; i < f.cam_ids.size(); ++i) {
+        BundleData::CameraPose& cp = bd.camera_poses[f.cam_ids[i]];
+        for (int k = 0; k < 3; ++k) {
+            f.cams[6 * i + k] = cp.rvec.at<double>(k, 0);
+            f.cams[6 * i + 3 + k] = cp.tvec.at<double>(k, 0);
+        }
+        if (bd.constant_camera_pose.count(f.cam_ids[i])) f.cam_const[i] = 1;   // :256-260
+    }
+    for (auto& el : bd.landmarks) f.pt_ids.push_back(el.first);
+    std::sort(f.pt_ids.begin(), f.pt_ids.end());
+    f.pts.resize(f.pt_ids.size() * 3);
+    for (size_t p = 0; p < f.pt_ids.size(); ++p) {
+        BundleData::Landmark& lm = bd.landmarks[f.pt_ids[p]];
+        for (int k = 0; k < 3; ++k) f.pts[3 * p + k] = lm.point3D(k);
+        for (const BundleData::Measurement& m : lm.measurements) {
+            f.obs_cam.push_back(cam_index.at(m.image_id));
+            f.obs_pt.push_back(static_cast<int32_t>(p));
+            f.uv.push_back(m.point2D(0) - f.cx);                               // :221-222
+            f.uv.push_back(m.point2D(1) - f.cy);
+        }
+    }
+    return f;
+}
+
+msfm_ba* CreateOnDevice(const Flat& f) {
+    msfm_ba_problem pr;
+    pr.n_cams = static_cast<int32_t>(f.cam_ids.size());
+    pr.n_pts = static_cast<int32_t>(f.pt_ids.size());
+    pr.n_obs = static_cast<int32_t>(f.obs_cam.size());
+    pr.reserved = 0;
+    pr.fx = f.fx; pr.fy = f.fy;
+    pr.cams = f.cams.data(); pr.pts = f.pts.data(); pr.obs_uv = f.uv.data();
+    pr.obs_cam = f.obs_cam.data(); pr.obs_pt = f.obs_pt.data(); pr.cam_const = f.cam_const.data();
+    msfm_ba* ba = nullptr;
+    device::Check(msfm_ba_create(device::Context(), &pr, &ba), "msfm_ba_create");
+    return ba;
+}
+}  // namespace
+
+double BundleData::Debug() {
+    // mean over landmarks of the mean per-measurement reprojection error (BundleData.cpp:9-37); the per-measurement
+    // error ||K [R|t] X - x|| equals the norm of the BA residual (Projection.cpp:114-133 vs CeresBundleOptimizer.cpp:44-51)
+    Flat f = Flatten(*this);
+    if (f.obs_cam.empty()) return 0.0;
+    msfm_ba* ba = CreateOnDevice(f);
+    std::vector<double> r(f.obs_cam.size() * 2);
+    double cost = 0;
+    device::Check(msfm_ba_evaluate(ba, r.data(), nullptr, &cost), "msfm_ba_evaluate");
+    msfm_ba_destroy(ba);
+    double sum = 0, num = 0;
+    size_t i = 0;
+    while (i < f.obs_pt.size()) {
+        size_t e = i;
+        double s = 0;
+        while (e < f.obs_pt.size() && f.obs_pt[e] == f.obs_pt[i]) { s += std::sqrt(r[2 * e] * r[2 * e] + r[2 * e + 1] * r[2 * e + 1]); ++e; }
+        sum += s / static_cast<double>(e - i);
+        num += 1;
+        i = e;
+    }
+    return sum / num;
+}
+
+CeresBundelOptimizer::CeresBundelOptimizer(const Parameters& params) : params_(params) {}
+
+bool CeresBundelOptimizer::Optimize(BundleData& bundle_data) {
+    if (params_.refine_focal_length) {
+        // The shared-focal variant (BundleAutoDiffCostFunction, CeresBundleOptimizer.cpp:76-121) is not on the device yet
+        // (SURVEY §8f-3); like every failed solve of the reference this prints and returns false (:296-301).
+        std::cout << "Bundle Adjustment failed. (refine_focal_length is not supported by the B200 path)" << std::endl;
+        return false;
+    }
+    Flat f = Flatten(bundle_data);
+    if (f.obs_cam.empty() || f.cam_ids.empty()) {
+        std::cout << "Bundle Adjustment failed." << std::endl;
+        return false;
+    }
+    msfm_ba* ba = CreateOnDevice(f);
+    msfm_ba_options opt;
+    msfm_ba_default_options(&opt, static_cast<int32_t>(bundle_data.camera_poses.size()));   // :262-291
+    msfm_ba_summary s;
+    device::Check(msfm_ba_solve(ba, &opt, &s), "msfm_ba_solve");
+    // parameters are written back in place whatever the outcome, like Ceres mutating the caller's blocks (:230-242)
+    device::Check(msfm_ba_get_params(ba, f.cams.data(), f.pts.data()), "msfm_ba_get_params");
+    msfm_ba_destroy(ba);
+    for (size_t i = 0; i < f.cam_ids.size(); ++i) {
+        BundleData::CameraPose& cp = bundle_data.camera_poses[f.cam_ids[i]];
+        for (int k = 0; k < 3; ++k) {
+            cp.rvec.at<double>(k, 0) = f.cams[6 * i + k];
+            cp.tvec.at<double>(k, 0) = f.cams[6 * i + 3 + k];
+        }
+    }
+    for (size_t p = 0; p < f.pt_ids.size(); ++p)
+        for (int k = 0; k < 3; ++k) bundle_data.landmarks[f.pt_ids[p]].point3D(k) = f.pts[3 * p + k];
+    last_iterations_ = s.iterations;
+    last_initial_cost_ = s.initial_cost;
+    last_final_cost_ = s.final_cost;
+    if (s.termination != MSFM_BA_CONVERGENCE) {                                // :296-301
+        std::cout << "Bundle Adjustment failed." << std::endl;
+        return false;
+    }
+    std::cout << std::endl
+              << "Bundle Adjustment statistics (approximated RMSE):\n"
+              << " #residuals: " << s.num_residuals << "\n"
+              << " Initial RMSE: " << std::sqrt(s.initial_cost * 2 / s.num_residuals) << "\n"
+              << " Final RMSE: " << std::sqrt(s.final_cost * 2 / s.num_residuals) << "\n"
+              << " Time (s): " << s.total_time_s << "\n"
+              << std::endl;                                                    // :303-310
+    return true;
+}

@@ -1,0 +1,183 @@
+#include "Feature/FeatureMatching.h"
+
+#include <algorithm>
+#include <chrono>
+#include <iostream>
+
+#include "DeviceContext.h"
+#include "Feature/FeatureUtils.h"
+
+using namespace MonocularSfM;
+
+namespace {
+const int32_t kTopScaleIdBase = 1000000000;   // device ids of the preemptive-matching (top-scale) descriptor subsets
+}
+
+// Read an image's descriptors from the database once, bridge CV_32F -> u8, keep them resident on the device.
+void FeatureMatcher::EnsureResident(image_t image_id) {
+    if (resident_.count(image_id)) return;
+    const cv::Mat desc = database_->ReadDescriptors(image_id);              // FeatureMatching.cpp:32-33
+    const cv::Mat u8 = FeatureUtils::ToUint8Descriptors(desc);
+    bool quantised = false;
+    if (desc.type() == CV_32F && desc.rows > 0) {
+        // integral rows are cast losslessly; anything else went through the x512 quantisation
+        const float v = desc.at<float>(0, 0);
+        quantised = !(u8.at<unsigned char>(0, 0) == v);
+        for (int j = 1; j < desc.cols && !quantised; ++j) quantised = !(u8.at<unsigned char>(0, j) == desc.at<float>(0, j));
+    }
+    quantised_[image_id] = quantised;
+    msfm_ctx* ctx = device::Context();
+    device::Check(msfm_desc_upload_u8(ctx, image_id, u8.data, u8.rows), "msfm_desc_upload_u8");
+    device::Check(msfm_sync(ctx), "msfm_sync");                             // u8 goes out of scope
+    resident_.insert(image_id);
+}
+
+void FeatureMatcher::MatchImagePairs(const std::vector<std::pair<image_t, image_t>>& image_pairs) {
+    database_->BeginTransaction();                                           // FeatureMatching.cpp:13
+    const auto t0 = std::chrono::steady_clock::now();
+    // pairs that already have a row are skipped — this is the reference's resume mechanism (:23-27)
+    std::vector<std::pair<image_t, image_t>> todo;
+    for (const auto& pr : image_pairs) {
+        if (database_->ExistMatches(pr.first, pr.second)) {
+            if (verbose_) std::cout << "Compute Matches " << pr.first << " - " << pr.second << " Existing, Continue!" << std::endl;
+            continue;
+        }
+        todo.push_back(pr);
+    }
+    bool any_quantised = false;
+    for (const auto& pr : todo) {
+        EnsureResident(pr.first);
+        EnsureResident(pr.second);
+        any_quantised = any_quantised || quantised_[pr.first] || quantised_[pr.second];
+    }
+    if (!todo.empty()) {
+        std::vector<int32_t> ids(todo.size() * 2);
+        int64_t bound = 0;
+        msfm_ctx* ctx = device::Context();
+        for (size_t p = 0; p < todo.size(); ++p) {
+            ids[2 * p] = todo[p].first;
+            ids[2 * p + 1] = todo[p].second;
+            bound += msfm_desc_count(ctx, todo[p].first);
+        }
+        msfm_match_options opt;
+        // FilterMatchesByDistance(max_distance_) (:49): max_distance_ is given for unit-norm float descriptors; on the
+        // quantised u8 scale it becomes max_distance_ * 512, on raw integral SIFT (norm ~512) likewise.
+        opt.max_distance = max_distance_ < 0 ? -1.0 : max_distance_ * FeatureUtils::QuantisationScale();
+        opt.distance_ratio = static_cast<float>(distance_ratio_);            // narrowed like FeatureUtils.h:95
+        opt.cross_check = cross_check_ ? 1 : 0;
+        opt.opencv_quirks = 1;
+        opt.reserved = 0;
+        std::vector<int64_t> offsets(todo.size() + 1);
+        std::vector<int32_t> out(static_cast<size_t>(std::max<int64_t>(1, bound)) * 2);
+        std::vector<float> dist(std::max<int64_t>(1, bound));
+        int64_t total = 0;
+        device::Check(msfm_match_pairs(ctx, ids.data(), static_cast<int32_t>(todo.size()), &opt, offsets.data(), out.data(),
+                                       dist.data(), bound, &total), "msfm_match_pairs");
+        for (size_t p = 0; p < todo.size(); ++p) {
+            std::vector<cv::DMatch> prune_matches;
+            for (int64_t k = offsets[p]; k < offsets[p + 1]; ++k)
+                prune_matches.push_back(cv::DMatch(out[2 * k], out[2 * k + 1], 0, dist[k]));
+            std::vector<cv::DMatch> verified;
+            if (geometric_filter_) {
+                std::vector<cv::KeyPoint> k1 = database_->ReadKeyPoints(todo[p].first), k2 = database_->ReadKeyPoints(todo[p].second);
+                std::vector<cv::Point2f> p1(k1.size()), p2(k2.size());
+                for (size_t i = 0; i < k1.size(); ++i) p1[i] = k1[i].pt;
+                for (size_t i = 0; i < k2.size(); ++i) p2[i] = k2[i].pt;
+                geometric_filter_(p1, p2, prune_matches, verified);          // FeatureUtils::FilterMatches (:60)
+            } else {
+                verified.swap(prune_matches);
+            }
+            if (verbose_) {
+                std::cout << "Compute Matches " << todo[p].first << " - " << todo[p].second << " ... " << std::endl;
+                std::cout << "\t matches num : " << verified.size() << std::endl;
+            }
+            database_->WriteMatches(todo[p].first, todo[p].second, verified);   // a row is written even for 0 matches (:68-70)
+        }
+    }
+    if (verbose_ && !todo.empty()) {
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::cout << "\t batch of " << todo.size() << " pairs: " << s << " s" << std::endl;
+    }
+    database_->EndTransaction();                                             // :72
+}
+
+void SequentialFeatureMatcher::RunMatching() {
+    database_ = cv::Ptr<Database>(new Database());
+    database_->Open(database_path_);
+    std::vector<Database::Image> images = database_->ReadAllImages();
+    // each image against its `overlap_` predecessors (FeatureMatching.cpp:82-98); the image list index is used as id,
+    // exactly as the reference does
+    for (size_t i = 1; i < images.size(); ++i) {
+        std::vector<std::pair<image_t, image_t>> image_pairs;
+        for (int k = 1; k <= overlap_; ++k) {
+            const int j = static_cast<int>(i) - k;
+            if (j < 0) break;
+            image_pairs.push_back(std::make_pair(static_cast<image_t>(i), static_cast<image_t>(j)));
+        }
+        MatchImagePairs(image_pairs);
+    }
+    database_->Close();
+}
+
+void BruteFeatureMatcher::RunMatching() {
+    database_ = cv::Ptr<Database>(new Database());
+    database_->Open(database_path_);
+    std::vector<Database::Image> images = database_->ReadAllImages();
+    for (size_t i = 0; i < images.size(); ++i) {                              // FeatureMatching.cpp:110-142
+        std::vector<std::pair<image_t, image_t>> image_pairs;
+        for (size_t j = 0; j < i; ++j) {
+            image_pairs.push_back(std::make_pair(static_cast<image_t>(i), static_cast<image_t>(j)));
+            if (static_cast<int>(image_pairs.size()) == max_pairs_size_) {
+                if (is_preemtive_) image_pairs = PreemptivelyFilterImagePairs(image_pairs);
+                MatchImagePairs(image_pairs);
+                image_pairs.clear();
+            }
+        }
+        if (!image_pairs.empty()) {
+            if (is_preemtive_) image_pairs = PreemptivelyFilterImagePairs(image_pairs);
+            MatchImagePairs(image_pairs);
+        }
+    }
+    database_->Close();
+}
+
+void BruteFeatureMatcher::EnsureTopScaleResident(image_t image_id) {
+    if (top_scale_resident_.count(image_id)) return;
+    const std::vector<cv::KeyPoint> kpts = database_->ReadKeyPoints(image_id);
+    const cv::Mat desc = database_->ReadDescriptors(image_id);
+    cv::Mat top;
+    FeatureUtils::ExtractTopScaleDescriptors(kpts, desc, preemtive_num_features_, top);   // :180-196
+    const cv::Mat u8 = FeatureUtils::ToUint8Descriptors(top);
+    msfm_ctx* ctx = device::Context();
+    device::Check(msfm_desc_upload_u8(ctx, kTopScaleIdBase + image_id, u8.data, u8.rows), "msfm_desc_upload_u8");
+    device::Check(msfm_sync(ctx), "msfm_sync");
+    top_scale_resident_.insert(image_id);
+}
+
+std::vector<std::pair<image_t, image_t>> BruteFeatureMatcher::PreemptivelyFilterImagePairs(
+    std::vector<std::pair<image_t, image_t>> image_pairs) {
+    std::vector<std::pair<image_t, image_t>> filtered;
+    if (image_pairs.empty()) return filtered;
+    std::vector<int32_t> ids(image_pairs.size() * 2);
+    for (size_t p = 0; p < image_pairs.size(); ++p) {
+        EnsureTopScaleResident(image_pairs[p].first);
+        EnsureTopScaleResident(image_pairs[p].second);
+        ids[2 * p] = kTopScaleIdBase + image_pairs[p].first;
+        ids[2 * p + 1] = kTopScaleIdBase + image_pairs[p].second;
+    }
+    msfm_match_options opt;
+    opt.max_distance = -1.0;                                                 // the pre-pass applies no distance filter (:160-170)
+    opt.distance_ratio = static_cast<float>(distance_ratio_);
+    opt.cross_check = cross_check_ ? 1 : 0;
+    opt.opencv_quirks = 1;
+    opt.reserved = 0;
+    const int64_t cap = static_cast<int64_t>(image_pairs.size()) * std::max(1, preemtive_num_features_);
+    std::vector<int64_t> offsets(image_pairs.size() + 1);
+    std::vector<int32_t> out(static_cast<size_t>(cap) * 2);
+    int64_t total = 0;
+    device::Check(msfm_match_pairs(device::Context(), ids.data(), static_cast<int32_t>(image_pairs.size()), &opt, offsets.data(),
+                                   out.data(), nullptr, cap, &total), "msfm_match_pairs(preemptive)");
+    for (size_t p = 0; p < image_pairs.size(); ++p)
+        if (offsets[p + 1] - offsets[p] >= preemtive_min_num_matches_) filtered.push_back(image_pairs[p]);   // :172-173
+    return filtered;
+}

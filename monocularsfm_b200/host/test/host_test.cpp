@@ -1,0 +1,182 @@
+// Test driver of the drop-in C++ classes (run by tests/test_host_cpp.py).
+//   host_test cpu <tmp.db>             Database round trip, pair ids, CrossCheck quirk, distance filter  (no GPU)
+//   host_test match <db> <preempt 0|1> BruteFeatureMatcher(db).RunMatching() on a database made by the Python test
+//   host_test seq <db>                 SequentialFeatureMatcher(db).RunMatching()
+//   host_test two <a.u8> <na> <b.u8> <nb> <out.txt>   FeatureUtils::ComputeMatches / ComputeCrossMatches on raw files
+//   host_test ba <in.bin> <out.bin>    CeresBundelOptimizer::Optimize on a BundleData read from a flat binary file
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "Database/Database.h"
+#include "Feature/FeatureMatching.h"
+#include "Feature/FeatureUtils.h"
+#include "Optimizer/CeresBundleOptimizer.h"
+
+using namespace MonocularSfM;
+
+#define REQUIRE(cond)                                                                    \
+    do {                                                                                 \
+        if (!(cond)) { std::fprintf(stderr, "REQUIRE failed: %s (line %d)\n", #cond, __LINE__); return 1; } \
+    } while (0)
+
+static int test_cpu(const std::string& path) {
+    std::remove(path.c_str());
+    {
+        Database db;
+        db.Open(path);
+        db.BeginTransaction();
+        Database::Image im;
+        im.name = "a.jpg";
+        const image_t id0 = db.WriteImage(im);
+        im.name = "b.jpg";
+        const image_t id1 = db.WriteImage(im);
+        REQUIRE(id0 == 1 && id1 == 2);                       // AUTOINCREMENT starts at 1, like the reference's DBs
+        cv::Mat d(3, 128, CV_32F);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 128; ++j) d.at<float>(i, j) = static_cast<float>((i * 7 + j) % 200);
+        db.WriteDescriptors(id0, d);
+        std::vector<cv::KeyPoint> kp(3);
+        kp[1].pt = cv::Point2f(3.5f, 4.5f);
+        kp[1].size = 9.f;
+        db.WriteKeyPoints(id0, kp);
+        std::vector<cv::DMatch> m;
+        m.push_back(cv::DMatch(5, 7, 0, 1.f));
+        m.push_back(cv::DMatch(6, 1, 0, 2.f));
+        db.WriteMatches(id1, id0, m);                        // id1 > id0: stored swapped
+        db.EndTransaction();
+        db.Close();
+    }
+    {
+        Database db;
+        db.Open(path);
+        REQUIRE(db.NumImages() == 2);
+        REQUIRE(db.ExistDescriptors(1) && !db.ExistDescriptors(2));
+        cv::Mat d = db.ReadDescriptors(1);
+        REQUIRE(d.rows == 3 && d.cols == 128 && d.type() == CV_32F && d.at<float>(2, 5) == 19.f);
+        REQUIRE(db.ReadKeyPoints(1)[1].size == 9.f && db.ReadKeyPoints(1)[1].pt.y == 4.5f);
+        REQUIRE(db.ExistMatches(2, 1) && db.ExistMatches(1, 2) && !db.ExistMatches(1, 3));
+        std::vector<cv::DMatch> a = db.ReadMatches(2, 1), b = db.ReadMatches(1, 2);
+        REQUIRE(a.size() == 2 && a[0].queryIdx == 5 && a[0].trainIdx == 7);
+        REQUIRE(b.size() == 2 && b[0].queryIdx == 7 && b[0].trainIdx == 5);     // read back in the other orientation
+        REQUIRE(db.ReadAllMatches().size() == 1 && db.ReadAllMatches()[0].first == 10002);
+        db.Close();
+    }
+    REQUIRE(Database::ImagePairToPairId(3, 12) == 30012 && Database::ImagePairToPairId(12, 3) == 30012);
+    image_t a, b;
+    Database::PairIdToImagePair(30012, &a, &b);
+    REQUIRE(a == 3 && b == 12);
+    // CrossCheck: queryIdx 0 survives when its trainIdx has no reverse match (unordered_map default 0)
+    std::vector<cv::DMatch> m12, m21, out;
+    m12.push_back(cv::DMatch(0, 4, 0, 1.f));
+    m12.push_back(cv::DMatch(1, 5, 0, 1.f));
+    m12.push_back(cv::DMatch(2, 6, 0, 1.f));
+    m21.push_back(cv::DMatch(6, 2, 0, 1.f));
+    FeatureUtils::CrossCheck(m12, m21, out);
+    REQUIRE(out.size() == 2 && out[0].queryIdx == 0 && out[1].queryIdx == 2);
+    std::vector<cv::DMatch> f;
+    m12[1].distance = 0.70001f;     // dropped
+    m12[0].distance = 0.7f;         // float(0.7) < 0.7 (double): kept, as `distance > max_distance` in the reference
+    m12[2].distance = 0.5f;
+    FeatureUtils::FilterMatchesByDistance(m12, f, 0.7);
+    REQUIRE(f.size() == 2);
+    // bridge: integral floats are cast, normalised floats are quantised x512
+    cv::Mat fl(1, 128, CV_32F);
+    fl.at<float>(0, 0) = 0.25f;
+    cv::Mat q = FeatureUtils::ToUint8Descriptors(fl);
+    REQUIRE(q.at<unsigned char>(0, 0) == 128);
+    std::printf("host cpu tests ok\n");
+    return 0;
+}
+
+static int run_two(char** argv) {
+    const int na = std::atoi(argv[3]), nb = std::atoi(argv[5]);
+    cv::Mat a(na, 128, CV_8U), b(nb, 128, CV_8U);
+    std::ifstream fa(argv[2], std::ios::binary), fb(argv[4], std::ios::binary);
+    fa.read(reinterpret_cast<char*>(a.data), static_cast<std::streamsize>(na) * 128);
+    fb.read(reinterpret_cast<char*>(b.data), static_cast<std::streamsize>(nb) * 128);
+    std::vector<cv::DMatch> m, mc;
+    FeatureUtils::ComputeMatches(a, b, m);                   // defaults: ratio 0.8
+    FeatureUtils::ComputeCrossMatches(a, b, mc, 0.8f);
+    std::ofstream out(argv[6]);
+    out.precision(9);
+    out << m.size() << "\n";
+    for (const cv::DMatch& d : m) out << d.queryIdx << " " << d.trainIdx << " " << d.distance << "\n";
+    out << mc.size() << "\n";
+    for (const cv::DMatch& d : mc) out << d.queryIdx << " " << d.trainIdx << " " << d.distance << "\n";
+    return 0;
+}
+
+static int run_ba(char** argv) {
+    // flat file: int32 n_cams n_pts n_obs n_const | f64 fx fy cx cy | cams[n_cams*6] | pts[n_pts*3] | obs_xy[n_obs*2] (pixels,
+    // NOT centred) | int32 obs_cam[n_obs] obs_pt[n_obs] const_ids[n_const]
+    std::ifstream in(argv[2], std::ios::binary);
+    int32_t hdr[4];
+    in.read(reinterpret_cast<char*>(hdr), sizeof hdr);
+    double k[4];
+    in.read(reinterpret_cast<char*>(k), sizeof k);
+    std::vector<double> cams(hdr[0] * 6), pts(hdr[1] * 3), xy(hdr[2] * 2);
+    std::vector<int32_t> oc(hdr[2]), op(hdr[2]), cst(hdr[3]);
+    in.read(reinterpret_cast<char*>(cams.data()), cams.size() * 8);
+    in.read(reinterpret_cast<char*>(pts.data()), pts.size() * 8);
+    in.read(reinterpret_cast<char*>(xy.data()), xy.size() * 8);
+    in.read(reinterpret_cast<char*>(oc.data()), oc.size() * 4);
+    in.read(reinterpret_cast<char*>(op.data()), op.size() * 4);
+    in.read(reinterpret_cast<char*>(cst.data()), cst.size() * 4);
+    BundleData bd;
+    bd.K = cv::Mat(3, 3, CV_64F);
+    bd.K.at<double>(0, 0) = k[0]; bd.K.at<double>(1, 1) = k[1]; bd.K.at<double>(0, 2) = k[2]; bd.K.at<double>(1, 2) = k[3];
+    bd.K.at<double>(2, 2) = 1.0;
+    const int id_off = 100;                                  // image ids need not be 0-based
+    for (int c = 0; c < hdr[0]; ++c) {
+        cv::Mat r(3, 1, CV_64F), t(3, 1, CV_64F);
+        for (int j = 0; j < 3; ++j) { r.at<double>(j, 0) = cams[6 * c + j]; t.at<double>(j, 0) = cams[6 * c + 3 + j]; }
+        bd.camera_poses[id_off + c] = BundleData::CameraPose(r, t);
+    }
+    for (int p = 0; p < hdr[1]; ++p) bd.landmarks[7 * p + 3].point3D = cv::Vec3d(pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]);
+    for (int i = 0; i < hdr[2]; ++i)
+        bd.landmarks[7 * op[i] + 3].measurements.push_back(BundleData::Measurement(id_off + oc[i], cv::Vec2d(xy[2 * i], xy[2 * i + 1])));
+    for (int32_t c : cst) bd.constant_camera_pose.insert(id_off + c);
+    const double before = bd.Debug();
+    CeresBundelOptimizer::Parameters params;
+    CeresBundelOptimizer opt(params);
+    const bool ok = opt.Optimize(bd);
+    const double after = bd.Debug();
+    for (int c = 0; c < hdr[0]; ++c)
+        for (int j = 0; j < 3; ++j) { cams[6 * c + j] = bd.camera_poses[id_off + c].rvec.at<double>(j, 0); cams[6 * c + 3 + j] = bd.camera_poses[id_off + c].tvec.at<double>(j, 0); }
+    for (int p = 0; p < hdr[1]; ++p)
+        for (int j = 0; j < 3; ++j) pts[3 * p + j] = bd.landmarks[7 * p + 3].point3D(j);
+    std::ofstream out(argv[3], std::ios::binary);
+    const double head[6] = {ok ? 1.0 : 0.0, before, after, opt.last_initial_cost(), opt.last_final_cost(), static_cast<double>(opt.last_iterations())};
+    out.write(reinterpret_cast<const char*>(head), sizeof head);
+    out.write(reinterpret_cast<const char*>(cams.data()), cams.size() * 8);
+    out.write(reinterpret_cast<const char*>(pts.data()), pts.size() * 8);
+    CeresBundelOptimizer::Parameters p2;
+    p2.refine_focal_length = true;
+    CeresBundelOptimizer opt2(p2);
+    if (opt2.Optimize(bd)) return 3;                         // unsupported variant must report failure
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) return 2;
+    const std::string mode = argv[1];
+    if (mode == "cpu" && argc >= 3) return test_cpu(argv[2]);
+    if (mode == "match" && argc >= 4) {
+        BruteFeatureMatcher matcher(argv[2], 100, std::atoi(argv[3]) != 0);
+        matcher.RunMatching();
+        return 0;
+    }
+    if (mode == "seq" && argc >= 3) {
+        SequentialFeatureMatcher matcher(argv[2]);
+        matcher.RunMatching();
+        return 0;
+    }
+    if (mode == "two" && argc >= 7) return run_two(argv);
+    if (mode == "ba" && argc >= 4) return run_ba(argv);
+    return 2;
+}

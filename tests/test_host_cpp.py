@@ -1,0 +1,195 @@
+"""The C++ classes that keep the reference's names (monocularsfm_b200/host), driven through build/host_test.
+CPU: Database format / pair ids / CrossCheck quirk.  GPU: FeatureUtils, Brute/SequentialFeatureMatcher on a database in the
+reference's schema (written here with Python's sqlite3), CeresBundelOptimizer::Optimize on a BundleData."""
+import os
+import sqlite3
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import ba_oracle as bo
+from oracle import match_oracle as mo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "build", "host_test")
+
+
+def _need_exe():
+    if not os.path.exists(EXE):
+        pytest.skip("build/host_test not built (make)")
+
+
+def test_host_cpu(tmp_path):
+    _need_exe()
+    db = str(tmp_path / "t.db")
+    out = subprocess.run([EXE, "cpu", db], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    # the file is a plain SQLite database in the reference's schema (Database.cpp:710-764)
+    con = sqlite3.connect(db)
+    names = {r[0] for r in con.execute("select name from sqlite_master where type='table'")}
+    assert {"images", "keypoints", "colors", "descriptors", "matches"} <= names
+    rows, cols, data = con.execute("select rows, cols, data from descriptors where image_id = 1").fetchone()
+    d = np.frombuffer(data, np.float32).reshape(rows, cols)
+    assert (rows, cols) == (3, 128) and d[2, 5] == 19.0
+    pid, r, c, blob = con.execute("select pair_id, rows, cols, data from matches").fetchone()
+    assert pid == 10002 and (r, c) == (2, 2)
+    assert np.frombuffer(blob, np.int32).reshape(2, 2).tolist() == [[7, 5], [1, 6]]     # stored with id1 < id2 orientation
+
+
+def _sift_like(rng, n):
+    x = np.abs(rng.standard_normal((n, 128)))
+    x = x / np.linalg.norm(x, axis=1, keepdims=True) * 512.0
+    return np.clip(np.rint(x), 0, 255).astype(np.uint8)
+
+
+def _make_db(path, rng, sizes):
+    """Reference-format database: image ids 0..N-1 (FeatureExtraction writes explicit ids), float32 descriptor blobs with
+    integral values (un-normalised SIFT), keypoints with distinct sizes."""
+    con = sqlite3.connect(path)
+    con.executescript("""
+        CREATE TABLE images(image_id INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, name TEXT NOT NULL UNIQUE);
+        CREATE TABLE keypoints(image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+        CREATE TABLE colors(image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+        CREATE TABLE descriptors(image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+        CREATE TABLE matches(pair_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+    """)
+    base = _sift_like(rng, max(sizes))
+    descs, scales = [], []
+    for i, n in enumerate(sizes):
+        d = _sift_like(rng, n)
+        m = int(0.4 * min(n, len(base)))
+        dst = rng.permutation(n)[:m]
+        src = rng.permutation(len(base))[:m]
+        d[dst] = np.clip(base[src].astype(np.int64) + rng.integers(-2, 3, (m, 128)), 0, 255).astype(np.uint8)
+        kp = np.zeros((n, 4), np.float32)
+        kp[:, :2] = rng.uniform(0, 1000, (n, 2))
+        kp[:, 2] = rng.permutation(n).astype(np.float32) + 1.0            # distinct scales
+        con.execute("insert into images(image_id, name) values(?, ?)", (i, f"img{i}.jpg"))
+        con.execute("insert into keypoints values(?,?,?,?)", (i, n, 4, kp.tobytes()))
+        con.execute("insert into descriptors values(?,?,?,?)", (i, n, 128, d.astype(np.float32).tobytes()))
+        descs.append(d)
+        scales.append(kp[:, 2])
+    con.commit()
+    con.close()
+    return descs, scales
+
+
+def _read_matches(path):
+    con = sqlite3.connect(path)
+    out = {}
+    for pid, r, c, blob in con.execute("select pair_id, rows, cols, data from matches"):
+        out[pid] = np.frombuffer(blob or b"", np.int32).reshape(r, 2)
+    con.close()
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preempt", [0, 1])
+def test_brute_feature_matcher_on_reference_database(tmp_path, preempt):
+    _need_exe()
+    rng = np.random.default_rng(21 + preempt)
+    db = str(tmp_path / "m.db")
+    sizes = [900, 700, 1100, 300]
+    descs, scales = _make_db(db, rng, sizes)
+    out = subprocess.run([EXE, "match", db, str(preempt)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr + out.stdout
+    got = _read_matches(db)
+    for i in range(len(sizes)):
+        for j in range(i):
+            pid = 10000 * j + i
+            keep = True
+            if preempt:
+                # FeatureMatching.cpp:148-179: 100 largest-scale descriptors each, cross matching, >= 4 matches
+                t1 = descs[i][np.argsort(-scales[i], kind="stable")[:100]]
+                t2 = descs[j][np.argsort(-scales[j], kind="stable")[:100]]
+                keep = len(mo.match_image_pair(t1, t2, 0.8, -1.0, True, True)[0]) >= 4
+            if not keep:
+                assert pid not in got
+                continue
+            # MatchImagePairs(i, j): query = image i, train = image j; max_distance 0.7 on the x512 scale
+            em, _ = mo.match_image_pair(descs[i], descs[j], 0.8, 0.7 * 512.0, True, True)
+            stored = em[:, ::-1] if i > j else em                             # swapped to id1 < id2 orientation on disk
+            np.testing.assert_array_equal(got[pid], stored, err_msg=f"pair {i}-{j}")
+    # resume: a second run finds every row and changes nothing
+    out = subprocess.run([EXE, "match", db, str(preempt)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "Existing" in out.stdout
+    again = _read_matches(db)
+    assert set(again) == set(got)
+
+
+@pytest.mark.gpu
+def test_sequential_feature_matcher(tmp_path):
+    _need_exe()
+    rng = np.random.default_rng(5)
+    db = str(tmp_path / "s.db")
+    sizes = [400, 500, 450, 300, 350]
+    descs, _ = _make_db(db, rng, sizes)
+    out = subprocess.run([EXE, "seq", db], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    got = _read_matches(db)
+    want = {10000 * j + i for i in range(1, 5) for j in range(max(0, i - 3), i)}          # overlap = 3
+    assert set(got) == want
+    em, _ = mo.match_image_pair(descs[4], descs[2], 0.8, 0.7 * 512.0, True, True)
+    np.testing.assert_array_equal(got[20004], em[:, ::-1])
+
+
+@pytest.mark.gpu
+def test_feature_utils_two_mats(tmp_path):
+    _need_exe()
+    rng = np.random.default_rng(9)
+    a, b = _sift_like(rng, 333), _sift_like(rng, 500)
+    b[rng.permutation(500)[:100]] = a[rng.permutation(333)[:100]]
+    (tmp_path / "a.u8").write_bytes(a.tobytes())
+    (tmp_path / "b.u8").write_bytes(b.tobytes())
+    out = subprocess.run([EXE, "two", str(tmp_path / "a.u8"), "333", str(tmp_path / "b.u8"), "500", str(tmp_path / "o.txt")],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = (tmp_path / "o.txt").read_text().split("\n")
+    n1 = int(lines[0])
+    m1 = np.array([l.split() for l in lines[1:1 + n1]], np.float64).reshape(-1, 3)
+    n2 = int(lines[1 + n1])
+    m2 = np.array([l.split() for l in lines[2 + n1:2 + n1 + n2]], np.float64).reshape(-1, 3)
+    e1, d1 = mo.compute_matches(a, b, 0.8)
+    e2, d2 = mo.compute_cross_matches(a, b, 0.8, True)
+    np.testing.assert_array_equal(m1[:, :2].astype(np.int32), e1)
+    np.testing.assert_allclose(m1[:, 2], d1, rtol=1e-7)
+    np.testing.assert_array_equal(m2[:, :2].astype(np.int32), e2)
+
+
+@pytest.mark.gpu
+def test_ceres_bundel_optimizer_dropin(tmp_path):
+    _need_exe()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ba_golden.npz"))
+    name = "ring16"
+    cams, pts = g[f"{name}/cams"], g[f"{name}/pts"]
+    cx, cy = 1080.0, 720.0
+    xy = g[f"{name}/obs_uv"] + [cx, cy]
+    oc, op = g[f"{name}/obs_cam"].astype(np.int32), g[f"{name}/obs_pt"].astype(np.int32)
+    const = np.nonzero(g[f"{name}/cam_const"])[0].astype(np.int32)
+    fin = tmp_path / "in.bin"
+    with open(fin, "wb") as f:
+        f.write(struct.pack("4i", len(cams), len(pts), len(oc), len(const)))
+        f.write(struct.pack("4d", float(g[f"{name}/fx"]), float(g[f"{name}/fy"]), cx, cy))
+        for arr in (cams, pts, xy):
+            f.write(np.ascontiguousarray(arr, np.float64).tobytes())
+        for arr in (oc, op, const):
+            f.write(arr.tobytes())
+    out = subprocess.run([EXE, "ba", str(fin), str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert "Bundle Adjustment statistics" in out.stdout and "Final RMSE" in out.stdout
+    raw = np.fromfile(tmp_path / "out.bin", np.float64)
+    ok, before, after, c0, c1, iters = raw[:6]
+    costs = g[f"{name}/lm_costs"]
+    assert ok == 1.0 and after < before
+    assert abs(c0 - costs[0]) <= 1e-9 * costs[0] and abs(c1 - costs[-1]) <= 1e-5 * costs[-1]
+    new_cams = raw[6:6 + cams.size].reshape(-1, 6)
+    new_pts = raw[6 + cams.size:].reshape(-1, 3)
+    np.testing.assert_array_equal(new_cams[const], cams[const])
+    r = bo.residuals_only(new_cams, new_pts, g[f"{name}/obs_uv"], oc, op, float(g[f"{name}/fx"]), float(g[f"{name}/fy"]))
+    assert abs(bo.cost_of(r) - c1) <= 1e-9 * c1
+    # BundleData::Debug() = mean over landmarks of the mean reprojection error (BundleData.cpp:9-37)
+    nrm = np.linalg.norm(r, axis=1)
+    per_pt = np.bincount(op, nrm) / np.bincount(op)
+    assert abs(per_pt.mean() - after) < 1e-9

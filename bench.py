@@ -204,6 +204,10 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.first = 0
+
+    def mark(self):
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -229,7 +233,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        use = self.lines[self.first:] or self.lines[-3:]
+        for ln in use:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -345,17 +350,18 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- device-resident throughput ("value")
     upload_resident()
     ctx.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # nvidia-smi needs a moment to come up: start before the warm-up steps
     for _ in range(args.warmup):
         total = step_resident()
     ctx.sync()
-    sampler = ClockSampler(local_rank)
+    sampler.mark()                       # only samples taken from here on (the timed region) are reported
     ctx.prof_enable(True)
     ctx.prof_reset()
     launches0 = ctx.launch_count
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)

@@ -1,8 +1,10 @@
 // M-path support kernels around the tensor kernel (match_k1.cu):
-//   desc_format_kernel     raw [n][128] u8  ->  swizzled resident layout + column constants
+//   desc_norm_key / desc_rank / desc_scatter / desc_groups
+//                          raw [n][128] u8  ->  resident sorted-space layout of match_types.cuh
 //   build_units_kernel     segment table    ->  unit table of one batch
-//   resolve_rows_kernel    K1 row results   ->  ratio test; rescans the winner's 32-column group when the
-//                                               runner-up could hide there; defers tie / sqrt-collapse rows
+//   resolve_rows_kernel    K1 row results   ->  ratio test; rescans the winner's 32-column group (best column +
+//                                               in-group runner-up) when the row can still pass; defers tie /
+//                                               sqrt-collapse rows
 //   exact_rows_kernel      exact CUDA-core scan in OpenCV's (sqrtf(d2), index) order for deferred rows
 //                          (and for every row in msfm_match_knn2_u8 mode 1)
 //   count/scan/write       CrossCheck (FeatureUtils.cpp:281-310) + FilterMatchesByDistance (:208-218) +
@@ -14,21 +16,103 @@
 
 namespace msfm {
 
-// ------------------------------------------------------------------------------------------------
-__global__ void desc_format_kernel(const uint8_t* __restrict__ raw, int n, int n_pad, uint8_t* __restrict__ sw,
-                                   int32_t* __restrict__ cj) {
-    const int warps_per_block = blockDim.x >> 5;
-    const int lane = threadIdx.x & 31;
-    for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n_pad; r += gridDim.x * warps_per_block) {
-        uint32_t w = 0;
-        if (r < n) w = reinterpret_cast<const uint32_t*>(raw + static_cast<size_t>(r) * 128)[lane];
-        int32_t s = __dp4a(w, w, 0u);                      // sum of the 4 squared bytes (unsigned)
+// ------------------------------------------------------------------------------------------------ upload formatting
+// sort key of a descriptor: (bucket, squared norm, original index); bucket = parity * 3 + norm / kBucketSpan
+__device__ __forceinline__ int bucket_of(int32_t nrm) { return (nrm & 1) * 3 + nrm / kBucketSpan; }
+
+// one warp per descriptor: squared norm and 64-bit sort key; bucket population counts
+__global__ void desc_norm_key_kernel(const uint8_t* __restrict__ raw, int n, int32_t* __restrict__ nrm_orig,
+                                     unsigned long long* __restrict__ keys, int32_t* __restrict__ bucket_cnt) {
+    const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < n; j += gridDim.x * wpb) {
+        const uint32_t w = reinterpret_cast<const uint32_t*>(raw + static_cast<size_t>(j) * 128)[lane];
+        int32_t s = static_cast<int32_t>(__dp4a(w, w, 0u));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            nrm_orig[j] = s;
+            const int b = bucket_of(s);
+            keys[j] = (static_cast<unsigned long long>(b) << 56) | (static_cast<unsigned long long>(s) << 24) |
+                      static_cast<unsigned long long>(j);
+            atomicAdd(&bucket_cnt[b], 1);
+        }
+    }
+}
+
+// rank of every key among all keys (O(n^2), tiled through shared memory; n is a few thousand) and from it the
+// sorted-space position: rank + dead columns inserted before the key's bucket
+__global__ void __launch_bounds__(256)
+desc_rank_kernel(const unsigned long long* __restrict__ keys, int n, const int32_t* __restrict__ bucket_cnt,
+                 int32_t* __restrict__ pos_of) {
+    __shared__ unsigned long long tile[1024];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long mine = j < n ? keys[j] : ~0ull;
+    int rank = 0;
+    for (int base = 0; base < n; base += 1024) {
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x) tile[k] = (base + k < n) ? keys[base + k] : ~0ull;
+        __syncthreads();
+        const int lim = min(1024, n - base);
+#pragma unroll 8
+        for (int k = 0; k < lim; ++k) rank += tile[k] < mine ? 1 : 0;
+        __syncthreads();
+    }
+    if (j >= n) return;
+    const int b = static_cast<int>(mine >> 56);
+    int pad = 0;
+    for (int k = 0; k < b; ++k) pad += (32 - (bucket_cnt[k] & 31)) & 31;
+    pos_of[j] = rank + pad;
+}
+
+// one warp per descriptor: write the swizzled row at its sorted position, its norm and original index
+__global__ void desc_scatter_kernel(const uint8_t* __restrict__ raw, int n, const int32_t* __restrict__ pos_of,
+                                    const int32_t* __restrict__ nrm_orig, uint8_t* __restrict__ sw,
+                                    int32_t* __restrict__ nrm, int32_t* __restrict__ perm) {
+    const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < n; j += gridDim.x * wpb) {
+        const int p = pos_of[j];
+        const uint32_t w = reinterpret_cast<const uint32_t*>(raw + static_cast<size_t>(j) * 128)[lane];
         const int chunk = lane >> 2;                          // 16-byte chunk of this lane's word
-        const int pos = ((chunk ^ (r & 7)) << 2) | (lane & 3);
-        reinterpret_cast<uint32_t*>(sw + static_cast<size_t>(r) * 128)[pos] = w;
-        if (lane == 0) cj[r] = (r < n) ? (s * 256 + (r & 255)) : (kPadKey | (r & 255));
+        const int slot = ((chunk ^ (p & 7)) << 2) | (lane & 3);
+        reinterpret_cast<uint32_t*>(sw + static_cast<size_t>(p) * 128)[slot] = w;
+        if (lane == 0) { nrm[p] = nrm_orig[j]; perm[p] = j; }
+    }
+}
+
+// one warp per 32-column group: C_g and the extension digits of every column
+__global__ void desc_groups_kernel(const int32_t* __restrict__ nrm, int n_pad, int32_t* __restrict__ cg,
+                                   uint8_t* __restrict__ ext) {
+    const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < n_pad / 32; g += gridDim.x * wpb) {
+        const int p = g * 32 + lane;
+        const int32_t v = nrm[p];
+        int32_t c = v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+        if (lane == 0) cg[g] = c >= 0 ? c : kDeadCg;
+        // digits of e = (C_g - ||d||^2) / 2 = b0 + 255 * (b1 + ... + b31); dead columns get e = 0
+        uint32_t e = (v >= 0) ? static_cast<uint32_t>(c - v) >> 1 : 0u;
+        uint32_t words[8];
+        uint32_t t = e / 255u;
+        const uint32_t b0 = e - t * 255u;
+#pragma unroll
+        for (int wi = 0; wi < 8; ++wi) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t digit;
+                if (wi == 0 && k == 0) digit = b0;
+                else { digit = t < 255u ? t : 255u; t -= digit; }
+                word |= digit << (8 * k);
+            }
+            words[wi] = word;
+        }
+        // column p = (4s+q)*256 + r  ->  bytes [32q, 32q+32) of row r of super-tile s (swizzled 16-byte chunks)
+        const int s = p >> 10, q = (p >> 8) & 3, r = p & 255;
+        uint8_t* rowp = ext + (static_cast<size_t>(s) * 256 + r) * 128;
+        uint4* c0 = reinterpret_cast<uint4*>(rowp + (((2 * q) ^ (r & 7)) << 4));
+        uint4* c1 = reinterpret_cast<uint4*>(rowp + (((2 * q + 1) ^ (r & 7)) << 4));
+        *c0 = make_uint4(words[0], words[1], words[2], words[3]);
+        *c1 = make_uint4(words[4], words[5], words[6], words[7]);
     }
 }
 
@@ -81,14 +165,14 @@ __device__ __forceinline__ bool dist_filter_ok(int32_t d1, double max_distance) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// One block of 128 threads per unit; thread r owns row r of the unit.
-// Outputs (global row index = unit*128 + r):
-//   m_j   train index of the accepted match or -1          m_d1  exact d2 of the best column (kIntInf = none)
+// One block of kUnitRows threads per unit; thread r owns sorted-space row r of the unit.
+// Final per-row outputs are indexed by the ORIGINAL query index: o = (unit - row_block)*kUnitRows + perm_q[row]
+//   m_j   original train index of the accepted match or -1     m_d1  exact d2 of the best column (kIntInf = none)
 //   m_d2  exact d2 of the runner-up when it was computed, else an upper bound (kIntInf = none)
-//   m_j0  [2g] best column regardless of the ratio test (knn2 API), [2g+1] runner-up column (exact path only) or -1
-__global__ void __launch_bounds__(128)
+//   m_j0  [2o] best column regardless of the ratio test (knn2 API), [2o+1] runner-up column (exact path only) or -1
+__global__ void __launch_bounds__(kUnitRows)
 resolve_rows_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ units, int num_units,
-                    const int32_t* __restrict__ res_j, const int32_t* __restrict__ res_d1,
+                    const int32_t* __restrict__ res_g, const int32_t* __restrict__ res_d1,
                     const int32_t* __restrict__ res_u, MatchOpts opt, int32_t* __restrict__ m_j,
                     int32_t* __restrict__ m_d1, int32_t* __restrict__ m_d2, int32_t* __restrict__ m_j0,
                     int32_t* __restrict__ exact_list, unsigned int* __restrict__ counters /*[0]=exact,[1]=rescans*/) {
@@ -99,33 +183,49 @@ resolve_rows_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__
     const ImgDev t = imgs[unit.t_slot];
     const int lane = threadIdx.x & 31;
     const int r = threadIdx.x;
-    const int qi = unit.row_block * 128 + r;
-    const size_t g = static_cast<size_t>(u) * 128 + r;
+    const int qp = unit.row_block * kUnitRows + r;           // sorted-space row of the query image
+    const size_t g = static_cast<size_t>(u) * kUnitRows + r; // K1 result slot
+    const int qorig = q.perm[qp];                            // -1 for dead rows
+    const bool valid = qorig >= 0;
+    const size_t o = static_cast<size_t>(u - unit.row_block) * kUnitRows + (valid ? qorig : 0);
 
-    int32_t j1 = -1, d1 = kIntInf, uu = kIntInf;
-    bool valid = qi < q.n;
-    if (valid) { j1 = res_j[g]; d1 = res_d1[g]; uu = res_u[g]; }
-    if (valid && (j1 < 0 || j1 >= t.n)) { j1 = -1; d1 = kIntInf; uu = kIntInf; }
+    int32_t g1 = -1, d1 = kIntInf, uu = kIntInf;
+    if (valid) { g1 = res_g[g]; d1 = res_d1[g]; uu = res_u[g]; }
+    const bool have = valid && g1 >= 0 && t.n >= 1;
     // rows that must be redone exactly: cross-group tie of the best distance, or float-sqrt collapse range
-    const bool need_exact = valid && j1 >= 0 && t.n >= 2 && (uu == d1 || d1 >= kSqrtExactLimit);
-    // the runner-up can only matter if the row passes against the upper bound uu (or the caller wants it exactly)
-    bool need_rescan = valid && j1 >= 0 && t.n >= 2 && !need_exact &&
-                       (opt.exact_second || uu == kIntInf || ratio_pass(d1, uu, opt.ratio));
+    const bool need_exact = have && t.n >= 2 && (uu == d1 || d1 >= kSqrtExactLimit);
+    // the best column / runner-up only matter if the row passes against the upper bound uu (or the caller wants them)
+    const bool need_rescan = have && !need_exact &&
+                             (opt.exact_second || t.n < 2 || uu == kIntInf || ratio_pass(d1, uu, opt.ratio));
 
     int32_t d2 = uu;
-    // ---- warp-cooperative rescan of the winner's 32-column group
+    int32_t j1 = -1;
+    // ---- warp-cooperative rescan of the winner's 32-column group: best column (lowest original index among equal
+    //      distances, OpenCV's order) and the in-group runner-up distance
     unsigned todo = __ballot_sync(0xffffffffu, need_rescan);
     while (todo) {
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
-        const int sj1 = __shfl_sync(0xffffffffu, j1, src);
-        const int sqi = __shfl_sync(0xffffffffu, qi, src);
-        const int col = (sj1 & ~31) + lane;
+        const int sg1 = __shfl_sync(0xffffffffu, g1, src);
+        const int sqp = __shfl_sync(0xffffffffu, qp, src);
+        const int col = sg1 * 32 + lane;                     // sorted-space column (< t.n_pad)
+        const int corig = t.perm[col];
         int32_t dd = kIntInf;
-        if (col < t.n && col != sj1) dd = sqdist_rows(q.sw, sqi, t.sw, col);
-        // only the runner-up's VALUE matters for the ratio test
-        const int32_t best = __reduce_min_sync(0xffffffffu, dd);
-        if (lane == src) d2 = min(d2, best);
+        if (corig >= 0) dd = sqdist_rows(q.sw, sqp, t.sw, col);
+        // (dd, corig) lexicographic minimum over the warp
+        int32_t bd = dd, bj = corig >= 0 ? corig : kIntInf;
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+            const int32_t od = __shfl_xor_sync(0xffffffffu, bd, ofs);
+            const int32_t oj = __shfl_xor_sync(0xffffffffu, bj, ofs);
+            if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+        }
+        // runner-up inside the group: minimum over the lanes that are not the winner
+        const int32_t second = __reduce_min_sync(0xffffffffu, (corig >= 0 && corig != bj) ? dd : kIntInf);
+        if (lane == src) {
+            j1 = bj;
+            d2 = min(d2, second);
+        }
     }
     const unsigned nres = __popc(__ballot_sync(0xffffffffu, need_rescan));
     if (lane == 0 && nres) atomicAdd(&counters[1], nres);
@@ -134,19 +234,19 @@ resolve_rows_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__
         const unsigned slot = atomicAdd(&counters[0], 1u);
         exact_list[slot] = static_cast<int32_t>(g);
     }
-    if (valid) {
+    if (valid && !need_exact) {
         int32_t mj = -1;
-        if (!need_exact && j1 >= 0 && t.n >= 2 && d2 != kIntInf && ratio_pass(d1, d2, opt.ratio)) mj = j1;
-        m_j[g] = mj;
-        m_d1[g] = d1;
-        m_d2[g] = (t.n >= 2) ? d2 : kIntInf;
-        m_j0[2 * g] = j1;
-        m_j0[2 * g + 1] = -1;      // the tensor path tracks the runner-up's distance, not its column
+        if (j1 >= 0 && t.n >= 2 && d2 != kIntInf && ratio_pass(d1, d2, opt.ratio)) mj = j1;
+        m_j[o] = mj;
+        m_d1[o] = have ? d1 : kIntInf;
+        m_d2[o] = (have && t.n >= 2) ? d2 : kIntInf;
+        m_j0[2 * o] = j1;
+        m_j0[2 * o + 1] = -1;      // the tensor path tracks the runner-up's distance, not its column
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Exact scan: one warp per listed row, all train columns, OpenCV order = (sqrtf(d2), column) lexicographic.
+// Exact scan: one warp per listed row, all train columns, OpenCV order = (sqrtf(d2), ORIGINAL column) lexicographic.
 struct Top2 {
     int32_t d0, j0, d1, j1;
 };
@@ -175,32 +275,37 @@ exact_rows_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
     const int wpb = blockDim.x >> 5;
     for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < nrows; w += gridDim.x * wpb) {
         const size_t g = row_list ? static_cast<size_t>(row_list[w]) : static_cast<size_t>(w);
-        const int u = static_cast<int>(g >> 7);
+        const int u = static_cast<int>(g / kUnitRows);
         const UnitDev unit = units[u];
         const ImgDev q = imgs[unit.q_slot];
         const ImgDev t = imgs[unit.t_slot];
-        const int qi = unit.row_block * 128 + static_cast<int>(g & 127);
-        if (qi >= q.n) continue;
+        const int qp = unit.row_block * kUnitRows + static_cast<int>(g % kUnitRows);
+        const int qorig = q.perm[qp];
+        if (qorig < 0) continue;
+        const size_t o = static_cast<size_t>(u - unit.row_block) * kUnitRows + qorig;
         Top2 s{kIntInf, -1, kIntInf, -1};
-        for (int col = lane; col < t.n; col += 32) top2_insert(s, sqdist_rows(q.sw, qi, t.sw, col), col);
+        for (int col = lane; col < t.n_pad; col += 32) {
+            const int corig = t.perm[col];
+            if (corig >= 0) top2_insert(s, sqdist_rows(q.sw, qp, t.sw, col), corig);
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
             Top2 other;
-            other.d0 = __shfl_xor_sync(0xffffffffu, s.d0, o);
-            other.j0 = __shfl_xor_sync(0xffffffffu, s.j0, o);
-            other.d1 = __shfl_xor_sync(0xffffffffu, s.d1, o);
-            other.j1 = __shfl_xor_sync(0xffffffffu, s.j1, o);
+            other.d0 = __shfl_xor_sync(0xffffffffu, s.d0, ofs);
+            other.j0 = __shfl_xor_sync(0xffffffffu, s.j0, ofs);
+            other.d1 = __shfl_xor_sync(0xffffffffu, s.d1, ofs);
+            other.j1 = __shfl_xor_sync(0xffffffffu, s.j1, ofs);
             top2_insert(s, other.d0, other.j0);
             top2_insert(s, other.d1, other.j1);
         }
         if (lane == 0) {
             int32_t mj = -1;
             if (s.j0 >= 0 && s.j1 >= 0 && ratio_pass(s.d0, s.d1, opt.ratio)) mj = s.j0;
-            m_j[g] = mj;
-            m_d1[g] = s.j0 >= 0 ? s.d0 : kIntInf;
-            m_d2[g] = s.j1 >= 0 ? s.d1 : kIntInf;
-            m_j0[2 * g] = s.j0;
-            m_j0[2 * g + 1] = s.j1;
+            m_j[o] = mj;
+            m_d1[o] = s.j0 >= 0 ? s.d0 : kIntInf;
+            m_d2[o] = s.j1 >= 0 ? s.d1 : kIntInf;
+            m_j0[2 * o] = s.j0;
+            m_j0[2 * o + 1] = s.j1;
         }
     }
 }
@@ -216,8 +321,8 @@ __device__ __forceinline__ PairView pair_view(const ImgDev* imgs, const SegDev* 
     PairView v;
     v.n1 = imgs[s12.q_slot].n;
     v.n2 = imgs[s12.t_slot].n;
-    v.base12 = static_cast<size_t>(s12.unit_base) * 128;
-    v.base21 = cross ? static_cast<size_t>(segs[2 * p + 1].unit_base) * 128 : 0;
+    v.base12 = static_cast<size_t>(s12.unit_base) * kUnitRows;
+    v.base21 = cross ? static_cast<size_t>(segs[2 * p + 1].unit_base) * kUnitRows : 0;
     return v;
 }
 __device__ __forceinline__ bool keep_match(const PairView& v, int i, const int32_t* m_j, const int32_t* m_d1,
@@ -343,12 +448,29 @@ write_matches_kernel(const ImgDev* __restrict__ imgs, const SegDev* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-cudaError_t launch_desc_format(const uint8_t* raw, int n, int n_pad, uint8_t* sw, int32_t* cj, cudaStream_t st) {
+// raw [n][128] (device) -> resident layout.  block = one allocation laid out by img_layout() (msfm_api.cu);
+// scratch: keys [n] u64 | nrm_orig [n] | pos_of [n] | bucket_cnt [8]
+cudaError_t launch_desc_format(const uint8_t* raw, int n, int n_pad, uint8_t* sw, uint8_t* ext, int32_t* cg,
+                               int32_t* nrm, int32_t* perm, unsigned long long* keys, int32_t* nrm_orig,
+                               int32_t* pos_of, int32_t* bucket_cnt, cudaStream_t st) {
     if (n_pad <= 0) return cudaSuccess;
-    const int wpb = 8;
-    int grid = (n_pad + wpb - 1) / wpb;
-    if (grid > 148 * 8) grid = 148 * 8;
-    desc_format_kernel<<<grid, wpb * 32, 0, st>>>(raw, n, n_pad, sw, cj);
+    const size_t ext_bytes = static_cast<size_t>((n_pad + 1023) / 1024) * 256 * 128;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(sw, 0, static_cast<size_t>(n_pad) * 128, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(ext, 0, ext_bytes, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(nrm, 0xFF, static_cast<size_t>(n_pad) * 4, st)) != cudaSuccess) return e;     // -1: dead
+    if ((e = cudaMemsetAsync(perm, 0xFF, static_cast<size_t>(n_pad) * 4, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(bucket_cnt, 0, 8 * 4, st)) != cudaSuccess) return e;
+    if (n > 0) {
+        const int wpb = 8;
+        int grid = (n + wpb - 1) / wpb;
+        if (grid > 148 * 8) grid = 148 * 8;
+        desc_norm_key_kernel<<<grid, wpb * 32, 0, st>>>(raw, n, nrm_orig, keys, bucket_cnt);
+        desc_rank_kernel<<<(n + 255) / 256, 256, 0, st>>>(keys, n, bucket_cnt, pos_of);
+        desc_scatter_kernel<<<grid, wpb * 32, 0, st>>>(raw, n, pos_of, nrm_orig, sw, nrm, perm);
+    }
+    int ggrid = (n_pad / 32 + 7) / 8;
+    desc_groups_kernel<<<ggrid, 256, 0, st>>>(nrm, n_pad, cg, ext);
     return cudaGetLastError();
 }
 cudaError_t launch_build_units(const SegDev* segs, int nseg, int num_units, UnitDev* units, cudaStream_t st) {
@@ -356,12 +478,12 @@ cudaError_t launch_build_units(const SegDev* segs, int nseg, int num_units, Unit
     build_units_kernel<<<(num_units + 255) / 256, 256, 0, st>>>(segs, nseg, num_units, units);
     return cudaGetLastError();
 }
-cudaError_t launch_resolve_rows(const ImgDev* imgs, const UnitDev* units, int num_units, const int32_t* res_j,
+cudaError_t launch_resolve_rows(const ImgDev* imgs, const UnitDev* units, int num_units, const int32_t* res_g,
                                 const int32_t* res_d1, const int32_t* res_u, MatchOpts opt, int32_t* m_j, int32_t* m_d1,
                                 int32_t* m_d2, int32_t* m_j0, int32_t* exact_list, unsigned int* counters,
                                 cudaStream_t st) {
     if (num_units <= 0) return cudaSuccess;
-    resolve_rows_kernel<<<num_units, 128, 0, st>>>(imgs, units, num_units, res_j, res_d1, res_u, opt, m_j, m_d1, m_d2,
+    resolve_rows_kernel<<<num_units, kUnitRows, 0, st>>>(imgs, units, num_units, res_g, res_d1, res_u, opt, m_j, m_d1, m_d2,
                                                    m_j0, exact_list, counters);
     return cudaGetLastError();
 }

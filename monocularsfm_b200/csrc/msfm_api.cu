@@ -9,7 +9,8 @@
 
 namespace msfm {
 cudaError_t launch_match_tile_kernel(const ImgDev*, const UnitDev*, int, int32_t*, int32_t*, int32_t*, int, cudaStream_t);
-cudaError_t launch_desc_format(const uint8_t*, int, int, uint8_t*, int32_t*, cudaStream_t);
+cudaError_t launch_desc_format(const uint8_t*, int, int, uint8_t*, uint8_t*, int32_t*, int32_t*, int32_t*, unsigned long long*,
+                               int32_t*, int32_t*, int32_t*, cudaStream_t);
 cudaError_t launch_build_units(const SegDev*, int, int, UnitDev*, cudaStream_t);
 cudaError_t launch_resolve_rows(const ImgDev*, const UnitDev*, int, const int32_t*, const int32_t*, const int32_t*,
                                 MatchOpts, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, unsigned int*, cudaStream_t);
@@ -81,7 +82,7 @@ void msfm_destroy(msfm_ctx* c) {
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (auto& im : c->imgs)
         if (im.block) cudaFree(im.block);
-    GrowBuf* bufs[] = {&c->d_imgs, &c->d_raw, &c->h_stage, &c->d_segs, &c->d_units, &c->d_res, &c->d_m, &c->d_exact,
+    GrowBuf* bufs[] = {&c->d_imgs, &c->d_raw, &c->d_fmt, &c->h_stage, &c->d_segs, &c->d_units, &c->d_res, &c->d_m, &c->d_exact,
                        &c->d_counts, &c->d_misc, &c->d_out_offsets, &c->d_out_matches, &c->d_out_dist};
     for (GrowBuf* b : bufs) b->release();
     cudaStreamDestroy(c->stream);
@@ -121,10 +122,28 @@ int msfm_prof_read(msfm_ctx* c, double ms[MSFM_PROF_NCAT], int64_t n[MSFM_PROF_N
 }
 
 // ------------------------------------------------------------------------------------------------ uploads
+// One allocation per image: sw | ext | cg | nrm | perm (match_types.cuh), every part 256-B aligned.
+struct ImgLayout {
+    size_t off_ext, off_cg, off_nrm, off_perm, total;
+};
+static ImgLayout img_layout(int32_t n_pad) {
+    ImgLayout L;
+    const size_t sw = static_cast<size_t>(n_pad) * 128;
+    const size_t ext = static_cast<size_t>((n_pad + 1023) / 1024) * 256 * 128;
+    const size_t cg = (static_cast<size_t>(n_pad) / 32 * 4 + 255) / 256 * 256;
+    L.off_ext = sw;
+    L.off_cg = L.off_ext + ext;
+    L.off_nrm = L.off_cg + cg;
+    L.off_perm = L.off_nrm + static_cast<size_t>(n_pad) * 4;
+    L.total = L.off_perm + static_cast<size_t>(n_pad) * 4;
+    return L;
+}
+static int32_t padded_count(int32_t n) { return n > 0 ? (n + kMaxPadPerImage + 255) / 256 * 256 : 0; }
+
 static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int32_t n, bool src_on_device) {
     if (!c || n < 0 || (n > 0 && !src)) return c ? c->fail(MSFM_E_INVALID, "msfm_desc_upload: bad arguments") : MSFM_E_INVALID;
     MSFM_CUDA(c, cudaSetDevice(c->device));
-    const int32_t n_pad = (n + 255) / 256 * 256;
+    const int32_t n_pad = padded_count(n);
     int slot;
     auto it = c->slot_of.find(image_id);
     if (it != c->slot_of.end()) {
@@ -145,7 +164,8 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
         MSFM_CUDA(c, cudaFree(im.block));
         im.block = nullptr;
     }
-    if (!im.block && n_pad > 0) MSFM_CUDA(c, cudaMalloc(&im.block, static_cast<size_t>(n_pad) * (128 + 4)));
+    const ImgLayout L = img_layout(n_pad);
+    if (!im.block && n_pad > 0) MSFM_CUDA(c, cudaMalloc(&im.block, L.total));
     im.n = n;
     im.n_pad = n_pad;
     im.live = true;
@@ -158,11 +178,18 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
         raw = c->d_raw.as<uint8_t>();
     }
     uint8_t* sw = static_cast<uint8_t*>(im.block);
-    int32_t* cj = reinterpret_cast<int32_t*>(sw + static_cast<size_t>(n_pad) * 128);
+    // formatting scratch: keys [n] u64 | nrm_orig [n] | pos_of [n] | bucket counts [8]
+    MSFM_CUDA(c, c->d_fmt.reserve(static_cast<size_t>(n) * 16 + 64));
+    unsigned long long* keys = c->d_fmt.as<unsigned long long>();
+    int32_t* nrm_orig = reinterpret_cast<int32_t*>(keys + n);
+    int32_t* pos_of = nrm_orig + n;
+    int32_t* bucket_cnt = pos_of + n;
     c->prof_begin(MSFM_PROF_DESC_FORMAT);
-    MSFM_CUDA(c, launch_desc_format(raw, n, n_pad, sw, cj, c->stream));
+    MSFM_CUDA(c, launch_desc_format(raw, n, n_pad, sw, sw + L.off_ext, reinterpret_cast<int32_t*>(sw + L.off_cg),
+                                    reinterpret_cast<int32_t*>(sw + L.off_nrm), reinterpret_cast<int32_t*>(sw + L.off_perm),
+                                    keys, nrm_orig, pos_of, bucket_cnt, c->stream));
     c->prof_end();
-    c->launches += 1;
+    c->launches += 4;
     return MSFM_OK;
 }
 
@@ -214,8 +241,12 @@ static int sync_img_table(msfm_ctx* c) {
     for (size_t i = 0; i < c->imgs.size(); ++i) {
         const ImgHost& im = c->imgs[i];
         uint8_t* sw = static_cast<uint8_t*>(im.block);
+        const ImgLayout L = img_layout(im.n_pad);
         tab[i].sw = sw;
-        tab[i].cj = sw ? reinterpret_cast<const int32_t*>(sw + static_cast<size_t>(im.n_pad) * 128) : nullptr;
+        tab[i].ext = sw ? sw + L.off_ext : nullptr;
+        tab[i].cg = sw ? reinterpret_cast<const int32_t*>(sw + L.off_cg) : nullptr;
+        tab[i].nrm = sw ? reinterpret_cast<const int32_t*>(sw + L.off_nrm) : nullptr;
+        tab[i].perm = sw ? reinterpret_cast<const int32_t*>(sw + L.off_perm) : nullptr;
         tab[i].n = im.n;
         tab[i].n_pad = im.n_pad;
     }
@@ -261,7 +292,7 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
             if (i1 == c->slot_of.end() || i2 == c->slot_of.end())
                 return c->fail(MSFM_E_NOT_FOUND, "pair %d: image %d or %d not resident", p, pairs[2 * p], pairs[2 * p + 1]);
             const int s1 = i1->second, s2 = i2->second;
-            const int u12 = (c->imgs[s1].n + 127) / 128, u21 = opt.cross_check ? (c->imgs[s2].n + 127) / 128 : 0;
+            const int u12 = c->imgs[s1].n_pad / kUnitRows, u21 = opt.cross_check ? c->imgs[s2].n_pad / kUnitRows : 0;
             if (cur.npairs > 0 && cur.nunits + u12 + u21 > kMaxUnitsPerBatch) {
                 batches.push_back(cur);
                 cur = Batch{p, 0, 0};
@@ -284,7 +315,7 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
 
     int max_units = 1, max_pairs = 1;
     for (const Batch& b : batches) { max_units = std::max(max_units, b.nunits); max_pairs = std::max(max_pairs, b.npairs); }
-    const size_t rows = static_cast<size_t>(max_units) * 128;
+    const size_t rows = static_cast<size_t>(max_units) * kUnitRows;
     const size_t nb = std::max<size_t>(1, batches.size());
     MSFM_CUDA(c, c->d_segs.reserve(std::max<size_t>(1, segs.size()) * sizeof(SegDev)));
     MSFM_CUDA(c, c->d_units.reserve(static_cast<size_t>(max_units) * sizeof(UnitDev)));
@@ -333,7 +364,7 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
             c->launches += (b.nunits > 0 ? 4 : 1);
         } else {
             c->prof_begin(MSFM_PROF_EXACT);
-            MSFM_CUDA(c, launch_exact_rows(d_imgs, units, nullptr, nullptr, b.nunits * 128, opt, m_j, m_d1, m_d2, m_j0,
+            MSFM_CUDA(c, launch_exact_rows(d_imgs, units, nullptr, nullptr, b.nunits * kUnitRows, opt, m_j, m_d1, m_d2, m_j0,
                                            c->num_sms, c->stream));
             c->prof_end();
             c->launches += 2;
@@ -345,7 +376,7 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
         c->prof_end();
         c->launches += 3;
         total_units += b.nunits;
-        total_rows += static_cast<int64_t>(b.nunits) * 128;
+        total_rows += static_cast<int64_t>(b.nunits) * kUnitRows;
         if (dump && bi == 0 && dump->n > 0) {
             MSFM_CUDA(c, cudaMemcpyAsync(dump->j0, m_j0, static_cast<size_t>(dump->n) * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
             MSFM_CUDA(c, cudaMemcpyAsync(dump->d1, m_d1, static_cast<size_t>(dump->n) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

@@ -62,10 +62,16 @@ def _make_db(path, rng, sizes):
         m = int(0.4 * min(n, len(base)))
         dst = rng.permutation(n)[:m]
         src = rng.permutation(len(base))[:m]
+        src[:60] = np.arange(60)                                             # every image shares base rows 0..59 ...
         d[dst] = np.clip(base[src].astype(np.int64) + rng.integers(-2, 3, (m, 128)), 0, 255).astype(np.uint8)
         kp = np.zeros((n, 4), np.float32)
         kp[:, :2] = rng.uniform(0, 1000, (n, 2))
         kp[:, 2] = rng.permutation(n).astype(np.float32) + 1.0            # distinct scales
+        if i != len(sizes) - 1:
+            kp[dst[:60], 2] += 10000.0                                       # ... among its largest-scale features,
+        else:
+            kp[dst, 2] *= 1e-4                                               # except the last image, whose planted rows
+                                                                             # are its smallest: preemption drops its pairs
         con.execute("insert into images(image_id, name) values(?, ?)", (i, f"img{i}.jpg"))
         con.execute("insert into keypoints values(?,?,?,?)", (i, n, 4, kp.tobytes()))
         con.execute("insert into descriptors values(?,?,?,?)", (i, n, 128, d.astype(np.float32).tobytes()))
@@ -96,6 +102,7 @@ def test_brute_feature_matcher_on_reference_database(tmp_path, preempt):
     out = subprocess.run([EXE, "match", db, str(preempt)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr + out.stdout
     got = _read_matches(db)
+    n_kept = 0
     for i in range(len(sizes)):
         for j in range(i):
             pid = 10000 * j + i
@@ -108,10 +115,12 @@ def test_brute_feature_matcher_on_reference_database(tmp_path, preempt):
             if not keep:
                 assert pid not in got
                 continue
+            n_kept += 1
             # MatchImagePairs(i, j): query = image i, train = image j; max_distance 0.7 on the x512 scale
             em, _ = mo.match_image_pair(descs[i], descs[j], 0.8, 0.7 * 512.0, True, True)
             stored = em[:, ::-1] if i > j else em                             # swapped to id1 < id2 orientation on disk
             np.testing.assert_array_equal(got[pid], stored, err_msg=f"pair {i}-{j}")
+    assert n_kept == (3 if preempt else 6), n_kept        # preemption keeps the pairs among images 0..2 only
     # resume: a second run finds every row and changes nothing
     out = subprocess.run([EXE, "match", db, str(preempt)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "Existing" in out.stdout

@@ -136,6 +136,73 @@ __global__ void k_mma(int iters, long long* cyc) {
     if (warp == 0) ptx::tmem_dealloc<512>(tptr);
 }
 
+// ---- 4. issue patterns of the real K1 loop, tensor pipe only (no epilogue): per "tile" 2 sub-tiles x (4 data + 1 ext) MMAs
+//        of shape 128 x N x 32, A from shared memory (TS=0) or tensor memory (TS=1); OVH=1 adds what the issuing thread
+//        does per tile in the real kernel: 3 waits on already-completed mbarriers + 3 commits.
+template <int N, int TS, int OVH>
+__global__ void k_mma_pat(int iters, long long* cyc) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t tptr;
+    __shared__ uint64_t bar, done_bar[3];
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (2 * 16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = i * 2654435761u;
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(&bar, 1);
+        for (int i = 0; i < 3; ++i) ptx::mbar_init(&done_bar[i], 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 0) ptx::tmem_alloc<512>(&tptr);
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before(); __syncthreads(); ptx::tc_fence_after();
+    if (threadIdx.x == 0) for (int i = 0; i < 3; ++i) ptx::mbar_arrive(&done_bar[i]);   // phase 0 complete
+    __syncthreads();
+    if (threadIdx.x == 32) {
+        const uint64_t ad = ptx::make_smem_desc_sw128(ptx::smem_u32(smem));
+        const uint64_t bd = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + 32768));
+        constexpr uint32_t idesc = ptx::make_idesc_u8(128, N);
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            // OVH bit 0: 3 waits, bit 1: fence, bit 2: 3 commits, bit 3: 1 wait, bit 4: 1 commit
+            if (OVH & 1) { ptx::mbar_wait(&done_bar[0], 0); ptx::mbar_wait(&done_bar[1], 0); ptx::mbar_wait(&done_bar[2], 0); }
+            if (OVH & 8) { ptx::mbar_wait(&done_bar[0], 0); }
+            if (OVH & 2) { ptx::tc_fence_after(); }
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+                const uint32_t d = tptr + (i & 1) * 2 * N * (N <= 96 ? 1 : 0) + sub * N * (N <= 128 ? 1 : 0);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    if (TS) ptx::mma_i8_ts(d, tptr + 448 + (k & 3) * 8, bd + 2 * (k & 3), idesc, k > 0);
+                    else ptx::mma_i8_ss(d, ad + sub * 1024 + 2 * (k & 3), bd + 2 * (k & 3), idesc, k > 0);
+                }
+            }
+            if (OVH & 4) { ptx::mma_commit(&bar); ptx::mma_commit(&bar); ptx::mma_commit(&bar); }
+            if (OVH & 16) { ptx::mma_commit(&bar); }
+        }
+        if (!(OVH & 20)) ptx::mma_commit(&bar);
+        // drain: wait for the last commit phase (phase parity unknown under OVH: just spin on time)
+        long long t1 = clock64();
+        while (clock64() - t1 < 20000) {}
+        cyc[blockIdx.x] = t1 - t0;
+    }
+    ptx::tc_fence_before(); __syncthreads();
+    if (warp == 0) ptx::tmem_dealloc<512>(tptr);
+}
+
+template <int N, int TS, int OVH>
+static int run_pat(int G, long long* d_cyc, long long* h, const char* name) {
+    if (cudaFuncSetAttribute(k_mma_pat<N, TS, OVH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000) != cudaSuccess) return 1;
+    const int iters = 2048;
+    for (int rep = 0; rep < 2; ++rep) k_mma_pat<N, TS, OVH><<<G, 64, 70000>>>(iters, d_cyc);
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("pattern %s failed: %s\n", name, cudaGetErrorString(cudaGetLastError())); return 1; }
+    cudaMemcpy(h, d_cyc, G * 8, cudaMemcpyDeviceToHost);
+    double s = 0; for (int i = 0; i < G; ++i) s += h[i];
+    const double c = s / G / iters;
+    printf("mma pattern %-34s: %.1f issue-cyc per tile (2 x 5 MMAs 128x%dx32; tensor floor %d cyc)\n", name, c, N, 10 * N / 2);
+    return 0;
+}
+
 static double avg(long long* h, int n) { double s = 0; for (int i = 0; i < n; ++i) s += h[i]; return s / n; }
 
 int main() {
@@ -181,6 +248,18 @@ int main() {
     k_mma<<<1, 64, 60000>>>(2048, d_cyc);
     CK(cudaDeviceSynchronize()); CK(cudaMemcpy(h, d_cyc, 8, cudaMemcpyDeviceToHost));
     printf("mma i8 128x256x128 (4 x K32): %.1f cyc per tile (1 SM)\n", (double)h[0] / 2048);
+    run_pat<128, 1, 0>(G, d_cyc, h, "TS N=128 plain");
+    run_pat<128, 1, 1>(G, d_cyc, h, "TS N=128 +3 waits");
+    run_pat<128, 1, 2>(G, d_cyc, h, "TS N=128 +fence");
+    run_pat<128, 1, 4>(G, d_cyc, h, "TS N=128 +3 commits");
+    run_pat<128, 1, 8>(G, d_cyc, h, "TS N=128 +1 wait");
+    run_pat<128, 1, 16>(G, d_cyc, h, "TS N=128 +1 commit");
+    run_pat<128, 1, 26>(G, d_cyc, h, "TS N=128 +1 wait+fence+1 commit");
+    run_pat<128, 0, 26>(G, d_cyc, h, "SS N=128 +1 wait+fence+1 commit");
+    run_pat<128, 1, 7>(G, d_cyc, h, "TS N=128 +3w+f+3c");
+    run_pat<64, 1, 26>(G, d_cyc, h, "TS N=64 +1 wait+fence+1 commit");
+    run_pat<96, 1, 26>(G, d_cyc, h, "TS N=96 +1 wait+fence+1 commit");
+    run_pat<256, 0, 26>(G, d_cyc, h, "SS N=256 +1 wait+fence+1 commit");
     printf("MICROBENCH DONE\n");
     return 0;
 }

@@ -330,7 +330,10 @@ def run_ours(args, rank, world, local_rank):
         uid = [ctx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(world, rank, uid[0])
-    descs = make_descriptors_torch(n_img, n, 1234 + rank, dev)           # [n_img, n, 128] u8, resident in HBM
+    if args.cpu_data:      # profiling runs: keep torch's data-generation kernels out of the ncu launch list
+        descs = torch.from_numpy(make_descriptors_numpy(n_img, n, 1234 + rank)).to(dev)
+    else:
+        descs = make_descriptors_torch(n_img, n, 1234 + rank, dev)       # [n_img, n, 128] u8, resident in HBM
     torch.cuda.synchronize()
     pairs = all_pairs(n_img)
     P = len(pairs)
@@ -485,6 +488,7 @@ def main():
     ap.add_argument("--ndesc", type=int, default=8192)
     ap.add_argument("--cpu-pairs", type=int, default=6, help="image pairs in the CPU-baseline sample")
     ap.add_argument("--no-ba", action="store_true", help="skip the secondary BA measurement")
+    ap.add_argument("--cpu-data", action="store_true", help="generate the synthetic descriptors with numpy (ncu launch lists)")
     ap.add_argument("--ba-cams", type=int, default=128)
     ap.add_argument("--ba-pts", type=int, default=50000)
     ap.add_argument("--ba-track", type=float, default=10.0)

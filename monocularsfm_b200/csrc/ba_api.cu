@@ -20,6 +20,9 @@ using ba::Problem;
 cudaError_t ba_launch_cam_prep(const double*, int, CamPre*, cudaStream_t);
 cudaError_t ba_launch_evaluate(const Problem&, double*, float*, double*, int, cudaStream_t);
 cudaError_t ba_launch_linearize(const Problem&, double, double*, int, cudaStream_t);
+cudaError_t ba_launch_count_tuples(const Problem&, int32_t*, int, cudaStream_t);
+cudaError_t ba_launch_scan_tuples(const int32_t*, long long, int32_t*, int32_t*, cudaStream_t);
+cudaError_t ba_launch_fill_tuples(const Problem&, int32_t*, int2*, int, cudaStream_t);
 cudaError_t ba_launch_damp(double*, int, double, cudaStream_t);
 cudaError_t ba_launch_backsub(const Problem&, double, const double*, double*, double*, int, cudaStream_t);
 cudaError_t ba_launch_update_cams(const double*, const int32_t*, int, const double*, double*, cudaStream_t);
@@ -74,6 +77,11 @@ struct msfm_ba {
     double* sys = nullptr;        // S | rhs | gc | udiag | scalars[8]
     double* xsol = nullptr;       // solver right-hand side / solution [n6]
     double* small = nullptr;      // [8] scratch scalars (backsub out[3], new cost, gpmax bits)
+    // gather structures + per-linearisation intermediates (ba_types.cuh)
+    int32_t *cam_obs_start = nullptr, *cam_obs_list = nullptr, *blk_start = nullptr;
+    int2* blk_tuples = nullptr;
+    float* obs_J = nullptr;
+    double *obs_r = nullptr, *pt_Vinv = nullptr, *pt_gp = nullptr;
     double* work = nullptr;       // cusolver workspace
     int work_len = 0;
     int* dev_info = nullptr;
@@ -88,6 +96,8 @@ struct msfm_ba {
         P.pre = pre[which]; P.pts = pts[which]; P.obs_uv = obs_uv; P.obs_cam = obs_cam; P.obs_pt = obs_pt;
         P.pt_start = pt_start; P.cam_free = cam_free;
         P.gpmax_bits = reinterpret_cast<unsigned long long*>(small + 4);
+        P.cam_obs_start = cam_obs_start; P.cam_obs_list = cam_obs_list; P.blk_start = blk_start; P.blk_tuples = blk_tuples;
+        P.obs_J = obs_J; P.obs_r = obs_r; P.pt_Vinv = pt_Vinv; P.pt_gp = pt_gp;
         return P;
     }
 };
@@ -133,7 +143,8 @@ void msfm_ba_destroy(msfm_ba* b) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void* ptrs[] = {b->cams[0], b->cams[1], b->pts[0], b->pts[1], b->pre[0], b->pre[1], b->obs_uv, b->obs_cam, b->obs_pt,
-                    b->pt_start, b->cam_free, b->sys, b->xsol, b->small, b->work, b->dev_info};
+                    b->pt_start, b->cam_free, b->sys, b->xsol, b->small, b->work, b->dev_info, b->cam_obs_start,
+                    b->cam_obs_list, b->blk_start, b->blk_tuples, b->obs_J, b->obs_r, b->pt_Vinv, b->pt_gp};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -161,6 +172,27 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     int nf = 0;
     for (int i = 0; i < pr->n_cams; ++i)
         if (!pr->cam_const[i]) cam_free[i] = nf++;
+    // a landmark holds at most one measurement per image (tracks in Map.cpp are keyed by image): the gather lists rely on it
+    for (int p = 0; p < pr->n_pts; ++p)
+        for (int a = pt_start[p]; a < pt_start[size_t(p) + 1]; ++a)
+            for (int q = a + 1; q < pt_start[size_t(p) + 1]; ++q)
+                if (pr->obs_cam[a] == pr->obs_cam[q])
+                    return c->fail(MSFM_E_INVALID, "msfm_ba_create: point %d is observed twice by camera %d", p, pr->obs_cam[a]);
+    // CSR of the observations of every free camera (counting sort)
+    std::vector<int32_t> cam_obs_start(size_t(nf) + 1, 0), cam_obs_list;
+    for (int i = 0; i < pr->n_obs; ++i) {
+        const int f = cam_free[pr->obs_cam[i]];
+        if (f >= 0) cam_obs_start[size_t(f) + 1] += 1;
+    }
+    for (int f = 0; f < nf; ++f) cam_obs_start[size_t(f) + 1] += cam_obs_start[f];
+    cam_obs_list.resize(size_t(cam_obs_start[nf]));
+    {
+        std::vector<int32_t> cur(cam_obs_start.begin(), cam_obs_start.end() - 1);
+        for (int i = 0; i < pr->n_obs; ++i) {
+            const int f = cam_free[pr->obs_cam[i]];
+            if (f >= 0) cam_obs_list[size_t(cur[f]++)] = i;
+        }
+    }
     msfm_ba* b = new (std::nothrow) msfm_ba();
     if (!b) return c->fail(MSFM_E_CUDA, "out of host memory");
     b->ctx = c;
@@ -189,6 +221,13 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     BA_ALLOC(b->xsol, std::max<size_t>(1, n6) * sizeof(double));
     BA_ALLOC(b->small, 8 * sizeof(double));
     BA_ALLOC(b->dev_info, sizeof(int));
+    BA_ALLOC(b->cam_obs_start, cam_obs_start.size() * sizeof(int32_t));
+    BA_ALLOC(b->cam_obs_list, cam_obs_list.size() * sizeof(int32_t));
+    BA_ALLOC(b->blk_start, (size_t(nf) * nf + 1) * sizeof(int32_t));
+    BA_ALLOC(b->obs_J, size_t(pr->n_obs) * 18 * sizeof(float));
+    BA_ALLOC(b->obs_r, size_t(pr->n_obs) * 2 * sizeof(double));
+    BA_ALLOC(b->pt_Vinv, size_t(pr->n_pts) * 6 * sizeof(double));
+    BA_ALLOC(b->pt_gp, size_t(pr->n_pts) * 3 * sizeof(double));
 #undef BA_ALLOC
     auto H2D = [&](void* dst, const void* src, size_t bytes) {
         return bytes ? cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
@@ -201,7 +240,30 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     if (e == cudaSuccess) e = H2D(b->obs_pt, pr->obs_pt, size_t(pr->n_obs) * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->pt_start, pt_start.data(), pt_start.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->cam_free, cam_free.data(), cam_free.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = H2D(b->cam_obs_start, cam_obs_start.data(), cam_obs_start.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = H2D(b->cam_obs_list, cam_obs_list.data(), cam_obs_list.size() * sizeof(int32_t));
     if (e != cudaSuccess) return fail_free(c->cuda_fail(e, "msfm_ba_create H2D"));
+    // co-observation tuples of every camera pair, built on the device: count -> scan -> fill
+    {
+        const long long nblk = static_cast<long long>(nf) * nf;
+        int32_t *counts = nullptr, *cursor = nullptr;
+        const size_t cbytes = std::max<size_t>(16, size_t(nblk) * sizeof(int32_t));
+        if ((e = cudaMalloc(&counts, cbytes)) == cudaSuccess) e = cudaMalloc(&cursor, cbytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(counts, 0, cbytes, c->stream);
+        const Problem P0 = b->view(0);
+        if (e == cudaSuccess) e = ba_launch_count_tuples(P0, counts, c->num_sms, c->stream);
+        if (e == cudaSuccess) e = ba_launch_scan_tuples(counts, nblk, b->blk_start, cursor, c->stream);
+        int32_t total = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&total, b->blk_start + nblk, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->blk_tuples), std::max<size_t>(16, size_t(total) * sizeof(int2)));
+        if (e == cudaSuccess) e = ba_launch_fill_tuples(b->view(0), cursor, b->blk_tuples, c->num_sms, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (counts) cudaFree(counts);
+        if (cursor) cudaFree(cursor);
+        c->launches += 3;
+        if (e != cudaSuccess) return fail_free(c->cuda_fail(e, "msfm_ba_create: building the gather lists"));
+    }
     *out = b;
     return MSFM_OK;
 }
@@ -272,7 +334,7 @@ static int linearize(msfm_ba* b, int which, double inv_radius) {
     c->prof_begin(MSFM_PROF_BA_SCHUR);
     BA_CUDA(ba_launch_linearize(b->view(which), inv_radius, b->sys, c->num_sms, c->stream));
     c->prof_end();
-    c->launches += 1;
+    c->launches += 3;
     if (c->comm) {
         int rc = msfm_comm_allreduce_f64(c, b->sys, static_cast<int64_t>(b->sys_len()), 0);
         if (rc) return rc;

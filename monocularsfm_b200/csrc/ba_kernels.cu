@@ -5,8 +5,13 @@
 //     Jacobian — here ANALYTIC, equal to the autodiff of Ceres' AngleAxisRotatePoint in both of its branches;
 //   * per point: V = sum Jp^T Jp (+ Marquardt damping), g_p; per camera: U, g_c;
 //   * Schur elimination of the points onto the free cameras: S = U + D_c - sum W V^-1 W^T, rhs = -(g_c - W V^-1 g_p)
-//     (Ceres SchurEliminator for DENSE_SCHUR / SPARSE_SCHUR, :264-273), written with fp64 atomics into one dense
-//     buffer [S | rhs | g_c | diag U | cost] that a single NCCL all-reduce sums across GPUs;
+//     (Ceres SchurEliminator for DENSE_SCHUR / SPARSE_SCHUR, :264-273) into one dense buffer
+//     [S | rhs | g_c | diag U | cost] that a single NCCL all-reduce sums across GPUs.  The reduction is a GATHER, not
+//     a scatter: the sparsity pattern is fixed across LM iterations, so per-camera observation lists and per
+//     camera-pair co-observation lists are built once per problem; each diagonal block is then owned by one CTA and
+//     each off-diagonal block by one warp, which sum their contributions in registers and store — no floating-point
+//     atomics (the first version scattered 1.1e8 fp64 atomics per linearisation and was bound by L2 atomic
+//     throughput: profiles/r01_k2_ncu_raw.csv);
 //   * back-substitution of the points, candidate-step evaluation.
 // Observations are grouped by point; one warp owns one point, one lane one observation (chunks of 32 for longer
 // tracks).  Geometry (projection, residual, V^-1) is evaluated in fp64, the 6x3 / 6x6 block products of the Schur
@@ -212,19 +217,17 @@ __device__ __forceinline__ void point_pass1(const Problem& P, int p, int beg, in
 }
 
 // ------------------------------------------------------------------------------------------------ linearize + Schur
-// sys layout (fp64): S [n6*n6] | rhs [n6] | gc [n6] | udiag [n6] | scalars[8] (0: cost, 1: max |g_p| as bits)
+// sys layout (fp64): S [n6*n6] | rhs [n6] | gc [n6] | udiag [n6] | scalars[8] (0: cost)
+
+// Pass P — one warp per point: residuals + Jacobians of its observations (stored), damped V^-1 and g_p (stored),
+// cost and max |g_p|.
 __global__ void __launch_bounds__(256)
-linearize_schur_kernel(Problem P, double inv_radius, double* __restrict__ sys) {
+point_pass_kernel(Problem P, double inv_radius, double* __restrict__ sys) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const size_t n6 = static_cast<size_t>(P.n_free) * 6;
-    double* S = sys;
-    double* rhs = S + n6 * n6;
-    double* gcv = rhs + n6;
-    double* udiag = gcv + n6;
-    double* scal = udiag + n6;
+    double* scal = sys + n6 * n6 + 3 * n6;
     double cost_local = 0.0, gpmax_local = 0.0;
-
     for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < P.n_pts; p += gridDim.x * wpb) {
         const int beg = P.pt_start[p], end = P.pt_start[p + 1];
         if (beg == end) continue;
@@ -233,69 +236,21 @@ linearize_schur_kernel(Problem P, double inv_radius, double* __restrict__ sys) {
         LaneObs A;
         point_pass1(P, p, beg, end, lane, X, inv_radius, Vinv, gp, A);
         gpmax_local = fmax(gpmax_local, fmax(fabs(gp[0]), fmax(fabs(gp[1]), fabs(gp[2]))));
-        const float vi0 = (float)Vinv[0], vi1 = (float)Vinv[1], vi2 = (float)Vinv[2], vi3 = (float)Vinv[3],
-                    vi4 = (float)Vinv[4], vi5 = (float)Vinv[5];
-        for (int abase = beg; abase < end; abase += 32) {
-            if (abase != beg) load_lane(P, abase + lane, abase + lane < end, X, A);
+        if (lane < 6) P.pt_Vinv[6 * static_cast<size_t>(p) + lane] = Vinv[lane];
+        if (lane < 3) P.pt_gp[3 * static_cast<size_t>(p) + lane] = gp[lane];
+        for (int base = beg; base < end; base += 32) {
+            if (base != beg) load_lane(P, base + lane, base + lane < end, X, A);
+            if (!A.valid) continue;
             cost_local += 0.5 * (A.r[0] * A.r[0] + A.r[1] * A.r[1]);
-            // W = Jc^T Jp (6x3), Y = W V^-1 (6x3)
-            float W[18], Y[18];
+            const size_t o = static_cast<size_t>(base + lane);
+            float2* J2 = reinterpret_cast<float2*>(P.obs_J + o * 18);          // 72-byte rows are 8-byte aligned
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
+            for (int k = 0; k < 6; ++k) J2[k] = make_float2(A.Jc[2 * k], A.Jc[2 * k + 1]);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) W[3 * i + k] = A.Jc[i] * A.Jp[k] + A.Jc[6 + i] * A.Jp[3 + k];
-                Y[3 * i + 0] = W[3 * i] * vi0 + W[3 * i + 1] * vi1 + W[3 * i + 2] * vi2;
-                Y[3 * i + 1] = W[3 * i] * vi1 + W[3 * i + 1] * vi3 + W[3 * i + 2] * vi4;
-                Y[3 * i + 2] = W[3 * i] * vi2 + W[3 * i + 1] * vi4 + W[3 * i + 2] * vi5;
-            }
-            if (A.valid && A.f >= 0) {
-                double* Sd = S + (static_cast<size_t>(A.f) * 6) * n6 + static_cast<size_t>(A.f) * 6;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    const double jr = static_cast<double>(A.Jc[i]) * A.r[0] + static_cast<double>(A.Jc[6 + i]) * A.r[1];
-                    const double yg = Y[3 * i] * gp[0] + Y[3 * i + 1] * gp[1] + Y[3 * i + 2] * gp[2];
-                    atomicAdd(&rhs[A.f * 6 + i], yg - jr);
-                    atomicAdd(&gcv[A.f * 6 + i], jr);
-                    atomicAdd(&udiag[A.f * 6 + i], static_cast<double>(A.Jc[i] * A.Jc[i] + A.Jc[6 + i] * A.Jc[6 + i]));
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        const float u = A.Jc[i] * A.Jc[j] + A.Jc[6 + i] * A.Jc[6 + j];
-                        const float yw = Y[3 * i] * W[3 * j] + Y[3 * i + 1] * W[3 * j + 1] + Y[3 * i + 2] * W[3 * j + 2];
-                        atomicAdd(&Sd[i * n6 + j], static_cast<double>(u - yw));
-                    }
-                }
-            }
-            // off-diagonal blocks: every other observation b of the same point
-            for (int bbase = beg; bbase < end; bbase += 32) {
-                LaneObs B;
-                if (bbase == abase) B = A; else load_lane(P, bbase + lane, bbase + lane < end, X, B);
-                float Wb[18];
-#pragma unroll
-                for (int i = 0; i < 6; ++i)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) Wb[3 * i + k] = B.Jc[i] * B.Jp[k] + B.Jc[6 + i] * B.Jp[3 + k];
-                const int nb = min(32, end - bbase);
-                for (int j = 0; j < nb; ++j) {
-                    const int fb = __shfl_sync(0xffffffffu, B.f, j);
-                    float wj[18];
-#pragma unroll
-                    for (int k = 0; k < 18; ++k) wj[k] = __shfl_sync(0xffffffffu, Wb[k], j);
-                    const bool same_obs = (bbase == abase) && (j == lane);
-                    if (!A.valid || A.f < 0 || fb < 0 || same_obs) continue;
-                    if (!(A.f < fb || A.f == fb)) continue;       // upper block triangle (+ same-camera pairs on the diagonal)
-                    double* Sb = S + (static_cast<size_t>(A.f) * 6) * n6 + static_cast<size_t>(fb) * 6;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i)
-#pragma unroll
-                        for (int jj = 0; jj < 6; ++jj) {
-                            const float yw = Y[3 * i] * wj[3 * jj] + Y[3 * i + 1] * wj[3 * jj + 1] + Y[3 * i + 2] * wj[3 * jj + 2];
-                            atomicAdd(&Sb[i * n6 + jj], static_cast<double>(-yw));
-                        }
-                }
-            }
+            for (int k = 0; k < 3; ++k) J2[6 + k] = make_float2(A.Jp[2 * k], A.Jp[2 * k + 1]);
+            reinterpret_cast<double2*>(P.obs_r)[o] = make_double2(A.r[0], A.r[1]);
         }
     }
-    // block-level reduction of the scalars
     __shared__ double sh_c[8], sh_g[8];
     cost_local = warp_sum(cost_local);
 #pragma unroll
@@ -305,10 +260,185 @@ linearize_schur_kernel(Problem P, double inv_radius, double* __restrict__ sys) {
     if (threadIdx.x == 0) {
         double c = 0.0, g = 0.0;
         for (int k = 0; k < wpb; ++k) { c += sh_c[k]; g = fmax(g, sh_g[k]); }
-        atomicAdd(&scal[0], c);
+        atomicAdd(&scal[0], c);          // one fp64 atomic per CTA (cost only)
         // max of non-negative doubles == max of their bit patterns
         atomicMax(reinterpret_cast<unsigned long long*>(P.gpmax_bits), static_cast<unsigned long long>(__double_as_longlong(g)));
     }
+}
+
+__device__ __forceinline__ void load_obs_J(const float* __restrict__ obs_J, int o, float Jc[12], float Jp[6]) {
+    const float2* J2 = reinterpret_cast<const float2*>(obs_J + static_cast<size_t>(o) * 18);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const float2 v = __ldg(J2 + k); Jc[2 * k] = v.x; Jc[2 * k + 1] = v.y; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const float2 v = __ldg(J2 + 6 + k); Jp[2 * k] = v.x; Jp[2 * k + 1] = v.y; }
+}
+// W = Jc^T Jp (6x3), Y = W V^-1 (6x3) with the symmetric V^-1 = (v0 v1 v2 / v1 v3 v4 / v2 v4 v5)
+__device__ __forceinline__ void make_WY(const float Jc[12], const float Jp[6], const float vi[6], float W[18], float Y[18]) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) W[3 * i + k] = Jc[i] * Jp[k] + Jc[6 + i] * Jp[3 + k];
+        Y[3 * i + 0] = W[3 * i] * vi[0] + W[3 * i + 1] * vi[1] + W[3 * i + 2] * vi[2];
+        Y[3 * i + 1] = W[3 * i] * vi[1] + W[3 * i + 1] * vi[3] + W[3 * i + 2] * vi[4];
+        Y[3 * i + 2] = W[3 * i] * vi[2] + W[3 * i + 1] * vi[4] + W[3 * i + 2] * vi[5];
+    }
+}
+
+// Pass C — one CTA per free camera: diagonal block U_c - sum Y W^T, rhs_c, g_c, diag U_c over the camera's observations.
+__global__ void __launch_bounds__(256)
+camera_diag_kernel(Problem P, double* __restrict__ sys) {
+    const int f = blockIdx.x;
+    if (f >= P.n_free) return;
+    const size_t n6 = static_cast<size_t>(P.n_free) * 6;
+    double acc[54];                      // 36 block | 6 rhs | 6 gc | 6 udiag
+#pragma unroll
+    for (int k = 0; k < 54; ++k) acc[k] = 0.0;
+    const int beg = P.cam_obs_start[f], end = P.cam_obs_start[f + 1];
+    for (int idx = beg + threadIdx.x; idx < end; idx += blockDim.x) {
+        const int o = __ldg(P.cam_obs_list + idx);
+        const int p = __ldg(P.obs_pt + o);
+        float Jc[12], Jp[6], vi[6], W[18], Y[18];
+        load_obs_J(P.obs_J, o, Jc, Jp);
+        double gp[3];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) vi[k] = static_cast<float>(__ldg(P.pt_Vinv + 6 * static_cast<size_t>(p) + k));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gp[k] = __ldg(P.pt_gp + 3 * static_cast<size_t>(p) + k);
+        const double2 r = __ldg(reinterpret_cast<const double2*>(P.obs_r) + o);
+        make_WY(Jc, Jp, vi, W, Y);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const double jr = static_cast<double>(Jc[i]) * r.x + static_cast<double>(Jc[6 + i]) * r.y;
+            acc[36 + i] += Y[3 * i] * gp[0] + Y[3 * i + 1] * gp[1] + Y[3 * i + 2] * gp[2] - jr;
+            acc[42 + i] += jr;
+            acc[48 + i] += static_cast<double>(Jc[i] * Jc[i] + Jc[6 + i] * Jc[6 + i]);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const float u = Jc[i] * Jc[j] + Jc[6 + i] * Jc[6 + j];
+                const float yw = Y[3 * i] * W[3 * j] + Y[3 * i + 1] * W[3 * j + 1] + Y[3 * i + 2] * W[3 * j + 2];
+                acc[6 * i + j] += static_cast<double>(u - yw);
+            }
+        }
+    }
+    __shared__ double sh[8][54];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 54; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) sh[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 54) {
+        double v = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) v += sh[w][threadIdx.x];
+        const int k = threadIdx.x;
+        double* S = sys;
+        double* rhs = S + n6 * n6;
+        if (k < 36) S[(static_cast<size_t>(f) * 6 + k / 6) * n6 + static_cast<size_t>(f) * 6 + k % 6] = v;
+        else if (k < 42) rhs[f * 6 + (k - 36)] = v;
+        else if (k < 48) rhs[n6 + f * 6 + (k - 42)] = v;           // gc
+        else rhs[2 * n6 + f * 6 + (k - 48)] = v;                   // udiag
+    }
+}
+
+// Pass B — one warp per non-empty camera-pair block (fa < fb): - sum over co-observing points of Y_a W_b^T.
+__global__ void __launch_bounds__(256)
+pair_block_kernel(Problem P, double* __restrict__ sys) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const size_t n6 = static_cast<size_t>(P.n_free) * 6;
+    const long long nblk = static_cast<long long>(P.n_free) * P.n_free;
+    for (long long b = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); b < nblk;
+         b += static_cast<long long>(gridDim.x) * wpb) {
+        const int beg = __ldg(P.blk_start + b), end = __ldg(P.blk_start + b + 1);
+        if (beg == end) continue;
+        float acc[36];
+#pragma unroll
+        for (int k = 0; k < 36; ++k) acc[k] = 0.f;
+        for (int idx = beg + lane; idx < end; idx += 32) {
+            const int2 t = __ldg(P.blk_tuples + idx);
+            const int p = __ldg(P.obs_pt + t.x);
+            float Jca[12], Jpa[6], Jcb[12], Jpb[6], vi[6], W[18], Y[18];
+            load_obs_J(P.obs_J, t.x, Jca, Jpa);
+            load_obs_J(P.obs_J, t.y, Jcb, Jpb);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) vi[k] = static_cast<float>(__ldg(P.pt_Vinv + 6 * static_cast<size_t>(p) + k));
+            make_WY(Jca, Jpa, vi, W, Y);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const float w0 = Jcb[j] * Jpb[0] + Jcb[6 + j] * Jpb[3];
+                const float w1 = Jcb[j] * Jpb[1] + Jcb[6 + j] * Jpb[4];
+                const float w2 = Jcb[j] * Jpb[2] + Jcb[6 + j] * Jpb[5];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) acc[6 * i + j] -= Y[3 * i] * w0 + Y[3 * i + 1] * w1 + Y[3 * i + 2] * w2;
+            }
+        }
+        const int fa = static_cast<int>(b / P.n_free), fb = static_cast<int>(b % P.n_free);
+        double* Sb = sys + (static_cast<size_t>(fa) * 6) * n6 + static_cast<size_t>(fb) * 6;
+#pragma unroll
+        for (int k = 0; k < 36; ++k) {
+            float v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) Sb[(k / 6) * n6 + (k % 6)] = static_cast<double>(v);
+        }
+    }
+}
+
+// ---- structure building (once per problem)
+// count / fill the co-observation tuples of every camera pair; mode 0 counts, mode 1 fills using cursors
+__global__ void pair_tuples_kernel(Problem P, int mode, int32_t* __restrict__ blk_count_or_cursor, int2* __restrict__ tuples_out) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n_pts; p += gridDim.x * blockDim.x) {
+        const int beg = P.pt_start[p], end = P.pt_start[p + 1];
+        for (int a = beg; a < end; ++a) {
+            const int fa = P.cam_free[P.obs_cam[a]];
+            if (fa < 0) continue;
+            for (int b = beg; b < end; ++b) {
+                if (b == a) continue;
+                const int fb = P.cam_free[P.obs_cam[b]];
+                if (fb < 0 || !(fa < fb)) continue;          // upper block triangle; same-camera pairs are not expected
+                const long long blk = static_cast<long long>(fa) * P.n_free + fb;
+                if (mode == 0) atomicAdd(&blk_count_or_cursor[blk], 1);
+                else {
+                    const int slot = atomicAdd(&blk_count_or_cursor[blk], 1);
+                    tuples_out[slot] = make_int2(a, b);
+                }
+            }
+        }
+    }
+}
+// single-block exclusive scan of int32 counts (n up to a few million) into out[0..n]; also copies the starts into cursor[]
+__global__ void __launch_bounds__(1024) scan_i32_kernel(const int32_t* __restrict__ counts, long long n, int32_t* __restrict__ out,
+                                                        int32_t* __restrict__ cursor) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = 0; base < n; base += blockDim.x) {
+        const long long i = base + threadIdx.x;
+        const int v = (i < n) ? counts[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int ws = warp_sums[lane];
+            int wincl = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, wincl, o); if (lane >= o) wincl += y; }
+            warp_sums[lane] = wincl - ws;
+        }
+        __syncthreads();
+        const int excl = carry + warp_sums[warp] + incl - v;
+        if (i < n) { out[i] = excl; cursor[i] = excl; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry;
 }
 
 // S_ii += max(udiag_i, 1e-6) / radius  (after the all-reduce), and mirror nothing: the solver reads one triangle.
@@ -428,7 +558,29 @@ cudaError_t ba_launch_linearize(const Problem& P, double inv_radius, double* sys
     if (P.n_pts <= 0) return cudaSuccess;
     int grid = (P.n_pts + 7) / 8;
     if (grid > num_sms * 8) grid = num_sms * 8;
-    linearize_schur_kernel<<<grid, 256, 0, st>>>(P, inv_radius, sys);
+    point_pass_kernel<<<grid, 256, 0, st>>>(P, inv_radius, sys);
+    if (P.n_free > 0) {
+        camera_diag_kernel<<<P.n_free, 256, 0, st>>>(P, sys);
+        const long long nblk = static_cast<long long>(P.n_free) * P.n_free;
+        long long g2 = (nblk + 7) / 8;
+        if (g2 > num_sms * 16) g2 = num_sms * 16;
+        pair_block_kernel<<<static_cast<int>(g2), 256, 0, st>>>(P, sys);
+    }
+    return cudaGetLastError();
+}
+// structure lists: counts -> starts (+cursor) -> tuples.  blk_start has n_free^2 + 1 entries.
+cudaError_t ba_launch_count_tuples(const Problem& P, int32_t* counts, int num_sms, cudaStream_t st) {
+    if (P.n_pts <= 0 || P.n_free <= 0) return cudaSuccess;
+    pair_tuples_kernel<<<num_sms * 4, 256, 0, st>>>(P, 0, counts, nullptr);
+    return cudaGetLastError();
+}
+cudaError_t ba_launch_scan_tuples(const int32_t* counts, long long n, int32_t* starts, int32_t* cursor, cudaStream_t st) {
+    scan_i32_kernel<<<1, 1024, 0, st>>>(counts, n, starts, cursor);
+    return cudaGetLastError();
+}
+cudaError_t ba_launch_fill_tuples(const Problem& P, int32_t* cursor, int2* tuples, int num_sms, cudaStream_t st) {
+    if (P.n_pts <= 0 || P.n_free <= 0) return cudaSuccess;
+    pair_tuples_kernel<<<num_sms * 4, 256, 0, st>>>(P, 1, cursor, tuples);
     return cudaGetLastError();
 }
 cudaError_t ba_launch_damp(double* sys, int n6, double inv_radius, cudaStream_t st) {

@@ -27,6 +27,16 @@ struct Problem {
     const int32_t* pt_start;    // [n_pts+1] CSR over observations
     const int32_t* cam_free;    // [n_cams] index among the free cameras or -1 (constant pose)
     unsigned long long* gpmax_bits;   // max |g_p| as the bit pattern of a non-negative double
+    // ---- gather structures (built once per problem: the sparsity pattern does not change between LM iterations)
+    const int32_t* cam_obs_start;   // [n_free+1] CSR: observations of every free camera
+    const int32_t* cam_obs_list;    // [#observations of free cameras]
+    const int32_t* blk_start;       // [n_free*n_free+1] CSR over camera-pair blocks (fa < fb): co-observing tuples
+    const int2* blk_tuples;         // (obs_a, obs_b) with cam_free[obs_cam[obs_a]] = fa < fb = cam_free[obs_cam[obs_b]]
+    // ---- per-linearisation intermediates
+    float* obs_J;                   // [n_obs][18]  Jc (2x6) | Jp (2x3), fp32
+    double* obs_r;                  // [n_obs][2]
+    double* pt_Vinv;                // [n_pts][6]   inverse of the damped point block (symmetric)
+    double* pt_gp;                  // [n_pts][3]
 };
 
 }  // namespace ba

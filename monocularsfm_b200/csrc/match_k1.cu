@@ -67,6 +67,9 @@ constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;               // slack for man
 static_assert(OFF_B % 1024 == 0 && OFF_E % 1024 == 0 && OFF_AEXT % 1024 == 0, "swizzle-128B tiles need 1 KiB alignment");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
+// occupied sorted positions of an image (0 for an empty image, which has no device block)
+__device__ __forceinline__ int img_used(const ImgDev& im) { return im.used ? __ldg(im.used) : 0; }
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ units, int num_units,
                   int32_t* __restrict__ res_g, int32_t* __restrict__ res_d1, int32_t* __restrict__ res_u) {
@@ -132,16 +135,18 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
         // ===================================================================== producer
         if (lane == 0) {
             uint32_t it = 0, un = 0, et = 0;
-            for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++un) {
+            for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
                 const UnitDev unit = units[u];
                 const ImgDev q = imgs[unit.q_slot];
                 const ImgDev t = imgs[unit.t_slot];
-                const uint32_t ab = un & 1;
-                ptx::mbar_wait(&a_empty[ab], ((un >> 1) & 1) ^ 1);
+                if (unit.row_block * BM >= img_used(q)) continue;      // all-dead query rows: every role skips the unit
+                const uint32_t cu = un++;                              // index among the units this CTA really processes
+                const uint32_t ab = cu & 1;
+                ptx::mbar_wait(&a_empty[ab], ((cu >> 1) & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(&a_full[ab], A_BYTES);
                 ptx::bulk_g2s(smA + ab * A_BYTES, q.sw + static_cast<size_t>(unit.row_block) * A_BYTES, A_BYTES,
                               &a_full[ab]);
-                const int ntiles = t.n_pad / BN;
+                const int ntiles = (img_used(t) + BN - 1) / BN;          // tiles beyond the occupied columns are skipped
                 for (int tile = 0; tile < ntiles; ++tile, ++it) {
                     if ((tile & 3) == 0) {
                         const uint32_t es = et % NE;
@@ -165,18 +170,21 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
             constexpr uint32_t idesc = ptx::make_idesc_u8(BM, BN);
             const uint64_t aext_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smAext));
             uint32_t it = 0, un = 0, et = 0;
-            for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++un) {
+            for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
                 const UnitDev unit = units[u];
                 const ImgDev t = imgs[unit.t_slot];
-                const uint32_t ab = un & 1;
-                const int ntiles = t.n_pad / BN;
+                if (unit.row_block * BM >= img_used(imgs[unit.q_slot])) continue;
+                const uint32_t cu = un++;
+                const uint32_t ab = cu & 1;
+                const int tcols = img_used(t);
+                const int ntiles = (tcols + BN - 1) / BN;
                 bool have_a = false, have_e = false;
                 uint64_t a_desc0 = 0;
                 for (int tile = 0; tile < ntiles; ++tile, ++it) {
                     const uint32_t es = et % NE;
                     if (it % NUM_ISSUERS == me) {
                         if (!have_a) {
-                            ptx::mbar_wait(&a_full[ab], (un >> 1) & 1);
+                            ptx::mbar_wait(&a_full[ab], (cu >> 1) & 1);
                             a_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smA + ab * A_BYTES));
                             have_a = true;
                         }
@@ -194,13 +202,16 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
                         const uint64_t b_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smB + s * B_BYTES));
                         const uint64_t e_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smE + es * E_BYTES));
                         const uint32_t d_tmem = tmem_base + acc * BN;
+                        // the last tile of an image may hold fewer than 256 occupied columns (a multiple of 32): narrower N
+                        const int ncols = min(BN, tcols - tile * BN);
+                        const uint32_t idesc_t = ncols == BN ? idesc : ptx::make_idesc_u8(BM, static_cast<uint32_t>(ncols));
 #pragma unroll
                         for (int k = 0; k < KBYTES / UMMA_KB; ++k) {
                             // advancing K by 32 bytes inside the 128-B swizzle atom = +2 in the (addr >> 4) field
-                            ptx::mma_i8_ss(d_tmem, a_desc0 + 2 * k, b_desc0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+                            ptx::mma_i8_ss(d_tmem, a_desc0 + 2 * k, b_desc0 + 2 * k, idesc_t, k > 0 ? 1u : 0u);
                         }
                         // + e_j : the tile's 32 extension bytes sit at K offset 32*(tile%4) of the super-tile rows
-                        ptx::mma_i8_ss(d_tmem, aext_desc, e_desc0 + 2 * (tile & 3), idesc, 1u);
+                        ptx::mma_i8_ss(d_tmem, aext_desc, e_desc0 + 2 * (tile & 3), idesc_t, 1u);
                         ptx::mma_commit(&b_empty[s]);
                         ptx::mma_commit(&t_full[acc]);
                     }
@@ -219,11 +230,14 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;             // query row inside the unit
         uint32_t it = 0, un = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++un) {
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
             const UnitDev unit = units[u];
             const ImgDev q = imgs[unit.q_slot];
             const ImgDev t = imgs[unit.t_slot];
-            const int ntiles = t.n_pad / BN;
+            if (unit.row_block * BM >= img_used(q)) continue;
+            const uint32_t cu = un++;
+            const int tcols = img_used(t);
+            const int ntiles = (tcols + BN - 1) / BN;
             int32_t k1 = kIntInf, k2 = kIntInf, g1 = 0;
             for (int tile = 0; tile < ntiles; ++tile, ++it) {
                 const uint32_t acc = it & 1;
@@ -232,6 +246,8 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
                 ptx::mbar_wait(&t_full[acc], aph);
                 ptx::tc_fence_after();
                 const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + wg * 128;
+                // occupied 32-column groups of this warpgroup's half (4 except in the narrow last tile of an image)
+                const int nch = min(4, max(0, (min(BN, tcols - tile * BN) - wg * 128) >> 5));
                 uint32_t va[32], vb[32];
                 ptx::tmem_ld_32x32(taddr0, va);
                 ptx::tmem_ld_wait();
@@ -257,9 +273,11 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
                     const int32_t cgc = (c == 0) ? cgv.x : (c == 1) ? cgv.y : (c == 2) ? cgv.z : cgv.w;
                     const int32_t key = cgc - 2 * m;      // = min over the group of (||d_j||^2 - 2 q.d_j)
                     // insert the group minimum into the running (best, best-of-other-groups)
-                    k2 = min(k2, max(k1, key));
-                    if (key < k1) g1 = tile * 8 + wg * 4 + c;
-                    k1 = min(k1, key);
+                    if (c < nch) {
+                        k2 = min(k2, max(k1, key));
+                        if (key < k1) g1 = tile * 8 + wg * 4 + c;
+                        k1 = min(k1, key);
+                    }
                     if (c < 3) {
                         ptx::tmem_ld_wait();
                         if (c == 2) {
@@ -272,7 +290,7 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
                 }
             }
             // ---- unit end: fold the two column halves, write the row results
-            int4* mbuf = smMerge + (un & 1) * 128;
+            int4* mbuf = smMerge + (cu & 1) * 128;
             if (wg == 1) mbuf[row] = make_int4(k1, k2, g1, 0);
             ptx::bar_sync(1, EPI_THREADS);
             if (wg == 0) {

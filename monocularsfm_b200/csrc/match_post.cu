@@ -39,37 +39,44 @@ __global__ void desc_norm_key_kernel(const uint8_t* __restrict__ raw, int n, int
     }
 }
 
-// rank of every key among all keys (O(n^2), tiled through shared memory; n is a few thousand) and from it the
-// sorted-space position: rank + dead columns inserted before the key's bucket
+// rank of every key among all keys: O(n^2) compares (n is a few thousand), tiled through shared memory and split over
+// gridDim.y slices of the comparison range so that all SMs take part; partial ranks are summed with integer atomics
 __global__ void __launch_bounds__(256)
 desc_rank_kernel(const unsigned long long* __restrict__ keys, int n, const int32_t* __restrict__ bucket_cnt,
-                 int32_t* __restrict__ pos_of) {
+                 int32_t* __restrict__ rank_of, int32_t* __restrict__ used) {
     __shared__ unsigned long long tile[1024];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long mine = j < n ? keys[j] : ~0ull;
+    const int per = (n + gridDim.y - 1) / gridDim.y;
+    const int lo = blockIdx.y * per, hi = min(n, lo + per);
     int rank = 0;
-    for (int base = 0; base < n; base += 1024) {
-        for (int k = threadIdx.x; k < 1024; k += blockDim.x) tile[k] = (base + k < n) ? keys[base + k] : ~0ull;
+    for (int base = lo; base < hi; base += 1024) {
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x) tile[k] = (base + k < hi) ? keys[base + k] : ~0ull;
         __syncthreads();
-        const int lim = min(1024, n - base);
+        const int lim = min(1024, hi - base);
 #pragma unroll 8
         for (int k = 0; k < lim; ++k) rank += tile[k] < mine ? 1 : 0;
         __syncthreads();
     }
-    if (j >= n) return;
-    const int b = static_cast<int>(mine >> 56);
-    int pad = 0;
-    for (int k = 0; k < b; ++k) pad += (32 - (bucket_cnt[k] & 31)) & 31;
-    pos_of[j] = rank + pad;
+    if (j == 0 && blockIdx.y == 0) {
+        int tot = 0;
+        for (int k = 0; k < kNumBuckets; ++k) tot += (bucket_cnt[k] + 31) & ~31;
+        used[0] = tot;
+    }
+    if (j < n && rank) atomicAdd(&rank_of[j], rank);
 }
 
 // one warp per descriptor: write the swizzled row at its sorted position, its norm and original index
-__global__ void desc_scatter_kernel(const uint8_t* __restrict__ raw, int n, const int32_t* __restrict__ pos_of,
-                                    const int32_t* __restrict__ nrm_orig, uint8_t* __restrict__ sw,
-                                    int32_t* __restrict__ nrm, int32_t* __restrict__ perm) {
+__global__ void desc_scatter_kernel(const uint8_t* __restrict__ raw, int n, const int32_t* __restrict__ rank_of,
+                                    const int32_t* __restrict__ nrm_orig, const int32_t* __restrict__ bucket_cnt,
+                                    uint8_t* __restrict__ sw, int32_t* __restrict__ nrm, int32_t* __restrict__ perm) {
     const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
     for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < n; j += gridDim.x * wpb) {
-        const int p = pos_of[j];
+        // sorted-space position: rank + dead columns inserted before this key's bucket
+        const int b = bucket_of(nrm_orig[j]);
+        int pad = 0;
+        for (int k = 0; k < b; ++k) pad += (32 - (bucket_cnt[k] & 31)) & 31;
+        const int p = rank_of[j] + pad;
         const uint32_t w = reinterpret_cast<const uint32_t*>(raw + static_cast<size_t>(j) * 128)[lane];
         const int chunk = lane >> 2;                          // 16-byte chunk of this lane's word
         const int slot = ((chunk ^ (p & 7)) << 2) | (lane & 3);
@@ -451,7 +458,7 @@ write_matches_kernel(const ImgDev* __restrict__ imgs, const SegDev* __restrict__
 // raw [n][128] (device) -> resident layout.  block = one allocation laid out by img_layout() (msfm_api.cu);
 // scratch: keys [n] u64 | nrm_orig [n] | pos_of [n] | bucket_cnt [8]
 cudaError_t launch_desc_format(const uint8_t* raw, int n, int n_pad, uint8_t* sw, uint8_t* ext, int32_t* cg,
-                               int32_t* nrm, int32_t* perm, unsigned long long* keys, int32_t* nrm_orig,
+                               int32_t* nrm, int32_t* perm, int32_t* used, unsigned long long* keys, int32_t* nrm_orig,
                                int32_t* pos_of, int32_t* bucket_cnt, cudaStream_t st) {
     if (n_pad <= 0) return cudaSuccess;
     const size_t ext_bytes = static_cast<size_t>((n_pad + 1023) / 1024) * 256 * 128;
@@ -461,13 +468,16 @@ cudaError_t launch_desc_format(const uint8_t* raw, int n, int n_pad, uint8_t* sw
     if ((e = cudaMemsetAsync(nrm, 0xFF, static_cast<size_t>(n_pad) * 4, st)) != cudaSuccess) return e;     // -1: dead
     if ((e = cudaMemsetAsync(perm, 0xFF, static_cast<size_t>(n_pad) * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(bucket_cnt, 0, 8 * 4, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(used, 0, 4, st)) != cudaSuccess) return e;
     if (n > 0) {
         const int wpb = 8;
         int grid = (n + wpb - 1) / wpb;
         if (grid > 148 * 8) grid = 148 * 8;
         desc_norm_key_kernel<<<grid, wpb * 32, 0, st>>>(raw, n, nrm_orig, keys, bucket_cnt);
-        desc_rank_kernel<<<(n + 255) / 256, 256, 0, st>>>(keys, n, bucket_cnt, pos_of);
-        desc_scatter_kernel<<<grid, wpb * 32, 0, st>>>(raw, n, pos_of, nrm_orig, sw, nrm, perm);
+        if ((e = cudaMemsetAsync(pos_of, 0, static_cast<size_t>(n) * 4, st)) != cudaSuccess) return e;
+        const int slices = n >= 2048 ? 8 : 1;
+        desc_rank_kernel<<<dim3((n + 255) / 256, slices), 256, 0, st>>>(keys, n, bucket_cnt, pos_of, used);
+        desc_scatter_kernel<<<grid, wpb * 32, 0, st>>>(raw, n, pos_of, nrm_orig, bucket_cnt, sw, nrm, perm);
     }
     int ggrid = (n_pad / 32 + 7) / 8;
     desc_groups_kernel<<<ggrid, 256, 0, st>>>(nrm, n_pad, cg, ext);

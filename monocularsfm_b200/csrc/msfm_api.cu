@@ -9,7 +9,7 @@
 
 namespace msfm {
 cudaError_t launch_match_tile_kernel(const ImgDev*, const UnitDev*, int, int32_t*, int32_t*, int32_t*, int, cudaStream_t);
-cudaError_t launch_desc_format(const uint8_t*, int, int, uint8_t*, uint8_t*, int32_t*, int32_t*, int32_t*, unsigned long long*,
+cudaError_t launch_desc_format(const uint8_t*, int, int, uint8_t*, uint8_t*, int32_t*, int32_t*, int32_t*, int32_t*, unsigned long long*,
                                int32_t*, int32_t*, int32_t*, cudaStream_t);
 cudaError_t launch_build_units(const SegDev*, int, int, UnitDev*, cudaStream_t);
 cudaError_t launch_resolve_rows(const ImgDev*, const UnitDev*, int, const int32_t*, const int32_t*, const int32_t*,
@@ -124,7 +124,7 @@ int msfm_prof_read(msfm_ctx* c, double ms[MSFM_PROF_NCAT], int64_t n[MSFM_PROF_N
 // ------------------------------------------------------------------------------------------------ uploads
 // One allocation per image: sw | ext | cg | nrm | perm (match_types.cuh), every part 256-B aligned.
 struct ImgLayout {
-    size_t off_ext, off_cg, off_nrm, off_perm, total;
+    size_t off_ext, off_cg, off_nrm, off_perm, off_used, total;
 };
 static ImgLayout img_layout(int32_t n_pad) {
     ImgLayout L;
@@ -135,7 +135,8 @@ static ImgLayout img_layout(int32_t n_pad) {
     L.off_cg = L.off_ext + ext;
     L.off_nrm = L.off_cg + cg;
     L.off_perm = L.off_nrm + static_cast<size_t>(n_pad) * 4;
-    L.total = L.off_perm + static_cast<size_t>(n_pad) * 4;
+    L.off_used = L.off_perm + static_cast<size_t>(n_pad) * 4;
+    L.total = L.off_used + 256;
     return L;
 }
 static int32_t padded_count(int32_t n) { return n > 0 ? (n + kMaxPadPerImage + 255) / 256 * 256 : 0; }
@@ -187,7 +188,7 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
     c->prof_begin(MSFM_PROF_DESC_FORMAT);
     MSFM_CUDA(c, launch_desc_format(raw, n, n_pad, sw, sw + L.off_ext, reinterpret_cast<int32_t*>(sw + L.off_cg),
                                     reinterpret_cast<int32_t*>(sw + L.off_nrm), reinterpret_cast<int32_t*>(sw + L.off_perm),
-                                    keys, nrm_orig, pos_of, bucket_cnt, c->stream));
+                                    reinterpret_cast<int32_t*>(sw + L.off_used), keys, nrm_orig, pos_of, bucket_cnt, c->stream));
     c->prof_end();
     c->launches += 4;
     return MSFM_OK;
@@ -247,6 +248,7 @@ static int sync_img_table(msfm_ctx* c) {
         tab[i].cg = sw ? reinterpret_cast<const int32_t*>(sw + L.off_cg) : nullptr;
         tab[i].nrm = sw ? reinterpret_cast<const int32_t*>(sw + L.off_nrm) : nullptr;
         tab[i].perm = sw ? reinterpret_cast<const int32_t*>(sw + L.off_perm) : nullptr;
+        tab[i].used = sw ? reinterpret_cast<const int32_t*>(sw + L.off_used) : nullptr;
         tab[i].n = im.n;
         tab[i].n_pad = im.n_pad;
     }

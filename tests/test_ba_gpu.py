@@ -105,3 +105,11 @@ def test_bad_problem_is_rejected(ctx):
     bad[0], bad[-1] = bad[-1], bad[0]
     with pytest.raises(m.MsfmError):
         ctx.ba_create(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], bad, P["cam_const"], P["fx"], P["fy"])
+
+
+def test_duplicate_camera_in_a_track_is_rejected(ctx):
+    P = bo.make_problem(4, 10, 3, 0)
+    oc = P["obs_cam"].copy()
+    oc[1] = oc[0]                                   # point 0 now observed twice by the same camera
+    with pytest.raises(m.MsfmError):
+        ctx.ba_create(P["cams"], P["pts"], P["obs_uv"], oc, P["obs_pt"], P["cam_const"], P["fx"], P["fy"])

@@ -135,3 +135,32 @@ def test_unknown_image_is_an_error(ctx):
     with pytest.raises(m.MsfmError) as ei:
         ctx.match_pairs([[12345, 1]], m.MatchOptions())
     assert ei.value.code == -5
+
+
+def test_many_small_pairs_cross_batch_boundaries(ctx):
+    """More work units than one internal batch holds (131072): offsets / running totals must chain across batches.
+    200 images x 260 descriptors -> 19900 pairs x 2 directions x 4 units."""
+    rng = np.random.default_rng(99)
+    n_img, n = 200, 260
+    base = _sift_like(rng, n)
+    imgs = []
+    for k in range(n_img):
+        x = _sift_like(rng, n)
+        m_ = 60
+        dst = rng.permutation(n)[:m_]
+        src = rng.permutation(n)[:m_]
+        x[dst] = np.clip(base[src].astype(np.int64) + rng.integers(-2, 3, (m_, 128)), 0, 255).astype(np.uint8)
+        imgs.append(x)
+        ctx.upload(1000 + k, x)
+    pairs = np.array([(1000 + i, 1000 + j) for i in range(n_img) for j in range(i)], np.int32)
+    off, mt, d = ctx.match_pairs(pairs, m.MatchOptions(0.8, -1.0, True, True))
+    st = ctx.match_stats()
+    assert st["units"] > 131072
+    assert off[0] == 0 and off[-1] == len(mt) and (np.diff(off) >= 0).all()
+    for p in list(range(0, len(pairs), 997)) + [len(pairs) - 1, 8190, 8191, 8192, 8193]:
+        i1, i2 = pairs[p] - 1000
+        em, ed = mo.match_image_pair(imgs[i1], imgs[i2], 0.8, -1.0, True, True)
+        np.testing.assert_array_equal(mt[off[p]:off[p + 1]], em, err_msg=f"pair {p}")
+        np.testing.assert_array_equal(d[off[p]:off[p + 1]], ed)
+    for k in range(n_img):
+        ctx.release(1000 + k)

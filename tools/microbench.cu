@@ -105,6 +105,30 @@ __global__ void k_alu(int iters, long long* cyc, int* sink, const int* in) {
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// ---- 2b. column-direction reduction candidate: per 32 registers: 32 x redux.max + lane select, then one shared atomicMax
+__global__ void k_redux(int iters, long long* cyc, int* sink, const int* in) {
+    __shared__ int colmax[256];
+    if (threadIdx.x < 256) colmax[threadIdx.x] = 0;
+    int v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = in[(threadIdx.x + k * 7) & 1023];
+    const int lane = threadIdx.x & 31;
+    __syncthreads();
+    long long t0 = clock64();
+    int keep = 0;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const int m = __reduce_max_sync(0xffffffffu, v[k] + i);
+            if (lane == k) keep = m;
+        }
+        atomicMax(&colmax[(i * 32 + lane) & 255], keep);
+    }
+    long long t1 = clock64();
+    if (keep == 0x7654321) sink[0] = keep + colmax[lane];
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 // ---- 3. MMA rate: one thread issues `iters` x (4 x tcgen05.mma 128x256x32 i8) on garbage smem, then commit + wait
 __global__ void k_mma(int iters, long long* cyc) {
     extern __shared__ uint8_t smem_raw[];
@@ -240,6 +264,12 @@ int main() {
             double c = avg(h, G);
             printf("alu %-55s warps=%2d: %.2f cyc/iter (per SM: %.2f cyc per warp-iter)\n", names[mode], nw, c / it, c / it / nw);
         }
+    }
+    for (int nw : {4, 8, 16}) {
+        for (int rep = 0; rep < 2; ++rep) k_redux<<<G, nw * 32>>>(it, d_cyc, d_sink, d_in);
+        CK(cudaDeviceSynchronize()); CK(cudaMemcpy(h, d_cyc, G * 8, cudaMemcpyDeviceToHost));
+        double c = avg(h, G);
+        printf("redux column-max (32 REDUX.MAX + select + 1 ATOMS.MAX per 32x32 chunk) warps=%2d: %.1f cyc per chunk per warp, %.1f per SM-chunk\n", nw, c / it, c / it / nw);
     }
     CK(cudaFuncSetAttribute(k_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 60000));
     for (int rep = 0; rep < 2; ++rep) k_mma<<<G, 64, 60000>>>(2048, d_cyc);

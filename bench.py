@@ -167,16 +167,23 @@ def bench_ba(ctx, args, rank, world, dist, dev, peaks):
            "metric": "observations/s per BA iteration (evaluate + Jacobians + Schur reduction" + (" + all-reduce)" if world > 1 else ")"),
            "value": n_obs_total / (ms * 1e-3), "unit": "observations/s", "ms_per_iteration": ms,
            "kernel_ms": k_ms, "dtype": "f64 geometry / f32 block products / f64 accumulation",
-           "roofline": {"bound": "hbm", "kernel": "linearize_schur_kernel", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None,
+           "roofline": {"bound": "hbm", "kernel": "point_pass + camera_diag + pair_block (one linearisation)", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None,
                         "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": (alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if k_ms else None, "traffic": None,
                         "algorithmic_bytes": alg_bytes,
-                        "note": "atomic-throughput bound, far from the HBM roof: see DESIGN.md B-path"}}
-    # full LM solve (the call CeresBundelOptimizer::Optimize makes)
+                        "note": "gather kernels over L2-resident intermediates; the algorithmic bytes of this small problem are ~3 us of HBM time, so launch latency and gather latency dominate: see DESIGN.md B-path"}}
+    # full LM solve (the call CeresBundelOptimizer::Optimize makes); the first solve pays one-time library initialisation
+    # (cuSOLVER handle, lazy kernel loading), so it is repeated from the same start and the second one is reported
+    cams0, pts0 = ba.get_params()
+    t0 = time.perf_counter()
+    summ = ba.solve()
+    first_s = time.perf_counter() - t0
+    ba.set_params(cams0, pts0)
     t0 = time.perf_counter()
     summ = ba.solve()
     out["lm"] = {"iterations": summ["iterations"], "termination": summ["termination"], "initial_cost": summ["initial_cost"],
-                 "final_cost": summ["final_cost"], "wall_s": time.perf_counter() - t0,
+                 "final_cost": summ["final_cost"], "wall_s": time.perf_counter() - t0, "first_call_wall_s": first_s,
+                 "linearize_s": summ["linearize_time_s"], "solve_backsub_eval_s": summ["solve_time_s"],
                  "rmse_px": float(np.sqrt(2 * summ["final_cost"] / max(1, summ["num_residuals"])))}
     if rank == 0 and world == 1 and args.cpu_pairs > 0:
         from oracle import ba_oracle as bo

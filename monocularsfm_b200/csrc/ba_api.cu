@@ -305,10 +305,17 @@ int msfm_ba_evaluate(msfm_ba* b, double* r, float* J, double* cost) {
     BA_CUDA(cudaSetDevice(c->device));
     int rc = prep(b, b->cur);
     if (rc) return rc;
+    // parity dumps go through two grow-only scratch buffers of the context (no allocation on the steady path)
     double* d_r = nullptr;
     float* d_J = nullptr;
-    if (r && b->n_obs) BA_CUDA(cudaMalloc(&d_r, size_t(b->n_obs) * 2 * sizeof(double)));
-    if (J && b->n_obs) BA_CUDA(cudaMalloc(&d_J, size_t(b->n_obs) * 18 * sizeof(float)));
+    if (r && b->n_obs) {
+        BA_CUDA(c->d_ba_r.reserve(size_t(b->n_obs) * 2 * sizeof(double)));
+        d_r = c->d_ba_r.as<double>();
+    }
+    if (J && b->n_obs) {
+        BA_CUDA(c->d_ba_J.reserve(size_t(b->n_obs) * 18 * sizeof(float)));
+        d_J = c->d_ba_J.as<float>();
+    }
     BA_CUDA(cudaMemsetAsync(b->small, 0, 8 * sizeof(double), c->stream));
     c->prof_begin(MSFM_PROF_BA_EVAL);
     BA_CUDA(ba_launch_evaluate(b->view(b->cur), d_r, d_J, b->small, c->num_sms, c->stream));
@@ -319,8 +326,6 @@ int msfm_ba_evaluate(msfm_ba* b, double* r, float* J, double* cost) {
     if (d_r) BA_CUDA(cudaMemcpyAsync(r, d_r, size_t(b->n_obs) * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (d_J) BA_CUDA(cudaMemcpyAsync(J, d_J, size_t(b->n_obs) * 18 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     BA_CUDA(cudaStreamSynchronize(c->stream));
-    if (d_r) cudaFree(d_r);
-    if (d_J) cudaFree(d_J);
     if (cost) *cost = h;
     return MSFM_OK;
 }

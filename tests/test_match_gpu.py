@@ -164,3 +164,59 @@ def test_many_small_pairs_cross_batch_boundaries(ctx):
         np.testing.assert_array_equal(d[off[p]:off[p + 1]], ed)
     for k in range(n_img):
         ctx.release(1000 + k)
+
+
+def test_api_edge_cases(ctx):
+    """Empty inputs, re-upload with a different size, release, zero pairs."""
+    rng = np.random.default_rng(17)
+    a, b = _planted_set(rng, 2, 300)
+    ctx.upload(50, a)
+    ctx.upload(51, b)
+    ctx.upload(52, np.zeros((0, 128), np.uint8))                 # an image without descriptors
+    assert ctx.desc_count(52) == 0
+    off, mt, d = ctx.match_pairs(np.zeros((0, 2), np.int32), m.MatchOptions(), capacity=1)
+    assert off.tolist() == [0] and len(mt) == 0
+    off, mt, d = ctx.match_pairs([[50, 52], [52, 50], [50, 51]], m.MatchOptions(0.8, -1.0, True, True))
+    assert off[1] == 0 and off[2] == 0
+    em, ed = mo.match_image_pair(a, b, 0.8, -1.0, True, True)
+    np.testing.assert_array_equal(mt, em)
+    # replace image 51 by a smaller set: results must follow the new data
+    b2 = b[:77]
+    ctx.upload(51, b2)
+    assert ctx.desc_count(51) == 77
+    off, mt, d = ctx.match_pairs([[50, 51]], m.MatchOptions(0.8, -1.0, True, True))
+    em, ed = mo.match_image_pair(a, b2, 0.8, -1.0, True, True)
+    np.testing.assert_array_equal(mt, em)
+    np.testing.assert_array_equal(d, ed)
+    # a pair of an image with itself: every descriptor's nearest neighbour is itself at distance 0
+    off, mt, d = ctx.match_pairs([[50, 50]], m.MatchOptions(0.8, -1.0, True, True))
+    em, ed = mo.match_image_pair(a, a, 0.8, -1.0, True, True)
+    np.testing.assert_array_equal(mt, em)
+    ctx.release(51)
+    with pytest.raises(m.MsfmError):
+        ctx.match_pairs([[50, 51]], m.MatchOptions())
+    for k in (50, 52):
+        ctx.release(k)
+
+
+def test_uniform_random_descriptors_full_norm_range(ctx):
+    """Uniform u8 rows have squared norms spread over several sort buckets and both parities (the SIFT-like sets do not)."""
+    rng = np.random.default_rng(23)
+    a = rng.integers(0, 256, (1500, 128), dtype=np.uint8)
+    b = rng.integers(0, 256, (1700, 128), dtype=np.uint8)
+    a[:40] = (a[:40] // 8)                       # small norms
+    b[:60] = 255 - (b[:60] // 16)                # very large norms (third bucket)
+    b[100:160] = a[100:160]                      # exact correspondences
+    ctx.upload(60, a)
+    ctx.upload(61, b)
+    for opt in (m.MatchOptions(0.8, -1.0, True, True), m.MatchOptions(0.97, -1.0, False, False)):
+        off, mt, d = ctx.match_pairs([[60, 61]], opt)
+        em, ed = mo.match_image_pair(a, b, opt.distance_ratio, -1.0, bool(opt.cross_check), bool(opt.opencv_quirks))
+        np.testing.assert_array_equal(mt, em)
+        np.testing.assert_array_equal(d, ed)
+    idx, dist, d2 = ctx.knn2(a, b, 0)
+    oi, od, _ = mo.knn2(a, b)
+    np.testing.assert_array_equal(idx[:, 0], oi[:, 0])
+    np.testing.assert_array_equal(dist, od)
+    ctx.release(60)
+    ctx.release(61)

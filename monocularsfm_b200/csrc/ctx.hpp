@@ -61,6 +61,7 @@ struct msfm_ctx {
     bool imgs_dirty = true;
     msfm::GrowBuf d_raw;                           // upload staging (device)
     msfm::GrowBuf d_fmt;                           // upload formatting scratch (sort keys, ranks)
+    msfm::GrowBuf d_temp;                          // temporary query images of the reverse (cross-check) pass
     msfm::GrowBuf h_stage;                         // pinned host staging (segments, offsets readback)
     msfm::GrowBuf d_segs, d_units, d_res, d_m, d_exact, d_counts, d_misc;
     msfm::GrowBuf d_out_offsets, d_out_matches, d_out_dist;

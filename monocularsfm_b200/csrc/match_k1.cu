@@ -71,7 +71,7 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 __device__ __forceinline__ int img_used(const ImgDev& im) { return im.used ? __ldg(im.used) : 0; }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ units, int num_units,
+match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ units, int unit0, int num_units,
                   int32_t* __restrict__ res_g, int32_t* __restrict__ res_d1, int32_t* __restrict__ res_u) {
     extern __shared__ uint8_t smem_raw[];
     // manual 1 KiB alignment (dynamic smem is only guaranteed 16-B aligned)
@@ -135,7 +135,7 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
         // ===================================================================== producer
         if (lane == 0) {
             uint32_t it = 0, un = 0, et = 0;
-            for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+            for (int u = unit0 + blockIdx.x; u < unit0 + num_units; u += gridDim.x) {
                 const UnitDev unit = units[u];
                 const ImgDev q = imgs[unit.q_slot];
                 const ImgDev t = imgs[unit.t_slot];
@@ -170,7 +170,7 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
             constexpr uint32_t idesc = ptx::make_idesc_u8(BM, BN);
             const uint64_t aext_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smAext));
             uint32_t it = 0, un = 0, et = 0;
-            for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+            for (int u = unit0 + blockIdx.x; u < unit0 + num_units; u += gridDim.x) {
                 const UnitDev unit = units[u];
                 const ImgDev t = imgs[unit.t_slot];
                 if (unit.row_block * BM >= img_used(imgs[unit.q_slot])) continue;
@@ -230,7 +230,7 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;             // query row inside the unit
         uint32_t it = 0, un = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        for (int u = unit0 + blockIdx.x; u < unit0 + num_units; u += gridDim.x) {
             const UnitDev unit = units[u];
             const ImgDev q = imgs[unit.q_slot];
             const ImgDev t = imgs[unit.t_slot];
@@ -319,14 +319,14 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
 }  // namespace k1
 
 // host launcher (called from msfm_api.cu)
-cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, int num_units, int32_t* res_g,
+cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, int unit0, int num_units, int32_t* res_g,
                                      int32_t* res_d1, int32_t* res_u, int num_sms, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(k1::match_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(k1::SMEM_BYTES));
     if (e != cudaSuccess) return e;
     if (num_units <= 0) return cudaSuccess;
     const int grid = num_units < num_sms ? num_units : num_sms;
-    k1::match_tile_kernel<<<grid, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(imgs, units, num_units, res_g, res_d1,
+    k1::match_tile_kernel<<<grid, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(imgs, units, unit0, num_units, res_g, res_d1,
                                                                             res_u);
     return cudaGetLastError();
 }

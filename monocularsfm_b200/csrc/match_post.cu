@@ -69,7 +69,8 @@ desc_rank_kernel(const unsigned long long* __restrict__ keys, int n, const int32
 // one warp per descriptor: write the swizzled row at its sorted position, its norm and original index
 __global__ void desc_scatter_kernel(const uint8_t* __restrict__ raw, int n, const int32_t* __restrict__ rank_of,
                                     const int32_t* __restrict__ nrm_orig, const int32_t* __restrict__ bucket_cnt,
-                                    uint8_t* __restrict__ sw, int32_t* __restrict__ nrm, int32_t* __restrict__ perm) {
+                                    uint8_t* __restrict__ sw, int32_t* __restrict__ nrm, int32_t* __restrict__ perm,
+                                    int32_t* __restrict__ inv) {
     const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
     for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < n; j += gridDim.x * wpb) {
         // sorted-space position: rank + dead columns inserted before this key's bucket
@@ -81,7 +82,7 @@ __global__ void desc_scatter_kernel(const uint8_t* __restrict__ raw, int n, cons
         const int chunk = lane >> 2;                          // 16-byte chunk of this lane's word
         const int slot = ((chunk ^ (p & 7)) << 2) | (lane & 3);
         reinterpret_cast<uint32_t*>(sw + static_cast<size_t>(p) * 128)[slot] = w;
-        if (lane == 0) { nrm[p] = nrm_orig[j]; perm[p] = j; }
+        if (lane == 0) { nrm[p] = nrm_orig[j]; perm[p] = j; inv[j] = p; }
     }
 }
 
@@ -178,18 +179,19 @@ __device__ __forceinline__ bool dist_filter_ok(int32_t d1, double max_distance) 
 //   m_d2  exact d2 of the runner-up when it was computed, else an upper bound (kIntInf = none)
 //   m_j0  [2o] best column regardless of the ratio test (knn2 API), [2o+1] runner-up column (exact path only) or -1
 __global__ void __launch_bounds__(kUnitRows)
-resolve_rows_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ units, int num_units,
+resolve_rows_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ units, int unit0, int num_units,
                     const int32_t* __restrict__ res_g, const int32_t* __restrict__ res_d1,
                     const int32_t* __restrict__ res_u, MatchOpts opt, int32_t* __restrict__ m_j,
                     int32_t* __restrict__ m_d1, int32_t* __restrict__ m_d2, int32_t* __restrict__ m_j0,
                     int32_t* __restrict__ exact_list, unsigned int* __restrict__ counters /*[0]=exact,[1]=rescans*/) {
-    const int u = blockIdx.x;
-    if (u >= num_units) return;
+    if (static_cast<int>(blockIdx.x) >= num_units) return;
+    const int u = unit0 + blockIdx.x;
     const UnitDev unit = units[u];
     const ImgDev q = imgs[unit.q_slot];
     const ImgDev t = imgs[unit.t_slot];
     const int lane = threadIdx.x & 31;
     const int r = threadIdx.x;
+    if (unit.row_block * kUnitRows >= (q.used ? __ldg(q.used) : 0)) return;     // all-dead rows (K1 skipped the unit too)
     const int qp = unit.row_block * kUnitRows + r;           // sorted-space row of the query image
     const size_t g = static_cast<size_t>(u) * kUnitRows + r; // K1 result slot
     const int qorig = q.perm[qp];                            // -1 for dead rows
@@ -323,13 +325,14 @@ struct PairView {
     int n1, n2;
     size_t base12, base21;   // global row base of the two directions (base21 unused without cross-check)
 };
-__device__ __forceinline__ PairView pair_view(const ImgDev* imgs, const SegDev* segs, int p, int cross) {
-    const SegDev s12 = segs[cross ? 2 * p : p];
+// segment table of a batch: [forward segments of all pairs][reverse segments of all pairs]
+__device__ __forceinline__ PairView pair_view(const ImgDev* imgs, const SegDev* segs, int p, int npairs, int cross) {
+    const SegDev s12 = segs[p];
     PairView v;
     v.n1 = imgs[s12.q_slot].n;
     v.n2 = imgs[s12.t_slot].n;
     v.base12 = static_cast<size_t>(s12.unit_base) * kUnitRows;
-    v.base21 = cross ? static_cast<size_t>(segs[2 * p + 1].unit_base) * kUnitRows : 0;
+    v.base21 = cross ? static_cast<size_t>(segs[npairs + p].unit_base) * kUnitRows : 0;
     return v;
 }
 __device__ __forceinline__ bool keep_match(const PairView& v, int i, const int32_t* m_j, const int32_t* m_d1,
@@ -351,7 +354,7 @@ count_matches_kernel(const ImgDev* __restrict__ imgs, const SegDev* __restrict__
                      const int32_t* __restrict__ m_j, const int32_t* __restrict__ m_d1, int32_t* __restrict__ counts) {
     const int p = blockIdx.x;
     if (p >= npairs) return;
-    const PairView v = pair_view(imgs, segs, p, opt.cross_check);
+    const PairView v = pair_view(imgs, segs, p, npairs, opt.cross_check);
     int c = 0;
     for (int i = threadIdx.x; i < v.n1; i += blockDim.x) {
         int32_t j;
@@ -420,7 +423,7 @@ write_matches_kernel(const ImgDev* __restrict__ imgs, const SegDev* __restrict__
                      int32_t* __restrict__ out_matches, float* __restrict__ out_dist) {
     const int p = blockIdx.x;
     if (p >= npairs) return;
-    const PairView v = pair_view(imgs, segs, p, opt.cross_check);
+    const PairView v = pair_view(imgs, segs, p, npairs, opt.cross_check);
     const long long off = offsets[p];
     __shared__ int warp_cnt[8];
     __shared__ int chunk_base;
@@ -454,11 +457,120 @@ write_matches_kernel(const ImgDev* __restrict__ imgs, const SegDev* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cross-check needs the reverse direction only for train descriptors that some query row actually matched
+// (FeatureUtils::CrossCheck looks up vis[m12.trainIdx] only, FeatureUtils.cpp:296-302).  After the forward pass the
+// matched train rows of every pair are gathered into a compact temporary "query image"; the reverse pass then runs on
+// ~n/10 rows instead of n.  Its perm[] holds the ORIGINAL train index, so the reverse results land where the full
+// reverse pass would have put them and the downstream kernels do not change.
+struct TempImgs {
+    uint8_t* sw;        // [pairs][n_pad_t][128]
+    int32_t* nrm;       // [pairs][n_pad_t]
+    int32_t* perm;      // [pairs][n_pad_t]
+    int32_t* used;      // [pairs]
+    int32_t* flags;     // [pairs][n_pad_t]
+    int32_t n_pad_t;    // rows reserved per pair (multiple of kUnitRows)
+};
+
+// table entries of the temporary query images: slot = first_temp_slot + pair
+__global__ void setup_temp_imgs_kernel(ImgDev* __restrict__ imgs, int first_temp_slot, const SegDev* __restrict__ segs,
+                                       int npairs, TempImgs T) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const int n2 = imgs[segs[p].t_slot].n;
+    ImgDev e;
+    e.sw = T.sw + static_cast<size_t>(p) * T.n_pad_t * 128;
+    e.ext = nullptr; e.cg = nullptr; e.inv = nullptr;
+    e.nrm = T.nrm + static_cast<size_t>(p) * T.n_pad_t;
+    e.perm = T.perm + static_cast<size_t>(p) * T.n_pad_t;
+    e.used = T.used + p;
+    e.n = n2;
+    e.n_pad = (n2 + kUnitRows - 1) / kUnitRows * kUnitRows;
+    imgs[first_temp_slot + p] = e;
+}
+
+// one CTA per pair: flag the train rows matched by the forward pass, compact them in ascending original index,
+// copy (re-swizzle) their descriptor rows
+__global__ void __launch_bounds__(256)
+gather_candidates_kernel(const ImgDev* __restrict__ imgs, const SegDev* __restrict__ segs, int npairs,
+                         const int32_t* __restrict__ m_j, TempImgs T) {
+    const int p = blockIdx.x;
+    if (p >= npairs) return;
+    const SegDev s12 = segs[p];
+    const ImgDev img1 = imgs[s12.q_slot], img2 = imgs[s12.t_slot];
+    const int n1 = img1.n, n2 = img2.n;
+    int32_t* flags = T.flags + static_cast<size_t>(p) * T.n_pad_t;
+    int32_t* t_nrm = T.nrm + static_cast<size_t>(p) * T.n_pad_t;
+    int32_t* t_perm = T.perm + static_cast<size_t>(p) * T.n_pad_t;
+    uint8_t* t_sw = T.sw + static_cast<size_t>(p) * T.n_pad_t * 128;
+    const size_t base12 = static_cast<size_t>(s12.unit_base) * kUnitRows;
+    for (int j = threadIdx.x; j < n2; j += blockDim.x) flags[j] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) {
+        const int32_t j = m_j[base12 + i];
+        if (j >= 0) flags[j] = 1;
+    }
+    __syncthreads();
+    // ordered compaction: flags[j] becomes the slot of row j (or -1)
+    __shared__ int warp_cnt[8];
+    __shared__ int chunk_base;
+    if (threadIdx.x == 0) chunk_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n2; base += blockDim.x) {
+        const int j = base + threadIdx.x;
+        const bool f = j < n2 && flags[j] != 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) warp_cnt[warp] = __popc(mask);
+        __syncthreads();
+        int pre = chunk_base;
+        for (int k = 0; k < warp; ++k) pre += warp_cnt[k];
+        if (j < n2) flags[j] = f ? pre + __popc(mask & ((1u << lane) - 1u)) : -1;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int s = 0;
+            for (int k = 0; k < (blockDim.x >> 5); ++k) s += warp_cnt[k];
+            chunk_base += s;
+        }
+        __syncthreads();
+    }
+    const int K = chunk_base;
+    const int Kpad = (K + kUnitRows - 1) / kUnitRows * kUnitRows;
+    if (threadIdx.x == 0) T.used[p] = Kpad;
+    // copy rows: one warp per train row j with a slot
+    for (int j = warp; j < n2; j += (blockDim.x >> 5)) {
+        const int slot = flags[j];
+        if (slot < 0) continue;
+        const int pos = __ldg(img2.inv + j);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(img2.sw + static_cast<size_t>(pos) * 128);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(t_sw + static_cast<size_t>(slot) * 128);
+        const int chunk = (lane >> 2) ^ (pos & 7);           // logical 16-byte chunk held at this lane's source word
+        dst[((chunk ^ (slot & 7)) << 2) | (lane & 3)] = __ldg(src + lane);
+        if (lane == 0) { t_nrm[slot] = __ldg(img2.nrm + pos); t_perm[slot] = j; }
+    }
+    // dead padding rows of the last unit
+    for (int k = K + warp; k < Kpad; k += (blockDim.x >> 5)) {
+        reinterpret_cast<uint32_t*>(t_sw + static_cast<size_t>(k) * 128)[lane] = 0u;
+        if (lane == 0) { t_nrm[k] = -1; t_perm[k] = -1; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
+cudaError_t launch_setup_temp_imgs(ImgDev* imgs, int first_temp_slot, const SegDev* segs, int npairs, TempImgs T, cudaStream_t st) {
+    if (npairs <= 0) return cudaSuccess;
+    setup_temp_imgs_kernel<<<(npairs + 127) / 128, 128, 0, st>>>(imgs, first_temp_slot, segs, npairs, T);
+    return cudaGetLastError();
+}
+cudaError_t launch_gather_candidates(const ImgDev* imgs, const SegDev* segs, int npairs, const int32_t* m_j, TempImgs T,
+                                     cudaStream_t st) {
+    if (npairs <= 0) return cudaSuccess;
+    gather_candidates_kernel<<<npairs, 256, 0, st>>>(imgs, segs, npairs, m_j, T);
+    return cudaGetLastError();
+}
 // raw [n][128] (device) -> resident layout.  block = one allocation laid out by img_layout() (msfm_api.cu);
 // scratch: keys [n] u64 | nrm_orig [n] | pos_of [n] | bucket_cnt [8]
 cudaError_t launch_desc_format(const uint8_t* raw, int n, int n_pad, uint8_t* sw, uint8_t* ext, int32_t* cg,
-                               int32_t* nrm, int32_t* perm, int32_t* used, unsigned long long* keys, int32_t* nrm_orig,
+                               int32_t* nrm, int32_t* perm, int32_t* inv, int32_t* used, unsigned long long* keys, int32_t* nrm_orig,
                                int32_t* pos_of, int32_t* bucket_cnt, cudaStream_t st) {
     if (n_pad <= 0) return cudaSuccess;
     const size_t ext_bytes = static_cast<size_t>((n_pad + 1023) / 1024) * 256 * 128;
@@ -477,7 +589,7 @@ cudaError_t launch_desc_format(const uint8_t* raw, int n, int n_pad, uint8_t* sw
         if ((e = cudaMemsetAsync(pos_of, 0, static_cast<size_t>(n) * 4, st)) != cudaSuccess) return e;
         const int slices = n >= 2048 ? 8 : 1;
         desc_rank_kernel<<<dim3((n + 255) / 256, slices), 256, 0, st>>>(keys, n, bucket_cnt, pos_of, used);
-        desc_scatter_kernel<<<grid, wpb * 32, 0, st>>>(raw, n, pos_of, nrm_orig, bucket_cnt, sw, nrm, perm);
+        desc_scatter_kernel<<<grid, wpb * 32, 0, st>>>(raw, n, pos_of, nrm_orig, bucket_cnt, sw, nrm, perm, inv);
     }
     int ggrid = (n_pad / 32 + 7) / 8;
     desc_groups_kernel<<<ggrid, 256, 0, st>>>(nrm, n_pad, cg, ext);
@@ -488,12 +600,12 @@ cudaError_t launch_build_units(const SegDev* segs, int nseg, int num_units, Unit
     build_units_kernel<<<(num_units + 255) / 256, 256, 0, st>>>(segs, nseg, num_units, units);
     return cudaGetLastError();
 }
-cudaError_t launch_resolve_rows(const ImgDev* imgs, const UnitDev* units, int num_units, const int32_t* res_g,
+cudaError_t launch_resolve_rows(const ImgDev* imgs, const UnitDev* units, int unit0, int num_units, const int32_t* res_g,
                                 const int32_t* res_d1, const int32_t* res_u, MatchOpts opt, int32_t* m_j, int32_t* m_d1,
                                 int32_t* m_d2, int32_t* m_j0, int32_t* exact_list, unsigned int* counters,
                                 cudaStream_t st) {
     if (num_units <= 0) return cudaSuccess;
-    resolve_rows_kernel<<<num_units, kUnitRows, 0, st>>>(imgs, units, num_units, res_g, res_d1, res_u, opt, m_j, m_d1, m_d2,
+    resolve_rows_kernel<<<num_units, kUnitRows, 0, st>>>(imgs, units, unit0, num_units, res_g, res_d1, res_u, opt, m_j, m_d1, m_d2,
                                                    m_j0, exact_list, counters);
     return cudaGetLastError();
 }

@@ -23,6 +23,7 @@ namespace msfm {
 //   cg   : [n_pad/32] s32  C_g (kDeadCg for groups without a real column)
 //   nrm  : [n_pad] s32     ||d||^2 of the column at sorted position p, -1 for dead columns
 //   perm : [n_pad] s32     original index of the column at sorted position p, -1 for dead columns
+//   inv  : [n] s32         sorted position of the column with original index j
 //   used : [1] s32         number of sorted positions actually occupied (sum of the padded bucket sizes, a multiple
 //                          of 32, <= n_pad): written on the device by the formatting kernels, read by K1 to skip the
 //                          all-dead tail (n_pad itself is the host-known upper bound n + 186 rounded to 256)
@@ -32,6 +33,7 @@ struct ImgDev {
     const int32_t* cg;
     const int32_t* nrm;
     const int32_t* perm;
+    const int32_t* inv;
     const int32_t* used;
     int32_t n;
     int32_t n_pad;

@@ -8,11 +8,16 @@
 #include "ctx.hpp"
 
 namespace msfm {
-cudaError_t launch_match_tile_kernel(const ImgDev*, const UnitDev*, int, int32_t*, int32_t*, int32_t*, int, cudaStream_t);
-cudaError_t launch_desc_format(const uint8_t*, int, int, uint8_t*, uint8_t*, int32_t*, int32_t*, int32_t*, int32_t*, unsigned long long*,
+struct TempImgs {
+    uint8_t* sw; int32_t* nrm; int32_t* perm; int32_t* used; int32_t* flags; int32_t n_pad_t;
+};
+cudaError_t launch_setup_temp_imgs(ImgDev*, int, const SegDev*, int, TempImgs, cudaStream_t);
+cudaError_t launch_gather_candidates(const ImgDev*, const SegDev*, int, const int32_t*, TempImgs, cudaStream_t);
+cudaError_t launch_match_tile_kernel(const ImgDev*, const UnitDev*, int, int, int32_t*, int32_t*, int32_t*, int, cudaStream_t);
+cudaError_t launch_desc_format(const uint8_t*, int, int, uint8_t*, uint8_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, unsigned long long*,
                                int32_t*, int32_t*, int32_t*, cudaStream_t);
 cudaError_t launch_build_units(const SegDev*, int, int, UnitDev*, cudaStream_t);
-cudaError_t launch_resolve_rows(const ImgDev*, const UnitDev*, int, const int32_t*, const int32_t*, const int32_t*,
+cudaError_t launch_resolve_rows(const ImgDev*, const UnitDev*, int, int, const int32_t*, const int32_t*, const int32_t*,
                                 MatchOpts, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, unsigned int*, cudaStream_t);
 cudaError_t launch_exact_rows(const ImgDev*, const UnitDev*, const int32_t*, const unsigned int*, int, MatchOpts,
                               int32_t*, int32_t*, int32_t*, int32_t*, int, cudaStream_t);
@@ -82,7 +87,7 @@ void msfm_destroy(msfm_ctx* c) {
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (auto& im : c->imgs)
         if (im.block) cudaFree(im.block);
-    GrowBuf* bufs[] = {&c->d_imgs, &c->d_raw, &c->d_fmt, &c->h_stage, &c->d_segs, &c->d_units, &c->d_res, &c->d_m, &c->d_exact,
+    GrowBuf* bufs[] = {&c->d_imgs, &c->d_raw, &c->d_fmt, &c->d_temp, &c->h_stage, &c->d_segs, &c->d_units, &c->d_res, &c->d_m, &c->d_exact,
                        &c->d_counts, &c->d_misc, &c->d_out_offsets, &c->d_out_matches, &c->d_out_dist, &c->d_ba_r, &c->d_ba_J};
     for (GrowBuf* b : bufs) b->release();
     cudaStreamDestroy(c->stream);
@@ -124,7 +129,7 @@ int msfm_prof_read(msfm_ctx* c, double ms[MSFM_PROF_NCAT], int64_t n[MSFM_PROF_N
 // ------------------------------------------------------------------------------------------------ uploads
 // One allocation per image: sw | ext | cg | nrm | perm (match_types.cuh), every part 256-B aligned.
 struct ImgLayout {
-    size_t off_ext, off_cg, off_nrm, off_perm, off_used, total;
+    size_t off_ext, off_cg, off_nrm, off_perm, off_inv, off_used, total;
 };
 static ImgLayout img_layout(int32_t n_pad) {
     ImgLayout L;
@@ -135,7 +140,8 @@ static ImgLayout img_layout(int32_t n_pad) {
     L.off_cg = L.off_ext + ext;
     L.off_nrm = L.off_cg + cg;
     L.off_perm = L.off_nrm + static_cast<size_t>(n_pad) * 4;
-    L.off_used = L.off_perm + static_cast<size_t>(n_pad) * 4;
+    L.off_inv = L.off_perm + static_cast<size_t>(n_pad) * 4;
+    L.off_used = L.off_inv + static_cast<size_t>(n_pad) * 4;
     L.total = L.off_used + 256;
     return L;
 }
@@ -188,7 +194,7 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
     c->prof_begin(MSFM_PROF_DESC_FORMAT);
     MSFM_CUDA(c, launch_desc_format(raw, n, n_pad, sw, sw + L.off_ext, reinterpret_cast<int32_t*>(sw + L.off_cg),
                                     reinterpret_cast<int32_t*>(sw + L.off_nrm), reinterpret_cast<int32_t*>(sw + L.off_perm),
-                                    reinterpret_cast<int32_t*>(sw + L.off_used), keys, nrm_orig, pos_of, bucket_cnt, c->stream));
+                                    reinterpret_cast<int32_t*>(sw + L.off_inv), reinterpret_cast<int32_t*>(sw + L.off_used), keys, nrm_orig, pos_of, bucket_cnt, c->stream));
     c->prof_end();
     c->launches += 4;
     return MSFM_OK;
@@ -248,12 +254,13 @@ static int sync_img_table(msfm_ctx* c) {
         tab[i].cg = sw ? reinterpret_cast<const int32_t*>(sw + L.off_cg) : nullptr;
         tab[i].nrm = sw ? reinterpret_cast<const int32_t*>(sw + L.off_nrm) : nullptr;
         tab[i].perm = sw ? reinterpret_cast<const int32_t*>(sw + L.off_perm) : nullptr;
+        tab[i].inv = sw ? reinterpret_cast<const int32_t*>(sw + L.off_inv) : nullptr;
         tab[i].used = sw ? reinterpret_cast<const int32_t*>(sw + L.off_used) : nullptr;
         tab[i].n = im.n;
         tab[i].n_pad = im.n_pad;
     }
     MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
-    MSFM_CUDA(c, c->d_imgs.reserve(std::max<size_t>(1, tab.size()) * sizeof(ImgDev)));
+    MSFM_CUDA(c, c->d_imgs.reserve((tab.size() + 1) * sizeof(ImgDev)));    // never shrinks: match_core reserves the temp slots
     if (!tab.empty())
         MSFM_CUDA(c, cudaMemcpy(c->d_imgs.p, tab.data(), tab.size() * sizeof(ImgDev), cudaMemcpyHostToDevice));
     c->imgs_dirty = false;
@@ -283,40 +290,72 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
     opt.exact_second = exact_second;
     const int spp = opt.cross_check ? 2 : 1;   // segments per pair
 
-    // ---- segments + batches (host)
-    std::vector<SegDev> segs(static_cast<size_t>(P) * spp);
-    struct Batch { int first_pair, npairs, nunits; };
+    // ---- segments + batches (host).  Per batch the segment table is [forward segments of its pairs][reverse segments]:
+    //      the forward pass runs first; the reverse pass (cross-check only) runs on the train rows the forward pass
+    //      matched, gathered into temporary query images (match_post.cu: gather_candidates_kernel).
+    struct Batch { int first_pair, npairs, units_fwd, units_rev; };
     std::vector<Batch> batches;
+    std::vector<int> slot1(P), slot2(P);
+    int n2_max = 0;
     {
-        Batch cur{0, 0, 0};
+        Batch cur{0, 0, 0, 0};
         for (int p = 0; p < P; ++p) {
             auto i1 = c->slot_of.find(pairs[2 * p]), i2 = c->slot_of.find(pairs[2 * p + 1]);
             if (i1 == c->slot_of.end() || i2 == c->slot_of.end())
                 return c->fail(MSFM_E_NOT_FOUND, "pair %d: image %d or %d not resident", p, pairs[2 * p], pairs[2 * p + 1]);
-            const int s1 = i1->second, s2 = i2->second;
-            const int u12 = c->imgs[s1].n_pad / kUnitRows, u21 = opt.cross_check ? c->imgs[s2].n_pad / kUnitRows : 0;
-            if (cur.npairs > 0 && cur.nunits + u12 + u21 > kMaxUnitsPerBatch) {
+            slot1[p] = i1->second; slot2[p] = i2->second;
+            const int n2 = c->imgs[slot2[p]].n;
+            n2_max = std::max(n2_max, n2);
+            const int u12 = c->imgs[slot1[p]].n_pad / kUnitRows;
+            const int u21 = opt.cross_check ? (n2 + kUnitRows - 1) / kUnitRows : 0;
+            if (cur.npairs > 0 && cur.units_fwd + cur.units_rev + u12 + u21 > kMaxUnitsPerBatch) {
                 batches.push_back(cur);
-                cur = Batch{p, 0, 0};
+                cur = Batch{p, 0, 0, 0};
             }
-            SegDev& a = segs[static_cast<size_t>(p) * spp];
-            a.q_slot = s1; a.t_slot = s2; a.unit_base = cur.nunits; a.n_units = u12;
-            cur.nunits += u12;
-            if (opt.cross_check) {
-                SegDev& b = segs[static_cast<size_t>(p) * spp + 1];
-                b.q_slot = s2; b.t_slot = s1; b.unit_base = cur.nunits; b.n_units = u21;
-                cur.nunits += u21;
-            }
-            cur.npairs += 1;
+            cur.units_fwd += u12; cur.units_rev += u21; cur.npairs += 1;
         }
         if (cur.npairs > 0) batches.push_back(cur);
+    }
+    int max_units = 1, max_pairs = 1;
+    for (const Batch& b : batches) {
+        max_units = std::max(max_units, b.units_fwd + b.units_rev);
+        max_pairs = std::max(max_pairs, b.npairs);
+    }
+    const int first_temp_slot = static_cast<int>(c->imgs.size());
+    std::vector<SegDev> segs(static_cast<size_t>(P) * spp);
+    for (const Batch& b : batches) {
+        SegDev* bs = segs.data() + static_cast<size_t>(b.first_pair) * spp;
+        int ub = 0;
+        for (int k = 0; k < b.npairs; ++k) {
+            const int p = b.first_pair + k;
+            SegDev& a = bs[k];
+            a.q_slot = slot1[p]; a.t_slot = slot2[p]; a.unit_base = ub; a.n_units = c->imgs[slot1[p]].n_pad / kUnitRows;
+            ub += a.n_units;
+        }
+        if (opt.cross_check)
+            for (int k = 0; k < b.npairs; ++k) {
+                const int p = b.first_pair + k;
+                SegDev& r = bs[b.npairs + k];
+                r.q_slot = first_temp_slot + k;          // temporary query image of pair k: matched rows of image 2
+                r.t_slot = slot1[p];
+                r.unit_base = ub;
+                r.n_units = (c->imgs[slot2[p]].n + kUnitRows - 1) / kUnitRows;
+                ub += r.n_units;
+            }
+    }
+    // image table: persistent slots + one temporary entry per pair of a batch
+    {
+        const size_t need = (static_cast<size_t>(first_temp_slot) + max_pairs + 1) * sizeof(ImgDev);
+        if (need > c->d_imgs.cap) {
+            MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
+            MSFM_CUDA(c, c->d_imgs.reserve(need));
+            c->imgs_dirty = true;
+        }
     }
     int rc = sync_img_table(c);
     if (rc) return rc;
     MSFM_CUDA(c, cudaStreamSynchronize(c->stream));   // scratch of an earlier call is free now
 
-    int max_units = 1, max_pairs = 1;
-    for (const Batch& b : batches) { max_units = std::max(max_units, b.nunits); max_pairs = std::max(max_pairs, b.npairs); }
     const size_t rows = static_cast<size_t>(max_units) * kUnitRows;
     const size_t nb = std::max<size_t>(1, batches.size());
     MSFM_CUDA(c, c->d_segs.reserve(std::max<size_t>(1, segs.size()) * sizeof(SegDev)));
@@ -325,14 +364,28 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
     MSFM_CUDA(c, c->d_m.reserve(rows * 5 * sizeof(int32_t)));
     MSFM_CUDA(c, c->d_exact.reserve(rows * sizeof(int32_t)));
     MSFM_CUDA(c, c->d_counts.reserve(static_cast<size_t>(max_pairs) * sizeof(int32_t)));
-    MSFM_CUDA(c, c->d_misc.reserve(16 + nb * 2 * sizeof(unsigned int)));
+    MSFM_CUDA(c, c->d_misc.reserve(16 + nb * 4 * sizeof(unsigned int)));
+    TempImgs T{};
+    if (opt.cross_check && P > 0) {
+        T.n_pad_t = std::max(kUnitRows, (n2_max + kUnitRows - 1) / kUnitRows * kUnitRows);
+        const size_t per = static_cast<size_t>(T.n_pad_t);
+        const size_t sw_bytes = static_cast<size_t>(max_pairs) * per * 128;
+        const size_t arr_bytes = static_cast<size_t>(max_pairs) * per * 4;
+        MSFM_CUDA(c, c->d_temp.reserve(sw_bytes + 3 * arr_bytes + static_cast<size_t>(max_pairs) * 4 + 256));
+        uint8_t* base = c->d_temp.as<uint8_t>();
+        T.sw = base;
+        T.nrm = reinterpret_cast<int32_t*>(base + sw_bytes);
+        T.perm = reinterpret_cast<int32_t*>(base + sw_bytes + arr_bytes);
+        T.flags = reinterpret_cast<int32_t*>(base + sw_bytes + 2 * arr_bytes);
+        T.used = reinterpret_cast<int32_t*>(base + sw_bytes + 3 * arr_bytes);
+    }
     if (!segs.empty())
         MSFM_CUDA(c, cudaMemcpy(c->d_segs.p, segs.data(), segs.size() * sizeof(SegDev), cudaMemcpyHostToDevice));
-    MSFM_CUDA(c, cudaMemsetAsync(c->d_misc.p, 0, 16 + nb * 2 * sizeof(unsigned int), c->stream));
+    MSFM_CUDA(c, cudaMemsetAsync(c->d_misc.p, 0, 16 + nb * 4 * sizeof(unsigned int), c->stream));
 
     long long* running_total = c->d_misc.as<long long>();
     unsigned int* counters = reinterpret_cast<unsigned int*>(c->d_misc.as<uint8_t>() + 16);
-    const ImgDev* d_imgs = c->d_imgs.as<ImgDev>();
+    ImgDev* d_imgs = c->d_imgs.as<ImgDev>();
     int32_t* res_j = c->d_res.as<int32_t>();
     int32_t* res_d1 = res_j + rows;
     int32_t* res_u = res_d1 + rows;
@@ -347,38 +400,57 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
         const Batch& b = batches[bi];
         const SegDev* bsegs = c->d_segs.as<SegDev>() + static_cast<size_t>(b.first_pair) * spp;
         UnitDev* units = c->d_units.as<UnitDev>();
-        unsigned int* bcnt = counters + 2 * bi;
+        const int nunits = b.units_fwd + b.units_rev;
+        unsigned int* bcnt = counters + 4 * bi;         // [0,1] forward pass: exact rows, rescans; [2,3] reverse pass
+        if (opt.cross_check) {
+            MSFM_CUDA(c, launch_setup_temp_imgs(d_imgs, first_temp_slot, bsegs, b.npairs, T, c->stream));
+            // reverse rows that are never computed (train rows nobody matched) must read as "no match"
+            MSFM_CUDA(c, cudaMemsetAsync(m_j, 0xFF, static_cast<size_t>(nunits) * kUnitRows * sizeof(int32_t), c->stream));
+            c->launches += 1;
+        }
         c->prof_begin(MSFM_PROF_BUILD_UNITS);
-        MSFM_CUDA(c, launch_build_units(bsegs, b.npairs * spp, b.nunits, units, c->stream));
+        MSFM_CUDA(c, launch_build_units(bsegs, b.npairs * spp, nunits, units, c->stream));
         c->prof_end();
         if (mode == 0) {
-            c->prof_begin(MSFM_PROF_MATCH_TILE);
-            MSFM_CUDA(c, launch_match_tile_kernel(d_imgs, units, b.nunits, res_j, res_d1, res_u, c->num_sms, c->stream));
-            c->prof_end();
-            c->prof_begin(MSFM_PROF_RESOLVE);
-            MSFM_CUDA(c, launch_resolve_rows(d_imgs, units, b.nunits, res_j, res_d1, res_u, opt, m_j, m_d1, m_d2, m_j0,
-                                             c->d_exact.as<int32_t>(), bcnt, c->stream));
-            c->prof_end();
-            c->prof_begin(MSFM_PROF_EXACT);
-            MSFM_CUDA(c, launch_exact_rows(d_imgs, units, c->d_exact.as<int32_t>(), bcnt, -1, opt, m_j, m_d1, m_d2, m_j0,
-                                           c->num_sms, c->stream));
-            c->prof_end();
-            c->launches += (b.nunits > 0 ? 4 : 1);
+            for (int pass = 0; pass < (opt.cross_check ? 2 : 1); ++pass) {
+                const int u0 = pass == 0 ? 0 : b.units_fwd;
+                const int nu = pass == 0 ? b.units_fwd : b.units_rev;
+                if (pass == 1) {
+                    c->prof_begin(MSFM_PROF_COMPACT);
+                    MSFM_CUDA(c, launch_gather_candidates(d_imgs, bsegs, b.npairs, m_j, T, c->stream));
+                    c->prof_end();
+                    c->launches += 1;
+                }
+                c->prof_begin(MSFM_PROF_MATCH_TILE);
+                MSFM_CUDA(c, launch_match_tile_kernel(d_imgs, units, u0, nu, res_j, res_d1, res_u, c->num_sms, c->stream));
+                c->prof_end();
+                c->prof_begin(MSFM_PROF_RESOLVE);
+                MSFM_CUDA(c, launch_resolve_rows(d_imgs, units, u0, nu, res_j, res_d1, res_u, opt, m_j, m_d1, m_d2, m_j0,
+                                                 c->d_exact.as<int32_t>(), bcnt + 2 * pass, c->stream));
+                c->prof_end();
+                c->prof_begin(MSFM_PROF_EXACT);
+                MSFM_CUDA(c, launch_exact_rows(d_imgs, units, c->d_exact.as<int32_t>(), bcnt + 2 * pass, -1, opt, m_j, m_d1,
+                                               m_d2, m_j0, c->num_sms, c->stream));
+                c->prof_end();
+                c->launches += (nu > 0 ? 3 : 1);
+            }
         } else {
+            // exact CUDA-core scan of every row (knn2 parity API; never combined with cross-check)
             c->prof_begin(MSFM_PROF_EXACT);
-            MSFM_CUDA(c, launch_exact_rows(d_imgs, units, nullptr, nullptr, b.nunits * kUnitRows, opt, m_j, m_d1, m_d2, m_j0,
+            MSFM_CUDA(c, launch_exact_rows(d_imgs, units, nullptr, nullptr, nunits * kUnitRows, opt, m_j, m_d1, m_d2, m_j0,
                                            c->num_sms, c->stream));
             c->prof_end();
-            c->launches += 2;
+            c->launches += 1;
         }
+        c->launches += 1;
         c->prof_begin(MSFM_PROF_COMPACT);
         MSFM_CUDA(c, launch_count_scan_write(d_imgs, bsegs, b.npairs, opt, m_j, m_d1, c->d_counts.as<int32_t>(),
                                              out_offsets_dev + b.first_pair, running_total, capacity, out_matches_dev,
                                              out_dist_dev, c->stream));
         c->prof_end();
         c->launches += 3;
-        total_units += b.nunits;
-        total_rows += static_cast<int64_t>(b.nunits) * kUnitRows;
+        total_units += nunits;
+        total_rows += static_cast<int64_t>(nunits) * kUnitRows;
         if (dump && bi == 0 && dump->n > 0) {
             MSFM_CUDA(c, cudaMemcpyAsync(dump->j0, m_j0, static_cast<size_t>(dump->n) * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
             MSFM_CUDA(c, cudaMemcpyAsync(dump->d1, m_d1, static_cast<size_t>(dump->n) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -386,13 +458,13 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
         }
     }
     // ---- totals (one small readback; this is the call's only host<->device sync besides the entry one)
-    MSFM_CUDA(c, c->h_stage.reserve(16 + nb * 2 * sizeof(unsigned int)));
-    MSFM_CUDA(c, cudaMemcpyAsync(c->h_stage.p, c->d_misc.p, 16 + nb * 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    MSFM_CUDA(c, c->h_stage.reserve(16 + nb * 4 * sizeof(unsigned int)));
+    MSFM_CUDA(c, cudaMemcpyAsync(c->h_stage.p, c->d_misc.p, 16 + nb * 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
     MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
     const long long total = *c->h_stage.as<long long>();
     const unsigned int* hc = reinterpret_cast<const unsigned int*>(c->h_stage.as<uint8_t>() + 16);
     int64_t n_exact = 0, n_rescan = 0;
-    for (size_t bi = 0; bi < batches.size(); ++bi) { n_exact += hc[2 * bi]; n_rescan += hc[2 * bi + 1]; }
+    for (size_t bi = 0; bi < batches.size(); ++bi) { n_exact += hc[4 * bi] + hc[4 * bi + 2]; n_rescan += hc[4 * bi + 1] + hc[4 * bi + 3]; }
     c->stats[0] = total_rows; c->stats[1] = n_rescan; c->stats[2] = n_exact; c->stats[3] = total_units;
     if (total_out) *total_out = total;
     if (total > capacity) return c->fail(MSFM_E_CAPACITY, "output capacity %lld < %lld matches", capacity, total);

@@ -255,7 +255,7 @@ resolve_rows_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// Exact scan: one warp per listed row, all train columns, OpenCV order = (sqrtf(d2), ORIGINAL column) lexicographic.
+// Exact scan of listed rows over all train columns, OpenCV order = (sqrtf(d2), ORIGINAL column) lexicographic.
 struct Top2 {
     int32_t d0, j0, d1, j1;
 };
@@ -273,6 +273,8 @@ __device__ __forceinline__ void top2_insert(Top2& s, int32_t d, int32_t j) {
     }
 }
 
+// One CTA per listed row (8 warps split the columns; a lone warp per row is latency-bound on ~260 dependent
+// load rounds).
 __global__ void __launch_bounds__(256)
 exact_rows_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ units,
                   const int32_t* __restrict__ row_list, const unsigned int* __restrict__ row_count_dev,
@@ -280,20 +282,21 @@ exact_rows_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
                   int32_t* __restrict__ m_j, int32_t* __restrict__ m_d1, int32_t* __restrict__ m_d2,
                   int32_t* __restrict__ m_j0) {
     const int nrows = row_count_host >= 0 ? row_count_host : static_cast<int>(*row_count_dev);
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
-    for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < nrows; w += gridDim.x * wpb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ Top2 part[8];
+    for (int w = blockIdx.x; w < nrows; w += gridDim.x) {
         const size_t g = row_list ? static_cast<size_t>(row_list[w]) : static_cast<size_t>(w);
         const int u = static_cast<int>(g / kUnitRows);
         const UnitDev unit = units[u];
         const ImgDev q = imgs[unit.q_slot];
         const ImgDev t = imgs[unit.t_slot];
         const int qp = unit.row_block * kUnitRows + static_cast<int>(g % kUnitRows);
-        const int qorig = q.perm[qp];
+        const int qorig = (q.used && qp < __ldg(q.used)) ? q.perm[qp] : -1;      // block-uniform
         if (qorig < 0) continue;
         const size_t o = static_cast<size_t>(u - unit.row_block) * kUnitRows + qorig;
+        const int tcols = t.used ? __ldg(t.used) : 0;
         Top2 s{kIntInf, -1, kIntInf, -1};
-        for (int col = lane; col < t.n_pad; col += 32) {
+        for (int col = threadIdx.x; col < tcols; col += blockDim.x) {
             const int corig = t.perm[col];
             if (corig >= 0) top2_insert(s, sqdist_rows(q.sw, qp, t.sw, col), corig);
         }
@@ -307,14 +310,22 @@ exact_rows_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
             top2_insert(s, other.d0, other.j0);
             top2_insert(s, other.d1, other.j1);
         }
-        if (lane == 0) {
+        __syncthreads();                       // part[] of the previous row has been consumed
+        if (lane == 0) part[warp] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Top2 r = part[0];
+            for (int k = 1; k < (blockDim.x >> 5); ++k) {
+                top2_insert(r, part[k].d0, part[k].j0);
+                top2_insert(r, part[k].d1, part[k].j1);
+            }
             int32_t mj = -1;
-            if (s.j0 >= 0 && s.j1 >= 0 && ratio_pass(s.d0, s.d1, opt.ratio)) mj = s.j0;
+            if (r.j0 >= 0 && r.j1 >= 0 && ratio_pass(r.d0, r.d1, opt.ratio)) mj = r.j0;
             m_j[o] = mj;
-            m_d1[o] = s.j0 >= 0 ? s.d0 : kIntInf;
-            m_d2[o] = s.j1 >= 0 ? s.d1 : kIntInf;
-            m_j0[2 * o] = s.j0;
-            m_j0[2 * o + 1] = s.j1;
+            m_d1[o] = r.j0 >= 0 ? r.d0 : kIntInf;
+            m_d2[o] = r.j1 >= 0 ? r.d1 : kIntInf;
+            m_j0[2 * o] = r.j0;
+            m_j0[2 * o + 1] = r.j1;
         }
     }
 }
@@ -612,7 +623,7 @@ cudaError_t launch_resolve_rows(const ImgDev* imgs, const UnitDev* units, int un
 cudaError_t launch_exact_rows(const ImgDev* imgs, const UnitDev* units, const int32_t* row_list,
                               const unsigned int* row_count_dev, int row_count_host, MatchOpts opt, int32_t* m_j,
                               int32_t* m_d1, int32_t* m_d2, int32_t* m_j0, int num_sms, cudaStream_t st) {
-    exact_rows_kernel<<<num_sms * 4, 256, 0, st>>>(imgs, units, row_list, row_count_dev, row_count_host, opt, m_j, m_d1,
+    exact_rows_kernel<<<num_sms * 8, 256, 0, st>>>(imgs, units, row_list, row_count_dev, row_count_host, opt, m_j, m_d1,
                                                    m_d2, m_j0);
     return cudaGetLastError();
 }

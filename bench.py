@@ -446,8 +446,16 @@ def run_ours(args, rank, world, local_rank):
         alg_ops_per_launch = float(P) * n * n * 256.0 * args.steps / steps_launches
         achieved = alg_ops_per_launch / k1_avg_s / 1e12 if k1_avg_s > 0 else 0.0
         peak_int8 = 2.0 * peaks["bf16_tflops_sustained"]
+        # DRAM traffic of one K1 launch of this workload, from the committed `ncu --set full` capture (bytes; null if absent)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         roofline = {"bound": "tensor", "kernel": "match_tile_kernel", "achieved": achieved, "peak": peak_int8,
-                    "unit": "TOP/s", "frac": achieved / peak_int8 if peak_int8 else None, "traffic": None,
+                    "unit": "TOP/s", "frac": achieved / peak_int8 if peak_int8 else None, "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "peak_note": f"2 x cuBLAS bf16 sustained ({peaks['bf16_tflops_sustained']} TF/s, {peaks['source']} "
                                  "MEASURED_PEAKS.json): int8 tcgen05 runs at twice the bf16 rate; no int8 GEMM peak is measured",
                     "executed_tensor_ops_frac": 2.0 * achieved / peak_int8 if peak_int8 else None,

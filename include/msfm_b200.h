@@ -91,7 +91,8 @@ int msfm_prof_read(msfm_ctx* ctx, double ms[MSFM_PROF_NCAT], int64_t launches[MS
 
 /* Upload (or replace) the descriptor set of one image and keep it resident on the device.
  * Replaces the per-pair Database::ReadDescriptors of FeatureMatching.cpp:32-33 (TODO "cache" at :31).
- * n may be 0.  image_id >= 0 (image_t, Common/Types.h:9). */
+ * n may be 0.  image_id >= 0 (image_t, Common/Types.h:9).  The copy is queued on the ctx stream: a PINNED host buffer
+ * must stay valid until the next msfm_sync / matching call returns (pageable memory is staged immediately). */
 int msfm_desc_upload_u8(msfm_ctx* ctx, int32_t image_id, const uint8_t* desc_host, int32_t n);
 /* Same, source already in device memory (synthetic-data benchmarks; inputs resident in HBM). */
 int msfm_desc_upload_u8_dev(msfm_ctx* ctx, int32_t image_id, const uint8_t* desc_dev, int32_t n);

@@ -7,7 +7,7 @@ import traceback
 
 import numpy as np
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import monocularsfm_b200 as m  # noqa: E402
 from oracle import match_oracle as mo  # noqa: E402
 

@@ -63,7 +63,7 @@ struct msfm_ctx {
     msfm::GrowBuf d_fmt;                           // upload formatting scratch (sort keys, ranks)
     msfm::GrowBuf d_temp;                          // temporary query images of the reverse (cross-check) pass
     msfm::GrowBuf h_stage;                         // pinned host staging (segments, offsets readback)
-    msfm::GrowBuf d_segs, d_units, d_res, d_m, d_exact, d_counts, d_misc;
+    msfm::GrowBuf d_segs, d_units, d_items, d_res, d_m, d_exact, d_counts, d_misc;
     msfm::GrowBuf d_out_offsets, d_out_matches, d_out_dist;
     msfm::GrowBuf d_ba_r, d_ba_J;                  // msfm_ba_evaluate parity dumps
     int64_t stats[4] = {0, 0, 0, 0};

@@ -1,27 +1,42 @@
-// K1 — match_tile_kernel: tcgen05 u8 x u8 -> s32 score tiles with a fused per-row top-2 reduction.
+// K1 — match_pair_kernel: tcgen05 u8 x u8 -> s32 score tiles with a fused per-row top-2 reduction, CTA-pair version.
 //
 // Replaces the arithmetic of OpenCV's batchDistance + k-NN update that the reference reaches through
 // FeatureUtils::ComputeMatches (src/Feature/FeatureUtils.cpp:146-149, knnMatch k=2).
 //
-// Work unit = 128 query rows (one UMMA M=128 tile, resident in smem) against ALL columns of the train image,
-// streamed as 256-column tiles (UMMA N=256).  Per tile the tensor core runs FIVE tcgen05.mma.kind::i8 (K = 32 bytes
-// each): four over the 128 descriptor bytes and one over the 32 "extension" bytes that add e_j = (C_g - ||d_j||^2)/2
-// to every column (match_types.cuh), so the accumulator is  acc(i,j) = q_i.d_j + e_j  and, inside a 32-column group,
+// Work item = TWO consecutive 128-row units of a segment (256 query rows) against ALL columns of the train image,
+// streamed as 256-column tiles, executed by a cluster of two CTAs on the two SMs of a TPC with
+// tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 32 bytes): CTA r keeps the query rows of unit u+r and loads only
+// columns 128r..128r+127 of every train tile; the tensor cores of the pair exchange the halves, and CTA r receives
+// the 128 x 256 accumulator block of its own rows in its own TMEM.  Per tile FIVE MMAs: four over the 128 descriptor
+// bytes and one over the 32 "extension" bytes that add e_j = (C_g - ||d_j||^2)/2 to every column (match_types.cuh),
+// so the accumulator is  acc(i,j) = q_i.d_j + e_j  and, inside a 32-column group,
 //     C_g - 2 * max_j acc(i,j) = min_j (||d_j||^2 - 2 q_i.d_j) = min_j d2(i,j) - ||q_i||^2 .
 // The epilogue therefore needs ONE integer max per two elements (VIMNMX3) and no per-column constants.
-// Persistent CTAs (one per SM) walk the unit table with stride gridDim.x.
 //
-// Warp roles (384 threads):
-//   warp 0      bulk-copy producer (cp.async.bulk = TMA engine, one elected lane): query tile, train tiles,
-//               extension super-tiles (one per 4 train tiles)
-//   warps 1-2   TWO MMA issuers (one elected lane each): issuer w owns the tiles with (tile counter & 1) == w, i.e. the
-//               accumulator stage w.  Measured on B200 (profiles/r01_microbench_mma_patterns.log): one pass of an
-//               issuer's loop (mbarrier waits + 5 MMAs + commits) has ~1000-1250 cycles of latency that only overlaps
-//               with >= ~1300 cycles of queued tensor work; a single issuer therefore caps a 640-cycle tile at ~1030
-//               cycles (versions 1-4 of this kernel all sat there).  Several issuers interleave their latency chains.
-//   warp 2      also the TMEM allocator
+// Why a CTA pair: the single-CTA kernel (match_k1_single.cu, 128 x 256 tiles) moves, per 640 tensor cycles and SM,
+// 40 KB L2 -> smem plus 60 KB smem -> tensor core, i.e. 156 B/clk against the 128 B/clk of an SM's shared memory, and
+// 9.4 KB/clk chip-wide against the ~6.3-6.9 KB/clk the L2 delivers (profiles/r01_k1_bench_launch_ncu_raw.csv:
+// 12.9 TB/s at 73 % tensor-pipe utilisation).  Sharing every train tile between two SMs halves both.
+//
+// Warp roles per CTA (384 threads):
+//   warp 0      bulk-copy producer (cp.async.bulk = TMA engine, one elected lane): this CTA's query rows, its half of
+//               every train tile and of every extension super-tile (one per 4 train tiles)
+//   warps 1-2   leader CTA (rank 0): TWO MMA issuers (one elected lane each); issuer w owns the tiles with
+//               (tile counter & 1) == w, i.e. accumulator stage w (one issuer's loop of mbarrier waits + MMAs + commits
+//               has ~1000-1250 cycles of latency, profiles/r01_microbench_mma_patterns.log; two interleave).
+//               peer CTA (rank 1): warp 1 relays "my half has landed" from its own full-barriers to the leader's
+//               (a 1-D bulk copy can only signal an mbarrier of the CTA it writes to).
+//   warp 2      also the TMEM allocator (both CTAs, cta_group::2 form)
 //   warps 4-11  epilogue: two warpgroups, each owns 128 of a tile's 256 columns; thread = query row
 //               (tcgen05.ld 32x32b: lane <-> row), so the row-wise reduction is thread-local.
+//
+// Barriers (every CTA has the full set at the same shared-memory offsets; tcgen05.commit multicasts to both):
+//   a_full/b_full/e_full   leader: 2 arrivals (own producer + peer relay); peer: 1 (own producer)
+//   done[tile % 12]        ONE commit per tile by the issuer that owns it, multicast to both CTAs: it publishes the
+//                          accumulator stage to the epilogues and tells the producers that the tile's smem stage (and,
+//                          after a super-tile's last tile, the extension stage) may be refilled
+//   a_empty                commits of both issuers after a unit pair's last tile, multicast
+//   t_empty                leader only: 16 arrivals (8 epilogue warps of each CTA)
 //
 // Output per row (sorted space of the query image): g1 = group holding the best column, d1 = exact squared distance of
 // the best column, u = exact squared distance of the best column of any OTHER group.  match_post.cu finds the best
@@ -30,27 +45,31 @@
 // (d1 >= 2^22) with the exact scan.
 #include "match_types.cuh"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace msfm {
+
+cudaError_t launch_match_tile_single(const ImgDev*, const UnitDev*, int, int, int32_t*, int32_t*, int32_t*, int, cudaStream_t);
+
 namespace k1 {
 
-constexpr int BM = kUnitRows;                // 128 query rows per unit (UMMA M)
+constexpr int BM = kUnitRows;                // 128 query rows per CTA (one unit); UMMA M = 256 over the pair
 constexpr int BN = 256;                      // train columns per tile (UMMA N)
+constexpr int HN = BN / 2;                   // columns of a tile this CTA loads
 constexpr int KBYTES = 128;
 constexpr int UMMA_KB = 32;                  // bytes of K per tcgen05.mma.kind::i8
-constexpr int NS = 3;                        // smem stages of the train-tile ring
+constexpr int NS = 6;                        // smem stages of the train-tile ring
 constexpr int NE = 2;                        // smem stages of the extension super-tile ring (one per 4 tiles)
 constexpr uint32_t A_BYTES = BM * KBYTES;    // 16 KiB
-constexpr uint32_t B_BYTES = BN * KBYTES;    // 32 KiB
-constexpr uint32_t E_BYTES = BN * 128;       // 32 KiB: extension bytes of 4 consecutive tiles
+constexpr uint32_t B_BYTES = HN * KBYTES;    // 16 KiB: this CTA's half of a train tile
+constexpr uint32_t E_BYTES = HN * 128;       // 16 KiB: this CTA's half of an extension super-tile
 constexpr int NUM_THREADS = 384;
-constexpr int NUM_ISSUERS = 2;               // warps 1, 2.  MUST equal the number of accumulator stages: with more
-                                             // issuers than stages two of them race for the same stage's parity-tracked
-                                             // t_empty barrier (seen as a deadlock, caught by the mbarrier watchdog)
+constexpr int NUM_ISSUERS = 2;               // warps 1, 2 of the leader.  MUST equal the number of accumulator stages
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-static_assert(BM == 128, "one UMMA M=128 tile per unit");
+constexpr uint16_t BOTH_CTAS = 0b11;
+static_assert(BM == 128, "one UMMA M=128 half per CTA");
 static_assert(NUM_ISSUERS == 2, "one issuer per accumulator stage");
 
 constexpr uint32_t OFF_A = 0;
@@ -59,7 +78,8 @@ constexpr uint32_t OFF_B = OFF_AEXT + A_BYTES;
 constexpr uint32_t OFF_E = OFF_B + NS * B_BYTES;
 constexpr uint32_t OFF_MERGE = OFF_E + NE * E_BYTES;            // [2][128] int4 (k1,k2,group,-)
 constexpr uint32_t OFF_BAR = OFF_MERGE + 2 * 128 * 16;
-constexpr uint32_t NUM_BARS = 2 + 2 + NS + NS + NE + NE + 2 + 2;
+constexpr int ND = 2 * NS;                   // ring of per-tile "MMAs done" barriers
+constexpr uint32_t NUM_BARS = 2 + 2 + NS + NE + ND + 2;
 constexpr uint32_t OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
 constexpr uint32_t SMEM_USED = OFF_TMEMPTR + 16;
 constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;               // slack for manual 1024-B alignment
@@ -70,11 +90,73 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 // occupied sorted positions of an image (0 for an empty image, which has no device block)
 __device__ __forceinline__ int img_used(const ImgDev& im) { return im.used ? __ldg(im.used) : 0; }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ units, int unit0, int num_units,
-                  int32_t* __restrict__ res_g, int32_t* __restrict__ res_d1, int32_t* __restrict__ res_u) {
+// Flat work item of one unit pair, written by build_items_kernel right before the tensor kernel.  Every role prefetches
+// the NEXT item while it works on the current one: resolving units[u] -> imgs[slot] -> *used on the fly is a chain of
+// three dependent global loads (~2000 cycles) per pair in every role — with only two accumulator stages (1280 tensor
+// cycles) queued behind the issuers, that chain was a bubble per pair that no per-tile tuning could remove.
+struct __align__(16) ItemSrc {     // producer
+    const uint8_t* q_rows;         // sorted-space rows of the pair's first unit (the second follows at +A_BYTES)
+    const uint8_t* t_sw;
+    const uint8_t* t_ext;
+    uint64_t pad;
+};
+struct __align__(16) ItemEpi {     // epilogue
+    const int32_t* t_cg;
+    const int32_t* q_nrm;          // ||q||^2 of the first unit's rows (second at +BM)
+};
+struct __align__(16) ItemCtl {     // every role
+    int32_t tcols;                 // occupied columns of the train image
+    int32_t live;                  // live units of the pair: 0 (skip), 1, 2
+    int32_t unit;                  // index of the first unit (K1 result slot = unit * BM + row)
+    int32_t pad;
+};
+struct __align__(16) Item {
+    ItemSrc src;
+    ItemEpi epi;
+    ItemCtl ctl;
+};
+static_assert(sizeof(Item) == 64 && sizeof(ItemSrc) == 32 && sizeof(ItemEpi) == 16 && sizeof(ItemCtl) == 16, "item layout");
+
+template <typename T>
+__device__ __forceinline__ T load_part(const T* p) {     // 16-byte read-only loads
+    T out;
+    const int4* s = reinterpret_cast<const int4*>(p);
+    int4* d = reinterpret_cast<int4*>(&out);
+#pragma unroll
+    for (int i = 0; i < static_cast<int>(sizeof(T) / 16); ++i) d[i] = __ldg(s + i);
+    return out;
+}
+
+__global__ void build_items_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ units, int unit0,
+                                   int num_items, Item* __restrict__ items) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_items) return;
+    const int u = unit0 + 2 * i;
+    const UnitDev unit = units[u];
+    const ImgDev q = imgs[unit.q_slot];
+    const ImgDev t = imgs[unit.t_slot];
+    const int qused = img_used(q);
+    Item it;
+    it.src.q_rows = q.sw + static_cast<size_t>(unit.row_block) * A_BYTES;
+    it.src.t_sw = t.sw;
+    it.src.t_ext = t.ext;
+    it.src.pad = 0;
+    it.epi.t_cg = t.cg;
+    it.epi.q_nrm = q.nrm + static_cast<size_t>(unit.row_block) * BM;
+    it.ctl.tcols = img_used(t);
+    it.ctl.live = unit.row_block * BM >= qused ? 0 : ((unit.row_block + 1) * BM < qused ? 2 : 1);
+    it.ctl.unit = u;
+    it.ctl.pad = 0;
+    items[i] = it;
+}
+
+// Units come in pairs (u, u+1) of the same segment: the host makes every segment an even number of units.
+// A pair is skipped by every role of both CTAs when its FIRST unit is all dead rows.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __restrict__ res_g,
+                  int32_t* __restrict__ res_d1, int32_t* __restrict__ res_u, long long* __restrict__ dbg, int dbg_mode) {
     extern __shared__ uint8_t smem_raw[];
-    // manual 1 KiB alignment (dynamic smem is only guaranteed 16-B aligned)
+    // manual 1 KiB alignment (dynamic smem is only guaranteed 16-B aligned); both CTAs of the pair get the same offset
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
@@ -85,17 +167,17 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
     int4* smMerge = reinterpret_cast<int4*>(smem + OFF_MERGE);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* a_full = bars;            // [2]
-    uint64_t* a_empty = a_full + 2;     // [2]   count NUM_ISSUERS
+    uint64_t* a_empty = a_full + 2;     // [2]
     uint64_t* b_full = a_empty + 2;     // [NS]
-    uint64_t* b_empty = b_full + NS;    // [NS]  count 1: the owning issuer's commit
-    uint64_t* e_full = b_empty + NS;    // [NE]
-    uint64_t* e_empty = e_full + NE;    // [NE]  count NUM_ISSUERS
-    uint64_t* t_full = e_empty + NE;    // [2]
-    uint64_t* t_empty = t_full + 2;     // [2]   count 8: epilogue warps
+    uint64_t* e_full = b_full + NS;     // [NE]
+    uint64_t* done = e_full + NE;       // [ND]  tile `it` -> done[it % ND]
+    uint64_t* t_empty = done + ND;      // [2]   used in the leader only
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEMPTR);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();          // 0 = leader
+    const bool leader = rank == 0;
 
     // constant A-side extension tile: every row is (1, 255 x 31, 0 ...) in the swizzled layout
     for (int i = threadIdx.x; i < BM * 8; i += NUM_THREADS) {
@@ -109,75 +191,125 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
     ptx::fence_proxy_async();            // generic-proxy writes -> visible to the tensor core (async proxy)
 
     if (warp == 1 && lane == 0) {
+        const uint32_t full_count = leader ? 2u : 1u;       // own producer (+ the peer's relay)
         for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(&a_full[i], 1);
+            ptx::mbar_init(&a_full[i], full_count);
             ptx::mbar_init(&a_empty[i], NUM_ISSUERS);
-            ptx::mbar_init(&t_full[i], 1);
-            ptx::mbar_init(&t_empty[i], EPI_WARPS);
+            ptx::mbar_init(&t_empty[i], 2 * EPI_WARPS);
         }
-        for (int i = 0; i < NS; ++i) {
-            ptx::mbar_init(&b_full[i], 1);
-            ptx::mbar_init(&b_empty[i], 1);
-        }
-        for (int i = 0; i < NE; ++i) {
-            ptx::mbar_init(&e_full[i], 1);
-            ptx::mbar_init(&e_empty[i], NUM_ISSUERS);
-        }
+        for (int i = 0; i < NS; ++i) ptx::mbar_init(&b_full[i], full_count);
+        for (int i = 0; i < NE; ++i) ptx::mbar_init(&e_full[i], full_count);
+        for (int i = 0; i < ND; ++i) ptx::mbar_init(&done[i], 1);
         ptx::fence_mbar_init();
     }
-    if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
+    if (warp == 2) ptx::tmem_alloc_pair<512>(tmem_ptr);
     ptx::tc_fence_before();
-    __syncthreads();
+    ptx::cluster_sync();                 // barriers of BOTH CTAs are initialised before anyone arrives remotely
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const int i_first = static_cast<int>(ptx::cluster_id_x());
+    const int i_step = static_cast<int>(ptx::num_clusters_x());
 
     if (warp == 0) {
-        // ===================================================================== producer
+        // ===================================================================== producer (both CTAs, own halves)
         if (lane == 0) {
             uint32_t it = 0, un = 0, et = 0;
-            for (int u = unit0 + blockIdx.x; u < unit0 + num_units; u += gridDim.x) {
-                const UnitDev unit = units[u];
-                const ImgDev q = imgs[unit.q_slot];
-                const ImgDev t = imgs[unit.t_slot];
-                if (unit.row_block * BM >= img_used(q)) continue;      // all-dead query rows: every role skips the unit
-                const uint32_t cu = un++;                              // index among the units this CTA really processes
+            uint32_t ext_last[NE] = {0, 0};                            // last tile (global counter) that reads each ext stage
+            ItemSrc nsrc{};
+            ItemCtl nctl{};
+            if (i_first < num_items) { nsrc = load_part(&items[i_first].src); nctl = load_part(&items[i_first].ctl); }
+            for (int i = i_first; i < num_items; i += i_step) {
+                const ItemSrc src = nsrc;
+                const ItemCtl ctl = nctl;
+                if (i + i_step < num_items) {                          // in flight while this pair is fed
+                    nsrc = load_part(&items[i + i_step].src);
+                    nctl = load_part(&items[i + i_step].ctl);
+                }
+                // all-dead query rows: every role skips the pair.  An empty train image needs no operands either (only the
+                // epilogue acts, writing "no match"): loading A for it would let this producer lap the peer's relay, which
+                // is otherwise throttled through the issuers' a_full waits
+                if (ctl.live == 0 || ctl.tcols == 0) continue;
+                const uint32_t cu = un++;                              // index among the pairs this cluster really processes
                 const uint32_t ab = cu & 1;
                 ptx::mbar_wait(&a_empty[ab], ((cu >> 1) & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(&a_full[ab], A_BYTES);
-                ptx::bulk_g2s(smA + ab * A_BYTES, q.sw + static_cast<size_t>(unit.row_block) * A_BYTES, A_BYTES,
-                              &a_full[ab]);
-                const int ntiles = (img_used(t) + BN - 1) / BN;          // tiles beyond the occupied columns are skipped
+                ptx::bulk_g2s(smA + ab * A_BYTES, src.q_rows + rank * A_BYTES, A_BYTES, &a_full[ab]);
+                const int ntiles = (ctl.tcols + BN - 1) / BN;            // tiles beyond the occupied columns are skipped
                 for (int tile = 0; tile < ntiles; ++tile, ++it) {
                     if ((tile & 3) == 0) {
                         const uint32_t es = et % NE;
-                        ptx::mbar_wait(&e_empty[es], ((et / NE) & 1) ^ 1);
+                        if (et >= NE) {                    // the stage's previous super-tile: wait for its last tile's MMAs
+                            const uint32_t l = ext_last[es];
+                            ptx::mbar_wait(&done[l % ND], (l / ND) & 1);
+                        }
+                        ext_last[es] = it + static_cast<uint32_t>(min(4, ntiles - tile)) - 1;
                         ptx::mbar_arrive_expect_tx(&e_full[es], E_BYTES);
-                        ptx::bulk_g2s(smE + es * E_BYTES, t.ext + static_cast<size_t>(tile >> 2) * E_BYTES, E_BYTES, &e_full[es]);
+                        ptx::bulk_g2s(smE + es * E_BYTES, src.t_ext + (static_cast<size_t>(tile >> 2) * 2 + rank) * E_BYTES, E_BYTES,
+                                      &e_full[es]);
                         ++et;
                     }
                     const uint32_t s = it % NS;
-                    const uint32_t ph = (it / NS) & 1;
-                    ptx::mbar_wait(&b_empty[s], ph ^ 1);
+                    if (it >= NS) {                        // the stage's previous tile, it - NS: wait for its MMAs
+                        const uint32_t l = it - NS;
+                        ptx::mbar_wait(&done[l % ND], (l / ND) & 1);
+                    }
                     ptx::mbar_arrive_expect_tx(&b_full[s], B_BYTES);
-                    ptx::bulk_g2s(smB + s * B_BYTES, t.sw + static_cast<size_t>(tile) * B_BYTES, B_BYTES, &b_full[s]);
+                    ptx::bulk_g2s(smB + s * B_BYTES, src.t_sw + (static_cast<size_t>(tile) * 2 + rank) * B_BYTES, B_BYTES, &b_full[s]);
+                }
+            }
+            // drain: every multicast commit aimed at this CTA's a_empty barriers has landed before the CTA may exit
+            // (the epilogue waits for every done[] arrival)
+            for (uint32_t i = 0; i < 2; ++i, ++un) ptx::mbar_wait(&a_empty[un & 1], ((un >> 1) & 1) ^ 1);
+        }
+    } else if (warp == 1 && !leader) {
+        // ===================================================================== relay (peer CTA): my half has landed
+        if (lane == 0) {
+            uint32_t it = 0, un = 0, et = 0;
+            ItemCtl nctl{};
+            if (i_first < num_items) nctl = load_part(&items[i_first].ctl);
+            for (int i = i_first; i < num_items; i += i_step) {
+                const ItemCtl ctl = nctl;
+                if (i + i_step < num_items) nctl = load_part(&items[i + i_step].ctl);
+                if (ctl.live == 0 || ctl.tcols == 0) continue;
+                const uint32_t cu = un++;
+                const uint32_t ab = cu & 1;
+                ptx::mbar_wait(&a_full[ab], (cu >> 1) & 1);
+                ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&a_full[ab]), 0));
+                const int ntiles = (ctl.tcols + BN - 1) / BN;
+                for (int tile = 0; tile < ntiles; ++tile, ++it) {
+                    if ((tile & 3) == 0) {
+                        const uint32_t es = et % NE;
+                        ptx::mbar_wait(&e_full[es], (et / NE) & 1);
+                        ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&e_full[es]), 0));
+                        ++et;
+                    }
+                    const uint32_t s = it % NS;
+                    ptx::mbar_wait(&b_full[s], (it / NS) & 1);
+                    ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&b_full[s]), 0));
                 }
             }
         }
-    } else if (warp >= 1 && warp <= NUM_ISSUERS) {
-        // ===================================================================== MMA issuers
+    } else if (warp >= 1 && warp <= NUM_ISSUERS && leader) {
+        // ===================================================================== MMA issuers (leader CTA)
         if (lane == 0) {
             const uint32_t me = static_cast<uint32_t>(warp - 1);   // owns the tiles with it % NUM_ISSUERS == me
-            constexpr uint32_t idesc = ptx::make_idesc_u8(BM, BN);
+            constexpr uint32_t idesc = ptx::make_idesc_u8(2 * BM, BN);
             const uint64_t aext_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smAext));
             uint32_t it = 0, un = 0, et = 0;
-            for (int u = unit0 + blockIdx.x; u < unit0 + num_units; u += gridDim.x) {
-                const UnitDev unit = units[u];
-                const ImgDev t = imgs[unit.t_slot];
-                if (unit.row_block * BM >= img_used(imgs[unit.q_slot])) continue;
+            long long dbg_c0 = 0, dbg_t0 = 0;
+            if (dbg && me == 0) {
+                dbg_c0 = clock64();
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+            }
+            ItemCtl nctl{};
+            if (i_first < num_items) nctl = load_part(&items[i_first].ctl);
+            for (int i = i_first; i < num_items; i += i_step) {
+                const ItemCtl ctl = nctl;
+                if (i + i_step < num_items) nctl = load_part(&items[i + i_step].ctl);
+                if (ctl.live == 0 || ctl.tcols == 0) continue;
                 const uint32_t cu = un++;
                 const uint32_t ab = cu & 1;
-                const int tcols = img_used(t);
-                const int ntiles = (tcols + BN - 1) / BN;
+                const int ntiles = (ctl.tcols + BN - 1) / BN;
                 bool have_a = false, have_e = false;
                 uint64_t a_desc0 = 0;
                 for (int tile = 0; tile < ntiles; ++tile, ++it) {
@@ -197,66 +329,106 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
                             have_e = true;
                         }
                         ptx::mbar_wait(&b_full[s], ph);
+                        const long long ts0 = dbg ? clock64() : 0;
                         ptx::mbar_wait(&t_empty[acc], aph ^ 1);
                         ptx::tc_fence_after();
+                        const long long ts1 = dbg ? clock64() : 0;
                         const uint64_t b_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smB + s * B_BYTES));
-                        const uint64_t e_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smE + es * E_BYTES));
+                        // the tile's 32 extension bytes sit at K offset 32*(tile%4) of the super-tile rows
+                        const uint64_t e_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smE + es * E_BYTES)) + 2 * (tile & 3);
                         const uint32_t d_tmem = tmem_base + acc * BN;
-                        // the last tile of an image may hold fewer than 256 occupied columns (a multiple of 32): narrower N
-                        const int ncols = min(BN, tcols - tile * BN);
-                        const uint32_t idesc_t = ncols == BN ? idesc : ptx::make_idesc_u8(BM, static_cast<uint32_t>(ncols));
 #pragma unroll
                         for (int k = 0; k < KBYTES / UMMA_KB; ++k) {
                             // advancing K by 32 bytes inside the 128-B swizzle atom = +2 in the (addr >> 4) field
-                            ptx::mma_i8_ss(d_tmem, a_desc0 + 2 * k, b_desc0 + 2 * k, idesc_t, k > 0 ? 1u : 0u);
+                            ptx::mma_i8_ss_pair(d_tmem, a_desc0 + 2 * k, b_desc0 + 2 * k, idesc, k > 0 ? 1u : 0u);
                         }
-                        // + e_j : the tile's 32 extension bytes sit at K offset 32*(tile%4) of the super-tile rows
-                        ptx::mma_i8_ss(d_tmem, aext_desc, e_desc0 + 2 * (tile & 3), idesc_t, 1u);
-                        ptx::mma_commit(&b_empty[s]);
-                        ptx::mma_commit(&t_full[acc]);
+                        if (dbg_mode != 3) ptx::mma_i8_ss_pair(d_tmem, aext_desc, e_desc, idesc, 1u);     // + e_j
+                        // ONE commit per tile: it frees the train-tile stage (producers), the extension stage when this was
+                        // the super-tile's last tile (producers) and publishes the accumulator (epilogues).  Every extra
+                        // commit or wait lengthens the issuer's latency chain, which is what bounds this kernel.
+                        ptx::mma_commit_pair(&done[it % ND], BOTH_CTAS);
+                        if (dbg && ptx::cluster_id_x() == 0 && it >= 1024 && it < 1024 + 64) {
+                            long long* d = dbg + 4 * 128 + (it - 1024) * 8;
+                            d[0] = ts0; d[1] = ts1; d[2] = clock64();
+                        }
                     }
                     if ((tile & 3) == 3 || tile == ntiles - 1) {
-                        ptx::mma_commit(&e_empty[es]);     // this issuer's MMAs on the super-tile (if any) are done
                         ++et;
                         have_e = false;
                     }
                 }
-                ptx::mma_commit(&a_empty[ab]);
+                ptx::mma_commit_pair(&a_empty[ab], BOTH_CTAS);
+            }
+            if (dbg && me == 0) {      // diagnostic (MSFM_K1_DEBUG=1): issue-loop cycles, wall time, tiles of this cluster
+                long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                long long* d = dbg + 4 * ptx::cluster_id_x();
+                d[0] = clock64() - dbg_c0;
+                d[1] = t1 - dbg_t0;
+                d[2] = it;
+                d[3] = un;
             }
         }
     } else if (warp >= EPI_WARP0) {
-        // ===================================================================== epilogue
+        // ===================================================================== epilogue (both CTAs, own rows)
         const int wg = (warp - EPI_WARP0) >> 2;          // column half of the tile
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;             // query row inside the unit
+        const uint32_t t_empty_leader[2] = {ptx::map_to_cta(ptx::smem_u32(&t_empty[0]), 0),
+                                            ptx::map_to_cta(ptx::smem_u32(&t_empty[1]), 0)};
         uint32_t it = 0, un = 0;
-        for (int u = unit0 + blockIdx.x; u < unit0 + num_units; u += gridDim.x) {
-            const UnitDev unit = units[u];
-            const ImgDev q = imgs[unit.q_slot];
-            const ImgDev t = imgs[unit.t_slot];
-            if (unit.row_block * BM >= img_used(q)) continue;
+        ItemEpi nepi{};
+        ItemCtl nctl{};
+        if (i_first < num_items) { nepi = load_part(&items[i_first].epi); nctl = load_part(&items[i_first].ctl); }
+        for (int i = i_first; i < num_items; i += i_step) {
+            const ItemEpi epi = nepi;
+            const ItemCtl ctl = nctl;
+            if (i + i_step < num_items) {
+                nepi = load_part(&items[i + i_step].epi);
+                nctl = load_part(&items[i + i_step].ctl);
+            }
+            if (ctl.live == 0) continue;
             const uint32_t cu = un++;
-            const int tcols = img_used(t);
+            const bool active = static_cast<int>(rank) < ctl.live;                // CTA-uniform; this CTA's unit is unit + rank
+            const int tcols = ctl.tcols;
             const int ntiles = (tcols + BN - 1) / BN;
+            // ||q_i||^2 (-1 for dead rows): requested now, needed when the pair is finished
+            const int32_t ni = (active && wg == 0) ? __ldg(epi.q_nrm + rank * BM + row) : -1;
             int32_t k1 = kIntInf, k2 = kIntInf, g1 = 0;
             for (int tile = 0; tile < ntiles; ++tile, ++it) {
                 const uint32_t acc = it & 1;
-                const uint32_t aph = (it >> 1) & 1;
-                const int4 cgv = __ldg(reinterpret_cast<const int4*>(t.cg) + tile * 2 + wg);   // C_g of this half's 4 groups
-                ptx::mbar_wait(&t_full[acc], aph);
+                if (!active || dbg_mode == 1) {          // all-dead second unit: keep the barrier protocol going
+                    ptx::mbar_wait(&done[it % ND], (it / ND) & 1);
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader[acc]);
+                    continue;
+                }
+                const int4 cgv = __ldg(reinterpret_cast<const int4*>(epi.t_cg) + tile * 2 + wg);   // C_g of this half's 4 groups
+                ptx::mbar_wait(&done[it % ND], (it / ND) & 1);
                 ptx::tc_fence_after();
+                const long long te0 = dbg ? clock64() : 0;
                 const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + wg * 128;
-                // occupied 32-column groups of this warpgroup's half (4 except in the narrow last tile of an image)
+                // occupied 32-column groups of this warpgroup's half (4 except at the end of the occupied columns;
+                // the groups behind them are all-dead and could never win, skipping them is only cheaper)
                 const int nch = min(4, max(0, (min(BN, tcols - tile * BN) - wg * 128) >> 5));
-                uint32_t va[32], vb[32];
-                ptx::tmem_ld_32x32(taddr0, va);
+                // all four 32-column chunks go to registers first, so that the accumulator stage returns to the tensor
+                // cores after ~one TMEM read time: the loop  MMA done -> t_full -> read -> t_empty -> next MMA issue  must fit
+                // into the 640 cycles the other stage computes, or the tensor pipe idles
+                uint32_t v[4][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32(taddr0 + c * 32, v[c]);
                 ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader[acc]);
+                if (dbg && leader && warp == EPI_WARP0 && lane == 0 && ptx::cluster_id_x() == 0 && it >= 1024 && it < 1024 + 64) {
+                    long long* d = dbg + 4 * 128 + (it - 1024) * 8;
+                    d[3] = te0; d[4] = clock64();
+                }
+                if (dbg_mode == 2) { k1 = min(k1, static_cast<int32_t>(v[0][0] ^ v[1][1] ^ v[2][2] ^ v[3][3])); continue; }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    // software pipeline: chunk c+1 is in flight while chunk c is reduced
-                    uint32_t(&cur)[32] = (c & 1) ? vb : va;
-                    uint32_t(&nxt)[32] = (c & 1) ? va : vb;
-                    if (c < 3) ptx::tmem_ld_32x32(taddr0 + (c + 1) * 32, nxt);
+                    uint32_t(&cur)[32] = v[c];
                     // max over the 32 columns of the group: four independent chains, two elements per VIMNMX3
                     int32_t m0 = static_cast<int32_t>(cur[0]), m1 = static_cast<int32_t>(cur[1]);
                     int32_t m2 = static_cast<int32_t>(cur[2]), m3 = static_cast<int32_t>(cur[3]);
@@ -278,17 +450,9 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
                         if (key < k1) g1 = tile * 8 + wg * 4 + c;
                         k1 = min(k1, key);
                     }
-                    if (c < 3) {
-                        ptx::tmem_ld_wait();
-                        if (c == 2) {
-                            // the last chunk is in registers: hand the accumulator stage back to the tensor core
-                            ptx::tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
-                        }
-                    }
                 }
             }
+            if (!active) continue;
             // ---- unit end: fold the two column halves, write the row results
             int4* mbuf = smMerge + (cu & 1) * 128;
             if (wg == 1) mbuf[row] = make_int4(k1, k2, g1, 0);
@@ -298,9 +462,7 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
                 k2 = __vimin3_s32(k2, o.y, max(k1, o.x));
                 if (o.x < k1) g1 = o.z;
                 k1 = min(k1, o.x);
-                const int grow = unit.row_block * BM + row;           // sorted-space row of the query image (< n_pad)
-                const int32_t ni = q.nrm[grow];                        // ||q_i||^2, -1 for dead rows
-                const size_t out = static_cast<size_t>(u) * BM + row;
+                const size_t out = static_cast<size_t>(ctl.unit + static_cast<int>(rank)) * BM + row;
                 const bool have1 = ni >= 0 && k1 < kDeadKey;
                 const bool have2 = have1 && k2 < kDeadKey;
                 res_g[out] = have1 ? g1 : -1;
@@ -310,24 +472,76 @@ match_tile_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ u
         }
     }
 
-    // ---- teardown
+    // ---- teardown: nobody leaves (and TMEM is not freed) while the peer may still signal or compute
     ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+    ptx::cluster_sync();
+    if (warp == 2) ptx::tmem_dealloc_pair<512>(tmem_base);
 }
 
 }  // namespace k1
 
-// host launcher (called from msfm_api.cu)
+// host launcher (called from msfm_api.cu).  unit0 and num_units must be even (segments are an even number of units).
+// item_scratch: device buffer of at least match_tile_item_bytes(num_units) bytes.
+size_t match_tile_item_bytes(int num_units) { return static_cast<size_t>(num_units / 2 + 1) * sizeof(k1::Item); }
+
 cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, int unit0, int num_units, int32_t* res_g,
-                                     int32_t* res_d1, int32_t* res_u, int num_sms, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(k1::match_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     int32_t* res_d1, int32_t* res_u, void* item_scratch, int num_sms, cudaStream_t stream) {
+    static const bool single = [] {
+        const char* e = std::getenv("MSFM_K1_SINGLE");       // diagnostic A/B switch, see match_k1_single.cu
+        return e && e[0] == '1';
+    }();
+    if (single) return launch_match_tile_single(imgs, units, unit0, num_units, res_g, res_d1, res_u, num_sms, stream);
+    cudaError_t e = cudaFuncSetAttribute(k1::match_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(k1::SMEM_BYTES));
     if (e != cudaSuccess) return e;
     if (num_units <= 0) return cudaSuccess;
-    const int grid = num_units < num_sms ? num_units : num_sms;
-    k1::match_tile_kernel<<<grid, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(imgs, units, unit0, num_units, res_g, res_d1,
-                                                                            res_u);
+    if ((unit0 | num_units) & 1) return cudaErrorInvalidValue;
+    const int num_items = num_units / 2;
+    const int clusters = num_items < num_sms / 2 ? num_items : num_sms / 2;
+    if (clusters <= 0) return cudaErrorInvalidConfiguration;
+    k1::Item* items = static_cast<k1::Item*>(item_scratch);
+    k1::build_items_kernel<<<(num_items + 255) / 256, 256, 0, stream>>>(imgs, units, unit0, num_items, items);
+    static const int debug = [] {
+        const char* e = std::getenv("MSFM_K1_DEBUG");       // 1: timing only; 11/12/13: + knock out a part (results garbage)
+        return e ? atoi(e) : 0;
+    }();
+    long long* dbg = nullptr;
+    if (debug) {
+        static long long* d_dbg = nullptr;
+        if (!d_dbg) cudaMalloc(&d_dbg, (4 * 128 + 64 * 8) * sizeof(long long));
+        dbg = d_dbg;
+        cudaMemsetAsync(dbg, 0, (4 * 128 + 64 * 8) * sizeof(long long), stream);
+    }
+    k1::match_pair_kernel<<<2 * clusters, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(items, num_items, res_g, res_d1, res_u, dbg, debug > 10 ? debug - 10 : 0);
+    if (debug) {
+        long long h[4 * 128 + 64 * 8];
+        cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, stream);
+        cudaStreamSynchronize(stream);
+        double cyc = 0, ns = 0, tiles = 0;
+        int n = 0;
+        for (int i = 0; i < clusters; ++i)
+            if (h[4 * i + 2] > 0) { cyc += double(h[4 * i]); ns += double(h[4 * i + 1]); tiles += double(h[4 * i + 2]); ++n; }
+        {   // per-tile timeline of cluster 0, tiles 1024..1087 (clock64 of the leader SM)
+            const long long* ts = h + 4 * 128;
+            double w_te = 0, issue = 0, exec = 0, epi = 0, back = 0;
+            int m = 0;
+            for (int k = 2; k < 62; ++k) {
+                const long long* a = ts + 8 * k;
+                const long long* nx = ts + 8 * (k + 2);      // same accumulator stage, two tiles later
+                if (!a[2] || !a[3] || !nx[1]) continue;
+                w_te += double(a[1] - a[0]);     // issuer: b_full satisfied -> t_empty satisfied
+                issue += double(a[2] - a[1]);    // issuer: 5 MMAs + commit issued
+                exec += double(a[3] - a[2]);     // commit issued -> epilogue sees done
+                epi += double(a[4] - a[3]);      // epilogue: TMEM -> registers, arrive sent
+                back += double(nx[1] - a[4]);    // arrive sent -> issuer of tile+2 sees t_empty
+                ++m;
+            }
+            if (m) fprintf(stderr, "K1 timeline (avg of %d tiles): wait_t_empty %.0f | issue %.0f | commit->done %.0f | epi ld+arrive %.0f | arrive->issuer %.0f\n",
+                           m, w_te / m, issue / m, exec / m, epi / m, back / m);
+        }
+        if (n) fprintf(stderr, "K1 debug: %d clusters, %.0f tiles/cluster, %.1f cycles/tile, %.3f ms, %.0f MHz\n", n, tiles / n,
+                       cyc / tiles, ns / n * 1e-6, cyc / ns * 1e3);
+    }
     return cudaGetLastError();
 }
 

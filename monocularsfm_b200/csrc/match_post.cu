@@ -496,7 +496,7 @@ __global__ void setup_temp_imgs_kernel(ImgDev* __restrict__ imgs, int first_temp
     e.perm = T.perm + static_cast<size_t>(p) * T.n_pad_t;
     e.used = T.used + p;
     e.n = n2;
-    e.n_pad = (n2 + kUnitRows - 1) / kUnitRows * kUnitRows;
+    e.n_pad = (n2 + 2 * kUnitRows - 1) / (2 * kUnitRows) * (2 * kUnitRows);     // unit pairs (match_k1.cu)
     imgs[first_temp_slot + p] = e;
 }
 

@@ -13,7 +13,8 @@ struct TempImgs {
 };
 cudaError_t launch_setup_temp_imgs(ImgDev*, int, const SegDev*, int, TempImgs, cudaStream_t);
 cudaError_t launch_gather_candidates(const ImgDev*, const SegDev*, int, const int32_t*, TempImgs, cudaStream_t);
-cudaError_t launch_match_tile_kernel(const ImgDev*, const UnitDev*, int, int, int32_t*, int32_t*, int32_t*, int, cudaStream_t);
+cudaError_t launch_match_tile_kernel(const ImgDev*, const UnitDev*, int, int, int32_t*, int32_t*, int32_t*, void*, int, cudaStream_t);
+size_t match_tile_item_bytes(int num_units);
 cudaError_t launch_desc_format(const uint8_t*, int, int, uint8_t*, uint8_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, unsigned long long*,
                                int32_t*, int32_t*, int32_t*, cudaStream_t);
 cudaError_t launch_build_units(const SegDev*, int, int, UnitDev*, cudaStream_t);
@@ -307,7 +308,7 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
             const int n2 = c->imgs[slot2[p]].n;
             n2_max = std::max(n2_max, n2);
             const int u12 = c->imgs[slot1[p]].n_pad / kUnitRows;
-            const int u21 = opt.cross_check ? (n2 + kUnitRows - 1) / kUnitRows : 0;
+            const int u21 = opt.cross_check ? 2 * ((n2 + 2 * kUnitRows - 1) / (2 * kUnitRows)) : 0;   // K1 works on unit pairs
             if (cur.npairs > 0 && cur.units_fwd + cur.units_rev + u12 + u21 > kMaxUnitsPerBatch) {
                 batches.push_back(cur);
                 cur = Batch{p, 0, 0, 0};
@@ -339,7 +340,7 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
                 r.q_slot = first_temp_slot + k;          // temporary query image of pair k: matched rows of image 2
                 r.t_slot = slot1[p];
                 r.unit_base = ub;
-                r.n_units = (c->imgs[slot2[p]].n + kUnitRows - 1) / kUnitRows;
+                r.n_units = 2 * ((c->imgs[slot2[p]].n + 2 * kUnitRows - 1) / (2 * kUnitRows));
                 ub += r.n_units;
             }
     }
@@ -360,6 +361,7 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
     const size_t nb = std::max<size_t>(1, batches.size());
     MSFM_CUDA(c, c->d_segs.reserve(std::max<size_t>(1, segs.size()) * sizeof(SegDev)));
     MSFM_CUDA(c, c->d_units.reserve(static_cast<size_t>(max_units) * sizeof(UnitDev)));
+    MSFM_CUDA(c, c->d_items.reserve(match_tile_item_bytes(max_units)));
     MSFM_CUDA(c, c->d_res.reserve(rows * 3 * sizeof(int32_t)));
     MSFM_CUDA(c, c->d_m.reserve(rows * 5 * sizeof(int32_t)));
     MSFM_CUDA(c, c->d_exact.reserve(rows * sizeof(int32_t)));
@@ -367,7 +369,7 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
     MSFM_CUDA(c, c->d_misc.reserve(16 + nb * 4 * sizeof(unsigned int)));
     TempImgs T{};
     if (opt.cross_check && P > 0) {
-        T.n_pad_t = std::max(kUnitRows, (n2_max + kUnitRows - 1) / kUnitRows * kUnitRows);
+        T.n_pad_t = std::max(2 * kUnitRows, (n2_max + 2 * kUnitRows - 1) / (2 * kUnitRows) * (2 * kUnitRows));
         const size_t per = static_cast<size_t>(T.n_pad_t);
         const size_t sw_bytes = static_cast<size_t>(max_pairs) * per * 128;
         const size_t arr_bytes = static_cast<size_t>(max_pairs) * per * 4;
@@ -422,7 +424,7 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
                     c->launches += 1;
                 }
                 c->prof_begin(MSFM_PROF_MATCH_TILE);
-                MSFM_CUDA(c, launch_match_tile_kernel(d_imgs, units, u0, nu, res_j, res_d1, res_u, c->num_sms, c->stream));
+                MSFM_CUDA(c, launch_match_tile_kernel(d_imgs, units, u0, nu, res_j, res_d1, res_u, c->d_items.p, c->num_sms, c->stream));
                 c->prof_end();
                 c->prof_begin(MSFM_PROF_RESOLVE);
                 MSFM_CUDA(c, launch_resolve_rows(d_imgs, units, u0, nu, res_j, res_d1, res_u, opt, m_j, m_d1, m_d2, m_j0,

@@ -68,6 +68,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---------------------------------------------------------------- thread-block cluster (CTA pair) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+// all threads of all CTAs of the cluster
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier that may live in another CTA of the cluster (address from map_to_cta).
+// Default (CTA-scope release) semantics on purpose: the .release.cluster / .acquire.cluster forms compile to
+// MEMBAR.ALL.GPU / CCTL.IVALL per call (seen in SASS; they doubled the kernel time), and nothing but tensor-core
+// (async proxy) traffic crosses the CTA pair here — the tcgen05 fences and commits order that.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // ---------------------------------------------------------------- bulk async copy (TMA engine, 1-D)
 // global -> shared::cta, completion counted in bytes on an mbarrier.  size % 16 == 0, 16-B aligned.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -122,6 +156,42 @@ __device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+
+// ---- CTA-pair (cta_group::2) forms: one thread of the leader CTA issues for both SMs of the pair.
+// TMEM allocation: warp-collective, issued by the same warp of BOTH CTAs with the same smem destination offset.
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B^T with M = 256: CTA r supplies rows 128r.. of A and columns (N/2)r.. of B from the
+// same shared-memory offsets and receives rows 128r.. of D (all N columns) at the same TMEM address.
+__device__ __forceinline__ void mma_i8_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// one arrival on the mbarrier at this shared-memory offset in every CTA of cta_mask, once all earlier pair-MMAs
+// of this thread have completed
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
 }
 
 // 32 lanes x 32 columns of 32-bit: thread t of the warp receives row (lane base + t), columns c..c+31.

@@ -43,3 +43,8 @@ microbench: build/microbench
 build/microbench: tools/microbench.cu $(CSRC)/ptx.cuh
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ $<
+
+microbench_pair: build/microbench_pair
+build/microbench_pair: tools/microbench_pair.cu $(CSRC)/ptx.cuh
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ $<

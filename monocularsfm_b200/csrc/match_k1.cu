@@ -64,13 +64,12 @@ constexpr uint32_t A_BYTES = BM * KBYTES;    // 16 KiB
 constexpr uint32_t B_BYTES = HN * KBYTES;    // 16 KiB: this CTA's half of a train tile
 constexpr uint32_t E_BYTES = HN * 128;       // 16 KiB: this CTA's half of an extension super-tile
 constexpr int NUM_THREADS = 384;
-constexpr int NUM_ISSUERS = 2;               // warps 1, 2 of the leader.  MUST equal the number of accumulator stages
+constexpr int MAX_ISSUERS = 2;               // warps 1, 2 of the leader; template parameter kIssuers = 1 or 2
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr uint16_t BOTH_CTAS = 0b11;
 static_assert(BM == 128, "one UMMA M=128 half per CTA");
-static_assert(NUM_ISSUERS == 2, "one issuer per accumulator stage");
 
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_AEXT = OFF_A + 2 * A_BYTES;
@@ -152,6 +151,7 @@ __global__ void build_items_kernel(const ImgDev* __restrict__ imgs, const UnitDe
 
 // Units come in pairs (u, u+1) of the same segment: the host makes every segment an even number of units.
 // A pair is skipped by every role of both CTAs when its FIRST unit is all dead rows.
+template <int NUM_ISSUERS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __restrict__ res_g,
                   int32_t* __restrict__ res_d1, int32_t* __restrict__ res_u, long long* __restrict__ dbg, int dbg_mode) {
@@ -212,7 +212,7 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
 
     if (warp == 0) {
         // ===================================================================== producer (both CTAs, own halves)
-        if (lane == 0) {
+        if (lane == 0 && dbg_mode < 6) {
             uint32_t it = 0, un = 0, et = 0;
             uint32_t ext_last[NE] = {0, 0};                            // last tile (global counter) that reads each ext stage
             ItemSrc nsrc{};
@@ -263,7 +263,7 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
         }
     } else if (warp == 1 && !leader) {
         // ===================================================================== relay (peer CTA): my half has landed
-        if (lane == 0) {
+        if (lane == 0 && dbg_mode < 6) {
             uint32_t it = 0, un = 0, et = 0;
             ItemCtl nctl{};
             if (i_first < num_items) nctl = load_part(&items[i_first].ctl);
@@ -315,8 +315,10 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
                 for (int tile = 0; tile < ntiles; ++tile, ++it) {
                     const uint32_t es = et % NE;
                     if (it % NUM_ISSUERS == me) {
+                        const long long tsp = dbg ? clock64() : 0;
+                        const bool nowait = dbg_mode >= 4;      // diagnostic: garbage operands, full barriers ignored
                         if (!have_a) {
-                            ptx::mbar_wait(&a_full[ab], (cu >> 1) & 1);
+                            if (!nowait) ptx::mbar_wait(&a_full[ab], (cu >> 1) & 1);
                             a_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smA + ab * A_BYTES));
                             have_a = true;
                         }
@@ -325,15 +327,15 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
                         const uint32_t acc = it & 1;
                         const uint32_t aph = (it >> 1) & 1;
                         if (!have_e) {                     // first owned tile of this super-tile
-                            ptx::mbar_wait(&e_full[es], (et / NE) & 1);
+                            if (!nowait) ptx::mbar_wait(&e_full[es], (et / NE) & 1);
                             have_e = true;
                         }
-                        ptx::mbar_wait(&b_full[s], ph);
+                        if (!nowait) ptx::mbar_wait(&b_full[s], ph);
                         const long long ts0 = dbg ? clock64() : 0;
-                        ptx::mbar_wait(&t_empty[acc], aph ^ 1);
+                        if (dbg_mode < 8) ptx::mbar_wait(&t_empty[acc], aph ^ 1);      // 8: free-running MMAs (diagnostic)
                         ptx::tc_fence_after();
                         const long long ts1 = dbg ? clock64() : 0;
-                        const uint64_t b_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smB + s * B_BYTES));
+                        const uint64_t b_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smB + (dbg_mode == 10 ? 0 : s) * B_BYTES));
                         // the tile's 32 extension bytes sit at K offset 32*(tile%4) of the super-tile rows
                         const uint64_t e_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smE + es * E_BYTES)) + 2 * (tile & 3);
                         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -349,7 +351,7 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
                         ptx::mma_commit_pair(&done[it % ND], BOTH_CTAS);
                         if (dbg && ptx::cluster_id_x() == 0 && it >= 1024 && it < 1024 + 64) {
                             long long* d = dbg + 4 * 128 + (it - 1024) * 8;
-                            d[0] = ts0; d[1] = ts1; d[2] = clock64();
+                            d[0] = ts0; d[1] = ts1; d[2] = clock64(); d[5] = tsp;
                         }
                     }
                     if ((tile & 3) == 3 || tile == ntiles - 1) {
@@ -359,6 +361,7 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
                 }
                 ptx::mma_commit_pair(&a_empty[ab], BOTH_CTAS);
             }
+            if (dbg_mode >= 8) { const long long tw = clock64(); while (clock64() - tw < 20000) {} }   // let free-running MMAs drain
             if (dbg && me == 0) {      // diagnostic (MSFM_K1_DEBUG=1): issue-loop cycles, wall time, tiles of this cluster
                 long long t1;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -369,7 +372,7 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
                 d[3] = un;
             }
         }
-    } else if (warp >= EPI_WARP0) {
+    } else if (warp >= EPI_WARP0 && dbg_mode < 9) {
         // ===================================================================== epilogue (both CTAs, own rows)
         const int wg = (warp - EPI_WARP0) >> 2;          // column half of the tile
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
@@ -397,7 +400,7 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
             int32_t k1 = kIntInf, k2 = kIntInf, g1 = 0;
             for (int tile = 0; tile < ntiles; ++tile, ++it) {
                 const uint32_t acc = it & 1;
-                if (!active || dbg_mode == 1) {          // all-dead second unit: keep the barrier protocol going
+                if (!active || dbg_mode == 1 || dbg_mode == 5 || dbg_mode >= 6) {          // all-dead second unit: keep the barrier protocol going
                     ptx::mbar_wait(&done[it % ND], (it / ND) & 1);
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader[acc]);
@@ -491,8 +494,12 @@ cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, i
         return e && e[0] == '1';
     }();
     if (single) return launch_match_tile_single(imgs, units, unit0, num_units, res_g, res_d1, res_u, num_sms, stream);
-    cudaError_t e = cudaFuncSetAttribute(k1::match_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(k1::SMEM_BYTES));
+    static const int issuers = [] {
+        const char* e = std::getenv("MSFM_K1_ISSUERS");      // diagnostic A/B switch: MMA issuer threads of the leader CTA
+        return (e && e[0] == '2') ? 2 : 1;
+    }();
+    auto kernel = issuers == 2 ? k1::match_pair_kernel<2> : k1::match_pair_kernel<1>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(k1::SMEM_BYTES));
     if (e != cudaSuccess) return e;
     if (num_units <= 0) return cudaSuccess;
     if ((unit0 | num_units) & 1) return cudaErrorInvalidValue;
@@ -512,7 +519,7 @@ cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, i
         dbg = d_dbg;
         cudaMemsetAsync(dbg, 0, (4 * 128 + 64 * 8) * sizeof(long long), stream);
     }
-    k1::match_pair_kernel<<<2 * clusters, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(items, num_items, res_g, res_d1, res_u, dbg, debug > 10 ? debug - 10 : 0);
+    kernel<<<2 * clusters, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(items, num_items, res_g, res_d1, res_u, dbg, debug > 10 ? debug - 10 : 0);
     if (debug) {
         long long h[4 * 128 + 64 * 8];
         cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, stream);
@@ -535,6 +542,14 @@ cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, i
                 epi += double(a[4] - a[3]);      // epilogue: TMEM -> registers, arrive sent
                 back += double(nx[1] - a[4]);    // arrive sent -> issuer of tile+2 sees t_empty
                 ++m;
+            }
+            if (m && std::getenv("MSFM_K1_DEBUG_RAW")) {      // absolute per-tile stamps relative to tile 1026's b_full
+                const long long base = ts[8 * 2];
+                for (int k = 2; k < 18; ++k) {
+                    const long long* a = ts + 8 * k;
+                    fprintf(stderr, "K1 raw tile %d (stage %d): top %lld b_full %lld t_empty %lld committed %lld | epi done-seen %lld released %lld\n",
+                            k, k & 1, a[5] - base, a[0] - base, a[1] - base, a[2] - base, a[3] - base, a[4] - base);
+                }
             }
             if (m) fprintf(stderr, "K1 timeline (avg of %d tiles): wait_t_empty %.0f | issue %.0f | commit->done %.0f | epi ld+arrive %.0f | arrive->issuer %.0f\n",
                            m, w_te / m, issue / m, exec / m, epi / m, back / m);

@@ -48,3 +48,8 @@ microbench_pair: build/microbench_pair
 build/microbench_pair: tools/microbench_pair.cu $(CSRC)/ptx.cuh
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ $<
+
+microbench_alu: build/microbench_alu
+build/microbench_alu: tools/microbench_alu.cu
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ $<

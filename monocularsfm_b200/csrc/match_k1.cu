@@ -58,13 +58,12 @@ constexpr int BN = 256;                      // train columns per tile (UMMA N)
 constexpr int HN = BN / 2;                   // columns of a tile this CTA loads
 constexpr int KBYTES = 128;
 constexpr int UMMA_KB = 32;                  // bytes of K per tcgen05.mma.kind::i8
-constexpr int NS = 6;                        // smem stages of the train-tile ring
+constexpr int NS = 8;                        // smem stages of the train-tile ring (power of two: ring index = it & 7)
 constexpr int NE = 2;                        // smem stages of the extension super-tile ring (one per 4 tiles)
 constexpr uint32_t A_BYTES = BM * KBYTES;    // 16 KiB
 constexpr uint32_t B_BYTES = HN * KBYTES;    // 16 KiB: this CTA's half of a train tile
 constexpr uint32_t E_BYTES = HN * 128;       // 16 KiB: this CTA's half of an extension super-tile
 constexpr int NUM_THREADS = 384;
-constexpr int MAX_ISSUERS = 2;               // warps 1, 2 of the leader; template parameter kIssuers = 1 or 2
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -80,6 +79,7 @@ constexpr uint32_t OFF_BAR = OFF_MERGE + 2 * 128 * 16;
 constexpr int ND = 2 * NS;                   // ring of per-tile "MMAs done" barriers
 constexpr uint32_t NUM_BARS = 2 + 2 + NS + NE + ND + 2;
 constexpr uint32_t OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
+constexpr uint32_t OFF_ZNEG = OFF_TMEMPTR + 8;                  // one s32 holding INT_MIN (see the epilogue)
 constexpr uint32_t SMEM_USED = OFF_TMEMPTR + 16;
 constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;               // slack for manual 1024-B alignment
 
@@ -149,9 +149,27 @@ __global__ void build_items_kernel(const ImgDev* __restrict__ imgs, const UnitDe
     items[i] = it;
 }
 
+// 32-bit / 64-bit values that every lane of the warp holds identically (loaded from one address): the shuffle tells
+// the compiler so, which lets it keep descriptors, addresses and loop state in UNIFORM registers.
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ int32_t uni(int32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ const uint8_t* uni(const uint8_t* p) {
+    const unsigned long long v = reinterpret_cast<unsigned long long>(p);
+    const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), 0);
+    const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), 0);
+    return reinterpret_cast<const uint8_t*>((static_cast<unsigned long long>(hi) << 32) | lo);
+}
+
 // Units come in pairs (u, u+1) of the same segment: the host makes every segment an even number of units.
 // A pair is skipped by every role of both CTAs when its FIRST unit is all dead rows.
-template <int NUM_ISSUERS>
+//
+// The producer, relay and issuer loops are executed by ALL 32 lanes of their warp with warp-uniform control flow and
+// operands; only the asynchronous instructions themselves (bulk copy, tcgen05.mma, tcgen05.commit, remote arrive) are
+// predicated on one elected lane.  Written as `if (lane == 0) { whole loop }` the same loop compiles to a
+// ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY sequence around every UTCIMMA plus ~200 scalar instructions per tile, which one
+// thread needs ~1400 cycles to get through — twice the 640 tensor cycles of a tile (tools/microbench_pair.cu,
+// profiles/r01b_microbench_pair.log).
+template <bool kDbg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __restrict__ res_g,
                   int32_t* __restrict__ res_d1, int32_t* __restrict__ res_u, long long* __restrict__ dbg, int dbg_mode) {
@@ -194,7 +212,7 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
         const uint32_t full_count = leader ? 2u : 1u;       // own producer (+ the peer's relay)
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&a_full[i], full_count);
-            ptx::mbar_init(&a_empty[i], NUM_ISSUERS);
+            ptx::mbar_init(&a_empty[i], 1);
             ptx::mbar_init(&t_empty[i], 2 * EPI_WARPS);
         }
         for (int i = 0; i < NS; ++i) ptx::mbar_init(&b_full[i], full_count);
@@ -202,6 +220,7 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
         for (int i = 0; i < ND; ++i) ptx::mbar_init(&done[i], 1);
         ptx::fence_mbar_init();
     }
+    if (threadIdx.x == 0) *reinterpret_cast<volatile int32_t*>(smem + OFF_ZNEG) = static_cast<int32_t>(0x80000000);
     if (warp == 2) ptx::tmem_alloc_pair<512>(tmem_ptr);
     ptx::tc_fence_before();
     ptx::cluster_sync();                 // barriers of BOTH CTAs are initialised before anyone arrives remotely
@@ -212,174 +231,174 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
 
     if (warp == 0) {
         // ===================================================================== producer (both CTAs, own halves)
-        if (lane == 0 && dbg_mode < 6) {
-            uint32_t it = 0, un = 0, et = 0;
-            uint32_t ext_last[NE] = {0, 0};                            // last tile (global counter) that reads each ext stage
-            ItemSrc nsrc{};
-            ItemCtl nctl{};
-            if (i_first < num_items) { nsrc = load_part(&items[i_first].src); nctl = load_part(&items[i_first].ctl); }
-            for (int i = i_first; i < num_items; i += i_step) {
-                const ItemSrc src = nsrc;
-                const ItemCtl ctl = nctl;
-                if (i + i_step < num_items) {                          // in flight while this pair is fed
-                    nsrc = load_part(&items[i + i_step].src);
-                    nctl = load_part(&items[i + i_step].ctl);
-                }
-                // all-dead query rows: every role skips the pair.  An empty train image needs no operands either (only the
-                // epilogue acts, writing "no match"): loading A for it would let this producer lap the peer's relay, which
-                // is otherwise throttled through the issuers' a_full waits
-                if (ctl.live == 0 || ctl.tcols == 0) continue;
-                const uint32_t cu = un++;                              // index among the pairs this cluster really processes
-                const uint32_t ab = cu & 1;
-                ptx::mbar_wait(&a_empty[ab], ((cu >> 1) & 1) ^ 1);
+        uint32_t it = 0, un = 0, et = 0;
+        uint32_t ext_last0 = 0, ext_last1 = 0;                     // last tile (global counter) that reads each ext stage
+        ItemSrc nsrc{};
+        ItemCtl nctl{};
+        if (i_first < num_items) { nsrc = load_part(&items[i_first].src); nctl = load_part(&items[i_first].ctl); }
+        for (int i = i_first; i < num_items; i += i_step) {
+            const uint8_t* q_rows = uni(nsrc.q_rows);
+            const uint8_t* t_sw = uni(nsrc.t_sw);
+            const uint8_t* t_ext = uni(nsrc.t_ext);
+            const int tcols = uni(nctl.tcols), live = uni(nctl.live);
+            if (i + i_step < num_items) {                          // in flight while this pair is fed
+                nsrc = load_part(&items[i + i_step].src);
+                nctl = load_part(&items[i + i_step].ctl);
+            }
+            // all-dead query rows: every role skips the pair.  An empty train image needs no operands either (only the
+            // epilogue acts, writing "no match"): loading A for it would let this producer lap the peer's relay, which
+            // is otherwise throttled through the issuer's a_full waits
+            if (live == 0 || tcols == 0) continue;
+            const uint32_t cu = un++;                              // index among the pairs this cluster really processes
+            const uint32_t ab = cu & 1;
+            ptx::mbar_wait(&a_empty[ab], ((cu >> 1) & 1) ^ 1);
+            if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(&a_full[ab], A_BYTES);
-                ptx::bulk_g2s(smA + ab * A_BYTES, src.q_rows + rank * A_BYTES, A_BYTES, &a_full[ab]);
-                const int ntiles = (ctl.tcols + BN - 1) / BN;            // tiles beyond the occupied columns are skipped
-                for (int tile = 0; tile < ntiles; ++tile, ++it) {
-                    if ((tile & 3) == 0) {
-                        const uint32_t es = et % NE;
-                        if (et >= NE) {                    // the stage's previous super-tile: wait for its last tile's MMAs
-                            const uint32_t l = ext_last[es];
-                            ptx::mbar_wait(&done[l % ND], (l / ND) & 1);
-                        }
-                        ext_last[es] = it + static_cast<uint32_t>(min(4, ntiles - tile)) - 1;
-                        ptx::mbar_arrive_expect_tx(&e_full[es], E_BYTES);
-                        ptx::bulk_g2s(smE + es * E_BYTES, src.t_ext + (static_cast<size_t>(tile >> 2) * 2 + rank) * E_BYTES, E_BYTES,
-                                      &e_full[es]);
-                        ++et;
-                    }
-                    const uint32_t s = it % NS;
-                    if (it >= NS) {                        // the stage's previous tile, it - NS: wait for its MMAs
-                        const uint32_t l = it - NS;
+                ptx::bulk_g2s(smA + ab * A_BYTES, q_rows + rank * A_BYTES, A_BYTES, &a_full[ab]);
+            }
+            __syncwarp();
+            const int ntiles = (tcols + BN - 1) / BN;              // tiles beyond the occupied columns are skipped
+            for (int tile = 0; tile < ntiles; ++tile, ++it) {
+                if ((tile & 3) == 0) {
+                    const uint32_t es = et & 1;
+                    if (et >= NE) {                    // the stage's previous super-tile: wait for its last tile's MMAs
+                        const uint32_t l = es ? ext_last1 : ext_last0;
                         ptx::mbar_wait(&done[l % ND], (l / ND) & 1);
                     }
-                    ptx::mbar_arrive_expect_tx(&b_full[s], B_BYTES);
-                    ptx::bulk_g2s(smB + s * B_BYTES, src.t_sw + (static_cast<size_t>(tile) * 2 + rank) * B_BYTES, B_BYTES, &b_full[s]);
+                    const uint32_t last = it + static_cast<uint32_t>(min(4, ntiles - tile)) - 1;
+                    if (es) ext_last1 = last; else ext_last0 = last;
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(&e_full[es], E_BYTES);
+                        ptx::bulk_g2s(smE + es * E_BYTES, t_ext + (static_cast<size_t>(tile >> 2) * 2 + rank) * E_BYTES, E_BYTES,
+                                      &e_full[es]);
+                    }
+                    __syncwarp();
+                    ++et;
                 }
+                const uint32_t s = it % NS;
+                if (it >= NS) {                        // the stage's previous tile, it - NS: wait for its MMAs
+                    const uint32_t l = it - NS;
+                    ptx::mbar_wait(&done[l % ND], (l / ND) & 1);
+                }
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(&b_full[s], B_BYTES);
+                    ptx::bulk_g2s(smB + s * B_BYTES, t_sw + (static_cast<size_t>(tile) * 2 + rank) * B_BYTES, B_BYTES, &b_full[s]);
+                }
+                __syncwarp();
             }
-            // drain: every multicast commit aimed at this CTA's a_empty barriers has landed before the CTA may exit
-            // (the epilogue waits for every done[] arrival)
-            for (uint32_t i = 0; i < 2; ++i, ++un) ptx::mbar_wait(&a_empty[un & 1], ((un >> 1) & 1) ^ 1);
         }
+        // drain: every multicast commit aimed at this CTA's a_empty barriers has landed before the CTA may exit
+        // (the epilogue waits for every done[] arrival)
+        for (uint32_t i = 0; i < 2; ++i, ++un) ptx::mbar_wait(&a_empty[un & 1], ((un >> 1) & 1) ^ 1);
     } else if (warp == 1 && !leader) {
         // ===================================================================== relay (peer CTA): my half has landed
-        if (lane == 0 && dbg_mode < 6) {
-            uint32_t it = 0, un = 0, et = 0;
-            ItemCtl nctl{};
-            if (i_first < num_items) nctl = load_part(&items[i_first].ctl);
-            for (int i = i_first; i < num_items; i += i_step) {
-                const ItemCtl ctl = nctl;
-                if (i + i_step < num_items) nctl = load_part(&items[i + i_step].ctl);
-                if (ctl.live == 0 || ctl.tcols == 0) continue;
-                const uint32_t cu = un++;
-                const uint32_t ab = cu & 1;
-                ptx::mbar_wait(&a_full[ab], (cu >> 1) & 1);
-                ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&a_full[ab]), 0));
-                const int ntiles = (ctl.tcols + BN - 1) / BN;
-                for (int tile = 0; tile < ntiles; ++tile, ++it) {
-                    if ((tile & 3) == 0) {
-                        const uint32_t es = et % NE;
-                        ptx::mbar_wait(&e_full[es], (et / NE) & 1);
-                        ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&e_full[es]), 0));
-                        ++et;
-                    }
-                    const uint32_t s = it % NS;
-                    ptx::mbar_wait(&b_full[s], (it / NS) & 1);
-                    ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&b_full[s]), 0));
+        const uint32_t a_full_leader[2] = {ptx::map_to_cta(ptx::smem_u32(&a_full[0]), 0), ptx::map_to_cta(ptx::smem_u32(&a_full[1]), 0)};
+        const uint32_t e_full_leader[2] = {ptx::map_to_cta(ptx::smem_u32(&e_full[0]), 0), ptx::map_to_cta(ptx::smem_u32(&e_full[1]), 0)};
+        const uint32_t b_full_leader0 = ptx::map_to_cta(ptx::smem_u32(&b_full[0]), 0);
+        uint32_t it = 0, un = 0, et = 0;
+        ItemCtl nctl{};
+        if (i_first < num_items) nctl = load_part(&items[i_first].ctl);
+        for (int i = i_first; i < num_items; i += i_step) {
+            const int tcols = uni(nctl.tcols), live = uni(nctl.live);
+            if (i + i_step < num_items) nctl = load_part(&items[i + i_step].ctl);
+            if (live == 0 || tcols == 0) continue;
+            const uint32_t cu = un++;
+            const uint32_t ab = cu & 1;
+            ptx::mbar_wait(&a_full[ab], (cu >> 1) & 1);
+            if (ptx::elect_one()) ptx::mbar_arrive_cluster(a_full_leader[ab]);
+            __syncwarp();
+            const int ntiles = (tcols + BN - 1) / BN;
+            for (int tile = 0; tile < ntiles; ++tile, ++it) {
+                if ((tile & 3) == 0) {
+                    const uint32_t es = et & 1;
+                    ptx::mbar_wait(&e_full[es], (et >> 1) & 1);
+                    if (ptx::elect_one()) ptx::mbar_arrive_cluster(e_full_leader[es]);
+                    __syncwarp();
+                    ++et;
                 }
+                const uint32_t s = it % NS;
+                ptx::mbar_wait(&b_full[s], (it / NS) & 1);
+                if (ptx::elect_one()) ptx::mbar_arrive_cluster(b_full_leader0 + s * 8);
+                __syncwarp();
             }
         }
-    } else if (warp >= 1 && warp <= NUM_ISSUERS && leader) {
-        // ===================================================================== MMA issuers (leader CTA)
-        if (lane == 0) {
-            const uint32_t me = static_cast<uint32_t>(warp - 1);   // owns the tiles with it % NUM_ISSUERS == me
-            constexpr uint32_t idesc = ptx::make_idesc_u8(2 * BM, BN);
-            const uint64_t aext_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smAext));
-            uint32_t it = 0, un = 0, et = 0;
-            long long dbg_c0 = 0, dbg_t0 = 0;
-            if (dbg && me == 0) {
-                dbg_c0 = clock64();
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
-            }
-            ItemCtl nctl{};
-            if (i_first < num_items) nctl = load_part(&items[i_first].ctl);
-            for (int i = i_first; i < num_items; i += i_step) {
-                const ItemCtl ctl = nctl;
-                if (i + i_step < num_items) nctl = load_part(&items[i + i_step].ctl);
-                if (ctl.live == 0 || ctl.tcols == 0) continue;
-                const uint32_t cu = un++;
-                const uint32_t ab = cu & 1;
-                const int ntiles = (ctl.tcols + BN - 1) / BN;
-                bool have_a = false, have_e = false;
-                uint64_t a_desc0 = 0;
-                for (int tile = 0; tile < ntiles; ++tile, ++it) {
-                    const uint32_t es = et % NE;
-                    if (it % NUM_ISSUERS == me) {
-                        const long long tsp = dbg ? clock64() : 0;
-                        const bool nowait = dbg_mode >= 4;      // diagnostic: garbage operands, full barriers ignored
-                        if (!have_a) {
-                            if (!nowait) ptx::mbar_wait(&a_full[ab], (cu >> 1) & 1);
-                            a_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smA + ab * A_BYTES));
-                            have_a = true;
-                        }
-                        const uint32_t s = it % NS;
-                        const uint32_t ph = (it / NS) & 1;
-                        const uint32_t acc = it & 1;
-                        const uint32_t aph = (it >> 1) & 1;
-                        if (!have_e) {                     // first owned tile of this super-tile
-                            if (!nowait) ptx::mbar_wait(&e_full[es], (et / NE) & 1);
-                            have_e = true;
-                        }
-                        if (!nowait) ptx::mbar_wait(&b_full[s], ph);
-                        const long long ts0 = dbg ? clock64() : 0;
-                        if (dbg_mode < 8) ptx::mbar_wait(&t_empty[acc], aph ^ 1);      // 8: free-running MMAs (diagnostic)
-                        ptx::tc_fence_after();
-                        const long long ts1 = dbg ? clock64() : 0;
-                        const uint64_t b_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smB + (dbg_mode == 10 ? 0 : s) * B_BYTES));
-                        // the tile's 32 extension bytes sit at K offset 32*(tile%4) of the super-tile rows
-                        const uint64_t e_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smE + es * E_BYTES)) + 2 * (tile & 3);
-                        const uint32_t d_tmem = tmem_base + acc * BN;
+    } else if (warp == 1 && leader) {
+        // ===================================================================== MMA issuer (leader CTA), in tile order
+        constexpr uint32_t idesc = ptx::make_idesc_u8(2 * BM, BN);
+        const uint32_t sbase = uni(ptx::smem_u32(smem));
+        const uint32_t tbase = uni(tmem_base);
+        const uint64_t aext_desc = ptx::make_smem_desc_sw128(sbase + OFF_AEXT);
+        uint32_t it = 0, un = 0, et = 0;
+        long long dbg_c0 = 0, dbg_t0 = 0;
+        if (kDbg) {
+            dbg_c0 = clock64();
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+        }
+        ItemCtl nctl{};
+        if (i_first < num_items) nctl = load_part(&items[i_first].ctl);
+        for (int i = i_first; i < num_items; i += i_step) {
+            const int tcols = uni(nctl.tcols), live = uni(nctl.live);
+            if (i + i_step < num_items) nctl = load_part(&items[i + i_step].ctl);
+            if (live == 0 || tcols == 0) continue;
+            const uint32_t cu = un++;
+            const uint32_t ab = cu & 1;
+            const int ntiles = (tcols + BN - 1) / BN;
+            ptx::mbar_wait(&a_full[ab], (cu >> 1) & 1);
+            const uint64_t a_desc0 = ptx::make_smem_desc_sw128(sbase + OFF_A + ab * A_BYTES);
+            for (int tile = 0; tile < ntiles; ++tile, ++it) {
+                const uint32_t es = et & 1;
+                const long long tsp = kDbg ? clock64() : 0;
+                if ((tile & 3) == 0) ptx::mbar_wait(&e_full[es], (et >> 1) & 1);
+                const uint32_t s = it % NS;
+                const uint32_t acc = it & 1;
+                ptx::mbar_wait(&b_full[s], (it / NS) & 1);
+                const long long ts0 = kDbg ? clock64() : 0;
+                ptx::mbar_wait(&t_empty[acc], ((it >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                const long long ts1 = kDbg ? clock64() : 0;
+                const uint64_t b_desc0 = ptx::make_smem_desc_sw128(sbase + OFF_B + s * B_BYTES);
+                // the tile's 32 extension bytes sit at K offset 32*(tile%4) of the super-tile rows
+                const uint64_t e_desc = ptx::make_smem_desc_sw128(sbase + OFF_E + es * E_BYTES) + 2 * (tile & 3);
+                const uint32_t d_tmem = tbase + acc * BN;
+                if (ptx::elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < KBYTES / UMMA_KB; ++k) {
-                            // advancing K by 32 bytes inside the 128-B swizzle atom = +2 in the (addr >> 4) field
-                            ptx::mma_i8_ss_pair(d_tmem, a_desc0 + 2 * k, b_desc0 + 2 * k, idesc, k > 0 ? 1u : 0u);
-                        }
-                        if (dbg_mode != 3) ptx::mma_i8_ss_pair(d_tmem, aext_desc, e_desc, idesc, 1u);     // + e_j
-                        // ONE commit per tile: it frees the train-tile stage (producers), the extension stage when this was
-                        // the super-tile's last tile (producers) and publishes the accumulator (epilogues).  Every extra
-                        // commit or wait lengthens the issuer's latency chain, which is what bounds this kernel.
-                        ptx::mma_commit_pair(&done[it % ND], BOTH_CTAS);
-                        if (dbg && ptx::cluster_id_x() == 0 && it >= 1024 && it < 1024 + 64) {
-                            long long* d = dbg + 4 * 128 + (it - 1024) * 8;
-                            d[0] = ts0; d[1] = ts1; d[2] = clock64(); d[5] = tsp;
-                        }
+                    for (int k = 0; k < KBYTES / UMMA_KB; ++k) {
+                        // advancing K by 32 bytes inside the 128-B swizzle atom = +2 in the (addr >> 4) field
+                        ptx::mma_i8_ss_pair(d_tmem, a_desc0 + 2 * k, b_desc0 + 2 * k, idesc, k > 0 ? 1u : 0u);
                     }
-                    if ((tile & 3) == 3 || tile == ntiles - 1) {
-                        ++et;
-                        have_e = false;
-                    }
+                    ptx::mma_i8_ss_pair(d_tmem, aext_desc, e_desc, idesc, 1u);     // + e_j
+                    // ONE commit per tile: it frees the train-tile stage (producers), the extension stage when this was
+                    // the super-tile's last tile (producers) and publishes the accumulator (epilogues)
+                    ptx::mma_commit_pair(&done[it % ND], BOTH_CTAS);
                 }
-                ptx::mma_commit_pair(&a_empty[ab], BOTH_CTAS);
+                __syncwarp();
+                if (kDbg && lane == 0 && ptx::cluster_id_x() == 0 && it >= 1024 && it < 1024 + 64) {
+                    long long* d = dbg + 4 * 128 + (it - 1024) * 8;
+                    d[0] = ts0; d[1] = ts1; d[2] = clock64(); d[5] = tsp;
+                }
+                if ((tile & 3) == 3 || tile == ntiles - 1) ++et;
             }
-            if (dbg_mode >= 8) { const long long tw = clock64(); while (clock64() - tw < 20000) {} }   // let free-running MMAs drain
-            if (dbg && me == 0) {      // diagnostic (MSFM_K1_DEBUG=1): issue-loop cycles, wall time, tiles of this cluster
-                long long t1;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                long long* d = dbg + 4 * ptx::cluster_id_x();
-                d[0] = clock64() - dbg_c0;
-                d[1] = t1 - dbg_t0;
-                d[2] = it;
-                d[3] = un;
-            }
+            if (ptx::elect_one()) ptx::mma_commit_pair(&a_empty[ab], BOTH_CTAS);
+            __syncwarp();
         }
-    } else if (warp >= EPI_WARP0 && dbg_mode < 9) {
+        if (kDbg && lane == 0) {       // diagnostic (MSFM_K1_DEBUG=1): issue-loop cycles, wall time, tiles of this cluster
+            long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            long long* d = dbg + 4 * ptx::cluster_id_x();
+            d[0] = clock64() - dbg_c0;
+            d[1] = t1 - dbg_t0;
+            d[2] = it;
+            d[3] = un;
+        }
+    } else if (warp >= EPI_WARP0) {
         // ===================================================================== epilogue (both CTAs, own rows)
         const int wg = (warp - EPI_WARP0) >> 2;          // column half of the tile
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;             // query row inside the unit
-        const uint32_t t_empty_leader[2] = {ptx::map_to_cta(ptx::smem_u32(&t_empty[0]), 0),
-                                            ptx::map_to_cta(ptx::smem_u32(&t_empty[1]), 0)};
+        const uint32_t t_empty_leader0 = ptx::map_to_cta(ptx::smem_u32(&t_empty[0]), 0);
+        const uint32_t zneg_addr = ptx::smem_u32(smem + OFF_ZNEG);
         uint32_t it = 0, un = 0;
+        long long ph_work = 0, ph_ld = 0, ph_all = 0, ph_t = kDbg ? clock64() : 0;     // kDbg: cycles per phase of this warp
         ItemEpi nepi{};
         ItemCtl nctl{};
         if (i_first < num_items) { nepi = load_part(&items[i_first].epi); nctl = load_part(&items[i_first].ctl); }
@@ -398,24 +417,26 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
             // ||q_i||^2 (-1 for dead rows): requested now, needed when the pair is finished
             const int32_t ni = (active && wg == 0) ? __ldg(epi.q_nrm + rank * BM + row) : -1;
             int32_t k1 = kIntInf, k2 = kIntInf, g1 = 0;
+            // C_g of this half's 4 groups, requested one tile ahead: an L2 round trip (~800 cycles) is longer than a tile
+            const int4* cg4 = reinterpret_cast<const int4*>(epi.t_cg) + wg;
+            int4 cg_next = (active && ntiles > 0) ? __ldg(cg4) : make_int4(0, 0, 0, 0);
             for (int tile = 0; tile < ntiles; ++tile, ++it) {
                 const uint32_t acc = it & 1;
-                if (!active || dbg_mode == 1 || dbg_mode == 5 || dbg_mode >= 6) {          // all-dead second unit: keep the barrier protocol going
+                if (!active || (kDbg && dbg_mode == 1)) {          // all-dead second unit: keep the barrier protocol going
                     ptx::mbar_wait(&done[it % ND], (it / ND) & 1);
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader[acc]);
+                    if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader0 + acc * 8);
                     continue;
                 }
-                const int4 cgv = __ldg(reinterpret_cast<const int4*>(epi.t_cg) + tile * 2 + wg);   // C_g of this half's 4 groups
+                const int4 cgv = cg_next;
+                if (tile + 1 < ntiles) cg_next = __ldg(cg4 + (tile + 1) * 2);
                 ptx::mbar_wait(&done[it % ND], (it / ND) & 1);
                 ptx::tc_fence_after();
-                const long long te0 = dbg ? clock64() : 0;
+                const long long te0 = kDbg ? clock64() : 0;
+                if (kDbg) { ph_all += te0 - ph_t; ph_t = te0; }      // previous tile's integer work + the wait for this tile
                 const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + wg * 128;
-                // occupied 32-column groups of this warpgroup's half (4 except at the end of the occupied columns;
-                // the groups behind them are all-dead and could never win, skipping them is only cheaper)
-                const int nch = min(4, max(0, (min(BN, tcols - tile * BN) - wg * 128) >> 5));
                 // all four 32-column chunks go to registers first, so that the accumulator stage returns to the tensor
-                // cores after ~one TMEM read time: the loop  MMA done -> t_full -> read -> t_empty -> next MMA issue  must fit
+                // cores after ~one TMEM read time: the loop  MMA done -> read -> t_empty -> next MMA issue  must fit
                 // into the 640 cycles the other stage computes, or the tensor pipe idles
                 uint32_t v[4][32];
 #pragma unroll
@@ -423,36 +444,44 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader[acc]);
-                if (dbg && leader && warp == EPI_WARP0 && lane == 0 && ptx::cluster_id_x() == 0 && it >= 1024 && it < 1024 + 64) {
+                if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader0 + acc * 8);
+                if (kDbg) { const long long t = clock64(); ph_ld += t - ph_t; ph_t = t; }
+                if (kDbg && leader && warp == EPI_WARP0 && lane == 0 && ptx::cluster_id_x() == 0 && it >= 1024 && it < 1024 + 64) {
                     long long* d = dbg + 4 * 128 + (it - 1024) * 8;
                     d[3] = te0; d[4] = clock64();
                 }
-                if (dbg_mode == 2) { k1 = min(k1, static_cast<int32_t>(v[0][0] ^ v[1][1] ^ v[2][2] ^ v[3][3])); continue; }
+                if (kDbg && dbg_mode == 2) { k1 = min(k1, static_cast<int32_t>(v[0][0] ^ v[1][1] ^ v[2][2] ^ v[3][3])); continue; }
+                // The integer work below must not start before the accumulator stage has been handed back: ptxas is free to
+                // sink the arrive (nothing depends on it) under the ~100 ALU instructions of the tile and did so.  Every max
+                // chain is therefore seeded with the neutral element INT_MIN read from shared memory by a volatile load that
+                // program order (and ptxas) keeps behind the arrive.
+                int32_t z;
+                asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(z) : "r"(zneg_addr) : "memory");
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t(&cur)[32] = v[c];
-                    // max over the 32 columns of the group: four independent chains, two elements per VIMNMX3
-                    int32_t m0 = static_cast<int32_t>(cur[0]), m1 = static_cast<int32_t>(cur[1]);
-                    int32_t m2 = static_cast<int32_t>(cur[2]), m3 = static_cast<int32_t>(cur[3]);
+                    // max over the 32 columns of the group: two independent chains, two elements per VIMNMX3
+                    int32_t m0 = __vimax3_s32(z, static_cast<int32_t>(cur[0]), static_cast<int32_t>(cur[1]));
+                    int32_t m1 = __vimax3_s32(z, static_cast<int32_t>(cur[2]), static_cast<int32_t>(cur[3]));
 #pragma unroll
-                    for (int e = 4; e < 28; e += 8) {
+                    for (int e = 4; e < 32; e += 4) {
                         m0 = __vimax3_s32(m0, static_cast<int32_t>(cur[e + 0]), static_cast<int32_t>(cur[e + 1]));
                         m1 = __vimax3_s32(m1, static_cast<int32_t>(cur[e + 2]), static_cast<int32_t>(cur[e + 3]));
-                        m2 = __vimax3_s32(m2, static_cast<int32_t>(cur[e + 4]), static_cast<int32_t>(cur[e + 5]));
-                        m3 = __vimax3_s32(m3, static_cast<int32_t>(cur[e + 6]), static_cast<int32_t>(cur[e + 7]));
                     }
-                    m0 = __vimax3_s32(m0, static_cast<int32_t>(cur[28]), static_cast<int32_t>(cur[29]));
-                    m1 = __vimax3_s32(m1, static_cast<int32_t>(cur[30]), static_cast<int32_t>(cur[31]));
-                    const int32_t m = max(__vimax3_s32(m0, m1, m2), m3);
+                    const int32_t m = max(m0, m1);
+                    if (kDbg && dbg_mode == 3) { k1 = min(k1, m); continue; }       // diagnostic: group maxima only
                     const int32_t cgc = (c == 0) ? cgv.x : (c == 1) ? cgv.y : (c == 2) ? cgv.z : cgv.w;
                     const int32_t key = cgc - 2 * m;      // = min over the group of (||d_j||^2 - 2 q.d_j)
-                    // insert the group minimum into the running (best, best-of-other-groups)
-                    if (c < nch) {
-                        k2 = min(k2, max(k1, key));
-                        if (key < k1) g1 = tile * 8 + wg * 4 + c;
-                        k1 = min(k1, key);
-                    }
+                    // insert the group minimum into the running (best, best-of-other-groups); all-dead groups (also the
+                    // ones behind the occupied columns of the last tile) carry C_g = kDeadCg and can never win
+                    k2 = min(k2, max(k1, key));
+                    if (key < k1) g1 = tile * 8 + wg * 4 + c;
+                    k1 = min(k1, key);
+                }
+                if (kDbg) {      // k1, k2 are inputs so that the stamp cannot be hoisted above the integer work
+                    long long t;
+                    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(k1), "r"(k2) : "memory");
+                    ph_work += t - ph_t;
                 }
             }
             if (!active) continue;
@@ -472,6 +501,10 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
                 res_d1[out] = have1 ? (k1 + ni) : kIntInf;
                 res_u[out] = have2 ? (k2 + ni) : kIntInf;
             }
+        }
+        if (kDbg && lane == 0 && ptx::cluster_id_x() == 0) {
+            long long* d = dbg + 4 * 128 + 64 * 8 + (rank * 8 + (warp - EPI_WARP0)) * 4;
+            d[0] = ph_ld; d[1] = ph_work; d[2] = ph_all; d[3] = it;
         }
     }
 
@@ -494,11 +527,11 @@ cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, i
         return e && e[0] == '1';
     }();
     if (single) return launch_match_tile_single(imgs, units, unit0, num_units, res_g, res_d1, res_u, num_sms, stream);
-    static const int issuers = [] {
-        const char* e = std::getenv("MSFM_K1_ISSUERS");      // diagnostic A/B switch: MMA issuer threads of the leader CTA
-        return (e && e[0] == '2') ? 2 : 1;
+    static const int debug = [] {
+        const char* e = std::getenv("MSFM_K1_DEBUG");       // 1: timeline + cycles; 11: no TMEM reads, 12: no integer work, 13: group maxima only (results garbage)
+        return e ? atoi(e) : 0;
     }();
-    auto kernel = issuers == 2 ? k1::match_pair_kernel<2> : k1::match_pair_kernel<1>;
+    auto kernel = debug ? k1::match_pair_kernel<true> : k1::match_pair_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(k1::SMEM_BYTES));
     if (e != cudaSuccess) return e;
     if (num_units <= 0) return cudaSuccess;
@@ -508,20 +541,16 @@ cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, i
     if (clusters <= 0) return cudaErrorInvalidConfiguration;
     k1::Item* items = static_cast<k1::Item*>(item_scratch);
     k1::build_items_kernel<<<(num_items + 255) / 256, 256, 0, stream>>>(imgs, units, unit0, num_items, items);
-    static const int debug = [] {
-        const char* e = std::getenv("MSFM_K1_DEBUG");       // 1: timing only; 11/12/13: + knock out a part (results garbage)
-        return e ? atoi(e) : 0;
-    }();
     long long* dbg = nullptr;
     if (debug) {
         static long long* d_dbg = nullptr;
-        if (!d_dbg) cudaMalloc(&d_dbg, (4 * 128 + 64 * 8) * sizeof(long long));
+        if (!d_dbg) cudaMalloc(&d_dbg, (4 * 128 + 64 * 8 + 64) * sizeof(long long));
         dbg = d_dbg;
-        cudaMemsetAsync(dbg, 0, (4 * 128 + 64 * 8) * sizeof(long long), stream);
+        cudaMemsetAsync(dbg, 0, (4 * 128 + 64 * 8 + 64) * sizeof(long long), stream);
     }
     kernel<<<2 * clusters, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(items, num_items, res_g, res_d1, res_u, dbg, debug > 10 ? debug - 10 : 0);
     if (debug) {
-        long long h[4 * 128 + 64 * 8];
+        long long h[4 * 128 + 64 * 8 + 64];
         cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, stream);
         cudaStreamSynchronize(stream);
         double cyc = 0, ns = 0, tiles = 0;
@@ -550,6 +579,13 @@ cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, i
                     fprintf(stderr, "K1 raw tile %d (stage %d): top %lld b_full %lld t_empty %lld committed %lld | epi done-seen %lld released %lld\n",
                             k, k & 1, a[5] - base, a[0] - base, a[1] - base, a[2] - base, a[3] - base, a[4] - base);
                 }
+            }
+            if (std::getenv("MSFM_K1_DEBUG_RAW")) {
+                const long long* w = h + 4 * 128 + 64 * 8;
+                for (int k = 0; k < 16; ++k)
+                    if (w[4 * k + 3] > 0)
+                        fprintf(stderr, "K1 epilogue warp cta%d w%d (subpartition %d, wg %d): per tile  TMEM read+release %.0f | integer work %.0f | work + wait for next tile %.0f\n",
+                                k / 8, 4 + k % 8, k % 4, (k % 8) / 4, double(w[4 * k]) / w[4 * k + 3], double(w[4 * k + 1]) / w[4 * k + 3], double(w[4 * k + 2]) / w[4 * k + 3]);
             }
             if (m) fprintf(stderr, "K1 timeline (avg of %d tiles): wait_t_empty %.0f | issue %.0f | commit->done %.0f | epi ld+arrive %.0f | arrive->issuer %.0f\n",
                            m, w_te / m, issue / m, exec / m, epi / m, back / m);

@@ -79,7 +79,6 @@ constexpr uint32_t OFF_BAR = OFF_MERGE + 2 * 128 * 16;
 constexpr int ND = 2 * NS;                   // ring of per-tile "MMAs done" barriers
 constexpr uint32_t NUM_BARS = 2 + 2 + NS + NE + ND + 2;
 constexpr uint32_t OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
-constexpr uint32_t OFF_ZNEG = OFF_TMEMPTR + 8;                  // one s32 holding INT_MIN (see the epilogue)
 constexpr uint32_t SMEM_USED = OFF_TMEMPTR + 16;
 constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;               // slack for manual 1024-B alignment
 
@@ -213,14 +212,13 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&a_full[i], full_count);
             ptx::mbar_init(&a_empty[i], 1);
-            ptx::mbar_init(&t_empty[i], 2 * EPI_WARPS);
+            ptx::mbar_init(&t_empty[i], EPI_WARPS);          // the 4 warps of the stage's warpgroup in each CTA
         }
         for (int i = 0; i < NS; ++i) ptx::mbar_init(&b_full[i], full_count);
         for (int i = 0; i < NE; ++i) ptx::mbar_init(&e_full[i], full_count);
         for (int i = 0; i < ND; ++i) ptx::mbar_init(&done[i], 1);
         ptx::fence_mbar_init();
     }
-    if (threadIdx.x == 0) *reinterpret_cast<volatile int32_t*>(smem + OFF_ZNEG) = static_cast<int32_t>(0x80000000);
     if (warp == 2) ptx::tmem_alloc_pair<512>(tmem_ptr);
     ptx::tc_fence_before();
     ptx::cluster_sync();                 // barriers of BOTH CTAs are initialised before anyone arrives remotely
@@ -351,9 +349,8 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
                 if ((tile & 3) == 0) ptx::mbar_wait(&e_full[es], (et >> 1) & 1);
                 const uint32_t s = it % NS;
                 const uint32_t acc = it & 1;
-                ptx::mbar_wait(&b_full[s], (it / NS) & 1);
                 const long long ts0 = kDbg ? clock64() : 0;
-                ptx::mbar_wait(&t_empty[acc], ((it >> 1) & 1) ^ 1);
+                ptx::mbar_wait2(&b_full[s], (it / NS) & 1, &t_empty[acc], ((it >> 1) & 1) ^ 1);
                 ptx::tc_fence_after();
                 const long long ts1 = kDbg ? clock64() : 0;
                 const uint64_t b_desc0 = ptx::make_smem_desc_sw128(sbase + OFF_B + s * B_BYTES);
@@ -372,9 +369,15 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
                     ptx::mma_commit_pair(&done[it % ND], BOTH_CTAS);
                 }
                 __syncwarp();
+                const long long ts2 = kDbg ? clock64() : 0;
+                long long ts3 = 0;
+                if (kDbg && dbg_mode == 5) {       // diagnostic: the issuer itself waits for the tile's MMAs (serialises the tiles)
+                    ptx::mbar_wait(&done[it % ND], (it / ND) & 1);
+                    ts3 = clock64();
+                }
                 if (kDbg && lane == 0 && ptx::cluster_id_x() == 0 && it >= 1024 && it < 1024 + 64) {
                     long long* d = dbg + 4 * 128 + (it - 1024) * 8;
-                    d[0] = ts0; d[1] = ts1; d[2] = clock64(); d[5] = tsp;
+                    d[0] = ts0; d[1] = ts1; d[2] = ts2; d[5] = tsp; d[6] = ts3;
                 }
                 if ((tile & 3) == 3 || tile == ntiles - 1) ++et;
             }
@@ -392,13 +395,12 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
         }
     } else if (warp >= EPI_WARP0) {
         // ===================================================================== epilogue (both CTAs, own rows)
-        const int wg = (warp - EPI_WARP0) >> 2;          // column half of the tile
+        const int wg = (warp - EPI_WARP0) >> 2;          // accumulator stage (tile parity) this warpgroup serves
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;             // query row inside the unit
         const uint32_t t_empty_leader0 = ptx::map_to_cta(ptx::smem_u32(&t_empty[0]), 0);
-        const uint32_t zneg_addr = ptx::smem_u32(smem + OFF_ZNEG);
         uint32_t it = 0, un = 0;
-        long long ph_work = 0, ph_ld = 0, ph_all = 0, ph_t = kDbg ? clock64() : 0;     // kDbg: cycles per phase of this warp
+        long long ph_work = 0, ph_ld = 0, ph_all = 0, ph_z = 0, ph_t = kDbg ? clock64() : 0;     // kDbg: cycles per phase of this warp
         ItemEpi nepi{};
         ItemCtl nctl{};
         if (i_first < num_items) { nepi = load_part(&items[i_first].epi); nctl = load_part(&items[i_first].ctl); }
@@ -417,67 +419,83 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
             // ||q_i||^2 (-1 for dead rows): requested now, needed when the pair is finished
             const int32_t ni = (active && wg == 0) ? __ldg(epi.q_nrm + rank * BM + row) : -1;
             int32_t k1 = kIntInf, k2 = kIntInf, g1 = 0;
-            // C_g of this half's 4 groups, requested one tile ahead: an L2 round trip (~800 cycles) is longer than a tile
-            const int4* cg4 = reinterpret_cast<const int4*>(epi.t_cg) + wg;
-            int4 cg_next = (active && ntiles > 0) ? __ldg(cg4) : make_int4(0, 0, 0, 0);
+            // C_g of the 8 groups of a tile, requested one own tile (= two tiles) ahead: an L2 round trip (~800 cycles) is
+            // longer than a tile
+            const int4* cg8 = reinterpret_cast<const int4*>(epi.t_cg);
+            const int tfirst = ((it & 1) == static_cast<uint32_t>(wg)) ? 0 : 1;          // first tile of this pair in my stage
+            int4 cg_next0 = make_int4(0, 0, 0, 0), cg_next1 = cg_next0;
+            if (active && tfirst < ntiles) { cg_next0 = __ldg(cg8 + tfirst * 2); cg_next1 = __ldg(cg8 + tfirst * 2 + 1); }
             for (int tile = 0; tile < ntiles; ++tile, ++it) {
                 const uint32_t acc = it & 1;
+                if (acc != static_cast<uint32_t>(wg)) continue;       // the other warpgroup's accumulator stage
                 if (!active || (kDbg && dbg_mode == 1)) {          // all-dead second unit: keep the barrier protocol going
                     ptx::mbar_wait(&done[it % ND], (it / ND) & 1);
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader0 + acc * 8);
                     continue;
                 }
-                const int4 cgv = cg_next;
-                if (tile + 1 < ntiles) cg_next = __ldg(cg4 + (tile + 1) * 2);
+                const int4 cgv0 = cg_next0, cgv1 = cg_next1;
+                if (tile + 2 < ntiles) { cg_next0 = __ldg(cg8 + (tile + 2) * 2); cg_next1 = __ldg(cg8 + (tile + 2) * 2 + 1); }
                 ptx::mbar_wait(&done[it % ND], (it / ND) & 1);
                 ptx::tc_fence_after();
                 const long long te0 = kDbg ? clock64() : 0;
                 if (kDbg) { ph_all += te0 - ph_t; ph_t = te0; }      // previous tile's integer work + the wait for this tile
-                const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + wg * 128;
-                // all four 32-column chunks go to registers first, so that the accumulator stage returns to the tensor
-                // cores after ~one TMEM read time: the loop  MMA done -> read -> t_empty -> next MMA issue  must fit
-                // into the 640 cycles the other stage computes, or the tensor pipe idles
+                const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
                 uint32_t v[4][32];
+                // group maxima of the four 32-column groups in v, inserted into the running (best, best-of-other-groups);
+                // all-dead groups (also the ones behind the occupied columns of the last tile) carry C_g = kDeadCg and
+                // can never win.  Every max chain starts from `seed` (a neutral element).
+                auto reduce4 = [&](const int4 cgv, const int gbase, const int32_t seed) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t(&cur)[32] = v[c];
+                        // max over the 32 columns of the group: two independent chains, two elements per VIMNMX3
+                        int32_t m0 = __vimax3_s32(seed, static_cast<int32_t>(cur[0]), static_cast<int32_t>(cur[1]));
+                        int32_t m1 = __vimax3_s32(seed, static_cast<int32_t>(cur[2]), static_cast<int32_t>(cur[3]));
+#pragma unroll
+                        for (int e = 4; e < 32; e += 4) {
+                            m0 = __vimax3_s32(m0, static_cast<int32_t>(cur[e + 0]), static_cast<int32_t>(cur[e + 1]));
+                            m1 = __vimax3_s32(m1, static_cast<int32_t>(cur[e + 2]), static_cast<int32_t>(cur[e + 3]));
+                        }
+                        const int32_t m = max(m0, m1);
+                        if (kDbg && dbg_mode == 3) { k1 = min(k1, m); continue; }       // diagnostic: group maxima only
+                        const int32_t cgc = (c == 0) ? cgv.x : (c == 1) ? cgv.y : (c == 2) ? cgv.z : cgv.w;
+                        const int32_t key = cgc - 2 * m;      // = min over the group of (||d_j||^2 - 2 q.d_j)
+                        k2 = min(k2, max(k1, key));
+                        if (key < k1) g1 = gbase + c;
+                        k1 = min(k1, key);
+                    }
+                };
+                // ---- columns 0..127 of the tile: read, reduce
 #pragma unroll
                 for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32(taddr0 + c * 32, v[c]);
+                ptx::tmem_ld_wait();
+                if (!(kDbg && dbg_mode == 2)) reduce4(cgv0, tile * 8, static_cast<int32_t>(0x80000000));
+                // ---- columns 128..255: read, hand the accumulator stage back, reduce
+#pragma unroll
+                for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32(taddr0 + 128 + c * 32, v[c]);
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader0 + acc * 8);
                 if (kDbg) { const long long t = clock64(); ph_ld += t - ph_t; ph_t = t; }
-                if (kDbg && leader && warp == EPI_WARP0 && lane == 0 && ptx::cluster_id_x() == 0 && it >= 1024 && it < 1024 + 64) {
+                if (kDbg && leader && quarter == 0 && lane == 0 && ptx::cluster_id_x() == 0 && it >= 1024 && it < 1024 + 64) {
                     long long* d = dbg + 4 * 128 + (it - 1024) * 8;
                     d[3] = te0; d[4] = clock64();
                 }
                 if (kDbg && dbg_mode == 2) { k1 = min(k1, static_cast<int32_t>(v[0][0] ^ v[1][1] ^ v[2][2] ^ v[3][3])); continue; }
-                // The integer work below must not start before the accumulator stage has been handed back: ptxas is free to
-                // sink the arrive (nothing depends on it) under the ~100 ALU instructions of the tile and did so.  Every max
-                // chain is therefore seeded with the neutral element INT_MIN read from shared memory by a volatile load that
-                // program order (and ptxas) keeps behind the arrive.
-                int32_t z;
-                asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(z) : "r"(zneg_addr) : "memory");
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t(&cur)[32] = v[c];
-                    // max over the 32 columns of the group: two independent chains, two elements per VIMNMX3
-                    int32_t m0 = __vimax3_s32(z, static_cast<int32_t>(cur[0]), static_cast<int32_t>(cur[1]));
-                    int32_t m1 = __vimax3_s32(z, static_cast<int32_t>(cur[2]), static_cast<int32_t>(cur[3]));
-#pragma unroll
-                    for (int e = 4; e < 32; e += 4) {
-                        m0 = __vimax3_s32(m0, static_cast<int32_t>(cur[e + 0]), static_cast<int32_t>(cur[e + 1]));
-                        m1 = __vimax3_s32(m1, static_cast<int32_t>(cur[e + 2]), static_cast<int32_t>(cur[e + 3]));
-                    }
-                    const int32_t m = max(m0, m1);
-                    if (kDbg && dbg_mode == 3) { k1 = min(k1, m); continue; }       // diagnostic: group maxima only
-                    const int32_t cgc = (c == 0) ? cgv.x : (c == 1) ? cgv.y : (c == 2) ? cgv.z : cgv.w;
-                    const int32_t key = cgc - 2 * m;      // = min over the group of (||d_j||^2 - 2 q.d_j)
-                    // insert the group minimum into the running (best, best-of-other-groups); all-dead groups (also the
-                    // ones behind the occupied columns of the last tile) carry C_g = kDeadCg and can never win
-                    k2 = min(k2, max(k1, key));
-                    if (key < k1) g1 = tile * 8 + wg * 4 + c;
-                    k1 = min(k1, key);
+                // The second reduction must not start before the stage has been handed back: ptxas is free to sink the arrive
+                // (nothing depends on it) under the ALU instructions and did so.  The chains are therefore seeded with a
+                // neutral element (INT_MIN or INT_MIN + 1) derived from a clock read that stays behind the arrive.
+                uint32_t clk;
+                asm volatile("mov.u32 %0, %%clock;" : "=r"(clk) : : "memory");
+                const int32_t z = static_cast<int32_t>(0x80000000u | (clk & 1u));
+                if (kDbg) {      // latency of the seed load (shared memory is busy with tensor-core operand reads)
+                    long long t;
+                    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(z) : "memory");
+                    ph_z += t - ph_t;
                 }
+                reduce4(cgv1, tile * 8 + 4, z);
                 if (kDbg) {      // k1, k2 are inputs so that the stamp cannot be hoisted above the integer work
                     long long t;
                     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(k1), "r"(k2) : "memory");
@@ -485,7 +503,7 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
                 }
             }
             if (!active) continue;
-            // ---- unit end: fold the two column halves, write the row results
+            // ---- unit end: fold the results of the two warpgroups (even / odd tiles), write the row results
             int4* mbuf = smMerge + (cu & 1) * 128;
             if (wg == 1) mbuf[row] = make_int4(k1, k2, g1, 0);
             ptx::bar_sync(1, EPI_THREADS);
@@ -504,7 +522,7 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
         }
         if (kDbg && lane == 0 && ptx::cluster_id_x() == 0) {
             long long* d = dbg + 4 * 128 + 64 * 8 + (rank * 8 + (warp - EPI_WARP0)) * 4;
-            d[0] = ph_ld; d[1] = ph_work; d[2] = ph_all; d[3] = it;
+            d[0] = ph_ld; d[1] = ph_work; d[2] = ph_all; d[3] = it / 2; d[64] = ph_z;
         }
     }
 
@@ -544,13 +562,13 @@ cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, i
     long long* dbg = nullptr;
     if (debug) {
         static long long* d_dbg = nullptr;
-        if (!d_dbg) cudaMalloc(&d_dbg, (4 * 128 + 64 * 8 + 64) * sizeof(long long));
+        if (!d_dbg) cudaMalloc(&d_dbg, (4 * 128 + 64 * 8 + 128) * sizeof(long long));
         dbg = d_dbg;
-        cudaMemsetAsync(dbg, 0, (4 * 128 + 64 * 8 + 64) * sizeof(long long), stream);
+        cudaMemsetAsync(dbg, 0, (4 * 128 + 64 * 8 + 128) * sizeof(long long), stream);
     }
     kernel<<<2 * clusters, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(items, num_items, res_g, res_d1, res_u, dbg, debug > 10 ? debug - 10 : 0);
     if (debug) {
-        long long h[4 * 128 + 64 * 8 + 64];
+        long long h[4 * 128 + 64 * 8 + 128];
         cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, stream);
         cudaStreamSynchronize(stream);
         double cyc = 0, ns = 0, tiles = 0;
@@ -584,8 +602,13 @@ cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, i
                 const long long* w = h + 4 * 128 + 64 * 8;
                 for (int k = 0; k < 16; ++k)
                     if (w[4 * k + 3] > 0)
-                        fprintf(stderr, "K1 epilogue warp cta%d w%d (subpartition %d, wg %d): per tile  TMEM read+release %.0f | integer work %.0f | work + wait for next tile %.0f\n",
-                                k / 8, 4 + k % 8, k % 4, (k % 8) / 4, double(w[4 * k]) / w[4 * k + 3], double(w[4 * k + 1]) / w[4 * k + 3], double(w[4 * k + 2]) / w[4 * k + 3]);
+                        fprintf(stderr, "K1 epilogue warp cta%d w%d (subpartition %d, wg %d): per own tile  done -> release %.0f | seed %.0f | integer work after release %.0f | work + wait for next tile %.0f\n",
+                                k / 8, 4 + k % 8, k % 4, (k % 8) / 4, double(w[4 * k]) / w[4 * k + 3], double(w[4 * k + 64]) / w[4 * k + 3], double(w[4 * k + 1]) / w[4 * k + 3], double(w[4 * k + 2]) / w[4 * k + 3]);
+            }
+            {
+                double own = 0; int mo = 0;
+                for (int k = 2; k < 62; ++k) { const long long* a = ts + 8 * k; if (a[6] && a[2]) { own += double(a[6] - a[2]); ++mo; } }
+                if (mo) fprintf(stderr, "K1 issuer: commit issued -> own observation of the tile's completion: %.0f cycles (avg of %d)\n", own / mo, mo);
             }
             if (m) fprintf(stderr, "K1 timeline (avg of %d tiles): wait_t_empty %.0f | issue %.0f | commit->done %.0f | epi ld+arrive %.0f | arrive->issuer %.0f\n",
                            m, w_te / m, issue / m, exec / m, epi / m, back / m);

@@ -68,6 +68,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Two barriers, one shared-memory round trip: under tensor-core load a generic shared-memory access (and therefore
+// every mbarrier poll) takes ~280 cycles, so waits that are issued back to back instead of one after the other halve the
+// latency of a loop that needs both (profiles/r01b_k1_phase_timeline.log).
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+    const uint32_t a = smem_u32(bar_a), b = smem_u32(bar_b);
+    uint32_t oka, okb;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P, Q;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%2], %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 Q, [%4], %5;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "selp.b32 %1, 1, 0, Q;\n\t"
+        "}\n"
+        : "=r"(oka), "=r"(okb)
+        : "r"(a), "r"(parity_a), "r"(b), "r"(parity_b)
+        : "memory");
+    if (!oka) mbar_wait(bar_a, parity_a);
+    if (!okb) mbar_wait(bar_b, parity_b);
+}
+
 // ---------------------------------------------------------------- thread-block cluster (CTA pair) helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

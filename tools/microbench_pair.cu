@@ -118,6 +118,11 @@ k_pair(int iters, long long* cyc, long long* stamps, int* sink) {
         }
     } else if (warp >= 4 && EPI >= 2) {
         const int quarter = warp & 3, wg = (warp - 4) >> 2;
+        long long ph_ld = 0, ph_work = 0, ph_all = 0, ph_t = clock64();
+        __shared__ int zneg;
+        if (threadIdx.x == 128) *reinterpret_cast<volatile int*>(&zneg) = static_cast<int>(0x80000000);
+        const uint32_t zaddr = ptx::smem_u32(&zneg);
+        int k1 = 0x7fffffff, k2 = 0x7fffffff, g1 = 0;
         const uint32_t te[4] = {ptx::map_to_cta(ptx::smem_u32(&t_empty[0]), 0), ptx::map_to_cta(ptx::smem_u32(&t_empty[1 % STAGES]), 0),
                                 ptx::map_to_cta(ptx::smem_u32(&t_empty[2 % STAGES]), 0), ptx::map_to_cta(ptx::smem_u32(&t_empty[3 % STAGES]), 0)};
         for (int it = 0; it < iters; ++it) {
@@ -125,6 +130,7 @@ k_pair(int iters, long long* cyc, long long* stamps, int* sink) {
             ptx::mbar_wait(&done[it % ND], (it / ND) & 1);
             ptx::tc_fence_after();
             const long long e0 = clock64();
+            ph_all += e0 - ph_t; ph_t = e0;
             if (EPI >= 3) {
                 constexpr int NCH = N / 64;          // 32-column chunks of this warpgroup's half
                 uint32_t v[NCH][32];
@@ -135,10 +141,34 @@ k_pair(int iters, long long* cyc, long long* stamps, int* sink) {
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive_cluster(te[st]);
+                { const long long t = clock64(); ph_ld += t - ph_t; ph_t = t; }
                 if (stamps && rank == 0 && warp == 4 && lane == 0 && blockIdx.x == 0 && it >= 512 && it < 512 + 32) {
                     long long* d = stamps + (it - 512) * 12;
                     d[10] = e0; d[11] = clock64();
                 }
+                if (EPI == 5) {          // the arithmetic of the real K1 epilogue (N = 256 only)
+                    int z;
+                    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(z) : "r"(zaddr) : "memory");
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        int m0 = __vimax3_s32(z, static_cast<int>(v[c][0]), static_cast<int>(v[c][1]));
+                        int m1 = __vimax3_s32(z, static_cast<int>(v[c][2]), static_cast<int>(v[c][3]));
+#pragma unroll
+                        for (int e = 4; e < 32; e += 4) {
+                            m0 = __vimax3_s32(m0, static_cast<int>(v[c][e]), static_cast<int>(v[c][e + 1]));
+                            m1 = __vimax3_s32(m1, static_cast<int>(v[c][e + 2]), static_cast<int>(v[c][e + 3]));
+                        }
+                        const int m = max(m0, m1);
+                        const int key = (it * 977 + c * 31) - 2 * m;
+                        k2 = min(k2, max(k1, key));
+                        if (key < k1) g1 = it * 8 + wg * 4 + c;
+                        k1 = min(k1, key);
+                    }
+                    long long t;
+                    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(k1), "r"(k2) : "memory");
+                    ph_work += t - ph_t;
+                    acc_sink = k1 ^ k2 ^ g1;
+                } else
                 if (EPI >= 4) {
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
@@ -163,6 +193,10 @@ k_pair(int iters, long long* cyc, long long* stamps, int* sink) {
                 }
             }
         }
+        if (stamps && blockIdx.x < 2 && lane == 0) {
+            long long* d = stamps + 32 * 12 + (rank * 8 + (warp - 4)) * 4;
+            d[0] = ph_ld; d[1] = ph_work; d[2] = ph_all; d[3] = iters;
+        }
     }
     if (acc_sink == 0x7654321) sink[0] = acc_sink;
     ptx::tc_fence_before();
@@ -175,7 +209,7 @@ static int run(int G, long long* d_cyc, long long* d_stamps, int* d_sink, const 
     auto k = k_pair<N, ISSUERS, EPI, DESC, UNI>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 140000) != cudaSuccess) return 1;
     const int iters = 4096;
-    cudaMemset(d_stamps, 0, 32 * 12 * 8);
+    cudaMemset(d_stamps, 0, (32 * 12 + 64) * 8);
     for (int rep = 0; rep < 2; ++rep) k<<<G, 384, 140000>>>(iters, d_cyc, print_stamps ? d_stamps : nullptr, d_sink);
     if (cudaDeviceSynchronize() != cudaSuccess) { printf("%s failed: %s\n", name, cudaGetErrorString(cudaGetLastError())); return 1; }
     static long long h[512];
@@ -183,8 +217,12 @@ static int run(int G, long long* d_cyc, long long* d_stamps, int* d_sink, const 
     double s = 0; for (int i = 0; i < G / 2; ++i) s += h[i];
     printf("pair %-52s: %7.1f cyc per tile (5 MMAs 256x%dx32, floor %d)\n", name, s / (G / 2) / iters, N, 5 * N / 2);
     if (print_stamps) {
-        static long long st[32 * 12];
+        static long long st[32 * 12 + 64];
         cudaMemcpy(st, d_stamps, sizeof(st), cudaMemcpyDeviceToHost);
+        for (int k = 0; k < 16; k += 5)
+            if (st[32 * 12 + 4 * k + 3] > 0)
+                printf("   epilogue warp cta%d w%d: per tile  TMEM read+release %.0f | integer work %.0f | work + wait %.0f\n", k / 8, 4 + k % 8,
+                       double(st[32 * 12 + 4 * k]) / iters, double(st[32 * 12 + 4 * k + 1]) / iters, double(st[32 * 12 + 4 * k + 2]) / iters);
         const long long base = st[4];
         for (int t = 0; t < 12; ++t) {
             const long long* d = st + t * 12;
@@ -202,7 +240,7 @@ int main() {
     printf("device %s SMs=%d\n", p.name, p.multiProcessorCount);
     const int G = p.multiProcessorCount / 2 * 2;
     long long *d_cyc, *d_stamps; int* d_sink;
-    CK(cudaMalloc(&d_cyc, 512 * 8)); CK(cudaMalloc(&d_stamps, 32 * 12 * 8)); CK(cudaMalloc(&d_sink, 64));
+    CK(cudaMalloc(&d_cyc, 512 * 8)); CK(cudaMalloc(&d_stamps, (32 * 12 + 64) * 8)); CK(cudaMalloc(&d_sink, 64));
     run<256, 1, 0>(G, d_cyc, d_stamps, d_sink, "N=256 1 issuer, free-running", true);
     run<256, 1, 0>(G, d_cyc, d_stamps, d_sink, "N=256 1 issuer, free-running (no stamps)", false);
     run<256, 2, 0>(G, d_cyc, d_stamps, d_sink, "N=256 2 issuers, free-running", false);
@@ -221,6 +259,7 @@ int main() {
     run<256, 1, 3, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, epilogue reads TMEM, per-tile desc", false);
     run<256, 1, 4, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, epilogue reads + max, per-tile desc", false);
     run<256, 2, 4, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 2 issuers, epilogue reads + max, per-tile desc", false);
+    run<256, 1, 5, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, REAL epilogue arithmetic", true);
     run<128, 1, 3, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=128 1 issuer, 4 stages, epilogue reads TMEM", false);
     run<128, 1, 4, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=128 1 issuer, 4 stages, epilogue reads + max", false);
     run<128, 2, 4, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=128 2 issuers, 4 stages, epilogue reads + max", false);

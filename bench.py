@@ -453,7 +453,7 @@ def run_ours(args, rank, world, local_rank):
             with open(tpath) as f:
                 tj = json.load(f)
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
-        roofline = {"bound": "tensor", "kernel": "match_tile_kernel", "achieved": achieved, "peak": peak_int8,
+        roofline = {"bound": "tensor", "kernel": "match_pair_kernel", "achieved": achieved, "peak": peak_int8,
                     "unit": "TOP/s", "frac": achieved / peak_int8 if peak_int8 else None, "traffic": traffic,
                     "traffic_source": traffic_src,
                     "peak_note": f"2 x cuBLAS bf16 sustained ({peaks['bf16_tflops_sustained']} TF/s, {peaks['source']} "

@@ -20,6 +20,7 @@ using ba::Problem;
 cudaError_t ba_launch_cam_prep(const double*, int, CamPre*, cudaStream_t);
 cudaError_t ba_launch_evaluate(const Problem&, double*, float*, double*, int, cudaStream_t);
 cudaError_t ba_launch_linearize(const Problem&, double, double*, int, cudaStream_t);
+cudaError_t ba_launch_compact_blocks(const int32_t*, long long, int32_t*, int32_t*, int, cudaStream_t);
 cudaError_t ba_launch_count_tuples(const Problem&, int32_t*, int, cudaStream_t);
 cudaError_t ba_launch_scan_tuples(const int32_t*, long long, int32_t*, int32_t*, cudaStream_t);
 cudaError_t ba_launch_fill_tuples(const Problem&, int32_t*, int2*, int, cudaStream_t);
@@ -80,6 +81,8 @@ struct msfm_ba {
     // gather structures + per-linearisation intermediates (ba_types.cuh)
     int32_t *cam_obs_start = nullptr, *cam_obs_list = nullptr, *blk_start = nullptr;
     int2* blk_tuples = nullptr;
+    int32_t* blk_list = nullptr;
+    int32_t n_blk_list = 0;
     float* obs_J = nullptr;
     double *obs_r = nullptr, *pt_Vinv = nullptr, *pt_gp = nullptr;
     double* work = nullptr;       // cusolver workspace
@@ -97,6 +100,7 @@ struct msfm_ba {
         P.pt_start = pt_start; P.cam_free = cam_free;
         P.gpmax_bits = reinterpret_cast<unsigned long long*>(small + 4);
         P.cam_obs_start = cam_obs_start; P.cam_obs_list = cam_obs_list; P.blk_start = blk_start; P.blk_tuples = blk_tuples;
+        P.blk_list = blk_list; P.n_blk_list = n_blk_list;
         P.obs_J = obs_J; P.obs_r = obs_r; P.pt_Vinv = pt_Vinv; P.pt_gp = pt_gp;
         return P;
     }
@@ -144,7 +148,7 @@ void msfm_ba_destroy(msfm_ba* b) {
     cudaStreamSynchronize(c->stream);
     void* ptrs[] = {b->cams[0], b->cams[1], b->pts[0], b->pts[1], b->pre[0], b->pre[1], b->obs_uv, b->obs_cam, b->obs_pt,
                     b->pt_start, b->cam_free, b->sys, b->xsol, b->small, b->work, b->dev_info, b->cam_obs_start,
-                    b->cam_obs_list, b->blk_start, b->blk_tuples, b->obs_J, b->obs_r, b->pt_Vinv, b->pt_gp};
+                    b->cam_obs_list, b->blk_start, b->blk_tuples, b->blk_list, b->obs_J, b->obs_r, b->pt_Vinv, b->pt_gp};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -258,10 +262,16 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->blk_tuples), std::max<size_t>(16, size_t(total) * sizeof(int2)));
         if (e == cudaSuccess) e = ba_launch_fill_tuples(b->view(0), cursor, b->blk_tuples, c->num_sms, c->stream);
+        // compact list of the non-empty blocks (at most one per tuple); `counts` is free again and serves as the counter
+        const size_t max_list = static_cast<size_t>(std::min<long long>(nblk, total));
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->blk_list), std::max<size_t>(16, max_list * sizeof(int32_t)));
+        if (e == cudaSuccess) e = cudaMemsetAsync(counts, 0, sizeof(int32_t), c->stream);
+        if (e == cudaSuccess) e = ba_launch_compact_blocks(b->blk_start, nblk, b->blk_list, counts, c->num_sms, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&b->n_blk_list, counts, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (counts) cudaFree(counts);
         if (cursor) cudaFree(cursor);
-        c->launches += 3;
+        c->launches += 4;
         if (e != cudaSuccess) return fail_free(c->cuda_fail(e, "msfm_ba_create: building the gather lists"));
     }
     *out = b;

@@ -342,21 +342,25 @@ camera_diag_kernel(Problem P, double* __restrict__ sys) {
     }
 }
 
-// Pass B — one warp per non-empty camera-pair block (fa < fb): - sum over co-observing points of Y_a W_b^T.
-__global__ void __launch_bounds__(256)
+// Pass B — one CTA (4 warps) per non-empty camera-pair block (fa < fb): - sum over co-observing points of Y_a W_b^T.
+// The tuples of a block are spread over the 128 threads (block-stride), summed in fp32 registers, reduced by warp
+// shuffles and combined across the four warps in a fixed order: plain stores, deterministic.  The first version gave a
+// whole block to ONE warp (grid = all n_free^2 blocks, most of them empty): ~2500 busy warps with ~1000 tuples each
+// were bound by the latency of the dependent gathers (ncu: sm throughput 11 %, L2 22 %; 418 of the 540 us of a
+// linearisation at configs[3], profiles/r01b_k2_ncu_summary.txt).
+constexpr int kPairBlockThreads = 128;
+__global__ void __launch_bounds__(kPairBlockThreads)
 pair_block_kernel(Problem P, double* __restrict__ sys) {
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t n6 = static_cast<size_t>(P.n_free) * 6;
-    const long long nblk = static_cast<long long>(P.n_free) * P.n_free;
-    for (long long b = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); b < nblk;
-         b += static_cast<long long>(gridDim.x) * wpb) {
+    __shared__ float part[kPairBlockThreads / 32][36];
+    for (int bi = blockIdx.x; bi < P.n_blk_list; bi += gridDim.x) {
+        const int b = __ldg(P.blk_list + bi);
         const int beg = __ldg(P.blk_start + b), end = __ldg(P.blk_start + b + 1);
-        if (beg == end) continue;
         float acc[36];
 #pragma unroll
         for (int k = 0; k < 36; ++k) acc[k] = 0.f;
-        for (int idx = beg + lane; idx < end; idx += 32) {
+        for (int idx = beg + threadIdx.x; idx < end; idx += kPairBlockThreads) {
             const int2 t = __ldg(P.blk_tuples + idx);
             const int p = __ldg(P.obs_pt + t.x);
             float Jca[12], Jpa[6], Jcb[12], Jpb[6], vi[6], W[18], Y[18];
@@ -374,16 +378,32 @@ pair_block_kernel(Problem P, double* __restrict__ sys) {
                 for (int i = 0; i < 6; ++i) acc[6 * i + j] -= Y[3 * i] * w0 + Y[3 * i + 1] * w1 + Y[3 * i + 2] * w2;
             }
         }
-        const int fa = static_cast<int>(b / P.n_free), fb = static_cast<int>(b % P.n_free);
-        double* Sb = sys + (static_cast<size_t>(fa) * 6) * n6 + static_cast<size_t>(fb) * 6;
 #pragma unroll
         for (int k = 0; k < 36; ++k) {
             float v = acc[k];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) Sb[(k / 6) * n6 + (k % 6)] = static_cast<double>(v);
+            if (lane == 0) part[warp][k] = v;
         }
+        __syncthreads();
+        if (threadIdx.x < 36) {
+            const int k = threadIdx.x;
+            float v = part[0][k];
+#pragma unroll
+            for (int w = 1; w < kPairBlockThreads / 32; ++w) v += part[w][k];
+            const int fa = b / P.n_free, fb = b - fa * P.n_free;
+            sys[(static_cast<size_t>(fa) * 6 + k / 6) * n6 + static_cast<size_t>(fb) * 6 + (k % 6)] = static_cast<double>(v);
+        }
+        __syncthreads();
     }
+}
+
+// list of the camera-pair blocks that have tuples (order irrelevant: one CTA owns one block)
+__global__ void compact_blocks_kernel(const int32_t* __restrict__ blk_start, long long nblk, int32_t* __restrict__ list,
+                                      int32_t* __restrict__ counter) {
+    for (long long b = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; b < nblk;
+         b += static_cast<long long>(gridDim.x) * blockDim.x)
+        if (blk_start[b + 1] > blk_start[b]) list[atomicAdd(counter, 1)] = static_cast<int32_t>(b);
 }
 
 // ---- structure building (once per problem)
@@ -561,10 +581,10 @@ cudaError_t ba_launch_linearize(const Problem& P, double inv_radius, double* sys
     point_pass_kernel<<<grid, 256, 0, st>>>(P, inv_radius, sys);
     if (P.n_free > 0) {
         camera_diag_kernel<<<P.n_free, 256, 0, st>>>(P, sys);
-        const long long nblk = static_cast<long long>(P.n_free) * P.n_free;
-        long long g2 = (nblk + 7) / 8;
-        if (g2 > num_sms * 16) g2 = num_sms * 16;
-        pair_block_kernel<<<static_cast<int>(g2), 256, 0, st>>>(P, sys);
+        if (P.n_blk_list > 0) {
+            const int g2 = P.n_blk_list < num_sms * 64 ? P.n_blk_list : num_sms * 64;
+            pair_block_kernel<<<g2, kPairBlockThreads, 0, st>>>(P, sys);
+        }
     }
     return cudaGetLastError();
 }
@@ -581,6 +601,12 @@ cudaError_t ba_launch_scan_tuples(const int32_t* counts, long long n, int32_t* s
 cudaError_t ba_launch_fill_tuples(const Problem& P, int32_t* cursor, int2* tuples, int num_sms, cudaStream_t st) {
     if (P.n_pts <= 0 || P.n_free <= 0) return cudaSuccess;
     pair_tuples_kernel<<<num_sms * 4, 256, 0, st>>>(P, 1, cursor, tuples);
+    return cudaGetLastError();
+}
+cudaError_t ba_launch_compact_blocks(const int32_t* blk_start, long long nblk, int32_t* list, int32_t* counter, int num_sms,
+                                     cudaStream_t st) {
+    if (nblk <= 0) return cudaSuccess;
+    compact_blocks_kernel<<<num_sms * 4, 256, 0, st>>>(blk_start, nblk, list, counter);
     return cudaGetLastError();
 }
 cudaError_t ba_launch_damp(double* sys, int n6, double inv_radius, cudaStream_t st) {

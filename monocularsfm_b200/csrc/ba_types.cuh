@@ -32,6 +32,8 @@ struct Problem {
     const int32_t* cam_obs_list;    // [#observations of free cameras]
     const int32_t* blk_start;       // [n_free*n_free+1] CSR over camera-pair blocks (fa < fb): co-observing tuples
     const int2* blk_tuples;         // (obs_a, obs_b) with cam_free[obs_cam[obs_a]] = fa < fb = cam_free[obs_cam[obs_b]]
+    const int32_t* blk_list;        // [n_blk_list] indices fa*n_free+fb of the blocks with at least one tuple
+    int32_t n_blk_list;
     // ---- per-linearisation intermediates
     float* obs_J;                   // [n_obs][18]  Jc (2x6) | Jp (2x3), fp32
     double* obs_r;                  // [n_obs][2]

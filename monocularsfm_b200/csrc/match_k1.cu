@@ -18,25 +18,26 @@
 // 9.4 KB/clk chip-wide against the ~6.3-6.9 KB/clk the L2 delivers (profiles/r01_k1_bench_launch_ncu_raw.csv:
 // 12.9 TB/s at 73 % tensor-pipe utilisation).  Sharing every train tile between two SMs halves both.
 //
-// Warp roles per CTA (384 threads):
-//   warp 0      bulk-copy producer (cp.async.bulk = TMA engine, one elected lane): this CTA's query rows, its half of
-//               every train tile and of every extension super-tile (one per 4 train tiles)
-//   warps 1-2   leader CTA (rank 0): TWO MMA issuers (one elected lane each); issuer w owns the tiles with
-//               (tile counter & 1) == w, i.e. accumulator stage w (one issuer's loop of mbarrier waits + MMAs + commits
-//               has ~1000-1250 cycles of latency, profiles/r01_microbench_mma_patterns.log; two interleave).
-//               peer CTA (rank 1): warp 1 relays "my half has landed" from its own full-barriers to the leader's
+// Warp roles per CTA (384 threads).  The producer, relay and issuer warps run their loops with all 32 lanes and
+// warp-uniform operands; one elected lane issues the asynchronous instruction (see match_pair_kernel).
+//   warp 0      bulk-copy producer (cp.async.bulk = TMA engine): this CTA's query rows, its half of every train
+//               tile (8-stage ring) and of every extension super-tile (one per 4 train tiles, 2-stage ring)
+//   warp 1      leader CTA (rank 0): THE MMA issuer, tiles in order, accumulator stage = tile counter & 1.
+//               peer CTA (rank 1): relays "my half has landed" from its own full-barriers to the leader's
 //               (a 1-D bulk copy can only signal an mbarrier of the CTA it writes to).
-//   warp 2      also the TMEM allocator (both CTAs, cta_group::2 form)
-//   warps 4-11  epilogue: two warpgroups, each owns 128 of a tile's 256 columns; thread = query row
-//               (tcgen05.ld 32x32b: lane <-> row), so the row-wise reduction is thread-local.
+//   warp 2      TMEM allocator (both CTAs, cta_group::2 form)
+//   warps 4-11  epilogue: two warpgroups, warpgroup w serves accumulator stage w (the even / the odd tiles), so that
+//               one warpgroup reduces while the other one reads; thread = query row (tcgen05.ld 32x32b: lane <-> row),
+//               the row-wise reduction is thread-local.  A tile is read in two passes of 128 columns (128 registers);
+//               the stage goes back to the tensor cores after the second read.
 //
 // Barriers (every CTA has the full set at the same shared-memory offsets; tcgen05.commit multicasts to both):
 //   a_full/b_full/e_full   leader: 2 arrivals (own producer + peer relay); peer: 1 (own producer)
-//   done[tile % 12]        ONE commit per tile by the issuer that owns it, multicast to both CTAs: it publishes the
-//                          accumulator stage to the epilogues and tells the producers that the tile's smem stage (and,
-//                          after a super-tile's last tile, the extension stage) may be refilled
-//   a_empty                commits of both issuers after a unit pair's last tile, multicast
-//   t_empty                leader only: 16 arrivals (8 epilogue warps of each CTA)
+//   done[tile % 16]        ONE commit per tile, multicast to both CTAs: it publishes the accumulator stage to the
+//                          epilogues and tells the producers that the tile's smem stage (and, after a super-tile's last
+//                          tile, the extension stage) may be refilled
+//   a_empty                commit after a unit pair's last tile, multicast
+//   t_empty[stage]         leader only: 8 arrivals (the 4 warps of the stage's warpgroup in each CTA)
 //
 // Output per row (sorted space of the query image): g1 = group holding the best column, d1 = exact squared distance of
 // the best column, u = exact squared distance of the best column of any OTHER group.  match_post.cu finds the best

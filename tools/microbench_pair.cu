@@ -56,7 +56,7 @@ k_pair(int iters, long long* cyc, long long* stamps, int* sink) {
         uint32_t st = 0, ph = 1, s6 = 0, dn = 0;
         for (int it = 0; it < iters; ++it) {
             if (ISSUERS == 1 || (it & 1) == static_cast<int>(me)) {
-                if (EPI >= 2) {
+                if (EPI >= 2 && EPI <= 5) {
                     ptx::mbar_wait(&t_empty[st], ph);
                     ptx::tc_fence_after();
                 }
@@ -116,6 +116,20 @@ k_pair(int iters, long long* cyc, long long* stamps, int* sink) {
             ptx::mbar_wait(&fin, 0);
             if (me == 0) cyc[blockIdx.x >> 1] = clock64() - t0;
         }
+    } else if (warp >= 4 && EPI == 6) {
+        // pure integer load on the epilogue warps (register-only VIMNMX3 chains), no TMEM reads, no barriers: does ALU
+        // activity by itself slow the free-running tensor pipe?
+        int a[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = threadIdx.x * 7 + k;
+        int x = threadIdx.x, y = lane;
+        for (int i = 0; i < iters * 4; ++i) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = __vimax3_s32(a[k], x + k, y - k);
+            x ^= i; y += a[3] & 1;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc_sink ^= a[k];
     } else if (warp >= 4 && EPI >= 2) {
         const int quarter = warp & 3, wg = (warp - 4) >> 2;
         long long ph_ld = 0, ph_work = 0, ph_all = 0, ph_t = clock64();
@@ -146,9 +160,12 @@ k_pair(int iters, long long* cyc, long long* stamps, int* sink) {
                     long long* d = stamps + (it - 512) * 12;
                     d[10] = e0; d[11] = clock64();
                 }
-                if (EPI == 5) {          // the arithmetic of the real K1 epilogue (N = 256 only)
-                    int z;
-                    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(z) : "r"(zaddr) : "memory");
+                if (EPI == 5 || EPI == 7 || EPI == 8 || EPI == 9) {   // the arithmetic of the real K1 epilogue (N = 256 only)
+                    // 5: seed from a volatile shared load + key/insert | 7: constant seed | 8: shared seed, group maxima only
+                    // 9: seed from a clock read
+                    int z = static_cast<int>(0x80000000);
+                    if (EPI == 5 || EPI == 8) asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(z) : "r"(zaddr) : "memory");
+                    if (EPI == 9) { uint32_t clk; asm volatile("mov.u32 %0, %%clock;" : "=r"(clk) : : "memory"); z = static_cast<int>(0x80000000u | (clk & 1u)); }
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
                         int m0 = __vimax3_s32(z, static_cast<int>(v[c][0]), static_cast<int>(v[c][1]));
@@ -159,6 +176,7 @@ k_pair(int iters, long long* cyc, long long* stamps, int* sink) {
                             m1 = __vimax3_s32(m1, static_cast<int>(v[c][e + 2]), static_cast<int>(v[c][e + 3]));
                         }
                         const int m = max(m0, m1);
+                        if (EPI == 8) { k1 = min(k1, m); continue; }
                         const int key = (it * 977 + c * 31) - 2 * m;
                         k2 = min(k2, max(k1, key));
                         if (key < k1) g1 = it * 8 + wg * 4 + c;
@@ -260,6 +278,10 @@ int main() {
     run<256, 1, 4, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, epilogue reads + max, per-tile desc", false);
     run<256, 2, 4, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 2 issuers, epilogue reads + max, per-tile desc", false);
     run<256, 1, 5, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, REAL epilogue arithmetic", true);
+    run<256, 1, 8, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, shared-load seed, group maxima only", true);
+    run<256, 1, 9, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, REAL arithmetic, clock seed", true);
+    run<256, 1, 1, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, free-running, idle epilogue warps", false);
+    run<256, 1, 6, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, free-running, ALU-busy epilogue warps", false);
     run<128, 1, 3, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=128 1 issuer, 4 stages, epilogue reads TMEM", false);
     run<128, 1, 4, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=128 1 issuer, 4 stages, epilogue reads + max", false);
     run<128, 2, 4, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=128 2 issuers, 4 stages, epilogue reads + max", false);

@@ -278,8 +278,6 @@ int main() {
     run<256, 1, 4, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, epilogue reads + max, per-tile desc", false);
     run<256, 2, 4, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 2 issuers, epilogue reads + max, per-tile desc", false);
     run<256, 1, 5, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, REAL epilogue arithmetic", true);
-    run<256, 1, 8, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, shared-load seed, group maxima only", true);
-    run<256, 1, 9, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, REAL arithmetic, clock seed", true);
     run<256, 1, 1, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, free-running, idle epilogue warps", false);
     run<256, 1, 6, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=256 1 issuer, free-running, ALU-busy epilogue warps", false);
     run<128, 1, 3, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=128 1 issuer, 4 stages, epilogue reads TMEM", false);

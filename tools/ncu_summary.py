@@ -40,16 +40,13 @@ def main():
         for col, u in zip(hdr, units):
             if any(k in col for k, _ in KEYS if _):
                 print(f"   {col:110s} {d[col]:>18s} {u}")
-        for col in hdr:
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for col, u in zip(hdr, units):
             if col.endswith("dram__bytes_read.sum"):
-                out["dram_bytes_read"] = float(d[col].replace(",", ""))
+                out["dram_bytes_read"] = float(d[col].replace(",", "")) * scale.get(u, 1.0)
             if col.endswith("dram__bytes_write.sum"):
-                out["dram_bytes_write"] = float(d[col].replace(",", ""))
+                out["dram_bytes_write"] = float(d[col].replace(",", "")) * scale.get(u, 1.0)
         if "--traffic-json" in sys.argv and "dram_bytes_read" in out:
-            u_r = units[hdr.index(next(c for c in hdr if c.endswith("dram__bytes_read.sum")))]
-            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u_r, 1.0)
-            out["dram_bytes_read"] *= scale
-            out["dram_bytes_write"] *= scale
             out["dram_bytes_per_launch"] = out["dram_bytes_read"] + out["dram_bytes_write"]
             if "--kernel-note" in sys.argv:
                 out["kernel"] = sys.argv[sys.argv.index("--kernel-note") + 1]

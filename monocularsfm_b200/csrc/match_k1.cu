@@ -446,35 +446,38 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
                 // group maxima of the four 32-column groups in v, inserted into the running (best, best-of-other-groups);
                 // all-dead groups (also the ones behind the occupied columns of the last tile) carry C_g = kDeadCg and
                 // can never win.  Every max chain starts from `seed` (a neutral element).
-                auto reduce4 = [&](const int4 cgv, const int gbase, const int32_t seed) {
+                auto reduce1 = [&](uint32_t(&cur)[32], const int32_t cgc, const int gid, const int32_t seed) -> int32_t {
+                    // max over the 32 columns of the group: two independent chains, two elements per VIMNMX3
+                    int32_t m0 = __vimax3_s32(seed, static_cast<int32_t>(cur[0]), static_cast<int32_t>(cur[1]));
+                    int32_t m1 = __vimax3_s32(seed, static_cast<int32_t>(cur[2]), static_cast<int32_t>(cur[3]));
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t(&cur)[32] = v[c];
-                        // max over the 32 columns of the group: two independent chains, two elements per VIMNMX3
-                        int32_t m0 = __vimax3_s32(seed, static_cast<int32_t>(cur[0]), static_cast<int32_t>(cur[1]));
-                        int32_t m1 = __vimax3_s32(seed, static_cast<int32_t>(cur[2]), static_cast<int32_t>(cur[3]));
-#pragma unroll
-                        for (int e = 4; e < 32; e += 4) {
-                            m0 = __vimax3_s32(m0, static_cast<int32_t>(cur[e + 0]), static_cast<int32_t>(cur[e + 1]));
-                            m1 = __vimax3_s32(m1, static_cast<int32_t>(cur[e + 2]), static_cast<int32_t>(cur[e + 3]));
-                        }
-                        const int32_t m = max(m0, m1);
-                        if (kDbg && dbg_mode == 3) { k1 = min(k1, m); continue; }       // diagnostic: group maxima only
-                        const int32_t cgc = (c == 0) ? cgv.x : (c == 1) ? cgv.y : (c == 2) ? cgv.z : cgv.w;
-                        const int32_t key = cgc - 2 * m;      // = min over the group of (||d_j||^2 - 2 q.d_j)
-                        k2 = min(k2, max(k1, key));
-                        if (key < k1) g1 = gbase + c;
-                        k1 = min(k1, key);
+                    for (int e = 4; e < 32; e += 4) {
+                        m0 = __vimax3_s32(m0, static_cast<int32_t>(cur[e + 0]), static_cast<int32_t>(cur[e + 1]));
+                        m1 = __vimax3_s32(m1, static_cast<int32_t>(cur[e + 2]), static_cast<int32_t>(cur[e + 3]));
                     }
+                    const int32_t m = max(m0, m1);
+                    if (kDbg && dbg_mode == 3) { k1 = min(k1, m); return m; }       // diagnostic: group maxima only
+                    const int32_t key = cgc - 2 * m;      // = min over the group of (||d_j||^2 - 2 q.d_j)
+                    k2 = min(k2, max(k1, key));
+                    if (key < k1) g1 = gid;
+                    k1 = min(k1, key);
+                    return m;
                 };
-                // ---- columns 0..127 of the tile: read, reduce
+                auto cg_of = [](const int4 cgv, const int c) { return (c == 0) ? cgv.x : (c == 1) ? cgv.y : (c == 2) ? cgv.z : cgv.w; };
+                // ---- columns 0..127 of the tile: read; reduce group by group and refill every group's registers with
+                //      the group 128 columns further right as soon as it has been reduced, so that the second read is in
+                //      flight under the first reduction and the stage can be handed back right after it
 #pragma unroll
                 for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32(taddr0 + c * 32, v[c]);
                 ptx::tmem_ld_wait();
-                if (!(kDbg && dbg_mode == 2)) reduce4(cgv0, tile * 8, static_cast<int32_t>(0x80000000));
-                // ---- columns 128..255: read, hand the accumulator stage back, reduce
+                // (the seed of a group is the previous group's maximum with the sign bit set — still below every accumulator
+                // value, which are non-negative — so that ptxas cannot interleave the four groups and finish them together)
+                int32_t seed = static_cast<int32_t>(0x80000000);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32(taddr0 + 128 + c * 32, v[c]);
+                for (int c = 0; c < 4; ++c) {
+                    if (!(kDbg && dbg_mode == 2)) seed = reduce1(v[c], cg_of(cgv0, c), tile * 8 + c, seed) | static_cast<int32_t>(0x80000000);
+                    ptx::tmem_ld_32x32(taddr0 + 128 + c * 32, v[c]);
+                }
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -496,7 +499,8 @@ match_pair_kernel(const Item* __restrict__ items, int num_items, int32_t* __rest
                     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(z) : "memory");
                     ph_z += t - ph_t;
                 }
-                reduce4(cgv1, tile * 8 + 4, z);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) reduce1(v[c], cg_of(cgv1, c), tile * 8 + 4 + c, z);
                 if (kDbg) {      // k1, k2 are inputs so that the stamp cannot be hoisted above the integer work
                     long long t;
                     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(k1), "r"(k2) : "memory");

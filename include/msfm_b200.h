@@ -94,6 +94,16 @@ int msfm_prof_read(msfm_ctx* ctx, double ms[MSFM_PROF_NCAT], int64_t launches[MS
  * n may be 0.  image_id >= 0 (image_t, Common/Types.h:9).  The copy is queued on the ctx stream: a PINNED host buffer
  * must stay valid until the next msfm_sync / matching call returns (pageable memory is staged immediately). */
 int msfm_desc_upload_u8(msfm_ctx* ctx, int32_t image_id, const uint8_t* desc_host, int32_t n);
+/* Same for the float32 descriptors the reference's database holds (Database::ReadDescriptors, src/Database/Database.cpp:
+ * 510-523; blob = rows x 128 little-endian float32, :174-199): the set is copied as float and converted to uint8 on the
+ * device.  mode 0: a set whose values are all integers in [0,255] (un-normalised SIFT) converts exactly, any other set
+ * is quantised as clamp(rint(512 v), 0, 255), round-half-to-even — the bridge INTEGRATION.md documents for the
+ * L1-root / L2 normalised descriptors of FeatureExtraction.cpp:260-281; mode 1: always quantise. */
+int msfm_desc_upload_f32(msfm_ctx* ctx, int32_t image_id, const float* desc_host, int32_t n, int32_t mode);
+/* 1 if the resident set of image_id came from a float32 upload that had to be quantised (distances are then on the
+ * x512 scale: FeatureUtils::FilterMatchesByDistance thresholds must be scaled), 0 otherwise
+ * (uint8 upload or exactly converted floats); negative error code.  Synchronises the stream. */
+int msfm_desc_quantised(msfm_ctx* ctx, int32_t image_id);
 /* Same, source already in device memory (synthetic-data benchmarks; inputs resident in HBM). */
 int msfm_desc_upload_u8_dev(msfm_ctx* ctx, int32_t image_id, const uint8_t* desc_dev, int32_t n);
 /* Number of descriptors of a resident image, or MSFM_E_NOT_FOUND. */

@@ -92,6 +92,8 @@ def load_library():
         "msfm_prof_read": (C.c_int, [vp, P(C.c_double), P(i64)]),
         "msfm_desc_upload_u8": (C.c_int, [vp, i32, vp, i32]),
         "msfm_desc_upload_u8_dev": (C.c_int, [vp, i32, vp, i32]),
+        "msfm_desc_upload_f32": (C.c_int, [vp, i32, vp, i32, i32]),
+        "msfm_desc_quantised": (C.c_int, [vp, i32]),
         "msfm_desc_count": (C.c_int, [vp, i32]),
         "msfm_desc_release": (C.c_int, [vp, i32]),
         "msfm_desc_release_all": (C.c_int, [vp]),
@@ -187,6 +189,15 @@ class Context:
         desc = np.ascontiguousarray(desc, dtype=np.uint8)
         assert desc.ndim == 2 and desc.shape[1] == 128, desc.shape
         self._check(self.lib.msfm_desc_upload_u8(self.h, image_id, _ptr(desc), desc.shape[0]))
+
+    def upload_f32(self, image_id: int, desc: np.ndarray, always_quantise: bool = False):
+        """float32 descriptors as the reference's database stores them; converted to uint8 on the device."""
+        desc = np.ascontiguousarray(desc, dtype=np.float32)
+        assert desc.ndim == 2 and desc.shape[1] == 128, desc.shape
+        self._check(self.lib.msfm_desc_upload_f32(self.h, image_id, _ptr(desc), desc.shape[0], 1 if always_quantise else 0))
+
+    def quantised(self, image_id: int) -> bool:
+        return bool(self._check(self.lib.msfm_desc_quantised(self.h, image_id), allow=(0, 1)))
 
     def upload_dev(self, image_id: int, dev_ptr: int, n: int):
         self._check(self.lib.msfm_desc_upload_u8_dev(self.h, image_id, C.c_void_p(dev_ptr), n))

@@ -578,6 +578,47 @@ cudaError_t launch_gather_candidates(const ImgDev* imgs, const SegDev* segs, int
     gather_candidates_kernel<<<npairs, 256, 0, st>>>(imgs, segs, npairs, m_j, T);
     return cudaGetLastError();
 }
+// ---- float32 descriptors (what the reference's Database stores, src/Database/Database.cpp:174-199) -> uint8.
+// The bridge documented in INTEGRATION.md: a set whose values are all integers in [0,255] (un-normalised SIFT) converts
+// exactly; any other set (L1-root / L2 normalised, FeatureExtraction.cpp:260-281) is quantised as
+// clamp(rint(512 v), 0, 255) with round-half-to-even.  flag[0] must be 1 on entry; mode 0 = decide per set, 1 = always quantise.
+__global__ void desc_f32_check_kernel(const float* __restrict__ src, size_t count, int32_t* __restrict__ flag) {
+    bool ok = true;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < count; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float v = __ldg(src + i);
+        ok = ok && (v >= 0.f && v <= 255.f && v == floorf(v));
+    }
+    if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(flag, 0);
+}
+__global__ void desc_f32_quantize_kernel(const float* __restrict__ src, size_t count4, int mode, const int32_t* __restrict__ flag,
+                                         uint32_t* __restrict__ dst) {
+    const bool integral = mode == 0 && flag[0] != 0;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < count4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+        const float in[4] = {v.x, v.y, v.z, v.w};
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float q = integral ? in[k] : rintf(__fmul_rn(in[k], 512.0f));
+            const float c = fminf(255.f, fmaxf(0.f, q));          // NaN -> 0, like std::max(0.f, NaN)
+            packed |= static_cast<uint32_t>(static_cast<int>(c)) << (8 * k);
+        }
+        dst[i] = packed;
+    }
+}
+cudaError_t launch_desc_quantize(const float* src, int n, int mode, int32_t* flag, uint8_t* dst, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const size_t count = static_cast<size_t>(n) * 128;
+    cudaError_t e;
+    const int32_t one = 1;
+    if ((e = cudaMemcpyAsync(flag, &one, sizeof(one), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    int grid = static_cast<int>((count / 4 + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (mode == 0) desc_f32_check_kernel<<<grid, 256, 0, st>>>(src, count, flag);
+    desc_f32_quantize_kernel<<<grid, 256, 0, st>>>(src, count / 4, mode, flag, reinterpret_cast<uint32_t*>(dst));
+    return cudaGetLastError();
+}
+
 // raw [n][128] (device) -> resident layout.  block = one allocation laid out by img_layout() (msfm_api.cu);
 // scratch: keys [n] u64 | nrm_orig [n] | pos_of [n] | bucket_cnt [8]
 cudaError_t launch_desc_format(const uint8_t* raw, int n, int n_pad, uint8_t* sw, uint8_t* ext, int32_t* cg,

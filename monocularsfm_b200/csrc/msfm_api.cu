@@ -17,6 +17,7 @@ cudaError_t launch_match_tile_kernel(const ImgDev*, const UnitDev*, int, int, in
 size_t match_tile_item_bytes(int num_units);
 cudaError_t launch_desc_format(const uint8_t*, int, int, uint8_t*, uint8_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, unsigned long long*,
                                int32_t*, int32_t*, int32_t*, cudaStream_t);
+cudaError_t launch_desc_quantize(const float*, int, int, int32_t*, uint8_t*, cudaStream_t);
 cudaError_t launch_build_units(const SegDev*, int, int, UnitDev*, cudaStream_t);
 cudaError_t launch_resolve_rows(const ImgDev*, const UnitDev*, int, int, const int32_t*, const int32_t*, const int32_t*,
                                 MatchOpts, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, unsigned int*, cudaStream_t);
@@ -148,8 +149,11 @@ static ImgLayout img_layout(int32_t n_pad) {
 }
 static int32_t padded_count(int32_t n) { return n > 0 ? (n + kMaxPadPerImage + 255) / 256 * 256 : 0; }
 
-static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int32_t n, bool src_on_device) {
-    if (!c || n < 0 || (n > 0 && !src)) return c ? c->fail(MSFM_E_INVALID, "msfm_desc_upload: bad arguments") : MSFM_E_INVALID;
+// src_f32 != nullptr: float32 host descriptors, converted on the device (f32_mode: 0 decide per set, 1 always quantise)
+static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int32_t n, bool src_on_device,
+                         const float* src_f32 = nullptr, int f32_mode = 0) {
+    if (!c || n < 0 || (n > 0 && !src && !src_f32))
+        return c ? c->fail(MSFM_E_INVALID, "msfm_desc_upload: bad arguments") : MSFM_E_INVALID;
     MSFM_CUDA(c, cudaSetDevice(c->device));
     const int32_t n_pad = padded_count(n);
     int slot;
@@ -180,7 +184,19 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
     c->imgs_dirty = true;
     if (n_pad == 0) return MSFM_OK;
     const uint8_t* raw = src;
-    if (!src_on_device) {
+    if (src_f32) {
+        // staging: [n][128] u8 | 256-B aligned [n][128] f32 | flag
+        const size_t u8_bytes = (static_cast<size_t>(n) * 128 + 255) / 256 * 256, f32_bytes = static_cast<size_t>(n) * 128 * 4;
+        MSFM_CUDA(c, c->d_raw.reserve(u8_bytes + f32_bytes + 256));
+        float* stage = reinterpret_cast<float*>(c->d_raw.as<uint8_t>() + u8_bytes);
+        MSFM_CUDA(c, cudaMemcpyAsync(stage, src_f32, f32_bytes, cudaMemcpyHostToDevice, c->stream));
+        c->prof_begin(MSFM_PROF_DESC_FORMAT);
+        MSFM_CUDA(c, launch_desc_quantize(stage, n, f32_mode, reinterpret_cast<int32_t*>(c->d_raw.as<uint8_t>() + u8_bytes + f32_bytes),
+                                          c->d_raw.as<uint8_t>(), c->stream));
+        c->prof_end();
+        c->launches += f32_mode == 0 ? 2 : 1;
+        raw = c->d_raw.as<uint8_t>();
+    } else if (!src_on_device) {
         MSFM_CUDA(c, c->d_raw.reserve(static_cast<size_t>(n) * 128));
         MSFM_CUDA(c, cudaMemcpyAsync(c->d_raw.p, src, static_cast<size_t>(n) * 128, cudaMemcpyHostToDevice, c->stream));
         raw = c->d_raw.as<uint8_t>();
@@ -198,6 +214,15 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
                                     reinterpret_cast<int32_t*>(sw + L.off_inv), reinterpret_cast<int32_t*>(sw + L.off_used), keys, nrm_orig, pos_of, bucket_cnt, c->stream));
     c->prof_end();
     c->launches += 4;
+    // word after `used`: 1 = the float32 set converted exactly (or uint8 upload), 0 = it was quantised
+    int32_t* exact_flag = reinterpret_cast<int32_t*>(sw + L.off_used) + 1;
+    if (src_f32 && f32_mode == 0) {
+        const size_t u8_bytes = (static_cast<size_t>(n) * 128 + 255) / 256 * 256, f32_bytes = static_cast<size_t>(n) * 128 * 4;
+        MSFM_CUDA(c, cudaMemcpyAsync(exact_flag, c->d_raw.as<uint8_t>() + u8_bytes + f32_bytes, sizeof(int32_t),
+                                     cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        MSFM_CUDA(c, cudaMemsetAsync(exact_flag, src_f32 ? 0x00 : 0x01, sizeof(int32_t), c->stream));   // any non-zero word = exact
+    }
     return MSFM_OK;
 }
 
@@ -208,6 +233,25 @@ int msfm_desc_upload_u8(msfm_ctx* c, int32_t image_id, const uint8_t* desc_host,
 int msfm_desc_upload_u8_dev(msfm_ctx* c, int32_t image_id, const uint8_t* desc_dev, int32_t n) {
     if (c && image_id < 0) return c->fail(MSFM_E_INVALID, "image_id must be >= 0");
     return upload_common(c, image_id, desc_dev, n, true);
+}
+int msfm_desc_upload_f32(msfm_ctx* c, int32_t image_id, const float* desc_host, int32_t n, int32_t mode) {
+    if (c && image_id < 0) return c->fail(MSFM_E_INVALID, "image_id must be >= 0");
+    if (c && mode != 0 && mode != 1) return c->fail(MSFM_E_INVALID, "msfm_desc_upload_f32: mode must be 0 or 1");
+    if (c && n > 0 && !desc_host) return c->fail(MSFM_E_INVALID, "msfm_desc_upload_f32: null descriptors");
+    return upload_common(c, image_id, nullptr, n, false, desc_host, mode);
+}
+int msfm_desc_quantised(msfm_ctx* c, int32_t image_id) {
+    if (!c) return MSFM_E_INVALID;
+    auto it = c->slot_of.find(image_id);
+    if (it == c->slot_of.end()) return c->fail(MSFM_E_NOT_FOUND, "image %d not resident", image_id);
+    const ImgHost& im = c->imgs[it->second];
+    if (!im.block) return 0;
+    MSFM_CUDA(c, cudaSetDevice(c->device));
+    int32_t exact = 1;
+    const ImgLayout L = img_layout(im.n_pad);
+    MSFM_CUDA(c, cudaMemcpyAsync(&exact, static_cast<uint8_t*>(im.block) + L.off_used + 4, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    MSFM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return exact ? 0 : 1;
 }
 int msfm_desc_count(msfm_ctx* c, int32_t image_id) {
     if (!c) return MSFM_E_INVALID;

@@ -32,6 +32,8 @@ public:
     // CV_32F otherwise (the reference's L1-root / L2 normalised rows): v -> clamp(round(512 v), 0, 255); this is the
     // COLMAP-style quantisation and is LOSSY w.r.t. the reference's float path (documented deviation).
     static cv::Mat ToUint8Descriptors(const cv::Mat& desc);
+    // upload a CV_8U or CV_32F descriptor set under image_id; the float -> uint8 bridge runs on the device
+    static void UploadDescriptors(int image_id, const cv::Mat& desc);
     // Distance scale of the quantised descriptors: a max_distance given for unit-norm floats is multiplied by this.
     static double QuantisationScale() { return 512.0; }
 };

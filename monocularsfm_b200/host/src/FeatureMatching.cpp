@@ -17,18 +17,13 @@ const int32_t kTopScaleIdBase = 1000000000;   // device ids of the preemptive-ma
 void FeatureMatcher::EnsureResident(image_t image_id) {
     if (resident_.count(image_id)) return;
     const cv::Mat desc = database_->ReadDescriptors(image_id);              // FeatureMatching.cpp:32-33
-    const cv::Mat u8 = FeatureUtils::ToUint8Descriptors(desc);
-    bool quantised = false;
-    if (desc.type() == CV_32F && desc.rows > 0) {
-        // integral rows are cast losslessly; anything else went through the x512 quantisation
-        const float v = desc.at<float>(0, 0);
-        quantised = !(u8.at<unsigned char>(0, 0) == v);
-        for (int j = 1; j < desc.cols && !quantised; ++j) quantised = !(u8.at<unsigned char>(0, j) == desc.at<float>(0, j));
-    }
-    quantised_[image_id] = quantised;
     msfm_ctx* ctx = device::Context();
-    device::Check(msfm_desc_upload_u8(ctx, image_id, u8.data, u8.rows), "msfm_desc_upload_u8");
-    device::Check(msfm_sync(ctx), "msfm_sync");                             // u8 goes out of scope
+    FeatureUtils::UploadDescriptors(image_id, desc);                        // CV_32F is bridged to uint8 on the device
+    // integral float rows convert losslessly; anything else went through the x512 quantisation (synchronises: `desc`
+    // may go out of scope)
+    const int q = msfm_desc_quantised(ctx, image_id);
+    if (q < 0) device::Check(q, "msfm_desc_quantised");
+    quantised_[image_id] = q == 1;
     resident_.insert(image_id);
 }
 
@@ -147,9 +142,8 @@ void BruteFeatureMatcher::EnsureTopScaleResident(image_t image_id) {
     const cv::Mat desc = database_->ReadDescriptors(image_id);
     cv::Mat top;
     FeatureUtils::ExtractTopScaleDescriptors(kpts, desc, preemtive_num_features_, top);   // :180-196
-    const cv::Mat u8 = FeatureUtils::ToUint8Descriptors(top);
     msfm_ctx* ctx = device::Context();
-    device::Check(msfm_desc_upload_u8(ctx, kTopScaleIdBase + image_id, u8.data, u8.rows), "msfm_desc_upload_u8");
+    FeatureUtils::UploadDescriptors(kTopScaleIdBase + image_id, top);
     device::Check(msfm_sync(ctx), "msfm_sync");
     top_scale_resident_.insert(image_id);
 }

@@ -14,11 +14,11 @@ const int32_t kScratchId1 = 2000000001, kScratchId2 = 2000000002;   // image ids
 
 void MatchTwoMats(const cv::Mat& desc1, const cv::Mat& desc2, std::vector<cv::DMatch>& matches, float distance_ratio,
                   bool cross_check) {
-    const cv::Mat a = FeatureUtils::ToUint8Descriptors(desc1), b = FeatureUtils::ToUint8Descriptors(desc2);
     msfm_ctx* ctx = device::Context();
-    device::Check(msfm_desc_upload_u8(ctx, kScratchId1, a.data, a.rows), "msfm_desc_upload_u8");
+    FeatureUtils::UploadDescriptors(kScratchId1, desc1);
     device::Check(msfm_sync(ctx), "msfm_sync");   // the upload staging buffer is reused by the next upload
-    device::Check(msfm_desc_upload_u8(ctx, kScratchId2, b.data, b.rows), "msfm_desc_upload_u8");
+    FeatureUtils::UploadDescriptors(kScratchId2, desc2);
+    const cv::Mat& a = desc1;
     msfm_match_options opt;
     opt.max_distance = -1.0;
     opt.distance_ratio = distance_ratio;
@@ -35,6 +35,16 @@ void MatchTwoMats(const cv::Mat& desc1, const cv::Mat& desc2, std::vector<cv::DM
         matches.push_back(cv::DMatch(out[2 * k], out[2 * k + 1], 0, dist[k]));   // imgIdx 0 like knnMatch on one train set
 }
 }  // namespace
+
+// CV_8U rows go to the device as they are; CV_32F rows (what Database::ReadDescriptors returns, Database.cpp:510-523) are
+// copied as float and bridged to uint8 ON THE DEVICE by the rule ToUint8Descriptors states on the host.
+void FeatureUtils::UploadDescriptors(int image_id, const cv::Mat& desc) {
+    assert(desc.cols == MSFM_DESC_DIM || desc.rows == 0);
+    assert(desc.type() == CV_8U || desc.type() == CV_32F);
+    msfm_ctx* ctx = device::Context();
+    if (desc.type() == CV_8U) device::Check(msfm_desc_upload_u8(ctx, image_id, desc.data, desc.rows), "msfm_desc_upload_u8");
+    else device::Check(msfm_desc_upload_f32(ctx, image_id, reinterpret_cast<const float*>(desc.data), desc.rows, 0), "msfm_desc_upload_f32");
+}
 
 cv::Mat FeatureUtils::ToUint8Descriptors(const cv::Mat& desc) {
     if (desc.type() == CV_8U) {

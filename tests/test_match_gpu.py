@@ -220,3 +220,49 @@ def test_uniform_random_descriptors_full_norm_range(ctx):
     np.testing.assert_array_equal(dist, od)
     ctx.release(60)
     ctx.release(61)
+
+
+def _quantise_like_the_bridge(x):
+    """Host statement of the float32 -> uint8 bridge (INTEGRATION.md; FeatureUtils::ToUint8Descriptors in the C++ shim):
+    sets of integers in [0,255] convert exactly, anything else is clamp(rint(512 v), 0, 255), round-half-to-even."""
+    x = np.asarray(x, np.float32)
+    integral = bool(np.all((x >= 0) & (x <= 255) & (x == np.floor(x))))
+    q = x if integral else np.rint(x * np.float32(512.0))
+    q = np.where(np.isnan(q), 0, q)                      # std::max(0.f, NaN) == 0.f in the C++ statement
+    return np.clip(q, 0, 255).astype(np.uint8), not integral
+
+
+@pytest.mark.gpu
+def test_float32_upload_bridge(ctx):
+    """msfm_desc_upload_f32: what Database::ReadDescriptors returns (CV_32F, Database.cpp:510-523) converted on the device
+    gives exactly the matches of the uint8 upload of the host-side statement of the bridge."""
+    rng = np.random.default_rng(77)
+    raw = rng.integers(0, 256, (700, 128)).astype(np.float32)                    # un-normalised SIFT: integers
+    raw2 = raw[rng.permutation(700)[:500]] + rng.integers(-3, 4, (500, 128))
+    raw2 = np.clip(raw2, 0, 255).astype(np.float32)
+    # L1-root normalised rows (FeatureExtraction.cpp:260-270), incl. exact .5 ties after scaling, a NaN and out-of-range values
+    l1 = np.sqrt(raw / np.maximum(raw.sum(1, keepdims=True), 1)).astype(np.float32)
+    l1b = np.sqrt(raw2 / np.maximum(raw2.sum(1, keepdims=True), 1)).astype(np.float32)
+    l1[0, :8] = np.array([0.5 / 512, 1.5 / 512, 2.5 / 512, 254.5 / 512, 255.5 / 512, -0.25, 3.0, np.nan], np.float32)
+    opt = m.MatchOptions(0.8, -1.0, True, True)
+    for a, b in ((raw, raw2), (l1, l1b)):
+        qa, quant_a = _quantise_like_the_bridge(a)
+        qb, quant_b = _quantise_like_the_bridge(b)
+        ctx.upload(10, qa)
+        ctx.upload(11, qb)
+        off_u8, mt_u8, d_u8 = ctx.match_pairs([[10, 11]], opt)
+        ctx.upload_f32(20, a)
+        ctx.sync()                                                   # the float staging buffer is reused by the next upload
+        ctx.upload_f32(21, b)
+        off_f, mt_f, d_f = ctx.match_pairs([[20, 21]], opt)
+        assert mt_f.tolist() == mt_u8.tolist() and (d_f == d_u8).all()
+        assert len(mt_f) > 50
+        assert ctx.quantised(20) == quant_a and ctx.quantised(21) == quant_b
+        assert ctx.quantised(10) is False
+        em, ed = mo.match_image_pair(qa, qb, 0.8, -1.0, True, True)   # and both equal the OpenCV-pinned oracle on the uint8 sets
+        assert mt_f.tolist() == em.tolist() and (d_f == ed).all()
+    # forced quantisation of an integral set: everything saturates at 255 except zeros
+    ctx.upload_f32(30, raw, always_quantise=True)
+    assert ctx.quantised(30) is True
+    for k in (10, 11, 20, 21, 30):
+        ctx.release(k)

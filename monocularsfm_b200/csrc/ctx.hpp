@@ -59,7 +59,14 @@ struct msfm_ctx {
     std::vector<int> free_slots;
     msfm::GrowBuf d_imgs;                          // ImgDev[slots]
     bool imgs_dirty = true;
-    msfm::GrowBuf d_raw;                           // upload staging (device)
+    msfm::GrowBuf d_raw;                           // upload staging (device): float32 uploads, knn2
+    // uint8 host uploads: two staging buffers filled on a copy stream, so that the H2D copy of image k+1 runs under the
+    // formatting kernels of image k
+    cudaStream_t copy_stream = nullptr;
+    msfm::GrowBuf d_rawq[2];
+    cudaEvent_t raw_ready[2] = {nullptr, nullptr}, raw_free[2] = {nullptr, nullptr};
+    bool raw_free_set[2] = {false, false};
+    uint32_t raw_turn = 0;
     msfm::GrowBuf d_fmt;                           // upload formatting scratch (sort keys, ranks)
     msfm::GrowBuf d_temp;                          // temporary query images of the reverse (cross-check) pass
     msfm::GrowBuf h_stage;                         // pinned host staging (segments, offsets readback)

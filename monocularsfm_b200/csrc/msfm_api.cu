@@ -70,10 +70,16 @@ int msfm_init(msfm_ctx** out, int device_id) {
     c->device = device_id;
     c->num_sms = prop.multiProcessorCount;
     c->h_stage.pinned_host = true;
-    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_init_error = cudaGetErrorString(e);
+        if (c->stream) cudaStreamDestroy(c->stream);
         delete c;
         return MSFM_E_CUDA;
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&c->raw_ready[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->raw_free[i], cudaEventDisableTiming);
     }
     *out = c;
     return MSFM_OK;
@@ -92,6 +98,12 @@ void msfm_destroy(msfm_ctx* c) {
     GrowBuf* bufs[] = {&c->d_imgs, &c->d_raw, &c->d_fmt, &c->d_temp, &c->h_stage, &c->d_segs, &c->d_units, &c->d_res, &c->d_m, &c->d_exact,
                        &c->d_counts, &c->d_misc, &c->d_out_offsets, &c->d_out_matches, &c->d_out_dist, &c->d_ba_r, &c->d_ba_J};
     for (GrowBuf* b : bufs) b->release();
+    for (int i = 0; i < 2; ++i) {
+        c->d_rawq[i].release();
+        if (c->raw_ready[i]) cudaEventDestroy(c->raw_ready[i]);
+        if (c->raw_free[i]) cudaEventDestroy(c->raw_free[i]);
+    }
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -184,6 +196,7 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
     c->imgs_dirty = true;
     if (n_pad == 0) return MSFM_OK;
     const uint8_t* raw = src;
+    int raw_q = -1;
     if (src_f32) {
         // staging: [n][128] u8 | 256-B aligned [n][128] f32 | flag
         const size_t u8_bytes = (static_cast<size_t>(n) * 128 + 255) / 256 * 256, f32_bytes = static_cast<size_t>(n) * 128 * 4;
@@ -197,9 +210,18 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
         c->launches += f32_mode == 0 ? 2 : 1;
         raw = c->d_raw.as<uint8_t>();
     } else if (!src_on_device) {
-        MSFM_CUDA(c, c->d_raw.reserve(static_cast<size_t>(n) * 128));
-        MSFM_CUDA(c, cudaMemcpyAsync(c->d_raw.p, src, static_cast<size_t>(n) * 128, cudaMemcpyHostToDevice, c->stream));
-        raw = c->d_raw.as<uint8_t>();
+        // double-buffered staging on the copy stream: this copy runs under the formatting kernels of the previous upload
+        raw_q = static_cast<int>(c->raw_turn++ & 1u);
+        GrowBuf& q = c->d_rawq[raw_q];
+        if (c->raw_free_set[raw_q]) MSFM_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->raw_free[raw_q], 0));
+        if (q.cap < static_cast<size_t>(n) * 128) {
+            MSFM_CUDA(c, cudaStreamSynchronize(c->stream));        // kernels of an earlier upload may still read the old buffer
+            MSFM_CUDA(c, q.reserve(static_cast<size_t>(n) * 128));
+        }
+        MSFM_CUDA(c, cudaMemcpyAsync(q.p, src, static_cast<size_t>(n) * 128, cudaMemcpyHostToDevice, c->copy_stream));
+        MSFM_CUDA(c, cudaEventRecord(c->raw_ready[raw_q], c->copy_stream));
+        MSFM_CUDA(c, cudaStreamWaitEvent(c->stream, c->raw_ready[raw_q], 0));
+        raw = q.as<uint8_t>();
     }
     uint8_t* sw = static_cast<uint8_t*>(im.block);
     // formatting scratch: keys [n] u64 | nrm_orig [n] | pos_of [n] | bucket counts [8]
@@ -214,6 +236,10 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
                                     reinterpret_cast<int32_t*>(sw + L.off_inv), reinterpret_cast<int32_t*>(sw + L.off_used), keys, nrm_orig, pos_of, bucket_cnt, c->stream));
     c->prof_end();
     c->launches += 4;
+    if (raw_q >= 0) {
+        MSFM_CUDA(c, cudaEventRecord(c->raw_free[raw_q], c->stream));
+        c->raw_free_set[raw_q] = true;
+    }
     // word after `used`: 1 = the float32 set converted exactly (or uint8 upload), 0 = it was quantised
     int32_t* exact_flag = reinterpret_cast<int32_t*>(sw + L.off_used) + 1;
     if (src_f32 && f32_mode == 0) {

@@ -215,6 +215,12 @@ int  msfm_ba_set_params(msfm_ba* ba, const double* cams, const double* pts);
  * autodiff cost function's three parameter blocks) of the local observations; cost = 1/2 sum r^2 (local).
  * r, J may be NULL. */
 int  msfm_ba_evaluate(msfm_ba* ba, double* r /*[n_obs][2]*/, float* J /*[n_obs][2][9]*/, double* cost);
+/* Mean reprojection error (pixels) of every local point over its observations at the current parameters:
+ * err[p] = mean_o sqrt(dx^2 + dy^2) — the per-track error Map::UpdateFromBAData recomputes on the host after
+ * every BA (src/Reconstruction/Map.cpp:1201 -> ComputeTrackError :1834-1846 ->
+ * Projection::CalculateReprojectionError, src/Reconstruction/Projection.cpp:114-133).  0 for a point without
+ * observations. */
+int  msfm_ba_track_errors(msfm_ba* ba, double* err /*[n_pts]*/);
 
 /* One linearisation at the current parameters: the reduced camera system of the free cameras with Marquardt
  * damping diag(J^T J) / radius (inv_radius = 1/radius; 0 = undamped), summed over all ranks.

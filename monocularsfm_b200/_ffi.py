@@ -107,6 +107,7 @@ def load_library():
         "msfm_ba_get_params": (C.c_int, [vp, vp, vp]),
         "msfm_ba_set_params": (C.c_int, [vp, vp, vp]),
         "msfm_ba_evaluate": (C.c_int, [vp, vp, vp, P(C.c_double)]),
+        "msfm_ba_track_errors": (C.c_int, [vp, vp]),
         "msfm_ba_linearize": (C.c_int, [vp, C.c_double, vp, vp, vp, P(C.c_double), P(i32)]),
         "msfm_ba_solve": (C.c_int, [vp, P(BAOptions), P(BASummary)]),
         "msfm_comm_unique_id": (C.c_int, [vp]),
@@ -317,6 +318,11 @@ class BAProblem:
         cost = C.c_double(0)
         self.ctx._check(self.lib.msfm_ba_evaluate(self.h, _ptr(r), _ptr(J), C.byref(cost)))
         return r, J, cost.value
+
+    def track_errors(self):
+        err = np.zeros(self.n_pts)
+        self.ctx._check(self.lib.msfm_ba_track_errors(self.h, _ptr(err)))
+        return err
 
     def linearize(self, inv_radius=0.0, want_S=True):
         n6 = 6 * self.n_free

@@ -20,6 +20,7 @@ using ba::Problem;
 cudaError_t ba_launch_cam_prep(const double*, int, CamPre*, cudaStream_t);
 cudaError_t ba_launch_evaluate(const Problem&, double*, float*, double*, int, cudaStream_t);
 cudaError_t ba_launch_linearize(const Problem&, double, double*, int, cudaStream_t);
+cudaError_t ba_launch_track_errors(const Problem&, double*, int, cudaStream_t);
 cudaError_t ba_launch_compact_blocks(const int32_t*, long long, int32_t*, int32_t*, int, cudaStream_t);
 cudaError_t ba_launch_count_tuples(const Problem&, int32_t*, int, cudaStream_t);
 cudaError_t ba_launch_scan_tuples(const int32_t*, long long, int32_t*, int32_t*, cudaStream_t);
@@ -337,6 +338,24 @@ int msfm_ba_evaluate(msfm_ba* b, double* r, float* J, double* cost) {
     if (d_J) BA_CUDA(cudaMemcpyAsync(J, d_J, size_t(b->n_obs) * 18 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     BA_CUDA(cudaStreamSynchronize(c->stream));
     if (cost) *cost = h;
+    return MSFM_OK;
+}
+
+int msfm_ba_track_errors(msfm_ba* b, double* err) {
+    if (!b) return MSFM_E_INVALID;
+    msfm_ctx* c = b->ctx;
+    if (!err && b->n_pts > 0) return c->fail(MSFM_E_INVALID, "msfm_ba_track_errors: null output");
+    if (b->n_pts == 0) return MSFM_OK;
+    BA_CUDA(cudaSetDevice(c->device));
+    int rc = prep(b, b->cur);
+    if (rc) return rc;
+    BA_CUDA(c->d_ba_r.reserve(size_t(b->n_pts) * sizeof(double)));
+    c->prof_begin(MSFM_PROF_BA_EVAL);
+    BA_CUDA(ba_launch_track_errors(b->view(b->cur), c->d_ba_r.as<double>(), c->num_sms, c->stream));
+    c->prof_end();
+    c->launches += 1;
+    BA_CUDA(cudaMemcpyAsync(err, c->d_ba_r.p, size_t(b->n_pts) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    BA_CUDA(cudaStreamSynchronize(c->stream));
     return MSFM_OK;
 }
 

@@ -145,6 +145,31 @@ __global__ void evaluate_kernel(const CamPre* __restrict__ pre, const double* __
 }
 
 // ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ double warp_sum(double v);
+
+// Mean reprojection error of every point over its observations, sqrt(dx^2 + dy^2) per observation: what
+// Map::UpdateFromBAData recomputes on the host after every BA through ComputeTrackError
+// (src/Reconstruction/Map.cpp:1201, 1834-1846; Projection::CalculateReprojectionError, Projection.cpp:114-133).
+// One warp per point, one lane per observation.
+__global__ void __launch_bounds__(256)
+track_error_kernel(Problem P, double* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < P.n_pts; p += gridDim.x * wpb) {
+        const int beg = P.pt_start[p], end = P.pt_start[p + 1];
+        const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
+        double s = 0.0;
+        for (int o = beg + lane; o < end; o += 32) {
+            const CamPre c = P.pre[P.obs_cam[o]];
+            double r[2], Jc[12], Jp[6];
+            obs_eval<false>(c, X, P.obs_uv[2 * o], P.obs_uv[2 * o + 1], P.fx, P.fy, r, Jc, Jp);
+            s += sqrt(r[0] * r[0] + r[1] * r[1]);
+        }
+        s = warp_sum(s);
+        if (lane == 0) err[p] = end > beg ? s / static_cast<double>(end - beg) : 0.0;
+    }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -572,6 +597,13 @@ cudaError_t ba_launch_evaluate(const Problem& P, double* r_out, float* J_out, do
     int grid = (P.n_obs + 255) / 256;
     if (grid > num_sms * 8) grid = num_sms * 8;
     evaluate_kernel<<<grid, 256, 0, st>>>(P.pre, P.pts, P.obs_uv, P.obs_cam, P.obs_pt, P.n_obs, P.fx, P.fy, r_out, J_out, cost);
+    return cudaGetLastError();
+}
+cudaError_t ba_launch_track_errors(const Problem& P, double* err, int num_sms, cudaStream_t st) {
+    if (P.n_pts <= 0) return cudaSuccess;
+    int grid = (P.n_pts + 7) / 8;
+    if (grid > num_sms * 8) grid = num_sms * 8;
+    track_error_kernel<<<grid, 256, 0, st>>>(P, err);
     return cudaGetLastError();
 }
 cudaError_t ba_launch_linearize(const Problem& P, double inv_radius, double* sys, int num_sms, cudaStream_t st) {

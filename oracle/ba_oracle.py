@@ -178,6 +178,23 @@ def reprojection_error_via_K(rvec, tvec, X, xy, K):
     return float(np.linalg.norm(h[:2] / h[2] - np.asarray(xy, np.float64)))
 
 
+def track_errors(cams, pts, obs_uv, obs_cam, obs_pt, fx, fy, cx=0.0, cy=0.0):
+    """Map::ComputeTrackError (src/Reconstruction/Map.cpp:1834-1846): per point, the mean over its track of
+    Projection::CalculateReprojectionError (Projection.cpp:114-133) = ||dehom(K [R|t] X) - xy||_2, with R = Rodrigues(rvec)
+    as Map::UpdateFromBAData builds it (:1186).  obs_uv are centred by (cx, cy) like the optimizer's inputs
+    (CeresBundleOptimizer.cpp:221-222); K is rebuilt with that principal point.  Plain loops: small cases only."""
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    n_pts = len(pts)
+    s = np.zeros(n_pts)
+    cnt = np.zeros(n_pts)
+    for o in range(len(obs_cam)):
+        c, p = int(obs_cam[o]), int(obs_pt[o])
+        xy = np.asarray(obs_uv[o], np.float64) + np.array([cx, cy])
+        s[p] += reprojection_error_via_K(cams[c, :3], cams[c, 3:], pts[p], xy, K)
+        cnt[p] += 1
+    return np.where(cnt > 0, s / np.maximum(cnt, 1), 0.0)
+
+
 # --------------------------------------------------------------------------------------------- normal equations
 def cost_of(r):
     return 0.5 * float((r * r).sum())

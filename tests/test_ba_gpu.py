@@ -45,6 +45,26 @@ def test_residuals_and_jacobians(ctx, golden_ba, name):
 
 
 @pytest.mark.parametrize("name", NAMES)
+def test_track_errors(ctx, golden_ba, name):
+    """msfm_ba_track_errors == Map::ComputeTrackError restated through K [R|t] (oracle.track_errors), before and after a
+    solve; and == the row norms of the golden residuals averaged per point."""
+    g = golden_ba
+    P = _prob(g, name)
+    ba = _create(ctx, P)
+    err = ba.track_errors()
+    ref = bo.track_errors(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"], 1080.0, 720.0)
+    np.testing.assert_allclose(err, ref, rtol=1e-9, atol=1e-9)
+    rn = np.linalg.norm(g[f"{name}/r"], axis=1)
+    mean = np.bincount(P["obs_pt"], rn, len(P["pts"])) / np.maximum(np.bincount(P["obs_pt"], minlength=len(P["pts"])), 1)
+    np.testing.assert_allclose(err, mean, rtol=1e-9, atol=1e-9)
+    ba.solve()
+    cams, pts = ba.get_params()
+    ref2 = bo.track_errors(cams, pts, P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
+    np.testing.assert_allclose(ba.track_errors(), ref2, rtol=1e-9, atol=1e-9)
+    ba.close()
+
+
+@pytest.mark.parametrize("name", NAMES)
 def test_schur_system(ctx, golden_ba, name):
     g = golden_ba
     ba = _create(ctx, _prob(g, name))

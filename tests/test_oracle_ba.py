@@ -158,3 +158,16 @@ def test_c_oracle_matches_python(golden_ba, name):
     np.testing.assert_allclose(S, g[f"{name}/S"], rtol=1e-9, atol=1e-7)
     np.testing.assert_allclose(rhs, g[f"{name}/rhs"], rtol=1e-9, atol=1e-7)
     assert abs(cost - float(g[f"{name}/cost"])) < 1e-9 * cost
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_track_errors_match_residual_norms(golden_ba, name):
+    """oracle.track_errors (Map::ComputeTrackError through K [R|t], Projection.cpp:114-133) == per-point mean of the
+    golden residual norms of the optimizer's functor: the reference's two statements of the reprojection error agree."""
+    g = golden_ba
+    cams, pts = g[f"{name}/cams"], g[f"{name}/pts"]
+    obs_cam, obs_pt = g[f"{name}/obs_cam"], g[f"{name}/obs_pt"]
+    err = bo.track_errors(cams, pts, g[f"{name}/obs_uv"], obs_cam, obs_pt, float(g[f"{name}/fx"]), float(g[f"{name}/fy"]), 1080.0, 720.0)
+    rn = np.linalg.norm(g[f"{name}/r"], axis=1)
+    mean = np.bincount(obs_pt, rn, len(pts)) / np.maximum(np.bincount(obs_pt, minlength=len(pts)), 1)
+    np.testing.assert_allclose(err, mean, rtol=1e-9, atol=1e-9)

@@ -166,10 +166,13 @@ int msfm_match_stats(msfm_ctx* ctx, int64_t stats[4]);
  * ------------------------------------------------------------------------------------------- */
 typedef struct msfm_ba msfm_ba;
 
+#define MSFM_BA_REFINE_FOCAL 1      /* msfm_ba_problem.flags: CeresBundelOptimizer::Parameters::refine_focal_length (:20) */
+
 typedef struct {
     int32_t n_cams, n_pts, n_obs;
-    int32_t reserved;             /* must be 0 */
-    double  fx, fy;               /* K(0,0), K(1,1) (:197-198) */
+    int32_t flags;                /* 0, or MSFM_BA_REFINE_FOCAL: (fx, fy) become ONE shared 2-parameter block of every residual
+                                     (BundleAutoDiffCostFunction :76-121, AddResidualBlock(..., focal) :227-233) */
+    double  fx, fy;               /* K(0,0), K(1,1) (:197-198); the initial focal block with MSFM_BA_REFINE_FOCAL */
     const double*  cams;          /* [n_cams][6]  rvec | tvec  (BundleData::CameraPose, cv::Mat 3x1 f64 each) */
     const double*  pts;           /* [n_pts][3]   Landmark::point3D */
     const double*  obs_uv;        /* [n_obs][2]   Measurement::point2D already centred: (x - cx, y - cy) as :221-222 */
@@ -228,6 +231,13 @@ int  msfm_ba_track_errors(msfm_ba* ba, double* err /*[n_pts]*/);
  * be NULL.  *n_free_out = F. */
 int  msfm_ba_linearize(msfm_ba* ba, double inv_radius, double* S, double* rhs, double* gc, double* cost,
                        int32_t* n_free_out);
+
+/* MSFM_BA_REFINE_FOCAL problems: the part of the same linearisation that involves the shared focal block, which borders
+ * the camera system:  [S B; B^T F] [dc; df] = [rhs; rhs_f].  B [6F][2], F [3] = (F00, F01, F11) damped like S,
+ * rhs_f [2], g_f [2] (gradient of the focal block); any may be NULL.  MSFM_E_INVALID for other problems. */
+int  msfm_ba_linearize_focal(msfm_ba* ba, double inv_radius, double* B, double* F, double* rhs_f, double* g_f);
+/* Current (fx, fy): what Optimize writes back into K after the solve (:313-317). */
+int  msfm_ba_get_focal(msfm_ba* ba, double focal[2]);
 
 /* The whole Levenberg-Marquardt solve; parameters stay on the device (msfm_ba_get_params to read). */
 int  msfm_ba_solve(msfm_ba* ba, const msfm_ba_options* opt, msfm_ba_summary* summary);

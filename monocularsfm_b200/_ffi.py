@@ -32,7 +32,7 @@ class MatchOptions(C.Structure):
 
 
 class BAProblemC(C.Structure):
-    _fields_ = [("n_cams", C.c_int32), ("n_pts", C.c_int32), ("n_obs", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("n_cams", C.c_int32), ("n_pts", C.c_int32), ("n_obs", C.c_int32), ("flags", C.c_int32),
                 ("fx", C.c_double), ("fy", C.c_double), ("cams", C.c_void_p), ("pts", C.c_void_p),
                 ("obs_uv", C.c_void_p), ("obs_cam", C.c_void_p), ("obs_pt", C.c_void_p), ("cam_const", C.c_void_p)]
 
@@ -108,6 +108,8 @@ def load_library():
         "msfm_ba_set_params": (C.c_int, [vp, vp, vp]),
         "msfm_ba_evaluate": (C.c_int, [vp, vp, vp, P(C.c_double)]),
         "msfm_ba_track_errors": (C.c_int, [vp, vp]),
+        "msfm_ba_linearize_focal": (C.c_int, [vp, C.c_double, vp, vp, vp, vp]),
+        "msfm_ba_get_focal": (C.c_int, [vp, vp]),
         "msfm_ba_linearize": (C.c_int, [vp, C.c_double, vp, vp, vp, P(C.c_double), P(i32)]),
         "msfm_ba_solve": (C.c_int, [vp, P(BAOptions), P(BASummary)]),
         "msfm_comm_unique_id": (C.c_int, [vp]),
@@ -249,8 +251,8 @@ class Context:
         return idx, dist, d2
 
     # ---- B-path
-    def ba_create(self, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy):
-        return BAProblem(self, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy)
+    def ba_create(self, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, refine_focal=False):
+        return BAProblem(self, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, refine_focal)
 
     # ---- multi-GPU
     def comm_unique_id(self) -> bytes:
@@ -277,7 +279,7 @@ class Context:
 class BAProblem:
     """msfm_ba: a flattened BundleData resident on the device."""
 
-    def __init__(self, ctx: Context, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy):
+    def __init__(self, ctx: Context, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, refine_focal=False):
         self.ctx = ctx
         self.lib = ctx.lib
         cams = np.ascontiguousarray(cams, np.float64).reshape(-1, 6)
@@ -288,7 +290,8 @@ class BAProblem:
         cam_const = np.ascontiguousarray(cam_const, np.uint8)
         self.n_cams, self.n_pts, self.n_obs = len(cams), len(pts), len(obs_cam)
         self.n_free = int((cam_const == 0).sum())
-        pr = BAProblemC(self.n_cams, self.n_pts, self.n_obs, 0, float(fx), float(fy), _ptr(cams), _ptr(pts),
+        self.refine_focal = bool(refine_focal)
+        pr = BAProblemC(self.n_cams, self.n_pts, self.n_obs, 1 if refine_focal else 0, float(fx), float(fy), _ptr(cams), _ptr(pts),
                         _ptr(obs_uv), _ptr(obs_cam), _ptr(obs_pt), _ptr(cam_const))
         h = C.c_void_p()
         ctx._check(self.lib.msfm_ba_create(ctx.h, C.byref(pr), C.byref(h)))
@@ -318,6 +321,21 @@ class BAProblem:
         cost = C.c_double(0)
         self.ctx._check(self.lib.msfm_ba_evaluate(self.h, _ptr(r), _ptr(J), C.byref(cost)))
         return r, J, cost.value
+
+    def focal(self):
+        f = (C.c_double * 2)()
+        self.ctx._check(self.lib.msfm_ba_get_focal(self.h, f))
+        return float(f[0]), float(f[1])
+
+    def linearize_focal(self, inv_radius=0.0):
+        """Border of the reduced system for a shared focal block: B [6F,2], F [2,2], rhs_f [2], g_f [2]."""
+        n6 = 6 * self.n_free
+        B = np.zeros((n6, 2))
+        F3 = np.zeros(3)
+        rf = np.zeros(2)
+        gf = np.zeros(2)
+        self.ctx._check(self.lib.msfm_ba_linearize_focal(self.h, float(inv_radius), _ptr(B), _ptr(F3), _ptr(rf), _ptr(gf)))
+        return B, np.array([[F3[0], F3[1]], [F3[1], F3[2]]]), rf, gf
 
     def track_errors(self):
         err = np.zeros(self.n_pts)

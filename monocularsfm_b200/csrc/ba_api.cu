@@ -70,7 +70,9 @@ static constexpr int kNcclSum = 0, kNcclMax = 2;
 struct msfm_ba {
     msfm_ctx* ctx = nullptr;
     int32_t n_cams = 0, n_pts = 0, n_obs = 0, n_free = 0;
-    double fx = 0, fy = 0;
+    int32_t refine_focal = 0;
+    double focal[2][2] = {{0, 0}, {0, 0}};      // (fx, fy) of the current / candidate parameter set
+    double* pt_Wf = nullptr;
     // device arrays
     double *cams[2] = {nullptr, nullptr}, *pts[2] = {nullptr, nullptr};   // current / candidate
     CamPre* pre[2] = {nullptr, nullptr};
@@ -92,11 +94,13 @@ struct msfm_ba {
     int cur = 0;
     std::vector<double> h_cams;   // host mirror of the current cameras
     std::vector<int32_t> h_cam_free;
-    size_t sys_len() const { const size_t n6 = size_t(n_free) * 6; return n6 * n6 + 3 * n6 + 8; }
+    // S | rhs | gc | udiag | scalars[8] (| B0 | B1 | focal[16] with a shared focal block)
+    size_t sys_len() const { const size_t n6 = size_t(n_free) * 6; return n6 * n6 + 3 * n6 + 8 + (refine_focal ? 2 * n6 + 16 : 0); }
     Problem view(int which) const {
         Problem P;
         P.n_cams = n_cams; P.n_pts = n_pts; P.n_obs = n_obs; P.n_free = n_free;
-        P.fx = fx; P.fy = fy;
+        P.fx = focal[which][0]; P.fy = focal[which][1];
+        P.refine_focal = refine_focal; P.pt_Wf = pt_Wf;
         P.pre = pre[which]; P.pts = pts[which]; P.obs_uv = obs_uv; P.obs_cam = obs_cam; P.obs_pt = obs_pt;
         P.pt_start = pt_start; P.cam_free = cam_free;
         P.gpmax_bits = reinterpret_cast<unsigned long long*>(small + 4);
@@ -149,7 +153,7 @@ void msfm_ba_destroy(msfm_ba* b) {
     cudaStreamSynchronize(c->stream);
     void* ptrs[] = {b->cams[0], b->cams[1], b->pts[0], b->pts[1], b->pre[0], b->pre[1], b->obs_uv, b->obs_cam, b->obs_pt,
                     b->pt_start, b->cam_free, b->sys, b->xsol, b->small, b->work, b->dev_info, b->cam_obs_start,
-                    b->cam_obs_list, b->blk_start, b->blk_tuples, b->blk_list, b->obs_J, b->obs_r, b->pt_Vinv, b->pt_gp};
+                    b->cam_obs_list, b->blk_start, b->blk_tuples, b->blk_list, b->obs_J, b->obs_r, b->pt_Vinv, b->pt_gp, b->pt_Wf};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -159,7 +163,7 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     if (!c) return MSFM_E_INVALID;
     if (!pr || !out) return c->fail(MSFM_E_INVALID, "msfm_ba_create: null argument");
     *out = nullptr;
-    if (pr->n_cams <= 0 || pr->n_pts < 0 || pr->n_obs < 0 || pr->reserved != 0 || !pr->cams || !pr->cam_const ||
+    if (pr->n_cams <= 0 || pr->n_pts < 0 || pr->n_obs < 0 || (pr->flags & ~MSFM_BA_REFINE_FOCAL) != 0 || !pr->cams || !pr->cam_const ||
         (pr->n_pts > 0 && !pr->pts) || (pr->n_obs > 0 && (!pr->obs_uv || !pr->obs_cam || !pr->obs_pt)))
         return c->fail(MSFM_E_INVALID, "msfm_ba_create: bad problem description");
     BA_CUDA(cudaSetDevice(c->device));
@@ -202,7 +206,8 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     if (!b) return c->fail(MSFM_E_CUDA, "out of host memory");
     b->ctx = c;
     b->n_cams = pr->n_cams; b->n_pts = pr->n_pts; b->n_obs = pr->n_obs; b->n_free = nf;
-    b->fx = pr->fx; b->fy = pr->fy;
+    b->refine_focal = (pr->flags & MSFM_BA_REFINE_FOCAL) ? 1 : 0;
+    b->focal[0][0] = b->focal[1][0] = pr->fx; b->focal[0][1] = b->focal[1][1] = pr->fy;
     b->h_cams.assign(pr->cams, pr->cams + size_t(pr->n_cams) * 6);
     b->h_cam_free = cam_free;
     const size_t n6 = size_t(nf) * 6;
@@ -223,7 +228,8 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     BA_ALLOC(b->pt_start, (size_t(pr->n_pts) + 1) * sizeof(int32_t));
     BA_ALLOC(b->cam_free, size_t(pr->n_cams) * sizeof(int32_t));
     BA_ALLOC(b->sys, b->sys_len() * sizeof(double));
-    BA_ALLOC(b->xsol, std::max<size_t>(1, n6) * sizeof(double));
+    BA_ALLOC(b->xsol, (3 * std::max<size_t>(1, n6) + 2) * sizeof(double));      // up to 3 right-hand sides + (d fx, d fy)
+    if (b->refine_focal) BA_ALLOC(b->pt_Wf, std::max<size_t>(1, size_t(pr->n_pts)) * 6 * sizeof(double));
     BA_ALLOC(b->small, 8 * sizeof(double));
     BA_ALLOC(b->dev_info, sizeof(int));
     BA_ALLOC(b->cam_obs_start, cam_obs_start.size() * sizeof(int32_t));
@@ -410,6 +416,38 @@ int msfm_ba_linearize(msfm_ba* b, double inv_radius, double* S, double* rhs, dou
     return MSFM_OK;
 }
 
+int msfm_ba_get_focal(msfm_ba* b, double focal[2]) {
+    if (!b || !focal) return MSFM_E_INVALID;
+    focal[0] = b->focal[b->cur][0];
+    focal[1] = b->focal[b->cur][1];
+    return MSFM_OK;
+}
+
+int msfm_ba_linearize_focal(msfm_ba* b, double inv_radius, double* B, double* F, double* rhs_f, double* g_f) {
+    if (!b) return MSFM_E_INVALID;
+    msfm_ctx* c = b->ctx;
+    if (!b->refine_focal) return c->fail(MSFM_E_INVALID, "msfm_ba_linearize_focal: the problem has no shared focal block");
+    BA_CUDA(cudaSetDevice(c->device));
+    int rc = prep(b, b->cur);
+    if (rc) return rc;
+    if ((rc = linearize(b, b->cur, inv_radius))) return rc;
+    const size_t N = size_t(b->n_free) * 6;
+    std::vector<double> tail(2 * N + 16);
+    BA_CUDA(cudaMemcpyAsync(tail.data(), b->sys + N * N + 3 * N + 8, tail.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    BA_CUDA(cudaStreamSynchronize(c->stream));
+    const double* ff = tail.data() + 2 * N;
+    if (B)
+        for (size_t i = 0; i < N; ++i) { B[2 * i] = tail[i]; B[2 * i + 1] = tail[N + i]; }
+    if (F) {
+        F[0] = ff[0] + std::max(ff[7], 1e-6) * inv_radius;
+        F[1] = ff[1];
+        F[2] = ff[2] + std::max(ff[8], 1e-6) * inv_radius;
+    }
+    if (rhs_f) { rhs_f[0] = ff[3]; rhs_f[1] = ff[4]; }
+    if (g_f) { g_f[0] = ff[5]; g_f[1] = ff[6]; }
+    return MSFM_OK;
+}
+
 int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum) {
     if (!b) return MSFM_E_INVALID;
     msfm_ctx* c = b->ctx;
@@ -440,7 +478,9 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
     double cost = 0.0;
     bool have_cost = false, converged = false, failed = false;
     long long nres_local = 2LL * b->n_obs;
-    std::vector<double> h_tail(3 * N + 8), h_dc(N), h_small(8);
+    const bool focal = b->refine_focal != 0;
+    const int nrhs = focal ? 3 : 1;
+    std::vector<double> h_tail(3 * N + 8 + (focal ? 2 * N + 16 : 0)), h_dc(N + 2), h_small(8), h_x(focal ? 3 * N : 0);
     int it = 0, good = 0;
     if ((rc = prep(b, b->cur))) return rc;
     while (it < uopt->max_num_iterations) {
@@ -457,6 +497,9 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
         if (!have_cost) { cost = lin_cost; sum->initial_cost = cost; have_cost = true; }
         double gmax = h_small[4];
         for (size_t i = 0; i < N; ++i) gmax = std::max(gmax, std::fabs(h_tail[N + i]));
+        const double* hB = h_tail.data() + 3 * N + 8;          // B0 | B1 (focal only)
+        const double* hff = hB + 2 * N;                        // F00 F01 F11 rhsf0 rhsf1 gf0 gf1 uf0 uf1
+        if (focal) gmax = std::max(gmax, std::max(std::fabs(hff[5]), std::fabs(hff[6])));
         if (gmax <= uopt->gradient_tolerance) { converged = true; break; }
         // ---- solve the reduced camera system (dense Cholesky; the row-major upper block triangle written by the
         //      kernel is the column-major lower triangle cuSOLVER reads)
@@ -465,6 +508,9 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
         if (n6 > 0) {
             BA_CUDA(ba_launch_damp(b->sys, n6, inv_radius, c->stream));
             BA_CUDA(ba_launch_copy(b->sys + N * N, b->xsol, n6, c->stream));
+            if (focal) {       // two more right-hand sides: the border columns (S^-1 B for the 2 x 2 Schur complement below)
+                BA_CUDA(cudaMemcpyAsync(b->xsol + N, b->sys + N * N + 3 * N + 8, 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            }
             c->launches += 2;
             if (cusolverDnDpotrf(solver, CUBLAS_FILL_MODE_LOWER, n6, b->sys, n6, b->work, b->work_len, b->dev_info) != CUSOLVER_STATUS_SUCCESS)
                 return c->fail(MSFM_E_CUDA, "cusolverDnDpotrf failed to launch");
@@ -474,8 +520,33 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
             if (info != 0) {
                 solved = false;
             } else {
-                if (cusolverDnDpotrs(solver, CUBLAS_FILL_MODE_LOWER, n6, 1, b->sys, n6, b->xsol, n6, b->dev_info) != CUSOLVER_STATUS_SUCCESS)
+                if (cusolverDnDpotrs(solver, CUBLAS_FILL_MODE_LOWER, n6, nrhs, b->sys, n6, b->xsol, n6, b->dev_info) != CUSOLVER_STATUS_SUCCESS)
                     return c->fail(MSFM_E_CUDA, "cusolverDnDpotrs failed to launch");
+            }
+        }
+        double df[2] = {0.0, 0.0};
+        if (focal && solved) {
+            // bordered system [S B; B^T F] [dc; df] = [rhs; rhs_f]:  (F - B^T S^-1 B) df = rhs_f - B^T S^-1 rhs,  dc = S^-1 rhs - S^-1 B df
+            if (n6 > 0) {
+                BA_CUDA(cudaMemcpyAsync(h_x.data(), b->xsol, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                BA_CUDA(cudaStreamSynchronize(c->stream));
+            }
+            double f00 = hff[0] + std::max(hff[7], 1e-6) * inv_radius, f01 = hff[1], f11 = hff[2] + std::max(hff[8], 1e-6) * inv_radius;
+            double r0 = hff[3], r1 = hff[4];
+            const double *y = h_x.data(), *x0 = h_x.data() + N, *x1 = h_x.data() + 2 * N;
+            for (size_t i = 0; i < N; ++i) {
+                f00 -= hB[i] * x0[i]; f01 -= hB[i] * x1[i]; f11 -= hB[N + i] * x1[i];
+                r0 -= hB[i] * y[i];   r1 -= hB[N + i] * y[i];
+            }
+            const double det = f00 * f11 - f01 * f01;
+            if (!(det > 0.0) || !(f00 > 0.0)) {
+                solved = false;
+            } else {
+                df[0] = (f11 * r0 - f01 * r1) / det;
+                df[1] = (f00 * r1 - f01 * r0) / det;
+                for (size_t i = 0; i < N; ++i) h_dc[i] = y[i] - x0[i] * df[0] - x1[i] * df[1];
+                h_dc[N] = df[0]; h_dc[N + 1] = df[1];
+                BA_CUDA(cudaMemcpyAsync(b->xsol, h_dc.data(), (N + 2) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
             }
         }
         if (!solved) {
@@ -492,6 +563,8 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
         BA_CUDA(ba_launch_update_cams(b->cams[b->cur], b->cam_free, b->n_cams, b->xsol, b->cams[nxt], c->stream));
         c->prof_end();
         c->launches += 2;
+        b->focal[nxt][0] = b->focal[b->cur][0] + df[0];
+        b->focal[nxt][1] = b->focal[b->cur][1] + df[1];
         if ((rc = prep(b, nxt))) return rc;
         c->prof_begin(MSFM_PROF_BA_EVAL);
         BA_CUDA(ba_launch_evaluate(b->view(nxt), nullptr, nullptr, b->small + 3, c->num_sms, c->stream));
@@ -499,7 +572,7 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
         c->launches += 1;
         if (c->comm && (rc = msfm_comm_allreduce_f64(c, b->small, 4, 0))) return rc;
         BA_CUDA(cudaMemcpyAsync(h_small.data(), b->small, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        if (n6 > 0) BA_CUDA(cudaMemcpyAsync(h_dc.data(), b->xsol, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (n6 > 0 && !focal) BA_CUDA(cudaMemcpyAsync(h_dc.data(), b->xsol, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         BA_CUDA(cudaStreamSynchronize(c->stream));
         t_sol += std::chrono::duration<double>(clk::now() - t0).count();
         const double model_decrease = h_small[0], new_cost = h_small[3];
@@ -508,6 +581,10 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
         for (int cam = 0; cam < b->n_cams; ++cam)
             if (b->h_cam_free[cam] >= 0)
                 for (int k = 0; k < 6; ++k) xc2 += b->h_cams[size_t(cam) * 6 + k] * b->h_cams[size_t(cam) * 6 + k];
+        if (focal) {
+            dc2 += df[0] * df[0] + df[1] * df[1];
+            xc2 += b->focal[b->cur][0] * b->focal[b->cur][0] + b->focal[b->cur][1] * b->focal[b->cur][1];
+        }
         const double step_norm = std::sqrt(dc2 + h_small[1]), x_norm = std::sqrt(xc2 + h_small[2]);
         if (step_norm <= uopt->parameter_tolerance * (x_norm + uopt->parameter_tolerance)) { converged = true; break; }
         const double rho = model_decrease > 0 ? (cost - new_cost) / model_decrease : -1.0;

@@ -69,7 +69,7 @@ struct ObsLin {
 
 template <bool kJac>
 __device__ __forceinline__ void obs_eval(const CamPre& c, const double X[3], double u, double v, double fx, double fy,
-                                         double r[2], double Jc[12], double Jp[6]) {
+                                         double r[2], double Jc[12], double Jp[6], double xy[2] = nullptr) {
     const double px = c.R[0] * X[0] + c.R[1] * X[1] + c.R[2] * X[2] + c.t[0];
     const double py = c.R[3] * X[0] + c.R[4] * X[1] + c.R[5] * X[2] + c.t[1];
     const double pz = c.R[6] * X[0] + c.R[7] * X[1] + c.R[8] * X[2] + c.t[2];
@@ -77,6 +77,7 @@ __device__ __forceinline__ void obs_eval(const CamPre& c, const double X[3], dou
     const double xp = px * iz, yp = py * iz;
     r[0] = fx * xp - u;
     r[1] = fy * yp - v;
+    if (xy) { xy[0] = xp; xy[1] = yp; }       // d r / d (fx, fy) = diag(xp, yp)
     if (!kJac) return;
     // A = d(u,v)/dp
     const double A00 = fx * iz, A02 = -fx * xp * iz, A11 = fy * iz, A12 = -fy * yp * iz;
@@ -192,6 +193,7 @@ struct LaneObs {           // one observation in a lane
     bool valid;
     int cam, f;            // camera index, reduced (free) index or -1
     double r[2];
+    double xy[2];          // (xp, yp): the focal Jacobian
     float Jc[12], Jp[6];
 };
 
@@ -199,6 +201,7 @@ __device__ __forceinline__ void load_lane(const Problem& P, int obs, bool valid,
     o.valid = valid;
     o.cam = -1; o.f = -1;
     o.r[0] = o.r[1] = 0.0;
+    o.xy[0] = o.xy[1] = 0.0;
 #pragma unroll
     for (int k = 0; k < 12; ++k) o.Jc[k] = 0.f;
 #pragma unroll
@@ -208,7 +211,7 @@ __device__ __forceinline__ void load_lane(const Problem& P, int obs, bool valid,
     o.f = P.cam_free[o.cam];
     const CamPre c = P.pre[o.cam];
     double Jc[12], Jp[6];
-    obs_eval<true>(c, X, P.obs_uv[2 * obs], P.obs_uv[2 * obs + 1], P.fx, P.fy, o.r, Jc, Jp);
+    obs_eval<true>(c, X, P.obs_uv[2 * obs], P.obs_uv[2 * obs + 1], P.fx, P.fy, o.r, Jc, Jp, o.xy);
     if (o.f >= 0) {
 #pragma unroll
         for (int k = 0; k < 12; ++k) o.Jc[k] = static_cast<float>(Jc[k]);
@@ -218,9 +221,12 @@ __device__ __forceinline__ void load_lane(const Problem& P, int obs, bool valid,
 }
 
 // per-point normal-equation pieces: V (damped), V^-1, g_p — reduced over the whole track
+// wf (nullable): Wf = sum Jf^T Jp (2x3);  fstat (nullable): sum xp^2, sum yp^2, sum xp r0, sum yp r1 over the track
 __device__ __forceinline__ void point_pass1(const Problem& P, int p, int beg, int end, int lane, const double X[3],
-                                            double inv_radius, double Vinv[6], double gp[3], LaneObs& first) {
+                                            double inv_radius, double Vinv[6], double gp[3], LaneObs& first,
+                                            double* wf = nullptr, double* fstat = nullptr) {
     double v[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    double w6[6] = {0, 0, 0, 0, 0, 0}, f4[4] = {0, 0, 0, 0};
     for (int base = beg; base < end; base += 32) {
         LaneObs o;
         load_lane(P, base + lane, base + lane < end, X, o);
@@ -229,6 +235,22 @@ __device__ __forceinline__ void point_pass1(const Problem& P, int p, int beg, in
         v[0] += j0 * j0 + j3 * j3; v[1] += j0 * j1 + j3 * j4; v[2] += j0 * j2 + j3 * j5;
         v[3] += j1 * j1 + j4 * j4; v[4] += j1 * j2 + j4 * j5; v[5] += j2 * j2 + j5 * j5;
         g[0] += j0 * o.r[0] + j3 * o.r[1]; g[1] += j1 * o.r[0] + j4 * o.r[1]; g[2] += j2 * o.r[0] + j5 * o.r[1];
+        if (wf) {
+            w6[0] += o.xy[0] * j0; w6[1] += o.xy[0] * j1; w6[2] += o.xy[0] * j2;
+            w6[3] += o.xy[1] * j3; w6[4] += o.xy[1] * j4; w6[5] += o.xy[1] * j5;
+        }
+        if (fstat) {
+            f4[0] += o.xy[0] * o.xy[0]; f4[1] += o.xy[1] * o.xy[1];
+            f4[2] += o.xy[0] * o.r[0];  f4[3] += o.xy[1] * o.r[1];
+        }
+    }
+    if (wf) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) wf[k] = warp_sum(w6[k]);
+    }
+    if (fstat) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fstat[k] = warp_sum(f4[k]);
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) v[k] = warp_sum(v[k]);
@@ -253,13 +275,32 @@ point_pass_kernel(Problem P, double inv_radius, double* __restrict__ sys) {
     const size_t n6 = static_cast<size_t>(P.n_free) * 6;
     double* scal = sys + n6 * n6 + 3 * n6;
     double cost_local = 0.0, gpmax_local = 0.0;
+    double ff[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};        // focal block sums of this warp (lane 0): F00 F01 F11 rhsf0 rhsf1 gf0 gf1 uf0 uf1
+    const bool focal = P.refine_focal != 0;
     for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < P.n_pts; p += gridDim.x * wpb) {
         const int beg = P.pt_start[p], end = P.pt_start[p + 1];
-        if (beg == end) continue;
+        if (beg == end) {
+            if (focal && lane < 6) P.pt_Wf[6 * static_cast<size_t>(p) + lane] = 0.0;
+            continue;
+        }
         const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
-        double Vinv[6], gp[3];
+        double Vinv[6], gp[3], Wf[6], fs[4];
         LaneObs A;
-        point_pass1(P, p, beg, end, lane, X, inv_radius, Vinv, gp, A);
+        point_pass1(P, p, beg, end, lane, X, inv_radius, Vinv, gp, A, focal ? Wf : nullptr, focal ? fs : nullptr);
+        if (focal) {
+            // T = Wf V^-1 (2x3);  F -= T Wf^T,  rhs_f += T g_p - g_f   (the point is eliminated from the focal block too)
+            if (lane < 6) P.pt_Wf[6 * static_cast<size_t>(p) + lane] = Wf[lane];
+            const double T0[3] = {Wf[0] * Vinv[0] + Wf[1] * Vinv[1] + Wf[2] * Vinv[2], Wf[0] * Vinv[1] + Wf[1] * Vinv[3] + Wf[2] * Vinv[4],
+                                  Wf[0] * Vinv[2] + Wf[1] * Vinv[4] + Wf[2] * Vinv[5]};
+            const double T1[3] = {Wf[3] * Vinv[0] + Wf[4] * Vinv[1] + Wf[5] * Vinv[2], Wf[3] * Vinv[1] + Wf[4] * Vinv[3] + Wf[5] * Vinv[4],
+                                  Wf[3] * Vinv[2] + Wf[4] * Vinv[4] + Wf[5] * Vinv[5]};
+            ff[0] += fs[0] - (T0[0] * Wf[0] + T0[1] * Wf[1] + T0[2] * Wf[2]);
+            ff[1] += -(T0[0] * Wf[3] + T0[1] * Wf[4] + T0[2] * Wf[5]);
+            ff[2] += fs[1] - (T1[0] * Wf[3] + T1[1] * Wf[4] + T1[2] * Wf[5]);
+            ff[3] += (T0[0] * gp[0] + T0[1] * gp[1] + T0[2] * gp[2]) - fs[2];
+            ff[4] += (T1[0] * gp[0] + T1[1] * gp[1] + T1[2] * gp[2]) - fs[3];
+            ff[5] += fs[2]; ff[6] += fs[3]; ff[7] += fs[0]; ff[8] += fs[1];
+        }
         gpmax_local = fmax(gpmax_local, fmax(fabs(gp[0]), fmax(fabs(gp[1]), fabs(gp[2]))));
         if (lane < 6) P.pt_Vinv[6 * static_cast<size_t>(p) + lane] = Vinv[lane];
         if (lane < 3) P.pt_gp[3 * static_cast<size_t>(p) + lane] = gp[lane];
@@ -282,6 +323,19 @@ point_pass_kernel(Problem P, double inv_radius, double* __restrict__ sys) {
     for (int o = 16; o > 0; o >>= 1) gpmax_local = fmax(gpmax_local, __shfl_xor_sync(0xffffffffu, gpmax_local, o));
     if (lane == 0) { sh_c[threadIdx.x >> 5] = cost_local; sh_g[threadIdx.x >> 5] = gpmax_local; }
     __syncthreads();
+    if (focal) {       // 9 fp64 atomics per CTA into the focal slots behind the scalars
+        __shared__ double sh_f[8][9];
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) sh_f[threadIdx.x >> 5][k] = ff[k];
+        }
+        __syncthreads();
+        if (threadIdx.x < 9) {
+            double v = 0.0;
+            for (int k = 0; k < wpb; ++k) v += sh_f[k][threadIdx.x];
+            atomicAdd(scal + 8 + 2 * n6 + threadIdx.x, v);
+        }
+    }
     if (threadIdx.x == 0) {
         double c = 0.0, g = 0.0;
         for (int k = 0; k < wpb; ++k) { c += sh_c[k]; g = fmax(g, sh_g[k]); }
@@ -364,6 +418,52 @@ camera_diag_kernel(Problem P, double* __restrict__ sys) {
         else if (k < 42) rhs[f * 6 + (k - 36)] = v;
         else if (k < 48) rhs[n6 + f * 6 + (k - 42)] = v;           // gc
         else rhs[2 * n6 + f * 6 + (k - 48)] = v;                   // udiag
+    }
+}
+
+// Pass F (refine_focal only) — one CTA per free camera: the 6 x 2 border block that couples the camera with the shared
+// focal block, B_c = sum_obs (Jc^T Jf - Y Wf_p^T), Jf = diag(xp, yp) recovered from the stored Jacobian
+// (Jc[3] = fx/pz, Jc[5] = -fx xp/pz;  Jc[10] = fy/pz, Jc[11] = -fy yp/pz).  Stored as two columns B0 | B1 behind the
+// scalars of the system buffer.
+__global__ void __launch_bounds__(256)
+camera_focal_border_kernel(Problem P, double* __restrict__ sys) {
+    const int f = blockIdx.x;
+    if (f >= P.n_free) return;
+    const size_t n6 = static_cast<size_t>(P.n_free) * 6;
+    double acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+    const int beg = P.cam_obs_start[f], end = P.cam_obs_start[f + 1];
+    for (int idx = beg + threadIdx.x; idx < end; idx += blockDim.x) {
+        const int o = __ldg(P.cam_obs_list + idx);
+        const int p = __ldg(P.obs_pt + o);
+        float Jc[12], Jp[6], vi[6], W[18], Y[18], wf[6];
+        load_obs_J(P.obs_J, o, Jc, Jp);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) vi[k] = static_cast<float>(__ldg(P.pt_Vinv + 6 * static_cast<size_t>(p) + k));
+#pragma unroll
+        for (int k = 0; k < 6; ++k) wf[k] = static_cast<float>(__ldg(P.pt_Wf + 6 * static_cast<size_t>(p) + k));
+        make_WY(Jc, Jp, vi, W, Y);
+        const float xp = -Jc[5] / Jc[3], yp = -Jc[11] / Jc[10];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            acc[2 * i] += static_cast<double>(Jc[i] * xp - (Y[3 * i] * wf[0] + Y[3 * i + 1] * wf[1] + Y[3 * i + 2] * wf[2]));
+            acc[2 * i + 1] += static_cast<double>(Jc[6 + i] * yp - (Y[3 * i] * wf[3] + Y[3 * i + 1] * wf[4] + Y[3 * i + 2] * wf[5]));
+        }
+    }
+    __shared__ double sh[8][12];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) sh[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        double v = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) v += sh[w][threadIdx.x];
+        double* B = sys + n6 * n6 + 3 * n6 + 8;
+        B[(threadIdx.x & 1) * n6 + static_cast<size_t>(f) * 6 + (threadIdx.x >> 1)] = v;
     }
 }
 
@@ -513,7 +613,10 @@ backsub_kernel(Problem P, double inv_radius, const double* __restrict__ dc /*[n_
         double Vinv[6], gp[3];
         LaneObs A;
         point_pass1(P, p, beg, end, lane, X, inv_radius, Vinv, gp, A);
-        // t = g_p + sum W^T dc = g_p + sum Jp^T (Jc dc)
+        // shared focal block: dc holds (d fx, d fy) behind the camera steps
+        const bool focal = P.refine_focal != 0;
+        const double df0 = focal ? dc[static_cast<size_t>(P.n_free) * 6] : 0.0, df1 = focal ? dc[static_cast<size_t>(P.n_free) * 6 + 1] : 0.0;
+        // t = g_p + sum W^T dc (+ Wf^T df) = g_p + sum Jp^T (Jc dc + Jf df)
         double t[3] = {0, 0, 0};
         for (int base = beg; base < end; base += 32) {
             if (base != beg) load_lane(P, base + lane, base + lane < end, X, A);
@@ -530,6 +633,11 @@ backsub_kernel(Problem P, double inv_radius, const double* __restrict__ dc /*[n_
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) t[k] = gp[k] + warp_sum(t[k]);
+        if (focal) {
+            const double* wf = P.pt_Wf + 6 * static_cast<size_t>(p);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) t[k] += wf[k] * df0 + wf[3 + k] * df1;
+        }
         double dp[3];
         dp[0] = -(Vinv[0] * t[0] + Vinv[1] * t[1] + Vinv[2] * t[2]);
         dp[1] = -(Vinv[1] * t[0] + Vinv[3] * t[1] + Vinv[4] * t[2]);
@@ -543,8 +651,8 @@ backsub_kernel(Problem P, double inv_radius, const double* __restrict__ dc /*[n_
         for (int base = beg; base < end; base += 32) {
             if (!(base == beg && end - beg <= 32)) load_lane(P, base + lane, base + lane < end, X, A);
             if (A.valid) {
-                double jd0 = A.Jp[0] * dp[0] + A.Jp[1] * dp[1] + A.Jp[2] * dp[2];
-                double jd1 = A.Jp[3] * dp[0] + A.Jp[4] * dp[1] + A.Jp[5] * dp[2];
+                double jd0 = A.Jp[0] * dp[0] + A.Jp[1] * dp[1] + A.Jp[2] * dp[2] + A.xy[0] * df0;
+                double jd1 = A.Jp[3] * dp[0] + A.Jp[4] * dp[1] + A.Jp[5] * dp[2] + A.xy[1] * df1;
                 if (A.f >= 0) {
 #pragma unroll
                     for (int i = 0; i < 6; ++i) {
@@ -613,6 +721,7 @@ cudaError_t ba_launch_linearize(const Problem& P, double inv_radius, double* sys
     point_pass_kernel<<<grid, 256, 0, st>>>(P, inv_radius, sys);
     if (P.n_free > 0) {
         camera_diag_kernel<<<P.n_free, 256, 0, st>>>(P, sys);
+        if (P.refine_focal) camera_focal_border_kernel<<<P.n_free, 256, 0, st>>>(P, sys);
         if (P.n_blk_list > 0) {
             const int g2 = P.n_blk_list < num_sms * 64 ? P.n_blk_list : num_sms * 64;
             pair_block_kernel<<<g2, kPairBlockThreads, 0, st>>>(P, sys);

@@ -39,6 +39,9 @@ struct Problem {
     double* obs_r;                  // [n_obs][2]
     double* pt_Vinv;                // [n_pts][6]   inverse of the damped point block (symmetric)
     double* pt_gp;                  // [n_pts][3]
+    // ---- shared focal block (BundleAutoDiffCostFunction, CeresBundleOptimizer.cpp:76-121; refine_focal_length)
+    int32_t refine_focal;           // 0: (fx, fy) constant; 1: one shared 2-parameter block, bordering the camera system
+    double* pt_Wf;                  // [n_pts][6]   Wf = sum_obs Jf^T Jp (2x3), Jf = d r / d (fx, fy) = diag(xp, yp)
 };
 
 }  // namespace ba

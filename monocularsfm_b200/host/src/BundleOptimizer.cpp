@@ -60,12 +60,12 @@ Flat Flatten(BundleData& bd) {
     return f;
 }
 
-msfm_ba* CreateOnDevice(const Flat& f) {
+msfm_ba* CreateOnDevice(const Flat& f, bool refine_focal_length) {
     msfm_ba_problem pr;
     pr.n_cams = static_cast<int32_t>(f.cam_ids.size());
     pr.n_pts = static_cast<int32_t>(f.pt_ids.size());
     pr.n_obs = static_cast<int32_t>(f.obs_cam.size());
-    pr.reserved = 0;
+    pr.flags = refine_focal_length ? MSFM_BA_REFINE_FOCAL : 0;        // shared focal block of every residual (:225-233)
     pr.fx = f.fx; pr.fy = f.fy;
     pr.cams = f.cams.data(); pr.pts = f.pts.data(); pr.obs_uv = f.uv.data();
     pr.obs_cam = f.obs_cam.data(); pr.obs_pt = f.obs_pt.data(); pr.cam_const = f.cam_const.data();
@@ -80,7 +80,7 @@ double BundleData::Debug() {
     // error ||K [R|t] X - x|| equals the norm of the BA residual (Projection.cpp:114-133 vs CeresBundleOptimizer.cpp:44-51)
     Flat f = Flatten(*this);
     if (f.obs_cam.empty()) return 0.0;
-    msfm_ba* ba = CreateOnDevice(f);
+    msfm_ba* ba = CreateOnDevice(f, false);
     std::vector<double> r(f.obs_cam.size() * 2);
     double cost = 0;
     device::Check(msfm_ba_evaluate(ba, r.data(), nullptr, &cost), "msfm_ba_evaluate");
@@ -101,24 +101,20 @@ double BundleData::Debug() {
 CeresBundelOptimizer::CeresBundelOptimizer(const Parameters& params) : params_(params) {}
 
 bool CeresBundelOptimizer::Optimize(BundleData& bundle_data) {
-    if (params_.refine_focal_length) {
-        // The shared-focal variant (BundleAutoDiffCostFunction, CeresBundleOptimizer.cpp:76-121) is not on the device yet
-        // (SURVEY §8f-3); like every failed solve of the reference this prints and returns false (:296-301).
-        std::cout << "Bundle Adjustment failed. (refine_focal_length is not supported by the B200 path)" << std::endl;
-        return false;
-    }
     Flat f = Flatten(bundle_data);
     if (f.obs_cam.empty() || f.cam_ids.empty()) {
         std::cout << "Bundle Adjustment failed." << std::endl;
         return false;
     }
-    msfm_ba* ba = CreateOnDevice(f);
+    msfm_ba* ba = CreateOnDevice(f, params_.refine_focal_length);
     msfm_ba_options opt;
     msfm_ba_default_options(&opt, static_cast<int32_t>(bundle_data.camera_poses.size()));   // :262-291
     msfm_ba_summary s;
     device::Check(msfm_ba_solve(ba, &opt, &s), "msfm_ba_solve");
     // parameters are written back in place whatever the outcome, like Ceres mutating the caller's blocks (:230-242)
     device::Check(msfm_ba_get_params(ba, f.cams.data(), f.pts.data()), "msfm_ba_get_params");
+    double focal[2] = {f.fx, f.fy};
+    device::Check(msfm_ba_get_focal(ba, focal), "msfm_ba_get_focal");
     msfm_ba_destroy(ba);
     for (size_t i = 0; i < f.cam_ids.size(); ++i) {
         BundleData::CameraPose& cp = bundle_data.camera_poses[f.cam_ids[i]];
@@ -143,5 +139,9 @@ bool CeresBundelOptimizer::Optimize(BundleData& bundle_data) {
               << " Final RMSE: " << std::sqrt(s.final_cost * 2 / s.num_residuals) << "\n"
               << " Time (s): " << s.total_time_s << "\n"
               << std::endl;                                                    // :303-310
+    if (params_.refine_focal_length) {                                         // :313-317
+        bundle_data.K.at<double>(0, 0) = focal[0];
+        bundle_data.K.at<double>(1, 1) = focal[1];
+    }
     return true;
 }

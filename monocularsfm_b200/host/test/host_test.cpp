@@ -155,10 +155,19 @@ static int run_ba(char** argv) {
     out.write(reinterpret_cast<const char*>(head), sizeof head);
     out.write(reinterpret_cast<const char*>(cams.data()), cams.size() * 8);
     out.write(reinterpret_cast<const char*>(pts.data()), pts.size() * 8);
+    // shared-focal variant (refine_focal_length, CeresBundleOptimizer.cpp:225-233, 313-317): start from a wrong focal
+    // length on the already optimised scene; the solve has to pull K(0,0), K(1,1) back and lower the error
     CeresBundelOptimizer::Parameters p2;
     p2.refine_focal_length = true;
     CeresBundelOptimizer opt2(p2);
-    if (opt2.Optimize(bd)) return 3;                         // unsupported variant must report failure
+    const double fx_true = bd.K.at<double>(0, 0), fy_true = bd.K.at<double>(1, 1);
+    bd.K.at<double>(0, 0) = fx_true * 1.02;
+    bd.K.at<double>(1, 1) = fy_true * 0.98;
+    const double before2 = bd.Debug();
+    if (!opt2.Optimize(bd)) return 3;
+    const double after2 = bd.Debug();
+    const double tail[4] = {before2, after2, bd.K.at<double>(0, 0) / fx_true, bd.K.at<double>(1, 1) / fy_true};
+    out.write(reinterpret_cast<const char*>(tail), sizeof tail);
     return 0;
 }
 

@@ -140,6 +140,125 @@ def residual_jacobian_jets(cams, pts, obs_uv, obs_cam, obs_pt, fx, fy):
     return r, J
 
 
+def residual_jacobian_jets_focal(cams, pts, obs_uv, obs_cam, obs_pt, fx, fy):
+    """BundleAutoDiffCostFunction (CeresBundleOptimizer.cpp:76-121; AutoDiffCostFunction<..., 2, 3, 3, 3, 2> at :116): the
+    same residual with (fx, fy) as a FOURTH parameter block `focal` shared by every residual (:227-233).
+    Returns r [N,2], J [N,2,11] (columns rvec(3) | tvec(3) | point(3) | focal(2))."""
+    cams = np.asarray(cams, np.float64)
+    pts = np.asarray(pts, np.float64)
+    n = len(obs_cam)
+    eye = np.eye(11)
+    cam_o = cams[obs_cam]
+    pt_o = pts[obs_pt]
+
+    def seed(vals, k):
+        return Jet(vals.copy(), np.broadcast_to(eye[k], (n, 11)).copy())
+
+    w = [seed(cam_o[:, k], k) for k in range(3)]
+    t = [seed(cam_o[:, 3 + k], 3 + k) for k in range(3)]
+    X = [seed(pt_o[:, k], 6 + k) for k in range(3)]
+    f = [seed(np.full(n, float(fx)), 9), seed(np.full(n, float(fy)), 10)]
+    p = angle_axis_rotate_point(w, X)
+    p = [p[k] + t[k] for k in range(3)]
+    xp = p[0] / p[2]
+    yp = p[1] / p[2]
+    rx = f[0] * xp - obs_uv[:, 0]
+    ry = f[1] * yp - obs_uv[:, 1]
+    return np.stack([rx.a, ry.a], 1), np.stack([rx.v, ry.v], 1)
+
+
+def reduced_system_focal(r, J11, obs_cam, obs_pt, n_cams, n_pts, cam_const, inv_radius):
+    """Dense statement of what Ceres' SchurEliminator does with the focal block among the f-blocks: full damped normal
+    equations over [free cameras (6 each) | focal (2) | points (3 each)], points eliminated.  Returns the reduced matrix
+    R [(6F+2),(6F+2)] = [[S, B], [B^T, F]], its right-hand side [6F+2] (R d = rhs), the gradient [6F+2], the damped point
+    blocks' inverse and the bookkeeping needed for back-substitution.  Small problems only."""
+    cam_const = np.asarray(cam_const, bool)
+    free_idx = np.nonzero(~cam_const)[0]
+    fmap = -np.ones(n_cams, np.int64)
+    fmap[free_idx] = np.arange(len(free_idx))
+    F = len(free_idx)
+    nc = 6 * F + 2
+    n = nc + 3 * n_pts
+    Jfull = np.zeros((2 * len(obs_cam), n))
+    for o in range(len(obs_cam)):
+        f = fmap[obs_cam[o]]
+        rows = slice(2 * o, 2 * o + 2)
+        if f >= 0:
+            Jfull[rows, 6 * f:6 * f + 6] = J11[o, :, :6]
+        Jfull[rows, 6 * F:6 * F + 2] = J11[o, :, 9:11]
+        Jfull[rows, nc + 3 * obs_pt[o]:nc + 3 * obs_pt[o] + 3] = J11[o, :, 6:9]
+    H = Jfull.T @ Jfull
+    g = Jfull.T @ r.reshape(-1)
+    d = np.arange(n)
+    H[d, d] += np.maximum(H[d, d], 1e-6) * inv_radius            # Ceres min_lm_diagonal on every parameter
+    Hcc, Hcp, Hpp = H[:nc, :nc], H[:nc, nc:], H[nc:, nc:]
+    Hpp_inv = np.linalg.inv(Hpp)                                  # block diagonal (3x3 per point)
+    R = Hcc - Hcp @ Hpp_inv @ Hcp.T
+    rhs = -(g[:nc] - Hcp @ Hpp_inv @ g[nc:])
+    return R, rhs, g[:nc], (Hcp, Hpp_inv, g[nc:], fmap, F)
+
+
+def lm_solve_focal(cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, max_iters=100, function_tol=1e-6,
+                   gradient_tol=1e-10, parameter_tol=1e-8, initial_radius=1e4):
+    """lm_solve with the shared focal block (refine_focal_length = true): identical trust-region rules, dense algebra."""
+    cams = np.array(cams, np.float64)
+    pts = np.array(pts, np.float64)
+    focal = np.array([fx, fy], np.float64)
+    n_cams, n_pts = len(cams), len(pts)
+    cam_const = np.asarray(cam_const, bool)
+    radius, decrease = initial_radius, 2.0
+    r, J = residual_jacobian_jets_focal(cams, pts, obs_uv, obs_cam, obs_pt, focal[0], focal[1])
+    cost = cost_of(r)
+    initial, costs, converged, it = cost, [cost], False, 0
+    while it < max_iters:
+        it += 1
+        R, rhs, gcf, (Hcp, Hpp_inv, gp, fmap, F) = reduced_system_focal(r, J, obs_cam, obs_pt, n_cams, n_pts, cam_const, 1.0 / radius)
+        gmax = max(np.abs(gcf).max(), np.abs(gp).max())
+        if gmax <= gradient_tol:
+            converged = True
+            break
+        try:
+            dcf = np.linalg.solve(R, rhs)
+        except np.linalg.LinAlgError:
+            radius /= decrease
+            decrease *= 2
+            continue
+        dp = (-Hpp_inv @ (gp + Hcp.T @ dcf)).reshape(-1, 3)
+        dc = np.zeros((n_cams, 6))
+        dc[fmap >= 0] = dcf[:6 * F].reshape(-1, 6)
+        df = dcf[6 * F:]
+        step_norm = np.sqrt((dcf ** 2).sum() + (dp ** 2).sum())
+        x_norm = np.sqrt((cams[~cam_const] ** 2).sum() + (focal ** 2).sum() + (pts ** 2).sum())
+        if step_norm <= parameter_tol * (x_norm + parameter_tol):
+            converged = True
+            break
+        Jc = J[:, :, :6].copy()
+        Jc[cam_const[obs_cam]] = 0
+        Jd = (np.einsum("nki,ni->nk", Jc, dc[obs_cam]) + np.einsum("nki,ni->nk", J[:, :, 6:9], dp[obs_pt]) + J[:, :, 9:11] @ df)
+        model_decrease = -(float((r * Jd).sum()) + 0.5 * float((Jd * Jd).sum()))
+        ncams, npts, nfocal = cams + dc, pts + dp, focal + df
+        new_cost = cost_of(residuals_only(ncams, npts, obs_uv, obs_cam, obs_pt, nfocal[0], nfocal[1]))
+        rho = (cost - new_cost) / model_decrease if model_decrease > 0 else -1.0
+        if rho > 1e-3:
+            cams, pts, focal = ncams, npts, nfocal
+            dcost = cost - new_cost
+            cost = new_cost
+            costs.append(cost)
+            radius = min(radius / max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3), 1e16)
+            decrease = 2.0
+            r, J = residual_jacobian_jets_focal(cams, pts, obs_uv, obs_cam, obs_pt, focal[0], focal[1])
+            if dcost <= function_tol * cost:
+                converged = True
+                break
+        else:
+            radius /= decrease
+            decrease *= 2
+            if radius < 1e-32:
+                break
+    return {"cams": cams, "pts": pts, "focal": focal, "iterations": it, "initial_cost": initial, "final_cost": cost,
+            "converged": converged, "costs": costs}
+
+
 def residuals_only(cams, pts, obs_uv, obs_cam, obs_pt, fx, fy):
     """Plain float64 evaluation of the same functor (no derivatives)."""
     cams = np.asarray(cams, np.float64)

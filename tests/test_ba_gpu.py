@@ -133,3 +133,56 @@ def test_duplicate_camera_in_a_track_is_rejected(ctx):
     oc[1] = oc[0]                                   # point 0 now observed twice by the same camera
     with pytest.raises(m.MsfmError):
         ctx.ba_create(P["cams"], P["pts"], P["obs_uv"], oc, P["obs_pt"], P["cam_const"], P["fx"], P["fy"])
+
+
+# ------------------------------------------------------------------------------------------------ shared focal block
+def _create_focal(ctx, P, fx=None, fy=None):
+    return ctx.ba_create(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"],
+                         P["fx"] if fx is None else fx, P["fy"] if fy is None else fy, refine_focal=True)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_focal_border_of_the_reduced_system(ctx, golden_ba, name):
+    """refine_focal_length (BundleAutoDiffCostFunction, CeresBundleOptimizer.cpp:76-121): S, rhs, and the border B, F, rhs_f
+    that the shared focal block adds, against the dense statement of the Schur elimination in the oracle."""
+    P = _prob(golden_ba, name)
+    n_cams, n_pts = len(P["cams"]), len(P["pts"])
+    r, J = bo.residual_jacobian_jets_focal(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
+    for inv_radius in (1e-2, 1e-4):       # damped: "special" holds a point with a single observation (V of rank 2)
+        R, rhs, g, _ = bo.reduced_system_focal(r, J, P["obs_cam"], P["obs_pt"], n_cams, n_pts, P["cam_const"], inv_radius)
+        ba = _create_focal(ctx, P)
+        S, rhs_c, gc, cost = ba.linearize(inv_radius)
+        B, F, rhs_f, g_f = ba.linearize_focal(inv_radius)
+        n6 = S.shape[0]
+        scale = np.abs(R).max()
+        assert np.abs(S - R[:n6, :n6]).max() <= 1e-5 * scale
+        assert np.abs(B - R[:n6, n6:]).max() <= 1e-5 * scale
+        assert np.abs(F - R[n6:, n6:]).max() <= 1e-5 * scale
+        rs = np.abs(rhs).max()
+        assert np.abs(rhs_c - rhs[:n6]).max() <= 1e-5 * rs and np.abs(rhs_f - rhs[n6:]).max() <= 1e-5 * rs
+        assert np.abs(g_f - g[n6:]).max() <= 1e-9 * max(1.0, np.abs(g).max())
+        ba.close()
+
+
+@pytest.mark.parametrize("name", ["small", "ring16"])
+def test_lm_solve_with_shared_focal_matches_oracle(ctx, golden_ba, name):
+    P = _prob(golden_ba, name)
+    fx0, fy0 = P["fx"] * 1.02, P["fy"] * 0.985
+    ref = bo.lm_solve_focal(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], fx0, fy0)
+    ba = _create_focal(ctx, P, fx0, fy0)
+    s = ba.solve()
+    assert s["termination"] == 0 and ref["converged"]
+    assert abs(s["initial_cost"] - ref["initial_cost"]) <= 1e-9 * ref["initial_cost"]
+    assert abs(s["final_cost"] - ref["final_cost"]) <= 1e-5 * ref["final_cost"], (s["final_cost"], ref["final_cost"])
+    f = ba.focal()
+    assert abs(f[0] - ref["focal"][0]) <= 1e-3 * ref["focal"][0] and abs(f[1] - ref["focal"][1]) <= 1e-3 * ref["focal"][1]
+    cams, pts = ba.get_params()
+    r = bo.residuals_only(cams, pts, P["obs_uv"], P["obs_cam"], P["obs_pt"], f[0], f[1])
+    assert abs(bo.cost_of(r) - s["final_cost"]) <= 1e-9 * s["final_cost"]
+    # the constant-focal problem is untouched by the flag's plumbing
+    ba0 = _create(ctx, P)
+    assert ba0.focal() == (P["fx"], P["fy"])
+    with pytest.raises(m.MsfmError):
+        ba0.linearize_focal(0.0)
+    ba0.close()
+    ba.close()

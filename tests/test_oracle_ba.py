@@ -171,3 +171,44 @@ def test_track_errors_match_residual_norms(golden_ba, name):
     rn = np.linalg.norm(g[f"{name}/r"], axis=1)
     mean = np.bincount(obs_pt, rn, len(pts)) / np.maximum(np.bincount(obs_pt, minlength=len(pts)), 1)
     np.testing.assert_allclose(err, mean, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_focal_jets_vs_finite_differences_and_base_functor(golden_ba, name):
+    """BundleAutoDiffCostFunction (:76-121): same residual and same first nine Jacobian columns as the constant-focal functor;
+    the two focal columns against central differences (the residual is linear in fx, fy: exact up to rounding)."""
+    P = _prob(golden_ba, name)
+    r, J = bo.residual_jacobian_jets_focal(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
+    r0, J0 = bo.residual_jacobian_jets(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
+    np.testing.assert_array_equal(r, r0)
+    np.testing.assert_array_equal(J[:, :, :9], J0)
+    h = 1e-3
+    for k, (dfx, dfy) in enumerate(((h, 0.0), (0.0, h))):
+        rp = bo.residuals_only(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"] + dfx, P["fy"] + dfy)
+        rm = bo.residuals_only(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"] - dfx, P["fy"] - dfy)
+        fd = (rp - rm) / (2 * h)
+        np.testing.assert_allclose(J[:, :, 9 + k], fd, rtol=1e-7, atol=1e-7 * np.abs(fd).max())
+
+
+def test_reduced_system_focal_contains_the_camera_system(golden_ba):
+    """The (6F+2) reduced system with the focal block among the f-blocks has the constant-focal camera system as its leading
+    block (same S, same rhs)."""
+    P = _prob(golden_ba, "ring16")
+    r, J = bo.residual_jacobian_jets_focal(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
+    n_cams, n_pts = len(P["cams"]), len(P["pts"])
+    R, rhs, g, _ = bo.reduced_system_focal(r, J, P["obs_cam"], P["obs_pt"], n_cams, n_pts, P["cam_const"], 1e-4)
+    U, gc, V, gp, W = bo.build_normal_equations(r, J[:, :, :9], P["obs_cam"], P["obs_pt"], n_cams, n_pts, P["cam_const"])
+    S, rhs_c, _, _ = bo.schur_reduce(U, gc, V, gp, W, P["obs_cam"], P["obs_pt"], P["cam_const"], 1e-4)
+    n6 = S.shape[0]
+    np.testing.assert_allclose(R[:n6, :n6], S, rtol=1e-9, atol=1e-9 * np.abs(S).max())
+    np.testing.assert_allclose(rhs[:n6], rhs_c, rtol=1e-9, atol=1e-9 * np.abs(rhs_c).max())
+
+
+def test_lm_focal_recovers_a_perturbed_focal_length():
+    P = bo.make_problem(10, 300, 6, 11, noise_px=0.3)
+    res = bo.lm_solve_focal(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"] * 1.03, P["fy"] * 0.97)
+    assert res["converged"] and res["final_cost"] < 0.05 * res["initial_cost"]
+    base = bo.lm_solve(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"])
+    assert res["final_cost"] <= 1.05 * base["final_cost"]           # the extra block can only fit better than the true focal ...
+    # ... and the gauge (only one camera fixed) lets scale trade against focal length, so the ratio is checked loosely
+    assert abs(res["focal"][0] / res["focal"][1] - P["fx"] / P["fy"]) < 0.02

@@ -168,34 +168,55 @@ def residual_jacobian_jets_focal(cams, pts, obs_uv, obs_cam, obs_pt, fx, fy):
 
 
 def reduced_system_focal(r, J11, obs_cam, obs_pt, n_cams, n_pts, cam_const, inv_radius):
-    """Dense statement of what Ceres' SchurEliminator does with the focal block among the f-blocks: full damped normal
-    equations over [free cameras (6 each) | focal (2) | points (3 each)], points eliminated.  Returns the reduced matrix
-    R [(6F+2),(6F+2)] = [[S, B], [B^T, F]], its right-hand side [6F+2] (R d = rhs), the gradient [6F+2], the damped point
-    blocks' inverse and the bookkeeping needed for back-substitution.  Small problems only."""
+    """What Ceres' SchurEliminator does with the focal block among the f-blocks: damped normal equations over
+    [free cameras (6 each) | focal (2) | points (3 each)], points eliminated.  Returns the reduced matrix
+    R [(6F+2),(6F+2)] = [[S, B], [B^T, F]], its right-hand side [6F+2] (R d = rhs), the gradient [6F+2] and the pieces
+    back-substitution needs (Hcp [6F+2, P, 3], damped V^-1 [P,3,3], g_p [P,3], free map, F).  Block algebra in numpy."""
     cam_const = np.asarray(cam_const, bool)
     free_idx = np.nonzero(~cam_const)[0]
     fmap = -np.ones(n_cams, np.int64)
     fmap[free_idx] = np.arange(len(free_idx))
     F = len(free_idx)
     nc = 6 * F + 2
-    n = nc + 3 * n_pts
-    Jfull = np.zeros((2 * len(obs_cam), n))
+    f_o = fmap[obs_cam]
+    free = f_o >= 0
+    Jc = np.where(free[:, None, None], J11[:, :, :6], 0.0)
+    Jp = J11[:, :, 6:9]
+    Jf = J11[:, :, 9:11]
+    Hcc = np.zeros((nc, nc))
+    g = np.zeros(nc)
+    # camera diagonal blocks, camera-focal blocks, focal block
+    Ucc = np.einsum("nki,nkj->nij", Jc, Jc)
+    Ucf = np.einsum("nki,nkj->nij", Jc, Jf)
+    for o in np.nonzero(free)[0]:
+        k = 6 * f_o[o]
+        Hcc[k:k + 6, k:k + 6] += Ucc[o]
+        Hcc[k:k + 6, 6 * F:] += Ucf[o]
+        Hcc[6 * F:, k:k + 6] += Ucf[o].T
+        g[k:k + 6] += Jc[o].T @ r[o]
+    Hcc[6 * F:, 6 * F:] = np.einsum("nki,nkj->ij", Jf, Jf)
+    g[6 * F:] = np.einsum("nki,nk->i", Jf, r)
+    # camera/focal x point blocks and the point blocks
+    Hcp = np.zeros((nc, n_pts, 3))
+    Wc = np.einsum("nki,nkj->nij", Jc, Jp)
+    Wf = np.einsum("nki,nkj->nij", Jf, Jp)
     for o in range(len(obs_cam)):
-        f = fmap[obs_cam[o]]
-        rows = slice(2 * o, 2 * o + 2)
-        if f >= 0:
-            Jfull[rows, 6 * f:6 * f + 6] = J11[o, :, :6]
-        Jfull[rows, 6 * F:6 * F + 2] = J11[o, :, 9:11]
-        Jfull[rows, nc + 3 * obs_pt[o]:nc + 3 * obs_pt[o] + 3] = J11[o, :, 6:9]
-    H = Jfull.T @ Jfull
-    g = Jfull.T @ r.reshape(-1)
-    d = np.arange(n)
-    H[d, d] += np.maximum(H[d, d], 1e-6) * inv_radius            # Ceres min_lm_diagonal on every parameter
-    Hcc, Hcp, Hpp = H[:nc, :nc], H[:nc, nc:], H[nc:, nc:]
-    Hpp_inv = np.linalg.inv(Hpp)                                  # block diagonal (3x3 per point)
-    R = Hcc - Hcp @ Hpp_inv @ Hcp.T
-    rhs = -(g[:nc] - Hcp @ Hpp_inv @ g[nc:])
-    return R, rhs, g[:nc], (Hcp, Hpp_inv, g[nc:], fmap, F)
+        if free[o]:
+            Hcp[6 * f_o[o]:6 * f_o[o] + 6, obs_pt[o]] += Wc[o]
+        Hcp[6 * F:, obs_pt[o]] += Wf[o]
+    V = np.zeros((n_pts, 3, 3))
+    gp = np.zeros((n_pts, 3))
+    np.add.at(V, obs_pt, np.einsum("nki,nkj->nij", Jp, Jp))
+    np.add.at(gp, obs_pt, np.einsum("nki,nk->ni", Jp, r))
+    d = np.arange(nc)
+    Hcc[d, d] += np.maximum(Hcc[d, d], 1e-6) * inv_radius        # Ceres min_lm_diagonal on every parameter
+    d3 = np.arange(3)
+    V[:, d3, d3] += np.maximum(V[:, d3, d3], 1e-6) * inv_radius
+    Vinv = np.linalg.inv(V)
+    T = np.einsum("cpi,pij->cpj", Hcp, Vinv)
+    R = Hcc - np.einsum("cpj,dpj->cd", T, Hcp)
+    rhs = -(g - np.einsum("cpj,pj->c", T, gp))
+    return R, rhs, g, (Hcp, Vinv, gp, fmap, F)
 
 
 def lm_solve_focal(cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, max_iters=100, function_tol=1e-6,
@@ -212,7 +233,7 @@ def lm_solve_focal(cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, max_it
     initial, costs, converged, it = cost, [cost], False, 0
     while it < max_iters:
         it += 1
-        R, rhs, gcf, (Hcp, Hpp_inv, gp, fmap, F) = reduced_system_focal(r, J, obs_cam, obs_pt, n_cams, n_pts, cam_const, 1.0 / radius)
+        R, rhs, gcf, (Hcp, Vinv, gp, fmap, F) = reduced_system_focal(r, J, obs_cam, obs_pt, n_cams, n_pts, cam_const, 1.0 / radius)
         gmax = max(np.abs(gcf).max(), np.abs(gp).max())
         if gmax <= gradient_tol:
             converged = True
@@ -223,7 +244,7 @@ def lm_solve_focal(cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, max_it
             radius /= decrease
             decrease *= 2
             continue
-        dp = (-Hpp_inv @ (gp + Hcp.T @ dcf)).reshape(-1, 3)
+        dp = -np.einsum("pij,pj->pi", Vinv, gp + np.einsum("cpi,c->pi", Hcp, dcf))
         dc = np.zeros((n_cams, 6))
         dc[fmap >= 0] = dcf[:6 * F].reshape(-1, 6)
         df = dcf[6 * F:]

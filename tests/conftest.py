@@ -1,6 +1,11 @@
 import os
 import sys
 
+# the GPU box's container may run under a CPU quota smaller than its core count: BLAS pools sized by the core count then
+# thrash (a dense oracle solve took minutes there).  Small pools, set before numpy loads its BLAS.
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, "4")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

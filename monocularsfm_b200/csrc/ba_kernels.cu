@@ -221,7 +221,10 @@ __device__ __forceinline__ void load_lane(const Problem& P, int obs, bool valid,
 }
 
 // per-point normal-equation pieces: V (damped), V^-1, g_p — reduced over the whole track
-// wf (nullable): Wf = sum Jf^T Jp (2x3);  fstat (nullable): sum xp^2, sum yp^2, sum xp r0, sum yp r1 over the track
+// kFocal: also wf = Wf = sum Jf^T Jp (2x3) and fstat = sum xp^2, sum yp^2, sum xp r0, sum yp r1 over the track.
+// A template parameter, not a run-time flag: the extra accumulators cost the constant-focal kernel 70 registers
+// (118 -> 188, one CTA per SM instead of two) when they were merely branched around.
+template <bool kFocal = false>
 __device__ __forceinline__ void point_pass1(const Problem& P, int p, int beg, int end, int lane, const double X[3],
                                             double inv_radius, double Vinv[6], double gp[3], LaneObs& first,
                                             double* wf = nullptr, double* fstat = nullptr) {
@@ -235,20 +238,18 @@ __device__ __forceinline__ void point_pass1(const Problem& P, int p, int beg, in
         v[0] += j0 * j0 + j3 * j3; v[1] += j0 * j1 + j3 * j4; v[2] += j0 * j2 + j3 * j5;
         v[3] += j1 * j1 + j4 * j4; v[4] += j1 * j2 + j4 * j5; v[5] += j2 * j2 + j5 * j5;
         g[0] += j0 * o.r[0] + j3 * o.r[1]; g[1] += j1 * o.r[0] + j4 * o.r[1]; g[2] += j2 * o.r[0] + j5 * o.r[1];
-        if (wf) {
+        if (kFocal) {
             w6[0] += o.xy[0] * j0; w6[1] += o.xy[0] * j1; w6[2] += o.xy[0] * j2;
             w6[3] += o.xy[1] * j3; w6[4] += o.xy[1] * j4; w6[5] += o.xy[1] * j5;
         }
-        if (fstat) {
+        if (kFocal) {
             f4[0] += o.xy[0] * o.xy[0]; f4[1] += o.xy[1] * o.xy[1];
             f4[2] += o.xy[0] * o.r[0];  f4[3] += o.xy[1] * o.r[1];
         }
     }
-    if (wf) {
+    if (kFocal) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) wf[k] = warp_sum(w6[k]);
-    }
-    if (fstat) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) fstat[k] = warp_sum(f4[k]);
     }
@@ -268,6 +269,7 @@ __device__ __forceinline__ void point_pass1(const Problem& P, int p, int beg, in
 
 // Pass P — one warp per point: residuals + Jacobians of its observations (stored), damped V^-1 and g_p (stored),
 // cost and max |g_p|.
+template <bool kFocal>
 __global__ void __launch_bounds__(256)
 point_pass_kernel(Problem P, double inv_radius, double* __restrict__ sys) {
     const int lane = threadIdx.x & 31;
@@ -276,7 +278,7 @@ point_pass_kernel(Problem P, double inv_radius, double* __restrict__ sys) {
     double* scal = sys + n6 * n6 + 3 * n6;
     double cost_local = 0.0, gpmax_local = 0.0;
     double ff[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};        // focal block sums of this warp (lane 0): F00 F01 F11 rhsf0 rhsf1 gf0 gf1 uf0 uf1
-    const bool focal = P.refine_focal != 0;
+    constexpr bool focal = kFocal;
     for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < P.n_pts; p += gridDim.x * wpb) {
         const int beg = P.pt_start[p], end = P.pt_start[p + 1];
         if (beg == end) {
@@ -286,7 +288,7 @@ point_pass_kernel(Problem P, double inv_radius, double* __restrict__ sys) {
         const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
         double Vinv[6], gp[3], Wf[6], fs[4];
         LaneObs A;
-        point_pass1(P, p, beg, end, lane, X, inv_radius, Vinv, gp, A, focal ? Wf : nullptr, focal ? fs : nullptr);
+        point_pass1<kFocal>(P, p, beg, end, lane, X, inv_radius, Vinv, gp, A, Wf, fs);
         if (focal) {
             // T = Wf V^-1 (2x3);  F -= T Wf^T,  rhs_f += T g_p - g_f   (the point is eliminated from the focal block too)
             if (lane < 6) P.pt_Wf[6 * static_cast<size_t>(p) + lane] = Wf[lane];
@@ -718,7 +720,8 @@ cudaError_t ba_launch_linearize(const Problem& P, double inv_radius, double* sys
     if (P.n_pts <= 0) return cudaSuccess;
     int grid = (P.n_pts + 7) / 8;
     if (grid > num_sms * 8) grid = num_sms * 8;
-    point_pass_kernel<<<grid, 256, 0, st>>>(P, inv_radius, sys);
+    if (P.refine_focal) point_pass_kernel<true><<<grid, 256, 0, st>>>(P, inv_radius, sys);
+    else point_pass_kernel<false><<<grid, 256, 0, st>>>(P, inv_radius, sys);
     if (P.n_free > 0) {
         camera_diag_kernel<<<P.n_free, 256, 0, st>>>(P, sys);
         if (P.refine_focal) camera_focal_border_kernel<<<P.n_free, 256, 0, st>>>(P, sys);

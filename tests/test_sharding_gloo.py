@@ -42,12 +42,21 @@ def _worker(rank, world, port, q):
     S, rhs, _, _ = bo.schur_reduce(U, gc, V, gp, W, L["obs_cam"], L["obs_pt"], L["cam_const"], 0.0)
     buf = torch.from_numpy(np.concatenate([S.reshape(-1), rhs, [bo.cost_of(r)]]))
     dist.all_reduce(buf)
+    # ---- BA with the shared focal block (refine_focal_length): the bordered system [[S, B], [B^T, F]] is additive too
+    r11, J11 = bo.residual_jacobian_jets_focal(L["cams"], L["pts"], L["obs_uv"], L["obs_cam"], L["obs_pt"], L["fx"], L["fy"])
+    Rl, rhsl, _, _ = bo.reduced_system_focal(r11, J11, L["obs_cam"], L["obs_pt"], len(L["cams"]), len(L["pts"]), L["cam_const"], 0.0)
+    buf_f = torch.from_numpy(np.concatenate([Rl.reshape(-1), rhsl]))
+    dist.all_reduce(buf_f)
     if rank == 0:
         r, J = bo.residual_jacobian_jets(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
         U, gc, V, gp, W = bo.build_normal_equations(r, J, P["obs_cam"], P["obs_pt"], len(P["cams"]), len(P["pts"]), P["cam_const"])
         S, rhs, _, _ = bo.schur_reduce(U, gc, V, gp, W, P["obs_cam"], P["obs_pt"], P["cam_const"], 0.0)
         full = np.concatenate([S.reshape(-1), rhs, [bo.cost_of(r)]])
-        q.put((ok_pairs, float(np.abs(buf.numpy() - full).max() / np.abs(full).max())))
+        r11, J11 = bo.residual_jacobian_jets_focal(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
+        Rf, rhsf, _, _ = bo.reduced_system_focal(r11, J11, P["obs_cam"], P["obs_pt"], len(P["cams"]), len(P["pts"]), P["cam_const"], 0.0)
+        full_f = np.concatenate([Rf.reshape(-1), rhsf])
+        q.put((ok_pairs, float(np.abs(buf.numpy() - full).max() / np.abs(full).max()),
+               float(np.abs(buf_f.numpy() - full_f).max() / np.abs(full_f).max())))
     dist.destroy_process_group()
 
 
@@ -58,9 +67,10 @@ def test_two_rank_sharding_over_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    ok_pairs, err = q.get(timeout=120)
+    ok_pairs, err, err_focal = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok_pairs
     assert err < 1e-12
+    assert err_focal < 1e-12

@@ -38,6 +38,32 @@ def sift_like(rng, n):
     return np.clip(np.rint(x), 0, 255).astype(np.uint8)
 
 
+def real_sift_pair(seed=5):
+    """Two synthetic textured views (random blobs + noise; the second one an affine warp of the first with fresh noise)
+    through cv2.SIFT — the detector/descriptor FeatureUtils::ExtractFeature uses (src/Feature/FeatureUtils.cpp:14-36).
+    Real SIFT output is integer-valued float32 in [0, 255]; stored as uint8 (lossless)."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    img = np.zeros((480, 640), np.float32)
+    for _ in range(400):
+        c = (int(rng.integers(0, 640)), int(rng.integers(0, 480)))
+        cv2.circle(img, c, int(rng.integers(3, 25)), float(rng.uniform(40, 255)), -1)
+        p1 = (int(rng.integers(0, 640)), int(rng.integers(0, 480)))
+        p2 = (int(rng.integers(0, 640)), int(rng.integers(0, 480)))
+        cv2.line(img, p1, p2, float(rng.uniform(0, 255)), int(rng.integers(1, 4)))
+    img = cv2.GaussianBlur(img, (0, 0), 1.2)
+    a_img = np.clip(img + rng.normal(0, 3, img.shape), 0, 255).astype(np.uint8)
+    M = cv2.getRotationMatrix2D((320, 240), 7.0, 1.08)
+    M[:, 2] += (9.0, -6.0)
+    b_img = cv2.warpAffine(img, M, (640, 480), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT)
+    b_img = np.clip(b_img + rng.normal(0, 3, img.shape), 0, 255).astype(np.uint8)
+    sift = cv2.SIFT_create()
+    _, da = sift.detectAndCompute(a_img, None)
+    _, db = sift.detectAndCompute(b_img, None)
+    assert da is not None and db is not None and (da == np.floor(da)).all() and da.max() <= 255 and da.min() >= 0
+    return da.astype(np.uint8), db.astype(np.uint8)
+
+
 def cases():
     rng = np.random.default_rng(0)
     out = {}
@@ -92,6 +118,8 @@ def cases():
     # extremes 0 / 255 (max d2 = 8 323 200)
     a = np.zeros((8, 128), np.uint8); b = np.full((9, 128), 255, np.uint8); b[4, :64] = 0
     out["extremes"] = (a, b)
+    # real SIFT descriptors of two views of a synthetic scene (true correspondences, repeated structure, many zeros)
+    out["real_sift"] = real_sift_pair()
     return out
 
 

@@ -8,7 +8,7 @@ from oracle import match_oracle as mo
 pytestmark = pytest.mark.gpu
 
 CASES = ["cfg1", "ragged", "sift_planted", "ties", "sqrt_collapse", "quirk_q0", "n2_is_1", "n2_is_2", "n1_is_1",
-         "preempt100", "all_equal", "extremes"]
+         "preempt100", "all_equal", "extremes", "real_sift"]
 
 
 def _check_knn(idx, dist, d2, gi, gd, mode):

@@ -6,7 +6,7 @@ import pytest
 from oracle import match_oracle as mo
 
 CASES = ["cfg1", "ragged", "sift_planted", "ties", "sqrt_collapse", "quirk_q0", "n2_is_1", "n2_is_2", "n1_is_1",
-         "preempt100", "all_equal", "extremes"]
+         "preempt100", "all_equal", "extremes", "real_sift"]
 
 
 @pytest.mark.parametrize("name", CASES)

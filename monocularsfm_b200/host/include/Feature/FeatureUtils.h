@@ -1,7 +1,7 @@
 // MonocularSfM::FeatureUtils — the three matching functions of the reference, same names / arguments / behaviour
 // (reference: include/Feature/FeatureUtils.h:94-108, src/Feature/FeatureUtils.cpp:141-174,208-218,281-310),
 // computed on the B200 through the C-ABI (include/msfm_b200.h).  Functions of the reference class that are not on
-// the hot path (SIFT extraction, F-matrix RANSAC, drawing) are intentionally absent.
+// the hot path (SIFT extraction, drawing) are intentionally absent.
 #ifndef MSFM_HOST_FEATURE_UTILS_H_
 #define MSFM_HOST_FEATURE_UTILS_H_
 #include <vector>
@@ -23,6 +23,18 @@ public:
                            std::vector<cv::DMatch>& prune_matches);
     static void FilterMatchesByDistance(const std::vector<cv::DMatch>& matches, std::vector<cv::DMatch>& prune_matches,
                                         const double& max_distance = 0.7);
+    // Geometric verification (FeatureUtils.cpp:176-206, 220-233): keeps the matches that are inliers of a fundamental
+    // matrix found by RANSAC (threshold 3 px, confidence 0.99).  The reference delegates to cv::findFundamentalMat; this is a
+    // from-scratch estimator with the same error measure and stopping rule, not bit-compatible with OpenCV's sampler
+    // (host/src/GeometricVerification.cpp).  Install with FeatureMatcher::SetGeometricFilter(FeatureUtils::FilterMatches).
+    static void FilterMatches(const std::vector<cv::Point2f>& pts1, const std::vector<cv::Point2f>& pts2,
+                              const std::vector<cv::DMatch>& matches, std::vector<cv::DMatch>& prune_matches);
+    static void GetAlignedPointsFromMatches(const std::vector<cv::Point2f>& pts1, const std::vector<cv::Point2f>& pts2,
+                                            const std::vector<cv::DMatch>& matches, std::vector<cv::Point2f>& aligned_pts1,
+                                            std::vector<cv::Point2f>& aligned_pts2);
+    // inlier mask of aligned correspondences; false (mask all zero) when no model with >= 8 inliers exists
+    static bool FundamentalInliersRANSAC(const std::vector<cv::Point2f>& pts1, const std::vector<cv::Point2f>& pts2, double threshold,
+                                         double confidence, std::vector<unsigned char>& mask);
     // Top-scale descriptor selection used by preemptive matching (FeatureUtils.cpp:68-96).
     static void ExtractTopScaleDescriptors(const std::vector<cv::KeyPoint> kpts, const cv::Mat& descriptors,
                                            const int& num_features, cv::Mat& top_scale_descriptors);

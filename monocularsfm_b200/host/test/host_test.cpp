@@ -4,6 +4,7 @@
 //   host_test seq <db>                 SequentialFeatureMatcher(db).RunMatching()
 //   host_test two <a.u8> <na> <b.u8> <nb> <out.txt>   FeatureUtils::ComputeMatches / ComputeCrossMatches on raw files
 //   host_test ba <in.bin> <out.bin>    CeresBundelOptimizer::Optimize on a BundleData read from a flat binary file
+//   host_test ransac <in.bin> <out.bin>  FeatureUtils::FilterMatches on float32 point pairs (no GPU)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -171,6 +172,33 @@ static int run_ba(char** argv) {
     return 0;
 }
 
+// in: int32 n | float32 [n][2] pts1 | float32 [n][2] pts2 ; matches are (i, i).  out: uint8 [n] kept-mask
+static int run_ransac(char** argv) {
+    std::ifstream in(argv[2], std::ios::binary);
+    int32_t n = 0;
+    in.read(reinterpret_cast<char*>(&n), 4);
+    std::vector<float> a(2 * n), b(2 * n);
+    in.read(reinterpret_cast<char*>(a.data()), a.size() * 4);
+    in.read(reinterpret_cast<char*>(b.data()), b.size() * 4);
+    std::vector<cv::Point2f> p1(n), p2(n);
+    std::vector<cv::DMatch> matches;
+    for (int i = 0; i < n; ++i) {
+        p1[i] = cv::Point2f(a[2 * i], a[2 * i + 1]);
+        p2[n - 1 - i] = cv::Point2f(b[2 * i], b[2 * i + 1]);      // train points stored reversed: exercises the index alignment
+        matches.push_back(cv::DMatch(i, n - 1 - i, 0, 1.f));
+    }
+    std::vector<cv::DMatch> kept;
+    FeatureUtils::FilterMatches(p1, p2, matches, kept);
+    std::vector<unsigned char> mask(n, 0);
+    for (const cv::DMatch& m : kept) {
+        if (m.trainIdx != n - 1 - m.queryIdx) return 4;
+        mask[m.queryIdx] = 1;
+    }
+    std::ofstream out(argv[3], std::ios::binary);
+    out.write(reinterpret_cast<const char*>(mask.data()), mask.size());
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
     const std::string mode = argv[1];
@@ -187,5 +215,6 @@ int main(int argc, char** argv) {
     }
     if (mode == "two" && argc >= 7) return run_two(argv);
     if (mode == "ba" && argc >= 4) return run_ba(argv);
+    if (mode == "ransac" && argc >= 4) return run_ransac(argv);
     return 2;
 }

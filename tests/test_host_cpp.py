@@ -206,3 +206,65 @@ def test_ceres_bundel_optimizer_dropin(tmp_path):
     nrm = np.linalg.norm(r, axis=1)
     per_pt = np.bincount(op, nrm) / np.bincount(op)
     assert abs(per_pt.mean() - after) < 1e-9
+
+
+def _two_view_scene(seed, n_in, n_out, noise_px):
+    """3-D points seen by two cameras (NEU intrinsics), `n_out` mismatched pairs appended; float32 pixel coordinates."""
+    rng = np.random.default_rng(seed)
+    fx = fy = 1449.2752980237
+    cx, cy = 1080.0, 720.0
+    X = np.c_[rng.uniform(-3, 3, n_in), rng.uniform(-2, 2, n_in), rng.uniform(6, 14, n_in)]
+    rvec = np.array([0.03, -0.12, 0.02])
+    R = bo.rodrigues_matrix(rvec)
+    t = np.array([1.2, 0.1, 0.3])
+    def proj(P):
+        return np.c_[fx * P[:, 0] / P[:, 2] + cx, fy * P[:, 1] / P[:, 2] + cy]
+    p1 = proj(X) + rng.normal(0, noise_px, (n_in, 2))
+    p2 = proj(X @ R.T + t) + rng.normal(0, noise_px, (n_in, 2))
+    o1 = np.c_[rng.uniform(0, 2160, n_out), rng.uniform(0, 1440, n_out)]
+    o2 = np.c_[rng.uniform(0, 2160, n_out), rng.uniform(0, 1440, n_out)]
+    truth = np.r_[np.ones(n_in, bool), np.zeros(n_out, bool)]
+    perm = rng.permutation(n_in + n_out)
+    return np.r_[p1, o1][perm].astype(np.float32), np.r_[p2, o2][perm].astype(np.float32), truth[perm]
+
+
+@pytest.mark.parametrize("seed,n_in,n_out", [(1, 400, 150), (2, 120, 120), (3, 60, 10)])
+def test_filter_matches_geometric_verification(tmp_path, seed, n_in, n_out):
+    """FeatureUtils::FilterMatches (F-matrix RANSAC, threshold 3 px, confidence 0.99; FeatureUtils.cpp:176-206) on a
+    synthetic two-view scene: keeps the true correspondences, drops the mismatches, and agrees with
+    cv2.findFundamentalMat(FM_RANSAC, 3.0, 0.99) — the call the reference makes — on all but a few borderline points."""
+    _need_exe()
+    p1, p2, truth = _two_view_scene(seed, n_in, n_out, 0.5)
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        f.write(struct.pack("i", len(p1)))
+        f.write(p1.tobytes())
+        f.write(p2.tobytes())
+    out = subprocess.run([EXE, "ransac", str(fin), str(fout)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr + out.stdout
+    mask = np.fromfile(fout, np.uint8).astype(bool)
+    assert len(mask) == len(truth)
+    recall = (mask & truth).sum() / truth.sum()
+    false_pos = (mask & ~truth).sum()
+    assert recall >= 0.97, recall
+    # a random mismatch survives only if it happens to lie within 3 px of its epipolar lines (~0.5 % here)
+    assert false_pos <= max(2, 0.03 * n_out), false_pos
+    cv2 = pytest.importorskip("cv2")
+    _, cvmask = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 3.0, 0.99)
+    cvmask = cvmask.ravel().astype(bool)
+    assert (cvmask != mask).sum() <= 0.03 * len(mask), int((cvmask != mask).sum())
+
+
+def test_filter_matches_degenerate_inputs(tmp_path):
+    """Fewer than 8 correspondences: nothing survives (OpenCV returns an empty mask below 7; the reference then keeps no
+    match)."""
+    _need_exe()
+    p1, p2, _ = _two_view_scene(5, 6, 0, 0.2)
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        f.write(struct.pack("i", len(p1)))
+        f.write(p1.tobytes())
+        f.write(p2.tobytes())
+    out = subprocess.run([EXE, "ransac", str(fin), str(fout)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0
+    assert not np.fromfile(fout, np.uint8).any()

@@ -5,6 +5,9 @@
 //   host_test two <a.u8> <na> <b.u8> <nb> <out.txt>   FeatureUtils::ComputeMatches / ComputeCrossMatches on raw files
 //   host_test ba <in.bin> <out.bin>    CeresBundelOptimizer::Optimize on a BundleData read from a flat binary file
 //   host_test ransac <in.bin> <out.bin>  FeatureUtils::FilterMatches on float32 point pairs (no GPU)
+//   host_test scenegraph <script.txt> <out.txt>  SceneGraph driven by a script of I / M / F / Q lines (no GPU)
+//   host_test scenegraph_db <db> <min_matches> <out.txt>  SceneGraph::Load on a database + the same dump (no GPU)
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +20,7 @@
 #include "Feature/FeatureMatching.h"
 #include "Feature/FeatureUtils.h"
 #include "Optimizer/CeresBundleOptimizer.h"
+#include "Reconstruction/SceneGraph.h"
 
 using namespace MonocularSfM;
 
@@ -199,6 +203,63 @@ static int run_ransac(char** argv) {
     return 0;
 }
 
+// full, order-independent dump of a scene graph: per image (ascending id) its counters and every point's list
+static void dump_scene_graph(SceneGraph& g, std::ostream& out) {
+    std::vector<image_t> ids = g.GetAllImageIds();
+    std::sort(ids.begin(), ids.end());
+    out << "images " << g.NumImages() << "\n";
+    for (image_t id : ids) {
+        out << "image " << id << " obs " << g.NumObservationsForImage(id) << " corrs " << g.NumCorrespondencesForImage(id) << "\n";
+    }
+    std::vector<std::pair<image_pair_t, point2D_t>> pairs;
+    for (const auto& kv : g.ImagePairs()) pairs.push_back(kv);
+    std::sort(pairs.begin(), pairs.end());
+    for (const auto& kv : pairs) out << "pair " << kv.first << " " << kv.second << "\n";
+}
+
+static int run_scenegraph(char** argv) {
+    std::ifstream in(argv[2]);
+    std::ofstream out(argv[3]);
+    SceneGraph g;
+    std::string op;
+    while (in >> op) {
+        if (op == "I") { int id, n; in >> id >> n; g.AddImage(id, n); }
+        else if (op == "M") {
+            int a, b, k; in >> a >> b >> k;
+            std::vector<cv::DMatch> m;
+            for (int i = 0; i < k; ++i) { int q, t; in >> q >> t; m.push_back(cv::DMatch(q, t, 0, 0.f)); }
+            g.AddCorrespondences(a, b, m);
+        }
+        else if (op == "F") { g.Finalize(); }
+        else if (op == "D") { dump_scene_graph(g, out); }
+        else if (op == "Q") {          // Q image point: correspondences, has, two-view
+            int id, p; in >> id >> p;
+            out << "q " << id << " " << p << " has " << (g.HasCorrespondences(id, p) ? 1 : 0) << " two " << (g.IsTwoViewObservation(id, p) ? 1 : 0) << " :";
+            for (const SceneGraph::Correspondence& c : g.FindCorrespondences(id, p)) out << " " << c.image_id << "," << c.point2D_idx;
+            out << "\n";
+        }
+        else if (op == "B") {          // B id1 id2: matches between two images + the pair counter
+            int a, b; in >> a >> b;
+            out << "b " << a << " " << b << " n " << g.NumCorrespondencesBetweenImages(a, b) << " :";
+            for (const cv::DMatch& m : g.FindCorrespondencesBetweenImages(a, b)) out << " " << m.queryIdx << "," << m.trainIdx;
+            out << "\n";
+        }
+        else return 5;
+    }
+    return 0;
+}
+
+static int run_scenegraph_db(char** argv) {
+    cv::Ptr<Database> db(new Database());
+    db->Open(argv[2]);
+    SceneGraph g;
+    g.Load(db, static_cast<size_t>(std::atoi(argv[3])));
+    std::ofstream out(argv[4]);
+    dump_scene_graph(g, out);
+    db->Close();
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
     const std::string mode = argv[1];
@@ -216,5 +277,7 @@ int main(int argc, char** argv) {
     if (mode == "two" && argc >= 7) return run_two(argv);
     if (mode == "ba" && argc >= 4) return run_ba(argv);
     if (mode == "ransac" && argc >= 4) return run_ransac(argv);
+    if (mode == "scenegraph" && argc >= 4) return run_scenegraph(argv);
+    if (mode == "scenegraph_db" && argc >= 5) return run_scenegraph_db(argv);
     return 2;
 }

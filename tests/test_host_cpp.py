@@ -268,3 +268,130 @@ def test_filter_matches_degenerate_inputs(tmp_path):
     out = subprocess.run([EXE, "ransac", str(fin), str(fout)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0
     assert not np.fromfile(fout, np.uint8).any()
+
+
+class _SceneGraphModel:
+    """Plain restatement of the reference's SceneGraph (src/Reconstruction/SceneGraph.cpp): per image a list of
+    correspondence lists; AddCorrespondences :170-251 (self-matches ignored, invalid / duplicate matches dropped and taken
+    back out of the counters), Finalize :88-117, IsTwoViewObservation :285-298."""
+
+    def __init__(self):
+        self.corrs, self.ncorr, self.nobs, self.pairs = {}, {}, {}, {}
+
+    def add_image(self, i, n):
+        self.corrs[i] = [[] for _ in range(n)]
+        self.ncorr[i] = 0
+        self.nobs[i] = 0
+
+    def add(self, a, b, matches):
+        if a == b:
+            return
+        pid = 10000 * min(a, b) + max(a, b)                       # Database::ImagePairToPairId (Database.cpp:6)
+        self.pairs.setdefault(pid, 0)
+        for q, t in matches:
+            if not (0 <= q < len(self.corrs[a]) and 0 <= t < len(self.corrs[b])):
+                continue
+            if (b, t) in self.corrs[a][q]:
+                continue
+            self.corrs[a][q].append((b, t))
+            self.corrs[b][t].append((a, q))
+            self.ncorr[a] += 1
+            self.ncorr[b] += 1
+            self.pairs[pid] += 1
+
+    def finalize(self):
+        for i in list(self.corrs):
+            self.nobs[i] = sum(1 for c in self.corrs[i] if c)
+            if self.nobs[i] == 0:
+                del self.corrs[i]
+
+    def dump(self):
+        out = [f"images {len(self.corrs)}"]
+        for i in sorted(self.corrs):
+            out.append(f"image {i} obs {self.nobs[i]} corrs {self.ncorr[i]}")
+        for p in sorted(self.pairs):
+            out.append(f"pair {p} {self.pairs[p]}")
+        return out
+
+    def q(self, i, p):
+        c = self.corrs[i][p]
+        two = len(c) == 1 and len(self.corrs[c[0][0]][c[0][1]]) == 1
+        return f"q {i} {p} has {1 if c else 0} two {1 if two else 0} :" + "".join(f" {a},{b}" for a, b in c)
+
+    def b(self, a, b):
+        pid = 10000 * min(a, b) + max(a, b)
+        found = [(p, t) for p, cl in enumerate(self.corrs[a]) for (o, t) in cl if o == b]
+        return f"b {a} {b} n {self.pairs.get(pid, 0)} :" + "".join(f" {x},{y}" for x, y in found)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_scene_graph_against_reference_semantics(tmp_path, seed):
+    """SceneGraph (consumer of the matches the M-path writes; CSR storage instead of the reference's nested vectors) driven
+    by a random script with duplicates, out-of-range indices, self-matches, repeated pairs, interleaved queries and a
+    Finalize: every observable equals the restated reference semantics."""
+    _need_exe()
+    rng = np.random.default_rng(seed)
+    n_img = 7
+    npts = {i + 1: int(rng.integers(0, 9)) for i in range(n_img)}
+    npts[n_img] = 0                                               # an image without key points
+    model = _SceneGraphModel()
+    script, expect = [], []
+    for i, n in npts.items():
+        script.append(f"I {i} {n}")
+        model.add_image(i, n)
+
+    def queries():
+        for i, n in npts.items():
+            if i not in model.corrs:
+                continue
+            for p in range(n):
+                script.append(f"Q {i} {p}")
+                expect.append(model.q(i, p))
+        for a in model.corrs:
+            for b in model.corrs:
+                if a != b:
+                    script.append(f"B {a} {b}")
+                    expect.append(model.b(a, b))
+        script.append("D")
+        expect.extend(model.dump())
+
+    for rnd in range(3):
+        for _ in range(8):
+            a, b = (int(x) for x in rng.integers(1, n_img + 1, 2))
+            k = int(rng.integers(0, 7))
+            m = [(int(rng.integers(-1, npts[a] + 2)), int(rng.integers(-1, npts[b] + 2))) for _ in range(k)]
+            if k and rng.random() < 0.5:
+                m.append(m[0])                                    # a duplicate inside one call
+            script.append(f"M {a} {b} {len(m)} " + " ".join(f"{q} {t}" for q, t in m))
+            model.add(a, b, m)
+        queries()
+    script.append("F")
+    model.finalize()
+    queries()
+    fin, fout = tmp_path / "s.txt", tmp_path / "o.txt"
+    fin.write_text("\n".join(script) + "\n")
+    out = subprocess.run([EXE, "scenegraph", str(fin), str(fout)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = fout.read_text().splitlines()
+    assert got == expect
+
+
+def test_scene_graph_load_from_database(tmp_path):
+    """SceneGraph::Load (:11-85) on a database in the reference's schema: every image is a node, pairs below min_num_matches
+    are ignored, blobs stored with swapped columns (image_id1 > image_id2, Database.cpp:637-640) come back the right way round."""
+    _need_exe()
+    db = str(tmp_path / "g.db")
+    subprocess.run([EXE, "cpu", db], capture_output=True, text=True, timeout=60, check=True)     # creates 2 images, 3 key points on image 1
+    con = sqlite3.connect(db)
+    con.execute("DELETE FROM matches")
+    con.execute("INSERT INTO keypoints(image_id, rows, cols, data) VALUES (2, 4, 4, ?)", (np.zeros((4, 4), np.float32).tobytes(),))
+    m = np.array([[0, 3], [2, 1], [2, 1], [1, 9]], np.int32)     # (point in image 1, point in image 2): one duplicate, one invalid
+    con.execute("INSERT INTO matches(pair_id, rows, cols, data) VALUES (?, ?, 2, ?)", (10000 * 1 + 2, len(m), m.tobytes()))
+    con.commit()
+    con.close()
+    fout = tmp_path / "o.txt"
+    out = subprocess.run([EXE, "scenegraph_db", db, "3", str(fout)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert fout.read_text().splitlines() == ["images 2", "image 1 obs 0 corrs 2", "image 2 obs 0 corrs 2", "pair 10002 2"]
+    out = subprocess.run([EXE, "scenegraph_db", db, "5", str(fout)], capture_output=True, text=True, timeout=60)
+    assert fout.read_text().splitlines() == ["images 2", "image 1 obs 0 corrs 0", "image 2 obs 0 corrs 0"]

@@ -205,6 +205,18 @@ __device__ __forceinline__ void mma_i8_ss_pair(uint32_t d_tmem, uint64_t a_desc,
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// pair form with the A operand resident in tensor memory (each CTA holds its own 128 rows; 4 K-bytes per 32-bit column)
+__device__ __forceinline__ void mma_i8_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // one arrival on the mbarrier at this shared-memory offset in every CTA of cta_mask, once all earlier pair-MMAs
 // of this thread have completed
 __device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t cta_mask) {

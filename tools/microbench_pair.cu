@@ -20,10 +20,12 @@ using namespace msfm;
 
 constexpr int ND = 8;     // ring of done barriers
 
-template <int N, int ISSUERS, int EPI, int DESC = 0, int UNI = 0>
+template <int N, int ISSUERS, int EPI, int DESC = 0, int UNI = 0, int TS = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 k_pair(int iters, long long* cyc, long long* stamps, int* sink) {
-    constexpr int STAGES = 512 / N;
+    // TS: the A operand (128 rows x 160 K-bytes = 40 columns, padded to 48) lives in tensor memory behind the accumulators
+    constexpr int STAGES = TS ? (512 - 48) / N : 512 / N;
+    constexpr uint32_t A_TMEM_COL = STAGES * N;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint32_t tptr;
     __shared__ uint64_t done[ND], t_empty[STAGES], fin;
@@ -64,7 +66,10 @@ k_pair(int iters, long long* cyc, long long* stamps, int* sink) {
                 const uint64_t bdx = ptx::make_smem_desc_sw128(sbase + (DESC ? 32768 + s6 * 16384 : 16384));
                 if (ptx::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) ptx::mma_i8_ss_pair(tb + st * N, adx + 2 * (k & 3), bdx + 2 * (k & 3), idesc, k > 0);
+                    for (int k = 0; k < 5; ++k) {
+                        if (TS) ptx::mma_i8_ts_pair(tb + st * N, tb + A_TMEM_COL + 8 * k, bdx + 2 * (k & 3), idesc, k > 0);
+                        else ptx::mma_i8_ss_pair(tb + st * N, adx + 2 * (k & 3), bdx + 2 * (k & 3), idesc, k > 0);
+                    }
                     if (EPI >= 1) ptx::mma_commit_pair(&done[dn], 0b11);
                 }
                 __syncwarp();
@@ -222,9 +227,9 @@ k_pair(int iters, long long* cyc, long long* stamps, int* sink) {
     if (warp == 2) ptx::tmem_dealloc_pair<512>(tmem_base);
 }
 
-template <int N, int ISSUERS, int EPI, int DESC = 0, int UNI = 0>
+template <int N, int ISSUERS, int EPI, int DESC = 0, int UNI = 0, int TS = 0>
 static int run(int G, long long* d_cyc, long long* d_stamps, int* d_sink, const char* name, bool print_stamps) {
-    auto k = k_pair<N, ISSUERS, EPI, DESC, UNI>;
+    auto k = k_pair<N, ISSUERS, EPI, DESC, UNI, TS>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 140000) != cudaSuccess) return 1;
     const int iters = 4096;
     cudaMemset(d_stamps, 0, (32 * 12 + 64) * 8);
@@ -283,6 +288,12 @@ int main() {
     run<128, 1, 3, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=128 1 issuer, 4 stages, epilogue reads TMEM", false);
     run<128, 1, 4, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=128 1 issuer, 4 stages, epilogue reads + max", false);
     run<128, 2, 4, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM N=128 2 issuers, 4 stages, epilogue reads + max", false);
+    // round-2 candidates: query operand in tensor memory, which frees 20 KB of shared-memory reads per
+    // tile and, with 192-column tiles, leaves room for the A operand next to two accumulator stages (or three of 128)
+    run<256, 1, 1, 1, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM TS N=256 1 issuer, free-running (1 stage + A)", false);
+    run<192, 1, 1, 1, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM TS N=192 1 issuer, free-running", false);
+    run<192, 1, 5, 1, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM TS N=192 1 issuer, 2 stages, REAL epilogue arithmetic", true);
+    run<128, 1, 3, 1, 1, 1>(G, d_cyc, d_stamps, d_sink, "UNIFORM TS N=128 1 issuer, 3 stages, epilogue reads TMEM", false);
     run<128, 1, 0>(G, d_cyc, d_stamps, d_sink, "N=128 1 issuer, free-running", false);
     run<128, 1, 2>(G, d_cyc, d_stamps, d_sink, "N=128 1 issuer, 4 stages, empty epilogue", false);
     run<128, 1, 3>(G, d_cyc, d_stamps, d_sink, "N=128 1 issuer, 4 stages, epilogue reads TMEM", true);

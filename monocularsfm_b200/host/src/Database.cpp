@@ -70,6 +70,28 @@ const size_t kMaxNumImages = 10000;   // Database.cpp:6 — pair ids are 10000 *
 
 struct Database::Impl {
     sqlite3* db = nullptr;
+    // number of rows of the blob stored under `key` (0 when absent)
+    size_t blob_rows(const char* sql, sqlite3_int64 key) const {
+        sqlite3_stmt* st = prepare(sql);
+        check(api().bind_int64(st, 1, key), __LINE__);
+        size_t n = 0;
+        if (check(api().step(st), __LINE__) == kRow) n = static_cast<size_t>(api().column_int64(st, 0));
+        api().finalize(st);
+        return n;
+    }
+    Database::Image image_row(const char* sql, const image_t* id, const std::string* name) const {
+        sqlite3_stmt* st = prepare(sql);
+        if (id) check(api().bind_int64(st, 1, *id), __LINE__);
+        else check(api().bind_text(st, 1, name->c_str(), static_cast<int>(name->size()), SQLITE_TRANSIENT_), __LINE__);
+        Database::Image im;
+        im.id = INVALID;
+        if (check(api().step(st), __LINE__) == kRow) {
+            im.id = static_cast<image_t>(api().column_int64(st, 0));
+            im.name = reinterpret_cast<const char*>(api().column_text(st, 1));
+        }
+        api().finalize(st);
+        return im;
+    }
     // Failures are fatal like in the reference (Database.cpp:8-22): message on stderr, exit(EXIT_FAILURE).
     int check(int rc, int line) const {
         if (rc == kOk || rc == kRow || rc == kDone) return rc;
@@ -164,6 +186,8 @@ void Database::BeginTransaction() const { impl_->exec("BEGIN TRANSACTION"); }
 void Database::EndTransaction() const { impl_->exec("END TRANSACTION"); }
 
 bool Database::ExistImageById(const image_t id) const { return impl_->exists("SELECT 1 FROM images WHERE image_id = ?", id); }
+bool Database::ExistImageByName(const std::string name) const { return ReadImageByName(name).id != INVALID; }
+bool Database::ExistKeyPointsColor(const image_t id) const { return impl_->exists("SELECT 1 FROM colors WHERE image_id = ?", id); }
 bool Database::ExistKeyPoints(const image_t id) const { return impl_->exists("SELECT 1 FROM keypoints WHERE image_id = ?", id); }
 bool Database::ExistDescriptors(const image_t id) const { return impl_->exists("SELECT 1 FROM descriptors WHERE image_id = ?", id); }
 bool Database::ExistMatches(const image_pair_t pair_id) const { return impl_->exists("SELECT 1 FROM matches WHERE pair_id = ?", pair_id); }
@@ -176,6 +200,11 @@ size_t Database::NumImages() const {
     api().finalize(st);
     return n;
 }
+size_t Database::NumKeyPoints(const image_t id) const { return impl_->blob_rows("SELECT rows FROM keypoints WHERE image_id = ?", id); }
+size_t Database::NumKeyPointsColor(const image_t id) const { return impl_->blob_rows("SELECT rows FROM colors WHERE image_id = ?", id); }
+size_t Database::NumMatches(const image_pair_t pair_id) const { return impl_->blob_rows("SELECT rows FROM matches WHERE pair_id = ?", pair_id); }
+Database::Image Database::ReadImageById(const image_t id) const { return impl_->image_row("SELECT image_id, name FROM images WHERE image_id = ?", &id, nullptr); }
+Database::Image Database::ReadImageByName(const std::string name) const { return impl_->image_row("SELECT image_id, name FROM images WHERE name = ?", nullptr, &name); }
 size_t Database::NumDescriptors(const image_t id) const {
     sqlite3_stmt* st = impl_->prepare("SELECT rows FROM descriptors WHERE image_id = ?");
     impl_->check(api().bind_int64(st, 1, id), __LINE__);
@@ -237,6 +266,24 @@ std::vector<cv::KeyPoint> Database::ReadKeyPoints(const image_t id) const {
     return out;
 }
 
+// colors blob: rows x 3 uint8 (KeyPointsColorToBlob, Database.cpp:143-155)
+void Database::WriteKeyPointsColor(const image_t id, const std::vector<cv::Vec3b>& colors) const {
+    std::vector<unsigned char> v(colors.size() * 3);
+    for (size_t i = 0; i < colors.size(); ++i)
+        for (int k = 0; k < 3; ++k) v[3 * i + k] = colors[i][k];
+    impl_->write_blob("INSERT INTO colors(image_id, rows, cols, data) VALUES(?, ?, ?, ?)", id, v, colors.size(), 3);
+}
+std::vector<cv::Vec3b> Database::ReadKeyPointsColor(const image_t id) const {
+    std::vector<unsigned char> v;
+    size_t rows, cols;
+    impl_->read_blob("SELECT rows, cols, data FROM colors WHERE image_id = ?", id, v, rows, cols);
+    assert(rows == 0 || cols == 3);
+    std::vector<cv::Vec3b> out(rows);
+    for (size_t i = 0; i < rows; ++i)
+        for (int k = 0; k < 3; ++k) out[i][k] = v[3 * i + k];
+    return out;
+}
+
 void Database::WriteDescriptors(const image_t id, const cv::Mat& desc) const {
     assert(desc.type() == CV_32F);   // Database.cpp:176
     std::vector<float> v(static_cast<size_t>(desc.rows) * desc.cols);
@@ -272,6 +319,11 @@ std::vector<cv::DMatch> Database::ReadMatches(const image_t a, const image_t b) 
         out[i].trainIdx = swap ? v[2 * i] : v[2 * i + 1];
     }
     return out;
+}
+std::vector<cv::DMatch> Database::ReadMatches(const image_pair_t pair_id) const {
+    image_t a, b;
+    PairIdToImagePair(pair_id, &a, &b);          // a < b: the stored orientation (Database.cpp:524-534)
+    return ReadMatches(a, b);
 }
 std::vector<std::pair<image_pair_t, std::vector<cv::DMatch>>> Database::ReadAllMatches() const {
     std::vector<std::pair<image_pair_t, std::vector<cv::DMatch>>> out;

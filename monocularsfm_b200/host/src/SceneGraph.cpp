@@ -19,7 +19,7 @@ void SceneGraph::Load(const cv::Ptr<Database> database, const size_t min_num_mat
     const std::vector<Database::Image> images = database->ReadAllImages();
     std::cout << "Total images : " << images.size() << std::endl;
     std::cout << "Building scene graph..." << std::flush;
-    for (const Database::Image& image : images) AddImage(image.id, database->ReadKeyPoints(image.id).size());
+    for (const Database::Image& image : images) AddImage(image.id, database->NumKeyPoints(image.id));
     std::cout << NumImages() << std::endl;
     size_t ignored = 0;
     for (const auto& pair : image_pairs) {

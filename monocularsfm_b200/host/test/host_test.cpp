@@ -60,6 +60,24 @@ static int test_cpu(const std::string& path) {
         Database db;
         db.Open(path);
         REQUIRE(db.NumImages() == 2);
+        // the rest of the reference's public surface (include/Database/Database.h:37-69)
+        REQUIRE(db.ExistImageByName("a.jpg") && !db.ExistImageByName("zzz.jpg"));
+        REQUIRE(db.ReadImageById(2).name == "b.jpg" && db.ReadImageByName("a.jpg").id == 1 && db.ReadImageById(77).id == INVALID);
+        REQUIRE(db.NumKeyPoints(1) == 3 && db.NumKeyPoints(2) == 0);
+        REQUIRE(!db.ExistKeyPointsColor(1) && db.NumKeyPointsColor(1) == 0);
+        {
+            std::vector<cv::Vec3b> col(3);
+            col[1] = cv::Vec3b(10, 20, 30);
+            db.WriteKeyPointsColor(1, col);
+            REQUIRE(db.ExistKeyPointsColor(1) && db.NumKeyPointsColor(1) == 3);
+            const std::vector<cv::Vec3b> back = db.ReadKeyPointsColor(1);
+            REQUIRE(back.size() == 3 && back[1][0] == 10 && back[1][1] == 20 && back[1][2] == 30 && back[2][0] == 0);
+        }
+        REQUIRE(db.NumMatches(Database::ImagePairToPairId(2, 1)) == 2);
+        {
+            const std::vector<cv::DMatch> pm = db.ReadMatches(Database::ImagePairToPairId(1, 2));   // (image 1, image 2) orientation
+            REQUIRE(pm.size() == 2 && pm[0].queryIdx == 7 && pm[0].trainIdx == 5);
+        }
         REQUIRE(db.ExistDescriptors(1) && !db.ExistDescriptors(2));
         cv::Mat d = db.ReadDescriptors(1);
         REQUIRE(d.rows == 3 && d.cols == 128 && d.type() == CV_32F && d.at<float>(2, 5) == 19.f);

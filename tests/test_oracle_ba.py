@@ -212,3 +212,39 @@ def test_lm_focal_recovers_a_perturbed_focal_length():
     assert res["final_cost"] <= 1.05 * base["final_cost"]           # the extra block can only fit better than the true focal ...
     # ... and the gauge (only one camera fixed) lets scale trade against focal length, so the ratio is checked loosely
     assert abs(res["focal"][0] / res["focal"][1] - P["fx"] / P["fy"]) < 0.02
+
+
+@pytest.mark.parametrize("focal", [False, True])
+def test_lm_optimum_vs_scipy_least_squares(golden_ba, focal):
+    """An independent solver (MINPACK's Levenberg-Marquardt through scipy.optimize.least_squares, finite-difference
+    Jacobian of the plain residual function) started from the same point reaches the same minimum as the restated Ceres
+    loop — the oracle's LM rules may differ from Ceres' in path, not in destination.  (Ceres itself is not installed:
+    SURVEY.md section 8c.)"""
+    scipy_opt = pytest.importorskip("scipy.optimize")
+    P = _prob(golden_ba, "small")
+    free = ~P["cam_const"].astype(bool)
+    n_free, n_pts = int(free.sum()), len(P["pts"])
+    fx0, fy0 = (P["fx"] * 1.02, P["fy"] * 0.985) if focal else (P["fx"], P["fy"])
+
+    def unpack(x):
+        cams = P["cams"].copy()
+        cams[free] = x[:6 * n_free].reshape(-1, 6)
+        pts = x[6 * n_free:6 * n_free + 3 * n_pts].reshape(-1, 3)
+        f = x[6 * n_free + 3 * n_pts:] if focal else (fx0, fy0)
+        return cams, pts, f
+
+    def fun(x):
+        cams, pts, f = unpack(x)
+        return bo.residuals_only(cams, pts, P["obs_uv"], P["obs_cam"], P["obs_pt"], f[0], f[1]).reshape(-1)
+
+    x0 = np.concatenate([P["cams"][free].reshape(-1), P["pts"].reshape(-1)] + ([np.array([fx0, fy0])] if focal else []))
+    sol = scipy_opt.least_squares(fun, x0, method="lm", x_scale="jac", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=200000)
+    c_scipy = 0.5 * float((sol.fun ** 2).sum())
+    if focal:
+        ref = bo.lm_solve_focal(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], fx0, fy0,
+                                function_tol=1e-12, max_iters=300)
+    else:
+        ref = bo.lm_solve(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"],
+                          function_tol=1e-12, max_iters=300)
+    assert ref["final_cost"] < 0.2 * ref["initial_cost"]
+    assert abs(ref["final_cost"] - c_scipy) <= 1e-6 * c_scipy, (ref["final_cost"], c_scipy)

@@ -467,7 +467,9 @@ def run_ours(args, rank, world, local_rank):
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
             ncu_ops_pct = tj.get("tensor_pipe_ops_pct_of_peak_ncu")
         roofline = {"bound": "tensor", "kernel": "match_pair_kernel", "achieved": achieved, "peak": peak_int8,
-                    "unit": "TOP/s", "frac": achieved / peak_int8 if peak_int8 else None, "traffic": traffic,
+                    "unit": "TFLOP/s", "ops": "integer: u8 x u8 -> s32 multiply-accumulates on the tensor cores, 2 ops each "
+                                              "(TOP/s; the contract's unit name is kept)",
+                    "frac": achieved / peak_int8 if peak_int8 else None, "traffic": traffic,
                     "traffic_source": traffic_src,
                     "peak_note": f"2 x cuBLAS bf16 sustained ({peaks['bf16_tflops_sustained']} TF/s, {peaks['source']} "
                                  "MEASURED_PEAKS.json): int8 tcgen05 runs at twice the bf16 rate; no int8 GEMM peak is measured",

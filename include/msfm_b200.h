@@ -67,7 +67,8 @@ int64_t msfm_launch_count(const msfm_ctx* ctx);
 #define MSFM_PROF_BA_EVAL      6   /* K2: residual + Jacobian + normal-equation blocks */
 #define MSFM_PROF_BA_SCHUR     7   /* K2: Schur reduction onto the camera system */
 #define MSFM_PROF_BA_OTHER     8
-#define MSFM_PROF_NCAT         9
+#define MSFM_PROF_BA_COMM      9   /* the all-reduce of the reduced camera system (multi-GPU) */
+#define MSFM_PROF_NCAT        10
 int msfm_prof_enable(msfm_ctx* ctx, int on);
 int msfm_prof_reset(msfm_ctx* ctx);
 int msfm_prof_read(msfm_ctx* ctx, double ms[MSFM_PROF_NCAT], int64_t launches[MSFM_PROF_NCAT]);
@@ -210,6 +211,11 @@ void msfm_ba_default_options(msfm_ba_options* opt, int32_t n_cams);
  * (msfm_comm_init) every rank passes ALL cameras and its own share of the points/observations. */
 int  msfm_ba_create(msfm_ctx* ctx, const msfm_ba_problem* prob, msfm_ba** out);
 void msfm_ba_destroy(msfm_ba* ba);
+/* Structure of the problem as the device sees it: info[0] free cameras F, [1] non-empty 6x6 blocks of the upper block
+ * triangle of the reduced camera system (the fp32 part of the all-reduce message), [2] point tiles, [3] max cameras per
+ * tile, [4] bytes of the system buffer (= the all-reduce message + 16), [5] shared memory per CTA of the linearisation
+ * kernel, [6] fp64 words of the message tail (scalars | rhs | g_c | diag U | focal border), [7] reserved. */
+int  msfm_ba_structure(msfm_ba* ba, int32_t info[8]);
 /* Current parameters -> host ([n_cams][6], [n_pts][3]; either may be NULL). */
 int  msfm_ba_get_params(msfm_ba* ba, double* cams, double* pts);
 int  msfm_ba_set_params(msfm_ba* ba, const double* cams, const double* pts);

@@ -104,6 +104,7 @@ def load_library():
         "msfm_ba_default_options": (None, [P(BAOptions), i32]),
         "msfm_ba_create": (C.c_int, [vp, P(BAProblemC), P(vp)]),
         "msfm_ba_destroy": (None, [vp]),
+        "msfm_ba_structure": (C.c_int, [vp, P(i32)]),
         "msfm_ba_get_params": (C.c_int, [vp, vp, vp]),
         "msfm_ba_set_params": (C.c_int, [vp, vp, vp]),
         "msfm_ba_evaluate": (C.c_int, [vp, vp, vp, P(C.c_double)]),
@@ -172,7 +173,7 @@ class Context:
         return int(self.lib.msfm_launch_count(self.h))
 
     PROF_NAMES = ["desc_format", "build_units", "match_tile", "resolve", "exact", "compact", "ba_eval", "ba_schur",
-                  "ba_other"]
+                  "ba_other", "ba_comm"]
 
     def prof_enable(self, on=True):
         self._check(self.lib.msfm_prof_enable(self.h, int(on)))
@@ -303,6 +304,12 @@ class BAProblem:
         self.h = None
 
     __del__ = close
+
+    def structure(self):
+        info = (C.c_int32 * 8)()
+        self.ctx._check(self.lib.msfm_ba_structure(self.h, info))
+        return {"n_free": info[0], "n_blocks": info[1], "n_tiles": info[2], "w_cap": info[3], "system_bytes": info[4],
+                "smem_per_cta": info[5], "tail_f64": info[6]}
 
     def get_params(self):
         cams = np.zeros((self.n_cams, 6))

@@ -11,24 +11,24 @@
 #include <new>
 #include <vector>
 
+#include "ba_tiles.hpp"
 #include "ba_types.cuh"
 #include "ctx.hpp"
 
 namespace msfm {
 using ba::CamPre;
 using ba::Problem;
+using ba::TailLayout;
+using ba::Tile;
 cudaError_t ba_launch_cam_prep(const double*, int, CamPre*, cudaStream_t);
 cudaError_t ba_launch_evaluate(const Problem&, double*, float*, double*, int, cudaStream_t);
-cudaError_t ba_launch_linearize(const Problem&, double, double*, int, cudaStream_t);
+cudaError_t ba_launch_linearize(const Problem&, double, int, cudaStream_t);
+cudaError_t ba_launch_expand_dense(const Problem&, double, double*, cudaStream_t);
 cudaError_t ba_launch_track_errors(const Problem&, double*, int, cudaStream_t);
-cudaError_t ba_launch_compact_blocks(const int32_t*, long long, int32_t*, int32_t*, int, cudaStream_t);
-cudaError_t ba_launch_count_tuples(const Problem&, int32_t*, int, cudaStream_t);
-cudaError_t ba_launch_scan_tuples(const int32_t*, long long, int32_t*, int32_t*, cudaStream_t);
-cudaError_t ba_launch_fill_tuples(const Problem&, int32_t*, int2*, int, cudaStream_t);
-cudaError_t ba_launch_damp(double*, int, double, cudaStream_t);
 cudaError_t ba_launch_backsub(const Problem&, double, const double*, double*, double*, int, cudaStream_t);
 cudaError_t ba_launch_update_cams(const double*, const int32_t*, int, const double*, double*, cudaStream_t);
 cudaError_t ba_launch_copy(const double*, double*, int, cudaStream_t);
+size_t ba_fused_smem_bytes(int, bool);
 }  // namespace msfm
 using namespace msfm;
 
@@ -40,6 +40,8 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, Id128, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -57,13 +59,15 @@ static const char* nccl_load() {
         dlsym(g_nccl.lib, "ncclAllReduce"));
     g_nccl.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(g_nccl.lib, "ncclCommDestroy"));
     g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(g_nccl.lib, "ncclGetErrorString"));
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    g_nccl.GroupStart = reinterpret_cast<int (*)()>(dlsym(g_nccl.lib, "ncclGroupStart"));
+    g_nccl.GroupEnd = reinterpret_cast<int (*)()>(dlsym(g_nccl.lib, "ncclGroupEnd"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
         g_nccl.lib = nullptr;
         return "NCCL symbols missing";
     }
     return nullptr;
 }
-static constexpr int kNcclFloat64 = 8;   // ncclDouble
+static constexpr int kNcclUint8 = 1, kNcclFloat32 = 7, kNcclFloat64 = 8;   // ncclDataType_t
 static constexpr int kNcclSum = 0, kNcclMax = 2;
 
 // ------------------------------------------------------------------------------------------------ problem object
@@ -77,36 +81,40 @@ struct msfm_ba {
     double *cams[2] = {nullptr, nullptr}, *pts[2] = {nullptr, nullptr};   // current / candidate
     CamPre* pre[2] = {nullptr, nullptr};
     double* obs_uv = nullptr;
-    int32_t *obs_cam = nullptr, *obs_pt = nullptr, *pt_start = nullptr, *cam_free = nullptr;
-    double* sys = nullptr;        // S | rhs | gc | udiag | scalars[8]
+    int32_t *obs_cam = nullptr, *obs_pt = nullptr, *obs_orig = nullptr, *pt_start = nullptr, *pt_order = nullptr, *cam_free = nullptr;
+    uint8_t* obs_lcam = nullptr;
+    // tiling + block structure (ba_types.cuh, ba_tiles.hpp)
+    Tile* tiles = nullptr;
+    int32_t *tile_cams = nullptr, *tile_slots = nullptr, *blk_row = nullptr, *blk_col = nullptr;
+    int32_t n_tiles = 0, w_cap = 32, n_blocks = 0;
+    std::vector<int32_t> h_blk_row, h_blk_col;
+    // the system of one linearisation, ONE allocation: tail (fp64: scalars | per-rank max |g_p| | rhs | gc | diag U | focal
+    // border) | tile counter | sblk (fp32 6x6 blocks).  tail and sblk are the two parts of the all-reduce message.
+    unsigned char* sysbuf = nullptr;
+    size_t sys_bytes = 0;
+    TailLayout tl{};
+    float* sblk = nullptr;
+    int32_t* tile_counter = nullptr;
+    double* dense = nullptr;      // [n6][n6] dense copy of S for the dense Cholesky (allocated by the first solve)
     double* xsol = nullptr;       // solver right-hand side / solution [n6]
-    double* small = nullptr;      // [8] scratch scalars (backsub out[3], new cost, gpmax bits)
-    // gather structures + per-linearisation intermediates (ba_types.cuh)
-    int32_t *cam_obs_start = nullptr, *cam_obs_list = nullptr, *blk_start = nullptr;
-    int2* blk_tuples = nullptr;
-    int32_t* blk_list = nullptr;
-    int32_t n_blk_list = 0;
-    float* obs_J = nullptr;
-    double *obs_r = nullptr, *pt_Vinv = nullptr, *pt_gp = nullptr;
+    double* small = nullptr;      // [8] scratch scalars (backsub out[3], new cost)
     double* work = nullptr;       // cusolver workspace
     int work_len = 0;
     int* dev_info = nullptr;
     int cur = 0;
     std::vector<double> h_cams;   // host mirror of the current cameras
     std::vector<int32_t> h_cam_free;
-    // S | rhs | gc | udiag | scalars[8] (| B0 | B1 | focal[16] with a shared focal block)
-    size_t sys_len() const { const size_t n6 = size_t(n_free) * 6; return n6 * n6 + 3 * n6 + 8 + (refine_focal ? 2 * n6 + 16 : 0); }
+    double* tail() const { return reinterpret_cast<double*>(sysbuf); }
     Problem view(int which) const {
-        Problem P;
+        Problem P{};
         P.n_cams = n_cams; P.n_pts = n_pts; P.n_obs = n_obs; P.n_free = n_free;
         P.fx = focal[which][0]; P.fy = focal[which][1];
         P.refine_focal = refine_focal; P.pt_Wf = pt_Wf;
-        P.pre = pre[which]; P.pts = pts[which]; P.obs_uv = obs_uv; P.obs_cam = obs_cam; P.obs_pt = obs_pt;
-        P.pt_start = pt_start; P.cam_free = cam_free;
-        P.gpmax_bits = reinterpret_cast<unsigned long long*>(small + 4);
-        P.cam_obs_start = cam_obs_start; P.cam_obs_list = cam_obs_list; P.blk_start = blk_start; P.blk_tuples = blk_tuples;
-        P.blk_list = blk_list; P.n_blk_list = n_blk_list;
-        P.obs_J = obs_J; P.obs_r = obs_r; P.pt_Vinv = pt_Vinv; P.pt_gp = pt_gp;
+        P.pre = pre[which]; P.pts = pts[which]; P.obs_uv = obs_uv; P.obs_cam = obs_cam; P.obs_pt = obs_pt; P.obs_orig = obs_orig;
+        P.obs_lcam = obs_lcam; P.pt_start = pt_start; P.pt_order = pt_order; P.cam_free = cam_free;
+        P.tiles = tiles; P.n_tiles = n_tiles; P.tile_cams = tile_cams; P.tile_slots = tile_slots; P.w_cap = w_cap;
+        P.n_blocks = n_blocks; P.blk_row = blk_row; P.blk_col = blk_col;
+        P.sblk = sblk; P.tail = tail(); P.tl = tl; P.gpm_slot = ctx->comm ? ctx->comm_rank : 0; P.tile_counter = tile_counter;
         return P;
     }
 };
@@ -127,6 +135,14 @@ void ctx_destroy_solver(msfm_ctx* c) {
     if (c && c->cusolver) { cusolverDnDestroy(static_cast<cusolverDnHandle_t>(c->cusolver)); c->cusolver = nullptr; }
 }
 }  // namespace msfm
+
+// sum / max of a device buffer across the ranks of the ctx's communicator, in place, on the ctx stream
+static int comm_allreduce(msfm_ctx* c, void* buf, size_t count, int dtype, int op) {
+    if (count == 0) return MSFM_OK;
+    const int r = g_nccl.AllReduce(buf, buf, count, dtype, op, c->comm, c->stream);
+    if (r != 0) return c->fail(MSFM_E_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    return MSFM_OK;
+}
 
 extern "C" {
 
@@ -151,9 +167,9 @@ void msfm_ba_destroy(msfm_ba* b) {
     msfm_ctx* c = b->ctx;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    void* ptrs[] = {b->cams[0], b->cams[1], b->pts[0], b->pts[1], b->pre[0], b->pre[1], b->obs_uv, b->obs_cam, b->obs_pt,
-                    b->pt_start, b->cam_free, b->sys, b->xsol, b->small, b->work, b->dev_info, b->cam_obs_start,
-                    b->cam_obs_list, b->blk_start, b->blk_tuples, b->blk_list, b->obs_J, b->obs_r, b->pt_Vinv, b->pt_gp, b->pt_Wf};
+    void* ptrs[] = {b->cams[0], b->cams[1], b->pts[0], b->pts[1], b->pre[0], b->pre[1], b->obs_uv, b->obs_cam, b->obs_pt, b->obs_orig,
+                    b->obs_lcam, b->pt_start, b->pt_order, b->cam_free, b->tiles, b->tile_cams, b->tile_slots, b->blk_row, b->blk_col,
+                    b->sysbuf, b->dense, b->xsol, b->small, b->work, b->dev_info, b->pt_Wf};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -167,41 +183,50 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
         (pr->n_pts > 0 && !pr->pts) || (pr->n_obs > 0 && (!pr->obs_uv || !pr->obs_cam || !pr->obs_pt)))
         return c->fail(MSFM_E_INVALID, "msfm_ba_create: bad problem description");
     BA_CUDA(cudaSetDevice(c->device));
-    // validate indices, build CSR over points and the free-camera map on the host
-    std::vector<int32_t> pt_start(size_t(pr->n_pts) + 1, 0), cam_free(pr->n_cams, -1);
+    // validate indices, free-camera map
+    std::vector<int32_t> cam_free(pr->n_cams, -1);
     int prev = 0;
     for (int i = 0; i < pr->n_obs; ++i) {
         const int p = pr->obs_pt[i], cam = pr->obs_cam[i];
         if (p < prev || p >= pr->n_pts || cam < 0 || cam >= pr->n_cams)
             return c->fail(MSFM_E_INVALID, "msfm_ba_create: observation %d has bad indices (obs_pt must be non-decreasing)", i);
         prev = p;
-        pt_start[size_t(p) + 1] += 1;
     }
-    for (int p = 0; p < pr->n_pts; ++p) pt_start[size_t(p) + 1] += pt_start[p];
     int nf = 0;
     for (int i = 0; i < pr->n_cams; ++i)
         if (!pr->cam_const[i]) cam_free[i] = nf++;
-    // a landmark holds at most one measurement per image (tracks in Map.cpp are keyed by image): the gather lists rely on it
-    for (int p = 0; p < pr->n_pts; ++p)
-        for (int a = pt_start[p]; a < pt_start[size_t(p) + 1]; ++a)
-            for (int q = a + 1; q < pt_start[size_t(p) + 1]; ++q)
-                if (pr->obs_cam[a] == pr->obs_cam[q])
-                    return c->fail(MSFM_E_INVALID, "msfm_ba_create: point %d is observed twice by camera %d", p, pr->obs_cam[a]);
-    // CSR of the observations of every free camera (counting sort)
-    std::vector<int32_t> cam_obs_start(size_t(nf) + 1, 0), cam_obs_list;
-    for (int i = 0; i < pr->n_obs; ++i) {
-        const int f = cam_free[pr->obs_cam[i]];
-        if (f >= 0) cam_obs_start[size_t(f) + 1] += 1;
-    }
-    for (int f = 0; f < nf; ++f) cam_obs_start[size_t(f) + 1] += cam_obs_start[f];
-    cam_obs_list.resize(size_t(cam_obs_start[nf]));
+    // ---- structure analysis (host): device order, tiles, block structure of the reduced camera system
+    ba::TilingParams tp;
     {
-        std::vector<int32_t> cur(cam_obs_start.begin(), cam_obs_start.end() - 1);
-        for (int i = 0; i < pr->n_obs; ++i) {
-            const int f = cam_free[pr->obs_cam[i]];
-            if (f >= 0) cam_obs_list[size_t(cur[f]++)] = i;
-        }
+        const char* e1 = getenv("MSFM_BA_WCAP");
+        const char* e2 = getenv("MSFM_BA_TILE_PTS");
+        if (e1 && atoi(e1) > 0) tp.w_cap = atoi(e1);
+        // enough tiles to keep every SM busy (two resident CTAs each) with a dynamic scheduler
+        tp.max_pts = std::max(16, std::min(256, pr->n_pts / (8 * std::max(1, c->num_sms))));
+        if (e2 && atoi(e2) > 0) tp.max_pts = atoi(e2);
     }
+    ba::Tiling T;
+    // a landmark holds at most one measurement per image (tracks in Map.cpp are keyed by image): the pair products rely on it
+    if (!ba::build_tiling(pr->n_cams, pr->n_pts, pr->n_obs, pr->obs_cam, pr->obs_pt, cam_free.data(), tp, T))
+        return c->fail(MSFM_E_INVALID, "msfm_ba_create: a point is observed twice by the same camera");
+    std::vector<uint8_t> present;
+    ba::mark_blocks(T, cam_free.data(), nf, present);
+    if (c->comm && c->comm_ranks > 1 && !present.empty()) {
+        // every rank owns other points: the block structure of the summed system is the union over the ranks
+        uint8_t* d_present = nullptr;
+        BA_CUDA(cudaMalloc(&d_present, present.size()));
+        cudaError_t e = cudaMemcpyAsync(d_present, present.data(), present.size(), cudaMemcpyHostToDevice, c->stream);
+        int rc = MSFM_OK;
+        if (e == cudaSuccess) rc = comm_allreduce(c, d_present, present.size(), kNcclUint8, kNcclMax);
+        if (e == cudaSuccess && rc == MSFM_OK) e = cudaMemcpyAsync(present.data(), d_present, present.size(), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && rc == MSFM_OK) e = cudaStreamSynchronize(c->stream);
+        cudaFree(d_present);
+        if (rc) return rc;
+        if (e != cudaSuccess) return c->cuda_fail(e, "msfm_ba_create: merging the block structure across ranks");
+    }
+    ba::assign_slots(T, cam_free.data(), nf, present);
+    present.clear(); present.shrink_to_fit();
+
     msfm_ba* b = new (std::nothrow) msfm_ba();
     if (!b) return c->fail(MSFM_E_CUDA, "out of host memory");
     b->ctx = c;
@@ -210,7 +235,27 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     b->focal[0][0] = b->focal[1][0] = pr->fx; b->focal[0][1] = b->focal[1][1] = pr->fy;
     b->h_cams.assign(pr->cams, pr->cams + size_t(pr->n_cams) * 6);
     b->h_cam_free = cam_free;
+    b->n_tiles = static_cast<int32_t>(T.tiles.size());
+    b->w_cap = std::max(32, T.w_max);
+    b->n_blocks = static_cast<int32_t>(T.blk_col.size());
+    b->h_blk_row = T.blk_row; b->h_blk_col = T.blk_col;
     const size_t n6 = size_t(nf) * 6;
+    {
+        const int R = c->comm ? c->comm_ranks : 1;
+        TailLayout& tl = b->tl;
+        tl.scal = 0; tl.gpm = 8; tl.rhs = 8 + R; tl.gc = tl.rhs + int(n6); tl.udiag = tl.gc + int(n6);
+        tl.B0 = tl.udiag + int(n6); tl.B1 = tl.B0 + (b->refine_focal ? int(n6) : 0); tl.ff = tl.B1 + (b->refine_focal ? int(n6) : 0);
+        tl.total = tl.ff + (b->refine_focal ? 16 : 0);
+        tl.total = (tl.total + 1) & ~1;          // sblk stays 16-byte aligned behind the 16-byte counter slot
+    }
+    // device-order copies of the observation arrays
+    std::vector<double> uv(size_t(pr->n_obs) * 2);
+    std::vector<int32_t> ocam(pr->n_obs), opt(pr->n_obs);
+    for (int i = 0; i < pr->n_obs; ++i) {
+        const int o = T.obs_perm[i];
+        uv[2 * size_t(i)] = pr->obs_uv[2 * size_t(o)]; uv[2 * size_t(i) + 1] = pr->obs_uv[2 * size_t(o) + 1];
+        ocam[i] = pr->obs_cam[o]; opt[i] = pr->obs_pt[o];
+    }
     auto fail_free = [&](int rc) { msfm_ba_destroy(b); return rc; };
 #define BA_ALLOC(ptr, bytes)                                                         \
     do {                                                                             \
@@ -225,20 +270,24 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     BA_ALLOC(b->obs_uv, size_t(pr->n_obs) * 2 * sizeof(double));
     BA_ALLOC(b->obs_cam, size_t(pr->n_obs) * sizeof(int32_t));
     BA_ALLOC(b->obs_pt, size_t(pr->n_obs) * sizeof(int32_t));
+    BA_ALLOC(b->obs_orig, size_t(pr->n_obs) * sizeof(int32_t));
+    BA_ALLOC(b->obs_lcam, size_t(pr->n_obs));
     BA_ALLOC(b->pt_start, (size_t(pr->n_pts) + 1) * sizeof(int32_t));
+    BA_ALLOC(b->pt_order, size_t(pr->n_pts) * sizeof(int32_t));
     BA_ALLOC(b->cam_free, size_t(pr->n_cams) * sizeof(int32_t));
-    BA_ALLOC(b->sys, b->sys_len() * sizeof(double));
+    BA_ALLOC(b->tiles, T.tiles.size() * sizeof(Tile));
+    BA_ALLOC(b->tile_cams, T.tile_cams.size() * sizeof(int32_t));
+    BA_ALLOC(b->tile_slots, T.tile_slots.size() * sizeof(int32_t));
+    BA_ALLOC(b->blk_row, T.blk_row.size() * sizeof(int32_t));
+    BA_ALLOC(b->blk_col, T.blk_col.size() * sizeof(int32_t));
+    b->sys_bytes = size_t(b->tl.total) * sizeof(double) + 16 + size_t(b->n_blocks) * 36 * sizeof(float);
+    BA_ALLOC(b->sysbuf, b->sys_bytes);
+    b->tile_counter = reinterpret_cast<int32_t*>(b->sysbuf + size_t(b->tl.total) * sizeof(double));
+    b->sblk = reinterpret_cast<float*>(b->sysbuf + size_t(b->tl.total) * sizeof(double) + 16);
     BA_ALLOC(b->xsol, (3 * std::max<size_t>(1, n6) + 2) * sizeof(double));      // up to 3 right-hand sides + (d fx, d fy)
     if (b->refine_focal) BA_ALLOC(b->pt_Wf, std::max<size_t>(1, size_t(pr->n_pts)) * 6 * sizeof(double));
     BA_ALLOC(b->small, 8 * sizeof(double));
     BA_ALLOC(b->dev_info, sizeof(int));
-    BA_ALLOC(b->cam_obs_start, cam_obs_start.size() * sizeof(int32_t));
-    BA_ALLOC(b->cam_obs_list, cam_obs_list.size() * sizeof(int32_t));
-    BA_ALLOC(b->blk_start, (size_t(nf) * nf + 1) * sizeof(int32_t));
-    BA_ALLOC(b->obs_J, size_t(pr->n_obs) * 18 * sizeof(float));
-    BA_ALLOC(b->obs_r, size_t(pr->n_obs) * 2 * sizeof(double));
-    BA_ALLOC(b->pt_Vinv, size_t(pr->n_pts) * 6 * sizeof(double));
-    BA_ALLOC(b->pt_gp, size_t(pr->n_pts) * 3 * sizeof(double));
 #undef BA_ALLOC
     auto H2D = [&](void* dst, const void* src, size_t bytes) {
         return bytes ? cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
@@ -246,42 +295,30 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = H2D(b->cams[0], pr->cams, size_t(pr->n_cams) * 6 * sizeof(double));
     if (e == cudaSuccess) e = H2D(b->pts[0], pr->pts, size_t(pr->n_pts) * 3 * sizeof(double));
-    if (e == cudaSuccess) e = H2D(b->obs_uv, pr->obs_uv, size_t(pr->n_obs) * 2 * sizeof(double));
-    if (e == cudaSuccess) e = H2D(b->obs_cam, pr->obs_cam, size_t(pr->n_obs) * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->obs_pt, pr->obs_pt, size_t(pr->n_obs) * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->pt_start, pt_start.data(), pt_start.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = H2D(b->obs_uv, uv.data(), uv.size() * sizeof(double));
+    if (e == cudaSuccess) e = H2D(b->obs_cam, ocam.data(), ocam.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = H2D(b->obs_pt, opt.data(), opt.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = H2D(b->obs_orig, T.obs_perm.data(), T.obs_perm.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = H2D(b->obs_lcam, T.obs_lcam.data(), T.obs_lcam.size());
+    if (e == cudaSuccess) e = H2D(b->pt_start, T.pt_start.data(), T.pt_start.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = H2D(b->pt_order, T.pt_order.data(), T.pt_order.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->cam_free, cam_free.data(), cam_free.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->cam_obs_start, cam_obs_start.data(), cam_obs_start.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->cam_obs_list, cam_obs_list.data(), cam_obs_list.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = H2D(b->tiles, T.tiles.data(), T.tiles.size() * sizeof(Tile));
+    if (e == cudaSuccess) e = H2D(b->tile_cams, T.tile_cams.data(), T.tile_cams.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = H2D(b->tile_slots, T.tile_slots.data(), T.tile_slots.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = H2D(b->blk_row, T.blk_row.data(), T.blk_row.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = H2D(b->blk_col, T.blk_col.data(), T.blk_col.size() * sizeof(int32_t));
     if (e != cudaSuccess) return fail_free(c->cuda_fail(e, "msfm_ba_create H2D"));
-    // co-observation tuples of every camera pair, built on the device: count -> scan -> fill
-    {
-        const long long nblk = static_cast<long long>(nf) * nf;
-        int32_t *counts = nullptr, *cursor = nullptr;
-        const size_t cbytes = std::max<size_t>(16, size_t(nblk) * sizeof(int32_t));
-        if ((e = cudaMalloc(&counts, cbytes)) == cudaSuccess) e = cudaMalloc(&cursor, cbytes);
-        if (e == cudaSuccess) e = cudaMemsetAsync(counts, 0, cbytes, c->stream);
-        const Problem P0 = b->view(0);
-        if (e == cudaSuccess) e = ba_launch_count_tuples(P0, counts, c->num_sms, c->stream);
-        if (e == cudaSuccess) e = ba_launch_scan_tuples(counts, nblk, b->blk_start, cursor, c->stream);
-        int32_t total = 0;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&total, b->blk_start + nblk, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->blk_tuples), std::max<size_t>(16, size_t(total) * sizeof(int2)));
-        if (e == cudaSuccess) e = ba_launch_fill_tuples(b->view(0), cursor, b->blk_tuples, c->num_sms, c->stream);
-        // compact list of the non-empty blocks (at most one per tuple); `counts` is free again and serves as the counter
-        const size_t max_list = static_cast<size_t>(std::min<long long>(nblk, total));
-        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->blk_list), std::max<size_t>(16, max_list * sizeof(int32_t)));
-        if (e == cudaSuccess) e = cudaMemsetAsync(counts, 0, sizeof(int32_t), c->stream);
-        if (e == cudaSuccess) e = ba_launch_compact_blocks(b->blk_start, nblk, b->blk_list, counts, c->num_sms, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&b->n_blk_list, counts, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (counts) cudaFree(counts);
-        if (cursor) cudaFree(cursor);
-        c->launches += 4;
-        if (e != cudaSuccess) return fail_free(c->cuda_fail(e, "msfm_ba_create: building the gather lists"));
-    }
     *out = b;
+    return MSFM_OK;
+}
+
+int msfm_ba_structure(msfm_ba* b, int32_t info[8]) {
+    if (!b || !info) return MSFM_E_INVALID;
+    info[0] = b->n_free; info[1] = b->n_blocks; info[2] = b->n_tiles; info[3] = b->w_cap;
+    info[4] = static_cast<int32_t>(std::min<size_t>(b->sys_bytes, 0x7fffffff));
+    info[5] = static_cast<int32_t>(ba_fused_smem_bytes(b->w_cap, b->refine_focal != 0));
+    info[6] = b->tl.total; info[7] = 0;
     return MSFM_OK;
 }
 
@@ -365,21 +402,27 @@ int msfm_ba_track_errors(msfm_ba* b, double* err) {
     return MSFM_OK;
 }
 
-// zero sys, linearize + Schur at parameter set `which`, all-reduce.  Leaves S undamped on the camera diagonal
-// (udiag is summed across ranks first); the caller applies damp afterwards.
+// Zero the system, linearize + Schur at parameter set `which` (one kernel), all-reduce.  The message of the ONE
+// collective (a single NCCL group launch) is the system buffer itself: the fp32 blocks of the upper block triangle that
+// exist (blk_row / blk_col) and the fp64 tail, in which every rank's max |g_p| has its own slot so that the sum also
+// delivers the maximum.  S stays undamped on the camera diagonal (diag U has to be summed first): the expansion for
+// the solver adds the damping.
 static int linearize(msfm_ba* b, int which, double inv_radius) {
     msfm_ctx* c = b->ctx;
-    BA_CUDA(cudaMemsetAsync(b->sys, 0, b->sys_len() * sizeof(double), c->stream));
-    BA_CUDA(cudaMemsetAsync(b->small, 0, 8 * sizeof(double), c->stream));
+    BA_CUDA(cudaMemsetAsync(b->sysbuf, 0, b->sys_bytes, c->stream));
     c->prof_begin(MSFM_PROF_BA_SCHUR);
-    BA_CUDA(ba_launch_linearize(b->view(which), inv_radius, b->sys, c->num_sms, c->stream));
+    BA_CUDA(ba_launch_linearize(b->view(which), inv_radius, c->num_sms, c->stream));
     c->prof_end();
-    c->launches += 3;
-    if (c->comm) {
-        int rc = msfm_comm_allreduce_f64(c, b->sys, static_cast<int64_t>(b->sys_len()), 0);
+    c->launches += b->n_tiles > 0 ? 1 : 0;
+    if (c->comm && c->comm_ranks > 1) {
+        c->prof_begin(MSFM_PROF_BA_COMM);
+        if (g_nccl.GroupStart() != 0) return c->fail(MSFM_E_CUDA, "ncclGroupStart failed");
+        int rc = comm_allreduce(c, b->sblk, size_t(b->n_blocks) * 36, kNcclFloat32, kNcclSum);
+        if (rc == MSFM_OK) rc = comm_allreduce(c, b->tail(), size_t(b->tl.total), kNcclFloat64, kNcclSum);
+        const int ge = g_nccl.GroupEnd();
+        c->prof_end();
         if (rc) return rc;
-        rc = msfm_comm_allreduce_f64(c, b->small + 4, 1, 1);     // max |g_p| (non-negative: bits order = value order)
-        if (rc) return rc;
+        if (ge != 0) return c->fail(MSFM_E_CUDA, "ncclGroupEnd: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ge) : "error");
     }
     return MSFM_OK;
 }
@@ -391,27 +434,33 @@ int msfm_ba_linearize(msfm_ba* b, double inv_radius, double* S, double* rhs, dou
     int rc = prep(b, b->cur);
     if (rc) return rc;
     if ((rc = linearize(b, b->cur, inv_radius))) return rc;
-    const int n6 = b->n_free * 6;
-    BA_CUDA(ba_launch_damp(b->sys, n6, inv_radius, c->stream));
-    c->launches += 1;
-    const size_t N = size_t(n6);
-    std::vector<double> hS, tail(3 * N + 8);
+    const size_t N = size_t(b->n_free) * 6;
+    std::vector<double> tail(size_t(b->tl.total));
+    std::vector<float> blk;
+    BA_CUDA(cudaMemcpyAsync(tail.data(), b->tail(), tail.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (S) {
-        hS.resize(N * N);
-        BA_CUDA(cudaMemcpyAsync(hS.data(), b->sys, N * N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        blk.resize(size_t(b->n_blocks) * 36);
+        if (!blk.empty()) BA_CUDA(cudaMemcpyAsync(blk.data(), b->sblk, blk.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     }
-    BA_CUDA(cudaMemcpyAsync(tail.data(), b->sys + N * N, tail.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     BA_CUDA(cudaStreamSynchronize(c->stream));
     if (S) {
-        for (size_t i = 0; i < N; ++i)
-            for (size_t j = 0; j < N; ++j) {
-                const size_t bi = i / 6, bj = j / 6;
-                S[i * N + j] = (bi <= bj) ? hS[i * N + j] : hS[j * N + i];     // device holds the upper block triangle
-            }
+        std::memset(S, 0, N * N * sizeof(double));
+        for (int k = 0; k < b->n_blocks; ++k) {
+            const size_t fa = size_t(b->h_blk_row[k]), fb = size_t(b->h_blk_col[k]);
+            for (int i = 0; i < 6; ++i)
+                for (int j = 0; j < 6; ++j) {
+                    // the device holds the upper block triangle; a diagonal block is taken from its own upper triangle
+                    if (fa == fb && j < i) continue;
+                    const double v = blk[size_t(k) * 36 + 6 * i + j];
+                    S[(fa * 6 + i) * N + fb * 6 + j] = v;
+                    S[(fb * 6 + j) * N + fa * 6 + i] = v;
+                }
+        }
+        for (size_t i = 0; i < N; ++i) S[i * N + i] += std::max(tail[size_t(b->tl.udiag) + i], 1e-6) * inv_radius;
     }
-    if (rhs) std::memcpy(rhs, tail.data(), N * sizeof(double));
-    if (gc) std::memcpy(gc, tail.data() + N, N * sizeof(double));
-    if (cost) *cost = tail[3 * N];
+    if (rhs) std::memcpy(rhs, tail.data() + b->tl.rhs, N * sizeof(double));
+    if (gc) std::memcpy(gc, tail.data() + b->tl.gc, N * sizeof(double));
+    if (cost) *cost = tail[size_t(b->tl.scal)];
     if (nf) *nf = b->n_free;
     return MSFM_OK;
 }
@@ -432,12 +481,12 @@ int msfm_ba_linearize_focal(msfm_ba* b, double inv_radius, double* B, double* F,
     if (rc) return rc;
     if ((rc = linearize(b, b->cur, inv_radius))) return rc;
     const size_t N = size_t(b->n_free) * 6;
-    std::vector<double> tail(2 * N + 16);
-    BA_CUDA(cudaMemcpyAsync(tail.data(), b->sys + N * N + 3 * N + 8, tail.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<double> tail(size_t(b->tl.total));
+    BA_CUDA(cudaMemcpyAsync(tail.data(), b->tail(), tail.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     BA_CUDA(cudaStreamSynchronize(c->stream));
-    const double* ff = tail.data() + 2 * N;
+    const double* ff = tail.data() + b->tl.ff;
     if (B)
-        for (size_t i = 0; i < N; ++i) { B[2 * i] = tail[i]; B[2 * i + 1] = tail[N + i]; }
+        for (size_t i = 0; i < N; ++i) { B[2 * i] = tail[size_t(b->tl.B0) + i]; B[2 * i + 1] = tail[size_t(b->tl.B1) + i]; }
     if (F) {
         F[0] = ff[0] + std::max(ff[7], 1e-6) * inv_radius;
         F[1] = ff[1];
@@ -462,8 +511,9 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
     const int n6 = b->n_free * 6;
     const size_t N = size_t(n6);
     if (n6 > 0) {
+        if (!b->dense) BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->dense), N * N * sizeof(double)));
         int lwork = 0;
-        if (cusolverDnDpotrf_bufferSize(solver, CUBLAS_FILL_MODE_LOWER, n6, b->sys, n6, &lwork) != CUSOLVER_STATUS_SUCCESS)
+        if (cusolverDnDpotrf_bufferSize(solver, CUBLAS_FILL_MODE_LOWER, n6, b->dense, n6, &lwork) != CUSOLVER_STATUS_SUCCESS)
             return c->fail(MSFM_E_CUDA, "cusolverDnDpotrf_bufferSize failed");
         if (lwork > b->work_len) {
             if (b->work) cudaFree(b->work);
@@ -480,7 +530,9 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
     long long nres_local = 2LL * b->n_obs;
     const bool focal = b->refine_focal != 0;
     const int nrhs = focal ? 3 : 1;
-    std::vector<double> h_tail(3 * N + 8 + (focal ? 2 * N + 16 : 0)), h_dc(N + 2), h_small(8), h_x(focal ? 3 * N : 0);
+    const TailLayout tl = b->tl;
+    const int n_ranks = c->comm ? c->comm_ranks : 1;
+    std::vector<double> h_tail(size_t(tl.total)), h_dc(N + 2), h_small(8), h_x(focal ? 3 * N : 0);
     int it = 0, good = 0;
     if ((rc = prep(b, b->cur))) return rc;
     while (it < uopt->max_num_iterations) {
@@ -488,17 +540,17 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
         const double inv_radius = 1.0 / radius;
         auto t0 = clk::now();
         if ((rc = linearize(b, b->cur, inv_radius))) return rc;
-        // tail of sys: rhs | gc | udiag | scalars ; plus max |g_p|
-        BA_CUDA(cudaMemcpyAsync(h_tail.data(), b->sys + N * N, h_tail.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        BA_CUDA(cudaMemcpyAsync(h_small.data(), b->small, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        // the fp64 tail of the system: scalars | max |g_p| per rank | rhs | gc | udiag (| focal border)
+        BA_CUDA(cudaMemcpyAsync(h_tail.data(), b->tail(), h_tail.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         BA_CUDA(cudaStreamSynchronize(c->stream));
         t_lin += std::chrono::duration<double>(clk::now() - t0).count();
-        const double lin_cost = h_tail[3 * N];
+        const double lin_cost = h_tail[size_t(tl.scal)];
         if (!have_cost) { cost = lin_cost; sum->initial_cost = cost; have_cost = true; }
-        double gmax = h_small[4];
-        for (size_t i = 0; i < N; ++i) gmax = std::max(gmax, std::fabs(h_tail[N + i]));
-        const double* hB = h_tail.data() + 3 * N + 8;          // B0 | B1 (focal only)
-        const double* hff = hB + 2 * N;                        // F00 F01 F11 rhsf0 rhsf1 gf0 gf1 uf0 uf1
+        double gmax = 0.0;
+        for (int r = 0; r < n_ranks; ++r) gmax = std::max(gmax, h_tail[size_t(tl.gpm) + r]);
+        for (size_t i = 0; i < N; ++i) gmax = std::max(gmax, std::fabs(h_tail[size_t(tl.gc) + i]));
+        const double* hB = h_tail.data() + tl.B0;              // B0 | B1 (focal only)
+        const double* hff = h_tail.data() + tl.ff;             // F00 F01 F11 rhsf0 rhsf1 gf0 gf1 uf0 uf1
         if (focal) gmax = std::max(gmax, std::max(std::fabs(hff[5]), std::fabs(hff[6])));
         if (gmax <= uopt->gradient_tolerance) { converged = true; break; }
         // ---- solve the reduced camera system (dense Cholesky; the row-major upper block triangle written by the
@@ -506,13 +558,14 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
         t0 = clk::now();
         bool solved = true;
         if (n6 > 0) {
-            BA_CUDA(ba_launch_damp(b->sys, n6, inv_radius, c->stream));
-            BA_CUDA(ba_launch_copy(b->sys + N * N, b->xsol, n6, c->stream));
+            BA_CUDA(cudaMemsetAsync(b->dense, 0, N * N * sizeof(double), c->stream));
+            BA_CUDA(ba_launch_expand_dense(b->view(b->cur), inv_radius, b->dense, c->stream));
+            BA_CUDA(ba_launch_copy(b->tail() + tl.rhs, b->xsol, n6, c->stream));
             if (focal) {       // two more right-hand sides: the border columns (S^-1 B for the 2 x 2 Schur complement below)
-                BA_CUDA(cudaMemcpyAsync(b->xsol + N, b->sys + N * N + 3 * N + 8, 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+                BA_CUDA(cudaMemcpyAsync(b->xsol + N, b->tail() + tl.B0, 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
             }
             c->launches += 2;
-            if (cusolverDnDpotrf(solver, CUBLAS_FILL_MODE_LOWER, n6, b->sys, n6, b->work, b->work_len, b->dev_info) != CUSOLVER_STATUS_SUCCESS)
+            if (cusolverDnDpotrf(solver, CUBLAS_FILL_MODE_LOWER, n6, b->dense, n6, b->work, b->work_len, b->dev_info) != CUSOLVER_STATUS_SUCCESS)
                 return c->fail(MSFM_E_CUDA, "cusolverDnDpotrf failed to launch");
             int info = 0;
             BA_CUDA(cudaMemcpyAsync(&info, b->dev_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -520,7 +573,7 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
             if (info != 0) {
                 solved = false;
             } else {
-                if (cusolverDnDpotrs(solver, CUBLAS_FILL_MODE_LOWER, n6, nrhs, b->sys, n6, b->xsol, n6, b->dev_info) != CUSOLVER_STATUS_SUCCESS)
+                if (cusolverDnDpotrs(solver, CUBLAS_FILL_MODE_LOWER, n6, nrhs, b->dense, n6, b->xsol, n6, b->dev_info) != CUSOLVER_STATUS_SUCCESS)
                     return c->fail(MSFM_E_CUDA, "cusolverDnDpotrs failed to launch");
             }
         }
@@ -570,7 +623,7 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
         BA_CUDA(ba_launch_evaluate(b->view(nxt), nullptr, nullptr, b->small + 3, c->num_sms, c->stream));
         c->prof_end();
         c->launches += 1;
-        if (c->comm && (rc = msfm_comm_allreduce_f64(c, b->small, 4, 0))) return rc;
+        if (c->comm && c->comm_ranks > 1 && (rc = msfm_comm_allreduce_f64(c, b->small, 4, 0))) return rc;
         BA_CUDA(cudaMemcpyAsync(h_small.data(), b->small, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if (n6 > 0 && !focal) BA_CUDA(cudaMemcpyAsync(h_dc.data(), b->xsol, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         BA_CUDA(cudaStreamSynchronize(c->stream));
@@ -609,7 +662,7 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
             if (radius < 1e-32) { failed = true; break; }
         }
     }
-    if (c->comm) {
+    if (c->comm && c->comm_ranks > 1) {
         // residual count over all ranks
         double v = static_cast<double>(nres_local);
         BA_CUDA(cudaMemcpyAsync(b->small, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream));

@@ -5,18 +5,19 @@
 //     Jacobian — here ANALYTIC, equal to the autodiff of Ceres' AngleAxisRotatePoint in both of its branches;
 //   * per point: V = sum Jp^T Jp (+ Marquardt damping), g_p; per camera: U, g_c;
 //   * Schur elimination of the points onto the free cameras: S = U + D_c - sum W V^-1 W^T, rhs = -(g_c - W V^-1 g_p)
-//     (Ceres SchurEliminator for DENSE_SCHUR / SPARSE_SCHUR, :264-273) into one dense buffer
-//     [S | rhs | g_c | diag U | cost] that a single NCCL all-reduce sums across GPUs.  The reduction is a GATHER, not
-//     a scatter: the sparsity pattern is fixed across LM iterations, so per-camera observation lists and per
-//     camera-pair co-observation lists are built once per problem; each diagonal block is then owned by one CTA and
-//     each off-diagonal block by one warp, which sum their contributions in registers and store — no floating-point
-//     atomics (the first version scattered 1.1e8 fp64 atomics per linearisation and was bound by L2 atomic
-//     throughput: profiles/r01_k2_ncu_raw.csv);
+//     (Ceres SchurEliminator for DENSE_SCHUR / SPARSE_SCHUR, :264-273);
 //   * back-substitution of the points, candidate-step evaluation.
-// Observations are grouped by point; one warp owns one point, one lane one observation (chunks of 32 for longer
-// tracks).  Geometry (projection, residual, V^-1) is evaluated in fp64, the 6x3 / 6x6 block products of the Schur
-// reduction in fp32, all accumulation into the normal equations in fp64.  Tensor cores are not used: the work is
-// a sparse gather/scatter bounded by HBM/L2 atomics, not by flops.
+//
+// ONE kernel per linearisation (fused_linearize_kernel).  Nothing per-observation is written to memory: the
+// 2 x 6 / 2 x 3 Jacobians of a point's observations live in registers and in a per-warp shared-memory staging area,
+// the 6x6 products Y_a W_b^T = Jc_a^T (Jp_a V^-1 Jp_b^T) Jc_b of its camera pairs are accumulated into the CTA's
+// shared-memory copy of the blocks its TILE of points touches (ba_types.cuh: Tile), and that copy is flushed once
+// per tile with vector reductions (red.global.add.v4.f32) into the block-sparse S.  History: v1 scattered every product with
+// fp64 global atomics (bound by L2 atomic throughput, profiles/r01_k2_ncu_raw.csv); v2 stored Jacobians and residuals
+// per observation and gathered them again per camera and per camera pair (three kernels, ~10x the algorithmic DRAM
+// traffic, latency-bound gathers: profiles/r01b_k2_ncu_summary.txt).
+// Geometry (projection, residual, V^-1, gradients) is evaluated in fp64, the 6x6 block products in fp32.  Tensor
+// cores are not used: sparse, irregular work.
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -57,16 +58,11 @@ __global__ void cam_prep_kernel(const double* __restrict__ cams, int n_cams, Cam
     p.R[0] = 1.0 + b * (wx * wx - th2); p.R[1] = -a * wz + b * wx * wy;      p.R[2] = a * wy + b * wx * wz;
     p.R[3] = a * wz + b * wx * wy;      p.R[4] = 1.0 + b * (wy * wy - th2); p.R[5] = -a * wx + b * wy * wz;
     p.R[6] = -a * wy + b * wx * wz;     p.R[7] = a * wx + b * wy * wz;      p.R[8] = 1.0 + b * (wz * wz - th2);
+    p.pad = 0.0;
     pre[c] = p;
 }
 
 // ------------------------------------------------------------------------------------------------ per observation
-struct ObsLin {
-    double r[2];
-    float Jc[12];   // [2][6]  d r / d (rvec | tvec)
-    float Jp[6];    // [2][3]  d r / d point
-};
-
 template <bool kJac>
 __device__ __forceinline__ void obs_eval(const CamPre& c, const double X[3], double u, double v, double fx, double fy,
                                          double r[2], double Jc[12], double Jp[6], double xy[2] = nullptr) {
@@ -108,23 +104,21 @@ __device__ __forceinline__ void obs_eval(const CamPre& c, const double X[3], dou
     Jp[3] = A11 * c.R[3] + A12 * c.R[6]; Jp[4] = A11 * c.R[4] + A12 * c.R[7]; Jp[5] = A11 * c.R[5] + A12 * c.R[8];
 }
 
-// residual + Jacobian dump for parity tests (msfm_ba_evaluate)
-__global__ void evaluate_kernel(const CamPre* __restrict__ pre, const double* __restrict__ pts,
-                                const double* __restrict__ obs_uv, const int32_t* __restrict__ obs_cam,
-                                const int32_t* __restrict__ obs_pt, int n_obs, double fx, double fy,
-                                double* __restrict__ r_out, float* __restrict__ J_out, double* __restrict__ cost) {
+// residual + Jacobian dump for parity tests (msfm_ba_evaluate); outputs in the CALLER's observation order
+__global__ void evaluate_kernel(Problem P, double* __restrict__ r_out, float* __restrict__ J_out, double* __restrict__ cost) {
     double local = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_obs; i += gridDim.x * blockDim.x) {
-        const CamPre c = pre[obs_cam[i]];
-        const int p = obs_pt[i];
-        const double X[3] = {pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_obs; i += gridDim.x * blockDim.x) {
+        const CamPre c = P.pre[P.obs_cam[i]];
+        const int p = P.obs_pt[i];
+        const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
         double r[2], Jc[12], Jp[6];
-        if (J_out) obs_eval<true>(c, X, obs_uv[2 * i], obs_uv[2 * i + 1], fx, fy, r, Jc, Jp);
-        else obs_eval<false>(c, X, obs_uv[2 * i], obs_uv[2 * i + 1], fx, fy, r, Jc, Jp);
+        if (J_out) obs_eval<true>(c, X, P.obs_uv[2 * i], P.obs_uv[2 * i + 1], P.fx, P.fy, r, Jc, Jp);
+        else obs_eval<false>(c, X, P.obs_uv[2 * i], P.obs_uv[2 * i + 1], P.fx, P.fy, r, Jc, Jp);
         local += 0.5 * (r[0] * r[0] + r[1] * r[1]);
-        if (r_out) { r_out[2 * i] = r[0]; r_out[2 * i + 1] = r[1]; }
+        const size_t o = (r_out || J_out) ? static_cast<size_t>(P.obs_orig[i]) : 0;
+        if (r_out) { r_out[2 * o] = r[0]; r_out[2 * o + 1] = r[1]; }
         if (J_out) {
-            float* J = J_out + static_cast<size_t>(i) * 18;
+            float* J = J_out + o * 18;
 #pragma unroll
             for (int k = 0; k < 6; ++k) { J[k] = static_cast<float>(Jc[k]); J[9 + k] = static_cast<float>(Jc[6 + k]); }
 #pragma unroll
@@ -146,7 +140,16 @@ __global__ void evaluate_kernel(const CamPre* __restrict__ pre, const double* __
 }
 
 // ------------------------------------------------------------------------------------------------ helpers
-__device__ __forceinline__ double warp_sum(double v);
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 
 // Mean reprojection error of every point over its observations, sqrt(dx^2 + dy^2) per observation: what
 // Map::UpdateFromBAData recomputes on the host after every BA through ComputeTrackError
@@ -156,8 +159,9 @@ __global__ void __launch_bounds__(256)
 track_error_kernel(Problem P, double* __restrict__ err) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < P.n_pts; p += gridDim.x * wpb) {
-        const int beg = P.pt_start[p], end = P.pt_start[p + 1];
+    for (int d = blockIdx.x * wpb + (threadIdx.x >> 5); d < P.n_pts; d += gridDim.x * wpb) {
+        const int p = P.pt_order[d];
+        const int beg = P.pt_start[d], end = P.pt_start[d + 1];
         const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
         double s = 0.0;
         for (int o = beg + lane; o < end; o += 32) {
@@ -171,11 +175,6 @@ track_error_kernel(Problem P, double* __restrict__ err) {
     }
 }
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 // inverse of the symmetric 3x3 V (v00 v01 v02 v11 v12 v22)
 __device__ __forceinline__ void sym3_inverse(const double v[6], double inv[6]) {
     const double c00 = v[3] * v[5] - v[4] * v[4];
@@ -207,11 +206,12 @@ __device__ __forceinline__ void load_lane(const Problem& P, int obs, bool valid,
 #pragma unroll
     for (int k = 0; k < 6; ++k) o.Jp[k] = 0.f;
     if (!valid) return;
-    o.cam = P.obs_cam[obs];
-    o.f = P.cam_free[o.cam];
+    o.cam = __ldg(P.obs_cam + obs);
+    o.f = __ldg(P.cam_free + o.cam);
     const CamPre c = P.pre[o.cam];
+    const double2 uv = __ldg(reinterpret_cast<const double2*>(P.obs_uv) + obs);
     double Jc[12], Jp[6];
-    obs_eval<true>(c, X, P.obs_uv[2 * obs], P.obs_uv[2 * obs + 1], P.fx, P.fy, o.r, Jc, Jp, o.xy);
+    obs_eval<true>(c, X, uv.x, uv.y, P.fx, P.fy, o.r, Jc, Jp, o.xy);
     if (o.f >= 0) {
 #pragma unroll
         for (int k = 0; k < 12; ++k) o.Jc[k] = static_cast<float>(Jc[k]);
@@ -220,20 +220,23 @@ __device__ __forceinline__ void load_lane(const Problem& P, int obs, bool valid,
     for (int k = 0; k < 6; ++k) o.Jp[k] = static_cast<float>(Jp[k]);
 }
 
-// per-point normal-equation pieces: V (damped), V^-1, g_p — reduced over the whole track
+// per-point normal-equation pieces: V (damped), V^-1, g_p — reduced over the whole track (observations beg..end-1 in
+// chunks of 32, one per lane).  `first` keeps the lane's observation of the first chunk; cost_lane adds the lane's share
+// of 1/2 sum r^2.
 // kFocal: also wf = Wf = sum Jf^T Jp (2x3) and fstat = sum xp^2, sum yp^2, sum xp r0, sum yp r1 over the track.
-// A template parameter, not a run-time flag: the extra accumulators cost the constant-focal kernel 70 registers
-// (118 -> 188, one CTA per SM instead of two) when they were merely branched around.
+// A template parameter, not a run-time flag: the extra accumulators cost the constant-focal kernel 70 registers when they
+// were merely branched around.
 template <bool kFocal = false>
-__device__ __forceinline__ void point_pass1(const Problem& P, int p, int beg, int end, int lane, const double X[3],
+__device__ __forceinline__ void point_pass1(const Problem& P, int beg, int end, int lane, const double X[3],
                                             double inv_radius, double Vinv[6], double gp[3], LaneObs& first,
-                                            double* wf = nullptr, double* fstat = nullptr) {
+                                            double& cost_lane, double* wf = nullptr, double* fstat = nullptr) {
     double v[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
     double w6[6] = {0, 0, 0, 0, 0, 0}, f4[4] = {0, 0, 0, 0};
     for (int base = beg; base < end; base += 32) {
         LaneObs o;
         load_lane(P, base + lane, base + lane < end, X, o);
         if (base == beg) first = o;
+        cost_lane += 0.5 * (o.r[0] * o.r[0] + o.r[1] * o.r[1]);
         const double j0 = o.Jp[0], j1 = o.Jp[1], j2 = o.Jp[2], j3 = o.Jp[3], j4 = o.Jp[4], j5 = o.Jp[5];
         v[0] += j0 * j0 + j3 * j3; v[1] += j0 * j1 + j3 * j4; v[2] += j0 * j2 + j3 * j5;
         v[3] += j1 * j1 + j4 * j4; v[4] += j1 * j2 + j4 * j5; v[5] += j2 * j2 + j5 * j5;
@@ -241,8 +244,6 @@ __device__ __forceinline__ void point_pass1(const Problem& P, int p, int beg, in
         if (kFocal) {
             w6[0] += o.xy[0] * j0; w6[1] += o.xy[0] * j1; w6[2] += o.xy[0] * j2;
             w6[3] += o.xy[1] * j3; w6[4] += o.xy[1] * j4; w6[5] += o.xy[1] * j5;
-        }
-        if (kFocal) {
             f4[0] += o.xy[0] * o.xy[0]; f4[1] += o.xy[1] * o.xy[1];
             f4[2] += o.xy[0] * o.r[0];  f4[3] += o.xy[1] * o.r[1];
         }
@@ -265,335 +266,259 @@ __device__ __forceinline__ void point_pass1(const Problem& P, int p, int beg, in
 }
 
 // ------------------------------------------------------------------------------------------------ linearize + Schur
-// sys layout (fp64): S [n6*n6] | rhs [n6] | gc [n6] | udiag [n6] | scalars[8] (0: cost)
+constexpr int kStageStride = 25;     // floats per staged observation: Jc[12] | Jp[6] | Q[6] | local camera (odd: no bank conflicts)
 
-// Pass P — one warp per point: residuals + Jacobians of its observations (stored), damped V^-1 and g_p (stored),
-// cost and max |g_p|.
+// base[e] += v[e], e < 6, on shared memory.  sm_100 has no native fp32 shared-memory atomic add (atomicAdd compiles to an
+// LDS / FADD / ATOMS.CAST.SPIN loop per element, one after the other); here the six compare-and-swaps of a block row are
+// independent instructions in flight together, and only a lost race falls back to the loop.
+__device__ __forceinline__ void smem_add6(float* base, const float v[6]) {
+    unsigned int* b = reinterpret_cast<unsigned int*>(base);
+    float old[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) old[e] = *reinterpret_cast<volatile float*>(base + e);
+    unsigned int got[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) got[e] = atomicCAS(b + e, __float_as_uint(old[e]), __float_as_uint(old[e] + v[e]));
+#pragma unroll
+    for (int e = 0; e < 6; ++e)
+        if (got[e] != __float_as_uint(old[e])) atomicAdd(base + e, v[e]);
+}
+
+size_t fused_smem_bytes(int w_cap, int threads, bool focal) {
+    const size_t cv = focal ? 30 : 18;
+    const size_t nb = static_cast<size_t>(w_cap) * (w_cap + 1) / 2;
+    return static_cast<size_t>(w_cap) * cv * sizeof(double) + nb * kBlkStride * sizeof(float) +
+           static_cast<size_t>(threads / 32) * 32 * kStageStride * sizeof(float) + static_cast<size_t>(w_cap) * sizeof(int32_t) + 16;
+}
+
+// One CTA per tile (dynamic scheduler), one warp per point, one lane per observation / per camera pair.
 template <bool kFocal>
-__global__ void __launch_bounds__(256)
-point_pass_kernel(Problem P, double inv_radius, double* __restrict__ sys) {
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
-    const size_t n6 = static_cast<size_t>(P.n_free) * 6;
-    double* scal = sys + n6 * n6 + 3 * n6;
+__global__ void __launch_bounds__(256, 2)
+fused_linearize_kernel(Problem P, double inv_radius) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int CV = kFocal ? 30 : 18;         // per local camera: rhs[6] | gc[6] | udiag[6] (| border B [6][2])
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double* camacc = reinterpret_cast<double*>(smem_raw);
+    float* acc = reinterpret_cast<float*>(camacc + P.w_cap * CV);
+    float* stage = acc + (P.w_cap * (P.w_cap + 1) / 2) * kBlkStride + warp * 32 * kStageStride;
+    int32_t* lfree = reinterpret_cast<int32_t*>(acc + (P.w_cap * (P.w_cap + 1) / 2) * kBlkStride + nwarps * 32 * kStageStride);
+    int32_t* s_tile = lfree + P.w_cap;
+    double* tail = P.tail;
     double cost_local = 0.0, gpmax_local = 0.0;
-    double ff[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};        // focal block sums of this warp (lane 0): F00 F01 F11 rhsf0 rhsf1 gf0 gf1 uf0 uf1
-    constexpr bool focal = kFocal;
-    for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < P.n_pts; p += gridDim.x * wpb) {
-        const int beg = P.pt_start[p], end = P.pt_start[p + 1];
-        if (beg == end) {
-            if (focal && lane < 6) P.pt_Wf[6 * static_cast<size_t>(p) + lane] = 0.0;
-            continue;
-        }
-        const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
-        double Vinv[6], gp[3], Wf[6], fs[4];
-        LaneObs A;
-        point_pass1<kFocal>(P, p, beg, end, lane, X, inv_radius, Vinv, gp, A, Wf, fs);
-        if (focal) {
-            // T = Wf V^-1 (2x3);  F -= T Wf^T,  rhs_f += T g_p - g_f   (the point is eliminated from the focal block too)
-            if (lane < 6) P.pt_Wf[6 * static_cast<size_t>(p) + lane] = Wf[lane];
-            const double T0[3] = {Wf[0] * Vinv[0] + Wf[1] * Vinv[1] + Wf[2] * Vinv[2], Wf[0] * Vinv[1] + Wf[1] * Vinv[3] + Wf[2] * Vinv[4],
-                                  Wf[0] * Vinv[2] + Wf[1] * Vinv[4] + Wf[2] * Vinv[5]};
-            const double T1[3] = {Wf[3] * Vinv[0] + Wf[4] * Vinv[1] + Wf[5] * Vinv[2], Wf[3] * Vinv[1] + Wf[4] * Vinv[3] + Wf[5] * Vinv[4],
-                                  Wf[3] * Vinv[2] + Wf[4] * Vinv[4] + Wf[5] * Vinv[5]};
-            ff[0] += fs[0] - (T0[0] * Wf[0] + T0[1] * Wf[1] + T0[2] * Wf[2]);
-            ff[1] += -(T0[0] * Wf[3] + T0[1] * Wf[4] + T0[2] * Wf[5]);
-            ff[2] += fs[1] - (T1[0] * Wf[3] + T1[1] * Wf[4] + T1[2] * Wf[5]);
-            ff[3] += (T0[0] * gp[0] + T0[1] * gp[1] + T0[2] * gp[2]) - fs[2];
-            ff[4] += (T1[0] * gp[0] + T1[1] * gp[1] + T1[2] * gp[2]) - fs[3];
-            ff[5] += fs[2]; ff[6] += fs[3]; ff[7] += fs[0]; ff[8] += fs[1];
-        }
-        gpmax_local = fmax(gpmax_local, fmax(fabs(gp[0]), fmax(fabs(gp[1]), fabs(gp[2]))));
-        if (lane < 6) P.pt_Vinv[6 * static_cast<size_t>(p) + lane] = Vinv[lane];
-        if (lane < 3) P.pt_gp[3 * static_cast<size_t>(p) + lane] = gp[lane];
-        for (int base = beg; base < end; base += 32) {
-            if (base != beg) load_lane(P, base + lane, base + lane < end, X, A);
-            if (!A.valid) continue;
-            cost_local += 0.5 * (A.r[0] * A.r[0] + A.r[1] * A.r[1]);
-            const size_t o = static_cast<size_t>(base + lane);
-            float2* J2 = reinterpret_cast<float2*>(P.obs_J + o * 18);          // 72-byte rows are 8-byte aligned
+    double ff[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};        // focal block sums (lane-uniform): F00 F01 F11 rhsf0 rhsf1 gf0 gf1 uf0 uf1
+
+    for (;;) {
+        if (threadIdx.x == 0) *s_tile = atomicAdd(P.tile_counter, 1);
+        __syncthreads();
+        const int ti = *s_tile;
+        if (ti >= P.n_tiles) break;
+        const Tile T = P.tiles[ti];
+        const int nb = T.w * (T.w + 1) / 2;
+        for (int i = threadIdx.x; i < nb * kBlkStride; i += blockDim.x) acc[i] = 0.f;
+        for (int i = threadIdx.x; i < T.w * CV; i += blockDim.x) camacc[i] = 0.0;
+        for (int i = threadIdx.x; i < T.w; i += blockDim.x) lfree[i] = __ldg(P.cam_free + __ldg(P.tile_cams + T.cam_begin + i));
+        __syncthreads();
+        const bool split = (T.flags & kTileSplit) != 0, primary = (T.flags & kTilePrimary) != 0;
+
+        for (int d = T.pt_begin + warp; d < T.pt_end; d += nwarps) {
+            const int p = __ldg(P.pt_order + d);
+            const int beg = __ldg(P.pt_start + d), end = __ldg(P.pt_start + d + 1);
+            const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
+            double Vinv[6], gp[3], Wf[6], fs[4], cl = 0.0;
+            LaneObs A;
+            point_pass1<kFocal>(P, beg, end, lane, X, inv_radius, Vinv, gp, A, cl, Wf, fs);
+            if (primary) {
+                cost_local += cl;
+                gpmax_local = fmax(gpmax_local, fmax(fabs(gp[0]), fmax(fabs(gp[1]), fabs(gp[2]))));
+                if (kFocal) {
+                    // T = Wf V^-1 (2x3);  F -= T Wf^T,  rhs_f += T g_p - g_f   (the point is eliminated from the focal block too)
+                    if (lane < 6) P.pt_Wf[6 * static_cast<size_t>(d) + lane] = Wf[lane];
+                    const double T0[3] = {Wf[0] * Vinv[0] + Wf[1] * Vinv[1] + Wf[2] * Vinv[2], Wf[0] * Vinv[1] + Wf[1] * Vinv[3] + Wf[2] * Vinv[4],
+                                          Wf[0] * Vinv[2] + Wf[1] * Vinv[4] + Wf[2] * Vinv[5]};
+                    const double T1[3] = {Wf[3] * Vinv[0] + Wf[4] * Vinv[1] + Wf[5] * Vinv[2], Wf[3] * Vinv[1] + Wf[4] * Vinv[3] + Wf[5] * Vinv[4],
+                                          Wf[3] * Vinv[2] + Wf[4] * Vinv[4] + Wf[5] * Vinv[5]};
+                    ff[0] += fs[0] - (T0[0] * Wf[0] + T0[1] * Wf[1] + T0[2] * Wf[2]);
+                    ff[1] += -(T0[0] * Wf[3] + T0[1] * Wf[4] + T0[2] * Wf[5]);
+                    ff[2] += fs[1] - (T1[0] * Wf[3] + T1[1] * Wf[4] + T1[2] * Wf[5]);
+                    ff[3] += (T0[0] * gp[0] + T0[1] * gp[1] + T0[2] * gp[2]) - fs[2];
+                    ff[4] += (T1[0] * gp[0] + T1[1] * gp[1] + T1[2] * gp[2]) - fs[3];
+                    ff[5] += fs[2]; ff[6] += fs[3]; ff[7] += fs[0]; ff[8] += fs[1];
+                }
+            }
+            // ---- the observations this tile couples: all of them (at most 32), or groups A | B of a split point
+            int nA = end - beg, nB = 0, lcam;
+            if (!split) {
+                lcam = A.valid ? static_cast<int>(__ldg(P.obs_lcam + beg + lane)) : 0;
+            } else {
+                nA = T.sub_a1 - T.sub_a0; nB = T.sub_b1 - T.sub_b0;
+                const bool valid = lane < nA + nB;
+                const int o = beg + (lane < nA ? T.sub_a0 + lane : T.sub_b0 + lane - nA);
+                load_lane(P, o, valid, X, A);
+                lcam = lane;
+            }
+            // Q = Jp V^-1 (2x3) in fp32; staged with the Jacobians for the pair products
+            float Q[6];
+            {
+                const float v0 = static_cast<float>(Vinv[0]), v1 = static_cast<float>(Vinv[1]), v2 = static_cast<float>(Vinv[2]),
+                            v3 = static_cast<float>(Vinv[3]), v4 = static_cast<float>(Vinv[4]), v5 = static_cast<float>(Vinv[5]);
+                Q[0] = A.Jp[0] * v0 + A.Jp[1] * v1 + A.Jp[2] * v2; Q[1] = A.Jp[0] * v1 + A.Jp[1] * v3 + A.Jp[2] * v4;
+                Q[2] = A.Jp[0] * v2 + A.Jp[1] * v4 + A.Jp[2] * v5;
+                Q[3] = A.Jp[3] * v0 + A.Jp[4] * v1 + A.Jp[5] * v2; Q[4] = A.Jp[3] * v1 + A.Jp[4] * v3 + A.Jp[5] * v4;
+                Q[5] = A.Jp[3] * v2 + A.Jp[4] * v4 + A.Jp[5] * v5;
+            }
+            if (A.valid) {
+                float* s = stage + lane * kStageStride;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) J2[k] = make_float2(A.Jc[2 * k], A.Jc[2 * k + 1]);
+                for (int k = 0; k < 12; ++k) s[k] = A.Jc[k];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) J2[6 + k] = make_float2(A.Jp[2 * k], A.Jp[2 * k + 1]);
-            reinterpret_cast<double2*>(P.obs_r)[o] = make_double2(A.r[0], A.r[1]);
+                for (int k = 0; k < 6; ++k) { s[12 + k] = A.Jp[k]; s[18 + k] = Q[k]; }
+                s[24] = __int_as_float(A.f >= 0 ? lcam : -1);
+            }
+            __syncwarp();
+            // ---- per observation: diagonal block U - Y W^T = Jc^T (I - Q Jp^T) Jc, rhs, g_c, diag U (not for the cross tiles A x B)
+            if (A.valid && A.f >= 0 && nB == 0) {
+                const double m00 = static_cast<double>(Q[0]) * A.Jp[0] + static_cast<double>(Q[1]) * A.Jp[1] + static_cast<double>(Q[2]) * A.Jp[2];
+                const double m01 = static_cast<double>(Q[0]) * A.Jp[3] + static_cast<double>(Q[1]) * A.Jp[4] + static_cast<double>(Q[2]) * A.Jp[5];
+                const double m11 = static_cast<double>(Q[3]) * A.Jp[3] + static_cast<double>(Q[4]) * A.Jp[4] + static_cast<double>(Q[5]) * A.Jp[5];
+                const float n00 = static_cast<float>(1.0 - m00), n01 = static_cast<float>(-m01), n11 = static_cast<float>(1.0 - m11);
+                float T0[6], T1[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { T0[j] = n00 * A.Jc[j] + n01 * A.Jc[6 + j]; T1[j] = n01 * A.Jc[j] + n11 * A.Jc[6 + j]; }
+                float* blk = acc + (lcam * (lcam + 1) / 2 + lcam) * kBlkStride;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    float row[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) row[j] = A.Jc[i] * T0[j] + A.Jc[6 + i] * T1[j];
+                    smem_add6(blk + 6 * i, row);
+                }
+                const double q0 = Q[0] * gp[0] + Q[1] * gp[1] + Q[2] * gp[2] - A.r[0];
+                const double q1 = Q[3] * gp[0] + Q[4] * gp[1] + Q[5] * gp[2] - A.r[1];
+                double* ca = camacc + lcam * CV;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const double j0 = A.Jc[i], j1 = A.Jc[6 + i];
+                    atomicAdd(ca + i, j0 * q0 + j1 * q1);
+                    atomicAdd(ca + 6 + i, j0 * A.r[0] + j1 * A.r[1]);
+                    atomicAdd(ca + 12 + i, j0 * j0 + j1 * j1);
+                }
+                if (kFocal) {
+                    // border B_c = Jc^T Jf - Y Wf^T = Jc^T (Jf - Q Wf^T),  Jf = diag(xp, yp)
+                    const double g00 = Q[0] * Wf[0] + Q[1] * Wf[1] + Q[2] * Wf[2], g01 = Q[0] * Wf[3] + Q[1] * Wf[4] + Q[2] * Wf[5];
+                    const double g10 = Q[3] * Wf[0] + Q[4] * Wf[1] + Q[5] * Wf[2], g11 = Q[3] * Wf[3] + Q[4] * Wf[4] + Q[5] * Wf[5];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const double j0 = A.Jc[i], j1 = A.Jc[6 + i];
+                        atomicAdd(ca + 18 + 2 * i, j0 * (A.xy[0] - g00) - j1 * g10);
+                        atomicAdd(ca + 18 + 2 * i + 1, -j0 * g01 + j1 * (A.xy[1] - g11));
+                    }
+                }
+            }
+            // ---- per camera pair (x < y): block (x, y) -= Jc_x^T (Q_x Jp_y^T) Jc_y
+            const int npairs = nB > 0 ? nA * nB : nA * (nA - 1) / 2;
+            for (int base = 0; base < npairs; base += 32) {
+                const int q = base + lane;
+                if (q < npairs) {
+                    int x, y;
+                    if (nB > 0) {
+                        x = q / nB; y = nA + (q - x * nB);
+                    } else {
+                        y = static_cast<int>((1.0f + sqrtf(1.0f + 8.0f * static_cast<float>(q))) * 0.5f);
+                        while (y * (y - 1) / 2 > q) --y;
+                        while ((y + 1) * y / 2 <= q) ++y;
+                        x = q - y * (y - 1) / 2;
+                    }
+                    const float* sx = stage + x * kStageStride;
+                    const float* sy = stage + y * kStageStride;
+                    const int lx = __float_as_int(sx[24]), ly = __float_as_int(sy[24]);
+                    if (lx >= 0 && ly >= 0) {
+                        const float m00 = sx[18] * sy[12] + sx[19] * sy[13] + sx[20] * sy[14];
+                        const float m01 = sx[18] * sy[15] + sx[19] * sy[16] + sx[20] * sy[17];
+                        const float m10 = sx[21] * sy[12] + sx[22] * sy[13] + sx[23] * sy[14];
+                        const float m11 = sx[21] * sy[15] + sx[22] * sy[16] + sx[23] * sy[17];
+                        float T0[6], T1[6];
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            const float c0 = sy[j], c1 = sy[6 + j];
+                            T0[j] = -(m00 * c0 + m01 * c1);
+                            T1[j] = -(m10 * c0 + m11 * c1);
+                        }
+                        float* blk = acc + (ly * (ly + 1) / 2 + lx) * kBlkStride;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                            const float a0 = sx[i], a1 = sx[6 + i];
+                            float row[6];
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) row[j] = a0 * T0[j] + a1 * T1[j];
+                            smem_add6(blk + 6 * i, row);
+                        }
+                    }
+                }
+            }
+            __syncwarp();          // the staging area is rewritten for the next point
         }
+        __syncthreads();
+        // ---- flush the tile: 6x6 blocks with vector reductions, camera vectors with fp64 reductions
+        const int32_t* slots = P.tile_slots + T.slot_begin;
+        for (int u = threadIdx.x; u < nb * 9; u += blockDim.x) {
+            const int b = u / 9, q4 = u - 9 * b;
+            const int slot = __ldg(slots + b);
+            if (slot < 0) continue;
+            const float* a = acc + b * kBlkStride + 4 * q4;
+            atomicAdd(reinterpret_cast<float4*>(P.sblk + static_cast<size_t>(slot) * 36) + q4, make_float4(a[0], a[1], a[2], a[3]));
+        }
+        for (int u = threadIdx.x; u < T.w * CV; u += blockDim.x) {
+            const int l = u / CV, e = u - l * CV;
+            const int f = lfree[l];
+            if (f < 0) continue;
+            double* dst;
+            if (e < 6) dst = tail + P.tl.rhs + f * 6 + e;
+            else if (e < 12) dst = tail + P.tl.gc + f * 6 + (e - 6);
+            else if (e < 18) dst = tail + P.tl.udiag + f * 6 + (e - 12);
+            else dst = tail + (((e - 18) & 1) ? P.tl.B1 : P.tl.B0) + f * 6 + ((e - 18) >> 1);
+            atomicAdd(dst, camacc[u]);
+        }
+        __syncthreads();
     }
+    // ---- scalars: one fp64 atomic per CTA
     __shared__ double sh_c[8], sh_g[8];
     cost_local = warp_sum(cost_local);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) gpmax_local = fmax(gpmax_local, __shfl_xor_sync(0xffffffffu, gpmax_local, o));
-    if (lane == 0) { sh_c[threadIdx.x >> 5] = cost_local; sh_g[threadIdx.x >> 5] = gpmax_local; }
+    gpmax_local = warp_max(gpmax_local);
+    if (lane == 0) { sh_c[warp] = cost_local; sh_g[warp] = gpmax_local; }
     __syncthreads();
-    if (focal) {       // 9 fp64 atomics per CTA into the focal slots behind the scalars
+    if (kFocal) {
         __shared__ double sh_f[8][9];
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) sh_f[threadIdx.x >> 5][k] = ff[k];
+            for (int k = 0; k < 9; ++k) sh_f[warp][k] = ff[k];
         }
         __syncthreads();
         if (threadIdx.x < 9) {
             double v = 0.0;
-            for (int k = 0; k < wpb; ++k) v += sh_f[k][threadIdx.x];
-            atomicAdd(scal + 8 + 2 * n6 + threadIdx.x, v);
+            for (int k = 0; k < nwarps; ++k) v += sh_f[k][threadIdx.x];
+            atomicAdd(tail + P.tl.ff + threadIdx.x, v);
         }
     }
     if (threadIdx.x == 0) {
         double c = 0.0, g = 0.0;
-        for (int k = 0; k < wpb; ++k) { c += sh_c[k]; g = fmax(g, sh_g[k]); }
-        atomicAdd(&scal[0], c);          // one fp64 atomic per CTA (cost only)
+        for (int k = 0; k < nwarps; ++k) { c += sh_c[k]; g = fmax(g, sh_g[k]); }
+        atomicAdd(tail + P.tl.scal, c);
         // max of non-negative doubles == max of their bit patterns
-        atomicMax(reinterpret_cast<unsigned long long*>(P.gpmax_bits), static_cast<unsigned long long>(__double_as_longlong(g)));
+        atomicMax(reinterpret_cast<unsigned long long*>(tail + P.tl.gpm + P.gpm_slot), static_cast<unsigned long long>(__double_as_longlong(g)));
     }
 }
 
-__device__ __forceinline__ void load_obs_J(const float* __restrict__ obs_J, int o, float Jc[12], float Jp[6]) {
-    const float2* J2 = reinterpret_cast<const float2*>(obs_J + static_cast<size_t>(o) * 18);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { const float2 v = __ldg(J2 + k); Jc[2 * k] = v.x; Jc[2 * k + 1] = v.y; }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { const float2 v = __ldg(J2 + 6 + k); Jp[2 * k] = v.x; Jp[2 * k + 1] = v.y; }
-}
-// W = Jc^T Jp (6x3), Y = W V^-1 (6x3) with the symmetric V^-1 = (v0 v1 v2 / v1 v3 v4 / v2 v4 v5)
-__device__ __forceinline__ void make_WY(const float Jc[12], const float Jp[6], const float vi[6], float W[18], float Y[18]) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) W[3 * i + k] = Jc[i] * Jp[k] + Jc[6 + i] * Jp[3 + k];
-        Y[3 * i + 0] = W[3 * i] * vi[0] + W[3 * i + 1] * vi[1] + W[3 * i + 2] * vi[2];
-        Y[3 * i + 1] = W[3 * i] * vi[1] + W[3 * i + 1] * vi[3] + W[3 * i + 2] * vi[4];
-        Y[3 * i + 2] = W[3 * i] * vi[2] + W[3 * i + 1] * vi[4] + W[3 * i + 2] * vi[5];
-    }
-}
-
-// Pass C — one CTA per free camera: diagonal block U_c - sum Y W^T, rhs_c, g_c, diag U_c over the camera's observations.
-__global__ void __launch_bounds__(256)
-camera_diag_kernel(Problem P, double* __restrict__ sys) {
-    const int f = blockIdx.x;
-    if (f >= P.n_free) return;
+// Dense fp64 copy of the block-sparse S for the dense Cholesky: upper block triangle, row-major (= the column-major lower
+// triangle cuSOLVER reads), Marquardt damping max(diag U, 1e-6) / radius added on the diagonal.  S must be zeroed.
+__global__ void expand_dense_kernel(Problem P, double inv_radius, double* __restrict__ S) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P.n_blocks * 36) return;
+    const int b = idx / 36, e = idx - 36 * b, i = e / 6, j = e - 6 * i;
+    const int fa = __ldg(P.blk_row + b), fb = __ldg(P.blk_col + b);
     const size_t n6 = static_cast<size_t>(P.n_free) * 6;
-    double acc[54];                      // 36 block | 6 rhs | 6 gc | 6 udiag
-#pragma unroll
-    for (int k = 0; k < 54; ++k) acc[k] = 0.0;
-    const int beg = P.cam_obs_start[f], end = P.cam_obs_start[f + 1];
-    for (int idx = beg + threadIdx.x; idx < end; idx += blockDim.x) {
-        const int o = __ldg(P.cam_obs_list + idx);
-        const int p = __ldg(P.obs_pt + o);
-        float Jc[12], Jp[6], vi[6], W[18], Y[18];
-        load_obs_J(P.obs_J, o, Jc, Jp);
-        double gp[3];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) vi[k] = static_cast<float>(__ldg(P.pt_Vinv + 6 * static_cast<size_t>(p) + k));
-#pragma unroll
-        for (int k = 0; k < 3; ++k) gp[k] = __ldg(P.pt_gp + 3 * static_cast<size_t>(p) + k);
-        const double2 r = __ldg(reinterpret_cast<const double2*>(P.obs_r) + o);
-        make_WY(Jc, Jp, vi, W, Y);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const double jr = static_cast<double>(Jc[i]) * r.x + static_cast<double>(Jc[6 + i]) * r.y;
-            acc[36 + i] += Y[3 * i] * gp[0] + Y[3 * i + 1] * gp[1] + Y[3 * i + 2] * gp[2] - jr;
-            acc[42 + i] += jr;
-            acc[48 + i] += static_cast<double>(Jc[i] * Jc[i] + Jc[6 + i] * Jc[6 + i]);
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const float u = Jc[i] * Jc[j] + Jc[6 + i] * Jc[6 + j];
-                const float yw = Y[3 * i] * W[3 * j] + Y[3 * i + 1] * W[3 * j + 1] + Y[3 * i + 2] * W[3 * j + 2];
-                acc[6 * i + j] += static_cast<double>(u - yw);
-            }
-        }
-    }
-    __shared__ double sh[8][54];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 54; ++k) {
-        const double v = warp_sum(acc[k]);
-        if (lane == 0) sh[warp][k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 54) {
-        double v = 0.0;
-        for (int w = 0; w < (blockDim.x >> 5); ++w) v += sh[w][threadIdx.x];
-        const int k = threadIdx.x;
-        double* S = sys;
-        double* rhs = S + n6 * n6;
-        if (k < 36) S[(static_cast<size_t>(f) * 6 + k / 6) * n6 + static_cast<size_t>(f) * 6 + k % 6] = v;
-        else if (k < 42) rhs[f * 6 + (k - 36)] = v;
-        else if (k < 48) rhs[n6 + f * 6 + (k - 42)] = v;           // gc
-        else rhs[2 * n6 + f * 6 + (k - 48)] = v;                   // udiag
-    }
-}
-
-// Pass F (refine_focal only) — one CTA per free camera: the 6 x 2 border block that couples the camera with the shared
-// focal block, B_c = sum_obs (Jc^T Jf - Y Wf_p^T), Jf = diag(xp, yp) recovered from the stored Jacobian
-// (Jc[3] = fx/pz, Jc[5] = -fx xp/pz;  Jc[10] = fy/pz, Jc[11] = -fy yp/pz).  Stored as two columns B0 | B1 behind the
-// scalars of the system buffer.
-__global__ void __launch_bounds__(256)
-camera_focal_border_kernel(Problem P, double* __restrict__ sys) {
-    const int f = blockIdx.x;
-    if (f >= P.n_free) return;
-    const size_t n6 = static_cast<size_t>(P.n_free) * 6;
-    double acc[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) acc[k] = 0.0;
-    const int beg = P.cam_obs_start[f], end = P.cam_obs_start[f + 1];
-    for (int idx = beg + threadIdx.x; idx < end; idx += blockDim.x) {
-        const int o = __ldg(P.cam_obs_list + idx);
-        const int p = __ldg(P.obs_pt + o);
-        float Jc[12], Jp[6], vi[6], W[18], Y[18], wf[6];
-        load_obs_J(P.obs_J, o, Jc, Jp);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) vi[k] = static_cast<float>(__ldg(P.pt_Vinv + 6 * static_cast<size_t>(p) + k));
-#pragma unroll
-        for (int k = 0; k < 6; ++k) wf[k] = static_cast<float>(__ldg(P.pt_Wf + 6 * static_cast<size_t>(p) + k));
-        make_WY(Jc, Jp, vi, W, Y);
-        const float xp = -Jc[5] / Jc[3], yp = -Jc[11] / Jc[10];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            acc[2 * i] += static_cast<double>(Jc[i] * xp - (Y[3 * i] * wf[0] + Y[3 * i + 1] * wf[1] + Y[3 * i + 2] * wf[2]));
-            acc[2 * i + 1] += static_cast<double>(Jc[6 + i] * yp - (Y[3 * i] * wf[3] + Y[3 * i + 1] * wf[4] + Y[3 * i + 2] * wf[5]));
-        }
-    }
-    __shared__ double sh[8][12];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) {
-        const double v = warp_sum(acc[k]);
-        if (lane == 0) sh[warp][k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 12) {
-        double v = 0.0;
-        for (int w = 0; w < (blockDim.x >> 5); ++w) v += sh[w][threadIdx.x];
-        double* B = sys + n6 * n6 + 3 * n6 + 8;
-        B[(threadIdx.x & 1) * n6 + static_cast<size_t>(f) * 6 + (threadIdx.x >> 1)] = v;
-    }
-}
-
-// Pass B — one CTA (4 warps) per non-empty camera-pair block (fa < fb): - sum over co-observing points of Y_a W_b^T.
-// The tuples of a block are spread over the 128 threads (block-stride), summed in fp32 registers, reduced by warp
-// shuffles and combined across the four warps in a fixed order: plain stores, deterministic.  The first version gave a
-// whole block to ONE warp (grid = all n_free^2 blocks, most of them empty): ~2500 busy warps with ~1000 tuples each
-// were bound by the latency of the dependent gathers (ncu: sm throughput 11 %, L2 22 %; 418 of the 540 us of a
-// linearisation at configs[3], profiles/r01b_k2_ncu_summary.txt).
-constexpr int kPairBlockThreads = 128;
-__global__ void __launch_bounds__(kPairBlockThreads)
-pair_block_kernel(Problem P, double* __restrict__ sys) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t n6 = static_cast<size_t>(P.n_free) * 6;
-    __shared__ float part[kPairBlockThreads / 32][36];
-    for (int bi = blockIdx.x; bi < P.n_blk_list; bi += gridDim.x) {
-        const int b = __ldg(P.blk_list + bi);
-        const int beg = __ldg(P.blk_start + b), end = __ldg(P.blk_start + b + 1);
-        float acc[36];
-#pragma unroll
-        for (int k = 0; k < 36; ++k) acc[k] = 0.f;
-        for (int idx = beg + threadIdx.x; idx < end; idx += kPairBlockThreads) {
-            const int2 t = __ldg(P.blk_tuples + idx);
-            const int p = __ldg(P.obs_pt + t.x);
-            float Jca[12], Jpa[6], Jcb[12], Jpb[6], vi[6], W[18], Y[18];
-            load_obs_J(P.obs_J, t.x, Jca, Jpa);
-            load_obs_J(P.obs_J, t.y, Jcb, Jpb);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) vi[k] = static_cast<float>(__ldg(P.pt_Vinv + 6 * static_cast<size_t>(p) + k));
-            make_WY(Jca, Jpa, vi, W, Y);
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const float w0 = Jcb[j] * Jpb[0] + Jcb[6 + j] * Jpb[3];
-                const float w1 = Jcb[j] * Jpb[1] + Jcb[6 + j] * Jpb[4];
-                const float w2 = Jcb[j] * Jpb[2] + Jcb[6 + j] * Jpb[5];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) acc[6 * i + j] -= Y[3 * i] * w0 + Y[3 * i + 1] * w1 + Y[3 * i + 2] * w2;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 36; ++k) {
-            float v = acc[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) part[warp][k] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x < 36) {
-            const int k = threadIdx.x;
-            float v = part[0][k];
-#pragma unroll
-            for (int w = 1; w < kPairBlockThreads / 32; ++w) v += part[w][k];
-            const int fa = b / P.n_free, fb = b - fa * P.n_free;
-            sys[(static_cast<size_t>(fa) * 6 + k / 6) * n6 + static_cast<size_t>(fb) * 6 + (k % 6)] = static_cast<double>(v);
-        }
-        __syncthreads();
-    }
-}
-
-// list of the camera-pair blocks that have tuples (order irrelevant: one CTA owns one block)
-__global__ void compact_blocks_kernel(const int32_t* __restrict__ blk_start, long long nblk, int32_t* __restrict__ list,
-                                      int32_t* __restrict__ counter) {
-    for (long long b = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; b < nblk;
-         b += static_cast<long long>(gridDim.x) * blockDim.x)
-        if (blk_start[b + 1] > blk_start[b]) list[atomicAdd(counter, 1)] = static_cast<int32_t>(b);
-}
-
-// ---- structure building (once per problem)
-// count / fill the co-observation tuples of every camera pair; mode 0 counts, mode 1 fills using cursors
-__global__ void pair_tuples_kernel(Problem P, int mode, int32_t* __restrict__ blk_count_or_cursor, int2* __restrict__ tuples_out) {
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n_pts; p += gridDim.x * blockDim.x) {
-        const int beg = P.pt_start[p], end = P.pt_start[p + 1];
-        for (int a = beg; a < end; ++a) {
-            const int fa = P.cam_free[P.obs_cam[a]];
-            if (fa < 0) continue;
-            for (int b = beg; b < end; ++b) {
-                if (b == a) continue;
-                const int fb = P.cam_free[P.obs_cam[b]];
-                if (fb < 0 || !(fa < fb)) continue;          // upper block triangle; same-camera pairs are not expected
-                const long long blk = static_cast<long long>(fa) * P.n_free + fb;
-                if (mode == 0) atomicAdd(&blk_count_or_cursor[blk], 1);
-                else {
-                    const int slot = atomicAdd(&blk_count_or_cursor[blk], 1);
-                    tuples_out[slot] = make_int2(a, b);
-                }
-            }
-        }
-    }
-}
-// single-block exclusive scan of int32 counts (n up to a few million) into out[0..n]; also copies the starts into cursor[]
-__global__ void __launch_bounds__(1024) scan_i32_kernel(const int32_t* __restrict__ counts, long long n, int32_t* __restrict__ out,
-                                                        int32_t* __restrict__ cursor) {
-    __shared__ int warp_sums[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (long long base = 0; base < n; base += blockDim.x) {
-        const long long i = base + threadIdx.x;
-        const int v = (i < n) ? counts[i] : 0;
-        int incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const int ws = warp_sums[lane];
-            int wincl = ws;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, wincl, o); if (lane >= o) wincl += y; }
-            warp_sums[lane] = wincl - ws;
-        }
-        __syncthreads();
-        const int excl = carry + warp_sums[warp] + incl - v;
-        if (i < n) { out[i] = excl; cursor[i] = excl; }
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[n] = carry;
-}
-
-// S_ii += max(udiag_i, 1e-6) / radius  (after the all-reduce), and mirror nothing: the solver reads one triangle.
-__global__ void damp_diagonal_kernel(double* __restrict__ sys, int n6, double inv_radius) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n6) return;
-    const double* udiag = sys + static_cast<size_t>(n6) * n6 + 2 * static_cast<size_t>(n6);
-    sys[static_cast<size_t>(i) * n6 + i] += fmax(udiag[i], 1e-6) * inv_radius;
+    double v = static_cast<double>(P.sblk[idx]);
+    if (fa == fb && i == j) v += fmax(P.tail[P.tl.udiag + fa * 6 + i], 1e-6) * inv_radius;
+    S[(static_cast<size_t>(fa) * 6 + i) * n6 + static_cast<size_t>(fb) * 6 + j] = v;
 }
 
 // ------------------------------------------------------------------------------------------------ back-substitution
@@ -605,16 +530,17 @@ backsub_kernel(Problem P, double inv_radius, const double* __restrict__ dc /*[n_
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     double acc_model = 0.0, acc_dp = 0.0, acc_x = 0.0;
-    for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < P.n_pts; p += gridDim.x * wpb) {
-        const int beg = P.pt_start[p], end = P.pt_start[p + 1];
+    for (int d = blockIdx.x * wpb + (threadIdx.x >> 5); d < P.n_pts; d += gridDim.x * wpb) {
+        const int p = P.pt_order[d];
+        const int beg = P.pt_start[d], end = P.pt_start[d + 1];
         const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
         if (beg == end) {
             if (lane == 0) { pts_new[3 * p] = X[0]; pts_new[3 * p + 1] = X[1]; pts_new[3 * p + 2] = X[2]; }
             continue;
         }
-        double Vinv[6], gp[3];
+        double Vinv[6], gp[3], unused = 0.0;
         LaneObs A;
-        point_pass1(P, p, beg, end, lane, X, inv_radius, Vinv, gp, A);
+        point_pass1(P, beg, end, lane, X, inv_radius, Vinv, gp, A, unused);
         // shared focal block: dc holds (d fx, d fy) behind the camera steps
         const bool focal = P.refine_focal != 0;
         const double df0 = focal ? dc[static_cast<size_t>(P.n_free) * 6] : 0.0, df1 = focal ? dc[static_cast<size_t>(P.n_free) * 6 + 1] : 0.0;
@@ -626,8 +552,8 @@ backsub_kernel(Problem P, double inv_radius, const double* __restrict__ dc /*[n_
                 double jd0 = 0.0, jd1 = 0.0;
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
-                    const double d = dc[A.f * 6 + i];
-                    jd0 += A.Jc[i] * d; jd1 += A.Jc[6 + i] * d;
+                    const double dd = dc[A.f * 6 + i];
+                    jd0 += A.Jc[i] * dd; jd1 += A.Jc[6 + i] * dd;
                 }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) t[k] += A.Jp[k] * jd0 + A.Jp[3 + k] * jd1;
@@ -636,7 +562,7 @@ backsub_kernel(Problem P, double inv_radius, const double* __restrict__ dc /*[n_
 #pragma unroll
         for (int k = 0; k < 3; ++k) t[k] = gp[k] + warp_sum(t[k]);
         if (focal) {
-            const double* wf = P.pt_Wf + 6 * static_cast<size_t>(p);
+            const double* wf = P.pt_Wf + 6 * static_cast<size_t>(d);
 #pragma unroll
             for (int k = 0; k < 3; ++k) t[k] += wf[k] * df0 + wf[3 + k] * df1;
         }
@@ -658,8 +584,8 @@ backsub_kernel(Problem P, double inv_radius, const double* __restrict__ dc /*[n_
                 if (A.f >= 0) {
 #pragma unroll
                     for (int i = 0; i < 6; ++i) {
-                        const double d = dc[A.f * 6 + i];
-                        jd0 += A.Jc[i] * d; jd1 += A.Jc[6 + i] * d;
+                        const double dd = dc[A.f * 6 + i];
+                        jd0 += A.Jc[i] * dd; jd1 += A.Jc[6 + i] * dd;
                     }
                 }
                 acc_model -= A.r[0] * jd0 + A.r[1] * jd1 + 0.5 * (jd0 * jd0 + jd1 * jd1);
@@ -687,7 +613,6 @@ __global__ void update_cams_kernel(const double* __restrict__ cams, const int32_
     cams_new[i] = cams[i] + (f >= 0 ? dc[f * 6 + k] : 0.0);
 }
 
-// rhs -> double column used by the solver;  also negative step bookkeeping helpers
 __global__ void copy_kernel(const double* __restrict__ src, double* __restrict__ dst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
@@ -706,7 +631,7 @@ cudaError_t ba_launch_evaluate(const Problem& P, double* r_out, float* J_out, do
     if (P.n_obs <= 0) return cudaSuccess;
     int grid = (P.n_obs + 255) / 256;
     if (grid > num_sms * 8) grid = num_sms * 8;
-    evaluate_kernel<<<grid, 256, 0, st>>>(P.pre, P.pts, P.obs_uv, P.obs_cam, P.obs_pt, P.n_obs, P.fx, P.fy, r_out, J_out, cost);
+    evaluate_kernel<<<grid, 256, 0, st>>>(P, r_out, J_out, cost);
     return cudaGetLastError();
 }
 cudaError_t ba_launch_track_errors(const Problem& P, double* err, int num_sms, cudaStream_t st) {
@@ -716,46 +641,25 @@ cudaError_t ba_launch_track_errors(const Problem& P, double* err, int num_sms, c
     track_error_kernel<<<grid, 256, 0, st>>>(P, err);
     return cudaGetLastError();
 }
-cudaError_t ba_launch_linearize(const Problem& P, double inv_radius, double* sys, int num_sms, cudaStream_t st) {
-    if (P.n_pts <= 0) return cudaSuccess;
-    int grid = (P.n_pts + 7) / 8;
-    if (grid > num_sms * 8) grid = num_sms * 8;
-    if (P.refine_focal) point_pass_kernel<true><<<grid, 256, 0, st>>>(P, inv_radius, sys);
-    else point_pass_kernel<false><<<grid, 256, 0, st>>>(P, inv_radius, sys);
-    if (P.n_free > 0) {
-        camera_diag_kernel<<<P.n_free, 256, 0, st>>>(P, sys);
-        if (P.refine_focal) camera_focal_border_kernel<<<P.n_free, 256, 0, st>>>(P, sys);
-        if (P.n_blk_list > 0) {
-            const int g2 = P.n_blk_list < num_sms * 64 ? P.n_blk_list : num_sms * 64;
-            pair_block_kernel<<<g2, kPairBlockThreads, 0, st>>>(P, sys);
-        }
-    }
+size_t ba_fused_smem_bytes(int w_cap, bool focal) { return fused_smem_bytes(w_cap, 256, focal); }
+// The system buffers (tail, tile counter, sblk) must be zero.
+cudaError_t ba_launch_linearize(const Problem& P, double inv_radius, int num_sms, cudaStream_t st) {
+    if (P.n_tiles <= 0) return cudaSuccess;
+    const size_t smem = fused_smem_bytes(P.w_cap, 256, P.refine_focal != 0);
+    cudaError_t e;
+    if (P.refine_focal) e = cudaFuncSetAttribute(fused_linearize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    else e = cudaFuncSetAttribute(fused_linearize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+    const int grid = P.n_tiles < num_sms * per_sm ? P.n_tiles : num_sms * per_sm;
+    if (P.refine_focal) fused_linearize_kernel<true><<<grid, 256, smem, st>>>(P, inv_radius);
+    else fused_linearize_kernel<false><<<grid, 256, smem, st>>>(P, inv_radius);
     return cudaGetLastError();
 }
-// structure lists: counts -> starts (+cursor) -> tuples.  blk_start has n_free^2 + 1 entries.
-cudaError_t ba_launch_count_tuples(const Problem& P, int32_t* counts, int num_sms, cudaStream_t st) {
-    if (P.n_pts <= 0 || P.n_free <= 0) return cudaSuccess;
-    pair_tuples_kernel<<<num_sms * 4, 256, 0, st>>>(P, 0, counts, nullptr);
-    return cudaGetLastError();
-}
-cudaError_t ba_launch_scan_tuples(const int32_t* counts, long long n, int32_t* starts, int32_t* cursor, cudaStream_t st) {
-    scan_i32_kernel<<<1, 1024, 0, st>>>(counts, n, starts, cursor);
-    return cudaGetLastError();
-}
-cudaError_t ba_launch_fill_tuples(const Problem& P, int32_t* cursor, int2* tuples, int num_sms, cudaStream_t st) {
-    if (P.n_pts <= 0 || P.n_free <= 0) return cudaSuccess;
-    pair_tuples_kernel<<<num_sms * 4, 256, 0, st>>>(P, 1, cursor, tuples);
-    return cudaGetLastError();
-}
-cudaError_t ba_launch_compact_blocks(const int32_t* blk_start, long long nblk, int32_t* list, int32_t* counter, int num_sms,
-                                     cudaStream_t st) {
-    if (nblk <= 0) return cudaSuccess;
-    compact_blocks_kernel<<<num_sms * 4, 256, 0, st>>>(blk_start, nblk, list, counter);
-    return cudaGetLastError();
-}
-cudaError_t ba_launch_damp(double* sys, int n6, double inv_radius, cudaStream_t st) {
-    if (n6 <= 0) return cudaSuccess;
-    damp_diagonal_kernel<<<(n6 + 127) / 128, 128, 0, st>>>(sys, n6, inv_radius);
+cudaError_t ba_launch_expand_dense(const Problem& P, double inv_radius, double* S, cudaStream_t st) {
+    if (P.n_blocks <= 0) return cudaSuccess;
+    const int n = P.n_blocks * 36;
+    expand_dense_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, inv_radius, S);
     return cudaGetLastError();
 }
 cudaError_t ba_launch_backsub(const Problem& P, double inv_radius, const double* dc, double* pts_new, double* out,

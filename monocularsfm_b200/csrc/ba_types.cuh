@@ -15,33 +15,68 @@ struct CamPre {
     double pad;
 };
 
+// A tile = a run of points (device order) that together touch at most w_cap cameras.  One CTA linearises one tile at
+// a time and accumulates the tile's share of the reduced camera system in shared memory: the upper triangle of 6x6
+// blocks over the tile's LOCAL camera list, flushed once per tile into the global block-sparse S.
+// A point observed by more than 32 cameras is split into several single-point tiles, each restricted to the pairs between
+// two groups of at most 16 of its observations (sub_*): the per-warp staging holds 32 observations.
+struct Tile {
+    int32_t pt_begin, pt_end;     // device points [pt_begin, pt_end)
+    int32_t cam_begin, w;         // local cameras: tile_cams[cam_begin .. cam_begin + w), ascending global camera index
+    int32_t slot_begin;           // tile_slots[slot_begin + lb (lb + 1) / 2 + la] (la <= lb): global block slot or -1
+    int32_t sub_a0, sub_a1;       // split tiles: observation positions [a0, a1) of the point form group A ...
+    int32_t sub_b0, sub_b1;       //              ... and [b0, b1) group B (empty: pairs inside A, plus A's diagonal blocks)
+    int32_t flags;                // kTileSplit | kTilePrimary
+    int32_t pad[2];
+};
+constexpr int32_t kTileSplit = 1;      // single-point tile with an observation subset
+constexpr int32_t kTilePrimary = 2;    // this tile accounts the point's cost / gradient maximum (every normal tile; one split tile per point)
+constexpr int kBlkStride = 37;         // 36 floats of a 6x6 block + 1: conflict-free shared-memory banks across blocks
+constexpr int kMaxWCap = 40;           // local cameras per tile (shared-memory accumulator = w (w+1)/2 blocks)
+
+// Offsets (in doubles) into the fp64 "tail" of the system: everything of the reduced system that is not a 6x6 block.
+struct TailLayout {
+    int32_t scal;      // [8]   0: cost
+    int32_t gpm;       // [R]   max |g_p| of every rank (own slot written, the sum all-reduce fills the others)
+    int32_t rhs, gc, udiag;   // [n6] each
+    int32_t B0, B1, ff;       // shared focal block: two border columns [n6] each, ff[16]
+    int32_t total;
+};
+
 // SoA view of a BundleData (include/Optimizer/BundleData.h:19-65) flattened for the device.
+// "Device order": points are reordered so that neighbours share cameras (pt_order), the observations of a point are
+// contiguous and sorted by camera.  pts / cams stay in the caller's order.
 struct Problem {
     int32_t n_cams, n_pts, n_obs, n_free;
     double fx, fy;
     const CamPre* pre;          // [n_cams]
-    const double* pts;          // [n_pts][3]
-    const double* obs_uv;       // [n_obs][2], centred by (cx, cy)
-    const int32_t* obs_cam;     // [n_obs]
-    const int32_t* obs_pt;      // [n_obs], non-decreasing
-    const int32_t* pt_start;    // [n_pts+1] CSR over observations
+    const double* pts;          // [n_pts][3]   caller's order
+    const double* obs_uv;       // [n_obs][2]   device order, centred by (cx, cy)
+    const int32_t* obs_cam;     // [n_obs]      device order
+    const int32_t* obs_pt;      // [n_obs]      device order: the caller's point index
+    const int32_t* obs_orig;    // [n_obs]      device order -> the caller's observation index
+    const uint8_t* obs_lcam;    // [n_obs]      index of the camera in the local list of the observation's tile
+    const int32_t* pt_start;    // [n_pts+1]    CSR over device-ordered observations, indexed by DEVICE point
+    const int32_t* pt_order;    // [n_pts]      device point -> caller's point index
     const int32_t* cam_free;    // [n_cams] index among the free cameras or -1 (constant pose)
-    unsigned long long* gpmax_bits;   // max |g_p| as the bit pattern of a non-negative double
-    // ---- gather structures (built once per problem: the sparsity pattern does not change between LM iterations)
-    const int32_t* cam_obs_start;   // [n_free+1] CSR: observations of every free camera
-    const int32_t* cam_obs_list;    // [#observations of free cameras]
-    const int32_t* blk_start;       // [n_free*n_free+1] CSR over camera-pair blocks (fa < fb): co-observing tuples
-    const int2* blk_tuples;         // (obs_a, obs_b) with cam_free[obs_cam[obs_a]] = fa < fb = cam_free[obs_cam[obs_b]]
-    const int32_t* blk_list;        // [n_blk_list] indices fa*n_free+fb of the blocks with at least one tuple
-    int32_t n_blk_list;
-    // ---- per-linearisation intermediates
-    float* obs_J;                   // [n_obs][18]  Jc (2x6) | Jp (2x3), fp32
-    double* obs_r;                  // [n_obs][2]
-    double* pt_Vinv;                // [n_pts][6]   inverse of the damped point block (symmetric)
-    double* pt_gp;                  // [n_pts][3]
+    // ---- tiling + block structure (built once per problem: the sparsity pattern does not change between LM iterations)
+    const Tile* tiles;
+    int32_t n_tiles;
+    const int32_t* tile_cams;
+    const int32_t* tile_slots;
+    int32_t w_cap;                  // max local cameras of any tile
+    int32_t n_blocks;               // non-empty 6x6 blocks of the upper block triangle (diagonal included)
+    const int32_t* blk_row;         // [n_blocks] free-camera row fa
+    const int32_t* blk_col;         // [n_blocks] free-camera column fb >= fa
+    // ---- the system (per linearisation)
+    float* sblk;                    // [n_blocks][36]  fp32 blocks of S = U - sum Y W^T (undamped)
+    double* tail;                   // TailLayout
+    TailLayout tl;
+    int32_t gpm_slot;               // this rank's slot in tail[gpm ..]
+    int32_t* tile_counter;          // dynamic tile scheduler
     // ---- shared focal block (BundleAutoDiffCostFunction, CeresBundleOptimizer.cpp:76-121; refine_focal_length)
     int32_t refine_focal;           // 0: (fx, fy) constant; 1: one shared 2-parameter block, bordering the camera system
-    double* pt_Wf;                  // [n_pts][6]   Wf = sum_obs Jf^T Jp (2x3), Jf = d r / d (fx, fy) = diag(xp, yp)
+    double* pt_Wf;                  // [n_pts][6] (device point)  Wf = sum_obs Jf^T Jp (2x3), Jf = d r / d (fx, fy) = diag(xp, yp)
 };
 
 }  // namespace ba

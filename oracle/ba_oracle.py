@@ -527,6 +527,31 @@ def make_problem(n_cams, n_pts, mean_track, seed, noise_px=0.5, perturb=True):
 
 
 # --------------------------------------------------------------------------------------------- C restatement
+def make_long_track_problem(seed=3, n_cams=90, n_pts=300):
+    """Ring problem with shuffled observation order inside every point, two constant cameras, a few very long tracks
+    (up to 70 views: split tiles) and one point without observations."""
+    P = make_problem(n_cams, n_pts, 6, seed)
+    rng = np.random.default_rng(seed)
+    oc, op, uv = [], [], []
+    for p in range(n_pts):
+        sel = np.nonzero(P["obs_pt"] == p)[0]
+        if p == 17:
+            continue                                        # a point nobody observes
+        cams = P["obs_cam"][sel]
+        if p % 40 == 5:                                     # long track: 33..70 cameras
+            k = int(rng.integers(33, 71))
+            cams = (cams[0] + np.arange(k)) % n_cams
+        cams = rng.permutation(cams)
+        oc.append(cams); op.append(np.full(len(cams), p))
+    oc = np.concatenate(oc).astype(np.int32); op = np.concatenate(op).astype(np.int32)
+    uv = residuals_only(P["cams"], P["pts"], np.zeros((len(oc), 2)), oc, op, P["fx"], P["fy"]) + rng.normal(0, 0.5, (len(oc), 2))
+    P = dict(P, obs_cam=oc, obs_pt=op, obs_uv=uv)
+    P["cam_const"] = P["cam_const"].copy()
+    P["cam_const"][7] = 1
+    return P
+
+
+
 def c_oracle():
     """ctypes handle of oracle/libba_oracle.so (built by oracle/Makefile) or None."""
     import ctypes as C

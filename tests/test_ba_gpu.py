@@ -119,6 +119,103 @@ def test_medium_problem_vs_oracle(ctx):
     ba.close()
 
 
+def _sys_path_bench():
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench
+    return bench
+
+
+@pytest.mark.parametrize("shape", ["configs3", "configs4"])
+def test_full_size_system_vs_c_oracle(ctx, shape):
+    """BASELINE configs[3] (128 cams / 50k points / ~500k observations) and the configs[4] shapes (1329 cams / 542k points /
+    ~5M observations): cost, S, rhs of one linearisation against oracle/ba_oracle.c (float64 Jets + dense Schur), and the
+    residuals / Jacobians of a 200k-observation sample against it.  fp32 block products: 1e-5 of the largest entry."""
+    bench = _sys_path_bench()
+    lib = bo.c_oracle()
+    if lib is None:
+        pytest.skip("oracle/libba_oracle.so not built")
+    P = bench.make_ba_problem(128, 50000, 10.0, 4321) if shape == "configs3" else bench.make_ba_problem(1329, 542000, 9.2, 4321)
+    ba = _create(ctx, P)
+    st = ba.structure()
+    assert st["n_free"] == len(P["cams"]) - 1 and st["n_tiles"] > 0 and st["w_cap"] <= 40
+    So, rhso, costo, _ = bo.c_linearize(P, 1e-4, lib)
+    S, rhs, gc, cost = ba.linearize(1e-4)
+    assert abs(cost - costo) <= 1e-9 * costo
+    smax = np.abs(So).max()
+    assert np.abs(S - So).max() <= 1e-5 * smax, np.abs(S - So).max() / smax
+    assert np.abs(rhs - rhso).max() <= 1e-5 * np.abs(rhso).max(), np.abs(rhs - rhso).max() / np.abs(rhso).max()
+    # the structure the device reports is the structure of the oracle's S (no block missed, none invented beyond zeros)
+    nf = st["n_free"]
+    nzo = np.abs(So).reshape(nf, 6, nf, 6).max(axis=(1, 3)) > 0
+    nz = np.abs(S).reshape(nf, 6, nf, 6).max(axis=(1, 3)) > 0
+    assert (nzo <= nz).all() and int(np.triu(nz).sum()) <= st["n_blocks"]
+    del S, So
+    r, J, c2 = ba.evaluate()
+    assert abs(c2 - costo) <= 1e-9 * costo
+    sel = np.random.default_rng(0).choice(len(P["obs_cam"]), min(200000, len(P["obs_cam"])), replace=False)
+    sel.sort()
+    ro, Jo = bo.residual_jacobian_jets(P["cams"], P["pts"], P["obs_uv"][sel], P["obs_cam"][sel], P["obs_pt"][sel], P["fx"], P["fy"])
+    np.testing.assert_allclose(r[sel], ro, rtol=0, atol=1e-9)
+    scale = np.abs(Jo).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(J[sel] - Jo) <= 1e-5 * scale).all()
+    ba.close()
+
+
+def test_long_tracks_and_shuffled_observations(ctx):
+    """Tracks of up to 70 views (split tiles), observations of a point in arbitrary camera order, two constant cameras, a point
+    without observations: S, rhs, gc and the LM solve against the Python oracle."""
+    P = bo.make_long_track_problem()
+    ba = _create(ctx, P)
+    r, J = bo.residual_jacobian_jets(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
+    rg, Jg, cost = ba.evaluate()
+    np.testing.assert_allclose(rg, r, rtol=0, atol=1e-9)
+    U, gc, V, gp, W = bo.build_normal_equations(r, J, P["obs_cam"], P["obs_pt"], len(P["cams"]), len(P["pts"]), P["cam_const"])
+    So, rhso, _, fmap = bo.schur_reduce(U, gc, V, gp, W, P["obs_cam"], P["obs_pt"], P["cam_const"], 1e-4)
+    S, rhs, gcg, cost = ba.linearize(1e-4)
+    assert np.abs(S - So).max() <= 1e-5 * np.abs(So).max(), np.abs(S - So).max() / np.abs(So).max()
+    assert np.abs(rhs - rhso).max() <= 1e-5 * np.abs(rhso).max()
+    gco = gc[fmap >= 0].ravel()
+    assert np.abs(gcg - gco).max() <= 1e-5 * np.abs(gco).max()
+    ref = bo.lm_solve(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"])
+    s = ba.solve()
+    assert s["termination"] == 0 and ref["converged"]
+    assert abs(s["final_cost"] - ref["final_cost"]) <= 1e-5 * ref["final_cost"], (s["final_cost"], ref["final_cost"])
+    cams, pts = ba.get_params()
+    np.testing.assert_array_equal(pts[17], P["pts"][17])          # the unobserved point does not move
+    ba.close()
+
+
+def test_local_ba_shape_and_small_problem_tolerances(ctx):
+    """The shape Map::GetLocalBAData builds (src/Reconstruction/Map.cpp:1000-1096): at most 6 cameras, one of them constant,
+    only the observations inside the set — and the tightened tolerances CeresBundleOptimizer.cpp:279-291 applies below 10
+    cameras (tolerances / 10, iterations x 2)."""
+    P = bo.make_problem(6, 400, 4, 21)
+    ba = _create(ctx, P)
+    o = ba.default_options()
+    assert o.max_num_iterations == 200
+    assert abs(o.function_tolerance - 1e-7) < 1e-20 and abs(o.gradient_tolerance - 1e-11) < 1e-24 and abs(o.parameter_tolerance - 1e-9) < 1e-22
+    o10 = _create(ctx, bo.make_problem(10, 30, 3, 2))
+    assert o10.default_options().max_num_iterations == 100 and o10.default_options().function_tolerance == 1e-6
+    o10.close()
+    r, J = bo.residual_jacobian_jets(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
+    U, gc, V, gp, W = bo.build_normal_equations(r, J, P["obs_cam"], P["obs_pt"], 6, len(P["pts"]), P["cam_const"])
+    So, rhso, _, _ = bo.schur_reduce(U, gc, V, gp, W, P["obs_cam"], P["obs_pt"], P["cam_const"], 1e-4)
+    S, rhs, _, _ = ba.linearize(1e-4)
+    assert S.shape == (30, 30)
+    assert np.abs(S - So).max() <= 1e-5 * np.abs(So).max() and np.abs(rhs - rhso).max() <= 1e-5 * np.abs(rhso).max()
+    ref = bo.lm_solve(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"],
+                      max_iters=200, function_tol=1e-7, gradient_tol=1e-11, parameter_tol=1e-9)
+    s = ba.solve()                                                 # default options = the tightened block
+    assert s["termination"] == 0 and ref["converged"]
+    assert abs(s["final_cost"] - ref["final_cost"]) <= 1e-5 * ref["final_cost"]
+    cams, pts = ba.get_params()
+    assert np.abs(cams - ref["cams"]).max() <= 1e-4 and np.abs(pts - ref["pts"]).max() <= 1e-3
+    ba.close()
+
+
 def test_bad_problem_is_rejected(ctx):
     P = bo.make_problem(4, 10, 3, 0)
     bad = P["obs_pt"].copy()

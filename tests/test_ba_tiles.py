@@ -1,0 +1,189 @@
+"""CPU tests of the B-path structure analysis (monocularsfm_b200/csrc/ba_tiles.hpp): device order, tiles, split tiles for
+long tracks, block structure of the reduced camera system — and a numpy emulation of what the fused linearisation kernel
+does with them (per-tile local accumulators indexed by local camera pairs, flushed through the slot tables), checked
+against the oracle's dense Schur elimination.  The CUDA kernel itself is checked in tests/test_ba_gpu.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import ba_oracle as bo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("tiling") / "libtiling.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                    os.path.join(ROOT, "tests", "tools", "tiling_harness.cpp")], check=True)
+    lib = C.CDLL(so)
+    ip = C.POINTER(C.c_int32)
+    lib.tiling_build.restype = C.c_int
+    lib.tiling_build.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, C.c_int, C.c_int, C.c_int, C.c_longlong, ip]
+    lib.tiling_fetch.restype = None
+    lib.tiling_fetch.argtypes = [ip, ip, ip, C.POINTER(C.c_uint8), ip, ip, ip, ip, ip]
+    return lib
+
+
+def run_tiling(lib, P, w_cap=32, max_pts=64, max_work=1 << 15):
+    oc = np.ascontiguousarray(P["obs_cam"], np.int32)
+    op = np.ascontiguousarray(P["obs_pt"], np.int32)
+    const = np.asarray(P["cam_const"]).astype(bool)
+    cam_free = -np.ones(len(const), np.int32)
+    cam_free[~const] = np.arange((~const).sum(), dtype=np.int32)
+    ip = C.POINTER(C.c_int32)
+    sizes = np.zeros(5, np.int32)
+    rc = lib.tiling_build(len(const), len(P["pts"]), len(oc), oc.ctypes.data_as(ip), op.ctypes.data_as(ip),
+                          cam_free.ctypes.data_as(ip), int((~const).sum()), w_cap, max_pts, max_work, sizes.ctypes.data_as(ip))
+    if rc:
+        return None
+    n_tiles, n_tc, n_marks, n_blocks, w_max = [int(x) for x in sizes]
+    T = {"pt_order": np.zeros(len(P["pts"]), np.int32), "pt_start": np.zeros(len(P["pts"]) + 1, np.int32),
+         "obs_perm": np.zeros(len(oc), np.int32), "obs_lcam": np.zeros(len(oc), np.uint8),
+         "tiles": np.zeros((n_tiles, 12), np.int32), "tile_cams": np.zeros(n_tc, np.int32),
+         "tile_slots": np.zeros(n_marks, np.int32), "blk_row": np.zeros(n_blocks, np.int32),
+         "blk_col": np.zeros(n_blocks, np.int32), "w_max": w_max, "cam_free": cam_free}
+    lib.tiling_fetch(T["pt_order"].ctypes.data_as(ip), T["pt_start"].ctypes.data_as(ip), T["obs_perm"].ctypes.data_as(ip),
+                     T["obs_lcam"].ctypes.data_as(C.POINTER(C.c_uint8)), T["tiles"].ctypes.data_as(ip),
+                     T["tile_cams"].ctypes.data_as(ip), T["tile_slots"].ctypes.data_as(ip), T["blk_row"].ctypes.data_as(ip),
+                     T["blk_col"].ctypes.data_as(ip))
+    return T
+
+
+long_track_problem = bo.make_long_track_problem
+
+
+def tri(la, lb):
+    return lb * (lb + 1) // 2 + la
+
+
+@pytest.mark.parametrize("which", ["ring", "long"])
+def test_tiling_invariants(harness, which):
+    P = bo.make_problem(40, 500, 8, 1) if which == "ring" else long_track_problem()
+    T = run_tiling(harness, P)
+    n_pts, n_obs = len(P["pts"]), len(P["obs_cam"])
+    assert sorted(T["pt_order"].tolist()) == list(range(n_pts))
+    assert sorted(T["obs_perm"].tolist()) == list(range(n_obs))
+    oc, op = P["obs_cam"][T["obs_perm"]], P["obs_pt"][T["obs_perm"]]
+    for d in range(n_pts):
+        s, e = T["pt_start"][d], T["pt_start"][d + 1]
+        assert (op[s:e] == T["pt_order"][d]).all()
+        assert (np.diff(oc[s:e]) > 0).all()                  # sorted by camera, no duplicates
+    assert T["w_max"] <= 32
+    covered = np.zeros(n_pts, int)
+    pair_count = {}
+    for t in T["tiles"]:
+        pb, pe, cb, w, sb, a0, a1, b0, b1, flags = [int(x) for x in t[:10]]
+        cams = T["tile_cams"][cb:cb + w]
+        assert w <= 32 and (np.diff(cams) > 0).all()
+        if flags & 1:                                        # split: one point, groups of <= 16 observations
+            assert pe == pb + 1 and a1 - a0 <= 16 and b1 - b0 <= 16
+            s = T["pt_start"][pb]
+            sel = list(range(s + a0, s + a1)) + list(range(s + b0, s + b1))
+            assert (oc[sel] == cams).all()
+            if flags & 2:
+                covered[pb] += 1
+            A, B = list(range(a0, a1)), list(range(b0, b1))
+            prs = [(x, y) for x in A for y in B] if B else [(x, y) for x in A for y in A if x <= y]
+            for x, y in prs:
+                pair_count[(pb, x, y)] = pair_count.get((pb, x, y), 0) + 1
+        else:
+            assert flags & 2
+            covered[pb:pe] += 1
+            for d in range(pb, pe):
+                s, e = T["pt_start"][d], T["pt_start"][d + 1]
+                assert e - s <= 32
+                assert (cams[T["obs_lcam"][s:e]] == oc[s:e]).all()
+    k = np.diff(T["pt_start"])
+    assert (covered[k > 0] == 1).all() and (covered[k == 0] == 0).all()
+    for d in np.nonzero(k > 32)[0]:                           # every pair (and diagonal) of a long track exactly once
+        kk = int(k[d])
+        assert all(pair_count.get((int(d), x, y), 0) == 1 for x in range(kk) for y in range(x, kk))
+    # block structure == co-observing free camera pairs (+ the full diagonal)
+    cf = T["cam_free"]
+    want = {(f, f) for f in range(int((cf >= 0).sum()))}
+    for d in range(n_pts):
+        f = cf[oc[T["pt_start"][d]:T["pt_start"][d + 1]]]
+        f = f[f >= 0]
+        want |= {(int(a), int(b)) for a in f for b in f if a <= b}
+    got = list(zip(T["blk_row"].tolist(), T["blk_col"].tolist()))
+    assert got == sorted(want)
+
+
+def test_duplicate_camera_rejected(harness):
+    P = bo.make_problem(6, 20, 3, 0)
+    oc = P["obs_cam"].copy()
+    oc[1] = oc[0]
+    assert run_tiling(harness, dict(P, obs_cam=oc)) is None
+
+
+@pytest.mark.parametrize("which", ["ring", "long"])
+def test_tile_accumulation_emulation_matches_dense_schur(harness, which):
+    """What fused_linearize_kernel computes, restated in numpy from the tiling tables: per tile a local block triangle over
+    the local cameras, block (x, y) -= Jc_x^T (Jp_x V^-1 Jp_y^T) Jc_y, diagonal += Jc^T (I - Jp V^-1 Jp^T) Jc, flushed to
+    the global block list through tile_slots.  Must equal the oracle's S, rhs."""
+    P = bo.make_problem(40, 500, 8, 1) if which == "ring" else long_track_problem()
+    T = run_tiling(harness, P)
+    inv_radius = 1e-4
+    r, J = bo.residual_jacobian_jets(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
+    U, gc, V, gp, W = bo.build_normal_equations(r, J, P["obs_cam"], P["obs_pt"], len(P["cams"]), len(P["pts"]), P["cam_const"])
+    So, rhso, _, _ = bo.schur_reduce(U, gc, V, gp, W, P["obs_cam"], P["obs_pt"], P["cam_const"], inv_radius)
+    cf = T["cam_free"]
+    nf = int((cf >= 0).sum())
+    perm = T["obs_perm"]
+    Jc, Jp, rr, oc = J[perm][:, :, :6], J[perm][:, :, 6:], r[perm], P["obs_cam"][perm]
+    sblk = np.zeros((len(T["blk_row"]), 6, 6))
+    rhs = np.zeros((nf, 6)); udiag = np.zeros((nf, 6))
+    for t in T["tiles"]:
+        pb, pe, cb, w, sb, a0, a1, b0, b1, flags = [int(x) for x in t[:10]]
+        lfree = cf[T["tile_cams"][cb:cb + w]]
+        acc = np.zeros((w * (w + 1) // 2, 6, 6))
+        camacc = np.zeros((w, 12))
+        for d in range(pb, pe):
+            s, e = int(T["pt_start"][d]), int(T["pt_start"][d + 1])
+            Vp = (Jp[s:e].transpose(0, 2, 1) @ Jp[s:e]).sum(0)
+            g = (Jp[s:e].transpose(0, 2, 1) @ rr[s:e, :, None]).sum(0)[:, 0]
+            Vp[np.arange(3), np.arange(3)] += np.maximum(np.diag(Vp), 1e-6) * inv_radius
+            Vi = np.linalg.inv(Vp)
+            if flags & 1:
+                sel = list(range(s + a0, s + a1)) + list(range(s + b0, s + b1))
+                lc = list(range(len(sel)))
+                nA, nB = a1 - a0, b1 - b0
+            else:
+                sel = list(range(s, e)); lc = T["obs_lcam"][s:e].tolist(); nA, nB = e - s, 0
+            Q = [Jp[o] @ Vi for o in sel]
+            if nB == 0:
+                for x, o in enumerate(sel):
+                    if cf[oc[o]] < 0:
+                        continue
+                    N = np.eye(2) - Q[x] @ Jp[o].T
+                    acc[tri(lc[x], lc[x])] += Jc[o].T @ N @ Jc[o]
+                    camacc[lc[x], :6] += Jc[o].T @ (Q[x] @ g - rr[o])
+                    camacc[lc[x], 6:] += (Jc[o] ** 2).sum(0)
+                prs = [(x, y) for y in range(nA) for x in range(y)]
+            else:
+                prs = [(x, nA + y) for x in range(nA) for y in range(nB)]
+            for x, y in prs:
+                if cf[oc[sel[x]]] < 0 or cf[oc[sel[y]]] < 0:
+                    continue
+                assert lc[x] < lc[y]
+                acc[tri(lc[x], lc[y])] -= Jc[sel[x]].T @ (Q[x] @ Jp[sel[y]].T) @ Jc[sel[y]]
+        slots = T["tile_slots"][sb:sb + w * (w + 1) // 2]
+        for b in range(len(slots)):
+            if slots[b] >= 0:
+                sblk[slots[b]] += acc[b]
+            else:
+                assert not acc[b].any()
+        for l in range(w):
+            if lfree[l] >= 0:
+                rhs[lfree[l]] += camacc[l, :6]; udiag[lfree[l]] += camacc[l, 6:]
+    S = np.zeros((6 * nf, 6 * nf))
+    for k, (fa, fb) in enumerate(zip(T["blk_row"], T["blk_col"])):
+        S[6 * fa:6 * fa + 6, 6 * fb:6 * fb + 6] = sblk[k]
+        S[6 * fb:6 * fb + 6, 6 * fa:6 * fa + 6] = sblk[k].T
+    S[np.arange(6 * nf), np.arange(6 * nf)] += np.maximum(udiag.ravel(), 1e-6) * inv_radius
+    assert np.abs(S - So).max() <= 1e-10 * np.abs(So).max()
+    assert np.abs(rhs.ravel() - rhso).max() <= 1e-9 * np.abs(rhso).max()

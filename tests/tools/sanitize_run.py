@@ -36,6 +36,15 @@ def main():
     s = ba.solve()
     assert s["termination"] == 0, s
     ba.close()
+    # long tracks (split tiles), shuffled observations, two constant cameras; with and without the shared focal block
+    P = bo.make_long_track_problem(n_cams=80, n_pts=120)
+    for focal in (False, True):
+        ba = ctx.ba_create(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"], refine_focal=focal)
+        ba.linearize(1e-4)
+        s2 = ba.solve()
+        assert s2["termination"] == 0, s2
+        ba.track_errors()
+        ba.close()
     ctx.close()
     print("sanitize workload ok", len(mt), "matches, BA", s["iterations"], "iterations")
 

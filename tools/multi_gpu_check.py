@@ -60,8 +60,8 @@ def main():
         ep = np.abs(cams_multi - cams_solo).max()
         print(f"BA sharded vs solo: S {eS:.2e} rhs {er:.2e} cost {abs(cost - cost1) / cost1:.2e} final {ec:.2e} "
               f"cams {ep:.2e} iters {s['iterations']}/{s1['iterations']} nres {s['num_residuals']}/{s1['num_residuals']}", flush=True)
-        # off-diagonal Schur blocks are summed in fp32 registers per rank before the fp64 all-reduce: 1e-7-level differences
-        ok &= eS < 1e-6 and er < 1e-6 and ec < 1e-9 and ep < 1e-6 and s["num_residuals"] == s1["num_residuals"] and s["termination"] == 0
+        # the 6x6 blocks are accumulated in fp32 (shared-memory tiles, fp32 reductions, fp32 all-reduce): 1e-7-level differences
+        ok &= eS < 1e-6 and er < 1e-6 and ec < 1e-7 and ep < 1e-5 and s["num_residuals"] == s1["num_residuals"] and s["termination"] == 0
         b1.close()
         solo.close()
     # ---- matching

@@ -38,13 +38,21 @@ def env_int(name, default):
 
 
 # ----------------------------------------------------------------------------------------------- synthetic data
-def make_descriptors_torch(n_img, n_desc, seed, device):
-    """SIFT-like (S) distribution of SURVEY §8d: |N(0,1)| vectors, L2-normalised to 512, clipped to 255, rounded;
-    image k>0 shares a planted 30 % of image 0's descriptors (random slots, +-2 noise)."""
+def make_descriptors_torch(n_img, n_desc, seed, device, distribution="S"):
+    """Synthetic descriptor sets of SURVEY 8d, generated on the device.
+    "S" SIFT-like: |N(0,1)| vectors, L2-normalised to 512, clipped to 255, rounded; image k>0 shares a planted 30 % of
+        image 0's descriptors (random slots, +-2 noise) so that the ratio / cross-check lists are non-trivial;
+    "D" dense overlap: the same with 90 % planted (most rows pass the ratio test: the worst case of the reverse pass);
+    "U" i.i.d. uniform bytes (almost nothing passes the ratio test)."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     out = torch.empty((n_img, n_desc, 128), dtype=torch.uint8, device=device)
+    if distribution == "U":
+        for k in range(n_img):
+            out[k] = torch.randint(0, 256, (n_desc, 128), generator=g, device=device, dtype=torch.int32).to(torch.uint8)
+        return out
+    frac = 0.9 if distribution == "D" else 0.3
     base = None
     for k in range(n_img):
         x = torch.randn((n_desc, 128), generator=g, device=device).abs_()
@@ -53,7 +61,7 @@ def make_descriptors_torch(n_img, n_desc, seed, device):
         if k == 0:
             base = x.clone()
         else:
-            m = int(0.3 * n_desc)
+            m = int(frac * n_desc)
             dst = torch.randperm(n_desc, generator=g, device=device)[:m]
             src = torch.randperm(n_desc, generator=g, device=device)[:m]
             noise = torch.randint(-2, 3, (m, 128), generator=g, device=device).float()
@@ -128,18 +136,30 @@ def make_ba_problem(n_cams, n_pts, mean_track, seed, noise_px=0.5):
             "fx": fx, "fy": fy}
 
 
-def bench_ba(ctx, args, rank, world, dist, dev, peaks, n_cams=None, n_pts=None, track=None, cpu_max_reps=20):
+def ceres_probe():
+    """Is the reference's real BA backend (Ceres) on this box?  (BASELINE.md section 3 prefers it over the restatement.)"""
+    import ctypes.util
+    found = ctypes.util.find_library("ceres")
+    ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref")) or os.path.isdir(os.path.join(ROOT, "oracle", "_ref"))
+    return {"ceres": found or "absent", "reference_build": "present" if ref else "absent (the reference needs OpenCV C++/Ceres/Eigen headers: DESIGN.md section 5)"}
+
+
+def bench_ba(ctx, args, rank, world, dist, dev, peaks, n_cams=None, n_pts=None, track=None, cpu_max_reps=20, tag="k2"):
     """BASELINE configs[3] by default: 128 cams / 50k points / ~500k observations (configs[4] shapes when called with
     1329 / 542k / 9.2).  One "BA iteration" = evaluate all residual blocks + Jacobians + Schur-eliminate onto the camera
-    system (+ the all-reduce when world > 1).  Returns a dict."""
+    system (+ the all-reduce when world > 1).  STRONG scaling: the same problem for every N, points sharded over the
+    ranks (monocularsfm_b200.sharding.shard_ba_problem), cameras replicated.  Returns a dict."""
     import torch
     from monocularsfm_b200.sharding import shard_ba_problem
     n_cams = n_cams or args.ba_cams
     n_pts = n_pts or args.ba_pts
     track = track or args.ba_track
-    P = make_ba_problem(n_cams, n_pts * world, track, 4321)          # weak scaling: points grow with N
+    P = make_ba_problem(n_cams, n_pts, track, 4321)
     L = shard_ba_problem(P, rank, world) if world > 1 else P
+    t0 = time.perf_counter()
     ba = ctx.ba_create(L["cams"], L["pts"], L["obs_uv"], L["obs_cam"], L["obs_pt"], L["cam_const"], L["fx"], L["fy"])
+    create_s = time.perf_counter() - t0
+    st = ba.structure()
     n_obs_total = len(P["obs_cam"])
     iters = max(10, args.steps * 4)
     for _ in range(3):
@@ -159,23 +179,36 @@ def bench_ba(ctx, args, rank, world, dist, dev, peaks, n_cams=None, n_pts=None, 
     ms = e0.elapsed_time(e1) / iters
     prof = ctx.prof_read()
     ctx.prof_enable(False)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    k_ms_local = prof["ba_schur"]["ms"] / max(1, prof["ba_schur"]["launches"])
+    comm_ms_local = prof["ba_comm"]["ms"] / max(1, prof["ba_comm"]["launches"]) if prof["ba_comm"]["launches"] else 0.0
+    t = torch.tensor([ms, k_ms_local, comm_ms_local], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0])
-    k_ms = prof["ba_schur"]["ms"] / max(1, prof["ba_schur"]["launches"])
-    n6 = 6 * ba.n_free
-    # algorithmic bytes of one launch on this rank (fp64 storage): 24 B/obs stream-in + parameters + reduced system write
-    alg_bytes = 24.0 * len(L["obs_cam"]) + 48.0 * len(L["cams"]) + 24.0 * len(L["pts"]) + 8.0 * (n6 * n6 + 3 * n6)
-    out = {"workload": f"BA {len(P['cams'])} cams / {len(P['pts'])} points / {n_obs_total} observations (all ranks)",
+    ms, k_ms, comm_ms = float(t[0]), float(t[1]), float(t[2])
+    # algorithmic bytes of one launch on this rank (SURVEY 8d, fp64 parameter / observation storage as resident here):
+    # 16 B (u, v) + 4 B camera index + 1 B local camera index per observation, 4 B point order + 24 B per point, 184 B per
+    # camera, and one write of the reduced system that exists: 144 B per non-empty 6x6 block + the fp64 tail
+    alg_bytes = 21.0 * len(L["obs_cam"]) + 28.0 * len(L["pts"]) + 184.0 * len(L["cams"]) + 144.0 * st["n_blocks"] + 8.0 * st["tail_f64"]
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        ent = tj.get(f"{n_cams}x{n_pts}")
+        if ent:
+            traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
+    ach = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None
+    out = {"workload": f"BA {len(P['cams'])} cams / {len(P['pts'])} points / {n_obs_total} observations, points sharded over {world} GPU(s)",
            "metric": "observations/s per BA iteration (evaluate + Jacobians + Schur reduction" + (" + all-reduce)" if world > 1 else ")"),
-           "value": n_obs_total / (ms * 1e-3), "unit": "observations/s", "ms_per_iteration": ms,
-           "kernel_ms": k_ms, "dtype": "f64 geometry / f32 block products / f64 accumulation",
-           "roofline": {"bound": "hbm", "kernel": "point_pass + camera_diag + pair_block (one linearisation)", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None,
-                        "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": (alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if k_ms else None, "traffic": None,
-                        "algorithmic_bytes": alg_bytes,
-                        "note": "gather kernels over L2-resident intermediates; the algorithmic bytes of this small problem are ~3 us of HBM time, so launch latency and gather latency dominate: see DESIGN.md B-path"}}
+           "value": n_obs_total / (ms * 1e-3), "unit": "observations/s", "ms_per_iteration": ms, "scaling": "strong",
+           "kernel_ms": k_ms, "allreduce_ms": comm_ms, "allreduce_message_bytes": st["system_bytes"] - 16,
+           "structure": st, "create_s": create_s,
+           "dtype": "f64 geometry and gradients / f32 6x6 block products and block accumulation",
+           "roofline": {"bound": "hbm", "kernel": "fused_linearize_kernel (one launch per linearisation)", "achieved": ach,
+                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (ach / peaks["hbm_gbs"]) if ach else None,
+                        "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes,
+                        "note": "the kernel is bound by issue slots (fp64 geometry + shared-memory compare-and-swap accumulation of "
+                                "the 6x6 products), not by HBM: see DESIGN.md B-path"}}
     # full LM solve (the call CeresBundelOptimizer::Optimize makes); the first solve pays one-time library initialisation
     # (cuSOLVER handle, lazy kernel loading), so it is repeated from the same start and the second one is reported
     cams0, pts0 = ba.get_params()
@@ -183,12 +216,27 @@ def bench_ba(ctx, args, rank, world, dist, dev, peaks, n_cams=None, n_pts=None, 
     summ = ba.solve()
     first_s = time.perf_counter() - t0
     ba.set_params(cams0, pts0)
+    if dist:
+        dist.barrier()
     t0 = time.perf_counter()
     summ = ba.solve()
     out["lm"] = {"iterations": summ["iterations"], "termination": summ["termination"], "initial_cost": summ["initial_cost"],
                  "final_cost": summ["final_cost"], "wall_s": time.perf_counter() - t0, "first_call_wall_s": first_s,
                  "linearize_s": summ["linearize_time_s"], "solve_backsub_eval_s": summ["solve_time_s"],
                  "rmse_px": float(np.sqrt(2 * summ["final_cost"] / max(1, summ["num_residuals"])))}
+    ba.close()
+    # end to end through the host-buffer C-ABI, as CeresBundelOptimizer::Optimize uses it: structure analysis + H2D of the
+    # problem, LM solve, D2H of the parameters
+    t0 = time.perf_counter()
+    ba2 = ctx.ba_create(L["cams"], L["pts"], L["obs_uv"], L["obs_cam"], L["obs_pt"], L["cam_const"], L["fx"], L["fy"])
+    s2 = ba2.solve()
+    ba2.get_params()
+    e2e_s = time.perf_counter() - t0
+    ba2.close()
+    out["e2e"] = {"wall_s": e2e_s, "observations_per_s_per_iteration": n_obs_total * s2["iterations"] / e2e_s,
+                  "h2d_bytes": int(L["cams"].nbytes + L["pts"].nbytes + L["obs_uv"].nbytes + 2 * L["obs_cam"].nbytes),
+                  "d2h_bytes": int(L["cams"].nbytes + L["pts"].nbytes),
+                  "what": "msfm_ba_create (host structure analysis + upload) + msfm_ba_solve + msfm_ba_get_params"}
     if rank == 0 and world == 1 and args.cpu_pairs > 0:
         from oracle import ba_oracle as bo
         lib = bo.c_oracle()
@@ -200,9 +248,8 @@ def bench_ba(ctx, args, rank, world, dist, dev, peaks, n_cams=None, n_pts=None, 
                 reps += 1
             out["cpu_baseline"] = {"value": n_obs_total * reps / tt, "unit": "observations/s", "cores": 1, "kind": "port",
                                    "sample": f"{reps} full evaluate+Schur passes of oracle/ba_oracle.c (float64 Jets + dense Schur, "
-                                             "1 thread like the reference's Ceres call, which never sets num_threads); Ceres "
-                                             "itself is not installed in this image"}
-    ba.close()
+                                             "1 thread like the reference's Ceres call, which never sets num_threads)",
+                                   **ceres_probe()}
     return out
 
 
@@ -280,30 +327,48 @@ def cpu_reference_pairs(descs_np, pairs, distance_ratio=0.8, f32=False):
     return time.perf_counter() - t0, nm
 
 
+def workload_of(args, world):
+    """The matching workload of an N-GPU run: BASELINE configs[1] on one GPU, configs[2] (ONE pair list, sharded) on several."""
+    n_img = args.images if args.images > 0 else (128 if world == 1 else 1329)
+    n = args.ndesc
+    P = n_img * (n_img - 1) // 2
+    name = (f"match {n_img} images x {n} descriptors, all {P} pairs (cross-check, ratio 0.8)"
+            + ("" if world == 1 else f", ONE pair list sharded over {world} GPUs"))
+    return n_img, n, P, name
+
+
+def reference_sample_pairs(args):
+    """Image pairs of the CPU sample per step: 32 unless the step count would push the arm beyond a few minutes
+    (~0.5 s per pair on 16 cores); never fewer than 8 per step."""
+    if args.cpu_pairs > 0:
+        return args.cpu_pairs
+    return int(max(8, min(32, 300 // max(1, args.steps + min(args.warmup, 1)))))
+
+
 def run_reference_arm(args, rank, world):
     """--impl reference: OpenCV+glue on the host cores, bounded sample per step (rank 0 only)."""
     if rank != 0:
         return
-    n_img, n = args.images, args.ndesc
-    sample_pairs = args.cpu_pairs
-    descs = make_descriptors_numpy(min(n_img, 2 * sample_pairs + 1), n, 1234)
+    n_img, n, P, name = workload_of(args, world)
+    sample_pairs = reference_sample_pairs(args)
+    descs = make_descriptors_numpy(sample_pairs + 1, n, 1234)
     pairs = [(k + 1, 0) for k in range(sample_pairs)]
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_pairs(descs, pairs[:1])
+        cpu_reference_pairs(descs, pairs[:2])
     t = 0.0
     for _ in range(args.steps):
         dt, _nm = cpu_reference_pairs(descs, pairs)
         t += dt
     val = args.steps * sample_pairs * float(n) * n / t
     cores = os.cpu_count() or 1
-    sample = (f"{sample_pairs} of the {n_img * (n_img - 1) // 2} image pairs per step ({n}x{n} u8 descriptors each), "
+    sample = (f"{sample_pairs} of the {P} image pairs per step ({n}x{n} u8 descriptors each), extrapolated linearly; "
               f"cv2 BFMatcher.knnMatch both directions + ratio + CrossCheck, cv2 threads={cores}")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"match {n_img} images x {n} descriptors, all pairs (cross-check, ratio 0.8)",
-                       "sampled_pairs_per_step": sample_pairs},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "config": {"workload": name, "distribution": "SIFT-like, 30% planted correspondences"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+                             **ceres_probe()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -319,9 +384,30 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def timed_resident(ctx, torch, dev, dist, pairs, opt, bufs, steps, warmup):
+    """`steps` passes over `pairs` with descriptors resident; returns (ms total on the library stream, matches of a pass)."""
+    d_off, d_mat, d_dst, capacity = bufs
+    total = 0
+    for _ in range(warmup):
+        total = ctx.match_pairs_dev(pairs, opt, d_off.data_ptr(), d_mat.data_ptr(), d_dst.data_ptr(), capacity)
+    ctx.sync()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        total = ctx.match_pairs_dev(pairs, opt, d_off.data_ptr(), d_mat.data_ptr(), d_dst.data_ptr(), capacity)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), total
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import monocularsfm_b200 as m
+    from monocularsfm_b200.sharding import shard_pairs
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
@@ -333,66 +419,69 @@ def run_ours(args, rank, world, local_rank):
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
 
-    n_img, n = args.images, args.ndesc
+    n_img, n, P_all, wl_name = workload_of(args, world)
     ctx = m.Context(local_rank)
     if dist:
-        # the library's own NCCL communicator (ncclAllReduce of the reduced camera system); id travels over the
+        # the library's own NCCL communicator (all-reduce of the reduced camera system); id travels over the
         # torch.distributed store
         uid = [ctx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(world, rank, uid[0])
+    # every rank holds ALL descriptors (1329 x 1 MiB replicated) and its share of the ONE pair list
     if args.cpu_data:      # profiling runs: keep torch's data-generation kernels out of the ncu launch list
-        descs = torch.from_numpy(make_descriptors_numpy(n_img, n, 1234 + rank)).to(dev)
+        descs = torch.from_numpy(make_descriptors_numpy(n_img, n, 1234)).to(dev)
     else:
-        descs = make_descriptors_torch(n_img, n, 1234 + rank, dev)       # [n_img, n, 128] u8, resident in HBM
+        descs = make_descriptors_torch(n_img, n, 1234, dev)              # [n_img, n, 128] u8, resident in HBM
     torch.cuda.synchronize()
-    pairs = all_pairs(n_img)
+    pairs_all = all_pairs(n_img)
+    pairs = np.ascontiguousarray(shard_pairs(pairs_all, rank, world)) if world > 1 else pairs_all
     P = len(pairs)
     opt = m.MatchOptions(0.8, -1.0, True, True)
-    capacity = int(P) * 4096
+    per_pair_cap = 4096 if P <= 20000 else 1280
+    capacity = int(P) * per_pair_cap + 65536
     d_off = torch.empty(P + 1, dtype=torch.int64, device=dev)
     d_mat = torch.empty((capacity, 2), dtype=torch.int32, device=dev)
     d_dst = torch.empty(capacity, dtype=torch.float32, device=dev)
-
-    def upload_resident():
-        for k in range(n_img):
-            ctx.upload_dev(k, descs[k].data_ptr(), n)
-
-    def step_resident():
-        return ctx.match_pairs_dev(pairs, opt, d_off.data_ptr(), d_mat.data_ptr(), d_dst.data_ptr(), capacity)
+    bufs = (d_off, d_mat, d_dst, capacity)
 
     # ---------------- device-resident throughput ("value")
-    upload_resident()
+    for k in range(n_img):
+        ctx.upload_dev(k, descs[k].data_ptr(), n)
     ctx.sync()
     sampler = ClockSampler(local_rank)
     sampler.start()                      # nvidia-smi needs a moment to come up: start before the warm-up steps
-    for _ in range(args.warmup):
-        total = step_resident()
-    ctx.sync()
+    timed_resident(ctx, torch, dev, None, pairs, opt, bufs, 0, args.warmup)
     sampler.mark()                       # only samples taken from here on (the timed region) are reported
     ctx.prof_enable(True)
     ctx.prof_reset()
     launches0 = ctx.launch_count
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        total = step_resident()
-    e1.record(stream)
-    torch.cuda.synchronize()
+    ms_total, total = timed_resident(ctx, torch, dev, dist, pairs, opt, bufs, args.steps, 0)
     if dist:
         dist.barrier()
     clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
     prof = ctx.prof_read()
     ctx.prof_enable(False)
     stats = ctx.match_stats()
 
-    # ---------------- end to end through the host-buffer C-ABI call ("e2e")
+    # ---------------- one sampled pair per step checked against the oracle (outside the timed region)
+    verify = None
+    if rank == 0 and not args.no_verify:
+        from oracle import match_oracle as mo
+        rng = np.random.default_rng(99)
+        off_h = d_off.cpu().numpy()
+        ok, checked = True, []
+        for p in rng.choice(P, size=min(P, max(1, args.steps)), replace=False):
+            i, j = int(pairs[p][0]), int(pairs[p][1])
+            got = d_mat[int(off_h[p]):int(off_h[p + 1])].cpu().numpy()
+            gd = d_dst[int(off_h[p]):int(off_h[p + 1])].cpu().numpy()
+            em, ed = mo.cv2_match_image_pair(descs[i].cpu().numpy(), descs[j].cpu().numpy(), 0.8, -1.0, True, True)
+            same = bool(np.array_equal(got, em) and np.array_equal(gd, ed))
+            ok &= same
+            checked.append([i, j, int(len(em)), same])
+        verify = {"pairs_checked_vs_cv2": checked, "bit_exact": ok}
+
+    # ---------------- end to end through the host-buffer C-ABI call ("e2e"), same number of steps
     host_descs = torch.empty((n_img, n, 128), dtype=torch.uint8, pin_memory=True)
     host_descs.copy_(descs)
     host_np = host_descs.numpy()
@@ -412,7 +501,7 @@ def run_ours(args, rank, world, local_rank):
         ctx._check(rc)
         return int(tot.value)
 
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = args.steps
     step_e2e()
     if dist:
         dist.barrier()
@@ -424,15 +513,58 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     h2d = n_img * n * 128 + pairs.nbytes
     d2h = (P + 1) * 8 + tot_e2e * 12 + 64
+    del host_descs, h_mat, h_dst
 
-    # ---------------- reduce over ranks (max time)
+    # ---------------- reduce over ranks (max time); per-rank times for the load imbalance
     times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    per_rank = [ms_total / args.steps]
     if dist:
+        gathered = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, times)
+        per_rank = [float(g[0]) / args.steps for g in gathered]
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_total_max, e2e_ms_max = float(times[0]), float(times[1])
-    work_per_step = float(P) * n * n * world              # descriptor pairs, each unordered image pair once
+    work_per_step = float(P_all) * n * n                  # descriptor pairs of the WHOLE job, each unordered image pair once
     value = work_per_step * args.steps / (ms_total_max * 1e-3)
     e2e_value = work_per_step * e2e_steps / (e2e_ms_max * 1e-3)
+
+    # ---------------- other distributions and the north_star target size (N = 1 only; descriptors resident, short runs)
+    dists_out, target = None, None
+    if world == 1 and not args.no_extra:
+        dists_out = {"S": {"value": value, "ms_per_step": ms_total_max / args.steps, "matches_per_step": int(total),
+                           "what": "SIFT-like, 30% planted (the headline)"}}
+        for tag, what in (("U", "i.i.d. uniform bytes"), ("D", "SIFT-like, 90% planted (dense overlap: most rows pass the ratio test)")):
+            dd = make_descriptors_torch(n_img, n, 4242, dev, tag)
+            for k in range(n_img):
+                ctx.upload_dev(k, dd[k].data_ptr(), n)
+            ms_d, tot_d = timed_resident(ctx, torch, dev, None, pairs, opt, bufs, 2, 1)
+            dists_out[tag] = {"value": work_per_step * 2 / (ms_d * 1e-3), "ms_per_step": ms_d / 2, "matches_per_step": int(tot_d),
+                              "rescans": ctx.match_stats()["rescans"], "what": what}
+            del dd
+    if world == 1 and not args.no_target:
+        # north_star's target: 1000 images x 8192, all 499 500 pairs, one pass, wall clock (descriptors resident)
+        del d_mat, d_dst, d_off
+        torch.cuda.empty_cache()
+        n_t = args.target_images
+        dt_ = make_descriptors_torch(n_t, n, 777, dev)
+        ctx.release_all()
+        for k in range(n_t):
+            ctx.upload_dev(k, dt_[k].data_ptr(), n)
+        pt = all_pairs(n_t)
+        cap_t = len(pt) * 1280 + 65536
+        t_off = torch.empty(len(pt) + 1, dtype=torch.int64, device=dev)
+        t_mat = torch.empty((cap_t, 2), dtype=torch.int32, device=dev)
+        ctx.sync()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tot_t = ctx.match_pairs_dev(pt, opt, t_off.data_ptr(), t_mat.data_ptr(), 0, cap_t)
+        ctx.sync()
+        wall = time.perf_counter() - t0
+        target = {"workload": f"match {n_t} images x {n} descriptors, all {len(pt)} pairs, one pass", "wall_s": wall,
+                  "value": float(len(pt)) * n * n / wall, "matches": int(tot_t)}
+        del t_mat, t_off, dt_
+        ctx.release_all()
+        torch.cuda.empty_cache()
 
     peaks = load_peaks()
     ba_out = None
@@ -442,9 +574,9 @@ def run_ours(args, rank, world, local_rank):
             ba_out = bench_ba(ctx, args, rank, world, dist, dev, peaks)
         except Exception as ex:                      # the matching headline must survive a BA failure
             ba_out = {"error": repr(ex)}
-        if world == 1 and not args.no_ba_large:
-            # the shapes north_star quotes its BA target on (BASELINE configs[4]: 1329 cams / 542k points / ~5M observations),
-            # on ONE GPU; the CPU port runs a single pass of it (~6 s)
+        if not args.no_ba_large:
+            # the shapes north_star quotes its BA target on (BASELINE configs[4]: 1329 cams / 542k points / ~5M observations);
+            # the CPU port runs a single pass of it (~6 s, N = 1 only)
             try:
                 ba_large = bench_ba(ctx, args, rank, world, dist, dev, peaks, 1329, 542000, 9.2, cpu_max_reps=1)
             except Exception as ex:
@@ -453,8 +585,8 @@ def run_ours(args, rank, world, local_rank):
         k1 = prof["match_tile"]
         k1_avg_s = (k1["ms"] / max(1, k1["launches"])) * 1e-3
         steps_launches = max(1, k1["launches"])
-        # algorithmic int8 ops of one K1 launch: 256 per descriptor pair, each unordered image pair once;
-        # the kernel executes twice that on the tensor cores (both directions, for the cross-check).
+        # algorithmic int8 ops of one K1 launch on this rank: 256 per descriptor pair, each unordered image pair once
+        # (SURVEY 8d); the kernel executes more on the tensor cores (forward + reverse pass for the cross-check).
         alg_ops_per_launch = float(P) * n * n * 256.0 * args.steps / steps_launches
         achieved = alg_ops_per_launch / k1_avg_s / 1e12 if k1_avg_s > 0 else 0.0
         peak_int8 = 2.0 * peaks["bf16_tflops_sustained"]
@@ -466,9 +598,9 @@ def run_ours(args, rank, world, local_rank):
                 tj = json.load(f)
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
             ncu_ops_pct = tj.get("tensor_pipe_ops_pct_of_peak_ncu")
+        step_frac = (float(P) * n * n * 256.0 * args.steps / (ms_total * 1e-3) / 1e12) / peak_int8 if ms_total else None
         roofline = {"bound": "tensor", "kernel": "match_pair_kernel", "achieved": achieved, "peak": peak_int8,
-                    "unit": "TFLOP/s", "ops": "integer: u8 x u8 -> s32 multiply-accumulates on the tensor cores, 2 ops each "
-                                              "(TOP/s; the contract's unit name is kept)",
+                    "unit": "TOP/s", "ops": "integer: u8 x u8 -> s32 multiply-accumulates on the tensor cores, 2 ops each",
                     "frac": achieved / peak_int8 if peak_int8 else None, "traffic": traffic,
                     "traffic_source": traffic_src,
                     "peak_note": f"2 x cuBLAS bf16 sustained ({peaks['bf16_tflops_sustained']} TF/s, {peaks['source']} "
@@ -480,33 +612,50 @@ def run_ours(args, rank, world, local_rank):
                     "hw_peak_note": "tcgen05 kind::i8 microbenchmarked at 8192 MAC/clk/SM = 4.77 POP/s at 1965 MHz "
                                     "(profiles/r01_microbench.log); achieved/4770 = %.3f" % (achieved / 4770.0),
                     "avg_launch_ms": k1_avg_s * 1e3, "launches_timed": k1["launches"],
-                    "kernel_share_of_step": k1["ms"] / ms_total if ms_total else None}
+                    "kernel_share_of_step": k1["ms"] / ms_total if ms_total else None,
+                    "step_level_frac": step_frac}
+        if ba_large and "roofline" in ba_large:
+            roofline["k2"] = dict(ba_large["roofline"], workload=ba_large["workload"], observations_per_s=ba_large["value"],
+                                  ms_per_iteration=ba_large["ms_per_iteration"], allreduce_ms=ba_large["allreduce_ms"])
         # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
         cpu = None
-        if world == 1 and args.cpu_pairs > 0:
-            sample_pairs = args.cpu_pairs
+        if world == 1 and args.cpu_pairs != 0:
+            sample_pairs = args.cpu_pairs if args.cpu_pairs > 0 else 32
+            sub = descs[: sample_pairs + 1].cpu().numpy()
             pl = [(k + 1, 0) for k in range(sample_pairs)]
-            sub = host_np[: sample_pairs + 1]
             t_u8, _ = cpu_reference_pairs(sub, pl)
             t_f32, _ = cpu_reference_pairs(sub, pl[: max(1, sample_pairs // 2)], f32=True)
             cores = os.cpu_count() or 1
             cpu = {"value": sample_pairs * float(n) * n / t_u8, "unit": UNIT, "cores": cores, "kind": "reference",
-                   "sample": f"{sample_pairs} of {P} image pairs ({n}x{n} u8), OpenCV BFMatcher.knnMatch both directions "
-                             f"+ ratio + CrossCheck via cv2 (the routine FeatureUtils.cpp:146-149 calls), cv2 threads={cores}",
+                   "sample": f"{sample_pairs} of {P_all} image pairs ({n}x{n} u8), extrapolated linearly; OpenCV BFMatcher.knnMatch both "
+                             f"directions + ratio + CrossCheck via cv2 (the routine FeatureUtils.cpp:146-149 calls), cv2 threads={cores}",
                    "f32_value": max(1, sample_pairs // 2) * float(n) * n / t_f32,
-                   "f32_note": "same pairs as float32 (what the reference's DB really stores; OpenCV's f32 path is faster)"}
+                   "f32_note": "same pairs as float32 (what the reference's DB really stores; OpenCV's f32 path is faster)",
+                   **ceres_probe()}
+            if ba_large and "cpu_baseline" in ba_large:
+                cpu["ba"] = dict(ba_large["cpu_baseline"], workload=ba_large["workload"],
+                                 gpu_over_cpu_per_iteration=ba_large["value"] / ba_large["cpu_baseline"]["value"])
+            if target:
+                target["cpu_extrapolated_s"] = {"u8": target["value"] * target["wall_s"] / cpu["value"],
+                                                "f32": target["value"] * target["wall_s"] / cpu["f32_value"]}
+                target["speedup_vs_cpu"] = {"u8": target["cpu_extrapolated_s"]["u8"] / target["wall_s"],
+                                            "f32": target["cpu_extrapolated_s"]["f32"] / target["wall_s"]}
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps}
+        if ba_large and "e2e" in ba_large:
+            e2e["ba"] = dict(ba_large["e2e"], workload=ba_large["workload"])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": f"match {n_img} images x {n} descriptors, all {P} pairs per GPU (cross-check, ratio 0.8)",
-                           "l2": "working set per step (128 MiB descriptors + ~2.7 GB row scratch) exceeds the 126 MB L2",
-                           "distribution": "SIFT-like, 30% planted correspondences", "matches_per_step": int(total)},
-                "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps},
-                "roofline": roofline, "cpu_baseline": cpu,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": wl_name, "distribution": "SIFT-like, 30% planted correspondences",
+                           "l2": "working set per step (descriptors + ~2.7 GB row scratch per batch) exceeds the 126 MB L2",
+                           "pairs_this_rank": int(P), "matches_this_rank_per_step": int(total),
+                           "per_rank_ms_per_step": per_rank,
+                           "load_imbalance": (max(per_rank) / (sum(per_rank) / len(per_rank))) if per_rank else None},
+                "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+                "roofline": roofline, "cpu_baseline": cpu, "verify": verify,
                 "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items() if v["launches"]},
-                "match_stats": stats, "ba": ba_out, "ba_large": ba_large}
+                "match_stats": stats, "distributions": dists_out, "target": target, "ba": ba_out, "ba_large": ba_large}
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist:
@@ -519,11 +668,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images", type=int, default=128)
+    ap.add_argument("--images", type=int, default=0, help="0: BASELINE configs[1] (128) on one GPU, configs[2] (1329) on several")
     ap.add_argument("--ndesc", type=int, default=8192)
-    ap.add_argument("--cpu-pairs", type=int, default=6, help="image pairs in the CPU-baseline sample")
-    ap.add_argument("--no-ba", action="store_true", help="skip the secondary BA measurements")
-    ap.add_argument("--no-ba-large", action="store_true", help="skip the configs[4]-sized BA measurement (N=1 only)")
+    ap.add_argument("--cpu-pairs", type=int, default=-1, help="image pairs in the CPU-baseline sample (-1: 32; 0: skip)")
+    ap.add_argument("--no-ba", action="store_true", help="skip the BA measurements")
+    ap.add_argument("--no-ba-large", action="store_true", help="skip the configs[4]-sized BA measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the U / dense-overlap distributions (N=1)")
+    ap.add_argument("--no-target", action="store_true", help="skip the 1000-image north_star target pass (N=1)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the per-step sampled-pair check against cv2")
+    ap.add_argument("--target-images", type=int, default=1000)
     ap.add_argument("--cpu-data", action="store_true", help="generate the synthetic descriptors with numpy (ncu launch lists)")
     ap.add_argument("--ba-cams", type=int, default=128)
     ap.add_argument("--ba-pts", type=int, default=50000)

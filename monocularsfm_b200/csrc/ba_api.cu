@@ -20,6 +20,7 @@ using ba::CamPre;
 using ba::Problem;
 using ba::TailLayout;
 using ba::Tile;
+using ba::Item;
 cudaError_t ba_launch_cam_prep(const double*, int, CamPre*, cudaStream_t);
 cudaError_t ba_launch_evaluate(const Problem&, double*, float*, double*, int, cudaStream_t);
 cudaError_t ba_launch_linearize(const Problem&, double, int, cudaStream_t);
@@ -85,6 +86,7 @@ struct msfm_ba {
     uint8_t* obs_lcam = nullptr;
     // tiling + block structure (ba_types.cuh, ba_tiles.hpp)
     Tile* tiles = nullptr;
+    Item* items = nullptr;
     int32_t *tile_cams = nullptr, *tile_slots = nullptr, *blk_row = nullptr, *blk_col = nullptr;
     int32_t n_tiles = 0, w_cap = 32, n_blocks = 0;
     std::vector<int32_t> h_blk_row, h_blk_col;
@@ -112,7 +114,7 @@ struct msfm_ba {
         P.refine_focal = refine_focal; P.pt_Wf = pt_Wf;
         P.pre = pre[which]; P.pts = pts[which]; P.obs_uv = obs_uv; P.obs_cam = obs_cam; P.obs_pt = obs_pt; P.obs_orig = obs_orig;
         P.obs_lcam = obs_lcam; P.pt_start = pt_start; P.pt_order = pt_order; P.cam_free = cam_free;
-        P.tiles = tiles; P.n_tiles = n_tiles; P.tile_cams = tile_cams; P.tile_slots = tile_slots; P.w_cap = w_cap;
+        P.tiles = tiles; P.items = items; P.n_tiles = n_tiles; P.tile_cams = tile_cams; P.tile_slots = tile_slots; P.w_cap = w_cap;
         P.n_blocks = n_blocks; P.blk_row = blk_row; P.blk_col = blk_col;
         P.sblk = sblk; P.tail = tail(); P.tl = tl; P.gpm_slot = ctx->comm ? ctx->comm_rank : 0; P.tile_counter = tile_counter;
         return P;
@@ -168,7 +170,7 @@ void msfm_ba_destroy(msfm_ba* b) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void* ptrs[] = {b->cams[0], b->cams[1], b->pts[0], b->pts[1], b->pre[0], b->pre[1], b->obs_uv, b->obs_cam, b->obs_pt, b->obs_orig,
-                    b->obs_lcam, b->pt_start, b->pt_order, b->cam_free, b->tiles, b->tile_cams, b->tile_slots, b->blk_row, b->blk_col,
+                    b->obs_lcam, b->pt_start, b->pt_order, b->cam_free, b->tiles, b->items, b->tile_cams, b->tile_slots, b->blk_row, b->blk_col,
                     b->sysbuf, b->dense, b->xsol, b->small, b->work, b->dev_info, b->pt_Wf};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -276,6 +278,7 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     BA_ALLOC(b->pt_order, size_t(pr->n_pts) * sizeof(int32_t));
     BA_ALLOC(b->cam_free, size_t(pr->n_cams) * sizeof(int32_t));
     BA_ALLOC(b->tiles, T.tiles.size() * sizeof(Tile));
+    BA_ALLOC(b->items, T.items.size() * sizeof(Item));
     BA_ALLOC(b->tile_cams, T.tile_cams.size() * sizeof(int32_t));
     BA_ALLOC(b->tile_slots, T.tile_slots.size() * sizeof(int32_t));
     BA_ALLOC(b->blk_row, T.blk_row.size() * sizeof(int32_t));
@@ -304,6 +307,7 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     if (e == cudaSuccess) e = H2D(b->pt_order, T.pt_order.data(), T.pt_order.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->cam_free, cam_free.data(), cam_free.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->tiles, T.tiles.data(), T.tiles.size() * sizeof(Tile));
+    if (e == cudaSuccess) e = H2D(b->items, T.items.data(), T.items.size() * sizeof(Item));
     if (e == cudaSuccess) e = H2D(b->tile_cams, T.tile_cams.data(), T.tile_cams.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->tile_slots, T.tile_slots.data(), T.tile_slots.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->blk_row, T.blk_row.data(), T.blk_row.size() * sizeof(int32_t));

@@ -284,6 +284,21 @@ __device__ __forceinline__ void smem_add6(float* base, const float v[6]) {
         if (got[e] != __float_as_uint(old[e])) atomicAdd(base + e, v[e]);
 }
 
+__device__ __forceinline__ void smem_add6(double* base, const double v[6]) {
+    unsigned long long* b = reinterpret_cast<unsigned long long*>(base);
+    double old[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) old[e] = *reinterpret_cast<volatile double*>(base + e);
+    unsigned long long got[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e)
+        got[e] = atomicCAS(b + e, static_cast<unsigned long long>(__double_as_longlong(old[e])),
+                           static_cast<unsigned long long>(__double_as_longlong(old[e] + v[e])));
+#pragma unroll
+    for (int e = 0; e < 6; ++e)
+        if (got[e] != static_cast<unsigned long long>(__double_as_longlong(old[e]))) atomicAdd(base + e, v[e]);
+}
+
 size_t fused_smem_bytes(int w_cap, int threads, bool focal) {
     const size_t cv = focal ? 30 : 18;
     const size_t nb = static_cast<size_t>(w_cap) * (w_cap + 1) / 2;
@@ -318,9 +333,18 @@ fused_linearize_kernel(Problem P, double inv_radius) {
         for (int i = threadIdx.x; i < T.w * CV; i += blockDim.x) camacc[i] = 0.0;
         for (int i = threadIdx.x; i < T.w; i += blockDim.x) lfree[i] = __ldg(P.cam_free + __ldg(P.tile_cams + T.cam_begin + i));
         __syncthreads();
-        const bool split = (T.flags & kTileSplit) != 0, primary = (T.flags & kTilePrimary) != 0;
+        const bool split = (T.flags & kTileSplit) != 0;
 
-        for (int d = T.pt_begin + warp; d < T.pt_end; d += nwarps) {
+        for (int u = T.begin + warp; u < T.end; u += nwarps) {
+            // a normal tile walks device points; an item tile walks items (a long track restricted to two observation groups)
+            int d = u, a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+            bool primary = true;
+            const Item* item = nullptr;
+            if (split) {
+                item = P.items + u;
+                d = item->d; a0 = item->a0; a1 = item->a1; b0 = item->b0; b1 = item->b1;
+                primary = item->primary != 0;
+            }
             const int p = __ldg(P.pt_order + d);
             const int beg = __ldg(P.pt_start + d), end = __ldg(P.pt_start + d + 1);
             const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
@@ -345,16 +369,16 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                     ff[5] += fs[2]; ff[6] += fs[3]; ff[7] += fs[0]; ff[8] += fs[1];
                 }
             }
-            // ---- the observations this tile couples: all of them (at most 32), or groups A | B of a split point
+            // ---- the observations this unit couples: all of them (at most 32), or groups A | B of a long track
             int nA = end - beg, nB = 0, lcam;
             if (!split) {
                 lcam = A.valid ? static_cast<int>(__ldg(P.obs_lcam + beg + lane)) : 0;
             } else {
-                nA = T.sub_a1 - T.sub_a0; nB = T.sub_b1 - T.sub_b0;
+                nA = a1 - a0; nB = b1 - b0;
                 const bool valid = lane < nA + nB;
-                const int o = beg + (lane < nA ? T.sub_a0 + lane : T.sub_b0 + lane - nA);
+                const int o = beg + (lane < nA ? a0 + lane : b0 + lane - nA);
                 load_lane(P, o, valid, X, A);
-                lcam = lane;
+                lcam = item->lc[lane];
             }
             // Q = Jp V^-1 (2x3) in fp32; staged with the Jacobians for the pair products
             float Q[6];
@@ -395,23 +419,32 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                 const double q0 = Q[0] * gp[0] + Q[1] * gp[1] + Q[2] * gp[2] - A.r[0];
                 const double q1 = Q[3] * gp[0] + Q[4] * gp[1] + Q[5] * gp[2] - A.r[1];
                 double* ca = camacc + lcam * CV;
+                {
+                    double v_rhs[6], v_gc[6], v_ud[6];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    const double j0 = A.Jc[i], j1 = A.Jc[6 + i];
-                    atomicAdd(ca + i, j0 * q0 + j1 * q1);
-                    atomicAdd(ca + 6 + i, j0 * A.r[0] + j1 * A.r[1]);
-                    atomicAdd(ca + 12 + i, j0 * j0 + j1 * j1);
+                    for (int i = 0; i < 6; ++i) {
+                        const double j0 = A.Jc[i], j1 = A.Jc[6 + i];
+                        v_rhs[i] = j0 * q0 + j1 * q1;
+                        v_gc[i] = j0 * A.r[0] + j1 * A.r[1];
+                        v_ud[i] = j0 * j0 + j1 * j1;
+                    }
+                    smem_add6(ca, v_rhs);
+                    smem_add6(ca + 6, v_gc);
+                    smem_add6(ca + 12, v_ud);
                 }
                 if (kFocal) {
                     // border B_c = Jc^T Jf - Y Wf^T = Jc^T (Jf - Q Wf^T),  Jf = diag(xp, yp)
                     const double g00 = Q[0] * Wf[0] + Q[1] * Wf[1] + Q[2] * Wf[2], g01 = Q[0] * Wf[3] + Q[1] * Wf[4] + Q[2] * Wf[5];
                     const double g10 = Q[3] * Wf[0] + Q[4] * Wf[1] + Q[5] * Wf[2], g11 = Q[3] * Wf[3] + Q[4] * Wf[4] + Q[5] * Wf[5];
+                    double v_b[12];
 #pragma unroll
                     for (int i = 0; i < 6; ++i) {
                         const double j0 = A.Jc[i], j1 = A.Jc[6 + i];
-                        atomicAdd(ca + 18 + 2 * i, j0 * (A.xy[0] - g00) - j1 * g10);
-                        atomicAdd(ca + 18 + 2 * i + 1, -j0 * g01 + j1 * (A.xy[1] - g11));
+                        v_b[2 * i] = j0 * (A.xy[0] - g00) - j1 * g10;
+                        v_b[2 * i + 1] = -j0 * g01 + j1 * (A.xy[1] - g11);
                     }
+                    smem_add6(ca + 18, v_b);
+                    smem_add6(ca + 24, v_b + 6);
                 }
             }
             // ---- per camera pair (x < y): block (x, y) -= Jc_x^T (Q_x Jp_y^T) Jc_y

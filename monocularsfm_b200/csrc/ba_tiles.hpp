@@ -16,8 +16,8 @@ namespace msfm {
 namespace ba {
 
 struct TilingParams {
-    int w_cap = 32;            // max local cameras per tile (<= kMaxWCap)
-    int max_pts = 256;         // max points per tile
+    int w_cap = 32;            // max local cameras per tile (32 .. kMaxWCap)
+    int max_pts = 256;         // max points (items) per tile
     long long max_work = 1 << 15;   // max sum of k (k + 1) / 2 per tile
 };
 
@@ -27,6 +27,7 @@ struct Tiling {
     std::vector<int32_t> obs_perm;      // device observation -> caller's observation
     std::vector<uint8_t> obs_lcam;      // device observation -> local camera of its (normal) tile
     std::vector<Tile> tiles;
+    std::vector<Item> items;
     std::vector<int32_t> tile_cams;
     std::vector<int32_t> tile_marks;    // per tile, tri(w) entries: 1 if some point of the tile couples the two local cameras
     std::vector<int32_t> tile_slots;    // same shape: global block slot or -1 (assign_slots)
@@ -54,13 +55,14 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
         std::sort(b, e, [&](int32_t x, int32_t y) { return obs_cam[x] < obs_cam[y]; });
         for (int32_t* q = b; q + 1 < e; ++q)
             if (obs_cam[q[0]] == obs_cam[q[1]]) return false;
-        // locality key: the three smallest cameras (21 bits each); points without observations go last
+        // locality key: the three smallest cameras (20 bits each).  Order of the classes: points with at most 32
+        // observations, long tracks, points without observations.
         uint64_t k = ~uint64_t(0);
         if (e > b) {
-            const uint64_t c0 = uint64_t(obs_cam[b[0]]) & 0x1FFFFF;
-            const uint64_t c1 = e - b > 1 ? uint64_t(obs_cam[b[1]]) & 0x1FFFFF : c0;
-            const uint64_t c2 = e - b > 2 ? uint64_t(obs_cam[b[2]]) & 0x1FFFFF : c1;
-            k = (c0 << 42) | (c1 << 21) | c2;
+            const uint64_t c0 = uint64_t(obs_cam[b[0]]) & 0xFFFFF;
+            const uint64_t c1 = e - b > 1 ? uint64_t(obs_cam[b[1]]) & 0xFFFFF : c0;
+            const uint64_t c2 = e - b > 2 ? uint64_t(obs_cam[b[2]]) & 0xFFFFF : c1;
+            k = (uint64_t(e - b > 32 ? 1 : 0) << 62) | (c0 << 40) | (c1 << 20) | c2;
         }
         key[p] = k;
     }
@@ -76,33 +78,32 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
         T.pt_start[size_t(d) + 1] = T.pt_start[d] + k;
         std::copy(sorted_obs.begin() + start[p], sorted_obs.begin() + start[size_t(p) + 1], T.obs_perm.begin() + T.pt_start[d]);
     }
-    // ---- greedy tiles over the device order
-    const int w_cap = std::max(32, std::min(prm.w_cap, kMaxWCap));   // split tiles hold up to 32 cameras
+    const int w_cap = std::max(32, std::min(prm.w_cap, kMaxWCap));   // an item holds up to 32 cameras
     std::vector<int32_t> stamp(static_cast<size_t>(std::max(1, n_cams)), -1), lidx(static_cast<size_t>(std::max(1, n_cams)), 0);
-    T.tiles.clear(); T.tile_cams.clear(); T.tile_marks.clear();
+    T.tiles.clear(); T.items.clear(); T.tile_cams.clear(); T.tile_marks.clear();
     T.w_max = 0;
+    auto cam_of = [&](int dev_obs) { return obs_cam[T.obs_perm[dev_obs]]; };
+    // ---- normal tiles: greedy over the device order
     auto close_tile = [&](int d0, int d1, std::vector<int32_t>& cams) {
         if (d1 <= d0) return;
         std::sort(cams.begin(), cams.end());
         Tile t{};
-        t.pt_begin = d0; t.pt_end = d1;
+        t.begin = d0; t.end = d1;
         t.cam_begin = static_cast<int32_t>(T.tile_cams.size());
         t.w = static_cast<int32_t>(cams.size());
         t.slot_begin = static_cast<int32_t>(T.tile_marks.size());
-        t.flags = kTilePrimary;
         for (size_t i = 0; i < cams.size(); ++i) lidx[cams[i]] = static_cast<int32_t>(i);
         T.tile_cams.insert(T.tile_cams.end(), cams.begin(), cams.end());
-        const size_t nb = size_t(t.w) * (t.w + 1) / 2;
-        T.tile_marks.resize(T.tile_marks.size() + nb, 0);
+        T.tile_marks.resize(T.tile_marks.size() + size_t(t.w) * (t.w + 1) / 2, 0);
         int32_t* marks = T.tile_marks.data() + t.slot_begin;
         for (int d = d0; d < d1; ++d)
             for (int a = T.pt_start[d]; a < T.pt_start[size_t(d) + 1]; ++a) {
-                const int ca = obs_cam[T.obs_perm[a]];
+                const int ca = cam_of(a);
                 const int la = lidx[ca];
                 T.obs_lcam[a] = static_cast<uint8_t>(la);
                 if (cam_free[ca] < 0) continue;
                 for (int b = a; b < T.pt_start[size_t(d) + 1]; ++b) {
-                    const int cb = obs_cam[T.obs_perm[b]];
+                    const int cb = cam_of(b);
                     if (cam_free[cb] >= 0) marks[tri_index(la, lidx[cb])] = 1;
                 }
             }
@@ -110,67 +111,107 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
         T.tiles.push_back(t);
         cams.clear();
     };
-    // a point with more than 32 observations: one tile per pair of 16-observation groups
-    auto split_point = [&](int d) {
-        const int beg = T.pt_start[d], k = T.pt_start[size_t(d) + 1] - beg;
-        const int ng = (k + 15) / 16;
-        for (int gi = 0; gi < ng; ++gi)
-            for (int gj = gi; gj < ng; ++gj) {
-                Tile t{};
-                t.pt_begin = d; t.pt_end = d + 1;
-                t.cam_begin = static_cast<int32_t>(T.tile_cams.size());
-                t.sub_a0 = gi * 16; t.sub_a1 = std::min(k, gi * 16 + 16);
-                if (gj != gi) { t.sub_b0 = gj * 16; t.sub_b1 = std::min(k, gj * 16 + 16); }
-                const int na = t.sub_a1 - t.sub_a0, nb_ = t.sub_b1 - t.sub_b0;
-                t.w = na + nb_;
-                t.slot_begin = static_cast<int32_t>(T.tile_marks.size());
-                t.flags = kTileSplit | ((gi == 0 && gj == 0) ? kTilePrimary : 0);
-                for (int i = 0; i < na; ++i) T.tile_cams.push_back(obs_cam[T.obs_perm[beg + t.sub_a0 + i]]);
-                for (int i = 0; i < nb_; ++i) T.tile_cams.push_back(obs_cam[T.obs_perm[beg + t.sub_b0 + i]]);
-                const size_t nb = size_t(t.w) * (t.w + 1) / 2;
-                T.tile_marks.resize(T.tile_marks.size() + nb, 0);
-                int32_t* marks = T.tile_marks.data() + t.slot_begin;
-                const int32_t* lc = T.tile_cams.data() + t.cam_begin;
-                if (gj == gi) {
-                    for (int x = 0; x < na; ++x)
-                        for (int y = x; y < na; ++y)
-                            if (cam_free[lc[x]] >= 0 && cam_free[lc[y]] >= 0) marks[tri_index(x, y)] = 1;
-                } else {
-                    for (int x = 0; x < na; ++x)
-                        for (int y = na; y < na + nb_; ++y)
-                            if (cam_free[lc[x]] >= 0 && cam_free[lc[y]] >= 0) marks[tri_index(x, y)] = 1;
-                }
-                T.w_max = std::max(T.w_max, int(t.w));
-                T.tiles.push_back(t);
-            }
-    };
     std::vector<int32_t> cams;
-    int d0 = 0, tile_id = 0;
+    int d0 = 0, tile_id = 0, first_long = n_pts;
     long long work = 0;
     for (int d = 0; d < n_pts; ++d) {
         const int beg = T.pt_start[d], k = T.pt_start[size_t(d) + 1] - beg;
-        if (k == 0) { close_tile(d0, d, cams); d0 = n_pts; break; }     // points without observations are sorted last
-        if (k > 32 || k > w_cap) {
-            close_tile(d0, d, cams);
-            ++tile_id; work = 0; d0 = d + 1;
-            split_point(d);
-            continue;
-        }
+        if (k == 0 || k > 32) { first_long = d; break; }                 // classes are sorted: normal | long | unobserved
         int fresh = 0;
         for (int a = beg; a < beg + k; ++a)
-            if (stamp[obs_cam[T.obs_perm[a]]] != tile_id) ++fresh;
+            if (stamp[cam_of(a)] != tile_id) ++fresh;
         const long long pw = static_cast<long long>(k) * (k + 1) / 2;
         if (d > d0 && (int(cams.size()) + fresh > w_cap || d - d0 >= prm.max_pts || work + pw > prm.max_work)) {
             close_tile(d0, d, cams);
             ++tile_id; work = 0; d0 = d;
         }
         for (int a = beg; a < beg + k; ++a) {
-            const int c = obs_cam[T.obs_perm[a]];
+            const int c = cam_of(a);
             if (stamp[c] != tile_id) { stamp[c] = tile_id; cams.push_back(c); }
         }
         work += pw;
     }
-    if (d0 < n_pts) close_tile(d0, n_pts, cams);
+    close_tile(d0, first_long, cams);
+    // ---- item tiles: long tracks cut into groups of 16 observations; one open tile per (group A, group B) index pair, so
+    //      that the items of neighbouring long points (nearly the same cameras) are packed together
+    struct Open { std::vector<int32_t> cams; std::vector<Item> items; long long work = 0; };
+    std::vector<Open> open;                    // index gi * ng_max + gj, grown on demand
+    int ng_max = 0;
+    auto close_items = [&](Open& o) {
+        if (o.items.empty()) return;
+        std::sort(o.cams.begin(), o.cams.end());
+        Tile t{};
+        t.flags = kTileSplit;
+        t.begin = static_cast<int32_t>(T.items.size());
+        t.end = t.begin + static_cast<int32_t>(o.items.size());
+        t.cam_begin = static_cast<int32_t>(T.tile_cams.size());
+        t.w = static_cast<int32_t>(o.cams.size());
+        t.slot_begin = static_cast<int32_t>(T.tile_marks.size());
+        for (size_t i = 0; i < o.cams.size(); ++i) lidx[o.cams[i]] = static_cast<int32_t>(i);
+        T.tile_cams.insert(T.tile_cams.end(), o.cams.begin(), o.cams.end());
+        T.tile_marks.resize(T.tile_marks.size() + size_t(t.w) * (t.w + 1) / 2, 0);
+        int32_t* marks = T.tile_marks.data() + t.slot_begin;
+        for (Item& it : o.items) {
+            const int beg = T.pt_start[it.d];
+            const int na = it.a1 - it.a0, nb = it.b1 - it.b0;
+            int cam_l[32];
+            for (int l = 0; l < na + nb; ++l) {
+                cam_l[l] = cam_of(beg + (l < na ? it.a0 + l : it.b0 + l - na));
+                it.lc[l] = static_cast<uint8_t>(lidx[cam_l[l]]);
+            }
+            for (int x = 0; x < na; ++x) {
+                if (cam_free[cam_l[x]] < 0) continue;
+                if (nb == 0) {
+                    for (int y = x; y < na; ++y)
+                        if (cam_free[cam_l[y]] >= 0) marks[tri_index(it.lc[x], it.lc[y])] = 1;
+                } else {
+                    for (int y = na; y < na + nb; ++y)
+                        if (cam_free[cam_l[y]] >= 0) marks[tri_index(it.lc[x], it.lc[y])] = 1;
+                }
+            }
+            T.items.push_back(it);
+        }
+        T.w_max = std::max(T.w_max, int(t.w));
+        T.tiles.push_back(t);
+        o = Open();
+    };
+    for (int d = first_long; d < n_pts; ++d) {
+        const int beg = T.pt_start[d], k = T.pt_start[size_t(d) + 1] - beg;
+        if (k == 0) break;
+        const int ng = (k + 15) / 16;
+        if (ng > ng_max) {                         // re-index the open tiles for the larger group count
+            std::vector<Open> grown(size_t(ng) * ng);
+            for (int gi = 0; gi < ng_max; ++gi)
+                for (int gj = gi; gj < ng_max; ++gj) grown[size_t(gi) * ng + gj] = std::move(open[size_t(gi) * ng_max + gj]);
+            open.swap(grown);
+            ng_max = ng;
+        }
+        for (int gi = 0; gi < ng; ++gi)
+            for (int gj = gi; gj < ng; ++gj) {
+                Item it{};
+                it.d = d;
+                it.a0 = static_cast<uint16_t>(gi * 16); it.a1 = static_cast<uint16_t>(std::min(k, gi * 16 + 16));
+                if (gj != gi) { it.b0 = static_cast<uint16_t>(gj * 16); it.b1 = static_cast<uint16_t>(std::min(k, gj * 16 + 16)); }
+                it.primary = (gi == 0 && gj == 0) ? 1 : 0;
+                const int na = it.a1 - it.a0, nb = it.b1 - it.b0;
+                Open& o = open[size_t(gi) * ng_max + gj];
+                int fresh = 0;
+                for (int l = 0; l < na + nb; ++l) {
+                    const int c = cam_of(beg + (l < na ? it.a0 + l : it.b0 + l - na));
+                    if (std::find(o.cams.begin(), o.cams.end(), c) == o.cams.end()) ++fresh;
+                }
+                const long long pw = nb ? static_cast<long long>(na) * nb : static_cast<long long>(na) * (na + 1) / 2;
+                if (!o.items.empty() && (int(o.cams.size()) + fresh > w_cap || int(o.items.size()) >= prm.max_pts || o.work + pw > prm.max_work))
+                    close_items(o);
+                for (int l = 0; l < na + nb; ++l) {
+                    const int c = cam_of(beg + (l < na ? it.a0 + l : it.b0 + l - na));
+                    if (std::find(o.cams.begin(), o.cams.end(), c) == o.cams.end()) o.cams.push_back(c);
+                }
+                o.items.push_back(it);
+                o.work += pw;
+            }
+    }
+    for (Open& o : open) close_items(o);
     return true;
 }
 

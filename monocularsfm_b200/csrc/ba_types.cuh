@@ -15,22 +15,28 @@ struct CamPre {
     double pad;
 };
 
-// A tile = a run of points (device order) that together touch at most w_cap cameras.  One CTA linearises one tile at
-// a time and accumulates the tile's share of the reduced camera system in shared memory: the upper triangle of 6x6
-// blocks over the tile's LOCAL camera list, flushed once per tile into the global block-sparse S.
-// A point observed by more than 32 cameras is split into several single-point tiles, each restricted to the pairs between
-// two groups of at most 16 of its observations (sub_*): the per-warp staging holds 32 observations.
+// A tile = a set of points that together touch at most w_cap cameras.  One CTA linearises one tile at a time and
+// accumulates the tile's share of the reduced camera system in shared memory: the upper triangle of 6x6 blocks over the
+// tile's LOCAL camera list, flushed once per tile into the global block-sparse S.
+//   normal tile: device points [begin, end), each observed by at most 32 cameras (one lane per observation);
+//   item tile:   items [begin, end) (struct Item): a point observed by more than 32 cameras is cut into groups of 16
+//                observations; an item couples group A with group B (or A with itself, which also owns A's diagonal blocks).
+//                Items of neighbouring long points with the same (A, B) group indices share cameras and are packed together.
 struct Tile {
-    int32_t pt_begin, pt_end;     // device points [pt_begin, pt_end)
+    int32_t begin, end;           // device points (normal) or items (kTileSplit)
     int32_t cam_begin, w;         // local cameras: tile_cams[cam_begin .. cam_begin + w), ascending global camera index
     int32_t slot_begin;           // tile_slots[slot_begin + lb (lb + 1) / 2 + la] (la <= lb): global block slot or -1
-    int32_t sub_a0, sub_a1;       // split tiles: observation positions [a0, a1) of the point form group A ...
-    int32_t sub_b0, sub_b1;       //              ... and [b0, b1) group B (empty: pairs inside A, plus A's diagonal blocks)
-    int32_t flags;                // kTileSplit | kTilePrimary
+    int32_t flags;                // kTileSplit
     int32_t pad[2];
 };
-constexpr int32_t kTileSplit = 1;      // single-point tile with an observation subset
-constexpr int32_t kTilePrimary = 2;    // this tile accounts the point's cost / gradient maximum (every normal tile; one split tile per point)
+struct Item {
+    int32_t d;                    // device point
+    uint16_t a0, a1, b0, b1;      // observation positions [a0, a1) = group A, [b0, b1) = group B (empty: pairs inside A)
+    uint16_t primary;             // 1: this item accounts the point's cost / gradient maximum / focal sums (exactly one per point)
+    uint16_t pad;
+    uint8_t lc[32];               // local camera of lane l: lanes 0 .. nA-1 hold group A, nA .. nA+nB-1 group B
+};
+constexpr int32_t kTileSplit = 1;
 constexpr int kBlkStride = 37;         // 36 floats of a 6x6 block + 1: conflict-free shared-memory banks across blocks
 constexpr int kMaxWCap = 40;           // local cameras per tile (shared-memory accumulator = w (w+1)/2 blocks)
 
@@ -61,6 +67,7 @@ struct Problem {
     const int32_t* cam_free;    // [n_cams] index among the free cameras or -1 (constant pose)
     // ---- tiling + block structure (built once per problem: the sparsity pattern does not change between LM iterations)
     const Tile* tiles;
+    const Item* items;
     int32_t n_tiles;
     const int32_t* tile_cams;
     const int32_t* tile_slots;

@@ -95,7 +95,7 @@ void msfm_destroy(msfm_ctx* c) {
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (auto& im : c->imgs)
         if (im.block) cudaFree(im.block);
-    GrowBuf* bufs[] = {&c->d_imgs, &c->d_raw, &c->d_fmt, &c->d_temp, &c->h_stage, &c->d_segs, &c->d_units, &c->d_res, &c->d_m, &c->d_exact,
+    GrowBuf* bufs[] = {&c->d_imgs, &c->d_raw, &c->d_fmt, &c->d_temp, &c->h_stage, &c->d_segs, &c->d_units, &c->d_items, &c->d_res, &c->d_m, &c->d_exact,
                        &c->d_counts, &c->d_misc, &c->d_out_offsets, &c->d_out_matches, &c->d_out_dist, &c->d_ba_r, &c->d_ba_J};
     for (GrowBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {

@@ -22,17 +22,19 @@ public:
     FeatureMatcher(const std::string& database_path, const int& max_num_matches = 10240, const double& max_distance = 0.7,
                    const double& distance_ratio = 0.8, const bool& cross_check = true)
         : database_path_(database_path), max_num_matches_(max_num_matches), max_distance_(max_distance),
-          distance_ratio_(distance_ratio), cross_check_(cross_check) {}
+          distance_ratio_(distance_ratio), cross_check_(cross_check), geometric_filter_(DefaultGeometricFilter()) {}
     virtual ~FeatureMatcher() {}
 
     void MatchImagePairs(const std::vector<std::pair<image_t, image_t>>& image_pairs);
     virtual void RunMatching() = 0;
 
-    // Geometric verification hook (FeatureUtils::FilterMatches = F-matrix RANSAC in the reference,
-    // FeatureMatching.cpp:60).  OUT OF SCOPE of the hot path: when unset, matches pass through.
-    // A build with OpenCV installs cv::findFundamentalMat here.
+    // Geometric verification (FeatureUtils::FilterMatches = F-matrix RANSAC, 3 px / 0.99, FeatureMatching.cpp:60).  As in the
+    // reference it ALWAYS runs before WriteMatches: the default is FeatureUtils::FilterMatches.  SetGeometricFilter
+    // replaces it (a build with OpenCV may install cv::findFundamentalMat); an empty function is an
+    // explicit opt-out (matches pass through unverified).
     typedef std::function<void(const std::vector<cv::Point2f>&, const std::vector<cv::Point2f>&,
                                const std::vector<cv::DMatch>&, std::vector<cv::DMatch>&)> GeometricFilter;
+    static GeometricFilter DefaultGeometricFilter();
     void SetGeometricFilter(GeometricFilter f) { geometric_filter_ = f; }
     void SetVerbose(bool v) { verbose_ = v; }
 

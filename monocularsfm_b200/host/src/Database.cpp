@@ -327,7 +327,7 @@ std::vector<cv::DMatch> Database::ReadMatches(const image_pair_t pair_id) const 
 }
 std::vector<std::pair<image_pair_t, std::vector<cv::DMatch>>> Database::ReadAllMatches() const {
     std::vector<std::pair<image_pair_t, std::vector<cv::DMatch>>> out;
-    sqlite3_stmt* st = impl_->prepare("SELECT pair_id, rows, cols, data FROM matches");
+    sqlite3_stmt* st = impl_->prepare("SELECT pair_id, rows, cols, data FROM matches WHERE rows > 0");   // as the reference's statement
     while (impl_->check(api().step(st), __LINE__) == kRow) {
         const image_pair_t pid = static_cast<image_pair_t>(api().column_int64(st, 0));
         const size_t rows = static_cast<size_t>(api().column_int64(st, 1));

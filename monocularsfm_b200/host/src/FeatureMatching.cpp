@@ -13,6 +13,8 @@ namespace {
 const int32_t kTopScaleIdBase = 1000000000;   // device ids of the preemptive-matching (top-scale) descriptor subsets
 }
 
+FeatureMatcher::GeometricFilter FeatureMatcher::DefaultGeometricFilter() { return FeatureUtils::FilterMatches; }
+
 // Read an image's descriptors from the database once, bridge CV_32F -> u8, keep them resident on the device.
 void FeatureMatcher::EnsureResident(image_t image_id) {
     if (resident_.count(image_id)) return;
@@ -39,12 +41,28 @@ void FeatureMatcher::MatchImagePairs(const std::vector<std::pair<image_t, image_
         }
         todo.push_back(pr);
     }
-    bool any_quantised = false;
     for (const auto& pr : todo) {
         EnsureResident(pr.first);
         EnsureResident(pr.second);
-        any_quantised = any_quantised || quantised_[pr.first] || quantised_[pr.second];
     }
+    // FilterMatchesByDistance(max_distance_) (:49) compares distances on the scale of the descriptors: unit-norm floats that
+    // went through the x512 quantisation need max_distance_ * 512, integral (un-normalised) sets the value as given.  A pair
+    // mixing the two scales has no meaningful distance: quantise both sides the same way upstream.  The batch is split by
+    // scale so that each device call carries ONE threshold.
+    std::vector<std::pair<image_t, image_t>> all_todo;
+    all_todo.swap(todo);
+    for (int pass = 0; pass < 2; ++pass) {
+    todo.clear();
+    for (const auto& pr : all_todo) {
+        const bool q1 = quantised_[pr.first], q2 = quantised_[pr.second];
+        if (q1 != q2) {
+            std::cerr << "FeatureMatcher: images " << pr.first << " and " << pr.second
+                      << " hold descriptors on different scales (one set was quantised x512, the other is integral)" << std::endl;
+            exit(EXIT_FAILURE);                                                  // the reference's error style (Database.cpp:16-20)
+        }
+        if ((q1 ? 1 : 0) == pass) todo.push_back(pr);
+    }
+    const double distance_scale = pass == 1 ? FeatureUtils::QuantisationScale() : 1.0;
     if (!todo.empty()) {
         std::vector<int32_t> ids(todo.size() * 2);
         int64_t bound = 0;
@@ -55,9 +73,7 @@ void FeatureMatcher::MatchImagePairs(const std::vector<std::pair<image_t, image_
             bound += msfm_desc_count(ctx, todo[p].first);
         }
         msfm_match_options opt;
-        // FilterMatchesByDistance(max_distance_) (:49): max_distance_ is given for unit-norm float descriptors; on the
-        // quantised u8 scale it becomes max_distance_ * 512, on raw integral SIFT (norm ~512) likewise.
-        opt.max_distance = max_distance_ < 0 ? -1.0 : max_distance_ * FeatureUtils::QuantisationScale();
+        opt.max_distance = max_distance_ < 0 ? -1.0 : max_distance_ * distance_scale;
         opt.distance_ratio = static_cast<float>(distance_ratio_);            // narrowed like FeatureUtils.h:95
         opt.cross_check = cross_check_ ? 1 : 0;
         opt.opencv_quirks = 1;
@@ -71,7 +87,7 @@ void FeatureMatcher::MatchImagePairs(const std::vector<std::pair<image_t, image_
         for (size_t p = 0; p < todo.size(); ++p) {
             std::vector<cv::DMatch> prune_matches;
             for (int64_t k = offsets[p]; k < offsets[p + 1]; ++k)
-                prune_matches.push_back(cv::DMatch(out[2 * k], out[2 * k + 1], 0, dist[k]));
+                prune_matches.push_back(cv::DMatch(out[2 * k], out[2 * k + 1], 0, static_cast<float>(dist[k] / distance_scale)));
             std::vector<cv::DMatch> verified;
             if (geometric_filter_) {
                 std::vector<cv::KeyPoint> k1 = database_->ReadKeyPoints(todo[p].first), k2 = database_->ReadKeyPoints(todo[p].second);
@@ -89,6 +105,8 @@ void FeatureMatcher::MatchImagePairs(const std::vector<std::pair<image_t, image_
             database_->WriteMatches(todo[p].first, todo[p].second, verified);   // a row is written even for 0 matches (:68-70)
         }
     }
+    }   // scale passes
+    todo.swap(all_todo);
     if (verbose_ && !todo.empty()) {
         const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::cout << "\t batch of " << todo.size() << " pairs: " << s << " s" << std::endl;

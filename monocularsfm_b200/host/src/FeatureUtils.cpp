@@ -18,6 +18,23 @@ void MatchTwoMats(const cv::Mat& desc1, const cv::Mat& desc2, std::vector<cv::DM
     FeatureUtils::UploadDescriptors(kScratchId1, desc1);
     device::Check(msfm_sync(ctx), "msfm_sync");   // the upload staging buffer is reused by the next upload
     FeatureUtils::UploadDescriptors(kScratchId2, desc2);
+    // Both operands must live on ONE scale.  If either float set had to be quantised (x512), the other is re-uploaded with
+    // forced quantisation, and the distances handed back are divided by the scale: a caller that keeps the reference idiom
+    // ComputeCrossMatches(...) + FilterMatchesByDistance(m, out, 0.7) sees unit-scale L2 distances as with OpenCV.
+    // Saturation: components above 255/512 = 0.498 clamp to 255; for such (sparse RootSIFT-like) rows distances and the
+    // ratio test can differ from the float path — documented deviation, covered by the host tests.
+    int q1 = msfm_desc_quantised(ctx, kScratchId1), q2 = msfm_desc_quantised(ctx, kScratchId2);
+    if (q1 < 0) device::Check(q1, "msfm_desc_quantised");
+    if (q2 < 0) device::Check(q2, "msfm_desc_quantised");
+    if (q1 != q2) {
+        const cv::Mat& other = q1 ? desc2 : desc1;
+        if (other.type() == CV_32F) {
+            device::Check(msfm_desc_upload_f32(ctx, q1 ? kScratchId2 : kScratchId1, reinterpret_cast<const float*>(other.data), other.rows, 1),
+                          "msfm_desc_upload_f32");
+            device::Check(msfm_sync(ctx), "msfm_sync");
+        }
+    }
+    const double scale = (q1 || q2) ? FeatureUtils::QuantisationScale() : 1.0;
     const cv::Mat& a = desc1;
     msfm_match_options opt;
     opt.max_distance = -1.0;
@@ -32,7 +49,7 @@ void MatchTwoMats(const cv::Mat& desc1, const cv::Mat& desc2, std::vector<cv::DM
     int64_t offsets[2] = {0, 0}, total = 0;
     device::Check(msfm_match_pairs(ctx, pair, 1, &opt, offsets, out.data(), dist.data(), cap, &total), "msfm_match_pairs");
     for (int64_t k = 0; k < total; ++k)
-        matches.push_back(cv::DMatch(out[2 * k], out[2 * k + 1], 0, dist[k]));   // imgIdx 0 like knnMatch on one train set
+        matches.push_back(cv::DMatch(out[2 * k], out[2 * k + 1], 0, static_cast<float>(dist[k] / scale)));   // imgIdx 0 like knnMatch on one train set
 }
 }  // namespace
 

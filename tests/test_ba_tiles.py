@@ -24,7 +24,7 @@ def harness(tmp_path_factory):
     lib.tiling_build.restype = C.c_int
     lib.tiling_build.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, C.c_int, C.c_int, C.c_int, C.c_longlong, ip]
     lib.tiling_fetch.restype = None
-    lib.tiling_fetch.argtypes = [ip, ip, ip, C.POINTER(C.c_uint8), ip, ip, ip, ip, ip]
+    lib.tiling_fetch.argtypes = [ip, ip, ip, C.POINTER(C.c_uint8), ip, ip, ip, ip, ip, ip]
     return lib
 
 
@@ -35,22 +35,41 @@ def run_tiling(lib, P, w_cap=32, max_pts=64, max_work=1 << 15):
     cam_free = -np.ones(len(const), np.int32)
     cam_free[~const] = np.arange((~const).sum(), dtype=np.int32)
     ip = C.POINTER(C.c_int32)
-    sizes = np.zeros(5, np.int32)
+    sizes = np.zeros(6, np.int32)
     rc = lib.tiling_build(len(const), len(P["pts"]), len(oc), oc.ctypes.data_as(ip), op.ctypes.data_as(ip),
                           cam_free.ctypes.data_as(ip), int((~const).sum()), w_cap, max_pts, max_work, sizes.ctypes.data_as(ip))
     if rc:
         return None
-    n_tiles, n_tc, n_marks, n_blocks, w_max = [int(x) for x in sizes]
+    n_tiles, n_tc, n_marks, n_blocks, w_max, n_items = [int(x) for x in sizes]
     T = {"pt_order": np.zeros(len(P["pts"]), np.int32), "pt_start": np.zeros(len(P["pts"]) + 1, np.int32),
          "obs_perm": np.zeros(len(oc), np.int32), "obs_lcam": np.zeros(len(oc), np.uint8),
-         "tiles": np.zeros((n_tiles, 12), np.int32), "tile_cams": np.zeros(n_tc, np.int32),
+         "tiles": np.zeros((n_tiles, 8), np.int32), "items_raw": np.zeros((n_items, 12), np.int32), "tile_cams": np.zeros(n_tc, np.int32),
          "tile_slots": np.zeros(n_marks, np.int32), "blk_row": np.zeros(n_blocks, np.int32),
          "blk_col": np.zeros(n_blocks, np.int32), "w_max": w_max, "cam_free": cam_free}
     lib.tiling_fetch(T["pt_order"].ctypes.data_as(ip), T["pt_start"].ctypes.data_as(ip), T["obs_perm"].ctypes.data_as(ip),
                      T["obs_lcam"].ctypes.data_as(C.POINTER(C.c_uint8)), T["tiles"].ctypes.data_as(ip),
-                     T["tile_cams"].ctypes.data_as(ip), T["tile_slots"].ctypes.data_as(ip), T["blk_row"].ctypes.data_as(ip),
+                     T["items_raw"].ctypes.data_as(ip), T["tile_cams"].ctypes.data_as(ip), T["tile_slots"].ctypes.data_as(ip), T["blk_row"].ctypes.data_as(ip),
                      T["blk_col"].ctypes.data_as(ip))
+    # struct Item { int32 d; uint16 a0, a1, b0, b1, primary, pad; uint8 lc[32]; }
+    raw = T["items_raw"].view(np.uint8).reshape(n_items, 48)
+    h = raw[:, 4:16].copy().view(np.uint16).reshape(n_items, 6)
+    T["items"] = [{"d": int(T["items_raw"][i, 0]), "a0": int(h[i, 0]), "a1": int(h[i, 1]), "b0": int(h[i, 2]), "b1": int(h[i, 3]),
+                   "primary": int(h[i, 4]), "lc": raw[i, 16:48].astype(int)} for i in range(n_items)]
     return T
+
+
+def tile_units(T, t):
+    """(device point, selected observation positions or None, local cameras or None, nA, nB, primary) of every unit of a tile."""
+    b, e, cb, w, sb, flags = [int(x) for x in t[:6]]
+    out = []
+    if flags & 1:
+        for it in T["items"][b:e]:
+            nA, nB = it["a1"] - it["a0"], it["b1"] - it["b0"]
+            sel = list(range(it["a0"], it["a1"])) + list(range(it["b0"], it["b1"]))
+            out.append((it["d"], sel, it["lc"][:nA + nB].tolist(), nA, nB, bool(it["primary"])))
+    else:
+        out = [(d, None, None, 0, 0, True) for d in range(b, e)]
+    return out
 
 
 long_track_problem = bo.make_long_track_problem
@@ -76,27 +95,23 @@ def test_tiling_invariants(harness, which):
     covered = np.zeros(n_pts, int)
     pair_count = {}
     for t in T["tiles"]:
-        pb, pe, cb, w, sb, a0, a1, b0, b1, flags = [int(x) for x in t[:10]]
+        b0_, e0_, cb, w, sb, flags = [int(x) for x in t[:6]]
         cams = T["tile_cams"][cb:cb + w]
         assert w <= 32 and (np.diff(cams) > 0).all()
-        if flags & 1:                                        # split: one point, groups of <= 16 observations
-            assert pe == pb + 1 and a1 - a0 <= 16 and b1 - b0 <= 16
-            s = T["pt_start"][pb]
-            sel = list(range(s + a0, s + a1)) + list(range(s + b0, s + b1))
-            assert (oc[sel] == cams).all()
-            if flags & 2:
-                covered[pb] += 1
-            A, B = list(range(a0, a1)), list(range(b0, b1))
-            prs = [(x, y) for x in A for y in B] if B else [(x, y) for x in A for y in A if x <= y]
-            for x, y in prs:
-                pair_count[(pb, x, y)] = pair_count.get((pb, x, y), 0) + 1
-        else:
-            assert flags & 2
-            covered[pb:pe] += 1
-            for d in range(pb, pe):
-                s, e = T["pt_start"][d], T["pt_start"][d + 1]
-                assert e - s <= 32
-                assert (cams[T["obs_lcam"][s:e]] == oc[s:e]).all()
+        for d, sel, lc, nA, nB, primary in tile_units(T, t):
+            s0, e0 = int(T["pt_start"][d]), int(T["pt_start"][d + 1])
+            if sel is None:
+                assert e0 - s0 <= 32
+                covered[d] += 1
+                assert (cams[T["obs_lcam"][s0:e0]] == oc[s0:e0]).all()
+            else:                                            # an item: groups of <= 16 observations of a long track
+                assert e0 - s0 > 32 and nA <= 16 and nB <= 16
+                assert (cams[lc] == oc[[s0 + x for x in sel]]).all() and (np.diff(lc) > 0).all()
+                covered[d] += int(primary)
+                A, B = sel[:nA], sel[nA:]
+                prs = [(x, y) for x in A for y in B] if B else [(x, y) for x in A for y in A if x <= y]
+                for x, y in prs:
+                    pair_count[(d, x, y)] = pair_count.get((d, x, y), 0) + 1
     k = np.diff(T["pt_start"])
     assert (covered[k > 0] == 1).all() and (covered[k == 0] == 0).all()
     for d in np.nonzero(k > 32)[0]:                           # every pair (and diagonal) of a long track exactly once
@@ -111,6 +126,21 @@ def test_tiling_invariants(harness, which):
         want |= {(int(a), int(b)) for a in f for b in f if a <= b}
     got = list(zip(T["blk_row"].tolist(), T["blk_col"].tolist()))
     assert got == sorted(want)
+
+
+def test_items_of_neighbouring_long_tracks_are_packed(harness):
+    """Ring problem with many long tracks (the BASELINE configs[3] generator, smaller): item tiles hold many items each."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    P = bench.make_ba_problem(128, 20000, 10.0, 4321)
+    T = run_tiling(harness, P, 32, 42)
+    split = (T["tiles"][:, 5] & 1) == 1
+    assert len(T["items"]) > 1000
+    # a cross item holds 32 cameras = the whole tile budget, so only long tracks that start at the same camera share a tile
+    assert split.sum() * 3 <= len(T["items"])
+    npts = T["tiles"][~split, 1] - T["tiles"][~split, 0]
+    assert npts.mean() > 25
 
 
 def test_duplicate_camera_rejected(harness):
@@ -138,20 +168,18 @@ def test_tile_accumulation_emulation_matches_dense_schur(harness, which):
     sblk = np.zeros((len(T["blk_row"]), 6, 6))
     rhs = np.zeros((nf, 6)); udiag = np.zeros((nf, 6))
     for t in T["tiles"]:
-        pb, pe, cb, w, sb, a0, a1, b0, b1, flags = [int(x) for x in t[:10]]
+        cb, w, sb = int(t[2]), int(t[3]), int(t[4])
         lfree = cf[T["tile_cams"][cb:cb + w]]
         acc = np.zeros((w * (w + 1) // 2, 6, 6))
         camacc = np.zeros((w, 12))
-        for d in range(pb, pe):
+        for d, sel_pos, lc_item, nA, nB, primary in tile_units(T, t):
             s, e = int(T["pt_start"][d]), int(T["pt_start"][d + 1])
             Vp = (Jp[s:e].transpose(0, 2, 1) @ Jp[s:e]).sum(0)
             g = (Jp[s:e].transpose(0, 2, 1) @ rr[s:e, :, None]).sum(0)[:, 0]
             Vp[np.arange(3), np.arange(3)] += np.maximum(np.diag(Vp), 1e-6) * inv_radius
             Vi = np.linalg.inv(Vp)
-            if flags & 1:
-                sel = list(range(s + a0, s + a1)) + list(range(s + b0, s + b1))
-                lc = list(range(len(sel)))
-                nA, nB = a1 - a0, b1 - b0
+            if sel_pos is not None:
+                sel = [s + x for x in sel_pos]; lc = lc_item
             else:
                 sel = list(range(s, e)); lc = T["obs_lcam"][s:e].tolist(); nA, nB = e - s, 0
             Q = [Jp[o] @ Vi for o in sel]

@@ -437,7 +437,7 @@ def run_ours(args, rank, world, local_rank):
     pairs = np.ascontiguousarray(shard_pairs(pairs_all, rank, world)) if world > 1 else pairs_all
     P = len(pairs)
     opt = m.MatchOptions(0.8, -1.0, True, True)
-    per_pair_cap = 4096 if P <= 20000 else 1280
+    per_pair_cap = 8192 if P <= 20000 else 1280       # at most one match per query row; the big pair lists hold ~800 per pair
     capacity = int(P) * per_pair_cap + 65536
     d_off = torch.empty(P + 1, dtype=torch.int64, device=dev)
     d_mat = torch.empty((capacity, 2), dtype=torch.int32, device=dev)
@@ -543,7 +543,7 @@ def run_ours(args, rank, world, local_rank):
             del dd
     if world == 1 and not args.no_target:
         # north_star's target: 1000 images x 8192, all 499 500 pairs, one pass, wall clock (descriptors resident)
-        del d_mat, d_dst, d_off
+        del d_mat, d_dst, d_off, bufs
         torch.cuda.empty_cache()
         n_t = args.target_images
         dt_ = make_descriptors_torch(n_t, n, 777, dev)

@@ -68,7 +68,8 @@ int64_t msfm_launch_count(const msfm_ctx* ctx);
 #define MSFM_PROF_BA_SCHUR     7   /* K2: Schur reduction onto the camera system */
 #define MSFM_PROF_BA_OTHER     8
 #define MSFM_PROF_BA_COMM      9   /* the all-reduce of the reduced camera system (multi-GPU) */
-#define MSFM_PROF_NCAT        10
+#define MSFM_PROF_VERIFY      10   /* batched F-matrix RANSAC */
+#define MSFM_PROF_NCAT        11
 int msfm_prof_enable(msfm_ctx* ctx, int on);
 int msfm_prof_reset(msfm_ctx* ctx);
 int msfm_prof_read(msfm_ctx* ctx, double ms[MSFM_PROF_NCAT], int64_t launches[MSFM_PROF_NCAT]);
@@ -156,6 +157,40 @@ int msfm_match_knn2_u8(msfm_ctx* ctx, const uint8_t* A, int32_t nA, const uint8_
 int msfm_match_stats(msfm_ctx* ctx, int64_t stats[4]);
 
 /* ---------------------------------------------------------------------------------------------
+ * Geometric verification of the matches (the step MatchImagePairs applies between matching and WriteMatches)
+ *
+ * Replaces FeatureUtils::FilterMatches (src/Feature/FeatureUtils.cpp:176-206) =
+ * cv::findFundamentalMat(aligned_pts1, aligned_pts2, cv::FM_RANSAC, 3.0, 0.99, inlier_mask), called per pair at
+ * src/Feature/FeatureMatching.cpp:60, by ONE batched kernel over all pairs of a call (one CTA per pair): RANSAC over
+ * minimal 8-point samples (Hartley normalisation, rank-2 constraint), OpenCV's error measure and adaptive iteration count,
+ * refits on the consensus set.  Deterministic (counter-based sampler).  NOT bit-compatible with OpenCV's RANSAC (different
+ * sampler and minimal solver): the parity criterion is inlier-set agreement, tests/test_verify_gpu.py.
+ * ------------------------------------------------------------------------------------------- */
+/* Keep the keypoint positions (KeyPoint::pt, x then y, pixels) of an image resident; uploaded once per image instead of
+ * Database::ReadKeyPoints per pair (FeatureMatching.cpp:51-52). */
+int  msfm_keypoints_upload(msfm_ctx* ctx, int32_t image_id, const float* xy /*[n][2]*/, int32_t n);
+int  msfm_keypoints_count(msfm_ctx* ctx, int32_t image_id);
+int  msfm_keypoints_release_all(msfm_ctx* ctx);
+typedef struct {
+    double  threshold;    /* 3.0 px (FeatureUtils.cpp:196) */
+    double  confidence;   /* 0.99 */
+    int32_t max_iters;    /* 1000 (OpenCV default) */
+    int32_t reserved;     /* must be 0 */
+} msfm_verify_options;
+void msfm_verify_default_options(msfm_verify_options* opt);
+/* Inlier masks for the matches of P pairs.  pairs / offsets / matches exactly as msfm_match_pairs takes and returns them
+ * (matches[k] = (queryIdx into image 1's keypoints, trainIdx into image 2's)).  inlier_mask[k] = 1 for the matches
+ * FilterMatches would keep (all 0 for a pair with fewer than 8 matches or without a model); inlier_counts [P] optional.
+ * HOST pointers. */
+int  msfm_verify_pairs(msfm_ctx* ctx, const int32_t* pairs /*[P][2]*/, int32_t P, const int64_t* offsets /*[P+1]*/,
+                       const int32_t* matches /*[offsets[P]][2]*/, const msfm_verify_options* opt,
+                       uint8_t* inlier_mask /*[offsets[P]]*/, int32_t* inlier_counts /*[P] or NULL*/);
+/* Same with DEVICE match lists / outputs (chained behind msfm_match_pairs_dev without a host round trip); pairs on the host. */
+int  msfm_verify_pairs_dev(msfm_ctx* ctx, const int32_t* pairs_host /*[P][2]*/, int32_t P, const int64_t* offsets_dev,
+                           const int32_t* matches_dev, const msfm_verify_options* opt, uint8_t* inlier_mask_dev,
+                           int32_t* inlier_counts_dev /*or NULL*/);
+
+/* ---------------------------------------------------------------------------------------------
  * B-path: bundle-adjustment inner loop
  *
  * Replaces what CeresBundelOptimizer::Optimize (src/Optimizer/CeresBundleOptimizer.cpp:188-328) delegates to
@@ -214,7 +249,8 @@ void msfm_ba_destroy(msfm_ba* ba);
 /* Structure of the problem as the device sees it: info[0] free cameras F, [1] non-empty 6x6 blocks of the upper block
  * triangle of the reduced camera system (the fp32 part of the all-reduce message), [2] point tiles, [3] max cameras per
  * tile, [4] bytes of the system buffer (= the all-reduce message + 16), [5] shared memory per CTA of the linearisation
- * kernel, [6] fp64 words of the message tail (scalars | rhs | g_c | diag U | focal border), [7] reserved. */
+ * kernel, [6] fp64 words of the message tail (scalars | rhs | g_c | diag U | focal border), [7] tracks longer than 32 views
+ * (handled by a pre-pass + item tiles). */
 int  msfm_ba_structure(msfm_ba* ba, int32_t info[8]);
 /* Current parameters -> host ([n_cams][6], [n_pts][3]; either may be NULL). */
 int  msfm_ba_get_params(msfm_ba* ba, double* cams, double* pts);

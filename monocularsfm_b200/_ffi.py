@@ -31,6 +31,14 @@ class MatchOptions(C.Structure):
                          int(bool(opencv_quirks)), 0)
 
 
+class VerifyOptions(C.Structure):
+    """msfm_verify_options; defaults = cv::findFundamentalMat(FM_RANSAC, 3.0, 0.99) as FeatureUtils.cpp:196 calls it."""
+    _fields_ = [("threshold", C.c_double), ("confidence", C.c_double), ("max_iters", C.c_int32), ("reserved", C.c_int32)]
+
+    def __init__(self, threshold=3.0, confidence=0.99, max_iters=1000):
+        super().__init__(float(threshold), float(confidence), int(max_iters), 0)
+
+
 class BAProblemC(C.Structure):
     _fields_ = [("n_cams", C.c_int32), ("n_pts", C.c_int32), ("n_obs", C.c_int32), ("flags", C.c_int32),
                 ("fx", C.c_double), ("fy", C.c_double), ("cams", C.c_void_p), ("pts", C.c_void_p),
@@ -101,6 +109,12 @@ def load_library():
         "msfm_match_pairs_dev": (C.c_int, [vp, vp, i32, P(MatchOptions), vp, vp, vp, i64, P(i64)]),
         "msfm_match_knn2_u8": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, vp]),
         "msfm_match_stats": (C.c_int, [vp, P(i64)]),
+        "msfm_keypoints_upload": (C.c_int, [vp, i32, vp, i32]),
+        "msfm_keypoints_count": (C.c_int, [vp, i32]),
+        "msfm_keypoints_release_all": (C.c_int, [vp]),
+        "msfm_verify_default_options": (None, [P(VerifyOptions)]),
+        "msfm_verify_pairs": (C.c_int, [vp, vp, i32, vp, vp, P(VerifyOptions), vp, vp]),
+        "msfm_verify_pairs_dev": (C.c_int, [vp, vp, i32, vp, vp, P(VerifyOptions), vp, vp]),
         "msfm_ba_default_options": (None, [P(BAOptions), i32]),
         "msfm_ba_create": (C.c_int, [vp, P(BAProblemC), P(vp)]),
         "msfm_ba_destroy": (None, [vp]),
@@ -173,7 +187,7 @@ class Context:
         return int(self.lib.msfm_launch_count(self.h))
 
     PROF_NAMES = ["desc_format", "build_units", "match_tile", "resolve", "exact", "compact", "ba_eval", "ba_schur",
-                  "ba_other", "ba_comm"]
+                  "ba_other", "ba_comm", "verify"]
 
     def prof_enable(self, on=True):
         self._check(self.lib.msfm_prof_enable(self.h, int(on)))
@@ -251,6 +265,23 @@ class Context:
                                                 _ptr(dist), _ptr(d2)))
         return idx, dist, d2
 
+    # ---- geometric verification
+    def upload_keypoints(self, image_id: int, xy: np.ndarray):
+        xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+        self._check(self.lib.msfm_keypoints_upload(self.h, image_id, _ptr(xy), xy.shape[0]))
+
+    def verify_pairs(self, pairs, offsets, matches, opt: "VerifyOptions | None" = None):
+        """Inlier mask (uint8 per match) and inlier count per pair of the batched F-matrix RANSAC."""
+        opt = opt or VerifyOptions()
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        matches = np.ascontiguousarray(matches, dtype=np.int32).reshape(-1, 2)
+        mask = np.zeros(max(1, int(offsets[-1])), np.uint8)
+        counts = np.zeros(len(pairs), np.int32)
+        self._check(self.lib.msfm_verify_pairs(self.h, _ptr(pairs), len(pairs), _ptr(offsets), _ptr(matches), C.byref(opt),
+                                               _ptr(mask), _ptr(counts)))
+        return mask[:int(offsets[-1])].astype(bool), counts
+
     # ---- B-path
     def ba_create(self, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, refine_focal=False):
         return BAProblem(self, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, refine_focal)
@@ -308,8 +339,8 @@ class BAProblem:
     def structure(self):
         info = (C.c_int32 * 8)()
         self.ctx._check(self.lib.msfm_ba_structure(self.h, info))
-        return {"n_free": info[0], "n_blocks": info[1], "n_tiles": info[2], "w_cap": info[3], "system_bytes": info[4],
-                "smem_per_cta": info[5], "tail_f64": info[6]}
+        return {"n_free": info[0], "n_blocks": info[1], "n_tiles": info[2], "w_max": info[3], "system_bytes": info[4],
+                "smem_per_cta": info[5], "tail_f64": info[6], "n_long_tracks": info[7]}
 
     def get_params(self):
         cams = np.zeros((self.n_cams, 6))

@@ -29,7 +29,7 @@ cudaError_t ba_launch_track_errors(const Problem&, double*, int, cudaStream_t);
 cudaError_t ba_launch_backsub(const Problem&, double, const double*, double*, double*, int, cudaStream_t);
 cudaError_t ba_launch_update_cams(const double*, const int32_t*, int, const double*, double*, cudaStream_t);
 cudaError_t ba_launch_copy(const double*, double*, int, cudaStream_t);
-size_t ba_fused_smem_bytes(int, bool);
+size_t ba_fused_smem_bytes(bool);
 }  // namespace msfm
 using namespace msfm;
 
@@ -88,7 +88,9 @@ struct msfm_ba {
     Tile* tiles = nullptr;
     Item* items = nullptr;
     int32_t *tile_cams = nullptr, *tile_slots = nullptr, *blk_row = nullptr, *blk_col = nullptr;
-    int32_t n_tiles = 0, w_cap = 32, n_blocks = 0;
+    int32_t n_tiles = 0, w_max = 0, n_blocks = 0, first_long = 0, n_long = 0;
+    uint8_t* obs_lpt = nullptr;
+    double* long_V = nullptr;      // per long track: V^-1 | g_p (| Wf), written by the pre-pass of every linearisation
     std::vector<int32_t> h_blk_row, h_blk_col;
     // the system of one linearisation, ONE allocation: tail (fp64: scalars | per-rank max |g_p| | rhs | gc | diag U | focal
     // border) | tile counter | sblk (fp32 6x6 blocks).  tail and sblk are the two parts of the all-reduce message.
@@ -114,7 +116,8 @@ struct msfm_ba {
         P.refine_focal = refine_focal; P.pt_Wf = pt_Wf;
         P.pre = pre[which]; P.pts = pts[which]; P.obs_uv = obs_uv; P.obs_cam = obs_cam; P.obs_pt = obs_pt; P.obs_orig = obs_orig;
         P.obs_lcam = obs_lcam; P.pt_start = pt_start; P.pt_order = pt_order; P.cam_free = cam_free;
-        P.tiles = tiles; P.items = items; P.n_tiles = n_tiles; P.tile_cams = tile_cams; P.tile_slots = tile_slots; P.w_cap = w_cap;
+        P.tiles = tiles; P.items = items; P.n_tiles = n_tiles; P.tile_cams = tile_cams; P.tile_slots = tile_slots;
+        P.obs_lpt = obs_lpt; P.first_long = first_long; P.n_long = n_long; P.long_V = long_V;
         P.n_blocks = n_blocks; P.blk_row = blk_row; P.blk_col = blk_col;
         P.sblk = sblk; P.tail = tail(); P.tl = tl; P.gpm_slot = ctx->comm ? ctx->comm_rank : 0; P.tile_counter = tile_counter;
         return P;
@@ -170,7 +173,7 @@ void msfm_ba_destroy(msfm_ba* b) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void* ptrs[] = {b->cams[0], b->cams[1], b->pts[0], b->pts[1], b->pre[0], b->pre[1], b->obs_uv, b->obs_cam, b->obs_pt, b->obs_orig,
-                    b->obs_lcam, b->pt_start, b->pt_order, b->cam_free, b->tiles, b->items, b->tile_cams, b->tile_slots, b->blk_row, b->blk_col,
+                    b->obs_lcam, b->obs_lpt, b->long_V, b->pt_start, b->pt_order, b->cam_free, b->tiles, b->items, b->tile_cams, b->tile_slots, b->blk_row, b->blk_col,
                     b->sysbuf, b->dense, b->xsol, b->small, b->work, b->dev_info, b->pt_Wf};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -200,11 +203,10 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     // ---- structure analysis (host): device order, tiles, block structure of the reduced camera system
     ba::TilingParams tp;
     {
-        const char* e1 = getenv("MSFM_BA_WCAP");
+        // development overrides of the tile shape (ba_tiles.hpp clamps them to the kernel's limits)
+        const char* e1 = getenv("MSFM_BA_TILE_OBS");
         const char* e2 = getenv("MSFM_BA_TILE_PTS");
-        if (e1 && atoi(e1) > 0) tp.w_cap = atoi(e1);
-        // enough tiles to keep every SM busy (two resident CTAs each) with a dynamic scheduler
-        tp.max_pts = std::max(16, std::min(256, pr->n_pts / (8 * std::max(1, c->num_sms))));
+        if (e1 && atoi(e1) > 0) tp.max_obs = atoi(e1);
         if (e2 && atoi(e2) > 0) tp.max_pts = atoi(e2);
     }
     ba::Tiling T;
@@ -238,7 +240,8 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     b->h_cams.assign(pr->cams, pr->cams + size_t(pr->n_cams) * 6);
     b->h_cam_free = cam_free;
     b->n_tiles = static_cast<int32_t>(T.tiles.size());
-    b->w_cap = std::max(32, T.w_max);
+    b->w_max = T.w_max;
+    b->first_long = T.first_long; b->n_long = T.n_long;
     b->n_blocks = static_cast<int32_t>(T.blk_col.size());
     b->h_blk_row = T.blk_row; b->h_blk_col = T.blk_col;
     const size_t n6 = size_t(nf) * 6;
@@ -274,6 +277,8 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     BA_ALLOC(b->obs_pt, size_t(pr->n_obs) * sizeof(int32_t));
     BA_ALLOC(b->obs_orig, size_t(pr->n_obs) * sizeof(int32_t));
     BA_ALLOC(b->obs_lcam, size_t(pr->n_obs));
+    BA_ALLOC(b->obs_lpt, size_t(pr->n_obs));
+    BA_ALLOC(b->long_V, size_t(std::max(1, T.n_long)) * 15 * sizeof(double));
     BA_ALLOC(b->pt_start, (size_t(pr->n_pts) + 1) * sizeof(int32_t));
     BA_ALLOC(b->pt_order, size_t(pr->n_pts) * sizeof(int32_t));
     BA_ALLOC(b->cam_free, size_t(pr->n_cams) * sizeof(int32_t));
@@ -303,6 +308,7 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     if (e == cudaSuccess) e = H2D(b->obs_pt, opt.data(), opt.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->obs_orig, T.obs_perm.data(), T.obs_perm.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->obs_lcam, T.obs_lcam.data(), T.obs_lcam.size());
+    if (e == cudaSuccess) e = H2D(b->obs_lpt, T.obs_lpt.data(), T.obs_lpt.size());
     if (e == cudaSuccess) e = H2D(b->pt_start, T.pt_start.data(), T.pt_start.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->pt_order, T.pt_order.data(), T.pt_order.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->cam_free, cam_free.data(), cam_free.size() * sizeof(int32_t));
@@ -319,10 +325,10 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
 
 int msfm_ba_structure(msfm_ba* b, int32_t info[8]) {
     if (!b || !info) return MSFM_E_INVALID;
-    info[0] = b->n_free; info[1] = b->n_blocks; info[2] = b->n_tiles; info[3] = b->w_cap;
+    info[0] = b->n_free; info[1] = b->n_blocks; info[2] = b->n_tiles; info[3] = b->w_max;
     info[4] = static_cast<int32_t>(std::min<size_t>(b->sys_bytes, 0x7fffffff));
-    info[5] = static_cast<int32_t>(ba_fused_smem_bytes(b->w_cap, b->refine_focal != 0));
-    info[6] = b->tl.total; info[7] = 0;
+    info[5] = static_cast<int32_t>(ba_fused_smem_bytes(b->refine_focal != 0));
+    info[6] = b->tl.total; info[7] = b->n_long;
     return MSFM_OK;
 }
 
@@ -417,7 +423,7 @@ static int linearize(msfm_ba* b, int which, double inv_radius) {
     c->prof_begin(MSFM_PROF_BA_SCHUR);
     BA_CUDA(ba_launch_linearize(b->view(which), inv_radius, c->num_sms, c->stream));
     c->prof_end();
-    c->launches += b->n_tiles > 0 ? 1 : 0;
+    c->launches += (b->n_tiles > 0 ? 1 : 0) + (b->n_long > 0 ? 1 : 0);
     if (c->comm && c->comm_ranks > 1) {
         c->prof_begin(MSFM_PROF_BA_COMM);
         if (g_nccl.GroupStart() != 0) return c->fail(MSFM_E_CUDA, "ncclGroupStart failed");

@@ -8,11 +8,12 @@
 //     (Ceres SchurEliminator for DENSE_SCHUR / SPARSE_SCHUR, :264-273);
 //   * back-substitution of the points, candidate-step evaluation.
 //
-// ONE kernel per linearisation (fused_linearize_kernel).  Nothing per-observation is written to memory: the
-// 2 x 6 / 2 x 3 Jacobians of a point's observations live in registers and in a per-warp shared-memory staging area,
-// the 6x6 products Y_a W_b^T = Jc_a^T (Jp_a V^-1 Jp_b^T) Jc_b of its camera pairs are accumulated into the CTA's
-// shared-memory copy of the blocks its TILE of points touches (ba_types.cuh: Tile), and that copy is flushed once
-// per tile with vector reductions (red.global.add.v4.f32) into the block-sparse S.  History: v1 scattered every product with
+// ONE kernel per linearisation (fused_linearize_kernel; a small pre-pass only for tracks longer than 32 views).  Nothing
+// per-observation is written to memory: the 2 x 6 / 2 x 3 Jacobians of a TILE's observations (ba_types.cuh: Tile, at most
+// 512 observations over at most 32 cameras) are staged in shared memory, the 6x6 products
+// Y_a W_b^T = Jc_a^T (Jp_a V^-1 Jp_b^T) Jc_b of all camera pairs of the tile's points are accumulated into the CTA's
+// shared-memory copy of the blocks the tile touches, and that copy is flushed once per tile with vector reductions
+// (red.global.add.v4.f32) into the block-sparse S.  History: v1 scattered every product with
 // fp64 global atomics (bound by L2 atomic throughput, profiles/r01_k2_ncu_raw.csv); v2 stored Jacobians and residuals
 // per observation and gathered them again per camera and per camera pair (three kernels, ~10x the algorithmic DRAM
 // traffic, latency-bound gathers: profiles/r01b_k2_ncu_summary.txt).
@@ -266,166 +267,360 @@ __device__ __forceinline__ void point_pass1(const Problem& P, int beg, int end, 
 }
 
 // ------------------------------------------------------------------------------------------------ linearize + Schur
-constexpr int kStageStride = 25;     // floats per staged observation: Jc[12] | Jp[6] | Q[6] | local camera (odd: no bank conflicts)
+// Shared-memory row of one staged observation (floats): Jc[12] | Q[6] | Jp[6] | local camera (-1: constant pose) | pad[3].
+// 28 floats = 7 x 16 bytes: 128-bit loads; rows r and r' collide on a bank group only when r = r' mod 8.
+constexpr int kStageStride = 28;
+constexpr int kFusedThreads = kTileObs;       // one thread per observation of a tile
 
-// base[e] += v[e], e < 6, on shared memory.  sm_100 has no native fp32 shared-memory atomic add (atomicAdd compiles to an
-// LDS / FADD / ATOMS.CAST.SPIN loop per element, one after the other); here the six compare-and-swaps of a block row are
-// independent instructions in flight together, and only a lost race falls back to the loop.
-__device__ __forceinline__ void smem_add6(float* base, const float v[6]) {
-    unsigned int* b = reinterpret_cast<unsigned int*>(base);
-    float old[6];
-#pragma unroll
-    for (int e = 0; e < 6; ++e) old[e] = *reinterpret_cast<volatile float*>(base + e);
-    unsigned int got[6];
-#pragma unroll
-    for (int e = 0; e < 6; ++e) got[e] = atomicCAS(b + e, __float_as_uint(old[e]), __float_as_uint(old[e] + v[e]));
-#pragma unroll
-    for (int e = 0; e < 6; ++e)
-        if (got[e] != __float_as_uint(old[e])) atomicAdd(base + e, v[e]);
+// acc[0..5] += v[0..5] on shared memory, 8-byte aligned.  sm_100 has no native fp32 shared-memory atomic add (atomicAdd
+// compiles to an LDS / FADD / ATOMS.CAST.SPIN loop per element, one after the other); here a row of a block is three 64-bit
+// compare-and-swaps in flight together, with ONE branch for the rare lost race.
+__device__ __forceinline__ void smem_add_row(float* base, const float v[6]) {
+    unsigned long long* b = reinterpret_cast<unsigned long long*>(base);
+    const float2 o0 = *reinterpret_cast<const float2*>(base), o1 = *reinterpret_cast<const float2*>(base + 2),
+                 o2 = *reinterpret_cast<const float2*>(base + 4);
+    const unsigned long long e0 = (static_cast<unsigned long long>(__float_as_uint(o0.y)) << 32) | __float_as_uint(o0.x);
+    const unsigned long long e1 = (static_cast<unsigned long long>(__float_as_uint(o1.y)) << 32) | __float_as_uint(o1.x);
+    const unsigned long long e2 = (static_cast<unsigned long long>(__float_as_uint(o2.y)) << 32) | __float_as_uint(o2.x);
+    const unsigned long long n0 = (static_cast<unsigned long long>(__float_as_uint(o0.y + v[1])) << 32) | __float_as_uint(o0.x + v[0]);
+    const unsigned long long n1 = (static_cast<unsigned long long>(__float_as_uint(o1.y + v[3])) << 32) | __float_as_uint(o1.x + v[2]);
+    const unsigned long long n2 = (static_cast<unsigned long long>(__float_as_uint(o2.y + v[5])) << 32) | __float_as_uint(o2.x + v[4]);
+    const unsigned long long g0 = atomicCAS(b, e0, n0), g1 = atomicCAS(b + 1, e1, n1), g2 = atomicCAS(b + 2, e2, n2);
+    if ((g0 != e0) | (g1 != e1) | (g2 != e2)) {
+        if (g0 != e0) { atomicAdd(base, v[0]); atomicAdd(base + 1, v[1]); }
+        if (g1 != e1) { atomicAdd(base + 2, v[2]); atomicAdd(base + 3, v[3]); }
+        if (g2 != e2) { atomicAdd(base + 4, v[4]); atomicAdd(base + 5, v[5]); }
+    }
 }
-
 __device__ __forceinline__ void smem_add6(double* base, const double v[6]) {
     unsigned long long* b = reinterpret_cast<unsigned long long*>(base);
     double old[6];
 #pragma unroll
     for (int e = 0; e < 6; ++e) old[e] = *reinterpret_cast<volatile double*>(base + e);
     unsigned long long got[6];
+    bool lost = false;
 #pragma unroll
-    for (int e = 0; e < 6; ++e)
+    for (int e = 0; e < 6; ++e) {
         got[e] = atomicCAS(b + e, static_cast<unsigned long long>(__double_as_longlong(old[e])),
                            static_cast<unsigned long long>(__double_as_longlong(old[e] + v[e])));
+        lost |= got[e] != static_cast<unsigned long long>(__double_as_longlong(old[e]));
+    }
+    if (lost) {
 #pragma unroll
-    for (int e = 0; e < 6; ++e)
-        if (got[e] != static_cast<unsigned long long>(__double_as_longlong(old[e]))) atomicAdd(base + e, v[e]);
+        for (int e = 0; e < 6; ++e)
+            if (got[e] != static_cast<unsigned long long>(__double_as_longlong(old[e]))) atomicAdd(base + e, v[e]);
+    }
 }
 
-size_t fused_smem_bytes(int w_cap, int threads, bool focal) {
-    const size_t cv = focal ? 30 : 18;
-    const size_t nb = static_cast<size_t>(w_cap) * (w_cap + 1) / 2;
-    return static_cast<size_t>(w_cap) * cv * sizeof(double) + nb * kBlkStride * sizeof(float) +
-           static_cast<size_t>(threads / 32) * 32 * kStageStride * sizeof(float) + static_cast<size_t>(w_cap) * sizeof(int32_t) + 16;
+// Shared-memory carve-up of the linearisation kernel
+struct FusedSmem {
+    size_t camacc, acc, stage, rbuf, xybuf, ptV, ptg, ptWf, pair_start, unit_info, lfree, misc, total;
+};
+__host__ __device__ inline FusedSmem fused_smem_layout(bool focal) {
+    FusedSmem L;
+    size_t o = 0;
+    L.camacc = o; o += static_cast<size_t>(kTileCams) * (focal ? 30 : 18) * sizeof(double);
+    L.ptg = o; o += static_cast<size_t>(kTilePts) * 3 * sizeof(double);
+    L.rbuf = o; o += static_cast<size_t>(kTileObs) * 2 * sizeof(double);
+    L.xybuf = o; o += focal ? static_cast<size_t>(kTileObs) * 2 * sizeof(double) : 0;
+    L.ptWf = o; o += focal ? static_cast<size_t>(kTilePts) * 6 * sizeof(double) : 0;
+    L.acc = o; o += static_cast<size_t>(kTileCams) * (kTileCams + 1) / 2 * kBlkStride * sizeof(float);
+    L.stage = o; o += static_cast<size_t>(kTileObs) * kStageStride * sizeof(float);
+    L.ptV = o; o += static_cast<size_t>(kTilePts) * 6 * sizeof(float);
+    L.pair_start = o; o += (static_cast<size_t>(kTilePts) + 1) * sizeof(int32_t) + 12;
+    L.unit_info = o; o += static_cast<size_t>(kTilePts) * sizeof(uint32_t);
+    L.lfree = o; o += static_cast<size_t>(kTileCams) * sizeof(int32_t);
+    L.misc = o; o += 64;
+    L.total = (o + 15) / 16 * 16;
+    return L;
 }
 
-// One CTA per tile (dynamic scheduler), one warp per point, one lane per observation / per camera pair.
+// Pre-pass over the long tracks (more than 32 observations): V^-1, g_p (and Wf) of every long point, its share of the
+// cost / gradient maximum / focal sums.  The items of the point read these instead of reducing over the whole track again.
 template <bool kFocal>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256)
+long_track_prepass_kernel(Problem P, double inv_radius) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    constexpr int kRec = kFocal ? 15 : 9;
+    double cost_local = 0.0, gpmax_local = 0.0;
+    double ff[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int li = blockIdx.x * wpb + warp; li < P.n_long; li += gridDim.x * wpb) {
+        const int d = P.first_long + li;
+        const int p = __ldg(P.pt_order + d);
+        const int beg = __ldg(P.pt_start + d), end = __ldg(P.pt_start + d + 1);
+        const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
+        double Vinv[6], gp[3], Wf[6], fs[4], cl = 0.0;
+        LaneObs A;
+        point_pass1<kFocal>(P, beg, end, lane, X, inv_radius, Vinv, gp, A, cl, Wf, fs);
+        cost_local += cl;
+        gpmax_local = fmax(gpmax_local, fmax(fabs(gp[0]), fmax(fabs(gp[1]), fabs(gp[2]))));
+        double* rec = P.long_V + static_cast<size_t>(li) * kRec;
+        if (lane < 6) rec[lane] = Vinv[lane];
+        if (lane < 3) rec[6 + lane] = gp[lane];
+        if (kFocal) {
+            if (lane < 6) { rec[9 + lane] = Wf[lane]; P.pt_Wf[6 * static_cast<size_t>(d) + lane] = Wf[lane]; }
+            const double T0[3] = {Wf[0] * Vinv[0] + Wf[1] * Vinv[1] + Wf[2] * Vinv[2], Wf[0] * Vinv[1] + Wf[1] * Vinv[3] + Wf[2] * Vinv[4],
+                                  Wf[0] * Vinv[2] + Wf[1] * Vinv[4] + Wf[2] * Vinv[5]};
+            const double T1[3] = {Wf[3] * Vinv[0] + Wf[4] * Vinv[1] + Wf[5] * Vinv[2], Wf[3] * Vinv[1] + Wf[4] * Vinv[3] + Wf[5] * Vinv[4],
+                                  Wf[3] * Vinv[2] + Wf[4] * Vinv[4] + Wf[5] * Vinv[5]};
+            ff[0] += fs[0] - (T0[0] * Wf[0] + T0[1] * Wf[1] + T0[2] * Wf[2]);
+            ff[1] += -(T0[0] * Wf[3] + T0[1] * Wf[4] + T0[2] * Wf[5]);
+            ff[2] += fs[1] - (T1[0] * Wf[3] + T1[1] * Wf[4] + T1[2] * Wf[5]);
+            ff[3] += (T0[0] * gp[0] + T0[1] * gp[1] + T0[2] * gp[2]) - fs[2];
+            ff[4] += (T1[0] * gp[0] + T1[1] * gp[1] + T1[2] * gp[2]) - fs[3];
+            ff[5] += fs[2]; ff[6] += fs[3]; ff[7] += fs[0]; ff[8] += fs[1];
+        }
+    }
+    __shared__ double sh_c[8], sh_g[8], sh_f[8][9];
+    cost_local = warp_sum(cost_local);                    // lanes hold disjoint shares of the cost
+    gpmax_local = warp_max(gpmax_local);
+    if (lane == 0) {
+        sh_c[warp] = cost_local; sh_g[warp] = gpmax_local;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sh_f[warp][k] = ff[k];     // lane-uniform
+    }
+    __syncthreads();
+    if (kFocal && threadIdx.x < 9) {
+        double v = 0.0;
+        for (int k = 0; k < wpb; ++k) v += sh_f[k][threadIdx.x];
+        atomicAdd(P.tail + P.tl.ff + threadIdx.x, v);
+    }
+    if (threadIdx.x == 0) {
+        double c = 0.0, g = 0.0;
+        for (int k = 0; k < wpb; ++k) { c += sh_c[k]; g = fmax(g, sh_g[k]); }
+        atomicAdd(P.tail + P.tl.scal, c);
+        atomicMax(reinterpret_cast<unsigned long long*>(P.tail + P.tl.gpm + P.gpm_slot), static_cast<unsigned long long>(__double_as_longlong(g)));
+    }
+}
+
+// One CTA per tile (dynamic scheduler), 512 threads.  Per tile:
+//   A  thread = observation: projection, residual, Jacobians (fp64) -> staged in shared memory as fp32 (r stays fp64)
+//   B  thread = point (unit): V, g_p over its staged observations, damping, 3x3 inverse; pair counts -> prefix sums
+//   C  thread = observation: Q = Jp V^-1; diagonal block, rhs, g_c, diag U of its camera (shared-memory accumulators)
+//   D  thread = camera pair of a point, over ALL pairs of the tile: block(x, y) -= Jc_x^T (Q_x Jp_y^T) Jc_y
+//   flush: blocks with red.global.add.v4.f32, camera vectors with fp64 reductions.
+template <bool kFocal>
+__global__ void __launch_bounds__(kFusedThreads, 1)
 fused_linearize_kernel(Problem P, double inv_radius) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CV = kFocal ? 30 : 18;         // per local camera: rhs[6] | gc[6] | udiag[6] (| border B [6][2])
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    double* camacc = reinterpret_cast<double*>(smem_raw);
-    float* acc = reinterpret_cast<float*>(camacc + P.w_cap * CV);
-    float* stage = acc + (P.w_cap * (P.w_cap + 1) / 2) * kBlkStride + warp * 32 * kStageStride;
-    int32_t* lfree = reinterpret_cast<int32_t*>(acc + (P.w_cap * (P.w_cap + 1) / 2) * kBlkStride + nwarps * 32 * kStageStride);
-    int32_t* s_tile = lfree + P.w_cap;
+    const FusedSmem L = fused_smem_layout(kFocal);
+    double* camacc = reinterpret_cast<double*>(smem_raw + L.camacc);
+    double* ptg = reinterpret_cast<double*>(smem_raw + L.ptg);
+    double* rbuf = reinterpret_cast<double*>(smem_raw + L.rbuf);
+    double* xybuf = reinterpret_cast<double*>(smem_raw + L.xybuf);
+    double* ptWf = reinterpret_cast<double*>(smem_raw + L.ptWf);
+    float* acc = reinterpret_cast<float*>(smem_raw + L.acc);
+    float* stage = reinterpret_cast<float*>(smem_raw + L.stage);
+    float* ptV = reinterpret_cast<float*>(smem_raw + L.ptV);
+    int32_t* pair_start = reinterpret_cast<int32_t*>(smem_raw + L.pair_start);
+    uint32_t* unit_info = reinterpret_cast<uint32_t*>(smem_raw + L.unit_info);       // obs base (16) | nA (8) | nB (8)
+    int32_t* lfree = reinterpret_cast<int32_t*>(smem_raw + L.lfree);
+    int32_t* misc = reinterpret_cast<int32_t*>(smem_raw + L.misc);                   // [0] tile, [1..8] warp sums of the scan
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* tail = P.tail;
     double cost_local = 0.0, gpmax_local = 0.0;
-    double ff[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};        // focal block sums (lane-uniform): F00 F01 F11 rhsf0 rhsf1 gf0 gf1 uf0 uf1
+    double ff[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};        // focal block sums of this thread's points
 
     for (;;) {
-        if (threadIdx.x == 0) *s_tile = atomicAdd(P.tile_counter, 1);
+        if (tid == 0) misc[0] = atomicAdd(P.tile_counter, 1);
         __syncthreads();
-        const int ti = *s_tile;
+        const int ti = misc[0];
         if (ti >= P.n_tiles) break;
         const Tile T = P.tiles[ti];
-        const int nb = T.w * (T.w + 1) / 2;
-        for (int i = threadIdx.x; i < nb * kBlkStride; i += blockDim.x) acc[i] = 0.f;
-        for (int i = threadIdx.x; i < T.w * CV; i += blockDim.x) camacc[i] = 0.0;
-        for (int i = threadIdx.x; i < T.w; i += blockDim.x) lfree[i] = __ldg(P.cam_free + __ldg(P.tile_cams + T.cam_begin + i));
-        __syncthreads();
         const bool split = (T.flags & kTileSplit) != 0;
-
-        for (int u = T.begin + warp; u < T.end; u += nwarps) {
-            // a normal tile walks device points; an item tile walks items (a long track restricted to two observation groups)
-            int d = u, a0 = 0, a1 = 0, b0 = 0, b1 = 0;
-            bool primary = true;
-            const Item* item = nullptr;
-            if (split) {
-                item = P.items + u;
-                d = item->d; a0 = item->a0; a1 = item->a1; b0 = item->b0; b1 = item->b1;
-                primary = item->primary != 0;
+        const int n_units = T.end - T.begin;
+        const int nb = T.w * (T.w + 1) / 2;
+        {
+            float4* a4 = reinterpret_cast<float4*>(acc);
+            for (int i = tid; i < nb * (kBlkStride / 4); i += kFusedThreads) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = tid; i < T.w * CV; i += kFusedThreads) camacc[i] = 0.0;
+            if (tid < T.w) lfree[tid] = __ldg(P.cam_free + __ldg(P.tile_cams + T.cam_begin + tid));
+        }
+        // ---- A: this thread's observation
+        int unit = 0, f_mine = -1, lcam = 0;
+        bool valid, diag_owner;
+        {
+            int o, d;
+            if (!split) {
+                valid = tid < T.n_obs;
+                o = T.obs_begin + tid;
+                unit = valid ? static_cast<int>(__ldg(P.obs_lpt + o)) : 0;
+                d = T.begin + unit;
+                lcam = valid ? static_cast<int>(__ldg(P.obs_lcam + o)) : 0;
+                diag_owner = true;
+                if (tid < n_units) {
+                    const int b0 = __ldg(P.pt_start + T.begin + tid), b1 = __ldg(P.pt_start + T.begin + tid + 1);
+                    unit_info[tid] = static_cast<uint32_t>(b0 - T.obs_begin) | (static_cast<uint32_t>(b1 - b0) << 16);
+                }
+            } else {
+                unit = tid >> 5;
+                const bool live = unit < n_units;
+                const Item* item = P.items + T.begin + (live ? unit : 0);
+                const int a0 = item->a0, a1 = item->a1, b0 = item->b0, b1 = item->b1;
+                const int nA = a1 - a0, nB = b1 - b0;
+                valid = live && lane < nA + nB;
+                d = item->d;
+                o = __ldg(P.pt_start + d) + (lane < nA ? a0 + lane : b0 + lane - nA);
+                lcam = item->lc[lane];
+                diag_owner = nB == 0;
+                if (live && lane == 0) unit_info[unit] = static_cast<uint32_t>(unit * 32) | (static_cast<uint32_t>(nA) << 16) | (static_cast<uint32_t>(nB) << 24);
             }
-            const int p = __ldg(P.pt_order + d);
-            const int beg = __ldg(P.pt_start + d), end = __ldg(P.pt_start + d + 1);
-            const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
-            double Vinv[6], gp[3], Wf[6], fs[4], cl = 0.0;
-            LaneObs A;
-            point_pass1<kFocal>(P, beg, end, lane, X, inv_radius, Vinv, gp, A, cl, Wf, fs);
-            if (primary) {
-                cost_local += cl;
-                gpmax_local = fmax(gpmax_local, fmax(fabs(gp[0]), fmax(fabs(gp[1]), fabs(gp[2]))));
+            float* srow = stage + tid * kStageStride;
+            if (valid) {
+                const int cam = __ldg(P.obs_cam + o);
+                f_mine = __ldg(P.cam_free + cam);
+                const int p = __ldg(P.pt_order + d);
+                const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
+                const double2 uv = __ldg(reinterpret_cast<const double2*>(P.obs_uv) + o);
+                double r[2], Jc[12], Jp[6], xy[2];
+                obs_eval<true>(P.pre[cam], X, uv.x, uv.y, P.fx, P.fy, r, Jc, Jp, xy);
+                float4* s4 = reinterpret_cast<float4*>(srow);
+                if (f_mine >= 0) {
+                    s4[0] = make_float4(static_cast<float>(Jc[0]), static_cast<float>(Jc[1]), static_cast<float>(Jc[2]), static_cast<float>(Jc[3]));
+                    s4[1] = make_float4(static_cast<float>(Jc[4]), static_cast<float>(Jc[5]), static_cast<float>(Jc[6]), static_cast<float>(Jc[7]));
+                    s4[2] = make_float4(static_cast<float>(Jc[8]), static_cast<float>(Jc[9]), static_cast<float>(Jc[10]), static_cast<float>(Jc[11]));
+                } else {
+                    s4[0] = s4[1] = s4[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                srow[18] = static_cast<float>(Jp[0]); srow[19] = static_cast<float>(Jp[1]); srow[20] = static_cast<float>(Jp[2]);
+                srow[21] = static_cast<float>(Jp[3]); srow[22] = static_cast<float>(Jp[4]); srow[23] = static_cast<float>(Jp[5]);
+                srow[24] = __int_as_float(f_mine >= 0 ? lcam : -1);
+                rbuf[2 * tid] = r[0]; rbuf[2 * tid + 1] = r[1];
+                if (kFocal) { xybuf[2 * tid] = xy[0]; xybuf[2 * tid + 1] = xy[1]; }
+            }
+        }
+        __syncthreads();
+        // ---- B: this thread's point: V^-1, g_p; pair counts
+        {
+            int npairs = 0;
+            if (tid < n_units) {
+                const uint32_t ui = unit_info[tid];
+                double Vinv[6], gp[3], Wf[6] = {0, 0, 0, 0, 0, 0};
+                if (!split) {
+                    const int ob = static_cast<int>(ui & 0xFFFFu), k = static_cast<int>(ui >> 16);
+                    double v[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, f4[4] = {0, 0, 0, 0}, cl = 0.0;
+                    for (int j = 0; j < k; ++j) {
+                        const float* sr = stage + (ob + j) * kStageStride;
+                        const double j0 = sr[18], j1 = sr[19], j2 = sr[20], j3 = sr[21], j4 = sr[22], j5 = sr[23];
+                        const double r0 = rbuf[2 * (ob + j)], r1 = rbuf[2 * (ob + j) + 1];
+                        cl += 0.5 * (r0 * r0 + r1 * r1);
+                        v[0] += j0 * j0 + j3 * j3; v[1] += j0 * j1 + j3 * j4; v[2] += j0 * j2 + j3 * j5;
+                        v[3] += j1 * j1 + j4 * j4; v[4] += j1 * j2 + j4 * j5; v[5] += j2 * j2 + j5 * j5;
+                        g[0] += j0 * r0 + j3 * r1; g[1] += j1 * r0 + j4 * r1; g[2] += j2 * r0 + j5 * r1;
+                        if (kFocal) {
+                            const double xp = xybuf[2 * (ob + j)], yp = xybuf[2 * (ob + j) + 1];
+                            Wf[0] += xp * j0; Wf[1] += xp * j1; Wf[2] += xp * j2; Wf[3] += yp * j3; Wf[4] += yp * j4; Wf[5] += yp * j5;
+                            f4[0] += xp * xp; f4[1] += yp * yp; f4[2] += xp * r0; f4[3] += yp * r1;
+                        }
+                    }
+                    // Marquardt damping D^2 = max(diag, 1e-6) / radius  (Ceres LM strategy with Jacobi scaling, min_lm_diagonal)
+                    v[0] += fmax(v[0], 1e-6) * inv_radius;
+                    v[3] += fmax(v[3], 1e-6) * inv_radius;
+                    v[5] += fmax(v[5], 1e-6) * inv_radius;
+                    sym3_inverse(v, Vinv);
+                    gp[0] = g[0]; gp[1] = g[1]; gp[2] = g[2];
+                    cost_local += cl;
+                    gpmax_local = fmax(gpmax_local, fmax(fabs(gp[0]), fmax(fabs(gp[1]), fabs(gp[2]))));
+                    if (kFocal) {
+                        // T = Wf V^-1 (2x3);  F -= T Wf^T,  rhs_f += T g_p - g_f   (the point is eliminated from the focal block too)
+                        double* gw = P.pt_Wf + 6 * static_cast<size_t>(T.begin + tid);
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) gw[q] = Wf[q];
+                        const double T0[3] = {Wf[0] * Vinv[0] + Wf[1] * Vinv[1] + Wf[2] * Vinv[2], Wf[0] * Vinv[1] + Wf[1] * Vinv[3] + Wf[2] * Vinv[4],
+                                              Wf[0] * Vinv[2] + Wf[1] * Vinv[4] + Wf[2] * Vinv[5]};
+                        const double T1[3] = {Wf[3] * Vinv[0] + Wf[4] * Vinv[1] + Wf[5] * Vinv[2], Wf[3] * Vinv[1] + Wf[4] * Vinv[3] + Wf[5] * Vinv[4],
+                                              Wf[3] * Vinv[2] + Wf[4] * Vinv[4] + Wf[5] * Vinv[5]};
+                        ff[0] += f4[0] - (T0[0] * Wf[0] + T0[1] * Wf[1] + T0[2] * Wf[2]);
+                        ff[1] += -(T0[0] * Wf[3] + T0[1] * Wf[4] + T0[2] * Wf[5]);
+                        ff[2] += f4[1] - (T1[0] * Wf[3] + T1[1] * Wf[4] + T1[2] * Wf[5]);
+                        ff[3] += (T0[0] * gp[0] + T0[1] * gp[1] + T0[2] * gp[2]) - f4[2];
+                        ff[4] += (T1[0] * gp[0] + T1[1] * gp[1] + T1[2] * gp[2]) - f4[3];
+                        ff[5] += f4[2]; ff[6] += f4[3]; ff[7] += f4[0]; ff[8] += f4[1];
+                    }
+                    npairs = k * (k - 1) / 2;
+                } else {
+                    // a long track: the pre-pass reduced over the whole track
+                    const int d = P.items[T.begin + tid].d;
+                    const double* rec = P.long_V + static_cast<size_t>(d - P.first_long) * (kFocal ? 15 : 9);
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) Vinv[q] = rec[q];
+                    gp[0] = rec[6]; gp[1] = rec[7]; gp[2] = rec[8];
+                    if (kFocal) {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) Wf[q] = rec[9 + q];
+                    }
+                    const int nA = static_cast<int>((ui >> 16) & 0xFFu), nB = static_cast<int>(ui >> 24);
+                    npairs = nB > 0 ? nA * nB : nA * (nA - 1) / 2;
+                }
+#pragma unroll
+                for (int q = 0; q < 6; ++q) ptV[6 * tid + q] = static_cast<float>(Vinv[q]);
+                ptg[3 * tid] = gp[0]; ptg[3 * tid + 1] = gp[1]; ptg[3 * tid + 2] = gp[2];
                 if (kFocal) {
-                    // T = Wf V^-1 (2x3);  F -= T Wf^T,  rhs_f += T g_p - g_f   (the point is eliminated from the focal block too)
-                    if (lane < 6) P.pt_Wf[6 * static_cast<size_t>(d) + lane] = Wf[lane];
-                    const double T0[3] = {Wf[0] * Vinv[0] + Wf[1] * Vinv[1] + Wf[2] * Vinv[2], Wf[0] * Vinv[1] + Wf[1] * Vinv[3] + Wf[2] * Vinv[4],
-                                          Wf[0] * Vinv[2] + Wf[1] * Vinv[4] + Wf[2] * Vinv[5]};
-                    const double T1[3] = {Wf[3] * Vinv[0] + Wf[4] * Vinv[1] + Wf[5] * Vinv[2], Wf[3] * Vinv[1] + Wf[4] * Vinv[3] + Wf[5] * Vinv[4],
-                                          Wf[3] * Vinv[2] + Wf[4] * Vinv[4] + Wf[5] * Vinv[5]};
-                    ff[0] += fs[0] - (T0[0] * Wf[0] + T0[1] * Wf[1] + T0[2] * Wf[2]);
-                    ff[1] += -(T0[0] * Wf[3] + T0[1] * Wf[4] + T0[2] * Wf[5]);
-                    ff[2] += fs[1] - (T1[0] * Wf[3] + T1[1] * Wf[4] + T1[2] * Wf[5]);
-                    ff[3] += (T0[0] * gp[0] + T0[1] * gp[1] + T0[2] * gp[2]) - fs[2];
-                    ff[4] += (T1[0] * gp[0] + T1[1] * gp[1] + T1[2] * gp[2]) - fs[3];
-                    ff[5] += fs[2]; ff[6] += fs[3]; ff[7] += fs[0]; ff[8] += fs[1];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) ptWf[6 * tid + q] = Wf[q];
                 }
             }
-            // ---- the observations this unit couples: all of them (at most 32), or groups A | B of a long track
-            int nA = end - beg, nB = 0, lcam;
-            if (!split) {
-                lcam = A.valid ? static_cast<int>(__ldg(P.obs_lcam + beg + lane)) : 0;
-            } else {
-                nA = a1 - a0; nB = b1 - b0;
-                const bool valid = lane < nA + nB;
-                const int o = beg + (lane < nA ? a0 + lane : b0 + lane - nA);
-                load_lane(P, o, valid, X, A);
-                lcam = item->lc[lane];
+            // exclusive prefix sums of the pair counts over the units (threads 0 .. kTilePts-1 = 8 warps)
+            if (tid < kTilePts) {
+                int incl = npairs;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                if (lane == 31) misc[1 + warp] = incl;
+                pair_start[tid + 1] = incl;                 // warp-local inclusive sum for now
             }
-            // Q = Jp V^-1 (2x3) in fp32; staged with the Jacobians for the pair products
+        }
+        __syncthreads();
+        if (tid < kTilePts) {
+            int base = 0;
+            for (int w2 = 0; w2 < warp; ++w2) base += misc[1 + w2];
+            pair_start[tid + 1] += base;
+            if (tid == 0) pair_start[0] = 0;
+        }
+        // ---- C: this thread's observation again: Q = Jp V^-1; per-camera sums
+        if (valid) {
+            float* srow = stage + tid * kStageStride;
+            const float* vi = ptV + 6 * unit;
+            const float jp0 = srow[18], jp1 = srow[19], jp2 = srow[20], jp3 = srow[21], jp4 = srow[22], jp5 = srow[23];
             float Q[6];
-            {
-                const float v0 = static_cast<float>(Vinv[0]), v1 = static_cast<float>(Vinv[1]), v2 = static_cast<float>(Vinv[2]),
-                            v3 = static_cast<float>(Vinv[3]), v4 = static_cast<float>(Vinv[4]), v5 = static_cast<float>(Vinv[5]);
-                Q[0] = A.Jp[0] * v0 + A.Jp[1] * v1 + A.Jp[2] * v2; Q[1] = A.Jp[0] * v1 + A.Jp[1] * v3 + A.Jp[2] * v4;
-                Q[2] = A.Jp[0] * v2 + A.Jp[1] * v4 + A.Jp[2] * v5;
-                Q[3] = A.Jp[3] * v0 + A.Jp[4] * v1 + A.Jp[5] * v2; Q[4] = A.Jp[3] * v1 + A.Jp[4] * v3 + A.Jp[5] * v4;
-                Q[5] = A.Jp[3] * v2 + A.Jp[4] * v4 + A.Jp[5] * v5;
-            }
-            if (A.valid) {
-                float* s = stage + lane * kStageStride;
+            Q[0] = jp0 * vi[0] + jp1 * vi[1] + jp2 * vi[2]; Q[1] = jp0 * vi[1] + jp1 * vi[3] + jp2 * vi[4]; Q[2] = jp0 * vi[2] + jp1 * vi[4] + jp2 * vi[5];
+            Q[3] = jp3 * vi[0] + jp4 * vi[1] + jp5 * vi[2]; Q[4] = jp3 * vi[1] + jp4 * vi[3] + jp5 * vi[4]; Q[5] = jp3 * vi[2] + jp4 * vi[4] + jp5 * vi[5];
+            srow[12] = Q[0]; srow[13] = Q[1]; srow[14] = Q[2]; srow[15] = Q[3]; srow[16] = Q[4]; srow[17] = Q[5];
+            if (f_mine >= 0 && diag_owner) {
+                // diagonal block U - Y W^T = Jc^T (I - Q Jp^T) Jc, rhs = Jc^T (Q g_p - r), g_c = Jc^T r, diag U
+                float Jc[12];
 #pragma unroll
-                for (int k = 0; k < 12; ++k) s[k] = A.Jc[k];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) { s[12 + k] = A.Jp[k]; s[18 + k] = Q[k]; }
-                s[24] = __int_as_float(A.f >= 0 ? lcam : -1);
-            }
-            __syncwarp();
-            // ---- per observation: diagonal block U - Y W^T = Jc^T (I - Q Jp^T) Jc, rhs, g_c, diag U (not for the cross tiles A x B)
-            if (A.valid && A.f >= 0 && nB == 0) {
-                const double m00 = static_cast<double>(Q[0]) * A.Jp[0] + static_cast<double>(Q[1]) * A.Jp[1] + static_cast<double>(Q[2]) * A.Jp[2];
-                const double m01 = static_cast<double>(Q[0]) * A.Jp[3] + static_cast<double>(Q[1]) * A.Jp[4] + static_cast<double>(Q[2]) * A.Jp[5];
-                const double m11 = static_cast<double>(Q[3]) * A.Jp[3] + static_cast<double>(Q[4]) * A.Jp[4] + static_cast<double>(Q[5]) * A.Jp[5];
+                for (int q = 0; q < 3; ++q) {
+                    const float4 t4 = reinterpret_cast<const float4*>(srow)[q];
+                    Jc[4 * q] = t4.x; Jc[4 * q + 1] = t4.y; Jc[4 * q + 2] = t4.z; Jc[4 * q + 3] = t4.w;
+                }
+                const double m00 = static_cast<double>(Q[0]) * jp0 + static_cast<double>(Q[1]) * jp1 + static_cast<double>(Q[2]) * jp2;
+                const double m01 = static_cast<double>(Q[0]) * jp3 + static_cast<double>(Q[1]) * jp4 + static_cast<double>(Q[2]) * jp5;
+                const double m11 = static_cast<double>(Q[3]) * jp3 + static_cast<double>(Q[4]) * jp4 + static_cast<double>(Q[5]) * jp5;
                 const float n00 = static_cast<float>(1.0 - m00), n01 = static_cast<float>(-m01), n11 = static_cast<float>(1.0 - m11);
                 float T0[6], T1[6];
 #pragma unroll
-                for (int j = 0; j < 6; ++j) { T0[j] = n00 * A.Jc[j] + n01 * A.Jc[6 + j]; T1[j] = n01 * A.Jc[j] + n11 * A.Jc[6 + j]; }
+                for (int j = 0; j < 6; ++j) { T0[j] = n00 * Jc[j] + n01 * Jc[6 + j]; T1[j] = n01 * Jc[j] + n11 * Jc[6 + j]; }
                 float* blk = acc + (lcam * (lcam + 1) / 2 + lcam) * kBlkStride;
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
                     float row[6];
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) row[j] = A.Jc[i] * T0[j] + A.Jc[6 + i] * T1[j];
-                    smem_add6(blk + 6 * i, row);
+                    for (int j = 0; j < 6; ++j) row[j] = Jc[i] * T0[j] + Jc[6 + i] * T1[j];
+                    smem_add_row(blk + 6 * i, row);
                 }
-                const double q0 = Q[0] * gp[0] + Q[1] * gp[1] + Q[2] * gp[2] - A.r[0];
-                const double q1 = Q[3] * gp[0] + Q[4] * gp[1] + Q[5] * gp[2] - A.r[1];
+                const double r0 = rbuf[2 * tid], r1 = rbuf[2 * tid + 1];
+                const double* gp = ptg + 3 * unit;
+                const double q0 = Q[0] * gp[0] + Q[1] * gp[1] + Q[2] * gp[2] - r0;
+                const double q1 = Q[3] * gp[0] + Q[4] * gp[1] + Q[5] * gp[2] - r1;
                 double* ca = camacc + lcam * CV;
                 {
                     double v_rhs[6], v_gc[6], v_ud[6];
 #pragma unroll
                     for (int i = 0; i < 6; ++i) {
-                        const double j0 = A.Jc[i], j1 = A.Jc[6 + i];
+                        const double j0 = Jc[i], j1 = Jc[6 + i];
                         v_rhs[i] = j0 * q0 + j1 * q1;
-                        v_gc[i] = j0 * A.r[0] + j1 * A.r[1];
+                        v_gc[i] = j0 * r0 + j1 * r1;
                         v_ud[i] = j0 * j0 + j1 * j1;
                     }
                     smem_add6(ca, v_rhs);
@@ -434,73 +629,92 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                 }
                 if (kFocal) {
                     // border B_c = Jc^T Jf - Y Wf^T = Jc^T (Jf - Q Wf^T),  Jf = diag(xp, yp)
+                    const double* Wf = ptWf + 6 * unit;
+                    const double xp = xybuf[2 * tid], yp = xybuf[2 * tid + 1];
                     const double g00 = Q[0] * Wf[0] + Q[1] * Wf[1] + Q[2] * Wf[2], g01 = Q[0] * Wf[3] + Q[1] * Wf[4] + Q[2] * Wf[5];
                     const double g10 = Q[3] * Wf[0] + Q[4] * Wf[1] + Q[5] * Wf[2], g11 = Q[3] * Wf[3] + Q[4] * Wf[4] + Q[5] * Wf[5];
                     double v_b[12];
 #pragma unroll
                     for (int i = 0; i < 6; ++i) {
-                        const double j0 = A.Jc[i], j1 = A.Jc[6 + i];
-                        v_b[2 * i] = j0 * (A.xy[0] - g00) - j1 * g10;
-                        v_b[2 * i + 1] = -j0 * g01 + j1 * (A.xy[1] - g11);
+                        const double j0 = Jc[i], j1 = Jc[6 + i];
+                        v_b[2 * i] = j0 * (xp - g00) - j1 * g10;
+                        v_b[2 * i + 1] = -j0 * g01 + j1 * (yp - g11);
                     }
                     smem_add6(ca + 18, v_b);
                     smem_add6(ca + 24, v_b + 6);
                 }
             }
-            // ---- per camera pair (x < y): block (x, y) -= Jc_x^T (Q_x Jp_y^T) Jc_y
-            const int npairs = nB > 0 ? nA * nB : nA * (nA - 1) / 2;
-            for (int base = 0; base < npairs; base += 32) {
-                const int q = base + lane;
-                if (q < npairs) {
-                    int x, y;
-                    if (nB > 0) {
-                        x = q / nB; y = nA + (q - x * nB);
-                    } else {
-                        y = static_cast<int>((1.0f + sqrtf(1.0f + 8.0f * static_cast<float>(q))) * 0.5f);
-                        while (y * (y - 1) / 2 > q) --y;
-                        while ((y + 1) * y / 2 <= q) ++y;
-                        x = q - y * (y - 1) / 2;
-                    }
-                    const float* sx = stage + x * kStageStride;
-                    const float* sy = stage + y * kStageStride;
-                    const int lx = __float_as_int(sx[24]), ly = __float_as_int(sy[24]);
-                    if (lx >= 0 && ly >= 0) {
-                        const float m00 = sx[18] * sy[12] + sx[19] * sy[13] + sx[20] * sy[14];
-                        const float m01 = sx[18] * sy[15] + sx[19] * sy[16] + sx[20] * sy[17];
-                        const float m10 = sx[21] * sy[12] + sx[22] * sy[13] + sx[23] * sy[14];
-                        const float m11 = sx[21] * sy[15] + sx[22] * sy[16] + sx[23] * sy[17];
-                        float T0[6], T1[6];
+        }
+        __syncthreads();
+        // ---- D: all camera pairs of the tile, one per thread: block (x, y) -= Jc_x^T (Q_x Jp_y^T) Jc_y
+        {
+            const int total_pairs = pair_start[n_units];
+            for (int q = tid; q < total_pairs; q += kFusedThreads) {
+                int lo = 0, hi = n_units - 1;                        // largest unit with pair_start[unit] <= q
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (pair_start[mid] <= q) lo = mid; else hi = mid - 1;
+                }
+                const uint32_t ui = unit_info[lo];
+                const int ql = q - pair_start[lo];
+                const int ob = static_cast<int>(ui & 0xFFFFu);
+                int x, y;
+                if (split && (ui >> 24) != 0) {
+                    const int nA = static_cast<int>((ui >> 16) & 0xFFu), nB = static_cast<int>(ui >> 24);
+                    x = ql / nB; y = nA + (ql - x * nB);
+                } else {
+                    y = static_cast<int>((1.0f + sqrtf(1.0f + 8.0f * static_cast<float>(ql))) * 0.5f);
+                    while (y * (y - 1) / 2 > ql) --y;
+                    while ((y + 1) * y / 2 <= ql) ++y;
+                    x = ql - y * (y - 1) / 2;
+                }
+                const float4* sx = reinterpret_cast<const float4*>(stage + (ob + x) * kStageStride);
+                const float4* sy = reinterpret_cast<const float4*>(stage + (ob + y) * kStageStride);
+                const float4 x6 = sx[6], y6 = sy[6];
+                const int lx = __float_as_int(x6.x), ly = __float_as_int(y6.x);
+                if (lx < 0 || ly < 0) continue;
+                const float4 xq0 = sx[3], xq1 = sx[4];                  // Q_x = (xq0.xyzw, xq1.xy)
+                const float4 yp0 = sy[4], yp1 = sy[5];                  // Jp_y = (yp0.zw, yp1.xyzw)
+                const float m00 = xq0.x * yp0.z + xq0.y * yp0.w + xq0.z * yp1.x;
+                const float m01 = xq0.x * yp1.y + xq0.y * yp1.z + xq0.z * yp1.w;
+                const float m10 = xq0.w * yp0.z + xq1.x * yp0.w + xq1.y * yp1.x;
+                const float m11 = xq0.w * yp1.y + xq1.x * yp1.z + xq1.y * yp1.w;
+                float Jy[12], Jx[12];
+                {
+                    const float4 a0 = sy[0], a1 = sy[1], a2 = sy[2];
+                    Jy[0] = a0.x; Jy[1] = a0.y; Jy[2] = a0.z; Jy[3] = a0.w; Jy[4] = a1.x; Jy[5] = a1.y;
+                    Jy[6] = a1.z; Jy[7] = a1.w; Jy[8] = a2.x; Jy[9] = a2.y; Jy[10] = a2.z; Jy[11] = a2.w;
+                    const float4 b0 = sx[0], b1 = sx[1], b2 = sx[2];
+                    Jx[0] = b0.x; Jx[1] = b0.y; Jx[2] = b0.z; Jx[3] = b0.w; Jx[4] = b1.x; Jx[5] = b1.y;
+                    Jx[6] = b1.z; Jx[7] = b1.w; Jx[8] = b2.x; Jx[9] = b2.y; Jx[10] = b2.z; Jx[11] = b2.w;
+                }
+                float T0[6], T1[6];
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) {
-                            const float c0 = sy[j], c1 = sy[6 + j];
-                            T0[j] = -(m00 * c0 + m01 * c1);
-                            T1[j] = -(m10 * c0 + m11 * c1);
-                        }
-                        float* blk = acc + (ly * (ly + 1) / 2 + lx) * kBlkStride;
+                for (int j = 0; j < 6; ++j) {
+                    T0[j] = -(m00 * Jy[j] + m01 * Jy[6 + j]);
+                    T1[j] = -(m10 * Jy[j] + m11 * Jy[6 + j]);
+                }
+                float* blk = acc + (ly * (ly + 1) / 2 + lx) * kBlkStride;
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) {
-                            const float a0 = sx[i], a1 = sx[6 + i];
-                            float row[6];
+                for (int i = 0; i < 6; ++i) {
+                    float row[6];
 #pragma unroll
-                            for (int j = 0; j < 6; ++j) row[j] = a0 * T0[j] + a1 * T1[j];
-                            smem_add6(blk + 6 * i, row);
-                        }
-                    }
+                    for (int j = 0; j < 6; ++j) row[j] = Jx[i] * T0[j] + Jx[6 + i] * T1[j];
+                    smem_add_row(blk + 6 * i, row);
                 }
             }
-            __syncwarp();          // the staging area is rewritten for the next point
         }
         __syncthreads();
         // ---- flush the tile: 6x6 blocks with vector reductions, camera vectors with fp64 reductions
         const int32_t* slots = P.tile_slots + T.slot_begin;
-        for (int u = threadIdx.x; u < nb * 9; u += blockDim.x) {
+        for (int u = tid; u < nb * 9; u += kFusedThreads) {
             const int b = u / 9, q4 = u - 9 * b;
             const int slot = __ldg(slots + b);
             if (slot < 0) continue;
-            const float* a = acc + b * kBlkStride + 4 * q4;
-            atomicAdd(reinterpret_cast<float4*>(P.sblk + static_cast<size_t>(slot) * 36) + q4, make_float4(a[0], a[1], a[2], a[3]));
+            const float4 v4 = reinterpret_cast<const float4*>(acc + b * kBlkStride)[q4];
+            atomicAdd(reinterpret_cast<float4*>(P.sblk + static_cast<size_t>(slot) * 36) + q4, v4);
         }
-        for (int u = threadIdx.x; u < T.w * CV; u += blockDim.x) {
+        for (int u = tid; u < T.w * CV; u += kFusedThreads) {
             const int l = u / CV, e = u - l * CV;
             const int f = lfree[l];
             if (f < 0) continue;
@@ -514,27 +728,28 @@ fused_linearize_kernel(Problem P, double inv_radius) {
         __syncthreads();
     }
     // ---- scalars: one fp64 atomic per CTA
-    __shared__ double sh_c[8], sh_g[8];
+    __shared__ double sh_c[kFusedThreads / 32], sh_g[kFusedThreads / 32];
     cost_local = warp_sum(cost_local);
     gpmax_local = warp_max(gpmax_local);
     if (lane == 0) { sh_c[warp] = cost_local; sh_g[warp] = gpmax_local; }
     __syncthreads();
     if (kFocal) {
-        __shared__ double sh_f[8][9];
-        if (lane == 0) {
+        __shared__ double sh_f[kFusedThreads / 32][9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) sh_f[warp][k] = ff[k];
+        for (int k = 0; k < 9; ++k) {
+            const double v = warp_sum(ff[k]);
+            if (lane == 0) sh_f[warp][k] = v;
         }
         __syncthreads();
-        if (threadIdx.x < 9) {
+        if (tid < 9) {
             double v = 0.0;
-            for (int k = 0; k < nwarps; ++k) v += sh_f[k][threadIdx.x];
-            atomicAdd(tail + P.tl.ff + threadIdx.x, v);
+            for (int k = 0; k < kFusedThreads / 32; ++k) v += sh_f[k][tid];
+            atomicAdd(tail + P.tl.ff + tid, v);
         }
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         double c = 0.0, g = 0.0;
-        for (int k = 0; k < nwarps; ++k) { c += sh_c[k]; g = fmax(g, sh_g[k]); }
+        for (int k = 0; k < kFusedThreads / 32; ++k) { c += sh_c[k]; g = fmax(g, sh_g[k]); }
         atomicAdd(tail + P.tl.scal, c);
         // max of non-negative doubles == max of their bit patterns
         atomicMax(reinterpret_cast<unsigned long long*>(tail + P.tl.gpm + P.gpm_slot), static_cast<unsigned long long>(__double_as_longlong(g)));
@@ -674,19 +889,24 @@ cudaError_t ba_launch_track_errors(const Problem& P, double* err, int num_sms, c
     track_error_kernel<<<grid, 256, 0, st>>>(P, err);
     return cudaGetLastError();
 }
-size_t ba_fused_smem_bytes(int w_cap, bool focal) { return fused_smem_bytes(w_cap, 256, focal); }
+size_t ba_fused_smem_bytes(bool focal) { return fused_smem_layout(focal).total; }
 // The system buffers (tail, tile counter, sblk) must be zero.
 cudaError_t ba_launch_linearize(const Problem& P, double inv_radius, int num_sms, cudaStream_t st) {
     if (P.n_tiles <= 0) return cudaSuccess;
-    const size_t smem = fused_smem_bytes(P.w_cap, 256, P.refine_focal != 0);
+    if (P.n_long > 0) {
+        int g = (P.n_long + 7) / 8;
+        if (g > num_sms * 4) g = num_sms * 4;
+        if (P.refine_focal) long_track_prepass_kernel<true><<<g, 256, 0, st>>>(P, inv_radius);
+        else long_track_prepass_kernel<false><<<g, 256, 0, st>>>(P, inv_radius);
+    }
+    const size_t smem = fused_smem_layout(P.refine_focal != 0).total;
     cudaError_t e;
     if (P.refine_focal) e = cudaFuncSetAttribute(fused_linearize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     else e = cudaFuncSetAttribute(fused_linearize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    const int per_sm = smem <= 112 * 1024 ? 2 : 1;
-    const int grid = P.n_tiles < num_sms * per_sm ? P.n_tiles : num_sms * per_sm;
-    if (P.refine_focal) fused_linearize_kernel<true><<<grid, 256, smem, st>>>(P, inv_radius);
-    else fused_linearize_kernel<false><<<grid, 256, smem, st>>>(P, inv_radius);
+    const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
+    if (P.refine_focal) fused_linearize_kernel<true><<<grid, kFusedThreads, smem, st>>>(P, inv_radius);
+    else fused_linearize_kernel<false><<<grid, kFusedThreads, smem, st>>>(P, inv_radius);
     return cudaGetLastError();
 }
 cudaError_t ba_launch_expand_dense(const Problem& P, double inv_radius, double* S, cudaStream_t st) {

@@ -16,9 +16,9 @@ namespace msfm {
 namespace ba {
 
 struct TilingParams {
-    int w_cap = 32;            // max local cameras per tile (32 .. kMaxWCap)
-    int max_pts = 256;         // max points (items) per tile
-    long long max_work = 1 << 15;   // max sum of k (k + 1) / 2 per tile
+    int max_pts = kTilePts;    // max points per normal tile (<= kTilePts)
+    int max_obs = kTileObs;    // max observations per normal tile (<= kTileObs)
+    int max_items = kTileItems;
 };
 
 struct Tiling {
@@ -26,6 +26,8 @@ struct Tiling {
     std::vector<int32_t> pt_start;      // [n_pts + 1] CSR over device-ordered observations
     std::vector<int32_t> obs_perm;      // device observation -> caller's observation
     std::vector<uint8_t> obs_lcam;      // device observation -> local camera of its (normal) tile
+    std::vector<uint8_t> obs_lpt;       // device observation -> index of its point inside its (normal) tile
+    int first_long = 0, n_long = 0;     // device points [first_long, first_long + n_long): more than 32 observations
     std::vector<Tile> tiles;
     std::vector<Item> items;
     std::vector<int32_t> tile_cams;
@@ -72,13 +74,16 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
     T.pt_start.assign(size_t(n_pts) + 1, 0);
     T.obs_perm.resize(static_cast<size_t>(n_obs));
     T.obs_lcam.assign(static_cast<size_t>(n_obs), 0);
+    T.obs_lpt.assign(static_cast<size_t>(n_obs), 0);
     for (int d = 0; d < n_pts; ++d) {
         const int p = T.pt_order[d];
         const int k = start[size_t(p) + 1] - start[p];
         T.pt_start[size_t(d) + 1] = T.pt_start[d] + k;
         std::copy(sorted_obs.begin() + start[p], sorted_obs.begin() + start[size_t(p) + 1], T.obs_perm.begin() + T.pt_start[d]);
     }
-    const int w_cap = std::max(32, std::min(prm.w_cap, kMaxWCap));   // an item holds up to 32 cameras
+    const int w_cap = kTileCams;
+    const int max_pts = std::max(1, std::min(prm.max_pts, kTilePts)), max_obs = std::max(32, std::min(prm.max_obs, kTileObs));
+    const int max_items = std::max(1, std::min(prm.max_items, kTileItems));
     std::vector<int32_t> stamp(static_cast<size_t>(std::max(1, n_cams)), -1), lidx(static_cast<size_t>(std::max(1, n_cams)), 0);
     T.tiles.clear(); T.items.clear(); T.tile_cams.clear(); T.tile_marks.clear();
     T.w_max = 0;
@@ -89,6 +94,7 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
         std::sort(cams.begin(), cams.end());
         Tile t{};
         t.begin = d0; t.end = d1;
+        t.obs_begin = T.pt_start[d0]; t.n_obs = T.pt_start[d1] - T.pt_start[d0];
         t.cam_begin = static_cast<int32_t>(T.tile_cams.size());
         t.w = static_cast<int32_t>(cams.size());
         t.slot_begin = static_cast<int32_t>(T.tile_marks.size());
@@ -101,6 +107,7 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
                 const int ca = cam_of(a);
                 const int la = lidx[ca];
                 T.obs_lcam[a] = static_cast<uint8_t>(la);
+                T.obs_lpt[a] = static_cast<uint8_t>(d - d0);
                 if (cam_free[ca] < 0) continue;
                 for (int b = a; b < T.pt_start[size_t(d) + 1]; ++b) {
                     const int cb = cam_of(b);
@@ -113,28 +120,29 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
     };
     std::vector<int32_t> cams;
     int d0 = 0, tile_id = 0, first_long = n_pts;
-    long long work = 0;
+    int tile_obs = 0;
     for (int d = 0; d < n_pts; ++d) {
         const int beg = T.pt_start[d], k = T.pt_start[size_t(d) + 1] - beg;
         if (k == 0 || k > 32) { first_long = d; break; }                 // classes are sorted: normal | long | unobserved
         int fresh = 0;
         for (int a = beg; a < beg + k; ++a)
             if (stamp[cam_of(a)] != tile_id) ++fresh;
-        const long long pw = static_cast<long long>(k) * (k + 1) / 2;
-        if (d > d0 && (int(cams.size()) + fresh > w_cap || d - d0 >= prm.max_pts || work + pw > prm.max_work)) {
+        if (d > d0 && (int(cams.size()) + fresh > w_cap || d - d0 >= max_pts || tile_obs + k > max_obs)) {
             close_tile(d0, d, cams);
-            ++tile_id; work = 0; d0 = d;
+            ++tile_id; tile_obs = 0; d0 = d;
         }
         for (int a = beg; a < beg + k; ++a) {
             const int c = cam_of(a);
             if (stamp[c] != tile_id) { stamp[c] = tile_id; cams.push_back(c); }
         }
-        work += pw;
+        tile_obs += k;
     }
     close_tile(d0, first_long, cams);
+    T.first_long = first_long;
+    T.n_long = 0;
     // ---- item tiles: long tracks cut into groups of 16 observations; one open tile per (group A, group B) index pair, so
     //      that the items of neighbouring long points (nearly the same cameras) are packed together
-    struct Open { std::vector<int32_t> cams; std::vector<Item> items; long long work = 0; };
+    struct Open { std::vector<int32_t> cams; std::vector<Item> items; };
     std::vector<Open> open;                    // index gi * ng_max + gj, grown on demand
     int ng_max = 0;
     auto close_items = [&](Open& o) {
@@ -178,6 +186,7 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
     for (int d = first_long; d < n_pts; ++d) {
         const int beg = T.pt_start[d], k = T.pt_start[size_t(d) + 1] - beg;
         if (k == 0) break;
+        T.n_long += 1;
         const int ng = (k + 15) / 16;
         if (ng > ng_max) {                         // re-index the open tiles for the larger group count
             std::vector<Open> grown(size_t(ng) * ng);
@@ -192,7 +201,6 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
                 it.d = d;
                 it.a0 = static_cast<uint16_t>(gi * 16); it.a1 = static_cast<uint16_t>(std::min(k, gi * 16 + 16));
                 if (gj != gi) { it.b0 = static_cast<uint16_t>(gj * 16); it.b1 = static_cast<uint16_t>(std::min(k, gj * 16 + 16)); }
-                it.primary = (gi == 0 && gj == 0) ? 1 : 0;
                 const int na = it.a1 - it.a0, nb = it.b1 - it.b0;
                 Open& o = open[size_t(gi) * ng_max + gj];
                 int fresh = 0;
@@ -200,15 +208,12 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
                     const int c = cam_of(beg + (l < na ? it.a0 + l : it.b0 + l - na));
                     if (std::find(o.cams.begin(), o.cams.end(), c) == o.cams.end()) ++fresh;
                 }
-                const long long pw = nb ? static_cast<long long>(na) * nb : static_cast<long long>(na) * (na + 1) / 2;
-                if (!o.items.empty() && (int(o.cams.size()) + fresh > w_cap || int(o.items.size()) >= prm.max_pts || o.work + pw > prm.max_work))
-                    close_items(o);
+                if (!o.items.empty() && (int(o.cams.size()) + fresh > w_cap || int(o.items.size()) >= max_items)) close_items(o);
                 for (int l = 0; l < na + nb; ++l) {
                     const int c = cam_of(beg + (l < na ? it.a0 + l : it.b0 + l - na));
                     if (std::find(o.cams.begin(), o.cams.end(), c) == o.cams.end()) o.cams.push_back(c);
                 }
                 o.items.push_back(it);
-                o.work += pw;
             }
     }
     for (Open& o : open) close_items(o);

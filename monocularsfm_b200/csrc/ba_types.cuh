@@ -15,30 +15,33 @@ struct CamPre {
     double pad;
 };
 
-// A tile = a set of points that together touch at most w_cap cameras.  One CTA linearises one tile at a time and
-// accumulates the tile's share of the reduced camera system in shared memory: the upper triangle of 6x6 blocks over the
-// tile's LOCAL camera list, flushed once per tile into the global block-sparse S.
-//   normal tile: device points [begin, end), each observed by at most 32 cameras (one lane per observation);
-//   item tile:   items [begin, end) (struct Item): a point observed by more than 32 cameras is cut into groups of 16
-//                observations; an item couples group A with group B (or A with itself, which also owns A's diagonal blocks).
-//                Items of neighbouring long points with the same (A, B) group indices share cameras and are packed together.
+// A tile = a set of points that together touch at most kTileCams cameras and hold at most kTileObs observations.  One CTA
+// linearises one tile at a time and accumulates the tile's share of the reduced camera system in shared memory: the upper
+// triangle of 6x6 blocks over the tile's LOCAL camera list, flushed once per tile into the global block-sparse S.
+//   normal tile: device points [begin, end) (at most kTilePts), each observed by at most 32 cameras; their observations are
+//                the contiguous device range [obs_begin, obs_begin + n_obs);
+//   item tile:   items [begin, end) (at most kTileItems, struct Item): a point observed by more than 32 cameras is cut into
+//                groups of 16 observations; an item couples group A with group B (or A with itself, which also owns A's
+//                diagonal blocks).  Items of neighbouring long points with the same (A, B) group indices are packed together.
 struct Tile {
     int32_t begin, end;           // device points (normal) or items (kTileSplit)
+    int32_t obs_begin, n_obs;     // normal tiles: device observations [obs_begin, obs_begin + n_obs)
     int32_t cam_begin, w;         // local cameras: tile_cams[cam_begin .. cam_begin + w), ascending global camera index
     int32_t slot_begin;           // tile_slots[slot_begin + lb (lb + 1) / 2 + la] (la <= lb): global block slot or -1
     int32_t flags;                // kTileSplit
-    int32_t pad[2];
 };
 struct Item {
     int32_t d;                    // device point
     uint16_t a0, a1, b0, b1;      // observation positions [a0, a1) = group A, [b0, b1) = group B (empty: pairs inside A)
-    uint16_t primary;             // 1: this item accounts the point's cost / gradient maximum / focal sums (exactly one per point)
-    uint16_t pad;
+    uint16_t pad[2];
     uint8_t lc[32];               // local camera of lane l: lanes 0 .. nA-1 hold group A, nA .. nA+nB-1 group B
 };
 constexpr int32_t kTileSplit = 1;
-constexpr int kBlkStride = 37;         // 36 floats of a 6x6 block + 1: conflict-free shared-memory banks across blocks
-constexpr int kMaxWCap = 40;           // local cameras per tile (shared-memory accumulator = w (w+1)/2 blocks)
+constexpr int kTileCams = 32;          // local cameras per tile (shared-memory accumulator = 528 blocks)
+constexpr int kTileObs = 512;          // observations per tile = threads of the linearisation kernel
+constexpr int kTilePts = 256;          // points per normal tile
+constexpr int kTileItems = 16;         // items per item tile (32 observation lanes each)
+constexpr int kBlkStride = 36;         // floats per 6x6 block in the shared-memory accumulator (16-byte aligned rows of 4)
 
 // Offsets (in doubles) into the fp64 "tail" of the system: everything of the reduced system that is not a 6x6 block.
 struct TailLayout {
@@ -62,6 +65,7 @@ struct Problem {
     const int32_t* obs_pt;      // [n_obs]      device order: the caller's point index
     const int32_t* obs_orig;    // [n_obs]      device order -> the caller's observation index
     const uint8_t* obs_lcam;    // [n_obs]      index of the camera in the local list of the observation's tile
+    const uint8_t* obs_lpt;     // [n_obs]      index of the observation's point inside its (normal) tile
     const int32_t* pt_start;    // [n_pts+1]    CSR over device-ordered observations, indexed by DEVICE point
     const int32_t* pt_order;    // [n_pts]      device point -> caller's point index
     const int32_t* cam_free;    // [n_cams] index among the free cameras or -1 (constant pose)
@@ -71,7 +75,8 @@ struct Problem {
     int32_t n_tiles;
     const int32_t* tile_cams;
     const int32_t* tile_slots;
-    int32_t w_cap;                  // max local cameras of any tile
+    int32_t first_long, n_long;     // device points [first_long, first_long + n_long) are long tracks (more than 32 observations)
+    double* long_V;                 // [n_long][9 (+6)]  per long track: V^-1 (6) | g_p (3) (| Wf (6)), written by the pre-pass
     int32_t n_blocks;               // non-empty 6x6 blocks of the upper block triangle (diagonal included)
     const int32_t* blk_row;         // [n_blocks] free-camera row fa
     const int32_t* blk_col;         // [n_blocks] free-camera column fb >= fa

@@ -73,6 +73,10 @@ struct msfm_ctx {
     msfm::GrowBuf d_segs, d_units, d_items, d_res, d_m, d_exact, d_counts, d_misc;
     msfm::GrowBuf d_out_offsets, d_out_matches, d_out_dist;
     msfm::GrowBuf d_ba_r, d_ba_J;                  // msfm_ba_evaluate parity dumps
+    // ---- geometric verification: resident keypoint positions per image, call tables, staged match lists / masks
+    struct KpHost { void* xy = nullptr; int32_t n = 0; };
+    std::unordered_map<int32_t, KpHost> kps;
+    msfm::GrowBuf d_kp_tab, d_kp_slots, d_vf_in, d_vf_out;
     int64_t stats[4] = {0, 0, 0, 0};
 
     // ---- B-path / multi-GPU

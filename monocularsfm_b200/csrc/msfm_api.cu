@@ -96,7 +96,10 @@ void msfm_destroy(msfm_ctx* c) {
     for (auto& im : c->imgs)
         if (im.block) cudaFree(im.block);
     GrowBuf* bufs[] = {&c->d_imgs, &c->d_raw, &c->d_fmt, &c->d_temp, &c->h_stage, &c->d_segs, &c->d_units, &c->d_items, &c->d_res, &c->d_m, &c->d_exact,
-                       &c->d_counts, &c->d_misc, &c->d_out_offsets, &c->d_out_matches, &c->d_out_dist, &c->d_ba_r, &c->d_ba_J};
+                       &c->d_counts, &c->d_misc, &c->d_out_offsets, &c->d_out_matches, &c->d_out_dist, &c->d_ba_r, &c->d_ba_J,
+                       &c->d_kp_tab, &c->d_kp_slots, &c->d_vf_in, &c->d_vf_out};
+    for (auto& kv : c->kps)
+        if (kv.second.xy) cudaFree(kv.second.xy);
     for (GrowBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         c->d_rawq[i].release();

@@ -1,7 +1,8 @@
 // Test driver of the drop-in C++ classes (run by tests/test_host_cpp.py).
 //   host_test cpu <tmp.db>             Database round trip, pair ids, CrossCheck quirk, distance filter  (no GPU)
-//   host_test match <db> <preempt 0|1> BruteFeatureMatcher(db).RunMatching() on a database made by the Python test
-//   host_test seq <db>                 SequentialFeatureMatcher(db).RunMatching()
+//   host_test match <db> <preempt 0|1> [noverify]  BruteFeatureMatcher(db).RunMatching() on a database made by the Python test
+//   host_test seq <db> [noverify]                  SequentialFeatureMatcher(db).RunMatching()
+//   (noverify = the explicit opt-out of the geometric verification, for tests of the exact match lists)
 //   host_test two <a.u8> <na> <b.u8> <nb> <out.txt>   FeatureUtils::ComputeMatches / ComputeCrossMatches on raw files
 //   host_test ba <in.bin> <out.bin>    CeresBundelOptimizer::Optimize on a BundleData read from a flat binary file
 //   host_test ransac <in.bin> <out.bin>  FeatureUtils::FilterMatches on float32 point pairs (no GPU)
@@ -284,11 +285,13 @@ int main(int argc, char** argv) {
     if (mode == "cpu" && argc >= 3) return test_cpu(argv[2]);
     if (mode == "match" && argc >= 4) {
         BruteFeatureMatcher matcher(argv[2], 100, std::atoi(argv[3]) != 0);
+        if (argc >= 5 && std::string(argv[4]) == "noverify") matcher.SetGeometricFilter(FeatureMatcher::GeometricFilter());
         matcher.RunMatching();
         return 0;
     }
     if (mode == "seq" && argc >= 3) {
         SequentialFeatureMatcher matcher(argv[2]);
+        if (argc >= 4 && std::string(argv[3]) == "noverify") matcher.SetGeometricFilter(FeatureMatcher::GeometricFilter());
         matcher.RunMatching();
         return 0;
     }

@@ -22,45 +22,47 @@ def harness(tmp_path_factory):
     lib = C.CDLL(so)
     ip = C.POINTER(C.c_int32)
     lib.tiling_build.restype = C.c_int
-    lib.tiling_build.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, C.c_int, C.c_int, C.c_int, C.c_longlong, ip]
+    lib.tiling_build.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, C.c_int, C.c_int, C.c_int, C.c_int, ip]
     lib.tiling_fetch.restype = None
-    lib.tiling_fetch.argtypes = [ip, ip, ip, C.POINTER(C.c_uint8), ip, ip, ip, ip, ip, ip]
+    lib.tiling_fetch.argtypes = [ip, ip, ip, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), ip, ip, ip, ip, ip, ip]
     return lib
 
 
-def run_tiling(lib, P, w_cap=32, max_pts=64, max_work=1 << 15):
+def run_tiling(lib, P, max_obs=512, max_pts=64, max_items=16):
     oc = np.ascontiguousarray(P["obs_cam"], np.int32)
     op = np.ascontiguousarray(P["obs_pt"], np.int32)
     const = np.asarray(P["cam_const"]).astype(bool)
     cam_free = -np.ones(len(const), np.int32)
     cam_free[~const] = np.arange((~const).sum(), dtype=np.int32)
     ip = C.POINTER(C.c_int32)
-    sizes = np.zeros(6, np.int32)
+    sizes = np.zeros(8, np.int32)
     rc = lib.tiling_build(len(const), len(P["pts"]), len(oc), oc.ctypes.data_as(ip), op.ctypes.data_as(ip),
-                          cam_free.ctypes.data_as(ip), int((~const).sum()), w_cap, max_pts, max_work, sizes.ctypes.data_as(ip))
+                          cam_free.ctypes.data_as(ip), int((~const).sum()), max_obs, max_pts, max_items, sizes.ctypes.data_as(ip))
     if rc:
         return None
-    n_tiles, n_tc, n_marks, n_blocks, w_max, n_items = [int(x) for x in sizes]
+    n_tiles, n_tc, n_marks, n_blocks, w_max, n_items, first_long, n_long = [int(x) for x in sizes]
     T = {"pt_order": np.zeros(len(P["pts"]), np.int32), "pt_start": np.zeros(len(P["pts"]) + 1, np.int32),
-         "obs_perm": np.zeros(len(oc), np.int32), "obs_lcam": np.zeros(len(oc), np.uint8),
+         "obs_perm": np.zeros(len(oc), np.int32), "obs_lcam": np.zeros(len(oc), np.uint8), "obs_lpt": np.zeros(len(oc), np.uint8),
+         "first_long": first_long, "n_long": n_long,
          "tiles": np.zeros((n_tiles, 8), np.int32), "items_raw": np.zeros((n_items, 12), np.int32), "tile_cams": np.zeros(n_tc, np.int32),
          "tile_slots": np.zeros(n_marks, np.int32), "blk_row": np.zeros(n_blocks, np.int32),
          "blk_col": np.zeros(n_blocks, np.int32), "w_max": w_max, "cam_free": cam_free}
     lib.tiling_fetch(T["pt_order"].ctypes.data_as(ip), T["pt_start"].ctypes.data_as(ip), T["obs_perm"].ctypes.data_as(ip),
-                     T["obs_lcam"].ctypes.data_as(C.POINTER(C.c_uint8)), T["tiles"].ctypes.data_as(ip),
+                     T["obs_lcam"].ctypes.data_as(C.POINTER(C.c_uint8)), T["obs_lpt"].ctypes.data_as(C.POINTER(C.c_uint8)),
+                     T["tiles"].ctypes.data_as(ip),
                      T["items_raw"].ctypes.data_as(ip), T["tile_cams"].ctypes.data_as(ip), T["tile_slots"].ctypes.data_as(ip), T["blk_row"].ctypes.data_as(ip),
                      T["blk_col"].ctypes.data_as(ip))
-    # struct Item { int32 d; uint16 a0, a1, b0, b1, primary, pad; uint8 lc[32]; }
+    # struct Item { int32 d; uint16 a0, a1, b0, b1, pad[2]; uint8 lc[32]; }
     raw = T["items_raw"].view(np.uint8).reshape(n_items, 48)
     h = raw[:, 4:16].copy().view(np.uint16).reshape(n_items, 6)
     T["items"] = [{"d": int(T["items_raw"][i, 0]), "a0": int(h[i, 0]), "a1": int(h[i, 1]), "b0": int(h[i, 2]), "b1": int(h[i, 3]),
-                   "primary": int(h[i, 4]), "lc": raw[i, 16:48].astype(int)} for i in range(n_items)]
+                   "primary": int(h[i, 0] == 0 and h[i, 2] == 0 and h[i, 3] == 0), "lc": raw[i, 16:48].astype(int)} for i in range(n_items)]
     return T
 
 
 def tile_units(T, t):
     """(device point, selected observation positions or None, local cameras or None, nA, nB, primary) of every unit of a tile."""
-    b, e, cb, w, sb, flags = [int(x) for x in t[:6]]
+    b, e, ob, no, cb, w, sb, flags = [int(x) for x in t[:8]]
     out = []
     if flags & 1:
         for it in T["items"][b:e]:
@@ -95,9 +97,14 @@ def test_tiling_invariants(harness, which):
     covered = np.zeros(n_pts, int)
     pair_count = {}
     for t in T["tiles"]:
-        b0_, e0_, cb, w, sb, flags = [int(x) for x in t[:6]]
+        b0_, e0_, ob_, no_, cb, w, sb, flags = [int(x) for x in t[:8]]
         cams = T["tile_cams"][cb:cb + w]
         assert w <= 32 and (np.diff(cams) > 0).all()
+        if flags & 1:
+            assert e0_ - b0_ <= 16
+        else:
+            assert e0_ - b0_ <= 256 and no_ <= 512 and ob_ == T["pt_start"][b0_] and ob_ + no_ == T["pt_start"][e0_]
+            assert (T["obs_lpt"][ob_:ob_ + no_] == np.repeat(np.arange(e0_ - b0_), np.diff(T["pt_start"][b0_:e0_ + 1]))).all()
         for d, sel, lc, nA, nB, primary in tile_units(T, t):
             s0, e0 = int(T["pt_start"][d]), int(T["pt_start"][d + 1])
             if sel is None:
@@ -134,13 +141,14 @@ def test_items_of_neighbouring_long_tracks_are_packed(harness):
     sys.path.insert(0, ROOT)
     import bench
     P = bench.make_ba_problem(128, 20000, 10.0, 4321)
-    T = run_tiling(harness, P, 32, 42)
-    split = (T["tiles"][:, 5] & 1) == 1
+    T = run_tiling(harness, P, 512, 256)
+    split = (T["tiles"][:, 7] & 1) == 1
     assert len(T["items"]) > 1000
     # a cross item holds 32 cameras = the whole tile budget, so only long tracks that start at the same camera share a tile
     assert split.sum() * 3 <= len(T["items"])
-    npts = T["tiles"][~split, 1] - T["tiles"][~split, 0]
-    assert npts.mean() > 25
+    nobs = T["tiles"][~split, 3]
+    assert nobs.mean() > 250 and np.median(nobs) > 400   # most normal tiles fill their 512 observation slots (not at the ring's wrap-around)
+    assert T["n_long"] == int((np.diff(T["pt_start"]) > 32).sum())
 
 
 def test_duplicate_camera_rejected(harness):
@@ -168,7 +176,7 @@ def test_tile_accumulation_emulation_matches_dense_schur(harness, which):
     sblk = np.zeros((len(T["blk_row"]), 6, 6))
     rhs = np.zeros((nf, 6)); udiag = np.zeros((nf, 6))
     for t in T["tiles"]:
-        cb, w, sb = int(t[2]), int(t[3]), int(t[4])
+        cb, w, sb = int(t[4]), int(t[5]), int(t[6])
         lfree = cf[T["tile_cams"][cb:cb + w]]
         acc = np.zeros((w * (w + 1) // 2, 6, 6))
         camacc = np.zeros((w, 12))

@@ -44,9 +44,11 @@ def _sift_like(rng, n):
     return np.clip(np.rint(x), 0, 255).astype(np.uint8)
 
 
-def _make_db(path, rng, sizes):
-    """Reference-format database: image ids 0..N-1 (FeatureExtraction writes explicit ids), float32 descriptor blobs with
-    integral values (un-normalised SIFT), keypoints with distinct sizes."""
+def _make_db(path, rng, sizes, normalised=False):
+    """Reference-format database: image ids 0..N-1 (FeatureExtraction writes explicit ids), float32 descriptor blobs —
+    integral values (un-normalised SIFT) or, with normalised=True, the same rows divided by 512 (unit-norm floats as the
+    reference's extraction stores them; the x512 quantisation of the device bridge recovers the integers exactly) —
+    and keypoints with distinct sizes."""
     con = sqlite3.connect(path)
     con.executescript("""
         CREATE TABLE images(image_id INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, name TEXT NOT NULL UNIQUE);
@@ -74,7 +76,8 @@ def _make_db(path, rng, sizes):
                                                                              # are its smallest: preemption drops its pairs
         con.execute("insert into images(image_id, name) values(?, ?)", (i, f"img{i}.jpg"))
         con.execute("insert into keypoints values(?,?,?,?)", (i, n, 4, kp.tobytes()))
-        con.execute("insert into descriptors values(?,?,?,?)", (i, n, 128, d.astype(np.float32).tobytes()))
+        con.execute("insert into descriptors values(?,?,?,?)",
+                    (i, n, 128, (d.astype(np.float32) / (512.0 if normalised else 1.0)).astype(np.float32).tobytes()))
         descs.append(d)
         scales.append(kp[:, 2])
     con.commit()
@@ -98,8 +101,8 @@ def test_brute_feature_matcher_on_reference_database(tmp_path, preempt):
     rng = np.random.default_rng(21 + preempt)
     db = str(tmp_path / "m.db")
     sizes = [900, 700, 1100, 300]
-    descs, scales = _make_db(db, rng, sizes)
-    out = subprocess.run([EXE, "match", db, str(preempt)], capture_output=True, text=True, timeout=300)
+    descs, scales = _make_db(db, rng, sizes, normalised=True)
+    out = subprocess.run([EXE, "match", db, str(preempt), "noverify"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr + out.stdout
     got = _read_matches(db)
     n_kept = 0
@@ -116,13 +119,14 @@ def test_brute_feature_matcher_on_reference_database(tmp_path, preempt):
                 assert pid not in got
                 continue
             n_kept += 1
-            # MatchImagePairs(i, j): query = image i, train = image j; max_distance 0.7 on the x512 scale
+            # MatchImagePairs(i, j): query = image i, train = image j; max_distance 0.7 of the unit-norm floats = 0.7 x 512 on
+            # the quantised scale
             em, _ = mo.match_image_pair(descs[i], descs[j], 0.8, 0.7 * 512.0, True, True)
             stored = em[:, ::-1] if i > j else em                             # swapped to id1 < id2 orientation on disk
             np.testing.assert_array_equal(got[pid], stored, err_msg=f"pair {i}-{j}")
     assert n_kept == (3 if preempt else 6), n_kept        # preemption keeps the pairs among images 0..2 only
     # resume: a second run finds every row and changes nothing
-    out = subprocess.run([EXE, "match", db, str(preempt)], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([EXE, "match", db, str(preempt), "noverify"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "Existing" in out.stdout
     again = _read_matches(db)
     assert set(again) == set(got)
@@ -135,13 +139,17 @@ def test_sequential_feature_matcher(tmp_path):
     db = str(tmp_path / "s.db")
     sizes = [400, 500, 450, 300, 350]
     descs, _ = _make_db(db, rng, sizes)
-    out = subprocess.run([EXE, "seq", db], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([EXE, "seq", db, "noverify"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     got = _read_matches(db)
     want = {10000 * j + i for i in range(1, 5) for j in range(max(0, i - 3), i)}          # overlap = 3
     assert set(got) == want
-    em, _ = mo.match_image_pair(descs[4], descs[2], 0.8, 0.7 * 512.0, True, True)
-    np.testing.assert_array_equal(got[20004], em[:, ::-1])
+    # integral (un-normalised) descriptors: FilterMatchesByDistance compares the RAW distances with max_distance 0.7, exactly
+    # as the reference would on such a database (FeatureMatching.cpp:49) — practically only duplicates survive
+    em, _ = mo.match_image_pair(descs[4], descs[2], 0.8, 0.7, True, True)
+    np.testing.assert_array_equal(got[20004], em[:, ::-1].reshape(-1, 2))
+    em_all, _ = mo.match_image_pair(descs[4], descs[2], 0.8, -1.0, True, True)
+    assert len(em) < len(em_all)
 
 
 @pytest.mark.gpu

@@ -314,7 +314,7 @@ __device__ __forceinline__ void smem_add6(double* base, const double v[6]) {
 
 // Shared-memory carve-up of the linearisation kernel
 struct FusedSmem {
-    size_t camacc, acc, stage, rbuf, xybuf, ptV, ptg, ptWf, pair_start, unit_info, lfree, misc, total;
+    size_t camacc, acc, stage, rbuf, qbuf, xybuf, ptV, ptg, ptWf, cam_start, cam_cursor, cam_obs, unit_info, lfree, misc, total;
 };
 __host__ __device__ inline FusedSmem fused_smem_layout(bool focal) {
     FusedSmem L;
@@ -322,12 +322,15 @@ __host__ __device__ inline FusedSmem fused_smem_layout(bool focal) {
     L.camacc = o; o += static_cast<size_t>(kTileCams) * (focal ? 30 : 18) * sizeof(double);
     L.ptg = o; o += static_cast<size_t>(kTilePts) * 3 * sizeof(double);
     L.rbuf = o; o += static_cast<size_t>(kTileObs) * 2 * sizeof(double);
+    L.qbuf = o; o += static_cast<size_t>(kTileObs) * 2 * sizeof(double);
     L.xybuf = o; o += focal ? static_cast<size_t>(kTileObs) * 2 * sizeof(double) : 0;
     L.ptWf = o; o += focal ? static_cast<size_t>(kTilePts) * 6 * sizeof(double) : 0;
     L.acc = o; o += static_cast<size_t>(kTileCams) * (kTileCams + 1) / 2 * kBlkStride * sizeof(float);
     L.stage = o; o += static_cast<size_t>(kTileObs) * kStageStride * sizeof(float);
     L.ptV = o; o += static_cast<size_t>(kTilePts) * 6 * sizeof(float);
-    L.pair_start = o; o += (static_cast<size_t>(kTilePts) + 1) * sizeof(int32_t) + 12;
+    L.cam_start = o; o += (static_cast<size_t>(kTileCams) + 4) * sizeof(int32_t);
+    L.cam_cursor = o; o += static_cast<size_t>(kTileCams) * sizeof(int32_t);
+    L.cam_obs = o; o += static_cast<size_t>(kTileObs) * sizeof(uint16_t);
     L.unit_info = o; o += static_cast<size_t>(kTilePts) * sizeof(uint32_t);
     L.lfree = o; o += static_cast<size_t>(kTileCams) * sizeof(int32_t);
     L.misc = o; o += 64;
@@ -395,10 +398,17 @@ long_track_prepass_kernel(Problem P, double inv_radius) {
 
 // One CTA per tile (dynamic scheduler), 512 threads.  Per tile:
 //   A  thread = observation: projection, residual, Jacobians (fp64) -> staged in shared memory as fp32 (r stays fp64)
-//   B  thread = point (unit): V, g_p over its staged observations, damping, 3x3 inverse; pair counts -> prefix sums
-//   C  thread = observation: Q = Jp V^-1; diagonal block, rhs, g_c, diag U of its camera (shared-memory accumulators)
-//   D  thread = camera pair of a point, over ALL pairs of the tile: block(x, y) -= Jc_x^T (Q_x Jp_y^T) Jc_y
+//   B  thread = point (unit): V, g_p over its staged observations, damping, 3x3 inverse
+//   C  thread = observation: Q = Jp V^-1, N = I - Q Jp^T, q = Q g_p - r -> staged; observations bucketed by local camera
+//   E  a work queue over the warps:
+//        camera items  lane = local camera: ONE part (a row of the diagonal block U - Y W^T = sum Jc^T N Jc, or rhs / g_c /
+//                      diag U) summed over the camera's observations of the tile — exclusive owner, plain stores;
+//        unit items    lanes = camera pairs (x < y) of one point: block (x, y) -= Jc_x^T (Q_x Jp_y^T) Jc_y, added to the
+//                      shared-memory block with 64-bit compare-and-swaps (pairs of one point never share a block; different
+//                      warps work on different points, so lost races are rare)
 //   flush: blocks with red.global.add.v4.f32, camera vectors with fp64 reductions.
+// (v4 of this kernel let every observation thread add its diagonal contribution itself: 512 threads into 32 cameras' accumulators
+// at the same instant, 16-way compare-and-swap contention, 86k cycles per tile — profiles/r02_k2_history.txt.)
 template <bool kFocal>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 fused_linearize_kernel(Problem P, double inv_radius) {
@@ -413,17 +423,21 @@ fused_linearize_kernel(Problem P, double inv_radius) {
     float* acc = reinterpret_cast<float*>(smem_raw + L.acc);
     float* stage = reinterpret_cast<float*>(smem_raw + L.stage);
     float* ptV = reinterpret_cast<float*>(smem_raw + L.ptV);
-    int32_t* pair_start = reinterpret_cast<int32_t*>(smem_raw + L.pair_start);
+    double* qbuf = reinterpret_cast<double*>(smem_raw + L.qbuf);
+    int32_t* cam_start = reinterpret_cast<int32_t*>(smem_raw + L.cam_start);      // [w + 1]; doubles as the histogram in phase A
+    int32_t* cam_cursor = reinterpret_cast<int32_t*>(smem_raw + L.cam_cursor);
+    uint16_t* cam_obs = reinterpret_cast<uint16_t*>(smem_raw + L.cam_obs);        // observation rows bucketed by local camera
     uint32_t* unit_info = reinterpret_cast<uint32_t*>(smem_raw + L.unit_info);       // obs base (16) | nA (8) | nB (8)
     int32_t* lfree = reinterpret_cast<int32_t*>(smem_raw + L.lfree);
-    int32_t* misc = reinterpret_cast<int32_t*>(smem_raw + L.misc);                   // [0] tile, [1..8] warp sums of the scan
+    int32_t* misc = reinterpret_cast<int32_t*>(smem_raw + L.misc);                   // [0] tile, [1] work-queue cursor
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* tail = P.tail;
     double cost_local = 0.0, gpmax_local = 0.0;
     double ff[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};        // focal block sums of this thread's points
+    if (tid <= kTileCams) cam_start[tid] = 0;
 
     for (;;) {
-        if (tid == 0) misc[0] = atomicAdd(P.tile_counter, 1);
+        if (tid == 0) { misc[0] = atomicAdd(P.tile_counter, 1); misc[1] = 0; }
         __syncthreads();
         const int ti = misc[0];
         if (ti >= P.n_tiles) break;
@@ -434,7 +448,6 @@ fused_linearize_kernel(Problem P, double inv_radius) {
         {
             float4* a4 = reinterpret_cast<float4*>(acc);
             for (int i = tid; i < nb * (kBlkStride / 4); i += kFusedThreads) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = tid; i < T.w * CV; i += kFusedThreads) camacc[i] = 0.0;
             if (tid < T.w) lfree[tid] = __ldg(P.cam_free + __ldg(P.tile_cams + T.cam_begin + tid));
         }
         // ---- A: this thread's observation
@@ -486,14 +499,14 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                 srow[18] = static_cast<float>(Jp[0]); srow[19] = static_cast<float>(Jp[1]); srow[20] = static_cast<float>(Jp[2]);
                 srow[21] = static_cast<float>(Jp[3]); srow[22] = static_cast<float>(Jp[4]); srow[23] = static_cast<float>(Jp[5]);
                 srow[24] = __int_as_float(f_mine >= 0 ? lcam : -1);
+                if (f_mine >= 0 && diag_owner) atomicAdd(cam_start + 1 + lcam, 1);      // bucket sizes (native integer atomic)
                 rbuf[2 * tid] = r[0]; rbuf[2 * tid + 1] = r[1];
                 if (kFocal) { xybuf[2 * tid] = xy[0]; xybuf[2 * tid + 1] = xy[1]; }
             }
         }
         __syncthreads();
-        // ---- B: this thread's point: V^-1, g_p; pair counts
+        // ---- B: this thread's point: V^-1, g_p
         {
-            int npairs = 0;
             if (tid < n_units) {
                 const uint32_t ui = unit_info[tid];
                 double Vinv[6], gp[3], Wf[6] = {0, 0, 0, 0, 0, 0};
@@ -538,7 +551,6 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                         ff[4] += (T1[0] * gp[0] + T1[1] * gp[1] + T1[2] * gp[2]) - f4[3];
                         ff[5] += f4[2]; ff[6] += f4[3]; ff[7] += f4[0]; ff[8] += f4[1];
                     }
-                    npairs = k * (k - 1) / 2;
                 } else {
                     // a long track: the pre-pass reduced over the whole track
                     const int d = P.items[T.begin + tid].d;
@@ -550,8 +562,6 @@ fused_linearize_kernel(Problem P, double inv_radius) {
 #pragma unroll
                         for (int q = 0; q < 6; ++q) Wf[q] = rec[9 + q];
                     }
-                    const int nA = static_cast<int>((ui >> 16) & 0xFFu), nB = static_cast<int>(ui >> 24);
-                    npairs = nB > 0 ? nA * nB : nA * (nA - 1) / 2;
                 }
 #pragma unroll
                 for (int q = 0; q < 6; ++q) ptV[6 * tid + q] = static_cast<float>(Vinv[q]);
@@ -561,23 +571,15 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                     for (int q = 0; q < 6; ++q) ptWf[6 * tid + q] = Wf[q];
                 }
             }
-            // exclusive prefix sums of the pair counts over the units (threads 0 .. kTilePts-1 = 8 warps)
-            if (tid < kTilePts) {
-                int incl = npairs;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-                if (lane == 31) misc[1 + warp] = incl;
-                pair_start[tid + 1] = incl;                 // warp-local inclusive sum for now
+            // bucket starts of the per-camera observation lists (the histogram of phase A, scanned in place)
+            if (tid == kFusedThreads - 1) {
+                int run = 0;
+                for (int l = 0; l < T.w; ++l) { const int cnt = cam_start[l + 1]; cam_start[l] = run; cam_cursor[l] = run; run += cnt; }
+                cam_start[T.w] = run;
             }
         }
         __syncthreads();
-        if (tid < kTilePts) {
-            int base = 0;
-            for (int w2 = 0; w2 < warp; ++w2) base += misc[1 + w2];
-            pair_start[tid + 1] += base;
-            if (tid == 0) pair_start[0] = 0;
-        }
-        // ---- C: this thread's observation again: Q = Jp V^-1; per-camera sums
+        // ---- C: this thread's observation again: Q = Jp V^-1, N = I - Q Jp^T, q = Q g_p - r; bucket by camera
         if (valid) {
             float* srow = stage + tid * kStageStride;
             const float* vi = ptV + 6 * unit;
@@ -587,120 +589,133 @@ fused_linearize_kernel(Problem P, double inv_radius) {
             Q[3] = jp3 * vi[0] + jp4 * vi[1] + jp5 * vi[2]; Q[4] = jp3 * vi[1] + jp4 * vi[3] + jp5 * vi[4]; Q[5] = jp3 * vi[2] + jp4 * vi[4] + jp5 * vi[5];
             srow[12] = Q[0]; srow[13] = Q[1]; srow[14] = Q[2]; srow[15] = Q[3]; srow[16] = Q[4]; srow[17] = Q[5];
             if (f_mine >= 0 && diag_owner) {
-                // diagonal block U - Y W^T = Jc^T (I - Q Jp^T) Jc, rhs = Jc^T (Q g_p - r), g_c = Jc^T r, diag U
-                float Jc[12];
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const float4 t4 = reinterpret_cast<const float4*>(srow)[q];
-                    Jc[4 * q] = t4.x; Jc[4 * q + 1] = t4.y; Jc[4 * q + 2] = t4.z; Jc[4 * q + 3] = t4.w;
-                }
                 const double m00 = static_cast<double>(Q[0]) * jp0 + static_cast<double>(Q[1]) * jp1 + static_cast<double>(Q[2]) * jp2;
                 const double m01 = static_cast<double>(Q[0]) * jp3 + static_cast<double>(Q[1]) * jp4 + static_cast<double>(Q[2]) * jp5;
                 const double m11 = static_cast<double>(Q[3]) * jp3 + static_cast<double>(Q[4]) * jp4 + static_cast<double>(Q[5]) * jp5;
-                const float n00 = static_cast<float>(1.0 - m00), n01 = static_cast<float>(-m01), n11 = static_cast<float>(1.0 - m11);
-                float T0[6], T1[6];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) { T0[j] = n00 * Jc[j] + n01 * Jc[6 + j]; T1[j] = n01 * Jc[j] + n11 * Jc[6 + j]; }
-                float* blk = acc + (lcam * (lcam + 1) / 2 + lcam) * kBlkStride;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    float row[6];
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) row[j] = Jc[i] * T0[j] + Jc[6 + i] * T1[j];
-                    smem_add_row(blk + 6 * i, row);
-                }
-                const double r0 = rbuf[2 * tid], r1 = rbuf[2 * tid + 1];
+                srow[25] = static_cast<float>(1.0 - m00); srow[26] = static_cast<float>(-m01); srow[27] = static_cast<float>(1.0 - m11);
                 const double* gp = ptg + 3 * unit;
-                const double q0 = Q[0] * gp[0] + Q[1] * gp[1] + Q[2] * gp[2] - r0;
-                const double q1 = Q[3] * gp[0] + Q[4] * gp[1] + Q[5] * gp[2] - r1;
-                double* ca = camacc + lcam * CV;
-                {
-                    double v_rhs[6], v_gc[6], v_ud[6];
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        const double j0 = Jc[i], j1 = Jc[6 + i];
-                        v_rhs[i] = j0 * q0 + j1 * q1;
-                        v_gc[i] = j0 * r0 + j1 * r1;
-                        v_ud[i] = j0 * j0 + j1 * j1;
-                    }
-                    smem_add6(ca, v_rhs);
-                    smem_add6(ca + 6, v_gc);
-                    smem_add6(ca + 12, v_ud);
-                }
-                if (kFocal) {
-                    // border B_c = Jc^T Jf - Y Wf^T = Jc^T (Jf - Q Wf^T),  Jf = diag(xp, yp)
-                    const double* Wf = ptWf + 6 * unit;
-                    const double xp = xybuf[2 * tid], yp = xybuf[2 * tid + 1];
-                    const double g00 = Q[0] * Wf[0] + Q[1] * Wf[1] + Q[2] * Wf[2], g01 = Q[0] * Wf[3] + Q[1] * Wf[4] + Q[2] * Wf[5];
-                    const double g10 = Q[3] * Wf[0] + Q[4] * Wf[1] + Q[5] * Wf[2], g11 = Q[3] * Wf[3] + Q[4] * Wf[4] + Q[5] * Wf[5];
-                    double v_b[12];
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        const double j0 = Jc[i], j1 = Jc[6 + i];
-                        v_b[2 * i] = j0 * (xp - g00) - j1 * g10;
-                        v_b[2 * i + 1] = -j0 * g01 + j1 * (yp - g11);
-                    }
-                    smem_add6(ca + 18, v_b);
-                    smem_add6(ca + 24, v_b + 6);
-                }
+                qbuf[2 * tid] = Q[0] * gp[0] + Q[1] * gp[1] + Q[2] * gp[2] - rbuf[2 * tid];
+                qbuf[2 * tid + 1] = Q[3] * gp[0] + Q[4] * gp[1] + Q[5] * gp[2] - rbuf[2 * tid + 1];
+                cam_obs[atomicAdd(cam_cursor + lcam, 1)] = static_cast<uint16_t>(tid);
             }
         }
         __syncthreads();
-        // ---- D: all camera pairs of the tile, one per thread: block (x, y) -= Jc_x^T (Q_x Jp_y^T) Jc_y
+        // ---- E: work queue: camera items first, then one item per unit
         {
-            const int total_pairs = pair_start[n_units];
-            for (int q = tid; q < total_pairs; q += kFusedThreads) {
-                int lo = 0, hi = n_units - 1;                        // largest unit with pair_start[unit] <= q
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (pair_start[mid] <= q) lo = mid; else hi = mid - 1;
-                }
-                const uint32_t ui = unit_info[lo];
-                const int ql = q - pair_start[lo];
-                const int ob = static_cast<int>(ui & 0xFFFFu);
-                int x, y;
-                if (split && (ui >> 24) != 0) {
-                    const int nA = static_cast<int>((ui >> 16) & 0xFFu), nB = static_cast<int>(ui >> 24);
-                    x = ql / nB; y = nA + (ql - x * nB);
-                } else {
-                    y = static_cast<int>((1.0f + sqrtf(1.0f + 8.0f * static_cast<float>(ql))) * 0.5f);
-                    while (y * (y - 1) / 2 > ql) --y;
-                    while ((y + 1) * y / 2 <= ql) ++y;
-                    x = ql - y * (y - 1) / 2;
-                }
-                const float4* sx = reinterpret_cast<const float4*>(stage + (ob + x) * kStageStride);
-                const float4* sy = reinterpret_cast<const float4*>(stage + (ob + y) * kStageStride);
-                const float4 x6 = sx[6], y6 = sy[6];
-                const int lx = __float_as_int(x6.x), ly = __float_as_int(y6.x);
-                if (lx < 0 || ly < 0) continue;
-                const float4 xq0 = sx[3], xq1 = sx[4];                  // Q_x = (xq0.xyzw, xq1.xy)
-                const float4 yp0 = sy[4], yp1 = sy[5];                  // Jp_y = (yp0.zw, yp1.xyzw)
-                const float m00 = xq0.x * yp0.z + xq0.y * yp0.w + xq0.z * yp1.x;
-                const float m01 = xq0.x * yp1.y + xq0.y * yp1.z + xq0.z * yp1.w;
-                const float m10 = xq0.w * yp0.z + xq1.x * yp0.w + xq1.y * yp1.x;
-                const float m11 = xq0.w * yp1.y + xq1.x * yp1.z + xq1.y * yp1.w;
-                float Jy[12], Jx[12];
-                {
-                    const float4 a0 = sy[0], a1 = sy[1], a2 = sy[2];
-                    Jy[0] = a0.x; Jy[1] = a0.y; Jy[2] = a0.z; Jy[3] = a0.w; Jy[4] = a1.x; Jy[5] = a1.y;
-                    Jy[6] = a1.z; Jy[7] = a1.w; Jy[8] = a2.x; Jy[9] = a2.y; Jy[10] = a2.z; Jy[11] = a2.w;
-                    const float4 b0 = sx[0], b1 = sx[1], b2 = sx[2];
-                    Jx[0] = b0.x; Jx[1] = b0.y; Jx[2] = b0.z; Jx[3] = b0.w; Jx[4] = b1.x; Jx[5] = b1.y;
-                    Jx[6] = b1.z; Jx[7] = b1.w; Jx[8] = b2.x; Jx[9] = b2.y; Jx[10] = b2.z; Jx[11] = b2.w;
-                }
-                float T0[6], T1[6];
+            constexpr int kCamParts = kFocal ? 11 : 9;      // 6 rows of the diagonal block | rhs | g_c | diag U (| border columns B0, B1)
+            const int n_items = kCamParts + n_units;
+            for (;;) {
+                int item = 0;
+                if (lane == 0) item = atomicAdd(misc + 1, 1);
+                item = __shfl_sync(0xffffffffu, item, 0);
+                if (item >= n_items) break;
+                if (item < kCamParts) {
+                    // lane = local camera, item = part: exclusive owner of its outputs
+                    const int l = lane, part = item;
+                    if (l < T.w) {
+                        const int pb = cam_start[l], pe = cam_start[l + 1];
+                        if (part < 6) {
+                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
+                            for (int pp = pb; pp < pe; ++pp) {
+                                const float* sr = stage + static_cast<int>(cam_obs[pp]) * kStageStride;
+                                const float4 j0 = reinterpret_cast<const float4*>(sr)[0], j1 = reinterpret_cast<const float4*>(sr)[1],
+                                             j2 = reinterpret_cast<const float4*>(sr)[2], nn = reinterpret_cast<const float4*>(sr)[6];
+                                const float n00 = nn.y, n01 = nn.z, n11 = nn.w;
+                                const float ci = sr[part], di = sr[6 + part];          // Jc[0][part], Jc[1][part]
+                                const float u = ci * n00 + di * n01, v = ci * n01 + di * n11;   // row `part` of Jc^T N  (1 x 2)
+                                a0 += u * j0.x + v * j1.z; a1 += u * j0.y + v * j1.w; a2 += u * j0.z + v * j2.x;
+                                a3 += u * j0.w + v * j2.y; a4 += u * j1.x + v * j2.z; a5 += u * j1.y + v * j2.w;
+                            }
+                            float* blk = acc + (l * (l + 1) / 2 + l) * kBlkStride + 6 * part;
+                            blk[0] = a0; blk[1] = a1; blk[2] = a2; blk[3] = a3; blk[4] = a4; blk[5] = a5;
+                        } else if (part < 9) {
+                            double a[6] = {0, 0, 0, 0, 0, 0};
+                            for (int pp = pb; pp < pe; ++pp) {
+                                const int row = cam_obs[pp];
+                                const float* sr = stage + row * kStageStride;
+                                double w0, w1;
+                                if (part == 6) { w0 = qbuf[2 * row]; w1 = qbuf[2 * row + 1]; }
+                                else { w0 = rbuf[2 * row]; w1 = rbuf[2 * row + 1]; }
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    T0[j] = -(m00 * Jy[j] + m01 * Jy[6 + j]);
-                    T1[j] = -(m10 * Jy[j] + m11 * Jy[6 + j]);
+                                for (int i = 0; i < 6; ++i) {
+                                    const double c0 = sr[i], c1 = sr[6 + i];
+                                    a[i] += part == 8 ? c0 * c0 + c1 * c1 : c0 * w0 + c1 * w1;
+                                }
+                            }
+                            double* ca = camacc + l * CV + 6 * (part - 6);
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) ca[i] = a[i];
+                        } else if (kFocal) {
+                            // border column (part - 9) of B_c = sum Jc^T (Jf - Q Wf^T),  Jf = diag(xp, yp)
+                            double a[6] = {0, 0, 0, 0, 0, 0};
+                            const int col = part - 9;
+                            for (int pp = pb; pp < pe; ++pp) {
+                                const int row = cam_obs[pp];
+                                const float* sr = stage + row * kStageStride;
+                                const int un = split ? row >> 5 : static_cast<int>(__ldg(P.obs_lpt + T.obs_begin + row));
+                                const double* Wf = ptWf + 6 * un + 3 * col;
+                                const double g0 = sr[12] * Wf[0] + sr[13] * Wf[1] + sr[14] * Wf[2];      // (Q Wf^T)[0][col]
+                                const double g1 = sr[15] * Wf[0] + sr[16] * Wf[1] + sr[17] * Wf[2];      // (Q Wf^T)[1][col]
+                                const double e0 = (col == 0 ? xybuf[2 * row] : 0.0) - g0, e1 = (col == 1 ? xybuf[2 * row + 1] : 0.0) - g1;
+#pragma unroll
+                                for (int i = 0; i < 6; ++i) a[i] += static_cast<double>(sr[i]) * e0 + static_cast<double>(sr[6 + i]) * e1;
+                            }
+                            double* ca = camacc + l * CV + 18 + 6 * col;
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) ca[i] = a[i];
+                        }
+                    }
+                    continue;
                 }
-                float* blk = acc + (ly * (ly + 1) / 2 + lx) * kBlkStride;
+                // ---- unit item: lanes = camera pairs (x < y) of one point
+                const uint32_t ui = unit_info[item - kCamParts];
+                const int ob = static_cast<int>(ui & 0xFFFFu), nA = static_cast<int>((ui >> 16) & 0xFFu), nB = static_cast<int>(ui >> 24);
+                const int npairs = nB > 0 ? nA * nB : nA * (nA - 1) / 2;
+                for (int base = 0; base < npairs; base += 32) {
+                    const int ql = base + lane;
+                    if (ql >= npairs) continue;
+                    int x, y;
+                    if (nB > 0) {
+                        x = ql / nB; y = nA + (ql - x * nB);
+                    } else {
+                        y = static_cast<int>((1.0f + sqrtf(1.0f + 8.0f * static_cast<float>(ql))) * 0.5f);
+                        while (y * (y - 1) / 2 > ql) --y;
+                        while ((y + 1) * y / 2 <= ql) ++y;
+                        x = ql - y * (y - 1) / 2;
+                    }
+                    const float4* sx = reinterpret_cast<const float4*>(stage + (ob + x) * kStageStride);
+                    const float4* sy = reinterpret_cast<const float4*>(stage + (ob + y) * kStageStride);
+                    const int lx = __float_as_int(sx[6].x), ly = __float_as_int(sy[6].x);
+                    if (lx < 0 || ly < 0) continue;
+                    const float4 xq0 = sx[3], xq1 = sx[4];                  // Q_x = (xq0.xyzw, xq1.xy)
+                    const float4 yp0 = sy[4], yp1 = sy[5];                  // Jp_y = (yp0.zw, yp1.xyzw)
+                    const float m00 = -(xq0.x * yp0.z + xq0.y * yp0.w + xq0.z * yp1.x);
+                    const float m01 = -(xq0.x * yp1.y + xq0.y * yp1.z + xq0.z * yp1.w);
+                    const float m10 = -(xq0.w * yp0.z + xq1.x * yp0.w + xq1.y * yp1.x);
+                    const float m11 = -(xq0.w * yp1.y + xq1.x * yp1.z + xq1.y * yp1.w);
+                    float Jy[12], Jx[12];
+                    {
+                        const float4 a0 = sy[0], a1 = sy[1], a2 = sy[2];
+                        Jy[0] = a0.x; Jy[1] = a0.y; Jy[2] = a0.z; Jy[3] = a0.w; Jy[4] = a1.x; Jy[5] = a1.y;
+                        Jy[6] = a1.z; Jy[7] = a1.w; Jy[8] = a2.x; Jy[9] = a2.y; Jy[10] = a2.z; Jy[11] = a2.w;
+                        const float4 b0 = sx[0], b1 = sx[1], b2 = sx[2];
+                        Jx[0] = b0.x; Jx[1] = b0.y; Jx[2] = b0.z; Jx[3] = b0.w; Jx[4] = b1.x; Jx[5] = b1.y;
+                        Jx[6] = b1.z; Jx[7] = b1.w; Jx[8] = b2.x; Jx[9] = b2.y; Jx[10] = b2.z; Jx[11] = b2.w;
+                    }
+                    float T0[6], T1[6];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    float row[6];
+                    for (int j = 0; j < 6; ++j) {
+                        T0[j] = m00 * Jy[j] + m01 * Jy[6 + j];
+                        T1[j] = m10 * Jy[j] + m11 * Jy[6 + j];
+                    }
+                    float* blk = acc + (ly * (ly + 1) / 2 + lx) * kBlkStride;
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) row[j] = Jx[i] * T0[j] + Jx[6 + i] * T1[j];
-                    smem_add_row(blk + 6 * i, row);
+                    for (int i = 0; i < 6; ++i) {
+                        float row[6];
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) row[j] = Jx[i] * T0[j] + Jx[6 + i] * T1[j];
+                        smem_add_row(blk + 6 * i, row);
+                    }
                 }
             }
         }
@@ -722,9 +737,10 @@ fused_linearize_kernel(Problem P, double inv_radius) {
             if (e < 6) dst = tail + P.tl.rhs + f * 6 + e;
             else if (e < 12) dst = tail + P.tl.gc + f * 6 + (e - 6);
             else if (e < 18) dst = tail + P.tl.udiag + f * 6 + (e - 12);
-            else dst = tail + (((e - 18) & 1) ? P.tl.B1 : P.tl.B0) + f * 6 + ((e - 18) >> 1);
+            else dst = tail + (e < 24 ? P.tl.B0 : P.tl.B1) + f * 6 + (e < 24 ? e - 18 : e - 24);
             atomicAdd(dst, camacc[u]);
         }
+        if (tid <= kTileCams) cam_start[tid] = 0;               // the histogram of the next tile
         __syncthreads();
     }
     // ---- scalars: one fp64 atomic per CTA

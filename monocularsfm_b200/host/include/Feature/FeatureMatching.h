@@ -29,13 +29,15 @@ public:
     virtual void RunMatching() = 0;
 
     // Geometric verification (FeatureUtils::FilterMatches = F-matrix RANSAC, 3 px / 0.99, FeatureMatching.cpp:60).  As in the
-    // reference it ALWAYS runs before WriteMatches: the default is FeatureUtils::FilterMatches.  SetGeometricFilter
-    // replaces it (a build with OpenCV may install cv::findFundamentalMat); an empty function is an
-    // explicit opt-out (matches pass through unverified).
+    // reference it ALWAYS runs before WriteMatches.  By default the whole batch of pairs is verified on the device by ONE
+    // msfm_verify_pairs call (keypoints are uploaded once per image).  SetGeometricFilter installs a per-pair HOST filter
+    // instead — FeatureUtils::FilterMatches (DefaultGeometricFilter(), the host statement of the same estimator) or, in a
+    // build with OpenCV, cv::findFundamentalMat; an empty function is an explicit opt-out (matches pass
+    // through unverified).
     typedef std::function<void(const std::vector<cv::Point2f>&, const std::vector<cv::Point2f>&,
                                const std::vector<cv::DMatch>&, std::vector<cv::DMatch>&)> GeometricFilter;
     static GeometricFilter DefaultGeometricFilter();
-    void SetGeometricFilter(GeometricFilter f) { geometric_filter_ = f; }
+    void SetGeometricFilter(GeometricFilter f) { geometric_filter_ = f; device_verification_ = false; }
     void SetVerbose(bool v) { verbose_ = v; }
 
 protected:
@@ -47,8 +49,9 @@ protected:
     bool cross_check_;
     cv::Ptr<Database> database_;
     GeometricFilter geometric_filter_;
+    bool device_verification_ = true;
     bool verbose_ = true;
-    std::unordered_set<image_t> resident_;          // images whose descriptors are on the device
+    std::unordered_set<image_t> resident_;          // images whose descriptors (and keypoint positions) are on the device
     std::unordered_map<image_t, bool> quantised_;   // true when the CV_32F rows had to be quantised (x512)
 };
 

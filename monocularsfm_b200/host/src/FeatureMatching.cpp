@@ -26,6 +26,13 @@ void FeatureMatcher::EnsureResident(image_t image_id) {
     const int q = msfm_desc_quantised(ctx, image_id);
     if (q < 0) device::Check(q, "msfm_desc_quantised");
     quantised_[image_id] = q == 1;
+    if (device_verification_) {
+        // keypoint positions for the batched verification: read ONCE per image (the reference reads them per pair, :51-52)
+        const std::vector<cv::KeyPoint> kpts = database_->ReadKeyPoints(image_id);
+        std::vector<float> xy(kpts.size() * 2);
+        for (size_t i = 0; i < kpts.size(); ++i) { xy[2 * i] = kpts[i].pt.x; xy[2 * i + 1] = kpts[i].pt.y; }
+        device::Check(msfm_keypoints_upload(ctx, image_id, xy.data(), static_cast<int32_t>(kpts.size())), "msfm_keypoints_upload");
+    }
     resident_.insert(image_id);
 }
 
@@ -84,12 +91,20 @@ void FeatureMatcher::MatchImagePairs(const std::vector<std::pair<image_t, image_
         int64_t total = 0;
         device::Check(msfm_match_pairs(ctx, ids.data(), static_cast<int32_t>(todo.size()), &opt, offsets.data(), out.data(),
                                        dist.data(), bound, &total), "msfm_match_pairs");
+        // FeatureUtils::FilterMatches (:60) for the whole batch in one device call
+        std::vector<uint8_t> inlier(static_cast<size_t>(std::max<int64_t>(1, total)), 1);
+        if (device_verification_) {
+            msfm_verify_options vo;
+            msfm_verify_default_options(&vo);                                   // 3.0 px, 0.99 (FeatureUtils.cpp:196)
+            device::Check(msfm_verify_pairs(ctx, ids.data(), static_cast<int32_t>(todo.size()), offsets.data(), out.data(), &vo,
+                                            inlier.data(), nullptr), "msfm_verify_pairs");
+        }
         for (size_t p = 0; p < todo.size(); ++p) {
             std::vector<cv::DMatch> prune_matches;
             for (int64_t k = offsets[p]; k < offsets[p + 1]; ++k)
-                prune_matches.push_back(cv::DMatch(out[2 * k], out[2 * k + 1], 0, static_cast<float>(dist[k] / distance_scale)));
+                if (inlier[k]) prune_matches.push_back(cv::DMatch(out[2 * k], out[2 * k + 1], 0, static_cast<float>(dist[k] / distance_scale)));
             std::vector<cv::DMatch> verified;
-            if (geometric_filter_) {
+            if (!device_verification_ && geometric_filter_) {
                 std::vector<cv::KeyPoint> k1 = database_->ReadKeyPoints(todo[p].first), k2 = database_->ReadKeyPoints(todo[p].second);
                 std::vector<cv::Point2f> p1(k1.size()), p2(k2.size());
                 for (size_t i = 0; i < k1.size(); ++i) p1[i] = k1[i].pt;

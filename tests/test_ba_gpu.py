@@ -140,7 +140,7 @@ def test_full_size_system_vs_c_oracle(ctx, shape):
     P = bench.make_ba_problem(128, 50000, 10.0, 4321) if shape == "configs3" else bench.make_ba_problem(1329, 542000, 9.2, 4321)
     ba = _create(ctx, P)
     st = ba.structure()
-    assert st["n_free"] == len(P["cams"]) - 1 and st["n_tiles"] > 0 and st["w_cap"] <= 40
+    assert st["n_free"] == len(P["cams"]) - 1 and st["n_tiles"] > 0 and st["w_max"] <= 32
     So, rhso, costo, _ = bo.c_linearize(P, 1e-4, lib)
     S, rhs, gc, cost = ba.linearize(1e-4)
     assert abs(cost - costo) <= 1e-9 * costo

@@ -133,6 +133,58 @@ def test_brute_feature_matcher_on_reference_database(tmp_path, preempt):
 
 
 @pytest.mark.gpu
+def test_matcher_verifies_geometry_by_default(tmp_path):
+    """Without any call to SetGeometricFilter the matcher runs the geometric verification (FeatureMatching.cpp:60) — batched
+    on the device — before WriteMatches: descriptor matches whose keypoints do not fit the two-view geometry are NOT stored."""
+    _need_exe()
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_verify_gpu import two_view
+    rng = np.random.default_rng(77)
+    n_in, n_out = 300, 200
+    kp1, kp2, matches, is_in = two_view(rng, n_in, n_out)
+    n = n_in + n_out
+    d1 = _sift_like(rng, n)
+    d2 = _sift_like(rng, n)
+    d2[matches[:, 1]] = d1[matches[:, 0]]                       # every (true or wrong) correspondence is a perfect descriptor match
+    db = str(tmp_path / "v.db")
+    con = sqlite3.connect(db)
+    con.executescript("""
+        CREATE TABLE images(image_id INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, name TEXT NOT NULL UNIQUE);
+        CREATE TABLE keypoints(image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+        CREATE TABLE colors(image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+        CREATE TABLE descriptors(image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+        CREATE TABLE matches(pair_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+    """)
+    for i, (kp, d) in enumerate(((kp1, d1), (kp2, d2))):
+        k4 = np.zeros((n, 4), np.float32)
+        k4[:, :2] = kp
+        k4[:, 2] = 2.0
+        con.execute("insert into images(image_id, name) values(?, ?)", (i, f"img{i}.jpg"))
+        con.execute("insert into keypoints values(?,?,?,?)", (i, n, 4, k4.tobytes()))
+        con.execute("insert into descriptors values(?,?,?,?)", (i, n, 128, (d.astype(np.float32) / 512.0).astype(np.float32).tobytes()))
+    con.commit()
+    con.close()
+    out = subprocess.run([EXE, "match", db, "0"], capture_output=True, text=True, timeout=300)      # default: verification on
+    assert out.returncode == 0, out.stderr + out.stdout
+    got = _read_matches(db)[1]                                     # pair (1, 0) stored as (image 0, image 1)
+    truth = {(int(a), int(b)) for (a, b), ok in zip(matches, is_in) if ok}
+    wrong = {(int(a), int(b)) for (a, b), ok in zip(matches, is_in) if not ok}
+    stored = {(int(a), int(b)) for a, b in got}
+    assert len(stored & truth) >= 0.95 * n_in
+    assert len(stored & wrong) <= 0.05 * n_out                     # a random wrong match fits the epipolar geometry by chance ~1 %
+    # the explicit opt-out stores everything the descriptor stage produced
+    os.remove(db + "-journal") if os.path.exists(db + "-journal") else None
+    con = sqlite3.connect(db)
+    con.execute("delete from matches")
+    con.commit()
+    con.close()
+    out = subprocess.run([EXE, "match", db, "0", "noverify"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0
+    assert len(_read_matches(db)[1]) >= 0.95 * n
+
+
+@pytest.mark.gpu
 def test_sequential_feature_matcher(tmp_path):
     _need_exe()
     rng = np.random.default_rng(5)

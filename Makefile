@@ -24,7 +24,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
 
 $(LIB): $(CU_OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -lcusolver -ldl -Xlinker -rpath=/usr/local/cuda/lib64
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lcusolver -lcublas -ldl -Xlinker -rpath=/usr/local/cuda/lib64
 
 # C++ classes with the reference's names (FeatureUtils, FeatureMatcher, Database, BundleData, CeresBundelOptimizer)
 $(HOSTLIB): $(HOST_SRCS) $(HOST_HDRS) $(LIB)

@@ -237,7 +237,7 @@ def bench_ba(ctx, args, rank, world, dist, dev, peaks, n_cams=None, n_pts=None, 
                   "h2d_bytes": int(L["cams"].nbytes + L["pts"].nbytes + L["obs_uv"].nbytes + 2 * L["obs_cam"].nbytes),
                   "d2h_bytes": int(L["cams"].nbytes + L["pts"].nbytes),
                   "what": "msfm_ba_create (host structure analysis + upload) + msfm_ba_solve + msfm_ba_get_params"}
-    if rank == 0 and world == 1 and args.cpu_pairs > 0:
+    if rank == 0 and world == 1 and args.cpu_pairs != 0:
         from oracle import ba_oracle as bo
         lib = bo.c_oracle()
         if lib is not None:

@@ -69,7 +69,8 @@ int64_t msfm_launch_count(const msfm_ctx* ctx);
 #define MSFM_PROF_BA_OTHER     8
 #define MSFM_PROF_BA_COMM      9   /* the all-reduce of the reduced camera system (multi-GPU) */
 #define MSFM_PROF_VERIFY      10   /* batched F-matrix RANSAC */
-#define MSFM_PROF_NCAT        11
+#define MSFM_PROF_BA_SOLVE    11   /* reduced camera system: expansion + Cholesky + triangular solves */
+#define MSFM_PROF_NCAT        12
 int msfm_prof_enable(msfm_ctx* ctx, int on);
 int msfm_prof_reset(msfm_ctx* ctx);
 int msfm_prof_read(msfm_ctx* ctx, double ms[MSFM_PROF_NCAT], int64_t launches[MSFM_PROF_NCAT]);
@@ -281,8 +282,13 @@ int  msfm_ba_linearize_focal(msfm_ba* ba, double inv_radius, double* B, double* 
 /* Current (fx, fy): what Optimize writes back into K after the solve (:313-317). */
 int  msfm_ba_get_focal(msfm_ba* ba, double focal[2]);
 
-/* The whole Levenberg-Marquardt solve; parameters stay on the device (msfm_ba_get_params to read). */
+/* The whole Levenberg-Marquardt solve; parameters stay on the device (msfm_ba_get_params to read).  One host
+ * synchronisation per iteration (a 72-byte record).  The reduced camera system is solved in fp64 as a block-tridiagonal
+ * chain after a reverse Cuthill-McKee renumbering of the cameras when its band is narrow, by a dense Cholesky otherwise. */
 int  msfm_ba_solve(msfm_ba* ba, const msfm_ba_options* opt, msfm_ba_summary* summary);
+/* After a solve: info[0] cameras per super-block of the chain, [1] its order M, [2] number of super-blocks (all 0: the dense
+ * path was used), [3] free cameras. */
+int  msfm_ba_solver_info(msfm_ba* ba, int32_t info[4]);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU: one process per GPU; the reduced camera system is summed with ONE ncclAllReduce per

@@ -127,6 +127,7 @@ def load_library():
         "msfm_ba_get_focal": (C.c_int, [vp, vp]),
         "msfm_ba_linearize": (C.c_int, [vp, C.c_double, vp, vp, vp, P(C.c_double), P(i32)]),
         "msfm_ba_solve": (C.c_int, [vp, P(BAOptions), P(BASummary)]),
+        "msfm_ba_solver_info": (C.c_int, [vp, P(i32)]),
         "msfm_comm_unique_id": (C.c_int, [vp]),
         "msfm_comm_init": (C.c_int, [vp, i32, i32, vp]),
         "msfm_comm_destroy": (C.c_int, [vp]),
@@ -187,7 +188,7 @@ class Context:
         return int(self.lib.msfm_launch_count(self.h))
 
     PROF_NAMES = ["desc_format", "build_units", "match_tile", "resolve", "exact", "compact", "ba_eval", "ba_schur",
-                  "ba_other", "ba_comm", "verify"]
+                  "ba_other", "ba_comm", "verify", "ba_solve"]
 
     def prof_enable(self, on=True):
         self._check(self.lib.msfm_prof_enable(self.h, int(on)))
@@ -395,6 +396,12 @@ class BAProblem:
         o = BAOptions()
         self.lib.msfm_ba_default_options(C.byref(o), self.n_cams)
         return o
+
+    def solver_info(self):
+        info = (C.c_int32 * 4)()
+        self.ctx._check(self.lib.msfm_ba_solver_info(self.h, info))
+        return {"cams_per_superblock": info[0], "superblock_order": info[1], "n_superblocks": info[2], "n_free": info[3],
+                "kind": "block-tridiagonal (RCM)" if info[2] else "dense"}
 
     def solve(self, opt: BAOptions | None = None):
         opt = opt or self.default_options()

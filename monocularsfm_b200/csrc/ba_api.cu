@@ -29,7 +29,15 @@ cudaError_t ba_launch_track_errors(const Problem&, double*, int, cudaStream_t);
 cudaError_t ba_launch_backsub(const Problem&, double, const double*, double*, double*, int, cudaStream_t);
 cudaError_t ba_launch_update_cams(const double*, const int32_t*, int, const double*, double*, cudaStream_t);
 cudaError_t ba_launch_copy(const double*, double*, int, cudaStream_t);
+cudaError_t ba_launch_lm_record(const Problem&, const double*, const double*, const double*, const int*, int, int, double*, cudaStream_t);
 size_t ba_fused_smem_bytes(bool);
+namespace ba { struct TridiagSolver; }
+ba::TridiagSolver* tridiag_create(int, const std::vector<int32_t>&, const std::vector<int32_t>&, cusolverDnHandle_t, cudaStream_t, cudaError_t*);
+void tridiag_destroy(ba::TridiagSolver*);
+void tridiag_info(const ba::TridiagSolver*, int32_t[4]);
+int* tridiag_dev_info(ba::TridiagSolver*);
+int tridiag_n_super(const ba::TridiagSolver*);
+cudaError_t tridiag_factor_solve(ba::TridiagSolver*, const Problem&, double, cusolverDnHandle_t, double*, int, cudaStream_t);
 }  // namespace msfm
 using namespace msfm;
 
@@ -87,6 +95,7 @@ struct msfm_ba {
     // tiling + block structure (ba_types.cuh, ba_tiles.hpp)
     Tile* tiles = nullptr;
     Item* items = nullptr;
+    uint32_t* runs = nullptr;
     int32_t *tile_cams = nullptr, *tile_slots = nullptr, *blk_row = nullptr, *blk_col = nullptr;
     int32_t n_tiles = 0, w_max = 0, n_blocks = 0, first_long = 0, n_long = 0;
     uint8_t* obs_lpt = nullptr;
@@ -99,7 +108,11 @@ struct msfm_ba {
     TailLayout tl{};
     float* sblk = nullptr;
     int32_t* tile_counter = nullptr;
-    double* dense = nullptr;      // [n6][n6] dense copy of S for the dense Cholesky (allocated by the first solve)
+    double* dense = nullptr;      // [n6][n6] dense copy of S for the dense Cholesky (allocated by the first solve that needs it)
+    ba::TridiagSolver* tri = nullptr;    // block-tridiagonal chain after RCM renumbering (ba_solver.cu), when the band is narrow
+    bool tri_tried = false;
+    double* rec = nullptr;        // [16] per-iteration record (lm_record_kernel)
+    cudaEvent_t ev[2] = {nullptr, nullptr};
     double* xsol = nullptr;       // solver right-hand side / solution [n6]
     double* small = nullptr;      // [8] scratch scalars (backsub out[3], new cost)
     double* work = nullptr;       // cusolver workspace
@@ -116,7 +129,7 @@ struct msfm_ba {
         P.refine_focal = refine_focal; P.pt_Wf = pt_Wf;
         P.pre = pre[which]; P.pts = pts[which]; P.obs_uv = obs_uv; P.obs_cam = obs_cam; P.obs_pt = obs_pt; P.obs_orig = obs_orig;
         P.obs_lcam = obs_lcam; P.pt_start = pt_start; P.pt_order = pt_order; P.cam_free = cam_free;
-        P.tiles = tiles; P.items = items; P.n_tiles = n_tiles; P.tile_cams = tile_cams; P.tile_slots = tile_slots;
+        P.tiles = tiles; P.items = items; P.runs = runs; P.n_tiles = n_tiles; P.tile_cams = tile_cams; P.tile_slots = tile_slots;
         P.obs_lpt = obs_lpt; P.first_long = first_long; P.n_long = n_long; P.long_V = long_V;
         P.n_blocks = n_blocks; P.blk_row = blk_row; P.blk_col = blk_col;
         P.sblk = sblk; P.tail = tail(); P.tl = tl; P.gpm_slot = ctx->comm ? ctx->comm_rank : 0; P.tile_counter = tile_counter;
@@ -173,10 +186,14 @@ void msfm_ba_destroy(msfm_ba* b) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void* ptrs[] = {b->cams[0], b->cams[1], b->pts[0], b->pts[1], b->pre[0], b->pre[1], b->obs_uv, b->obs_cam, b->obs_pt, b->obs_orig,
-                    b->obs_lcam, b->obs_lpt, b->long_V, b->pt_start, b->pt_order, b->cam_free, b->tiles, b->items, b->tile_cams, b->tile_slots, b->blk_row, b->blk_col,
+                    b->obs_lcam, b->obs_lpt, b->long_V, b->pt_start, b->pt_order, b->cam_free, b->tiles, b->items, b->runs, b->tile_cams, b->tile_slots, b->blk_row, b->blk_col,
                     b->sysbuf, b->dense, b->xsol, b->small, b->work, b->dev_info, b->pt_Wf};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (b->rec) cudaFree(b->rec);
+    if (b->tri) tridiag_destroy(b->tri);
+    for (cudaEvent_t e : b->ev)
+        if (e) cudaEventDestroy(e);
     delete b;
 }
 
@@ -284,6 +301,7 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     BA_ALLOC(b->cam_free, size_t(pr->n_cams) * sizeof(int32_t));
     BA_ALLOC(b->tiles, T.tiles.size() * sizeof(Tile));
     BA_ALLOC(b->items, T.items.size() * sizeof(Item));
+    BA_ALLOC(b->runs, T.runs.size() * sizeof(uint32_t));
     BA_ALLOC(b->tile_cams, T.tile_cams.size() * sizeof(int32_t));
     BA_ALLOC(b->tile_slots, T.tile_slots.size() * sizeof(int32_t));
     BA_ALLOC(b->blk_row, T.blk_row.size() * sizeof(int32_t));
@@ -295,7 +313,7 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     BA_ALLOC(b->xsol, (3 * std::max<size_t>(1, n6) + 2) * sizeof(double));      // up to 3 right-hand sides + (d fx, d fy)
     if (b->refine_focal) BA_ALLOC(b->pt_Wf, std::max<size_t>(1, size_t(pr->n_pts)) * 6 * sizeof(double));
     BA_ALLOC(b->small, 8 * sizeof(double));
-    BA_ALLOC(b->dev_info, sizeof(int));
+    BA_ALLOC(b->dev_info, 4 * sizeof(int));
 #undef BA_ALLOC
     auto H2D = [&](void* dst, const void* src, size_t bytes) {
         return bytes ? cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
@@ -314,6 +332,7 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     if (e == cudaSuccess) e = H2D(b->cam_free, cam_free.data(), cam_free.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->tiles, T.tiles.data(), T.tiles.size() * sizeof(Tile));
     if (e == cudaSuccess) e = H2D(b->items, T.items.data(), T.items.size() * sizeof(Item));
+    if (e == cudaSuccess) e = H2D(b->runs, T.runs.data(), T.runs.size() * sizeof(uint32_t));
     if (e == cudaSuccess) e = H2D(b->tile_cams, T.tile_cams.data(), T.tile_cams.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->tile_slots, T.tile_slots.data(), T.tile_slots.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = H2D(b->blk_row, T.blk_row.data(), T.blk_row.size() * sizeof(int32_t));
@@ -507,6 +526,18 @@ int msfm_ba_linearize_focal(msfm_ba* b, double inv_radius, double* B, double* F,
     return MSFM_OK;
 }
 
+int msfm_ba_solver_info(msfm_ba* b, int32_t info[4]) {
+    if (!b || !info) return MSFM_E_INVALID;
+    info[0] = info[1] = info[2] = 0; info[3] = b->n_free;
+    if (b->tri) tridiag_info(b->tri, info);
+    return MSFM_OK;
+}
+
+// The Levenberg-Marquardt loop of Ceres' TrustRegionMinimizer + LevenbergMarquardtStrategy for this problem class.  Every
+// iteration is queued as a whole — linearise, solve the reduced camera system, back-substitute, evaluate the candidate, one
+// small kernel that condenses everything the step decision needs into a 72-byte record — and the host synchronises ONCE per
+// iteration to read that record and accept or reject the step (with a shared focal block the 2 x 2 Schur complement of
+// the border adds a second round trip).
 int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum) {
     if (!b) return MSFM_E_INVALID;
     msfm_ctx* c = b->ctx;
@@ -517,10 +548,21 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
     cusolverDnHandle_t solver = static_cast<cusolverDnHandle_t>(c->cusolver);
     using clk = std::chrono::steady_clock;
     const auto t_begin = clk::now();
-    double t_lin = 0, t_sol = 0;
+    double t_lin = 0;
     const int n6 = b->n_free * 6;
     const size_t N = size_t(n6);
-    if (n6 > 0) {
+    if (!b->rec) BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->rec), 16 * sizeof(double)));
+    for (cudaEvent_t& e : b->ev)
+        if (!e) BA_CUDA(cudaEventCreate(&e));
+    if (n6 > 0 && !b->tri_tried) {
+        b->tri_tried = true;
+        if (!getenv("MSFM_BA_DENSE_SOLVER")) {
+            cudaError_t e = cudaSuccess;
+            b->tri = tridiag_create(b->n_free, b->h_blk_row, b->h_blk_col, solver, c->stream, &e);
+            if (e != cudaSuccess) return c->cuda_fail(e, "msfm_ba_solve: block-tridiagonal solver setup");
+        }
+    }
+    if (n6 > 0 && !b->tri) {
         if (!b->dense) BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->dense), N * N * sizeof(double)));
         int lwork = 0;
         if (cusolverDnDpotrf_bufferSize(solver, CUBLAS_FILL_MODE_LOWER, n6, b->dense, n6, &lwork) != CUSOLVER_STATUS_SUCCESS)
@@ -542,58 +584,52 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
     const int nrhs = focal ? 3 : 1;
     const TailLayout tl = b->tl;
     const int n_ranks = c->comm ? c->comm_ranks : 1;
-    std::vector<double> h_tail(size_t(tl.total)), h_dc(N + 2), h_small(8), h_x(focal ? 3 * N : 0);
+    const bool multi = c->comm && c->comm_ranks > 1;
+    std::vector<double> h_tail(focal ? size_t(tl.total) : 0), h_dc(focal ? N + 2 : 0), h_x(focal ? 3 * N : 0);
+    double h_rec[16];
     int it = 0, good = 0;
     if ((rc = prep(b, b->cur))) return rc;
     while (it < uopt->max_num_iterations) {
         ++it;
         const double inv_radius = 1.0 / radius;
-        auto t0 = clk::now();
+        BA_CUDA(cudaEventRecord(b->ev[0], c->stream));
         if ((rc = linearize(b, b->cur, inv_radius))) return rc;
-        // the fp64 tail of the system: scalars | max |g_p| per rank | rhs | gc | udiag (| focal border)
-        BA_CUDA(cudaMemcpyAsync(h_tail.data(), b->tail(), h_tail.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        BA_CUDA(cudaStreamSynchronize(c->stream));
-        t_lin += std::chrono::duration<double>(clk::now() - t0).count();
-        const double lin_cost = h_tail[size_t(tl.scal)];
-        if (!have_cost) { cost = lin_cost; sum->initial_cost = cost; have_cost = true; }
-        double gmax = 0.0;
-        for (int r = 0; r < n_ranks; ++r) gmax = std::max(gmax, h_tail[size_t(tl.gpm) + r]);
-        for (size_t i = 0; i < N; ++i) gmax = std::max(gmax, std::fabs(h_tail[size_t(tl.gc) + i]));
-        const double* hB = h_tail.data() + tl.B0;              // B0 | B1 (focal only)
-        const double* hff = h_tail.data() + tl.ff;             // F00 F01 F11 rhsf0 rhsf1 gf0 gf1 uf0 uf1
-        if (focal) gmax = std::max(gmax, std::max(std::fabs(hff[5]), std::fabs(hff[6])));
-        if (gmax <= uopt->gradient_tolerance) { converged = true; break; }
-        // ---- solve the reduced camera system (dense Cholesky; the row-major upper block triangle written by the
-        //      kernel is the column-major lower triangle cuSOLVER reads)
-        t0 = clk::now();
-        bool solved = true;
+        BA_CUDA(cudaEventRecord(b->ev[1], c->stream));
+        // ---- solve the reduced camera system
+        const int* info_ptr = b->dev_info;
+        int n_info = 0;
         if (n6 > 0) {
-            BA_CUDA(cudaMemsetAsync(b->dense, 0, N * N * sizeof(double), c->stream));
-            BA_CUDA(ba_launch_expand_dense(b->view(b->cur), inv_radius, b->dense, c->stream));
             BA_CUDA(ba_launch_copy(b->tail() + tl.rhs, b->xsol, n6, c->stream));
-            if (focal) {       // two more right-hand sides: the border columns (S^-1 B for the 2 x 2 Schur complement below)
+            if (focal)         // two more right-hand sides: the border columns (S^-1 B for the 2 x 2 Schur complement below)
                 BA_CUDA(cudaMemcpyAsync(b->xsol + N, b->tail() + tl.B0, 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-            }
-            c->launches += 2;
-            if (cusolverDnDpotrf(solver, CUBLAS_FILL_MODE_LOWER, n6, b->dense, n6, b->work, b->work_len, b->dev_info) != CUSOLVER_STATUS_SUCCESS)
-                return c->fail(MSFM_E_CUDA, "cusolverDnDpotrf failed to launch");
-            int info = 0;
-            BA_CUDA(cudaMemcpyAsync(&info, b->dev_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            BA_CUDA(cudaStreamSynchronize(c->stream));
-            if (info != 0) {
-                solved = false;
+            c->prof_begin(MSFM_PROF_BA_SOLVE);
+            if (b->tri) {
+                BA_CUDA(tridiag_factor_solve(b->tri, b->view(b->cur), inv_radius, solver, b->xsol, nrhs, c->stream));
+                info_ptr = tridiag_dev_info(b->tri);
+                n_info = tridiag_n_super(b->tri);
             } else {
-                if (cusolverDnDpotrs(solver, CUBLAS_FILL_MODE_LOWER, n6, nrhs, b->dense, n6, b->xsol, n6, b->dev_info) != CUSOLVER_STATUS_SUCCESS)
+                // dense Cholesky: the row-major upper block triangle is the column-major lower triangle cuSOLVER reads
+                BA_CUDA(cudaMemsetAsync(b->dense, 0, N * N * sizeof(double), c->stream));
+                BA_CUDA(ba_launch_expand_dense(b->view(b->cur), inv_radius, b->dense, c->stream));
+                if (cusolverDnDpotrf(solver, CUBLAS_FILL_MODE_LOWER, n6, b->dense, n6, b->work, b->work_len, b->dev_info) != CUSOLVER_STATUS_SUCCESS)
+                    return c->fail(MSFM_E_CUDA, "cusolverDnDpotrf failed to launch");
+                // a failed factorisation leaves garbage behind; the record carries the status and the step is then rejected
+                if (cusolverDnDpotrs(solver, CUBLAS_FILL_MODE_LOWER, n6, nrhs, b->dense, n6, b->xsol, n6, b->dev_info + 1) != CUSOLVER_STATUS_SUCCESS)
                     return c->fail(MSFM_E_CUDA, "cusolverDnDpotrs failed to launch");
+                n_info = 1;
             }
+            c->prof_end();
+            c->launches += 3;
         }
         double df[2] = {0.0, 0.0};
-        if (focal && solved) {
+        bool solved = true;
+        if (focal) {
             // bordered system [S B; B^T F] [dc; df] = [rhs; rhs_f]:  (F - B^T S^-1 B) df = rhs_f - B^T S^-1 rhs,  dc = S^-1 rhs - S^-1 B df
-            if (n6 > 0) {
-                BA_CUDA(cudaMemcpyAsync(h_x.data(), b->xsol, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-                BA_CUDA(cudaStreamSynchronize(c->stream));
-            }
+            BA_CUDA(cudaMemcpyAsync(h_tail.data(), b->tail(), h_tail.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            if (n6 > 0) BA_CUDA(cudaMemcpyAsync(h_x.data(), b->xsol, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            BA_CUDA(cudaStreamSynchronize(c->stream));
+            const double* hB = h_tail.data() + tl.B0;              // B0 | B1
+            const double* hff = h_tail.data() + tl.ff;             // F00 F01 F11 rhsf0 rhsf1 gf0 gf1 uf0 uf1
             double f00 = hff[0] + std::max(hff[7], 1e-6) * inv_radius, f01 = hff[1], f11 = hff[2] + std::max(hff[8], 1e-6) * inv_radius;
             double r0 = hff[3], r1 = hff[4];
             const double *y = h_x.data(), *x0 = h_x.data() + N, *x1 = h_x.data() + 2 * N;
@@ -602,7 +638,7 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
                 r0 -= hB[i] * y[i];   r1 -= hB[N + i] * y[i];
             }
             const double det = f00 * f11 - f01 * f01;
-            if (!(det > 0.0) || !(f00 > 0.0)) {
+            if (!(det > 0.0) || !(f00 > 0.0) || !std::isfinite(det)) {
                 solved = false;
             } else {
                 df[0] = (f11 * r0 - f01 * r1) / det;
@@ -612,55 +648,54 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
                 BA_CUDA(cudaMemcpyAsync(b->xsol, h_dc.data(), (N + 2) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
             }
         }
+        // ---- back-substitute the points, build and evaluate the candidate
+        const int nxt = b->cur ^ 1;
+        BA_CUDA(cudaMemsetAsync(b->small, 0, 4 * sizeof(double), c->stream));
+        if (solved) {
+            c->prof_begin(MSFM_PROF_BA_OTHER);
+            BA_CUDA(ba_launch_backsub(b->view(b->cur), inv_radius, b->xsol, b->pts[nxt], b->small, c->num_sms, c->stream));
+            BA_CUDA(ba_launch_update_cams(b->cams[b->cur], b->cam_free, b->n_cams, b->xsol, b->cams[nxt], c->stream));
+            c->prof_end();
+            c->launches += 2;
+            b->focal[nxt][0] = b->focal[b->cur][0] + df[0];
+            b->focal[nxt][1] = b->focal[b->cur][1] + df[1];
+            if ((rc = prep(b, nxt))) return rc;
+            c->prof_begin(MSFM_PROF_BA_EVAL);
+            BA_CUDA(ba_launch_evaluate(b->view(nxt), nullptr, nullptr, b->small + 3, c->num_sms, c->stream));
+            c->prof_end();
+            c->launches += 1;
+            if (multi && (rc = msfm_comm_allreduce_f64(c, b->small, 4, 0))) return rc;
+        }
+        BA_CUDA(ba_launch_lm_record(b->view(b->cur), b->cams[b->cur], b->xsol, b->small, info_ptr, n_info, n_ranks, b->rec, c->stream));
+        c->launches += 1;
+        BA_CUDA(cudaMemcpyAsync(h_rec, b->rec, 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        BA_CUDA(cudaStreamSynchronize(c->stream));                  // the iteration's one synchronisation
+        {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, b->ev[0], b->ev[1]) == cudaSuccess) t_lin += ms * 1e-3;
+        }
+        const double lin_cost = h_rec[0], gmax = h_rec[1];
+        if (!have_cost) { cost = lin_cost; sum->initial_cost = cost; have_cost = true; }
+        if (gmax <= uopt->gradient_tolerance) { converged = true; break; }
+        if (h_rec[8] != 0.0) solved = false;                          // not positive definite
         if (!solved) {
-            t_sol += std::chrono::duration<double>(clk::now() - t0).count();
             radius /= decrease; decrease *= 2;
             if (radius < 1e-32) { failed = true; break; }
             continue;
         }
-        // ---- back-substitute the points, build the candidate
-        const int nxt = b->cur ^ 1;
-        BA_CUDA(cudaMemsetAsync(b->small, 0, 4 * sizeof(double), c->stream));
-        c->prof_begin(MSFM_PROF_BA_OTHER);
-        BA_CUDA(ba_launch_backsub(b->view(b->cur), inv_radius, b->xsol, b->pts[nxt], b->small, c->num_sms, c->stream));
-        BA_CUDA(ba_launch_update_cams(b->cams[b->cur], b->cam_free, b->n_cams, b->xsol, b->cams[nxt], c->stream));
-        c->prof_end();
-        c->launches += 2;
-        b->focal[nxt][0] = b->focal[b->cur][0] + df[0];
-        b->focal[nxt][1] = b->focal[b->cur][1] + df[1];
-        if ((rc = prep(b, nxt))) return rc;
-        c->prof_begin(MSFM_PROF_BA_EVAL);
-        BA_CUDA(ba_launch_evaluate(b->view(nxt), nullptr, nullptr, b->small + 3, c->num_sms, c->stream));
-        c->prof_end();
-        c->launches += 1;
-        if (c->comm && c->comm_ranks > 1 && (rc = msfm_comm_allreduce_f64(c, b->small, 4, 0))) return rc;
-        BA_CUDA(cudaMemcpyAsync(h_small.data(), b->small, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        if (n6 > 0 && !focal) BA_CUDA(cudaMemcpyAsync(h_dc.data(), b->xsol, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        BA_CUDA(cudaStreamSynchronize(c->stream));
-        t_sol += std::chrono::duration<double>(clk::now() - t0).count();
-        const double model_decrease = h_small[0], new_cost = h_small[3];
-        double dc2 = 0, xc2 = 0;
-        for (size_t i = 0; i < N; ++i) dc2 += h_dc[i] * h_dc[i];
-        for (int cam = 0; cam < b->n_cams; ++cam)
-            if (b->h_cam_free[cam] >= 0)
-                for (int k = 0; k < 6; ++k) xc2 += b->h_cams[size_t(cam) * 6 + k] * b->h_cams[size_t(cam) * 6 + k];
+        const double model_decrease = h_rec[4], new_cost = h_rec[7];
+        double dc2 = h_rec[2], xc2 = h_rec[3];
         if (focal) {
-            dc2 += df[0] * df[0] + df[1] * df[1];
             xc2 += b->focal[b->cur][0] * b->focal[b->cur][0] + b->focal[b->cur][1] * b->focal[b->cur][1];
+            dc2 += df[0] * df[0] + df[1] * df[1];
         }
-        const double step_norm = std::sqrt(dc2 + h_small[1]), x_norm = std::sqrt(xc2 + h_small[2]);
+        const double step_norm = std::sqrt(dc2 + h_rec[5]), x_norm = std::sqrt(xc2 + h_rec[6]);
         if (step_norm <= uopt->parameter_tolerance * (x_norm + uopt->parameter_tolerance)) { converged = true; break; }
         const double rho = model_decrease > 0 ? (cost - new_cost) / model_decrease : -1.0;
         if (uopt->verbose)
             printf("msfm_ba it %d cost %.9e -> %.9e rho %.3f radius %.3e |g|max %.3e\n", it, cost, new_cost, rho, radius, gmax);
         if (rho > 1e-3 && std::isfinite(new_cost)) {
-            // accept: the candidate buffers become current
-            for (int cam = 0; cam < b->n_cams; ++cam) {
-                const int f = b->h_cam_free[cam];
-                if (f >= 0)
-                    for (int k = 0; k < 6; ++k) b->h_cams[size_t(cam) * 6 + k] += h_dc[size_t(f) * 6 + k];
-            }
-            b->cur = nxt;
+            b->cur = nxt;                                             // accept: the candidate buffers become current
             const double dcost = cost - new_cost;
             cost = new_cost;
             ++good;
@@ -672,7 +707,7 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
             if (radius < 1e-32) { failed = true; break; }
         }
     }
-    if (c->comm && c->comm_ranks > 1) {
+    if (multi) {
         // residual count over all ranks
         double v = static_cast<double>(nres_local);
         BA_CUDA(cudaMemcpyAsync(b->small, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -686,9 +721,9 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
     sum->termination = failed ? MSFM_BA_FAILURE : (converged ? MSFM_BA_CONVERGENCE : MSFM_BA_NO_CONVERGENCE);
     sum->num_residuals = static_cast<int32_t>(nres_local);
     sum->final_cost = cost;
-    sum->linearize_time_s = t_lin;
-    sum->solve_time_s = t_sol;
     sum->total_time_s = std::chrono::duration<double>(clk::now() - t_begin).count();
+    sum->linearize_time_s = t_lin;
+    sum->solve_time_s = sum->total_time_s - t_lin;
     return MSFM_OK;
 }
 

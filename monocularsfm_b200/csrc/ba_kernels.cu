@@ -292,6 +292,39 @@ __device__ __forceinline__ void smem_add_row(float* base, const float v[6]) {
         if (g2 != e2) { atomicAdd(base + 4, v[4]); atomicAdd(base + 5, v[5]); }
     }
 }
+// blk[0..35] += v (18 float2), blk 16-byte aligned: nine 128-bit compare-and-swaps (ATOMS.CAS.128), three in flight at a
+// time, one branch per three for the rare lost race.
+__device__ __forceinline__ void smem_add_block(float* blk, const float2 v[18]) {
+    const unsigned base = static_cast<unsigned>(__cvta_generic_to_shared(blk));
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        unsigned long long elo[3], ehi[3], glo[3], ghi[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int q = 3 * g + t;
+            const float4 o = reinterpret_cast<const float4*>(blk)[q];
+            const float2 n0 = __fadd2_rn(make_float2(o.x, o.y), v[2 * q]), n1 = __fadd2_rn(make_float2(o.z, o.w), v[2 * q + 1]);
+            elo[t] = (static_cast<unsigned long long>(__float_as_uint(o.y)) << 32) | __float_as_uint(o.x);
+            ehi[t] = (static_cast<unsigned long long>(__float_as_uint(o.w)) << 32) | __float_as_uint(o.z);
+            const unsigned long long nlo = (static_cast<unsigned long long>(__float_as_uint(n0.y)) << 32) | __float_as_uint(n0.x);
+            const unsigned long long nhi = (static_cast<unsigned long long>(__float_as_uint(n1.y)) << 32) | __float_as_uint(n1.x);
+            asm volatile("{\n .reg .b128 e, n, g;\n mov.b128 e, {%2, %3};\n mov.b128 n, {%4, %5};\n atom.shared.cas.b128 g, [%6], e, n;\n mov.b128 {%0, %1}, g;\n}"
+                         : "=l"(glo[t]), "=l"(ghi[t]) : "l"(elo[t]), "l"(ehi[t]), "l"(nlo), "l"(nhi), "r"(base + 16u * q) : "memory");
+        }
+        bool lost = false;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) lost |= (glo[t] != elo[t]) | (ghi[t] != ehi[t]);
+        if (lost) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+                if ((glo[t] != elo[t]) | (ghi[t] != ehi[t])) {
+                    float* d = blk + 4 * (3 * g + t);
+                    atomicAdd(d, v[2 * (3 * g + t)].x); atomicAdd(d + 1, v[2 * (3 * g + t)].y);
+                    atomicAdd(d + 2, v[2 * (3 * g + t) + 1].x); atomicAdd(d + 3, v[2 * (3 * g + t) + 1].y);
+                }
+        }
+    }
+}
 __device__ __forceinline__ void smem_add6(double* base, const double v[6]) {
     unsigned long long* b = reinterpret_cast<unsigned long long*>(base);
     double old[6];
@@ -603,7 +636,7 @@ fused_linearize_kernel(Problem P, double inv_radius) {
         // ---- E: work queue: camera items first, then one item per unit
         {
             constexpr int kCamParts = kFocal ? 11 : 9;      // 6 rows of the diagonal block | rhs | g_c | diag U (| border columns B0, B1)
-            const int n_items = kCamParts + n_units;
+            const int n_items = kCamParts + T.n_runs;
             for (;;) {
                 int item = 0;
                 if (lane == 0) item = atomicAdd(misc + 1, 1);
@@ -667,9 +700,12 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                     }
                     continue;
                 }
-                // ---- unit item: lanes = camera pairs (x < y) of one point
-                const uint32_t ui = unit_info[item - kCamParts];
-                const int ob = static_cast<int>(ui & 0xFFFFu), nA = static_cast<int>((ui >> 16) & 0xFFu), nB = static_cast<int>(ui >> 24);
+                // ---- run item: lanes = camera pairs (x < y) of a run of points with identical camera lists; the products of
+                //      the whole run are summed in registers (packed fp32x2 FMAs) and added to the shared block once
+                const uint32_t rn = __ldg(P.runs + T.run_begin + (item - kCamParts));
+                const int u0 = static_cast<int>(rn & 0xFFFFu), nrun = static_cast<int>(rn >> 16);
+                const uint32_t ui = unit_info[u0];
+                const int nA = static_cast<int>((ui >> 16) & 0xFFu), nB = static_cast<int>(ui >> 24);
                 const int npairs = nB > 0 ? nA * nB : nA * (nA - 1) / 2;
                 for (int base = 0; base < npairs; base += 32) {
                     const int ql = base + lane;
@@ -679,43 +715,46 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                         x = ql / nB; y = nA + (ql - x * nB);
                     } else {
                         y = static_cast<int>((1.0f + sqrtf(1.0f + 8.0f * static_cast<float>(ql))) * 0.5f);
-                        while (y * (y - 1) / 2 > ql) --y;
-                        while ((y + 1) * y / 2 <= ql) ++y;
+                        y -= (y * (y - 1) / 2 > ql) ? 1 : 0;
+                        y += ((y + 1) * y / 2 <= ql) ? 1 : 0;
                         x = ql - y * (y - 1) / 2;
                     }
-                    const float4* sx = reinterpret_cast<const float4*>(stage + (ob + x) * kStageStride);
-                    const float4* sy = reinterpret_cast<const float4*>(stage + (ob + y) * kStageStride);
-                    const int lx = __float_as_int(sx[6].x), ly = __float_as_int(sy[6].x);
+                    float2 av[18];
+#pragma unroll
+                    for (int e = 0; e < 18; ++e) av[e] = make_float2(0.f, 0.f);
+                    int lx = 0, ly = 0;
+                    for (int j = 0; j < nrun; ++j) {
+                        const int ob = static_cast<int>(unit_info[u0 + j] & 0xFFFFu);
+                        const float4* sx = reinterpret_cast<const float4*>(stage + (ob + x) * kStageStride);
+                        const float4* sy = reinterpret_cast<const float4*>(stage + (ob + y) * kStageStride);
+                        if (j == 0) { lx = __float_as_int(sx[6].x); ly = __float_as_int(sy[6].x); }
+                        if (lx < 0 || ly < 0) break;                            // a constant camera: the same for the whole run
+                        const float4 xq0 = sx[3], xq1 = sx[4];                  // Q_x = (xq0.xyzw, xq1.xy)
+                        const float4 yp0 = sy[4], yp1 = sy[5];                  // Jp_y = (yp0.zw, yp1.xyzw)
+                        const float m00 = -(xq0.x * yp0.z + xq0.y * yp0.w + xq0.z * yp1.x);
+                        const float m01 = -(xq0.x * yp1.y + xq0.y * yp1.z + xq0.z * yp1.w);
+                        const float m10 = -(xq0.w * yp0.z + xq1.x * yp0.w + xq1.y * yp1.x);
+                        const float m11 = -(xq0.w * yp1.y + xq1.x * yp1.z + xq1.y * yp1.w);
+                        const float4 a0 = sy[0], a1 = sy[1], a2 = sy[2];        // Jc_y rows: (a0.xyzw a1.xy) | (a1.zw a2.xyzw)
+                        const float2 d00 = make_float2(m00, m00), d01 = make_float2(m01, m01), d10 = make_float2(m10, m10), d11 = make_float2(m11, m11);
+                        float2 T0[3], T1[3];
+                        T0[0] = __ffma2_rn(d01, make_float2(a1.z, a1.w), __fmul2_rn(d00, make_float2(a0.x, a0.y)));
+                        T0[1] = __ffma2_rn(d01, make_float2(a2.x, a2.y), __fmul2_rn(d00, make_float2(a0.z, a0.w)));
+                        T0[2] = __ffma2_rn(d01, make_float2(a2.z, a2.w), __fmul2_rn(d00, make_float2(a1.x, a1.y)));
+                        T1[0] = __ffma2_rn(d11, make_float2(a1.z, a1.w), __fmul2_rn(d10, make_float2(a0.x, a0.y)));
+                        T1[1] = __ffma2_rn(d11, make_float2(a2.x, a2.y), __fmul2_rn(d10, make_float2(a0.z, a0.w)));
+                        T1[2] = __ffma2_rn(d11, make_float2(a2.z, a2.w), __fmul2_rn(d10, make_float2(a1.x, a1.y)));
+                        const float4 b0 = sx[0], b1 = sx[1], b2 = sx[2];        // Jc_x
+                        const float jx0[6] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y}, jx1[6] = {b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                            const float2 c0 = make_float2(jx0[i], jx0[i]), c1 = make_float2(jx1[i], jx1[i]);
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) av[3 * i + c] = __ffma2_rn(c1, T1[c], __ffma2_rn(c0, T0[c], av[3 * i + c]));
+                        }
+                    }
                     if (lx < 0 || ly < 0) continue;
-                    const float4 xq0 = sx[3], xq1 = sx[4];                  // Q_x = (xq0.xyzw, xq1.xy)
-                    const float4 yp0 = sy[4], yp1 = sy[5];                  // Jp_y = (yp0.zw, yp1.xyzw)
-                    const float m00 = -(xq0.x * yp0.z + xq0.y * yp0.w + xq0.z * yp1.x);
-                    const float m01 = -(xq0.x * yp1.y + xq0.y * yp1.z + xq0.z * yp1.w);
-                    const float m10 = -(xq0.w * yp0.z + xq1.x * yp0.w + xq1.y * yp1.x);
-                    const float m11 = -(xq0.w * yp1.y + xq1.x * yp1.z + xq1.y * yp1.w);
-                    float Jy[12], Jx[12];
-                    {
-                        const float4 a0 = sy[0], a1 = sy[1], a2 = sy[2];
-                        Jy[0] = a0.x; Jy[1] = a0.y; Jy[2] = a0.z; Jy[3] = a0.w; Jy[4] = a1.x; Jy[5] = a1.y;
-                        Jy[6] = a1.z; Jy[7] = a1.w; Jy[8] = a2.x; Jy[9] = a2.y; Jy[10] = a2.z; Jy[11] = a2.w;
-                        const float4 b0 = sx[0], b1 = sx[1], b2 = sx[2];
-                        Jx[0] = b0.x; Jx[1] = b0.y; Jx[2] = b0.z; Jx[3] = b0.w; Jx[4] = b1.x; Jx[5] = b1.y;
-                        Jx[6] = b1.z; Jx[7] = b1.w; Jx[8] = b2.x; Jx[9] = b2.y; Jx[10] = b2.z; Jx[11] = b2.w;
-                    }
-                    float T0[6], T1[6];
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        T0[j] = m00 * Jy[j] + m01 * Jy[6 + j];
-                        T1[j] = m10 * Jy[j] + m11 * Jy[6 + j];
-                    }
-                    float* blk = acc + (ly * (ly + 1) / 2 + lx) * kBlkStride;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        float row[6];
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) row[j] = Jx[i] * T0[j] + Jx[6 + i] * T1[j];
-                        smem_add_row(blk + 6 * i, row);
-                    }
+                    smem_add_block(acc + (ly * (ly + 1) / 2 + lx) * kBlkStride, av);
                 }
             }
         }
@@ -877,6 +916,36 @@ __global__ void update_cams_kernel(const double* __restrict__ cams, const int32_
     cams_new[i] = cams[i] + (f >= 0 ? dc[f * 6 + k] : 0.0);
 }
 
+// The 72-byte record of one LM iteration the host reads back (one D2H per iteration instead of the tail / the step / the
+// camera mirror): rec[0] cost at the linearisation point, [1] max |gradient| (cameras, points of every rank, focal block),
+// [2] |dc|^2, [3] |x_c|^2 over the free cameras, [4] model decrease, [5] |dp|^2, [6] |x_p|^2, [7] cost of the candidate,
+// [8] status of the linear solve (0 = positive definite).
+__global__ void __launch_bounds__(256)
+lm_record_kernel(Problem P, const double* __restrict__ cams, const double* __restrict__ dc, const double* __restrict__ small,
+                 const int* __restrict__ info, int n_info, int n_ranks, double* __restrict__ rec) {
+    const int n6 = P.n_free * 6;
+    double gmax = 0.0, dc2 = 0.0, xc2 = 0.0, bad = 0.0;
+    for (int i = threadIdx.x; i < n6; i += blockDim.x) {
+        gmax = fmax(gmax, fabs(P.tail[P.tl.gc + i]));
+        dc2 += dc[i] * dc[i];
+    }
+    for (int i = threadIdx.x; i < P.n_cams * 6; i += blockDim.x)
+        if (P.cam_free[i / 6] >= 0) xc2 += cams[i] * cams[i];
+    for (int i = threadIdx.x; i < n_ranks; i += blockDim.x) gmax = fmax(gmax, P.tail[P.tl.gpm + i]);
+    for (int i = threadIdx.x; i < n_info; i += blockDim.x) bad = fmax(bad, fabs(static_cast<double>(info[i])));
+    if (P.refine_focal && threadIdx.x == 0) gmax = fmax(gmax, fmax(fabs(P.tail[P.tl.ff + 5]), fabs(P.tail[P.tl.ff + 6])));
+    __shared__ double sh[4][8];
+    gmax = warp_max(gmax); bad = warp_max(bad); dc2 = warp_sum(dc2); xc2 = warp_sum(xc2);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = gmax; sh[1][threadIdx.x >> 5] = dc2; sh[2][threadIdx.x >> 5] = xc2; sh[3][threadIdx.x >> 5] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double g = 0.0, a = 0.0, b = 0.0, e = 0.0;
+        for (int k = 0; k < (blockDim.x >> 5); ++k) { g = fmax(g, sh[0][k]); a += sh[1][k]; b += sh[2][k]; e = fmax(e, sh[3][k]); }
+        rec[0] = P.tail[P.tl.scal]; rec[1] = g; rec[2] = a; rec[3] = b;
+        rec[4] = small[0]; rec[5] = small[1]; rec[6] = small[2]; rec[7] = small[3]; rec[8] = e;
+    }
+}
+
 __global__ void copy_kernel(const double* __restrict__ src, double* __restrict__ dst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
@@ -943,6 +1012,11 @@ cudaError_t ba_launch_update_cams(const double* cams, const int32_t* cam_free, i
                                   double* cams_new, cudaStream_t st) {
     if (n_cams <= 0) return cudaSuccess;
     update_cams_kernel<<<(n_cams * 6 + 127) / 128, 128, 0, st>>>(cams, cam_free, n_cams, dc, cams_new);
+    return cudaGetLastError();
+}
+cudaError_t ba_launch_lm_record(const Problem& P, const double* cams, const double* dc, const double* small, const int* info, int n_info,
+                                int n_ranks, double* rec, cudaStream_t st) {
+    lm_record_kernel<<<1, 256, 0, st>>>(P, cams, dc, small, info, n_info, n_ranks, rec);
     return cudaGetLastError();
 }
 cudaError_t ba_launch_copy(const double* src, double* dst, int n, cudaStream_t st) {

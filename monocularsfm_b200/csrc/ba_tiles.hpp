@@ -30,6 +30,7 @@ struct Tiling {
     int first_long = 0, n_long = 0;     // device points [first_long, first_long + n_long): more than 32 observations
     std::vector<Tile> tiles;
     std::vector<Item> items;
+    std::vector<uint32_t> runs;         // per tile: first unit | count << 16 of every run of units with identical camera lists
     std::vector<int32_t> tile_cams;
     std::vector<int32_t> tile_marks;    // per tile, tri(w) entries: 1 if some point of the tile couples the two local cameras
     std::vector<int32_t> tile_slots;    // same shape: global block slot or -1 (assign_slots)
@@ -70,7 +71,20 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
     }
     T.pt_order.resize(static_cast<size_t>(n_pts));
     std::iota(T.pt_order.begin(), T.pt_order.end(), 0);
-    std::stable_sort(T.pt_order.begin(), T.pt_order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+    // Device order: class (key bit 62), then the camera list in lexicographic order — neighbours share cameras (few cameras per
+    // tile), and points with IDENTICAL camera lists end up adjacent (runs: their 6x6 products are summed in registers before
+    // they touch the shared-memory accumulator).
+    std::stable_sort(T.pt_order.begin(), T.pt_order.end(), [&](int32_t a, int32_t b) {
+        if (key[a] != key[b]) return key[a] < key[b];
+        const int ka = start[size_t(a) + 1] - start[a], kb = start[size_t(b) + 1] - start[b];
+        const int32_t* oa = sorted_obs.data() + start[a];
+        const int32_t* ob = sorted_obs.data() + start[b];
+        for (int i = 3; i < ka && i < kb; ++i) {            // the first three cameras are in the key
+            const int ca = obs_cam[oa[i]], cb = obs_cam[ob[i]];
+            if (ca != cb) return ca < cb;
+        }
+        return ka < kb;
+    });
     T.pt_start.assign(size_t(n_pts) + 1, 0);
     T.obs_perm.resize(static_cast<size_t>(n_obs));
     T.obs_lcam.assign(static_cast<size_t>(n_obs), 0);
@@ -114,6 +128,21 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
                     if (cam_free[cb] >= 0) marks[tri_index(la, lidx[cb])] = 1;
                 }
             }
+        // runs of consecutive points with identical camera lists
+        t.run_begin = static_cast<int32_t>(T.runs.size());
+        for (int d = d0; d < d1;) {
+            int e = d + 1;
+            const int kd = T.pt_start[size_t(d) + 1] - T.pt_start[d];
+            while (e < d1 && e - d < 0xFFFF && T.pt_start[size_t(e) + 1] - T.pt_start[e] == kd) {
+                bool same = true;
+                for (int i = 0; i < kd && same; ++i) same = cam_of(T.pt_start[d] + i) == cam_of(T.pt_start[e] + i);
+                if (!same) break;
+                ++e;
+            }
+            T.runs.push_back(static_cast<uint32_t>(d - d0) | (static_cast<uint32_t>(e - d) << 16));
+            d = e;
+        }
+        t.n_runs = static_cast<int32_t>(T.runs.size()) - t.run_begin;
         T.w_max = std::max(T.w_max, int(t.w));
         T.tiles.push_back(t);
         cams.clear();
@@ -179,6 +208,9 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
             }
             T.items.push_back(it);
         }
+        t.run_begin = static_cast<int32_t>(T.runs.size());
+        for (int u = 0; u < t.end - t.begin; ++u) T.runs.push_back(static_cast<uint32_t>(u) | (1u << 16));     // one item per run
+        t.n_runs = t.end - t.begin;
         T.w_max = std::max(T.w_max, int(t.w));
         T.tiles.push_back(t);
         o = Open();

@@ -216,6 +216,33 @@ def test_local_ba_shape_and_small_problem_tolerances(ctx):
     ba.close()
 
 
+def test_block_tridiagonal_solver_matches_dense(ctx):
+    """A ring of 240 cameras with short tracks: the reduced camera system is a narrow band after the RCM renumbering, so
+    msfm_ba_solve factors it as a block-tridiagonal chain.  Same LM trajectory as the dense Cholesky of the whole system
+    (both fp64), same optimum as the Python oracle."""
+    P = bo.make_problem(240, 3000, 4, 13)
+    ba = _create(ctx, P)
+    s = ba.solve()
+    info = ba.solver_info()
+    assert info["n_superblocks"] >= 3 and info["kind"].startswith("block-tridiagonal"), info
+    cams, pts = ba.get_params()
+    ba.close()
+    os.environ["MSFM_BA_DENSE_SOLVER"] = "1"
+    try:
+        bd = _create(ctx, P)
+        sd = bd.solve()
+        assert bd.solver_info()["n_superblocks"] == 0
+        cams_d, pts_d = bd.get_params()
+        bd.close()
+    finally:
+        del os.environ["MSFM_BA_DENSE_SOLVER"]
+    assert s["termination"] == 0 and sd["termination"] == 0 and s["iterations"] == sd["iterations"]
+    assert abs(s["final_cost"] - sd["final_cost"]) <= 1e-9 * sd["final_cost"]
+    assert np.abs(cams - cams_d).max() <= 1e-6 and np.abs(pts - pts_d).max() <= 1e-5
+    ref = bo.lm_solve(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"])
+    assert ref["converged"] and abs(s["final_cost"] - ref["final_cost"]) <= 1e-5 * ref["final_cost"]
+
+
 def test_bad_problem_is_rejected(ctx):
     P = bo.make_problem(4, 10, 3, 0)
     bad = P["obs_pt"].copy()

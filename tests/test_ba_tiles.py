@@ -24,7 +24,7 @@ def harness(tmp_path_factory):
     lib.tiling_build.restype = C.c_int
     lib.tiling_build.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, C.c_int, C.c_int, C.c_int, C.c_int, ip]
     lib.tiling_fetch.restype = None
-    lib.tiling_fetch.argtypes = [ip, ip, ip, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), ip, ip, ip, ip, ip, ip]
+    lib.tiling_fetch.argtypes = [ip, ip, ip, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), ip, ip, ip, ip, ip, ip, C.POINTER(C.c_uint32)]
     return lib
 
 
@@ -35,23 +35,23 @@ def run_tiling(lib, P, max_obs=512, max_pts=64, max_items=16):
     cam_free = -np.ones(len(const), np.int32)
     cam_free[~const] = np.arange((~const).sum(), dtype=np.int32)
     ip = C.POINTER(C.c_int32)
-    sizes = np.zeros(8, np.int32)
+    sizes = np.zeros(9, np.int32)
     rc = lib.tiling_build(len(const), len(P["pts"]), len(oc), oc.ctypes.data_as(ip), op.ctypes.data_as(ip),
                           cam_free.ctypes.data_as(ip), int((~const).sum()), max_obs, max_pts, max_items, sizes.ctypes.data_as(ip))
     if rc:
         return None
-    n_tiles, n_tc, n_marks, n_blocks, w_max, n_items, first_long, n_long = [int(x) for x in sizes]
+    n_tiles, n_tc, n_marks, n_blocks, w_max, n_items, first_long, n_long, n_runs = [int(x) for x in sizes]
     T = {"pt_order": np.zeros(len(P["pts"]), np.int32), "pt_start": np.zeros(len(P["pts"]) + 1, np.int32),
          "obs_perm": np.zeros(len(oc), np.int32), "obs_lcam": np.zeros(len(oc), np.uint8), "obs_lpt": np.zeros(len(oc), np.uint8),
          "first_long": first_long, "n_long": n_long,
-         "tiles": np.zeros((n_tiles, 8), np.int32), "items_raw": np.zeros((n_items, 12), np.int32), "tile_cams": np.zeros(n_tc, np.int32),
+         "tiles": np.zeros((n_tiles, 12), np.int32), "runs": np.zeros(n_runs, np.uint32), "items_raw": np.zeros((n_items, 12), np.int32), "tile_cams": np.zeros(n_tc, np.int32),
          "tile_slots": np.zeros(n_marks, np.int32), "blk_row": np.zeros(n_blocks, np.int32),
          "blk_col": np.zeros(n_blocks, np.int32), "w_max": w_max, "cam_free": cam_free}
     lib.tiling_fetch(T["pt_order"].ctypes.data_as(ip), T["pt_start"].ctypes.data_as(ip), T["obs_perm"].ctypes.data_as(ip),
                      T["obs_lcam"].ctypes.data_as(C.POINTER(C.c_uint8)), T["obs_lpt"].ctypes.data_as(C.POINTER(C.c_uint8)),
                      T["tiles"].ctypes.data_as(ip),
                      T["items_raw"].ctypes.data_as(ip), T["tile_cams"].ctypes.data_as(ip), T["tile_slots"].ctypes.data_as(ip), T["blk_row"].ctypes.data_as(ip),
-                     T["blk_col"].ctypes.data_as(ip))
+                     T["blk_col"].ctypes.data_as(ip), T["runs"].ctypes.data_as(C.POINTER(C.c_uint32)))
     # struct Item { int32 d; uint16 a0, a1, b0, b1, pad[2]; uint8 lc[32]; }
     raw = T["items_raw"].view(np.uint8).reshape(n_items, 48)
     h = raw[:, 4:16].copy().view(np.uint16).reshape(n_items, 6)
@@ -102,6 +102,18 @@ def test_tiling_invariants(harness, which):
         assert w <= 32 and (np.diff(cams) > 0).all()
         if flags & 1:
             assert e0_ - b0_ <= 16
+        rb, nr = int(t[8]), int(t[9])
+        runs = T["runs"][rb:rb + nr]
+        # the runs partition the units in order; inside a run every unit has the same camera list
+        assert (runs & 0xFFFF).tolist() == np.concatenate([[0], np.cumsum(runs >> 16)[:-1]]).tolist() and int((runs >> 16).sum()) == e0_ - b0_
+        if not (flags & 1):
+            for rn in runs:
+                u0, n = int(rn & 0xFFFF), int(rn >> 16)
+                ref = oc[T["pt_start"][b0_ + u0]:T["pt_start"][b0_ + u0 + 1]]
+                for u in range(u0 + 1, u0 + n):
+                    assert np.array_equal(oc[T["pt_start"][b0_ + u]:T["pt_start"][b0_ + u + 1]], ref)
+        if flags & 1:
+            pass
         else:
             assert e0_ - b0_ <= 256 and no_ <= 512 and ob_ == T["pt_start"][b0_] and ob_ + no_ == T["pt_start"][e0_]
             assert (T["obs_lpt"][ob_:ob_ + no_] == np.repeat(np.arange(e0_ - b0_), np.diff(T["pt_start"][b0_:e0_ + 1]))).all()
@@ -149,6 +161,14 @@ def test_items_of_neighbouring_long_tracks_are_packed(harness):
     nobs = T["tiles"][~split, 3]
     assert nobs.mean() > 250 and np.median(nobs) > 400   # most normal tiles fill their 512 observation slots (not at the ring's wrap-around)
     assert T["n_long"] == int((np.diff(T["pt_start"]) > 32).sum())
+    # identical camera lists are adjacent: the pair-weighted mean run length is well above 1 on this ring problem
+    k = np.diff(T["pt_start"])
+    w = tot = 0
+    for t in T["tiles"][~split]:
+        for rn in T["runs"][int(t[8]):int(t[8]) + int(t[9])]:
+            kk = int(k[int(t[0]) + int(rn & 0xFFFF)])
+            w += kk * (kk - 1) // 2 * int(rn >> 16) * int(rn >> 16); tot += kk * (kk - 1) // 2 * int(rn >> 16)
+    assert w / tot > 1.5, w / tot
 
 
 def test_duplicate_camera_rejected(harness):

@@ -42,6 +42,10 @@ def run(ctx, name, n_cams, n_pts, track, iters):
     t0 = time.perf_counter()
     s = ba.solve()
     print(f"{name}: solve {time.perf_counter() - t0:.3f}s", s, flush=True)
+    cams0, pts0 = None, None
+    t0 = time.perf_counter()
+    s = ba.solve()          # from the optimum: one or two iterations; shows the per-iteration cost without first-call effects
+    print(f"{name}: second solve {time.perf_counter() - t0:.3f}s iterations {s['iterations']} solver {ba.solver_info()}", flush=True)
     ba.close()
 
 

@@ -103,6 +103,16 @@ int msfm_desc_upload_u8(msfm_ctx* ctx, int32_t image_id, const uint8_t* desc_hos
  * is quantised as clamp(rint(512 v), 0, 255), round-half-to-even — the bridge INTEGRATION.md documents for the
  * L1-root / L2 normalised descriptors of FeatureExtraction.cpp:260-281; mode 1: always quantise. */
 int msfm_desc_upload_f32(msfm_ctx* ctx, int32_t image_id, const float* desc_host, int32_t n, int32_t mode);
+/* RAW SIFT rows (what cv::SIFT::compute returns, FeatureUtils.cpp:27-66) of one image: the extraction-time normalisation
+ * of the reference (FeatureExtraction.cpp:143-160: L1RootNormalized :260-271 = row /= |row|_1 then sqrt, or L2Normalized
+ * :272-281 = row /= |row|_2, with OpenCV's arithmetic) runs on the device, followed by the x512 quantisation of the
+ * bridge above; the set becomes resident.  normalized_out (optional, HOST, [n][128] float32) receives the normalised rows —
+ * bit for bit what FeatureExtraction hands to Database::WriteDescriptors (:157) — so that extraction can store them and
+ * matching needs no second upload. */
+#define MSFM_NORM_L1_ROOT 1
+#define MSFM_NORM_L2      2
+int msfm_desc_upload_raw_f32(msfm_ctx* ctx, int32_t image_id, const float* desc_host, int32_t n, int32_t normalization,
+                             float* normalized_out);
 /* 1 if the resident set of image_id came from a float32 upload that had to be quantised (distances are then on the
  * x512 scale: FeatureUtils::FilterMatchesByDistance thresholds must be scaled), 0 otherwise
  * (uint8 upload or exactly converted floats); negative error code.  Synchronises the stream. */
@@ -268,6 +278,16 @@ int  msfm_ba_evaluate(msfm_ba* ba, double* r /*[n_obs][2]*/, float* J /*[n_obs][
  * observations. */
 int  msfm_ba_track_errors(msfm_ba* ba, double* err /*[n_pts]*/);
 
+/* The statistics Map::FilterAllPoints3D recomputes on the host after every global BA (src/Reconstruction/Map.cpp:793-917),
+ * served from the resident problem at the current parameters: obs_keep[o] = HasPositiveDepth && reprojection error <=
+ * max_reproj_error (the observations FilterPoints3DWithLargeReprojectionError keeps, :804-870; caller's observation order),
+ * pt_mean_error[p] = mean error over the kept observations (what SetError stores, :860), pt_kept[p] their number, and
+ * pt_max_parallax_deg[p] = the largest Projection::CalculateParallaxAngle over the point's camera pairs
+ * (Projection.cpp:149-194) — FilterPoints3DWithSmallTriangulationAngle keeps a point iff it is >= min_tri_angle (:871-917).
+ * Any output may be NULL.  The removals themselves stay with the caller's Map. */
+int  msfm_ba_filter_stats(msfm_ba* ba, double max_reproj_error, uint8_t* obs_keep /*[n_obs]*/, double* pt_mean_error /*[n_pts]*/,
+                          int32_t* pt_kept /*[n_pts]*/, double* pt_max_parallax_deg /*[n_pts]*/);
+
 /* One linearisation at the current parameters: the reduced camera system of the free cameras with Marquardt
  * damping diag(J^T J) / radius (inv_radius = 1/radius; 0 = undamped), summed over all ranks.
  * S [6F][6F] (symmetric, fully filled), rhs [6F] (S dc = rhs), gc [6F] (gradient of the camera blocks); any may
@@ -286,6 +306,10 @@ int  msfm_ba_get_focal(msfm_ba* ba, double focal[2]);
  * synchronisation per iteration (a 72-byte record).  The reduced camera system is solved in fp64 as a block-tridiagonal
  * chain after a reverse Cuthill-McKee renumbering of the cameras when its band is narrow, by a dense Cholesky otherwise. */
 int  msfm_ba_solve(msfm_ba* ba, const msfm_ba_options* opt, msfm_ba_summary* summary);
+/* One linearisation at the current parameters and the solution dc [6F] of the damped reduced camera system S dc = rhs by the
+ * solver msfm_ba_solve uses (parity hook: tests compare it with a host solve of msfm_ba_linearize's S, rhs).  *status != 0:
+ * the system was not positive definite. */
+int  msfm_ba_solve_system(msfm_ba* ba, double inv_radius, double* dc /*[6F]*/, int32_t* status);
 /* After a solve: info[0] cameras per super-block of the chain, [1] its order M, [2] number of super-blocks (all 0: the dense
  * path was used), [3] free cameras. */
 int  msfm_ba_solver_info(msfm_ba* ba, int32_t info[4]);

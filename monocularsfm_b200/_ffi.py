@@ -101,6 +101,7 @@ def load_library():
         "msfm_desc_upload_u8": (C.c_int, [vp, i32, vp, i32]),
         "msfm_desc_upload_u8_dev": (C.c_int, [vp, i32, vp, i32]),
         "msfm_desc_upload_f32": (C.c_int, [vp, i32, vp, i32, i32]),
+        "msfm_desc_upload_raw_f32": (C.c_int, [vp, i32, vp, i32, i32, vp]),
         "msfm_desc_quantised": (C.c_int, [vp, i32]),
         "msfm_desc_count": (C.c_int, [vp, i32]),
         "msfm_desc_release": (C.c_int, [vp, i32]),
@@ -123,11 +124,13 @@ def load_library():
         "msfm_ba_set_params": (C.c_int, [vp, vp, vp]),
         "msfm_ba_evaluate": (C.c_int, [vp, vp, vp, P(C.c_double)]),
         "msfm_ba_track_errors": (C.c_int, [vp, vp]),
+        "msfm_ba_filter_stats": (C.c_int, [vp, C.c_double, vp, vp, vp, vp]),
         "msfm_ba_linearize_focal": (C.c_int, [vp, C.c_double, vp, vp, vp, vp]),
         "msfm_ba_get_focal": (C.c_int, [vp, vp]),
         "msfm_ba_linearize": (C.c_int, [vp, C.c_double, vp, vp, vp, P(C.c_double), P(i32)]),
         "msfm_ba_solve": (C.c_int, [vp, P(BAOptions), P(BASummary)]),
         "msfm_ba_solver_info": (C.c_int, [vp, P(i32)]),
+        "msfm_ba_solve_system": (C.c_int, [vp, C.c_double, vp, P(i32)]),
         "msfm_comm_unique_id": (C.c_int, [vp]),
         "msfm_comm_init": (C.c_int, [vp, i32, i32, vp]),
         "msfm_comm_destroy": (C.c_int, [vp]),
@@ -214,6 +217,16 @@ class Context:
         desc = np.ascontiguousarray(desc, dtype=np.float32)
         assert desc.ndim == 2 and desc.shape[1] == 128, desc.shape
         self._check(self.lib.msfm_desc_upload_f32(self.h, image_id, _ptr(desc), desc.shape[0], 1 if always_quantise else 0))
+
+    def upload_raw_f32(self, image_id: int, desc: np.ndarray, normalization: str = "l1_root"):
+        """Raw SIFT rows: extraction-time normalisation (FeatureExtraction.cpp:143-160) + x512 quantisation on the device.
+        Returns the normalised float32 rows the reference would store in its database."""
+        desc = np.ascontiguousarray(desc, dtype=np.float32)
+        assert desc.ndim == 2 and desc.shape[1] == 128, desc.shape
+        out = np.zeros_like(desc)
+        kind = {"l1_root": 1, "l2": 2}[normalization]
+        self._check(self.lib.msfm_desc_upload_raw_f32(self.h, image_id, _ptr(desc), desc.shape[0], kind, _ptr(out)))
+        return out
 
     def quantised(self, image_id: int) -> bool:
         return bool(self._check(self.lib.msfm_desc_quantised(self.h, image_id), allow=(0, 1)))
@@ -381,6 +394,15 @@ class BAProblem:
         self.ctx._check(self.lib.msfm_ba_track_errors(self.h, _ptr(err)))
         return err
 
+    def filter_stats(self, max_reproj_error: float):
+        """(obs_keep bool [n_obs], mean error of the kept observations [n_pts], kept count [n_pts], max parallax in degrees [n_pts])."""
+        keep = np.zeros(self.n_obs, np.uint8)
+        err = np.zeros(self.n_pts)
+        kept = np.zeros(self.n_pts, np.int32)
+        ang = np.zeros(self.n_pts)
+        self.ctx._check(self.lib.msfm_ba_filter_stats(self.h, float(max_reproj_error), _ptr(keep), _ptr(err), _ptr(kept), _ptr(ang)))
+        return keep.astype(bool), err, kept, ang
+
     def linearize(self, inv_radius=0.0, want_S=True):
         n6 = 6 * self.n_free
         S = np.zeros((n6, n6)) if want_S else None
@@ -396,6 +418,13 @@ class BAProblem:
         o = BAOptions()
         self.lib.msfm_ba_default_options(C.byref(o), self.n_cams)
         return o
+
+    def solve_system(self, inv_radius: float):
+        """dc [6F] of the damped reduced camera system by the device solver, and its status (0 = positive definite)."""
+        dc = np.zeros(6 * self.n_free)
+        st = C.c_int32(0)
+        self.ctx._check(self.lib.msfm_ba_solve_system(self.h, float(inv_radius), _ptr(dc), C.byref(st)))
+        return dc, int(st.value)
 
     def solver_info(self):
         info = (C.c_int32 * 4)()

@@ -30,6 +30,7 @@ cudaError_t ba_launch_backsub(const Problem&, double, const double*, double*, do
 cudaError_t ba_launch_update_cams(const double*, const int32_t*, int, const double*, double*, cudaStream_t);
 cudaError_t ba_launch_copy(const double*, double*, int, cudaStream_t);
 cudaError_t ba_launch_lm_record(const Problem&, const double*, const double*, const double*, const int*, int, int, double*, cudaStream_t);
+cudaError_t ba_launch_filter_stats(const Problem&, double, uint8_t*, double*, int32_t*, double*, int, cudaStream_t);
 size_t ba_fused_smem_bytes(bool);
 namespace ba { struct TridiagSolver; }
 ba::TridiagSolver* tridiag_create(int, const std::vector<int32_t>&, const std::vector<int32_t>&, cusolverDnHandle_t, cudaStream_t, cudaError_t*);
@@ -431,6 +432,32 @@ int msfm_ba_track_errors(msfm_ba* b, double* err) {
     return MSFM_OK;
 }
 
+int msfm_ba_filter_stats(msfm_ba* b, double max_reproj_error, uint8_t* obs_keep, double* pt_mean_error, int32_t* pt_kept, double* pt_max_parallax_deg) {
+    if (!b) return MSFM_E_INVALID;
+    msfm_ctx* c = b->ctx;
+    if (b->n_pts == 0) return MSFM_OK;
+    BA_CUDA(cudaSetDevice(c->device));
+    int rc = prep(b, b->cur);
+    if (rc) return rc;
+    // scratch: err [n_pts] f64 | angle [n_pts] f64 | kept [n_pts] i32 | keep [n_obs] u8
+    const size_t np = size_t(b->n_pts), no = size_t(b->n_obs);
+    BA_CUDA(c->d_ba_r.reserve(np * 20 + no + 64));
+    double* d_err = c->d_ba_r.as<double>();
+    double* d_ang = d_err + np;
+    int32_t* d_kept = reinterpret_cast<int32_t*>(d_ang + np);
+    uint8_t* d_keep = reinterpret_cast<uint8_t*>(d_kept + np);
+    c->prof_begin(MSFM_PROF_BA_EVAL);
+    BA_CUDA(ba_launch_filter_stats(b->view(b->cur), max_reproj_error, d_keep, d_err, d_kept, d_ang, c->num_sms, c->stream));
+    c->prof_end();
+    c->launches += 1;
+    if (obs_keep && no) BA_CUDA(cudaMemcpyAsync(obs_keep, d_keep, no, cudaMemcpyDeviceToHost, c->stream));
+    if (pt_mean_error) BA_CUDA(cudaMemcpyAsync(pt_mean_error, d_err, np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (pt_kept) BA_CUDA(cudaMemcpyAsync(pt_kept, d_kept, np * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (pt_max_parallax_deg) BA_CUDA(cudaMemcpyAsync(pt_max_parallax_deg, d_ang, np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    BA_CUDA(cudaStreamSynchronize(c->stream));
+    return MSFM_OK;
+}
+
 // Zero the system, linearize + Schur at parameter set `which` (one kernel), all-reduce.  The message of the ONE
 // collective (a single NCCL group launch) is the system buffer itself: the fp32 blocks of the upper block triangle that
 // exist (blk_row / blk_col) and the fp64 tail, in which every rank's max |g_p| has its own slot so that the sum also
@@ -526,29 +553,12 @@ int msfm_ba_linearize_focal(msfm_ba* b, double inv_radius, double* B, double* F,
     return MSFM_OK;
 }
 
-int msfm_ba_solver_info(msfm_ba* b, int32_t info[4]) {
-    if (!b || !info) return MSFM_E_INVALID;
-    info[0] = info[1] = info[2] = 0; info[3] = b->n_free;
-    if (b->tri) tridiag_info(b->tri, info);
-    return MSFM_OK;
-}
-
-// The Levenberg-Marquardt loop of Ceres' TrustRegionMinimizer + LevenbergMarquardtStrategy for this problem class.  Every
-// iteration is queued as a whole — linearise, solve the reduced camera system, back-substitute, evaluate the candidate, one
-// small kernel that condenses everything the step decision needs into a 72-byte record — and the host synchronises ONCE per
-// iteration to read that record and accept or reject the step (with a shared focal block the 2 x 2 Schur complement of
-// the border adds a second round trip).
-int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum) {
-    if (!b) return MSFM_E_INVALID;
+// allocations and the choice of the linear solver, once per problem
+static int solver_setup(msfm_ba* b) {
     msfm_ctx* c = b->ctx;
-    if (!uopt || !sum) return c->fail(MSFM_E_INVALID, "msfm_ba_solve: null argument");
-    BA_CUDA(cudaSetDevice(c->device));
     int rc = ensure_solver(c);
     if (rc) return rc;
     cusolverDnHandle_t solver = static_cast<cusolverDnHandle_t>(c->cusolver);
-    using clk = std::chrono::steady_clock;
-    const auto t_begin = clk::now();
-    double t_lin = 0;
     const int n6 = b->n_free * 6;
     const size_t N = size_t(n6);
     if (!b->rec) BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->rec), 16 * sizeof(double)));
@@ -574,6 +584,86 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
             b->work_len = lwork;
         }
     }
+    return MSFM_OK;
+}
+// queue expansion + factorisation + solve of S x = xsol (nrhs columns) on the ctx stream; status words at *info_ptr
+static int solver_queue(msfm_ba* b, double inv_radius, int nrhs, const int** info_ptr, int* n_info) {
+    msfm_ctx* c = b->ctx;
+    cusolverDnHandle_t solver = static_cast<cusolverDnHandle_t>(c->cusolver);
+    const int n6 = b->n_free * 6;
+    const size_t N = size_t(n6);
+    c->prof_begin(MSFM_PROF_BA_SOLVE);
+    if (b->tri) {
+        BA_CUDA(tridiag_factor_solve(b->tri, b->view(b->cur), inv_radius, solver, b->xsol, nrhs, c->stream));
+        *info_ptr = tridiag_dev_info(b->tri);
+        *n_info = tridiag_n_super(b->tri);
+    } else {
+        // dense Cholesky: the row-major upper block triangle is the column-major lower triangle cuSOLVER reads
+        BA_CUDA(cudaMemsetAsync(b->dense, 0, N * N * sizeof(double), c->stream));
+        BA_CUDA(ba_launch_expand_dense(b->view(b->cur), inv_radius, b->dense, c->stream));
+        if (cusolverDnDpotrf(solver, CUBLAS_FILL_MODE_LOWER, n6, b->dense, n6, b->work, b->work_len, b->dev_info) != CUSOLVER_STATUS_SUCCESS)
+            return c->fail(MSFM_E_CUDA, "cusolverDnDpotrf failed to launch");
+        // a failed factorisation leaves garbage behind; the record carries the status and the step is then rejected
+        if (cusolverDnDpotrs(solver, CUBLAS_FILL_MODE_LOWER, n6, nrhs, b->dense, n6, b->xsol, n6, b->dev_info + 1) != CUSOLVER_STATUS_SUCCESS)
+            return c->fail(MSFM_E_CUDA, "cusolverDnDpotrs failed to launch");
+        *info_ptr = b->dev_info;
+        *n_info = 1;
+    }
+    c->prof_end();
+    c->launches += 3;
+    return MSFM_OK;
+}
+
+int msfm_ba_solver_info(msfm_ba* b, int32_t info[4]) {
+    if (!b || !info) return MSFM_E_INVALID;
+    info[0] = info[1] = info[2] = 0; info[3] = b->n_free;
+    if (b->tri) tridiag_info(b->tri, info);
+    return MSFM_OK;
+}
+
+int msfm_ba_solve_system(msfm_ba* b, double inv_radius, double* dc, int32_t* status) {
+    if (!b) return MSFM_E_INVALID;
+    msfm_ctx* c = b->ctx;
+    if (!dc && b->n_free > 0) return c->fail(MSFM_E_INVALID, "msfm_ba_solve_system: null output");
+    if (b->refine_focal) return c->fail(MSFM_E_INVALID, "msfm_ba_solve_system: not for problems with a shared focal block");
+    BA_CUDA(cudaSetDevice(c->device));
+    int rc = solver_setup(b);
+    if (rc) return rc;
+    if ((rc = prep(b, b->cur))) return rc;
+    if ((rc = linearize(b, b->cur, inv_radius))) return rc;
+    const int n6 = b->n_free * 6;
+    if (status) *status = 0;
+    if (n6 == 0) return MSFM_OK;
+    BA_CUDA(ba_launch_copy(b->tail() + b->tl.rhs, b->xsol, n6, c->stream));
+    const int* info_ptr = nullptr;
+    int n_info = 0;
+    if ((rc = solver_queue(b, inv_radius, 1, &info_ptr, &n_info))) return rc;
+    std::vector<int> h_info(size_t(std::max(1, n_info)), 0);
+    BA_CUDA(cudaMemcpyAsync(h_info.data(), info_ptr, size_t(n_info) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    BA_CUDA(cudaMemcpyAsync(dc, b->xsol, size_t(n6) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    BA_CUDA(cudaStreamSynchronize(c->stream));
+    if (status)
+        for (int v : h_info) if (v != 0) *status = v;
+    return MSFM_OK;
+}
+
+// The Levenberg-Marquardt loop of Ceres' TrustRegionMinimizer + LevenbergMarquardtStrategy for this problem class.  Every
+// iteration is queued as a whole — linearise, solve the reduced camera system, back-substitute, evaluate the candidate, one
+// small kernel that condenses everything the step decision needs into a 72-byte record — and the host synchronises ONCE per
+// iteration to read that record and accept or reject the step (with a shared focal block the 2 x 2 Schur complement of
+// the border adds a second round trip).
+int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum) {
+    if (!b) return MSFM_E_INVALID;
+    msfm_ctx* c = b->ctx;
+    if (!uopt || !sum) return c->fail(MSFM_E_INVALID, "msfm_ba_solve: null argument");
+    BA_CUDA(cudaSetDevice(c->device));
+    int rc;
+    using clk = std::chrono::steady_clock;
+    const auto t_begin = clk::now();
+    double t_lin = 0;
+    const int n6 = b->n_free * 6;
+    const size_t N = size_t(n6);
+    if ((rc = solver_setup(b))) return rc;
     std::memset(sum, 0, sizeof *sum);
     double radius = uopt->initial_trust_region_radius;
     double decrease = 2.0;
@@ -602,24 +692,7 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
             BA_CUDA(ba_launch_copy(b->tail() + tl.rhs, b->xsol, n6, c->stream));
             if (focal)         // two more right-hand sides: the border columns (S^-1 B for the 2 x 2 Schur complement below)
                 BA_CUDA(cudaMemcpyAsync(b->xsol + N, b->tail() + tl.B0, 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-            c->prof_begin(MSFM_PROF_BA_SOLVE);
-            if (b->tri) {
-                BA_CUDA(tridiag_factor_solve(b->tri, b->view(b->cur), inv_radius, solver, b->xsol, nrhs, c->stream));
-                info_ptr = tridiag_dev_info(b->tri);
-                n_info = tridiag_n_super(b->tri);
-            } else {
-                // dense Cholesky: the row-major upper block triangle is the column-major lower triangle cuSOLVER reads
-                BA_CUDA(cudaMemsetAsync(b->dense, 0, N * N * sizeof(double), c->stream));
-                BA_CUDA(ba_launch_expand_dense(b->view(b->cur), inv_radius, b->dense, c->stream));
-                if (cusolverDnDpotrf(solver, CUBLAS_FILL_MODE_LOWER, n6, b->dense, n6, b->work, b->work_len, b->dev_info) != CUSOLVER_STATUS_SUCCESS)
-                    return c->fail(MSFM_E_CUDA, "cusolverDnDpotrf failed to launch");
-                // a failed factorisation leaves garbage behind; the record carries the status and the step is then rejected
-                if (cusolverDnDpotrs(solver, CUBLAS_FILL_MODE_LOWER, n6, nrhs, b->dense, n6, b->xsol, n6, b->dev_info + 1) != CUSOLVER_STATUS_SUCCESS)
-                    return c->fail(MSFM_E_CUDA, "cusolverDnDpotrs failed to launch");
-                n_info = 1;
-            }
-            c->prof_end();
-            c->launches += 3;
+            if ((rc = solver_queue(b, inv_radius, nrhs, &info_ptr, &n_info))) return rc;
         }
         double df[2] = {0.0, 0.0};
         bool solved = true;

@@ -176,6 +176,58 @@ track_error_kernel(Problem P, double* __restrict__ err) {
     }
 }
 
+// Post-BA filter statistics: what Map::FilterAllPoints3D recomputes on the host after every global BA
+// (src/Reconstruction/Map.cpp:793-917): per observation HasPositiveDepth && reprojection error <= max_reproj_error
+// (Projection.cpp:6-19, 114-133), per point the mean error over the observations that pass and the LARGEST parallax angle
+// over its camera pairs (Projection::CalculateParallaxAngle, Projection.cpp:149-194: law of cosines on the rays from the two
+// projection centres O = -R^T t, min(angle, pi - angle), degrees, NaN -> 0).  One warp per point, one lane per observation.
+__global__ void __launch_bounds__(256)
+filter_stats_kernel(Problem P, double max_reproj_error, uint8_t* __restrict__ obs_keep, double* __restrict__ pt_err,
+                    int32_t* __restrict__ pt_kept, double* __restrict__ pt_angle) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int d = blockIdx.x * wpb + (threadIdx.x >> 5); d < P.n_pts; d += gridDim.x * wpb) {
+        const int p = P.pt_order[d];
+        const int beg = P.pt_start[d], end = P.pt_start[d + 1];
+        const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
+        double sum = 0.0, amax = 0.0;
+        int kept = 0;
+        for (int o = beg + lane; o < end; o += 32) {
+            const CamPre c = P.pre[P.obs_cam[o]];
+            const double pz = c.R[6] * X[0] + c.R[7] * X[1] + c.R[8] * X[2] + c.t[2];
+            double r[2], Jc[12], Jp[6];
+            obs_eval<false>(c, X, P.obs_uv[2 * o], P.obs_uv[2 * o + 1], P.fx, P.fy, r, Jc, Jp);
+            const double e = sqrt(r[0] * r[0] + r[1] * r[1]);
+            const bool keep = pz > 0.0 && !(e > max_reproj_error);
+            if (obs_keep) obs_keep[P.obs_orig[o]] = keep ? 1 : 0;
+            if (keep) { sum += e; kept += 1; }
+            // parallax against every earlier observation of the track
+            const double O1[3] = {-(c.R[0] * c.t[0] + c.R[3] * c.t[1] + c.R[6] * c.t[2]), -(c.R[1] * c.t[0] + c.R[4] * c.t[1] + c.R[7] * c.t[2]),
+                                  -(c.R[2] * c.t[0] + c.R[5] * c.t[1] + c.R[8] * c.t[2])};
+            const double ray1 = sqrt((X[0] - O1[0]) * (X[0] - O1[0]) + (X[1] - O1[1]) * (X[1] - O1[1]) + (X[2] - O1[2]) * (X[2] - O1[2]));
+            for (int q = beg; q < o; ++q) {
+                const CamPre& c2 = P.pre[P.obs_cam[q]];
+                const double O2[3] = {-(c2.R[0] * c2.t[0] + c2.R[3] * c2.t[1] + c2.R[6] * c2.t[2]), -(c2.R[1] * c2.t[0] + c2.R[4] * c2.t[1] + c2.R[7] * c2.t[2]),
+                                      -(c2.R[2] * c2.t[0] + c2.R[5] * c2.t[1] + c2.R[8] * c2.t[2])};
+                const double ray2 = sqrt((X[0] - O2[0]) * (X[0] - O2[0]) + (X[1] - O2[1]) * (X[1] - O2[1]) + (X[2] - O2[2]) * (X[2] - O2[2]));
+                const double base2 = (O1[0] - O2[0]) * (O1[0] - O2[0]) + (O1[1] - O2[1]) * (O1[1] - O2[1]) + (O1[2] - O2[2]) * (O1[2] - O2[2]);
+                const double ang = fabs(acos((ray1 * ray1 + ray2 * ray2 - base2) / (2.0 * ray1 * ray2)));
+                const double deg = isnan(ang) ? 0.0 : fmin(ang, 3.14159265358979323846 - ang) * 180.0 / 3.14159265358979323846;
+                amax = fmax(amax, deg);
+            }
+        }
+        sum = warp_sum(sum);
+        amax = warp_max(amax);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+        if (lane == 0) {
+            if (pt_err) pt_err[p] = kept > 0 ? sum / static_cast<double>(kept) : 0.0;
+            if (pt_kept) pt_kept[p] = kept;
+            if (pt_angle) pt_angle[p] = amax;
+        }
+    }
+}
+
 // inverse of the symmetric 3x3 V (v00 v01 v02 v11 v12 v22)
 __device__ __forceinline__ void sym3_inverse(const double v[6], double inv[6]) {
     const double c00 = v[3] * v[5] - v[4] * v[4];
@@ -435,10 +487,11 @@ long_track_prepass_kernel(Problem P, double inv_radius) {
 //   C  thread = observation: Q = Jp V^-1, N = I - Q Jp^T, q = Q g_p - r -> staged; observations bucketed by local camera
 //   E  a work queue over the warps:
 //        camera items  lane = local camera: ONE part (a row of the diagonal block U - Y W^T = sum Jc^T N Jc, or rhs / g_c /
-//                      diag U) summed over the camera's observations of the tile — exclusive owner, plain stores;
-//        unit items    lanes = camera pairs (x < y) of one point: block (x, y) -= Jc_x^T (Q_x Jp_y^T) Jc_y, added to the
-//                      shared-memory block with 64-bit compare-and-swaps (pairs of one point never share a block; different
-//                      warps work on different points, so lost races are rare)
+//                      diag U) summed over a quarter of the camera's observations of the tile — four adders per address;
+//        run items     lanes = 32 camera pairs (x < y) of a RUN of points with identical camera lists: block (x, y) -=
+//                      sum over the run of Jc_x^T (Q_x Jp_y^T) Jc_y, summed in registers with packed fp32x2 FMAs and added to
+//                      the shared-memory block with 128-bit compare-and-swaps (the pairs of a point never share a block;
+//                      different warps work on different points, so lost races are rare)
 //   flush: blocks with red.global.add.v4.f32, camera vectors with fp64 reductions.
 // (v4 of this kernel let every observation thread add its diagonal contribution itself: 512 threads into 32 cameras' accumulators
 // at the same instant, 16-way compare-and-swap contention, 86k cycles per tile — profiles/r02_k2_history.txt.)
@@ -481,6 +534,7 @@ fused_linearize_kernel(Problem P, double inv_radius) {
         {
             float4* a4 = reinterpret_cast<float4*>(acc);
             for (int i = tid; i < nb * (kBlkStride / 4); i += kFusedThreads) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = tid; i < T.w * CV; i += kFusedThreads) camacc[i] = 0.0;
             if (tid < T.w) lfree[tid] = __ldg(P.cam_free + __ldg(P.tile_cams + T.cam_begin + tid));
         }
         // ---- A: this thread's observation
@@ -635,7 +689,8 @@ fused_linearize_kernel(Problem P, double inv_radius) {
         __syncthreads();
         // ---- E: work queue: camera items first, then one item per unit
         {
-            constexpr int kCamParts = kFocal ? 11 : 9;      // 6 rows of the diagonal block | rhs | g_c | diag U (| border columns B0, B1)
+            constexpr int kCamSplit = 4;                    // every camera part is summed by four items (a quarter of the list each)
+            constexpr int kCamParts = (kFocal ? 11 : 9) * kCamSplit;   // 6 rows of the diagonal block | rhs | g_c | diag U (| border columns)
             const int n_items = kCamParts + T.n_runs;
             for (;;) {
                 int item = 0;
@@ -643,13 +698,14 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                 item = __shfl_sync(0xffffffffu, item, 0);
                 if (item >= n_items) break;
                 if (item < kCamParts) {
-                    // lane = local camera, item = part: exclusive owner of its outputs
-                    const int l = lane, part = item;
+                    // lane = local camera, item = (part, quarter of the camera's observation list); the four quarters meet in
+                    // the shared accumulators (at most four adders per address)
+                    const int l = lane, part = item / kCamSplit, quarter = item - part * kCamSplit;
                     if (l < T.w) {
-                        const int pb = cam_start[l], pe = cam_start[l + 1];
+                        const int pb = cam_start[l] + quarter, pe = cam_start[l + 1];
                         if (part < 6) {
                             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
-                            for (int pp = pb; pp < pe; ++pp) {
+                            for (int pp = pb; pp < pe; pp += kCamSplit) {
                                 const float* sr = stage + static_cast<int>(cam_obs[pp]) * kStageStride;
                                 const float4 j0 = reinterpret_cast<const float4*>(sr)[0], j1 = reinterpret_cast<const float4*>(sr)[1],
                                              j2 = reinterpret_cast<const float4*>(sr)[2], nn = reinterpret_cast<const float4*>(sr)[6];
@@ -659,11 +715,13 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                                 a0 += u * j0.x + v * j1.z; a1 += u * j0.y + v * j1.w; a2 += u * j0.z + v * j2.x;
                                 a3 += u * j0.w + v * j2.y; a4 += u * j1.x + v * j2.z; a5 += u * j1.y + v * j2.w;
                             }
-                            float* blk = acc + (l * (l + 1) / 2 + l) * kBlkStride + 6 * part;
-                            blk[0] = a0; blk[1] = a1; blk[2] = a2; blk[3] = a3; blk[4] = a4; blk[5] = a5;
+                            if (pb < pe) {
+                                const float row[6] = {a0, a1, a2, a3, a4, a5};
+                                smem_add_row(acc + (l * (l + 1) / 2 + l) * kBlkStride + 6 * part, row);
+                            }
                         } else if (part < 9) {
                             double a[6] = {0, 0, 0, 0, 0, 0};
-                            for (int pp = pb; pp < pe; ++pp) {
+                            for (int pp = pb; pp < pe; pp += kCamSplit) {
                                 const int row = cam_obs[pp];
                                 const float* sr = stage + row * kStageStride;
                                 double w0, w1;
@@ -675,14 +733,12 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                                     a[i] += part == 8 ? c0 * c0 + c1 * c1 : c0 * w0 + c1 * w1;
                                 }
                             }
-                            double* ca = camacc + l * CV + 6 * (part - 6);
-#pragma unroll
-                            for (int i = 0; i < 6; ++i) ca[i] = a[i];
+                            if (pb < pe) smem_add6(camacc + l * CV + 6 * (part - 6), a);
                         } else if (kFocal) {
                             // border column (part - 9) of B_c = sum Jc^T (Jf - Q Wf^T),  Jf = diag(xp, yp)
                             double a[6] = {0, 0, 0, 0, 0, 0};
                             const int col = part - 9;
-                            for (int pp = pb; pp < pe; ++pp) {
+                            for (int pp = pb; pp < pe; pp += kCamSplit) {
                                 const int row = cam_obs[pp];
                                 const float* sr = stage + row * kStageStride;
                                 const int un = split ? row >> 5 : static_cast<int>(__ldg(P.obs_lpt + T.obs_begin + row));
@@ -693,9 +749,7 @@ fused_linearize_kernel(Problem P, double inv_radius) {
 #pragma unroll
                                 for (int i = 0; i < 6; ++i) a[i] += static_cast<double>(sr[i]) * e0 + static_cast<double>(sr[6 + i]) * e1;
                             }
-                            double* ca = camacc + l * CV + 18 + 6 * col;
-#pragma unroll
-                            for (int i = 0; i < 6; ++i) ca[i] = a[i];
+                            if (pb < pe) smem_add6(camacc + l * CV + 18 + 6 * col, a);
                         }
                     }
                     continue;
@@ -703,12 +757,12 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                 // ---- run item: lanes = camera pairs (x < y) of a run of points with identical camera lists; the products of
                 //      the whole run are summed in registers (packed fp32x2 FMAs) and added to the shared block once
                 const uint32_t rn = __ldg(P.runs + T.run_begin + (item - kCamParts));
-                const int u0 = static_cast<int>(rn & 0xFFFFu), nrun = static_cast<int>(rn >> 16);
+                const int u0 = static_cast<int>(rn & 0xFFFFu), nrun = static_cast<int>((rn >> 16) & 0xFFu);
                 const uint32_t ui = unit_info[u0];
                 const int nA = static_cast<int>((ui >> 16) & 0xFFu), nB = static_cast<int>(ui >> 24);
                 const int npairs = nB > 0 ? nA * nB : nA * (nA - 1) / 2;
-                for (int base = 0; base < npairs; base += 32) {
-                    const int ql = base + lane;
+                {
+                    const int ql = static_cast<int>(rn >> 24) * 32 + lane;
                     if (ql >= npairs) continue;
                     int x, y;
                     if (nB > 0) {
@@ -972,6 +1026,14 @@ cudaError_t ba_launch_track_errors(const Problem& P, double* err, int num_sms, c
     int grid = (P.n_pts + 7) / 8;
     if (grid > num_sms * 8) grid = num_sms * 8;
     track_error_kernel<<<grid, 256, 0, st>>>(P, err);
+    return cudaGetLastError();
+}
+cudaError_t ba_launch_filter_stats(const Problem& P, double max_err, uint8_t* keep, double* err, int32_t* kept, double* angle, int num_sms,
+                                   cudaStream_t st) {
+    if (P.n_pts <= 0) return cudaSuccess;
+    int grid = (P.n_pts + 7) / 8;
+    if (grid > num_sms * 8) grid = num_sms * 8;
+    filter_stats_kernel<<<grid, 256, 0, st>>>(P, max_err, keep, err, kept, angle);
     return cudaGetLastError();
 }
 size_t ba_fused_smem_bytes(bool focal) { return fused_smem_layout(focal).total; }

@@ -64,8 +64,23 @@ void rcm_order(int n, const std::vector<int32_t>& blk_row, const std::vector<int
     std::reverse(order.begin(), order.end());
     pos.assign(static_cast<size_t>(n), 0);
     for (int i = 0; i < n; ++i) pos[order[i]] = i;
-    bw = 0;
-    for (size_t k = 0; k < blk_row.size(); ++k) bw = std::max(bw, std::abs(pos[blk_row[k]] - pos[blk_col[k]]));
+    auto width = [&](const std::vector<int32_t>& ps) {
+        int w = 0;
+        for (size_t k = 0; k < blk_row.size(); ++k) w = std::max(w, std::abs(ps[blk_row[k]] - ps[blk_col[k]]));
+        return w;
+    };
+    bw = width(pos);
+    // Two cheap alternatives that beat BFS level orderings on the graphs sequential capture produces: the cameras' own order
+    // (an open chain: neighbours in time see the same points) and the same order FOLDED (0, n-1, 1, n-2, ...: a closed loop,
+    // where the first and the last cameras meet again — a ring's band is then twice the co-visibility window instead of a
+    // BFS level pair).  The narrowest band wins.
+    std::vector<int32_t> cand(static_cast<size_t>(n));
+    std::iota(cand.begin(), cand.end(), 0);
+    int w = width(cand);
+    if (w < bw) { bw = w; pos = cand; }
+    for (int i = 0; i < n; ++i) cand[i] = i <= n - 1 - i ? 2 * i : 2 * (n - 1 - i) + 1;
+    w = width(cand);
+    if (w < bw) { bw = w; pos = cand; }
 }
 
 // block slot -> (super-block, local offsets) scatter of the fp32 blocks into the fp64 block-tridiagonal storage

@@ -30,7 +30,8 @@ struct Tiling {
     int first_long = 0, n_long = 0;     // device points [first_long, first_long + n_long): more than 32 observations
     std::vector<Tile> tiles;
     std::vector<Item> items;
-    std::vector<uint32_t> runs;         // per tile: first unit | count << 16 of every run of units with identical camera lists
+    std::vector<uint32_t> runs;         // per tile, the work items of the pair phase: first unit of a run of units with identical
+                                        // camera lists (16 bits) | units in the run (8 bits) | round of 32 camera pairs (8 bits)
     std::vector<int32_t> tile_cams;
     std::vector<int32_t> tile_marks;    // per tile, tri(w) entries: 1 if some point of the tile couples the two local cameras
     std::vector<int32_t> tile_slots;    // same shape: global block slot or -1 (assign_slots)
@@ -128,18 +129,20 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
                     if (cam_free[cb] >= 0) marks[tri_index(la, lidx[cb])] = 1;
                 }
             }
-        // runs of consecutive points with identical camera lists
+        // runs of consecutive points with identical camera lists (at most 255 points each), one work item per 32 camera pairs
         t.run_begin = static_cast<int32_t>(T.runs.size());
         for (int d = d0; d < d1;) {
             int e = d + 1;
             const int kd = T.pt_start[size_t(d) + 1] - T.pt_start[d];
-            while (e < d1 && e - d < 0xFFFF && T.pt_start[size_t(e) + 1] - T.pt_start[e] == kd) {
+            while (e < d1 && e - d < 255 && T.pt_start[size_t(e) + 1] - T.pt_start[e] == kd) {
                 bool same = true;
                 for (int i = 0; i < kd && same; ++i) same = cam_of(T.pt_start[d] + i) == cam_of(T.pt_start[e] + i);
                 if (!same) break;
                 ++e;
             }
-            T.runs.push_back(static_cast<uint32_t>(d - d0) | (static_cast<uint32_t>(e - d) << 16));
+            const int rounds = (kd * (kd - 1) / 2 + 31) / 32;
+            for (int r = 0; r < rounds; ++r)
+                T.runs.push_back(static_cast<uint32_t>(d - d0) | (static_cast<uint32_t>(e - d) << 16) | (static_cast<uint32_t>(r) << 24));
             d = e;
         }
         t.n_runs = static_cast<int32_t>(T.runs.size()) - t.run_begin;
@@ -209,8 +212,13 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
             T.items.push_back(it);
         }
         t.run_begin = static_cast<int32_t>(T.runs.size());
-        for (int u = 0; u < t.end - t.begin; ++u) T.runs.push_back(static_cast<uint32_t>(u) | (1u << 16));     // one item per run
-        t.n_runs = t.end - t.begin;
+        for (int u = 0; u < t.end - t.begin; ++u) {                          // an item is a run of one; a work item per 32 pairs
+            const Item& it = T.items[size_t(t.begin) + u];
+            const int na = it.a1 - it.a0, nb = it.b1 - it.b0;
+            const int rounds = ((nb ? na * nb : na * (na - 1) / 2) + 31) / 32;
+            for (int r = 0; r < rounds; ++r) T.runs.push_back(static_cast<uint32_t>(u) | (1u << 16) | (static_cast<uint32_t>(r) << 24));
+        }
+        t.n_runs = static_cast<int32_t>(T.runs.size()) - t.run_begin;
         T.w_max = std::max(T.w_max, int(t.w));
         T.tiles.push_back(t);
         o = Open();

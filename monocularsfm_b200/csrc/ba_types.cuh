@@ -29,7 +29,8 @@ struct Tile {
     int32_t cam_begin, w;         // local cameras: tile_cams[cam_begin .. cam_begin + w), ascending global camera index
     int32_t slot_begin;           // tile_slots[slot_begin + lb (lb + 1) / 2 + la] (la <= lb): global block slot or -1
     int32_t flags;                // kTileSplit
-    int32_t run_begin, n_runs;    // runs[run_begin .. +n_runs): maximal runs of consecutive units with IDENTICAL camera lists
+    int32_t run_begin, n_runs;    // runs[run_begin .. +n_runs): work items of the pair phase = (run of consecutive units with
+                                  // IDENTICAL camera lists, round of 32 camera pairs)
     int32_t pad[2];
 };
 struct Item {
@@ -74,7 +75,7 @@ struct Problem {
     // ---- tiling + block structure (built once per problem: the sparsity pattern does not change between LM iterations)
     const Tile* tiles;
     const Item* items;
-    const uint32_t* runs;           // first unit of the run inside its tile (16 bits) | number of units (16 bits)
+    const uint32_t* runs;           // first unit of the run inside its tile (16 bits) | units (8 bits) | round of 32 pairs (8 bits)
     int32_t n_tiles;
     const int32_t* tile_cams;
     const int32_t* tile_slots;

@@ -606,6 +606,35 @@ __global__ void desc_f32_quantize_kernel(const float* __restrict__ src, size_t c
         dst[i] = packed;
     }
 }
+// Extraction-time normalisation of raw SIFT rows (FeatureExtraction.cpp:143-160, 260-281), in place, one warp per row, with
+// OpenCV's arithmetic: the norm accumulated in double (cv::norm), every element multiplied IN FLOAT by float(1 / norm)
+// (Mat /= double is convertTo(alpha = 1 / norm), which scales 32F data in float), then — L1_ROOT — a correctly rounded sqrtf.
+//   kind 1: L1RootNormalized   row /= |row|_1 ; sqrt(row)          kind 2: L2Normalized   row /= |row|_2
+__global__ void desc_f32_normalize_kernel(float* __restrict__ data, int n, int kind) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < n; row += gridDim.x * wpb) {
+        float4* p = reinterpret_cast<float4*>(data + static_cast<size_t>(row) * 128) + lane;
+        const float4 v = *p;
+        double s = kind == 1 ? static_cast<double>(fabsf(v.x)) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w)
+                             : static_cast<double>(v.x) * v.x + static_cast<double>(v.y) * v.y + static_cast<double>(v.z) * v.z +
+                                   static_cast<double>(v.w) * v.w;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const double norm = kind == 1 ? s : sqrt(s);
+        const float a = static_cast<float>(1.0 / norm);
+        float4 r = make_float4(__fmul_rn(v.x, a), __fmul_rn(v.y, a), __fmul_rn(v.z, a), __fmul_rn(v.w, a));
+        if (kind == 1) r = make_float4(__fsqrt_rn(r.x), __fsqrt_rn(r.y), __fsqrt_rn(r.z), __fsqrt_rn(r.w));
+        *p = r;
+    }
+}
+cudaError_t launch_desc_normalize(float* data, int n, int kind, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    int grid = (n + 7) / 8;
+    if (grid > 148 * 8) grid = 148 * 8;
+    desc_f32_normalize_kernel<<<grid, 256, 0, st>>>(data, n, kind);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_desc_quantize(const float* src, int n, int mode, int32_t* flag, uint8_t* dst, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     const size_t count = static_cast<size_t>(n) * 128;

@@ -18,6 +18,7 @@ size_t match_tile_item_bytes(int num_units);
 cudaError_t launch_desc_format(const uint8_t*, int, int, uint8_t*, uint8_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, unsigned long long*,
                                int32_t*, int32_t*, int32_t*, cudaStream_t);
 cudaError_t launch_desc_quantize(const float*, int, int, int32_t*, uint8_t*, cudaStream_t);
+cudaError_t launch_desc_normalize(float*, int, int, cudaStream_t);
 cudaError_t launch_build_units(const SegDev*, int, int, UnitDev*, cudaStream_t);
 cudaError_t launch_resolve_rows(const ImgDev*, const UnitDev*, int, int, const int32_t*, const int32_t*, const int32_t*,
                                 MatchOpts, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, unsigned int*, cudaStream_t);
@@ -165,8 +166,10 @@ static ImgLayout img_layout(int32_t n_pad) {
 static int32_t padded_count(int32_t n) { return n > 0 ? (n + kMaxPadPerImage + 255) / 256 * 256 : 0; }
 
 // src_f32 != nullptr: float32 host descriptors, converted on the device (f32_mode: 0 decide per set, 1 always quantise)
+// normalize: 0 none, 1 L1-root, 2 L2 (raw SIFT rows, extraction-time normalisation on the device); normalized_out: optional host
+// copy of the normalised floats (what the reference writes to its database)
 static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int32_t n, bool src_on_device,
-                         const float* src_f32 = nullptr, int f32_mode = 0) {
+                         const float* src_f32 = nullptr, int f32_mode = 0, int normalize = 0, float* normalized_out = nullptr) {
     if (!c || n < 0 || (n > 0 && !src && !src_f32))
         return c ? c->fail(MSFM_E_INVALID, "msfm_desc_upload: bad arguments") : MSFM_E_INVALID;
     MSFM_CUDA(c, cudaSetDevice(c->device));
@@ -206,6 +209,13 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
         MSFM_CUDA(c, c->d_raw.reserve(u8_bytes + f32_bytes + 256));
         float* stage = reinterpret_cast<float*>(c->d_raw.as<uint8_t>() + u8_bytes);
         MSFM_CUDA(c, cudaMemcpyAsync(stage, src_f32, f32_bytes, cudaMemcpyHostToDevice, c->stream));
+        if (normalize) {
+            c->prof_begin(MSFM_PROF_DESC_FORMAT);
+            MSFM_CUDA(c, launch_desc_normalize(stage, n, normalize, c->stream));
+            c->prof_end();
+            c->launches += 1;
+            if (normalized_out) MSFM_CUDA(c, cudaMemcpyAsync(normalized_out, stage, f32_bytes, cudaMemcpyDeviceToHost, c->stream));
+        }
         c->prof_begin(MSFM_PROF_DESC_FORMAT);
         MSFM_CUDA(c, launch_desc_quantize(stage, n, f32_mode, reinterpret_cast<int32_t*>(c->d_raw.as<uint8_t>() + u8_bytes + f32_bytes),
                                           c->d_raw.as<uint8_t>(), c->stream));
@@ -268,6 +278,15 @@ int msfm_desc_upload_f32(msfm_ctx* c, int32_t image_id, const float* desc_host, 
     if (c && mode != 0 && mode != 1) return c->fail(MSFM_E_INVALID, "msfm_desc_upload_f32: mode must be 0 or 1");
     if (c && n > 0 && !desc_host) return c->fail(MSFM_E_INVALID, "msfm_desc_upload_f32: null descriptors");
     return upload_common(c, image_id, nullptr, n, false, desc_host, mode);
+}
+int msfm_desc_upload_raw_f32(msfm_ctx* c, int32_t image_id, const float* desc_host, int32_t n, int32_t normalization, float* normalized_out) {
+    if (c && image_id < 0) return c->fail(MSFM_E_INVALID, "image_id must be >= 0");
+    if (c && normalization != MSFM_NORM_L1_ROOT && normalization != MSFM_NORM_L2)
+        return c->fail(MSFM_E_INVALID, "msfm_desc_upload_raw_f32: normalization must be MSFM_NORM_L1_ROOT or MSFM_NORM_L2");
+    if (c && n > 0 && !desc_host) return c->fail(MSFM_E_INVALID, "msfm_desc_upload_raw_f32: null descriptors");
+    int rc = upload_common(c, image_id, nullptr, n, false, desc_host, 1, normalization, normalized_out);
+    if (rc == MSFM_OK && normalized_out && n > 0) MSFM_CUDA(c, cudaStreamSynchronize(c->stream));     // the host copy is complete on return
+    return rc;
 }
 int msfm_desc_quantised(msfm_ctx* c, int32_t image_id) {
     if (!c) return MSFM_E_INVALID;

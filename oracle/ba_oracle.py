@@ -336,6 +336,36 @@ def track_errors(cams, pts, obs_uv, obs_cam, obs_pt, fx, fy, cx=0.0, cy=0.0):
 
 
 # --------------------------------------------------------------------------------------------- normal equations
+def filter_stats(cams, pts, obs_uv, obs_cam, obs_pt, fx, fy, max_reproj_error):
+    """Map::FilterPoints3DWithLargeReprojectionError / ...SmallTriangulationAngle restated (src/Reconstruction/Map.cpp:804-917,
+    Projection.cpp:6-19, 114-133, 149-194): keep flag per observation, mean error of the kept observations and their number
+    per point, largest parallax angle (degrees) over the camera pairs of every point."""
+    cams, pts = np.asarray(cams, np.float64), np.asarray(pts, np.float64)
+    n_pts = len(pts)
+    Rm = np.stack([rodrigues_matrix(c[:3]) for c in cams])
+    p_cam = np.einsum("nij,nj->ni", Rm[obs_cam], pts[obs_pt]) + cams[obs_cam, 3:]
+    r = residuals_only(cams, pts, obs_uv, obs_cam, obs_pt, fx, fy)
+    err = np.sqrt((r * r).sum(1))
+    keep = (p_cam[:, 2] > 0) & ~(err > max_reproj_error)
+    kept = np.bincount(obs_pt[keep], minlength=n_pts)
+    mean = np.bincount(obs_pt[keep], err[keep], n_pts) / np.maximum(kept, 1)
+    centers = -np.einsum("nji,nj->ni", Rm, cams[:, 3:])
+    ang = np.zeros(n_pts)
+    order = np.argsort(obs_pt, kind="stable")
+    starts = np.r_[0, np.cumsum(np.bincount(obs_pt, minlength=n_pts))]
+    for p in range(n_pts):
+        cs = obs_cam[order[starts[p]:starts[p + 1]]]
+        for i in range(len(cs)):
+            for j in range(i):
+                o1, o2 = centers[cs[i]], centers[cs[j]]
+                b, r1, r2 = np.linalg.norm(o1 - o2), np.linalg.norm(pts[p] - o1), np.linalg.norm(pts[p] - o2)
+                with np.errstate(invalid="ignore"):
+                    a = abs(np.arccos((r1 * r1 + r2 * r2 - b * b) / (2 * r1 * r2)))
+                a = 0.0 if np.isnan(a) else min(a, np.pi - a) * 180 / np.pi
+                ang[p] = max(ang[p], a)
+    return keep, mean, kept, ang
+
+
 def cost_of(r):
     return 0.5 * float((r * r).sum())
 

@@ -177,3 +177,37 @@ def cv2_match_image_pair(desc1, desc2, distance_ratio=0.8, max_distance=-1.0, cr
         m21, _ = cv2_compute_matches(desc2, desc1, distance_ratio)
         m12, d12 = cross_check(m12, d12, m21, opencv_quirks)
     return filter_matches_by_distance(m12, d12, max_distance)
+
+
+# --------------------------------------------------------------------------------------------- extraction-time normalisation
+def normalize_descriptors(desc, kind):
+    """FeatureExtraction.cpp:260-281 restated with OpenCV's arithmetic (pinned against cv2 in tests/test_oracle_match.py):
+    L1RootNormalized: row /= cv::norm(row, NORM_L1); cv::sqrt(row)      L2Normalized: row /= cv::norm(row, NORM_L2).
+    cv::norm accumulates in double; `Mat /= double` is convertTo(alpha = 1 / norm), which multiplies 32F data by float(alpha)
+    in float."""
+    desc = np.asarray(desc, np.float32)
+    d64 = desc.astype(np.float64)
+    norm = np.abs(d64).sum(1) if kind == "l1_root" else np.sqrt((d64 * d64).sum(1))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = desc * (1.0 / norm).astype(np.float32)[:, None]
+        if kind == "l1_root":
+            out = np.sqrt(out)
+    return out.astype(np.float32)
+
+
+def cv2_normalize_descriptors(desc, kind):
+    """The same through cv2 itself (cv2.normalize = convertTo with alpha / norm, then cv2.sqrt), row by row as the reference."""
+    import cv2
+    desc = np.asarray(desc, np.float32)
+    out = np.empty_like(desc)
+    for i in range(len(desc)):
+        row = cv2.normalize(desc[i:i + 1], None, 1.0, 0.0, cv2.NORM_L1 if kind == "l1_root" else cv2.NORM_L2)
+        out[i] = cv2.sqrt(row) if kind == "l1_root" else row
+    return out
+
+
+def quantize_descriptors(desc):
+    """The x512 bridge of the device path: clamp(rint(512 v), 0, 255), round half to even, NaN -> 0."""
+    q = np.rint(np.asarray(desc, np.float32) * np.float32(512.0))
+    q = np.where(np.isnan(q), 0.0, q)
+    return np.clip(q, 0, 255).astype(np.uint8)

@@ -217,30 +217,60 @@ def test_local_ba_shape_and_small_problem_tolerances(ctx):
 
 
 def test_block_tridiagonal_solver_matches_dense(ctx):
-    """A ring of 240 cameras with short tracks: the reduced camera system is a narrow band after the RCM renumbering, so
-    msfm_ba_solve factors it as a block-tridiagonal chain.  Same LM trajectory as the dense Cholesky of the whole system
-    (both fp64), same optimum as the Python oracle."""
+    """A ring of 240 cameras with short tracks: the reduced camera system is a narrow band after renumbering, so msfm_ba_solve
+    factors it as a block-tridiagonal chain.  The step it computes equals a host solve of the dumped system and the dense
+    Cholesky's step (all fp64), and the LM solve reaches the optimum of the dense path and of the Python oracle."""
     P = bo.make_problem(240, 3000, 4, 13)
     ba = _create(ctx, P)
-    s = ba.solve()
+    S, rhs, _, _ = ba.linearize(1e-4)
+    dc, st = ba.solve_system(1e-4)
     info = ba.solver_info()
-    assert info["n_superblocks"] >= 3 and info["kind"].startswith("block-tridiagonal"), info
-    cams, pts = ba.get_params()
+    assert st == 0 and info["n_superblocks"] >= 3 and info["kind"].startswith("block-tridiagonal"), info
+    ref_dc = np.linalg.solve(S, rhs)
+    # S itself carries fp32 accumulation noise that differs from launch to launch (atomic order): compare through the residual
+    assert np.abs(S @ dc - rhs).max() <= 1e-6 * np.abs(rhs).max()
+    assert np.abs(dc - ref_dc).max() <= 1e-4 * np.abs(ref_dc).max()
+    s = ba.solve()
     ba.close()
     os.environ["MSFM_BA_DENSE_SOLVER"] = "1"
     try:
         bd = _create(ctx, P)
+        dcd, std = bd.solve_system(1e-4)
+        assert std == 0 and bd.solver_info()["n_superblocks"] == 0
+        assert np.abs(dcd - ref_dc).max() <= 1e-4 * np.abs(ref_dc).max()
         sd = bd.solve()
-        assert bd.solver_info()["n_superblocks"] == 0
-        cams_d, pts_d = bd.get_params()
         bd.close()
     finally:
         del os.environ["MSFM_BA_DENSE_SOLVER"]
-    assert s["termination"] == 0 and sd["termination"] == 0 and s["iterations"] == sd["iterations"]
-    assert abs(s["final_cost"] - sd["final_cost"]) <= 1e-9 * sd["final_cost"]
-    assert np.abs(cams - cams_d).max() <= 1e-6 and np.abs(pts - pts_d).max() <= 1e-5
+    # the scale of the scene is a gauge freedom (one constant camera): the two trajectories may drift apart along it, the optimum
+    # they reach is the same
+    assert s["termination"] == 0 and sd["termination"] == 0
+    assert abs(s["final_cost"] - sd["final_cost"]) <= 1e-6 * sd["final_cost"]
     ref = bo.lm_solve(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"])
     assert ref["converged"] and abs(s["final_cost"] - ref["final_cost"]) <= 1e-5 * ref["final_cost"]
+
+
+def test_filter_stats_match_the_reference_filters(ctx):
+    """msfm_ba_filter_stats == Map::FilterAllPoints3D's tests restated (oracle.filter_stats): keep flags bit-exact away from the
+    threshold, mean errors / parallax angles to 1e-9; includes a point behind a camera and long tracks."""
+    P = bo.make_long_track_problem()
+    pts = P["pts"].copy()
+    pts[3] = P["pts"][3] + np.array([0.0, 0.0, 40.0])          # far away: huge error in some views
+    cams = P["cams"]
+    c0 = -bo.rodrigues_matrix(cams[int(P["obs_cam"][np.nonzero(P["obs_pt"] == 9)[0][0]]), :3]).T @ cams[int(P["obs_cam"][np.nonzero(P["obs_pt"] == 9)[0][0]]), 3:]
+    pts[9] = c0 + 1.5 * (c0 - pts[9]) / np.linalg.norm(c0 - pts[9])    # behind its first camera: negative depth
+    ba = ctx.ba_create(cams, pts, P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"])
+    keep, mean, kept, ang = ba.filter_stats(4.0)
+    ko, mo_, no, ao = bo.filter_stats(cams, pts, P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"], 4.0)
+    r = bo.residuals_only(cams, pts, P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
+    clear = np.abs(np.sqrt((r * r).sum(1)) - 4.0) > 1e-6
+    assert (keep[clear] == ko[clear]).all() and (~ko).sum() > 10 and ko.sum() > 100
+    same = np.bincount(P["obs_pt"], ~clear, len(pts)) == 0
+    assert (kept[same] == no[same]).all()
+    np.testing.assert_allclose(mean[same], mo_[same], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(ang, ao, rtol=1e-9, atol=1e-7)
+    assert not keep[np.nonzero(P["obs_pt"] == 9)[0][0]]
+    ba.close()
 
 
 def test_bad_problem_is_rejected(ctx):

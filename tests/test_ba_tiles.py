@@ -104,11 +104,23 @@ def test_tiling_invariants(harness, which):
             assert e0_ - b0_ <= 16
         rb, nr = int(t[8]), int(t[9])
         runs = T["runs"][rb:rb + nr]
-        # the runs partition the units in order; inside a run every unit has the same camera list
-        assert (runs & 0xFFFF).tolist() == np.concatenate([[0], np.cumsum(runs >> 16)[:-1]]).tolist() and int((runs >> 16).sum()) == e0_ - b0_
+        # work items = (run, round of 32 pairs); the runs (round 0 entries) partition the units in order, and inside a run every
+        # unit has the same camera list
+        items = runs
+        runs = items[(items >> 24) == 0]
+        cnt = (runs >> 16) & 0xFF
+        kk_ = np.diff(T["pt_start"])
+        covered_units = np.zeros(e0_ - b0_, int)
+        for rn in runs:
+            covered_units[int(rn & 0xFFFF):int(rn & 0xFFFF) + int((rn >> 16) & 0xFF)] += 1
+        assert (np.diff(runs & 0xFFFF) > 0).all() and covered_units.max() <= 1
         if not (flags & 1):
+            # a unit without a work item has no camera pair (a single observation)
+            assert (kk_[b0_:e0_][covered_units == 0] < 2).all() and (kk_[b0_:e0_][covered_units == 1] >= 2).all()
+            want_items = sum((int(kk_[b0_ + int(rn & 0xFFFF)]) * (int(kk_[b0_ + int(rn & 0xFFFF)]) - 1) // 2 + 31) // 32 for rn in runs)
+            assert len(items) == want_items
             for rn in runs:
-                u0, n = int(rn & 0xFFFF), int(rn >> 16)
+                u0, n = int(rn & 0xFFFF), int((rn >> 16) & 0xFF)
                 ref = oc[T["pt_start"][b0_ + u0]:T["pt_start"][b0_ + u0 + 1]]
                 for u in range(u0 + 1, u0 + n):
                     assert np.array_equal(oc[T["pt_start"][b0_ + u]:T["pt_start"][b0_ + u + 1]], ref)
@@ -166,8 +178,10 @@ def test_items_of_neighbouring_long_tracks_are_packed(harness):
     w = tot = 0
     for t in T["tiles"][~split]:
         for rn in T["runs"][int(t[8]):int(t[8]) + int(t[9])]:
-            kk = int(k[int(t[0]) + int(rn & 0xFFFF)])
-            w += kk * (kk - 1) // 2 * int(rn >> 16) * int(rn >> 16); tot += kk * (kk - 1) // 2 * int(rn >> 16)
+            if rn >> 24:
+                continue
+            kk, n = int(k[int(t[0]) + int(rn & 0xFFFF)]), int((rn >> 16) & 0xFF)
+            w += kk * (kk - 1) // 2 * n * n; tot += kk * (kk - 1) // 2 * n
     assert w / tot > 1.5, w / tot
 
 

@@ -266,3 +266,23 @@ def test_float32_upload_bridge(ctx):
     assert ctx.quantised(30) is True
     for k in (10, 11, 20, 21, 30):
         ctx.release(k)
+
+
+@pytest.mark.parametrize("kind", ["l1_root", "l2"])
+def test_raw_sift_upload_normalises_like_the_reference_extraction(ctx, kind):
+    """msfm_desc_upload_raw_f32: the normalised rows it returns equal FeatureExtraction's (oracle pinned to cv2) bit for bit on
+    integer-valued SIFT rows, and the resident set is their x512 quantisation: matching the raw upload against an upload of
+    the oracle's quantised bytes gives identical lists."""
+    rng = np.random.default_rng(17)
+    raw1 = np.floor(np.abs(rng.standard_normal((700, 128))) * 40).astype(np.float32)
+    raw2 = np.floor(np.abs(rng.standard_normal((900, 128))) * 40).astype(np.float32)
+    raw2[rng.permutation(900)[:250]] = raw1[rng.permutation(700)[:250]]
+    raw1[5] = 0.0                                             # an all-zero row: 0 / 0 -> NaN rows quantise to zeros
+    n1 = ctx.upload_raw_f32(10, raw1, kind)
+    n2 = ctx.upload_raw_f32(11, raw2, kind)
+    o1, o2 = mo.normalize_descriptors(raw1, kind), mo.normalize_descriptors(raw2, kind)
+    assert np.array_equal(n1.view(np.uint32), o1.view(np.uint32)) and np.array_equal(n2.view(np.uint32), o2.view(np.uint32))
+    assert ctx.quantised(10) and ctx.quantised(11)
+    off, mt, d = ctx.match_pairs([[10, 11]], m.MatchOptions(0.8, 0.7 * 512.0, True, True))
+    em, ed = mo.match_image_pair(mo.quantize_descriptors(o1), mo.quantize_descriptors(o2), 0.8, 0.7 * 512.0, True, True)
+    assert mt.tolist() == em.tolist() and np.array_equal(d, ed) and len(em) > 150

@@ -71,3 +71,17 @@ def test_filter_by_distance():
     assert mm.tolist() == [[0, 1], [1, 2]]
     mm, dd = mo.filter_matches_by_distance(m, d, -1.0)
     assert len(mm) == 3
+
+
+def test_descriptor_normalisation_restatement_is_pinned_to_cv2():
+    """oracle.normalize_descriptors (FeatureExtraction.cpp:260-281) bit for bit against cv2.normalize / cv2.sqrt on raw SIFT-like
+    rows (integer valued floats as cv::SIFT produces) and on arbitrary floats."""
+    rng = np.random.default_rng(3)
+    sift = np.floor(np.abs(rng.standard_normal((600, 128))) * 40).astype(np.float32)
+    anyf = np.abs(rng.standard_normal((300, 128))).astype(np.float32) * 7.3
+    for d in (sift, anyf):
+        for kind in ("l1_root", "l2"):
+            a, b = mo.normalize_descriptors(d, kind), mo.cv2_normalize_descriptors(d, kind)
+            assert (a.view(np.uint32) == b.view(np.uint32)).mean() >= (1.0 if d is sift else 0.999)     # double summation order
+            np.testing.assert_allclose(a, b, rtol=2e-7, atol=0)
+    assert np.allclose(np.linalg.norm(mo.normalize_descriptors(sift, "l1_root"), axis=1), 1.0, atol=1e-5)   # RootSIFT rows are unit L2

@@ -46,6 +46,16 @@ def run(ctx, name, n_cams, n_pts, track, iters):
     t0 = time.perf_counter()
     s = ba.solve()          # from the optimum: one or two iterations; shows the per-iteration cost without first-call effects
     print(f"{name}: second solve {time.perf_counter() - t0:.3f}s iterations {s['iterations']} solver {ba.solver_info()}", flush=True)
+    ba.set_params(P["cams"], P["pts"])
+    ctx.prof_enable(True)
+    ctx.prof_reset()
+    t0 = time.perf_counter()
+    s = ba.solve()
+    wall = time.perf_counter() - t0
+    prof = ctx.prof_read()
+    ctx.prof_enable(False)
+    print(f"{name}: full solve again {wall:.4f}s iterations {s['iterations']} final {s['final_cost']:.6e} "
+          + " ".join(f"{k}={v['ms']:.2f}ms/{v['launches']}" for k, v in prof.items() if v['launches']), flush=True)
     ba.close()
 
 

@@ -323,6 +323,7 @@ __device__ __forceinline__ void point_pass1(const Problem& P, int beg, int end, 
 // 28 floats = 7 x 16 bytes: 128-bit loads; rows r and r' collide on a bank group only when r = r' mod 8.
 constexpr int kStageStride = 28;
 constexpr int kFusedThreads = kTileObs;       // one thread per observation of a tile
+constexpr int kTileRunItems = 1024;           // work items of the pair phase staged in shared memory (more: read from global)
 
 // acc[0..5] += v[0..5] on shared memory, 8-byte aligned.  sm_100 has no native fp32 shared-memory atomic add (atomicAdd
 // compiles to an LDS / FADD / ATOMS.CAST.SPIN loop per element, one after the other); here a row of a block is three 64-bit
@@ -399,7 +400,7 @@ __device__ __forceinline__ void smem_add6(double* base, const double v[6]) {
 
 // Shared-memory carve-up of the linearisation kernel
 struct FusedSmem {
-    size_t camacc, acc, stage, rbuf, qbuf, xybuf, ptV, ptg, ptWf, cam_start, cam_cursor, cam_obs, unit_info, lfree, misc, total;
+    size_t camacc, acc, stage, rbuf, qbuf, xybuf, ptV, ptg, ptWf, cam_start, cam_cursor, cam_obs, unit_info, run_items, lfree, misc, total;
 };
 __host__ __device__ inline FusedSmem fused_smem_layout(bool focal) {
     FusedSmem L;
@@ -417,6 +418,7 @@ __host__ __device__ inline FusedSmem fused_smem_layout(bool focal) {
     L.cam_cursor = o; o += static_cast<size_t>(kTileCams) * sizeof(int32_t);
     L.cam_obs = o; o += static_cast<size_t>(kTileObs) * sizeof(uint16_t);
     L.unit_info = o; o += static_cast<size_t>(kTilePts) * sizeof(uint32_t);
+    L.run_items = o; o += static_cast<size_t>(kTileRunItems) * sizeof(uint32_t);
     L.lfree = o; o += static_cast<size_t>(kTileCams) * sizeof(int32_t);
     L.misc = o; o += 64;
     L.total = (o + 15) / 16 * 16;
@@ -514,6 +516,7 @@ fused_linearize_kernel(Problem P, double inv_radius) {
     int32_t* cam_cursor = reinterpret_cast<int32_t*>(smem_raw + L.cam_cursor);
     uint16_t* cam_obs = reinterpret_cast<uint16_t*>(smem_raw + L.cam_obs);        // observation rows bucketed by local camera
     uint32_t* unit_info = reinterpret_cast<uint32_t*>(smem_raw + L.unit_info);       // obs base (16) | nA (8) | nB (8)
+    uint32_t* run_items = reinterpret_cast<uint32_t*>(smem_raw + L.run_items);
     int32_t* lfree = reinterpret_cast<int32_t*>(smem_raw + L.lfree);
     int32_t* misc = reinterpret_cast<int32_t*>(smem_raw + L.misc);                   // [0] tile, [1] work-queue cursor
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -535,6 +538,7 @@ fused_linearize_kernel(Problem P, double inv_radius) {
             float4* a4 = reinterpret_cast<float4*>(acc);
             for (int i = tid; i < nb * (kBlkStride / 4); i += kFusedThreads) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int i = tid; i < T.w * CV; i += kFusedThreads) camacc[i] = 0.0;
+            for (int i = tid; i < T.n_runs && i < kTileRunItems; i += kFusedThreads) run_items[i] = __ldg(P.runs + T.run_begin + i);
             if (tid < T.w) lfree[tid] = __ldg(P.cam_free + __ldg(P.tile_cams + T.cam_begin + tid));
         }
         // ---- A: this thread's observation
@@ -756,7 +760,8 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                 }
                 // ---- run item: lanes = camera pairs (x < y) of a run of points with identical camera lists; the products of
                 //      the whole run are summed in registers (packed fp32x2 FMAs) and added to the shared block once
-                const uint32_t rn = __ldg(P.runs + T.run_begin + (item - kCamParts));
+                const int ri = item - kCamParts;
+                const uint32_t rn = ri < kTileRunItems ? run_items[ri] : __ldg(P.runs + T.run_begin + ri);
                 const int u0 = static_cast<int>(rn & 0xFFFFu), nrun = static_cast<int>((rn >> 16) & 0xFFu);
                 const uint32_t ui = unit_info[u0];
                 const int nA = static_cast<int>((ui >> 16) & 0xFFu), nB = static_cast<int>(ui >> 24);

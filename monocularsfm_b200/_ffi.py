@@ -427,10 +427,13 @@ class BAProblem:
         return dc, int(st.value)
 
     def solver_info(self):
-        info = (C.c_int32 * 4)()
+        info = (C.c_int32 * 6)()
         self.ctx._check(self.lib.msfm_ba_solver_info(self.h, info))
-        return {"cams_per_superblock": info[0], "superblock_order": info[1], "n_superblocks": info[2], "n_free": info[3],
-                "kind": "block-tridiagonal (RCM)" if info[2] else "dense"}
+        kind = {0: "dense", 1: "block-tridiagonal chain (library)", 2: "band Cholesky (own kernel)"}[info[5]]
+        if info[5] == 2:
+            return {"kind": kind, "band_cameras": info[0], "tile": info[1], "tile_rows": info[2], "band_tiles": info[3], "n_free": info[4],
+                    "n_superblocks": 0}
+        return {"kind": kind, "cams_per_superblock": info[0], "superblock_order": info[1], "n_superblocks": info[2], "n_free": info[4]}
 
     def solve(self, opt: BAOptions | None = None):
         opt = opt or self.default_options()

@@ -39,6 +39,12 @@ void tridiag_info(const ba::TridiagSolver*, int32_t[4]);
 int* tridiag_dev_info(ba::TridiagSolver*);
 int tridiag_n_super(const ba::TridiagSolver*);
 cudaError_t tridiag_factor_solve(ba::TridiagSolver*, const Problem&, double, cusolverDnHandle_t, double*, int, cudaStream_t);
+namespace band { struct BandSolver; }
+band::BandSolver* band_create(int, const std::vector<int32_t>&, const std::vector<int32_t>&, int, cudaError_t*);
+void band_destroy(band::BandSolver*);
+void band_info(const band::BandSolver*, int32_t[4]);
+int32_t* band_dev_info(band::BandSolver*);
+cudaError_t band_factor_solve(band::BandSolver*, const Problem&, double, double*, int, cudaStream_t);
 }  // namespace msfm
 using namespace msfm;
 
@@ -110,7 +116,8 @@ struct msfm_ba {
     float* sblk = nullptr;
     int32_t* tile_counter = nullptr;
     double* dense = nullptr;      // [n6][n6] dense copy of S for the dense Cholesky (allocated by the first solve that needs it)
-    ba::TridiagSolver* tri = nullptr;    // block-tridiagonal chain after RCM renumbering (ba_solver.cu), when the band is narrow
+    band::BandSolver* bands = nullptr;   // own cooperative band Cholesky after renumbering (ba_band.cu), when the band is narrow
+    ba::TridiagSolver* tri = nullptr;    // the same band as a block-tridiagonal chain of library calls (ba_solver.cu; MSFM_BA_SOLVER=chain)
     bool tri_tried = false;
     double* rec = nullptr;        // [16] per-iteration record (lm_record_kernel)
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -193,6 +200,7 @@ void msfm_ba_destroy(msfm_ba* b) {
         if (p) cudaFree(p);
     if (b->rec) cudaFree(b->rec);
     if (b->tri) tridiag_destroy(b->tri);
+    if (b->bands) band_destroy(b->bands);
     for (cudaEvent_t e : b->ev)
         if (e) cudaEventDestroy(e);
     delete b;
@@ -566,13 +574,16 @@ static int solver_setup(msfm_ba* b) {
         if (!e) BA_CUDA(cudaEventCreate(&e));
     if (n6 > 0 && !b->tri_tried) {
         b->tri_tried = true;
-        if (!getenv("MSFM_BA_DENSE_SOLVER")) {
-            cudaError_t e = cudaSuccess;
-            b->tri = tridiag_create(b->n_free, b->h_blk_row, b->h_blk_col, solver, c->stream, &e);
-            if (e != cudaSuccess) return c->cuda_fail(e, "msfm_ba_solve: block-tridiagonal solver setup");
-        }
+        // MSFM_BA_SOLVER = band (default: own band Cholesky) | chain (library block-tridiagonal chain) | dense (cuSOLVER potrf of
+        // the whole system); the band solvers fall back to dense when the band is wide.  MSFM_BA_DENSE_SOLVER=1 = dense.
+        const char* sel = getenv("MSFM_BA_SOLVER");
+        const bool dense = getenv("MSFM_BA_DENSE_SOLVER") || (sel && !strcmp(sel, "dense"));
+        cudaError_t e = cudaSuccess;
+        if (!dense && sel && !strcmp(sel, "chain")) b->tri = tridiag_create(b->n_free, b->h_blk_row, b->h_blk_col, solver, c->stream, &e);
+        else if (!dense) b->bands = band_create(b->n_free, b->h_blk_row, b->h_blk_col, c->num_sms, &e);
+        if (e != cudaSuccess) return c->cuda_fail(e, "msfm_ba_solve: band solver setup");
     }
-    if (n6 > 0 && !b->tri) {
+    if (n6 > 0 && !b->tri && !b->bands) {
         if (!b->dense) BA_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->dense), N * N * sizeof(double)));
         int lwork = 0;
         if (cusolverDnDpotrf_bufferSize(solver, CUBLAS_FILL_MODE_LOWER, n6, b->dense, n6, &lwork) != CUSOLVER_STATUS_SUCCESS)
@@ -593,7 +604,11 @@ static int solver_queue(msfm_ba* b, double inv_radius, int nrhs, const int** inf
     const int n6 = b->n_free * 6;
     const size_t N = size_t(n6);
     c->prof_begin(MSFM_PROF_BA_SOLVE);
-    if (b->tri) {
+    if (b->bands) {
+        BA_CUDA(band_factor_solve(b->bands, b->view(b->cur), inv_radius, b->xsol, nrhs, c->stream));
+        *info_ptr = band_dev_info(b->bands);
+        *n_info = 1;
+    } else if (b->tri) {
         BA_CUDA(tridiag_factor_solve(b->tri, b->view(b->cur), inv_radius, solver, b->xsol, nrhs, c->stream));
         *info_ptr = tridiag_dev_info(b->tri);
         *n_info = tridiag_n_super(b->tri);
@@ -614,10 +629,12 @@ static int solver_queue(msfm_ba* b, double inv_radius, int nrhs, const int** inf
     return MSFM_OK;
 }
 
-int msfm_ba_solver_info(msfm_ba* b, int32_t info[4]) {
+int msfm_ba_solver_info(msfm_ba* b, int32_t info[6]) {
     if (!b || !info) return MSFM_E_INVALID;
-    info[0] = info[1] = info[2] = 0; info[3] = b->n_free;
-    if (b->tri) tridiag_info(b->tri, info);
+    info[0] = info[1] = info[2] = info[3] = 0;
+    info[4] = b->n_free; info[5] = 0;
+    if (b->bands) { band_info(b->bands, info); info[5] = 2; }
+    else if (b->tri) { tridiag_info(b->tri, info); info[5] = 1; }
     return MSFM_OK;
 }
 

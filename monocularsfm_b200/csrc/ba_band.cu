@@ -1,0 +1,374 @@
+// Band Cholesky of the reduced camera system, hand-written: ONE cooperative kernel factors the renumbered system
+// S = L L^T inside its band, carries the right-hand sides through the forward substitution, and back-substitutes.
+//
+// Replaces the linear solver Ceres runs behind ceres::Solve for DENSE_SCHUR / SPARSE_SCHUR
+// (src/Optimizer/CeresBundleOptimizer.cpp:264-273,293).  Round 2 first walked the band as a block-tridiagonal chain of library
+// calls (cuSOLVER potrf + cuBLAS trsm / syrk per super-block, ba_solver.cu): at BASELINE configs[4] (7968 unknowns, band of
+// 126 cameras) that chain is latency-bound — 334 us per potrf(756) panel kernel, 1439 small trsm kernels, 9.2 ms per solve
+// (profiles/r02_ba_launches_library_chain.csv) — no faster than the dense potrf it replaced.  Here the whole factorisation is
+// one launch: the lower band is stored as 48 x 48 fp64 tiles (8 cameras per tile row), and per tile column j
+//     D   one CTA:      L_jj = chol(T_jj)            thread = row, the row in registers, rows published through shared memory
+//     P   nbk CTAs:     L_Ij = T_Ij L_jj^-T          thread = row of the tile, forward substitution against L_jj in shared memory
+//                       y_j  = L_jj^-1 y_j           (the right-hand sides ride along as one more panel task)
+//     U   all CTAs:     T_IK -= L_Ij L_Kj^T          one 48x48x48 tile product per CTA (3x3 register blocks), j < K <= I <= j + nbk
+//                       y_I  -= L_Ij y_j
+// separated by grid barriers (cooperative launch: every CTA is resident), then CTA 0 back-substitutes.
+// fp64 throughout.  Tensor cores are not used (north_star: not for the sparse BA).
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+#include "ba_types.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace msfm {
+namespace band {
+
+constexpr int NB = 48;             // tile order: 8 cameras
+constexpr int kThreads = 256;
+constexpr int kLd = NB + 1;        // shared-memory leading dimension (doubles)
+
+struct Params {
+    double* tiles;     // [R][nbk + 1][NB][NB] row-major tiles of the lower band: slot d of block row I holds tile (I, I - nbk + d)
+    double* y;         // [nrhs][R * NB] right-hand sides / solutions (renumbered order)
+    int32_t* info;     // != 0: a pivot was not positive
+    int32_t R, nbk, nrhs;
+};
+
+__device__ __forceinline__ double* tile_ptr(const Params& p, int I, int J) {
+    return p.tiles + (static_cast<size_t>(I) * (p.nbk + 1) + (J - I + p.nbk)) * (NB * NB);
+}
+
+// global tile (row-major) <-> shared [NB][kLd]
+__device__ __forceinline__ void load_tile(const double* __restrict__ g, double* s) {
+    for (int i = threadIdx.x; i < NB * NB; i += kThreads) s[(i / NB) * kLd + (i % NB)] = g[i];
+}
+
+// ---- D: Cholesky of a 48 x 48 tile in shared memory sA (lower triangle used), L written to sA and to global g.
+// Thread r < 48 owns row r in registers; after step k every thread has published L[r][k], so row k (needed by all at the next
+// dot product) is complete in shared memory.
+__device__ void diag_cholesky(double* sA, double* __restrict__ g, int32_t* info) {
+    const int r = threadIdx.x;
+    double a[NB];
+    if (r < NB) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) a[c] = sA[r * kLd + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        double s = 0.0;
+        if (r < NB && r >= k) {
+            double s0 = a[k], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int m = 0; m + 3 < k; m += 4) {
+                s0 -= a[m] * sA[k * kLd + m];
+                s1 -= a[m + 1] * sA[k * kLd + m + 1];
+                s2 -= a[m + 2] * sA[k * kLd + m + 2];
+                s3 -= a[m + 3] * sA[k * kLd + m + 3];
+            }
+#pragma unroll
+            for (int m = k & ~3; m < k; ++m) s0 -= a[m] * sA[k * kLd + m];
+            s = (s0 + s1) + (s2 + s3);
+            if (r == k) {
+                if (!(s > 0.0)) { atomicExch(info, 1); s = 1.0; }
+                s = sqrt(s);
+                a[k] = s;
+                sA[k * kLd + k] = s;
+            }
+        }
+        __syncthreads();
+        if (r < NB && r > k) {
+            a[k] = s / sA[k * kLd + k];
+            sA[r * kLd + k] = a[k];
+        }
+        __syncthreads();
+    }
+    if (r < NB) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) g[r * NB + c] = c <= r ? a[c] : 0.0;
+    }
+}
+
+// ---- P: rows x of a tile solved against L (shared memory sL): x <- x L^-T, i.e. x[c] = (x[c] - sum_{k<c} x[k] L[c][k]) / L[c][c].
+// One thread per row, the row in registers, no communication.
+__device__ __forceinline__ void solve_row(double x[NB], const double* sL) {
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        double s0 = x[c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 3 < c; k += 4) {
+            s0 -= x[k] * sL[c * kLd + k];
+            s1 -= x[k + 1] * sL[c * kLd + k + 1];
+            s2 -= x[k + 2] * sL[c * kLd + k + 2];
+            s3 -= x[k + 3] * sL[c * kLd + k + 3];
+        }
+#pragma unroll
+        for (int k = c & ~3; k < c; ++k) s0 -= x[k] * sL[c * kLd + k];
+        x[c] = ((s0 + s1) + (s2 + s3)) / sL[c * kLd + c];
+    }
+}
+
+// ---- U: C -= A B^T for 48 x 48 tiles; A, B staged in shared memory TRANSPOSED ([k][row]); 16 x 16 threads, 3 x 3 outputs each
+__device__ void tile_update(const double* __restrict__ gA, const double* __restrict__ gB, double* __restrict__ gC, double* sA, double* sB) {
+    for (int i = threadIdx.x; i < NB * NB; i += kThreads) {
+        const int row = i / NB, k = i % NB;
+        sA[k * kLd + row] = gA[i];
+        sB[k * kLd + row] = gB[i];
+    }
+    __syncthreads();
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll 4
+    for (int k = 0; k < NB; ++k) {
+        const double a0 = sA[k * kLd + 3 * ty], a1 = sA[k * kLd + 3 * ty + 1], a2 = sA[k * kLd + 3 * ty + 2];
+        const double b0 = sB[k * kLd + 3 * tx], b1 = sB[k * kLd + 3 * tx + 1], b2 = sB[k * kLd + 3 * tx + 2];
+        acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[0][2] += a0 * b2;
+        acc[1][0] += a1 * b0; acc[1][1] += a1 * b1; acc[1][2] += a1 * b2;
+        acc[2][0] += a2 * b0; acc[2][1] += a2 * b1; acc[2][2] += a2 * b2;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gC[(3 * ty + i) * NB + 3 * tx + j] -= acc[i][j];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+band_cholesky_kernel(Params p) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sA[NB * kLd];
+    __shared__ double sB[NB * kLd];
+    __shared__ double sv[4 * NB];
+    const int R = p.R, nbk = p.nbk, Npad = R * NB;
+    const int bid = blockIdx.x, nblk = gridDim.x;
+
+    for (int j = 0; j < R; ++j) {
+        const int m = min(nbk, R - 1 - j);                 // tile rows below the diagonal in this column
+        // ---- D
+        if (bid == 0) {
+            load_tile(tile_ptr(p, j, j), sA);
+            __syncthreads();
+            diag_cholesky(sA, tile_ptr(p, j, j), p.info);
+        }
+        grid.sync();
+        // ---- P: tasks 0 .. m-1 = tiles (j + 1 + t, j); task m = the right-hand sides
+        for (int t = bid; t <= m; t += nblk) {
+            load_tile(tile_ptr(p, j, j), sB);              // L_jj
+            __syncthreads();
+            if (t < m) {
+                double* g = tile_ptr(p, j + 1 + t, j);
+                if (threadIdx.x < NB) {
+                    double x[NB];
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) x[c] = g[threadIdx.x * NB + c];
+                    solve_row(x, sB);
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) g[threadIdx.x * NB + c] = x[c];
+                }
+            } else if (threadIdx.x < p.nrhs) {
+                double* yj = p.y + static_cast<size_t>(threadIdx.x) * Npad + static_cast<size_t>(j) * NB;
+                double x[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) x[c] = yj[c];
+                solve_row(x, sB);
+#pragma unroll
+                for (int c = 0; c < NB; ++c) yj[c] = x[c];
+            }
+            __syncthreads();
+        }
+        grid.sync();
+        // ---- U: tasks 0 .. m(m+1)/2 - 1 = tiles (I, K), j < K <= I <= j + m; the last task = right-hand side updates
+        const int ntile = m * (m + 1) / 2;
+        for (int t = bid; t <= ntile; t += nblk) {
+            if (t < ntile) {
+                int a = static_cast<int>((sqrtf(8.0f * static_cast<float>(t) + 1.0f) - 1.0f) * 0.5f);
+                while (a * (a + 1) / 2 > t) --a;
+                while ((a + 1) * (a + 2) / 2 <= t) ++a;
+                const int b = t - a * (a + 1) / 2;           // 0 <= b <= a < m
+                const int I = j + 1 + a, K = j + 1 + b;
+                tile_update(tile_ptr(p, I, j), tile_ptr(p, K, j), tile_ptr(p, I, K), sA, sB);
+            } else if (m > 0) {
+                // y_I -= L_Ij y_j for the m tile rows below: thread = (rhs, tile row a, row r)
+                for (int q = 0; q < p.nrhs; ++q) {
+                    const double* yj = p.y + static_cast<size_t>(q) * Npad + static_cast<size_t>(j) * NB;
+                    if (threadIdx.x < NB) sv[threadIdx.x] = yj[threadIdx.x];
+                    __syncthreads();
+                    for (int i = threadIdx.x; i < m * NB; i += kThreads) {
+                        const int a = i / NB, r = i % NB;
+                        const double* L = tile_ptr(p, j + 1 + a, j) + r * NB;
+                        double s = 0.0;
+#pragma unroll 8
+                        for (int c = 0; c < NB; ++c) s += L[c] * sv[c];
+                        p.y[static_cast<size_t>(q) * Npad + static_cast<size_t>(j + 1 + a) * NB + r] -= s;
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        grid.sync();
+    }
+    // ---- back substitution by CTA 0: x_j = L_jj^-T (y_j - sum_{I > j} L_Ij^T x_I)
+    if (bid != 0) return;
+    for (int q = 0; q < p.nrhs; ++q) {
+        double* y = p.y + static_cast<size_t>(q) * Npad;
+        for (int j = R - 1; j >= 0; --j) {
+            const int m = min(nbk, R - 1 - j);
+            // partial sums over the tile rows below: thread = (column c, slice), rows of the tiles are read coalesced over c
+            const int c = threadIdx.x % NB, slice = threadIdx.x / NB;          // 5 full slices (240 threads)
+            double s = 0.0;
+            if (slice < 5) {
+                for (int i = slice; i < m * NB; i += 5) {
+                    const int a = i / NB, r = i % NB;
+                    s += tile_ptr(p, j + 1 + a, j)[r * NB + c] * y[static_cast<size_t>(j + 1 + a) * NB + r];
+                }
+            }
+            load_tile(tile_ptr(p, j, j), sA);
+            if (slice < 5) sB[slice * NB + c] = s;
+            __syncthreads();
+            if (threadIdx.x < NB) sv[threadIdx.x] = y[static_cast<size_t>(j) * NB + threadIdx.x] -
+                                                    (sB[threadIdx.x] + sB[NB + threadIdx.x] + sB[2 * NB + threadIdx.x] + sB[3 * NB + threadIdx.x] + sB[4 * NB + threadIdx.x]);
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                // L_jj^T x = sv by warp 0, from the last unknown up: x[cc] is final once every later unknown has been
+                // eliminated from it; lanes then remove it from the earlier ones (row cc of L)
+                for (int cc = NB - 1; cc >= 0; --cc) {
+                    const double x = sv[cc] / sA[cc * kLd + cc];
+                    __syncwarp();
+                    if (threadIdx.x == 0) sv[cc] = x;
+                    for (int k = threadIdx.x; k < cc; k += 32) sv[k] -= sA[cc * kLd + k] * x;
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < NB) y[static_cast<size_t>(j) * NB + threadIdx.x] = sv[threadIdx.x];
+            __syncthreads();
+        }
+    }
+}
+
+// block slot -> tile scatter of the fp32 blocks into the fp64 band (lower triangle of the renumbered matrix), damping added
+__global__ void expand_band_kernel(ba::Problem P, const int32_t* __restrict__ pos, Params p, double inv_radius) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P.n_blocks * 36) return;
+    const int b = idx / 36, e = idx - 36 * b, i = e / 6, j = e - 6 * i;
+    const int fa = __ldg(P.blk_row + b), fb = __ldg(P.blk_col + b);
+    const int pa = __ldg(pos + fa), pb = __ldg(pos + fb);
+    double v = static_cast<double>(P.sblk[idx]);                    // S[fa*6+i][fb*6+j]
+    if (fa == fb) {
+        if (j > i) return;                                         // lower triangle of a diagonal block, taken from its upper triangle
+        v = static_cast<double>(P.sblk[b * 36 + 6 * j + i]);
+        if (i == j) v += fmax(P.tail[P.tl.udiag + fa * 6 + i], 1e-6) * inv_radius;
+    }
+    int r, c;
+    if (pa >= pb) { r = pa * 6 + i; c = pb * 6 + j; } else { r = pb * 6 + j; c = pa * 6 + i; }
+    const int I = r / NB, J = c / NB;
+    tile_ptr(p, I, J)[(r - I * NB) * NB + (c - J * NB)] = v;
+}
+// unit diagonal on the padding rows behind the last unknown
+__global__ void pad_band_kernel(Params p, int n) {
+    const int r = n + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.R * NB) return;
+    const int I = r / NB;
+    tile_ptr(p, I, I)[(r - I * NB) * (NB + 1)] = 1.0;
+}
+__global__ void permute_in_kernel(const double* __restrict__ src, const int32_t* __restrict__ pos, int nf, double* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf * 6) return;
+    const int f = i / 6, k = i - 6 * f;
+    dst[static_cast<size_t>(pos[f]) * 6 + k] = src[i];
+}
+__global__ void permute_out_kernel(const double* __restrict__ src, const int32_t* __restrict__ pos, int nf, double* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf * 6) return;
+    const int f = i / 6, k = i - 6 * f;
+    dst[i] = src[static_cast<size_t>(pos[f]) * 6 + k];
+}
+
+struct BandSolver {
+    int nf = 0, bw = 0, R = 0, nbk = 0, grid = 0;
+    int32_t* d_pos = nullptr;
+    double *tiles = nullptr, *y = nullptr;
+    int32_t* d_info = nullptr;
+    size_t tile_bytes = 0;
+};
+
+}  // namespace band
+
+namespace ba { void rcm_order(int, const std::vector<int32_t>&, const std::vector<int32_t>&, std::vector<int32_t>&, int&); }
+using band::BandSolver;
+
+// nullptr: the band is too wide for band storage to pay (the caller keeps the dense path), or an allocation failed (*err set)
+BandSolver* band_create(int nf, const std::vector<int32_t>& blk_row, const std::vector<int32_t>& blk_col, int num_sms, cudaError_t* err) {
+    *err = cudaSuccess;
+    if (nf < 48) return nullptr;
+    std::vector<int32_t> pos;
+    int bw = 0;
+    ba::rcm_order(nf, blk_row, blk_col, pos, bw);
+    if (3 * std::max(1, bw) >= nf) return nullptr;
+    BandSolver* B = new BandSolver();
+    B->nf = nf; B->bw = bw;
+    B->R = (6 * nf + band::NB - 1) / band::NB;
+    B->nbk = 0;
+    for (size_t k = 0; k < blk_row.size(); ++k) {
+        const int pa = pos[blk_row[k]], pb = pos[blk_col[k]];
+        const int hi = std::max(pa, pb) * 6 + 5, lo = std::min(pa, pb) * 6;
+        B->nbk = std::max(B->nbk, hi / band::NB - lo / band::NB);
+    }
+    B->tile_bytes = static_cast<size_t>(B->R) * (B->nbk + 1) * band::NB * band::NB * sizeof(double);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&B->d_pos), static_cast<size_t>(nf) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->tiles), B->tile_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->y), 3 * static_cast<size_t>(B->R) * band::NB * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->d_info), 4 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(B->d_pos, pos.data(), static_cast<size_t>(nf) * sizeof(int32_t), cudaMemcpyHostToDevice);
+    int per_sm = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, band::band_cholesky_kernel, band::kThreads, 0);
+    if (e == cudaSuccess && per_sm < 1) e = cudaErrorLaunchOutOfResources;
+    if (e != cudaSuccess) {
+        *err = e;
+        cudaFree(B->d_pos); cudaFree(B->tiles); cudaFree(B->y); cudaFree(B->d_info);
+        delete B;
+        return nullptr;
+    }
+    // one CTA per SM, no more than the widest phase can use
+    const int widest = B->nbk * (B->nbk + 1) / 2 + 1;
+    B->grid = std::max(1, std::min(num_sms, widest));
+    return B;
+}
+void band_destroy(BandSolver* B) {
+    if (!B) return;
+    cudaFree(B->d_pos); cudaFree(B->tiles); cudaFree(B->y); cudaFree(B->d_info);
+    delete B;
+}
+void band_info(const BandSolver* B, int32_t out[4]) { out[0] = B->bw; out[1] = band::NB; out[2] = B->R; out[3] = B->nbk; }
+int32_t* band_dev_info(BandSolver* B) { return B->d_info; }
+
+// Expand S (+ damping) into the band, factor, solve nrhs right-hand sides (columns of N = 6 nf doubles at stride N, caller's
+// camera order; overwritten by the solutions).  Asynchronous on st; *band_dev_info != 0 afterwards = not positive definite.
+cudaError_t band_factor_solve(BandSolver* B, const ba::Problem& P, double inv_radius, double* rhs, int nrhs, cudaStream_t st) {
+    band::Params p;
+    p.tiles = B->tiles; p.y = B->y; p.info = B->d_info; p.R = B->R; p.nbk = B->nbk; p.nrhs = nrhs;
+    const int N = 6 * B->nf, Npad = B->R * band::NB;
+    cudaError_t e = cudaMemsetAsync(B->tiles, 0, B->tile_bytes, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(B->y, 0, 3 * static_cast<size_t>(Npad) * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(B->d_info, 0, 4 * sizeof(int32_t), st);
+    if (e != cudaSuccess) return e;
+    const int tot = P.n_blocks * 36;
+    band::expand_band_kernel<<<(tot + 255) / 256, 256, 0, st>>>(P, B->d_pos, p, inv_radius);
+    if (Npad > N) band::pad_band_kernel<<<(Npad - N + 63) / 64, 64, 0, st>>>(p, N);
+    for (int c = 0; c < nrhs; ++c)
+        band::permute_in_kernel<<<(N + 255) / 256, 256, 0, st>>>(rhs + static_cast<size_t>(c) * N, B->d_pos, B->nf, B->y + static_cast<size_t>(c) * Npad);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    void* args[] = {&p};
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(band::band_cholesky_kernel), dim3(B->grid), dim3(band::kThreads), args, 0, st);
+    if (e != cudaSuccess) return e;
+    for (int c = 0; c < nrhs; ++c)
+        band::permute_out_kernel<<<(N + 255) / 256, 256, 0, st>>>(B->y + static_cast<size_t>(c) * Npad, B->d_pos, B->nf, rhs + static_cast<size_t>(c) * N);
+    return cudaGetLastError();
+}
+
+}  // namespace msfm

@@ -398,6 +398,32 @@ __device__ __forceinline__ void smem_add6(double* base, const double v[6]) {
     }
 }
 
+// Rows I0 and 5 - I0 of a camera's diagonal block U - Y W^T = sum Jc^T N Jc over the observations cam_obs[pb], cam_obs[pb + step],
+// ...: UPPER triangle only (the block is symmetric: 21 of its 36 entries; every reader takes the upper triangle), 7 sums.
+template <int I0>
+__device__ __forceinline__ void diag_row_pair(const float* __restrict__ stage, const uint16_t* __restrict__ cam_obs, int pb, int pe, int step,
+                                              float* blk) {
+    constexpr int I1 = 5 - I0;
+    float r0[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, r1[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int pp = pb; pp < pe; pp += step) {
+        const float* sr = stage + static_cast<int>(cam_obs[pp]) * kStageStride;
+        const float4 j0 = reinterpret_cast<const float4*>(sr)[0], j1 = reinterpret_cast<const float4*>(sr)[1],
+                     j2 = reinterpret_cast<const float4*>(sr)[2], nn = reinterpret_cast<const float4*>(sr)[6];
+        const float n00 = nn.y, n01 = nn.z, n11 = nn.w;
+        const float c0[6] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y}, c1[6] = {j1.z, j1.w, j2.x, j2.y, j2.z, j2.w};
+        const float ua = c0[I0] * n00 + c1[I0] * n01, va = c0[I0] * n01 + c1[I0] * n11;     // row I0 of Jc^T N
+        const float ub = c0[I1] * n00 + c1[I1] * n01, vb = c0[I1] * n01 + c1[I1] * n11;     // row I1 of Jc^T N
+#pragma unroll
+        for (int j = I0; j < 6; ++j) r0[j] += ua * c0[j] + va * c1[j];
+#pragma unroll
+        for (int j = I1; j < 6; ++j) r1[j] += ub * c0[j] + vb * c1[j];
+    }
+    if (pb < pe) {
+        smem_add_row(blk + 6 * I0, r0);
+        smem_add_row(blk + 6 * I1, r1);
+    }
+}
+
 // Shared-memory carve-up of the linearisation kernel
 struct FusedSmem {
     size_t camacc, acc, stage, rbuf, qbuf, xybuf, ptV, ptg, ptWf, cam_start, cam_cursor, cam_obs, unit_info, run_items, lfree, misc, total;
@@ -488,8 +514,9 @@ long_track_prepass_kernel(Problem P, double inv_radius) {
 //   B  thread = point (unit): V, g_p over its staged observations, damping, 3x3 inverse
 //   C  thread = observation: Q = Jp V^-1, N = I - Q Jp^T, q = Q g_p - r -> staged; observations bucketed by local camera
 //   E  a work queue over the warps:
-//        camera items  lane = local camera: ONE part (a row of the diagonal block U - Y W^T = sum Jc^T N Jc, or rhs / g_c /
-//                      diag U) summed over a quarter of the camera's observations of the tile — four adders per address;
+//        camera items  lane = local camera: ONE part (two rows of the upper triangle of the diagonal block U - Y W^T =
+//                      sum Jc^T N Jc, or rhs / g_c / diag U) summed over a quarter of the camera's observations of the tile —
+//                      four adders per address;
 //        run items     lanes = 32 camera pairs (x < y) of a RUN of points with identical camera lists: block (x, y) -=
 //                      sum over the run of Jc_x^T (Q_x Jp_y^T) Jc_y, summed in registers with packed fp32x2 FMAs and added to
 //                      the shared-memory block with 128-bit compare-and-swaps (the pairs of a point never share a block;
@@ -694,7 +721,7 @@ fused_linearize_kernel(Problem P, double inv_radius) {
         // ---- E: work queue: camera items first, then one item per unit
         {
             constexpr int kCamSplit = 4;                    // every camera part is summed by four items (a quarter of the list each)
-            constexpr int kCamParts = (kFocal ? 11 : 9) * kCamSplit;   // 6 rows of the diagonal block | rhs | g_c | diag U (| border columns)
+            constexpr int kCamParts = (kFocal ? 6 : 4) * kCamSplit;   // 3 row pairs of the diagonal block | rhs, g_c, diag U (| 2 border columns)
             const int n_items = kCamParts + T.n_runs;
             for (;;) {
                 int item = 0;
@@ -707,41 +734,40 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                     const int l = lane, part = item / kCamSplit, quarter = item - part * kCamSplit;
                     if (l < T.w) {
                         const int pb = cam_start[l] + quarter, pe = cam_start[l + 1];
-                        if (part < 6) {
-                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
-                            for (int pp = pb; pp < pe; pp += kCamSplit) {
-                                const float* sr = stage + static_cast<int>(cam_obs[pp]) * kStageStride;
-                                const float4 j0 = reinterpret_cast<const float4*>(sr)[0], j1 = reinterpret_cast<const float4*>(sr)[1],
-                                             j2 = reinterpret_cast<const float4*>(sr)[2], nn = reinterpret_cast<const float4*>(sr)[6];
-                                const float n00 = nn.y, n01 = nn.z, n11 = nn.w;
-                                const float ci = sr[part], di = sr[6 + part];          // Jc[0][part], Jc[1][part]
-                                const float u = ci * n00 + di * n01, v = ci * n01 + di * n11;   // row `part` of Jc^T N  (1 x 2)
-                                a0 += u * j0.x + v * j1.z; a1 += u * j0.y + v * j1.w; a2 += u * j0.z + v * j2.x;
-                                a3 += u * j0.w + v * j2.y; a4 += u * j1.x + v * j2.z; a5 += u * j1.y + v * j2.w;
-                            }
-                            if (pb < pe) {
-                                const float row[6] = {a0, a1, a2, a3, a4, a5};
-                                smem_add_row(acc + (l * (l + 1) / 2 + l) * kBlkStride + 6 * part, row);
-                            }
-                        } else if (part < 9) {
-                            double a[6] = {0, 0, 0, 0, 0, 0};
+                        if (part < 3) {
+                            float* blk = acc + (l * (l + 1) / 2 + l) * kBlkStride;
+                            if (part == 0) diag_row_pair<0>(stage, cam_obs, pb, pe, kCamSplit, blk);
+                            else if (part == 1) diag_row_pair<1>(stage, cam_obs, pb, pe, kCamSplit, blk);
+                            else diag_row_pair<2>(stage, cam_obs, pb, pe, kCamSplit, blk);
+                        } else if (part == 3) {
+                            // rhs = sum Jc^T q, g_c = sum Jc^T r (fp64), diag U = sum Jc^2 (only scales the damping: fp32 sums)
+                            double ar[6] = {0, 0, 0, 0, 0, 0}, ag[6] = {0, 0, 0, 0, 0, 0};
+                            float au[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                             for (int pp = pb; pp < pe; pp += kCamSplit) {
                                 const int row = cam_obs[pp];
                                 const float* sr = stage + row * kStageStride;
-                                double w0, w1;
-                                if (part == 6) { w0 = qbuf[2 * row]; w1 = qbuf[2 * row + 1]; }
-                                else { w0 = rbuf[2 * row]; w1 = rbuf[2 * row + 1]; }
+                                const double q0 = qbuf[2 * row], q1 = qbuf[2 * row + 1], e0 = rbuf[2 * row], e1 = rbuf[2 * row + 1];
 #pragma unroll
                                 for (int i = 0; i < 6; ++i) {
-                                    const double c0 = sr[i], c1 = sr[6 + i];
-                                    a[i] += part == 8 ? c0 * c0 + c1 * c1 : c0 * w0 + c1 * w1;
+                                    const float f0 = sr[i], f1 = sr[6 + i];
+                                    const double c0 = f0, c1 = f1;
+                                    ar[i] += c0 * q0 + c1 * q1;
+                                    ag[i] += c0 * e0 + c1 * e1;
+                                    au[i] += f0 * f0 + f1 * f1;
                                 }
                             }
-                            if (pb < pe) smem_add6(camacc + l * CV + 6 * (part - 6), a);
+                            if (pb < pe) {
+                                double ud[6];
+#pragma unroll
+                                for (int i = 0; i < 6; ++i) ud[i] = au[i];
+                                smem_add6(camacc + l * CV, ar);
+                                smem_add6(camacc + l * CV + 6, ag);
+                                smem_add6(camacc + l * CV + 12, ud);
+                            }
                         } else if (kFocal) {
-                            // border column (part - 9) of B_c = sum Jc^T (Jf - Q Wf^T),  Jf = diag(xp, yp)
+                            // border column (part - 4) of B_c = sum Jc^T (Jf - Q Wf^T),  Jf = diag(xp, yp)
                             double a[6] = {0, 0, 0, 0, 0, 0};
-                            const int col = part - 9;
+                            const int col = part - 4;
                             for (int pp = pb; pp < pe; pp += kCamSplit) {
                                 const int row = cam_obs[pp];
                                 const float* sr = stage + row * kStageStride;
@@ -879,7 +905,10 @@ __global__ void expand_dense_kernel(Problem P, double inv_radius, double* __rest
     const int fa = __ldg(P.blk_row + b), fb = __ldg(P.blk_col + b);
     const size_t n6 = static_cast<size_t>(P.n_free) * 6;
     double v = static_cast<double>(P.sblk[idx]);
-    if (fa == fb && i == j) v += fmax(P.tail[P.tl.udiag + fa * 6 + i], 1e-6) * inv_radius;
+    if (fa == fb) {
+        v = static_cast<double>(P.sblk[b * 36 + (i <= j ? 6 * i + j : 6 * j + i)]);     // a diagonal block holds its upper triangle
+        if (i == j) v += fmax(P.tail[P.tl.udiag + fa * 6 + i], 1e-6) * inv_radius;
+    }
     S[(static_cast<size_t>(fa) * 6 + i) * n6 + static_cast<size_t>(fb) * 6 + j] = v;
 }
 

@@ -220,38 +220,53 @@ def test_local_ba_shape_and_small_problem_tolerances(ctx):
     ba.close()
 
 
-def test_block_tridiagonal_solver_matches_dense(ctx):
+@pytest.mark.parametrize("solver", ["band", "chain"])
+def test_band_solvers_match_dense(ctx, solver):
     """A ring of 240 cameras with short tracks: the reduced camera system is a narrow band after renumbering, so msfm_ba_solve
-    factors it as a block-tridiagonal chain.  The step it computes equals a host solve of the dumped system and the dense
-    Cholesky's step (all fp64), and the LM solve reaches the optimum of the dense path and of the Python oracle."""
+    factors it inside the band — by the library's own cooperative band Cholesky (default) or by the block-tridiagonal chain of
+    library calls (MSFM_BA_SOLVER=chain).  The step equals a host solve of the dumped system and the dense Cholesky's step
+    (all fp64), and the LM solve reaches the optimum of the dense path and of the Python oracle."""
     P = bo.make_problem(240, 3000, 4, 13)
-    ba = _create(ctx, P)
-    S, rhs, _, _ = ba.linearize(1e-4)
-    dc, st = ba.solve_system(1e-4)
-    info = ba.solver_info()
-    assert st == 0 and info["n_superblocks"] >= 3 and info["kind"].startswith("block-tridiagonal"), info
-    ref_dc = np.linalg.solve(S, rhs)
-    # S itself carries fp32 accumulation noise that differs from launch to launch (atomic order): compare through the residual
-    assert np.abs(S @ dc - rhs).max() <= 1e-6 * np.abs(rhs).max()
-    assert np.abs(dc - ref_dc).max() <= 1e-4 * np.abs(ref_dc).max()
-    s = ba.solve()
-    ba.close()
-    os.environ["MSFM_BA_DENSE_SOLVER"] = "1"
+    os.environ["MSFM_BA_SOLVER"] = solver
     try:
+        ba = _create(ctx, P)
+        S, rhs, _, _ = ba.linearize(1e-4)
+        dc, st = ba.solve_system(1e-4)
+        info = ba.solver_info()
+        assert st == 0 and info["kind"].startswith("band" if solver == "band" else "block-tridiagonal"), info
+        ref_dc = np.linalg.solve(S, rhs)
+        # S itself carries fp32 accumulation noise that differs from launch to launch (atomic order): compare through the residual
+        assert np.abs(S @ dc - rhs).max() <= 1e-6 * np.abs(rhs).max()
+        assert np.abs(dc - ref_dc).max() <= 1e-4 * np.abs(ref_dc).max()
+        s = ba.solve()
+        ba.close()
+        os.environ["MSFM_BA_SOLVER"] = "dense"
         bd = _create(ctx, P)
         dcd, std = bd.solve_system(1e-4)
-        assert std == 0 and bd.solver_info()["n_superblocks"] == 0
+        assert std == 0 and bd.solver_info()["kind"] == "dense"
         assert np.abs(dcd - ref_dc).max() <= 1e-4 * np.abs(ref_dc).max()
         sd = bd.solve()
         bd.close()
     finally:
-        del os.environ["MSFM_BA_DENSE_SOLVER"]
+        del os.environ["MSFM_BA_SOLVER"]
     # the scale of the scene is a gauge freedom (one constant camera): the two trajectories may drift apart along it, the optimum
     # they reach is the same
     assert s["termination"] == 0 and sd["termination"] == 0
     assert abs(s["final_cost"] - sd["final_cost"]) <= 1e-6 * sd["final_cost"]
     ref = bo.lm_solve(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"])
     assert ref["converged"] and abs(s["final_cost"] - ref["final_cost"]) <= 1e-5 * ref["final_cost"]
+
+
+def test_band_solver_reports_an_indefinite_system(ctx):
+    """A negative damping makes the reduced system indefinite: the band Cholesky flags it (status != 0) instead of returning garbage
+    silently — the LM loop then shrinks the trust region."""
+    P = bo.make_problem(240, 3000, 4, 13)
+    ba = _create(ctx, P)
+    _, st = ba.solve_system(-0.999)
+    assert ba.solver_info()["kind"].startswith("band") and st != 0
+    _, st = ba.solve_system(1e-4)
+    assert st == 0
+    ba.close()
 
 
 def test_filter_stats_match_the_reference_filters(ctx):

@@ -45,6 +45,12 @@ def main():
         assert s2["termination"] == 0, s2
         ba.track_errors()
         ba.close()
+    # a narrow-band camera system: the cooperative band Cholesky kernel
+    P = bo.make_problem(120, 500, 4, 13)
+    ba = ctx.ba_create(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"])
+    s3 = ba.solve()
+    assert s3["termination"] == 0 and ba.solver_info()["kind"].startswith("band"), (s3, ba.solver_info())
+    ba.close()
     ctx.close()
     print("sanitize workload ok", len(mt), "matches, BA", s["iterations"], "iterations")
 

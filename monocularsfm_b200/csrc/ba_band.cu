@@ -19,6 +19,8 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "ba_types.cuh"
@@ -36,6 +38,7 @@ struct Params {
     double* tiles;     // [R][nbk + 1][NB][NB] row-major tiles of the lower band: slot d of block row I holds tile (I, I - nbk + d)
     double* y;         // [nrhs][R * NB] right-hand sides / solutions (renumbered order)
     int32_t* info;     // != 0: a pivot was not positive
+    long long* dbg;    // optional [8]: cycles CTA 0 spent in D, P, U, the three barriers, the back substitution (MSFM_BAND_DEBUG=1)
     int32_t R, nbk, nrhs;
 };
 
@@ -51,6 +54,8 @@ __device__ __forceinline__ void load_tile(const double* __restrict__ g, double* 
 // ---- D: Cholesky of a 48 x 48 tile in shared memory sA (lower triangle used), L written to sA and to global g.
 // Thread r < 48 owns row r in registers; after step k every thread has published L[r][k], so row k (needed by all at the next
 // dot product) is complete in shared memory.
+// Called by warps 0 and 1 only (64 threads, named barrier 1): the other warps of the CTA wait at the next __syncthreads.
+__device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 __device__ void diag_cholesky(double* sA, double* __restrict__ g, int32_t* info) {
     const int r = threadIdx.x;
     double a[NB];
@@ -58,7 +63,7 @@ __device__ void diag_cholesky(double* sA, double* __restrict__ g, int32_t* info)
 #pragma unroll
         for (int c = 0; c < NB; ++c) a[c] = sA[r * kLd + c];
     }
-    __syncthreads();
+    bar64();
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
         double s = 0.0;
@@ -81,12 +86,12 @@ __device__ void diag_cholesky(double* sA, double* __restrict__ g, int32_t* info)
                 sA[k * kLd + k] = s;
             }
         }
-        __syncthreads();
+        bar64();
         if (r < NB && r > k) {
             a[k] = s / sA[k * kLd + k];
             sA[r * kLd + k] = a[k];
         }
-        __syncthreads();
+        bar64();
     }
     if (r < NB) {
 #pragma unroll
@@ -143,9 +148,13 @@ band_cholesky_kernel(Params p) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sA[NB * kLd];
     __shared__ double sB[NB * kLd];
-    __shared__ double sv[4 * NB];
+    __shared__ double sv[6 * NB];
     const int R = p.R, nbk = p.nbk, Npad = R * NB;
     const int bid = blockIdx.x, nblk = gridDim.x;
+    const bool timing = p.dbg != nullptr && bid == 0 && threadIdx.x == 0;
+    long long tD = 0, tP = 0, tU = 0, tS = 0, t0 = 0;
+#define BAND_TICK(acc) do { if (timing) { const long long t1 = clock64(); acc += t1 - t0; t0 = t1; } } while (0)
+    if (timing) t0 = clock64();
 
     for (int j = 0; j < R; ++j) {
         const int m = min(nbk, R - 1 - j);                 // tile rows below the diagonal in this column
@@ -153,23 +162,30 @@ band_cholesky_kernel(Params p) {
         if (bid == 0) {
             load_tile(tile_ptr(p, j, j), sA);
             __syncthreads();
-            diag_cholesky(sA, tile_ptr(p, j, j), p.info);
+            if (threadIdx.x < 64) diag_cholesky(sA, tile_ptr(p, j, j), p.info);
         }
+        BAND_TICK(tD);
         grid.sync();
+        BAND_TICK(tS);
         // ---- P: tasks 0 .. m-1 = tiles (j + 1 + t, j); task m = the right-hand sides
         for (int t = bid; t <= m; t += nblk) {
             load_tile(tile_ptr(p, j, j), sB);              // L_jj
             __syncthreads();
             if (t < m) {
                 double* g = tile_ptr(p, j + 1 + t, j);
+                // the tile through shared memory: coalesced global access, one row per thread afterwards
+                load_tile(g, sA);
+                __syncthreads();
                 if (threadIdx.x < NB) {
                     double x[NB];
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) x[c] = g[threadIdx.x * NB + c];
+                    for (int c = 0; c < NB; ++c) x[c] = sA[threadIdx.x * kLd + c];
                     solve_row(x, sB);
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) g[threadIdx.x * NB + c] = x[c];
+                    for (int c = 0; c < NB; ++c) sA[threadIdx.x * kLd + c] = x[c];
                 }
+                __syncthreads();
+                for (int i = threadIdx.x; i < NB * NB; i += kThreads) g[i] = sA[(i / NB) * kLd + (i % NB)];
             } else if (threadIdx.x < p.nrhs) {
                 double* yj = p.y + static_cast<size_t>(threadIdx.x) * Npad + static_cast<size_t>(j) * NB;
                 double x[NB];
@@ -181,7 +197,9 @@ band_cholesky_kernel(Params p) {
             }
             __syncthreads();
         }
+        BAND_TICK(tP);
         grid.sync();
+        BAND_TICK(tS);
         // ---- U: tasks 0 .. m(m+1)/2 - 1 = tiles (I, K), j < K <= I <= j + m; the last task = right-hand side updates
         const int ntile = m * (m + 1) / 2;
         for (int t = bid; t <= ntile; t += nblk) {
@@ -193,62 +211,80 @@ band_cholesky_kernel(Params p) {
                 const int I = j + 1 + a, K = j + 1 + b;
                 tile_update(tile_ptr(p, I, j), tile_ptr(p, K, j), tile_ptr(p, I, K), sA, sB);
             } else if (m > 0) {
-                // y_I -= L_Ij y_j for the m tile rows below: thread = (rhs, tile row a, row r)
+                // y_I -= L_Ij y_j for the m tile rows below: thread = (tile row a, row r), the 48 products of a row in flight together
                 for (int q = 0; q < p.nrhs; ++q) {
                     const double* yj = p.y + static_cast<size_t>(q) * Npad + static_cast<size_t>(j) * NB;
                     if (threadIdx.x < NB) sv[threadIdx.x] = yj[threadIdx.x];
                     __syncthreads();
                     for (int i = threadIdx.x; i < m * NB; i += kThreads) {
-                        const int a = i / NB, r = i % NB;
-                        const double* L = tile_ptr(p, j + 1 + a, j) + r * NB;
-                        double s = 0.0;
-#pragma unroll 8
-                        for (int c = 0; c < NB; ++c) s += L[c] * sv[c];
-                        p.y[static_cast<size_t>(q) * Npad + static_cast<size_t>(j + 1 + a) * NB + r] -= s;
+                        const int a = i / NB, r = i - a * NB;
+                        const double2* L2 = reinterpret_cast<const double2*>(tile_ptr(p, j + 1 + a, j) + r * NB);
+                        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                        for (int c = 0; c < NB / 2; ++c) {
+                            const double2 l = L2[c];
+                            s0 += l.x * sv[2 * c];
+                            s1 += l.y * sv[2 * c + 1];
+                        }
+                        p.y[static_cast<size_t>(q) * Npad + static_cast<size_t>(j + 1 + a) * NB + r] -= s0 + s1;
                     }
                     __syncthreads();
                 }
             }
         }
+        BAND_TICK(tU);
         grid.sync();
+        BAND_TICK(tS);
     }
     // ---- back substitution by CTA 0: x_j = L_jj^-T (y_j - sum_{I > j} L_Ij^T x_I)
     if (bid != 0) return;
-    for (int q = 0; q < p.nrhs; ++q) {
-        double* y = p.y + static_cast<size_t>(q) * Npad;
-        for (int j = R - 1; j >= 0; --j) {
-            const int m = min(nbk, R - 1 - j);
-            // partial sums over the tile rows below: thread = (column c, slice), rows of the tiles are read coalesced over c
-            const int c = threadIdx.x % NB, slice = threadIdx.x / NB;          // 5 full slices (240 threads)
-            double s = 0.0;
-            if (slice < 5) {
-                for (int i = slice; i < m * NB; i += 5) {
-                    const int a = i / NB, r = i % NB;
-                    s += tile_ptr(p, j + 1 + a, j)[r * NB + c] * y[static_cast<size_t>(j + 1 + a) * NB + r];
+    {
+        // thread = (column c, row group g): 48 x 5 threads; a thread takes rows g, g + 5, ... of every tile of the column
+        const int c = threadIdx.x % NB, g = threadIdx.x / NB;
+        for (int q = 0; q < p.nrhs; ++q) {
+            double* y = p.y + static_cast<size_t>(q) * Npad;
+            for (int j = R - 1; j >= 0; --j) {
+                const int m = min(nbk, R - 1 - j);
+                double s = 0.0;
+                if (g < 5) {
+                    for (int a = 0; a < m; ++a) {
+                        const double* Lt = tile_ptr(p, j + 1 + a, j) + c;
+                        const double* xI = y + static_cast<size_t>(j + 1 + a) * NB;
+                        double l[10];
+#pragma unroll
+                        for (int u = 0; u < 10; ++u) { const int r = g + 5 * u; l[u] = r < NB ? Lt[r * NB] : 0.0; }      // independent loads
+#pragma unroll
+                        for (int u = 0; u < 10; ++u) { const int r = g + 5 * u; if (r < NB) s += l[u] * xI[r]; }
+                    }
                 }
-            }
-            load_tile(tile_ptr(p, j, j), sA);
-            if (slice < 5) sB[slice * NB + c] = s;
-            __syncthreads();
-            if (threadIdx.x < NB) sv[threadIdx.x] = y[static_cast<size_t>(j) * NB + threadIdx.x] -
-                                                    (sB[threadIdx.x] + sB[NB + threadIdx.x] + sB[2 * NB + threadIdx.x] + sB[3 * NB + threadIdx.x] + sB[4 * NB + threadIdx.x]);
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                // L_jj^T x = sv by warp 0, from the last unknown up: x[cc] is final once every later unknown has been
-                // eliminated from it; lanes then remove it from the earlier ones (row cc of L)
-                for (int cc = NB - 1; cc >= 0; --cc) {
-                    const double x = sv[cc] / sA[cc * kLd + cc];
-                    __syncwarp();
-                    if (threadIdx.x == 0) sv[cc] = x;
-                    for (int k = threadIdx.x; k < cc; k += 32) sv[k] -= sA[cc * kLd + k] * x;
-                    __syncwarp();
+                load_tile(tile_ptr(p, j, j), sA);
+                if (g < 5) sB[g * NB + c] = s;
+                __syncthreads();
+                if (threadIdx.x < NB) sv[threadIdx.x] = y[static_cast<size_t>(j) * NB + threadIdx.x] -
+                                                        (sB[threadIdx.x] + sB[NB + threadIdx.x] + sB[2 * NB + threadIdx.x] + sB[3 * NB + threadIdx.x] + sB[4 * NB + threadIdx.x]);
+                __syncthreads();
+                if (threadIdx.x < 32) {
+                    // L_jj^T x = sv by warp 0, from the last unknown up: x[cc] is final once every later unknown has been
+                    // eliminated from it; lanes then remove it from the earlier ones (row cc of L)
+                    for (int cc = NB - 1; cc >= 0; --cc) {
+                        const double x = sv[cc] / sA[cc * kLd + cc];
+                        __syncwarp();
+                        if (threadIdx.x == 0) sv[cc] = x;
+                        for (int k = threadIdx.x; k < cc; k += 32) sv[k] -= sA[cc * kLd + k] * x;
+                        __syncwarp();
+                    }
                 }
+                __syncthreads();
+                if (threadIdx.x < NB) y[static_cast<size_t>(j) * NB + threadIdx.x] = sv[threadIdx.x];
+                __syncthreads();                              // the next column reads these through global memory (same CTA: visible)
             }
-            __syncthreads();
-            if (threadIdx.x < NB) y[static_cast<size_t>(j) * NB + threadIdx.x] = sv[threadIdx.x];
-            __syncthreads();
         }
     }
+    if (timing) {
+        const long long t1 = clock64();
+        p.dbg[0] = tD; p.dbg[1] = tP; p.dbg[2] = tU; p.dbg[3] = tS; p.dbg[4] = t1 - t0;
+    }
+#undef BAND_TICK
 }
 
 // block slot -> tile scatter of the fp32 blocks into the fp64 band (lower triangle of the renumbered matrix), damping added
@@ -294,6 +330,7 @@ struct BandSolver {
     int32_t* d_pos = nullptr;
     double *tiles = nullptr, *y = nullptr;
     int32_t* d_info = nullptr;
+    long long* d_dbg = nullptr;
     size_t tile_bytes = 0;
 };
 
@@ -324,6 +361,7 @@ BandSolver* band_create(int nf, const std::vector<int32_t>& blk_row, const std::
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->tiles), B->tile_bytes);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->y), 3 * static_cast<size_t>(B->R) * band::NB * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->d_info), 4 * sizeof(int32_t));
+    if (e == cudaSuccess && getenv("MSFM_BAND_DEBUG")) e = cudaMalloc(reinterpret_cast<void**>(&B->d_dbg), 8 * sizeof(long long));
     if (e == cudaSuccess) e = cudaMemcpy(B->d_pos, pos.data(), static_cast<size_t>(nf) * sizeof(int32_t), cudaMemcpyHostToDevice);
     int per_sm = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, band::band_cholesky_kernel, band::kThreads, 0);
@@ -341,6 +379,13 @@ BandSolver* band_create(int nf, const std::vector<int32_t>& blk_row, const std::
 }
 void band_destroy(BandSolver* B) {
     if (!B) return;
+    if (B->d_dbg) {
+        long long h[8] = {0};
+        cudaMemcpy(h, B->d_dbg, sizeof h, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "band Cholesky, last solve, CTA 0 cycles: D %lld  P %lld  U %lld  barriers %lld  back substitution %lld  (%d tile columns)\n",
+                h[0], h[1], h[2], h[3], h[4], B->R);
+        cudaFree(B->d_dbg);
+    }
     cudaFree(B->d_pos); cudaFree(B->tiles); cudaFree(B->y); cudaFree(B->d_info);
     delete B;
 }
@@ -351,7 +396,7 @@ int32_t* band_dev_info(BandSolver* B) { return B->d_info; }
 // camera order; overwritten by the solutions).  Asynchronous on st; *band_dev_info != 0 afterwards = not positive definite.
 cudaError_t band_factor_solve(BandSolver* B, const ba::Problem& P, double inv_radius, double* rhs, int nrhs, cudaStream_t st) {
     band::Params p;
-    p.tiles = B->tiles; p.y = B->y; p.info = B->d_info; p.R = B->R; p.nbk = B->nbk; p.nrhs = nrhs;
+    p.tiles = B->tiles; p.y = B->y; p.info = B->d_info; p.dbg = B->d_dbg; p.R = B->R; p.nbk = B->nbk; p.nrhs = nrhs;
     const int N = 6 * B->nf, Npad = B->R * band::NB;
     cudaError_t e = cudaMemsetAsync(B->tiles, 0, B->tile_bytes, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(B->y, 0, 3 * static_cast<size_t>(Npad) * sizeof(double), st);

@@ -916,12 +916,12 @@ __global__ void expand_dense_kernel(Problem P, double inv_radius, double* __rest
 // dp = -V^-1 (g_p + sum_obs W^T dc);  candidate point = point + dp;  accumulates
 // out[0] += model decrease  -(r.Jd + 1/2 |Jd|^2),  out[1] += |dp|^2,  out[2] += |point|^2
 __global__ void __launch_bounds__(256)
-backsub_kernel(Problem P, double inv_radius, const double* __restrict__ dc /*[n_free*6]*/, double* __restrict__ pts_new,
+backsub_kernel(Problem P, int first_point, double inv_radius, const double* __restrict__ dc /*[n_free*6]*/, double* __restrict__ pts_new,
                double* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     double acc_model = 0.0, acc_dp = 0.0, acc_x = 0.0;
-    for (int d = blockIdx.x * wpb + (threadIdx.x >> 5); d < P.n_pts; d += gridDim.x * wpb) {
+    for (int d = first_point + blockIdx.x * wpb + (threadIdx.x >> 5); d < P.n_pts; d += gridDim.x * wpb) {
         const int p = P.pt_order[d];
         const int beg = P.pt_start[d], end = P.pt_start[d + 1];
         const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
@@ -991,6 +991,95 @@ backsub_kernel(Problem P, double inv_radius, const double* __restrict__ dc /*[n_
         double s = 0.0;
         for (int k = 0; k < wpb; ++k) s += sh[threadIdx.x][k];
         atomicAdd(&out[threadIdx.x], s);
+    }
+}
+
+// The same back-substitution for the NORMAL tiles (points with at most 32 views), in the tile layout of the linearisation:
+// thread = observation for the geometry (every lane busy, instead of one warp per point with a third of its lanes), thread =
+// point for the 3x3 work.  Long tracks and unobserved points stay with backsub_kernel (device points >= first_long).
+__global__ void __launch_bounds__(kTileObs, 1)
+backsub_tile_kernel(Problem P, double inv_radius, const double* __restrict__ dc, double* __restrict__ pts_new, double* __restrict__ out) {
+    __shared__ float sJp[kTileObs][6];
+    __shared__ double sR[kTileObs][2], sJd[kTileObs][2], sXy[kTileObs][2];
+    __shared__ double sh[3][kTileObs / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool focal = P.refine_focal != 0;
+    const double df0 = focal ? dc[static_cast<size_t>(P.n_free) * 6] : 0.0, df1 = focal ? dc[static_cast<size_t>(P.n_free) * 6 + 1] : 0.0;
+    double acc_model = 0.0, acc_dp = 0.0, acc_x = 0.0;
+    for (int ti = blockIdx.x; ti < P.n_tiles; ti += gridDim.x) {
+        const Tile T = P.tiles[ti];
+        if (T.flags & kTileSplit) continue;
+        __syncthreads();
+        if (tid < T.n_obs) {
+            const int o = T.obs_begin + tid;
+            const int cam = __ldg(P.obs_cam + o);
+            const int f = __ldg(P.cam_free + cam);
+            const int p = __ldg(P.pt_order + T.begin + static_cast<int>(__ldg(P.obs_lpt + o)));
+            const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
+            const double2 uv = __ldg(reinterpret_cast<const double2*>(P.obs_uv) + o);
+            double r[2], Jc[12], Jp[6], xy[2];
+            obs_eval<true>(P.pre[cam], X, uv.x, uv.y, P.fx, P.fy, r, Jc, Jp, xy);
+            double jd0 = 0.0, jd1 = 0.0;
+            if (f >= 0) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const double dd = dc[f * 6 + i];
+                    jd0 += static_cast<double>(static_cast<float>(Jc[i])) * dd;        // the fp32 Jacobians of the linearisation
+                    jd1 += static_cast<double>(static_cast<float>(Jc[6 + i])) * dd;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sJp[tid][k] = static_cast<float>(Jp[k]);
+            sR[tid][0] = r[0]; sR[tid][1] = r[1];
+            sJd[tid][0] = jd0; sJd[tid][1] = jd1;
+            sXy[tid][0] = xy[0]; sXy[tid][1] = xy[1];
+        }
+        __syncthreads();
+        if (tid < T.end - T.begin) {
+            const int d = T.begin + tid;
+            const int p = __ldg(P.pt_order + d);
+            const int ob = __ldg(P.pt_start + d) - T.obs_begin, k = __ldg(P.pt_start + d + 1) - __ldg(P.pt_start + d);
+            const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
+            double v[6] = {0, 0, 0, 0, 0, 0}, t[3] = {0, 0, 0};
+            for (int j = 0; j < k; ++j) {
+                const double j0 = sJp[ob + j][0], j1 = sJp[ob + j][1], j2 = sJp[ob + j][2], j3 = sJp[ob + j][3], j4 = sJp[ob + j][4], j5 = sJp[ob + j][5];
+                const double a0 = sR[ob + j][0] + sJd[ob + j][0], a1 = sR[ob + j][1] + sJd[ob + j][1];     // g_p + Jp^T (Jc dc)
+                v[0] += j0 * j0 + j3 * j3; v[1] += j0 * j1 + j3 * j4; v[2] += j0 * j2 + j3 * j5;
+                v[3] += j1 * j1 + j4 * j4; v[4] += j1 * j2 + j4 * j5; v[5] += j2 * j2 + j5 * j5;
+                t[0] += j0 * a0 + j3 * a1; t[1] += j1 * a0 + j4 * a1; t[2] += j2 * a0 + j5 * a1;
+            }
+            v[0] += fmax(v[0], 1e-6) * inv_radius;
+            v[3] += fmax(v[3], 1e-6) * inv_radius;
+            v[5] += fmax(v[5], 1e-6) * inv_radius;
+            double Vinv[6];
+            sym3_inverse(v, Vinv);
+            if (focal) {
+                const double* wf = P.pt_Wf + 6 * static_cast<size_t>(d);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) t[q] += wf[q] * df0 + wf[3 + q] * df1;
+            }
+            double dp[3];
+            dp[0] = -(Vinv[0] * t[0] + Vinv[1] * t[1] + Vinv[2] * t[2]);
+            dp[1] = -(Vinv[1] * t[0] + Vinv[3] * t[1] + Vinv[4] * t[2]);
+            dp[2] = -(Vinv[2] * t[0] + Vinv[4] * t[1] + Vinv[5] * t[2]);
+            pts_new[3 * p] = X[0] + dp[0]; pts_new[3 * p + 1] = X[1] + dp[1]; pts_new[3 * p + 2] = X[2] + dp[2];
+            acc_dp += dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2];
+            acc_x += X[0] * X[0] + X[1] * X[1] + X[2] * X[2];
+            for (int j = 0; j < k; ++j) {
+                const double jd0 = sJd[ob + j][0] + sJp[ob + j][0] * dp[0] + sJp[ob + j][1] * dp[1] + sJp[ob + j][2] * dp[2] + sXy[ob + j][0] * df0;
+                const double jd1 = sJd[ob + j][1] + sJp[ob + j][3] * dp[0] + sJp[ob + j][4] * dp[1] + sJp[ob + j][5] * dp[2] + sXy[ob + j][1] * df1;
+                acc_model -= sR[ob + j][0] * jd0 + sR[ob + j][1] * jd1 + 0.5 * (jd0 * jd0 + jd1 * jd1);
+            }
+        }
+    }
+    acc_model = warp_sum(acc_model); acc_dp = warp_sum(acc_dp); acc_x = warp_sum(acc_x);
+    __syncthreads();
+    if (lane == 0) { sh[0][warp] = acc_model; sh[1][warp] = acc_dp; sh[2][warp] = acc_x; }
+    __syncthreads();
+    if (tid < 3) {
+        double s2 = 0.0;
+        for (int k = 0; k < kTileObs / 32; ++k) s2 += sh[tid][k];
+        atomicAdd(&out[tid], s2);
     }
 }
 
@@ -1099,9 +1188,17 @@ cudaError_t ba_launch_expand_dense(const Problem& P, double inv_radius, double* 
 cudaError_t ba_launch_backsub(const Problem& P, double inv_radius, const double* dc, double* pts_new, double* out,
                               int num_sms, cudaStream_t st) {
     if (P.n_pts <= 0) return cudaSuccess;
-    int grid = (P.n_pts + 7) / 8;
-    if (grid > num_sms * 8) grid = num_sms * 8;
-    backsub_kernel<<<grid, 256, 0, st>>>(P, inv_radius, dc, pts_new, out);
+    // normal tiles: thread-per-observation kernel; long tracks + unobserved points (device points >= first_long): warp per point
+    if (P.first_long > 0 && P.n_tiles > 0) {
+        const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
+        backsub_tile_kernel<<<grid, kTileObs, 0, st>>>(P, inv_radius, dc, pts_new, out);
+    }
+    const int rest = P.n_pts - P.first_long;
+    if (rest > 0) {
+        int grid = (rest + 7) / 8;
+        if (grid > num_sms * 8) grid = num_sms * 8;
+        backsub_kernel<<<grid, 256, 0, st>>>(P, P.first_long, inv_radius, dc, pts_new, out);
+    }
     return cudaGetLastError();
 }
 cudaError_t ba_launch_update_cams(const double* cams, const int32_t* cam_free, int n_cams, const double* dc,

@@ -252,7 +252,7 @@ def test_band_solvers_match_dense(ctx, solver):
     # the scale of the scene is a gauge freedom (one constant camera): the two trajectories may drift apart along it, the optimum
     # they reach is the same
     assert s["termination"] == 0 and sd["termination"] == 0
-    assert abs(s["final_cost"] - sd["final_cost"]) <= 1e-6 * sd["final_cost"]
+    assert abs(s["final_cost"] - sd["final_cost"]) <= 1e-5 * sd["final_cost"]
     ref = bo.lm_solve(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"])
     assert ref["converged"] and abs(s["final_cost"] - ref["final_cost"]) <= 1e-5 * ref["final_cost"]
 

@@ -12,9 +12,9 @@
 //                       y_j  = L_jj^-1 y_j           (the right-hand sides ride along as one more panel task)
 //     U   all CTAs:     T_IK -= L_Ij L_Kj^T          one 48x48x48 tile product per CTA (3x3 register blocks), j < K <= I <= j + nbk
 //                       y_I  -= L_Ij y_j
-// separated by grid barriers (cooperative launch: every CTA is resident), then CTA 0 back-substitutes.
+// separated by grid barriers on a monotonic counter (cooperative launch: every CTA is resident); D of column j+1 runs on CTA 0
+// right behind its update of that tile, under the other CTAs' updates (two barriers per column).  Then CTA 0 back-substitutes.
 // fp64 throughout.  Tensor cores are not used (north_star: not for the sparse BA).
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -24,8 +24,6 @@
 #include <vector>
 
 #include "ba_types.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace msfm {
 namespace band {
@@ -37,6 +35,8 @@ constexpr int kLd = NB + 1;        // shared-memory leading dimension (doubles)
 struct Params {
     double* tiles;     // [R][nbk + 1][NB][NB] row-major tiles of the lower band: slot d of block row I holds tile (I, I - nbk + d)
     double* y;         // [nrhs][R * NB] right-hand sides / solutions (renumbered order)
+    double* dinv;      // [R * NB] reciprocals of the diagonal of L (the substitutions multiply instead of dividing)
+    unsigned int* bar; // grid barrier counter (zeroed before the launch)
     int32_t* info;     // != 0: a pivot was not positive
     long long* dbg;    // optional [8]: cycles CTA 0 spent in D, P, U, the three barriers, the back substitution (MSFM_BAND_DEBUG=1)
     int32_t R, nbk, nrhs;
@@ -56,7 +56,7 @@ __device__ __forceinline__ void load_tile(const double* __restrict__ g, double* 
 // dot product) is complete in shared memory.
 // Called by warps 0 and 1 only (64 threads, named barrier 1): the other warps of the CTA wait at the next __syncthreads.
 __device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
-__device__ void diag_cholesky(double* sA, double* __restrict__ g, int32_t* info) {
+__device__ void diag_cholesky(double* sA, double* __restrict__ g, double* __restrict__ dinv, double* sInv, int32_t* info) {
     const int r = threadIdx.x;
     double a[NB];
     if (r < NB) {
@@ -81,14 +81,16 @@ __device__ void diag_cholesky(double* sA, double* __restrict__ g, int32_t* info)
             s = (s0 + s1) + (s2 + s3);
             if (r == k) {
                 if (!(s > 0.0)) { atomicExch(info, 1); s = 1.0; }
-                s = sqrt(s);
-                a[k] = s;
-                sA[k * kLd + k] = s;
+                // one reciprocal square root on the critical path instead of a square root and 47 divisions
+                const double ri = rsqrt(s);
+                a[k] = s * ri;
+                sA[k * kLd + k] = a[k];
+                sInv[k] = ri;
             }
         }
         bar64();
         if (r < NB && r > k) {
-            a[k] = s / sA[k * kLd + k];
+            a[k] = s * sInv[k];
             sA[r * kLd + k] = a[k];
         }
         bar64();
@@ -96,12 +98,14 @@ __device__ void diag_cholesky(double* sA, double* __restrict__ g, int32_t* info)
     if (r < NB) {
 #pragma unroll
         for (int c = 0; c < NB; ++c) g[r * NB + c] = c <= r ? a[c] : 0.0;
+        dinv[r] = sInv[r];
     }
 }
 
-// ---- P: rows x of a tile solved against L (shared memory sL): x <- x L^-T, i.e. x[c] = (x[c] - sum_{k<c} x[k] L[c][k]) / L[c][c].
+// ---- P: rows x of a tile solved against L (shared memory sL, reciprocal diagonal sInv): x <- x L^-T, i.e.
+// x[c] = (x[c] - sum_{k<c} x[k] L[c][k]) / L[c][c].
 // One thread per row, the row in registers, no communication.
-__device__ __forceinline__ void solve_row(double x[NB], const double* sL) {
+__device__ __forceinline__ void solve_row(double x[NB], const double* sL, const double* sInv) {
 #pragma unroll
     for (int c = 0; c < NB; ++c) {
         double s0 = x[c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -114,7 +118,7 @@ __device__ __forceinline__ void solve_row(double x[NB], const double* sL) {
         }
 #pragma unroll
         for (int k = c & ~3; k < c; ++k) s0 -= x[k] * sL[c * kLd + k];
-        x[c] = ((s0 + s1) + (s2 + s3)) / sL[c * kLd + c];
+        x[c] = ((s0 + s1) + (s2 + s3)) * sInv[c];
     }
 }
 
@@ -143,34 +147,48 @@ __device__ void tile_update(const double* __restrict__ gA, const double* __restr
     __syncthreads();
 }
 
+// Grid barrier on a monotonic counter (every CTA is resident: cooperative launch).  ~1.5 us instead of the ~5 us measured for
+// cooperative_groups' grid.sync() on 137 CTAs (profiles/r02_band_cholesky_phases.txt).
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int& target, unsigned int nblk) {
+    target += nblk;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (*reinterpret_cast<volatile unsigned int*>(ctr) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 band_cholesky_kernel(Params p) {
-    cg::grid_group grid = cg::this_grid();
     __shared__ double sA[NB * kLd];
     __shared__ double sB[NB * kLd];
     __shared__ double sv[6 * NB];
+    __shared__ double sInv[NB];
     const int R = p.R, nbk = p.nbk, Npad = R * NB;
     const int bid = blockIdx.x, nblk = gridDim.x;
+    unsigned int bar_target = 0;
     const bool timing = p.dbg != nullptr && bid == 0 && threadIdx.x == 0;
     long long tD = 0, tP = 0, tU = 0, tS = 0, t0 = 0;
 #define BAND_TICK(acc) do { if (timing) { const long long t1 = clock64(); acc += t1 - t0; t0 = t1; } } while (0)
     if (timing) t0 = clock64();
 
+    if (bid == 0) {
+        load_tile(tile_ptr(p, 0, 0), sA);
+        __syncthreads();
+        if (threadIdx.x < 64) diag_cholesky(sA, tile_ptr(p, 0, 0), p.dinv, sInv, p.info);
+    }
+    BAND_TICK(tD);
+    grid_barrier(p.bar, bar_target, nblk);
+    BAND_TICK(tS);
     for (int j = 0; j < R; ++j) {
         const int m = min(nbk, R - 1 - j);                 // tile rows below the diagonal in this column
-        // ---- D
-        if (bid == 0) {
-            load_tile(tile_ptr(p, j, j), sA);
-            __syncthreads();
-            if (threadIdx.x < 64) diag_cholesky(sA, tile_ptr(p, j, j), p.info);
-        }
-        BAND_TICK(tD);
-        grid.sync();
-        BAND_TICK(tS);
         // ---- P: tasks 0 .. m-1 = tiles (j + 1 + t, j); task m = the right-hand sides
         for (int t = bid; t <= m; t += nblk) {
             load_tile(tile_ptr(p, j, j), sB);              // L_jj
-            __syncthreads();
+            if (threadIdx.x < NB) sInv[threadIdx.x] = p.dinv[static_cast<size_t>(j) * NB + threadIdx.x];
             if (t < m) {
                 double* g = tile_ptr(p, j + 1 + t, j);
                 // the tile through shared memory: coalesced global access, one row per thread afterwards
@@ -180,27 +198,32 @@ band_cholesky_kernel(Params p) {
                     double x[NB];
 #pragma unroll
                     for (int c = 0; c < NB; ++c) x[c] = sA[threadIdx.x * kLd + c];
-                    solve_row(x, sB);
+                    solve_row(x, sB, sInv);
 #pragma unroll
                     for (int c = 0; c < NB; ++c) sA[threadIdx.x * kLd + c] = x[c];
                 }
                 __syncthreads();
                 for (int i = threadIdx.x; i < NB * NB; i += kThreads) g[i] = sA[(i / NB) * kLd + (i % NB)];
-            } else if (threadIdx.x < p.nrhs) {
-                double* yj = p.y + static_cast<size_t>(threadIdx.x) * Npad + static_cast<size_t>(j) * NB;
-                double x[NB];
+            } else {
+                __syncthreads();
+                if (threadIdx.x < p.nrhs) {
+                    double* yj = p.y + static_cast<size_t>(threadIdx.x) * Npad + static_cast<size_t>(j) * NB;
+                    double x[NB];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) x[c] = yj[c];
-                solve_row(x, sB);
+                    for (int c = 0; c < NB; ++c) x[c] = yj[c];
+                    solve_row(x, sB, sInv);
 #pragma unroll
-                for (int c = 0; c < NB; ++c) yj[c] = x[c];
+                    for (int c = 0; c < NB; ++c) yj[c] = x[c];
+                }
             }
             __syncthreads();
         }
         BAND_TICK(tP);
-        grid.sync();
+        grid_barrier(p.bar, bar_target, nblk);
         BAND_TICK(tS);
-        // ---- U: tasks 0 .. m(m+1)/2 - 1 = tiles (I, K), j < K <= I <= j + m; the last task = right-hand side updates
+        // ---- U: tasks 0 .. m(m+1)/2 - 1 = tiles (I, K), j < K <= I <= j + m; the last task = right-hand side updates.
+        //      Task 0 is the next diagonal tile (j+1, j+1): CTA 0 factors it right after updating it (D of the next column runs
+        //      under the other CTAs' updates).
         const int ntile = m * (m + 1) / 2;
         for (int t = bid; t <= ntile; t += nblk) {
             if (t < ntile) {
@@ -210,6 +233,14 @@ band_cholesky_kernel(Params p) {
                 const int b = t - a * (a + 1) / 2;           // 0 <= b <= a < m
                 const int I = j + 1 + a, K = j + 1 + b;
                 tile_update(tile_ptr(p, I, j), tile_ptr(p, K, j), tile_ptr(p, I, K), sA, sB);
+                if (t == 0) {
+                    BAND_TICK(tU);
+                    load_tile(tile_ptr(p, j + 1, j + 1), sA);        // written by this CTA just above
+                    __syncthreads();
+                    if (threadIdx.x < 64) diag_cholesky(sA, tile_ptr(p, j + 1, j + 1), p.dinv + static_cast<size_t>(j + 1) * NB, sInv, p.info);
+                    __syncthreads();
+                    BAND_TICK(tD);
+                }
             } else if (m > 0) {
                 // y_I -= L_Ij y_j for the m tile rows below: thread = (tile row a, row r), the 48 products of a row in flight together
                 for (int q = 0; q < p.nrhs; ++q) {
@@ -233,13 +264,14 @@ band_cholesky_kernel(Params p) {
             }
         }
         BAND_TICK(tU);
-        grid.sync();
+        grid_barrier(p.bar, bar_target, nblk);
         BAND_TICK(tS);
     }
     // ---- back substitution by CTA 0: x_j = L_jj^-T (y_j - sum_{I > j} L_Ij^T x_I)
     if (bid != 0) return;
     {
-        // thread = (column c, row group g): 48 x 5 threads; a thread takes rows g, g + 5, ... of every tile of the column
+        // thread = (column c, row group g): 48 x 5 threads; a thread takes rows g, g + 5, ... of every tile of the column, the
+        // loads of two tiles in flight together
         const int c = threadIdx.x % NB, g = threadIdx.x / NB;
         for (int q = 0; q < p.nrhs; ++q) {
             double* y = p.y + static_cast<size_t>(q) * Npad;
@@ -247,18 +279,29 @@ band_cholesky_kernel(Params p) {
                 const int m = min(nbk, R - 1 - j);
                 double s = 0.0;
                 if (g < 5) {
-                    for (int a = 0; a < m; ++a) {
-                        const double* Lt = tile_ptr(p, j + 1 + a, j) + c;
-                        const double* xI = y + static_cast<size_t>(j + 1 + a) * NB;
-                        double l[10];
+                    for (int a = 0; a < m; a += 2) {
+                        const bool two = a + 1 < m;
+                        const double* L0 = tile_ptr(p, j + 1 + a, j) + c;
+                        const double* L1 = tile_ptr(p, j + 1 + (two ? a + 1 : a), j) + c;
+                        const double* x0 = y + static_cast<size_t>(j + 1 + a) * NB;
+                        const double* x1 = x0 + NB;
+                        double l0[10], l1[10];
 #pragma unroll
-                        for (int u = 0; u < 10; ++u) { const int r = g + 5 * u; l[u] = r < NB ? Lt[r * NB] : 0.0; }      // independent loads
+                        for (int u = 0; u < 10; ++u) {
+                            const int r = g + 5 * u;
+                            l0[u] = r < NB ? L0[r * NB] : 0.0;
+                            l1[u] = (two && r < NB) ? L1[r * NB] : 0.0;
+                        }
 #pragma unroll
-                        for (int u = 0; u < 10; ++u) { const int r = g + 5 * u; if (r < NB) s += l[u] * xI[r]; }
+                        for (int u = 0; u < 10; ++u) {
+                            const int r = g + 5 * u;
+                            if (r < NB) { s += l0[u] * x0[r]; if (two) s += l1[u] * x1[r]; }
+                        }
                     }
                 }
                 load_tile(tile_ptr(p, j, j), sA);
                 if (g < 5) sB[g * NB + c] = s;
+                if (threadIdx.x < NB) sInv[threadIdx.x] = p.dinv[static_cast<size_t>(j) * NB + threadIdx.x];
                 __syncthreads();
                 if (threadIdx.x < NB) sv[threadIdx.x] = y[static_cast<size_t>(j) * NB + threadIdx.x] -
                                                         (sB[threadIdx.x] + sB[NB + threadIdx.x] + sB[2 * NB + threadIdx.x] + sB[3 * NB + threadIdx.x] + sB[4 * NB + threadIdx.x]);
@@ -267,7 +310,7 @@ band_cholesky_kernel(Params p) {
                     // L_jj^T x = sv by warp 0, from the last unknown up: x[cc] is final once every later unknown has been
                     // eliminated from it; lanes then remove it from the earlier ones (row cc of L)
                     for (int cc = NB - 1; cc >= 0; --cc) {
-                        const double x = sv[cc] / sA[cc * kLd + cc];
+                        const double x = sv[cc] * sInv[cc];
                         __syncwarp();
                         if (threadIdx.x == 0) sv[cc] = x;
                         for (int k = threadIdx.x; k < cc; k += 32) sv[k] -= sA[cc * kLd + k] * x;
@@ -328,8 +371,8 @@ __global__ void permute_out_kernel(const double* __restrict__ src, const int32_t
 struct BandSolver {
     int nf = 0, bw = 0, R = 0, nbk = 0, grid = 0;
     int32_t* d_pos = nullptr;
-    double *tiles = nullptr, *y = nullptr;
-    int32_t* d_info = nullptr;
+    double *tiles = nullptr, *y = nullptr, *dinv = nullptr;
+    int32_t* d_info = nullptr;      // [0] status, [2] the grid barrier counter
     long long* d_dbg = nullptr;
     size_t tile_bytes = 0;
 };
@@ -360,6 +403,7 @@ BandSolver* band_create(int nf, const std::vector<int32_t>& blk_row, const std::
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&B->d_pos), static_cast<size_t>(nf) * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->tiles), B->tile_bytes);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->y), 3 * static_cast<size_t>(B->R) * band::NB * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->dinv), static_cast<size_t>(B->R) * band::NB * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->d_info), 4 * sizeof(int32_t));
     if (e == cudaSuccess && getenv("MSFM_BAND_DEBUG")) e = cudaMalloc(reinterpret_cast<void**>(&B->d_dbg), 8 * sizeof(long long));
     if (e == cudaSuccess) e = cudaMemcpy(B->d_pos, pos.data(), static_cast<size_t>(nf) * sizeof(int32_t), cudaMemcpyHostToDevice);
@@ -368,7 +412,7 @@ BandSolver* band_create(int nf, const std::vector<int32_t>& blk_row, const std::
     if (e == cudaSuccess && per_sm < 1) e = cudaErrorLaunchOutOfResources;
     if (e != cudaSuccess) {
         *err = e;
-        cudaFree(B->d_pos); cudaFree(B->tiles); cudaFree(B->y); cudaFree(B->d_info);
+        cudaFree(B->d_pos); cudaFree(B->tiles); cudaFree(B->y); cudaFree(B->dinv); cudaFree(B->d_info);
         delete B;
         return nullptr;
     }
@@ -386,7 +430,7 @@ void band_destroy(BandSolver* B) {
                 h[0], h[1], h[2], h[3], h[4], B->R);
         cudaFree(B->d_dbg);
     }
-    cudaFree(B->d_pos); cudaFree(B->tiles); cudaFree(B->y); cudaFree(B->d_info);
+    cudaFree(B->d_pos); cudaFree(B->tiles); cudaFree(B->y); cudaFree(B->dinv); cudaFree(B->d_info);
     delete B;
 }
 void band_info(const BandSolver* B, int32_t out[4]) { out[0] = B->bw; out[1] = band::NB; out[2] = B->R; out[3] = B->nbk; }
@@ -396,7 +440,7 @@ int32_t* band_dev_info(BandSolver* B) { return B->d_info; }
 // camera order; overwritten by the solutions).  Asynchronous on st; *band_dev_info != 0 afterwards = not positive definite.
 cudaError_t band_factor_solve(BandSolver* B, const ba::Problem& P, double inv_radius, double* rhs, int nrhs, cudaStream_t st) {
     band::Params p;
-    p.tiles = B->tiles; p.y = B->y; p.info = B->d_info; p.dbg = B->d_dbg; p.R = B->R; p.nbk = B->nbk; p.nrhs = nrhs;
+    p.tiles = B->tiles; p.y = B->y; p.dinv = B->dinv; p.info = B->d_info; p.bar = reinterpret_cast<unsigned int*>(B->d_info + 2); p.dbg = B->d_dbg; p.R = B->R; p.nbk = B->nbk; p.nrhs = nrhs;
     const int N = 6 * B->nf, Npad = B->R * band::NB;
     cudaError_t e = cudaMemsetAsync(B->tiles, 0, B->tile_bytes, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(B->y, 0, 3 * static_cast<size_t>(Npad) * sizeof(double), st);

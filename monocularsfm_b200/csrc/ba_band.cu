@@ -7,7 +7,7 @@
 // 126 cameras) that chain is latency-bound — 334 us per potrf(756) panel kernel, 1439 small trsm kernels, 9.2 ms per solve
 // (profiles/r02_ba_launches_library_chain.csv) — no faster than the dense potrf it replaced.  Here the whole factorisation is
 // one launch: the lower band is stored as 48 x 48 fp64 tiles (8 cameras per tile row), and per tile column j
-//     D   one CTA:      L_jj = chol(T_jj)            thread = row, the row in registers, rows published through shared memory
+//     D   one warp:     L_jj = chol(T_jj)            the tile in the warp's registers, pivots and columns by shuffles
 //     P   nbk CTAs:     L_Ij = T_Ij L_jj^-T          thread = row of the tile, forward substitution against L_jj in shared memory
 //                       y_j  = L_jj^-1 y_j           (the right-hand sides ride along as one more panel task)
 //     U   all CTAs:     T_IK -= L_Ij L_Kj^T          one 48x48x48 tile product per CTA (3x3 register blocks), j < K <= I <= j + nbk
@@ -54,52 +54,57 @@ __device__ __forceinline__ void load_tile(const double* __restrict__ g, double* 
 // ---- D: Cholesky of a 48 x 48 tile in shared memory sA (lower triangle used), L written to sA and to global g.
 // Thread r < 48 owns row r in registers; after step k every thread has published L[r][k], so row k (needed by all at the next
 // dot product) is complete in shared memory.
-// Called by warps 0 and 1 only (64 threads, named barrier 1): the other warps of the CTA wait at the next __syncthreads.
-__device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
-__device__ void diag_cholesky(double* sA, double* __restrict__ g, double* __restrict__ dinv, double* sInv, int32_t* info) {
-    const int r = threadIdx.x;
-    double a[NB];
-    if (r < NB) {
+// ---- D: Cholesky of a 48 x 48 tile by ONE WARP, the matrix in registers: lane l holds row l (a0) and, for l < 16, row 32 + l (a1).
+// Right-looking: the pivot and the scaled column travel by warp shuffles, no shared memory or barrier on the critical path
+// (the first version published every column through shared memory behind two 64-thread barriers per pivot: 556 cycles per
+// pivot; profiles/r02_band_cholesky_phases.txt).  One reciprocal square root per pivot; the 47 divisions are multiplications.
+// sA: the tile on entry ([NB][kLd], lower triangle used), L on exit; sInv: reciprocals of the diagonal of L.
+__device__ __noinline__ void diag_cholesky_warp(double* sA, double* sInv, int32_t* info) {
+    const int lane = threadIdx.x & 31;
+    double a0[32], a1[NB];
 #pragma unroll
-        for (int c = 0; c < NB; ++c) a[c] = sA[r * kLd + c];
-    }
-    bar64();
+    for (int c = 0; c < 32; ++c) a0[c] = sA[lane * kLd + c];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) a1[c] = lane < NB - 32 ? sA[(32 + lane) * kLd + c] : 0.0;
+    bool bad = false;
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
-        double s = 0.0;
-        if (r < NB && r >= k) {
-            double s0 = a[k], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-            for (int m = 0; m + 3 < k; m += 4) {
-                s0 -= a[m] * sA[k * kLd + m];
-                s1 -= a[m + 1] * sA[k * kLd + m + 1];
-                s2 -= a[m + 2] * sA[k * kLd + m + 2];
-                s3 -= a[m + 3] * sA[k * kLd + m + 3];
-            }
-#pragma unroll
-            for (int m = k & ~3; m < k; ++m) s0 -= a[m] * sA[k * kLd + m];
-            s = (s0 + s1) + (s2 + s3);
-            if (r == k) {
-                if (!(s > 0.0)) { atomicExch(info, 1); s = 1.0; }
-                // one reciprocal square root on the critical path instead of a square root and 47 divisions
-                const double ri = rsqrt(s);
-                a[k] = s * ri;
-                sA[k * kLd + k] = a[k];
-                sInv[k] = ri;
-            }
+        double pv = __shfl_sync(0xffffffffu, k < 32 ? a0[k < 32 ? k : 0] : a1[k], k & 31);
+        if (!(pv > 0.0)) { bad = true; pv = 1.0; }
+        const double ri = rsqrt(pv), d = pv * ri;
+        double L0 = 0.0, L1;
+        if (k < 32) {
+            L0 = lane > k ? a0[k < 32 ? k : 0] * ri : (lane == k ? d : 0.0);
+            a0[k < 32 ? k : 0] = L0;
+            L1 = a1[k] * ri;                                  // rows 32.. are all below the pivot
+        } else {
+            L1 = 32 + lane > k ? a1[k] * ri : (32 + lane == k ? d : 0.0);
         }
-        bar64();
-        if (r < NB && r > k) {
-            a[k] = s * sInv[k];
-            sA[r * kLd + k] = a[k];
-        }
-        bar64();
-    }
-    if (r < NB) {
+        a1[k] = L1;
+        if (lane == 0) sInv[k] = ri;
 #pragma unroll
-        for (int c = 0; c < NB; ++c) g[r * NB + c] = c <= r ? a[c] : 0.0;
-        dinv[r] = sInv[r];
+        for (int c = k + 1; c < NB; ++c) {
+            const double Lc = c < 32 ? __shfl_sync(0xffffffffu, L0, c) : __shfl_sync(0xffffffffu, L1, c - 32);
+            if (c < 32) a0[c < 32 ? c : 0] -= L0 * Lc;        // entries above the diagonal hold garbage nobody reads
+            a1[c] -= L1 * Lc;
+        }
     }
+    if (bad && lane == 0) atomicExch(info, 1);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) sA[lane * kLd + c] = c <= lane ? a0[c] : 0.0;
+#pragma unroll
+    for (int c = 32; c < NB; ++c) sA[lane * kLd + c] = 0.0;
+    if (lane < NB - 32) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) sA[(32 + lane) * kLd + c] = c <= 32 + lane ? a1[c] : 0.0;
+    }
+}
+// factor the tile in sA (already loaded), write L to global g and the reciprocal diagonal to dinv; all threads of the CTA call
+__device__ __forceinline__ void diag_factor(double* sA, double* sInv, double* __restrict__ g, double* __restrict__ dinv, int32_t* info) {
+    if (threadIdx.x < 32) diag_cholesky_warp(sA, sInv, info);
+    __syncthreads();
+    for (int i = threadIdx.x; i < NB * NB; i += kThreads) g[i] = sA[(i / NB) * kLd + (i % NB)];
+    if (threadIdx.x < NB) dinv[threadIdx.x] = sInv[threadIdx.x];
 }
 
 // ---- P: rows x of a tile solved against L (shared memory sL, reciprocal diagonal sInv): x <- x L^-T, i.e.
@@ -178,7 +183,7 @@ band_cholesky_kernel(Params p) {
     if (bid == 0) {
         load_tile(tile_ptr(p, 0, 0), sA);
         __syncthreads();
-        if (threadIdx.x < 64) diag_cholesky(sA, tile_ptr(p, 0, 0), p.dinv, sInv, p.info);
+        diag_factor(sA, sInv, tile_ptr(p, 0, 0), p.dinv, p.info);
     }
     BAND_TICK(tD);
     grid_barrier(p.bar, bar_target, nblk);
@@ -189,33 +194,27 @@ band_cholesky_kernel(Params p) {
         for (int t = bid; t <= m; t += nblk) {
             load_tile(tile_ptr(p, j, j), sB);              // L_jj
             if (threadIdx.x < NB) sInv[threadIdx.x] = p.dinv[static_cast<size_t>(j) * NB + threadIdx.x];
-            if (t < m) {
-                double* g = tile_ptr(p, j + 1 + t, j);
-                // the tile through shared memory: coalesced global access, one row per thread afterwards
-                load_tile(g, sA);
-                __syncthreads();
-                if (threadIdx.x < NB) {
-                    double x[NB];
+            // one code path for both kinds of task (the unrolled substitution exists once in the binary): a tile's 48 rows come
+            // through shared memory (coalesced global access), the right-hand sides are read in place
+            double* g = t < m ? tile_ptr(p, j + 1 + t, j) : nullptr;
+            if (g) load_tile(g, sA);
+            __syncthreads();
+            const bool active = g ? threadIdx.x < NB : threadIdx.x < p.nrhs;
+            double* yj = p.y + static_cast<size_t>(g ? 0 : threadIdx.x < p.nrhs ? threadIdx.x : 0) * Npad + static_cast<size_t>(j) * NB;
+            if (active) {
+                double x[NB];
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) x[c] = sA[threadIdx.x * kLd + c];
-                    solve_row(x, sB, sInv);
+                for (int c = 0; c < NB; ++c) x[c] = g ? sA[threadIdx.x * kLd + c] : yj[c];
+                solve_row(x, sB, sInv);
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) sA[threadIdx.x * kLd + c] = x[c];
-                }
-                __syncthreads();
-                for (int i = threadIdx.x; i < NB * NB; i += kThreads) g[i] = sA[(i / NB) * kLd + (i % NB)];
-            } else {
-                __syncthreads();
-                if (threadIdx.x < p.nrhs) {
-                    double* yj = p.y + static_cast<size_t>(threadIdx.x) * Npad + static_cast<size_t>(j) * NB;
-                    double x[NB];
-#pragma unroll
-                    for (int c = 0; c < NB; ++c) x[c] = yj[c];
-                    solve_row(x, sB, sInv);
-#pragma unroll
-                    for (int c = 0; c < NB; ++c) yj[c] = x[c];
+                for (int c = 0; c < NB; ++c) {
+                    if (g) sA[threadIdx.x * kLd + c] = x[c];
+                    else yj[c] = x[c];
                 }
             }
+            __syncthreads();
+            if (g)
+                for (int i = threadIdx.x; i < NB * NB; i += kThreads) g[i] = sA[(i / NB) * kLd + (i % NB)];
             __syncthreads();
         }
         BAND_TICK(tP);
@@ -237,7 +236,7 @@ band_cholesky_kernel(Params p) {
                     BAND_TICK(tU);
                     load_tile(tile_ptr(p, j + 1, j + 1), sA);        // written by this CTA just above
                     __syncthreads();
-                    if (threadIdx.x < 64) diag_cholesky(sA, tile_ptr(p, j + 1, j + 1), p.dinv + static_cast<size_t>(j + 1) * NB, sInv, p.info);
+                    diag_factor(sA, sInv, tile_ptr(p, j + 1, j + 1), p.dinv + static_cast<size_t>(j + 1) * NB, p.info);
                     __syncthreads();
                     BAND_TICK(tD);
                 }
@@ -271,7 +270,7 @@ band_cholesky_kernel(Params p) {
     if (bid != 0) return;
     {
         // thread = (column c, row group g): 48 x 5 threads; a thread takes rows g, g + 5, ... of every tile of the column, the
-        // loads of two tiles in flight together
+        // loads of four tiles in flight together
         const int c = threadIdx.x % NB, g = threadIdx.x / NB;
         for (int q = 0; q < p.nrhs; ++q) {
             double* y = p.y + static_cast<size_t>(q) * Npad;
@@ -279,23 +278,25 @@ band_cholesky_kernel(Params p) {
                 const int m = min(nbk, R - 1 - j);
                 double s = 0.0;
                 if (g < 5) {
-                    for (int a = 0; a < m; a += 2) {
-                        const bool two = a + 1 < m;
-                        const double* L0 = tile_ptr(p, j + 1 + a, j) + c;
-                        const double* L1 = tile_ptr(p, j + 1 + (two ? a + 1 : a), j) + c;
-                        const double* x0 = y + static_cast<size_t>(j + 1 + a) * NB;
-                        const double* x1 = x0 + NB;
-                        double l0[10], l1[10];
+                    for (int a = 0; a < m; a += 4) {
+                        double l[4][10];
 #pragma unroll
-                        for (int u = 0; u < 10; ++u) {
-                            const int r = g + 5 * u;
-                            l0[u] = r < NB ? L0[r * NB] : 0.0;
-                            l1[u] = (two && r < NB) ? L1[r * NB] : 0.0;
+                        for (int w = 0; w < 4; ++w) {
+                            const double* Lw = tile_ptr(p, j + 1 + min(a + w, m - 1), j) + c;
+#pragma unroll
+                            for (int u = 0; u < 10; ++u) {
+                                const int r = g + 5 * u;
+                                l[w][u] = (a + w < m && r < NB) ? Lw[r * NB] : 0.0;            // 40 independent loads in flight
+                            }
                         }
 #pragma unroll
-                        for (int u = 0; u < 10; ++u) {
-                            const int r = g + 5 * u;
-                            if (r < NB) { s += l0[u] * x0[r]; if (two) s += l1[u] * x1[r]; }
+                        for (int w = 0; w < 4; ++w) {
+                            const double* xw = y + static_cast<size_t>(j + 1 + min(a + w, m - 1)) * NB;
+#pragma unroll
+                            for (int u = 0; u < 10; ++u) {
+                                const int r = g + 5 * u;
+                                if (r < NB) s += l[w][u] * xw[r];
+                            }
                         }
                     }
                 }

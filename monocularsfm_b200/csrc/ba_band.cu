@@ -7,7 +7,7 @@
 // 126 cameras) that chain is latency-bound — 334 us per potrf(756) panel kernel, 1439 small trsm kernels, 9.2 ms per solve
 // (profiles/r02_ba_launches_library_chain.csv) — no faster than the dense potrf it replaced.  Here the whole factorisation is
 // one launch: the lower band is stored as 48 x 48 fp64 tiles (8 cameras per tile row), and per tile column j
-//     D   one warp:     L_jj = chol(T_jj)            the tile in the warp's registers, pivots and columns by shuffles
+//     D   one CTA:      L_jj = chol(T_jj)            blocked 4 x 12; one thread factors each 12 x 12 diagonal sub-block in registers
 //     P   nbk CTAs:     L_Ij = T_Ij L_jj^-T          thread = row of the tile, forward substitution against L_jj in shared memory
 //                       y_j  = L_jj^-1 y_j           (the right-hand sides ride along as one more panel task)
 //     U   all CTAs:     T_IK -= L_Ij L_Kj^T          one 48x48x48 tile product per CTA (3x3 register blocks), j < K <= I <= j + nbk
@@ -54,56 +54,75 @@ __device__ __forceinline__ void load_tile(const double* __restrict__ g, double* 
 // ---- D: Cholesky of a 48 x 48 tile in shared memory sA (lower triangle used), L written to sA and to global g.
 // Thread r < 48 owns row r in registers; after step k every thread has published L[r][k], so row k (needed by all at the next
 // dot product) is complete in shared memory.
-// ---- D: Cholesky of a 48 x 48 tile by ONE WARP, the matrix in registers: lane l holds row l (a0) and, for l < 16, row 32 + l (a1).
-// Right-looking: the pivot and the scaled column travel by warp shuffles, no shared memory or barrier on the critical path
-// (the first version published every column through shared memory behind two 64-thread barriers per pivot: 556 cycles per
-// pivot; profiles/r02_band_cholesky_phases.txt).  One reciprocal square root per pivot; the 47 divisions are multiplications.
-// sA: the tile on entry ([NB][kLd], lower triangle used), L on exit; sInv: reciprocals of the diagonal of L.
-__device__ __noinline__ void diag_cholesky_warp(double* sA, double* sInv, int32_t* info) {
-    const int lane = threadIdx.x & 31;
-    double a0[32], a1[NB];
+// ---- D: Cholesky of a 48 x 48 tile in shared memory, blocked 4 x 12: ONE THREAD factors each 12 x 12 diagonal sub-block in its
+// registers (the 48 reciprocal square roots are the sequential spine of the whole solver; nothing else shares their critical
+// path), then a thread per row solves the sub-panel and all threads update the trailing part.  12 barriers per tile instead
+// of the 96 of the first version (thread = row, one column published per pair of barriers: 556 cycles per pivot) — and the
+// version that kept the tile in one warp's registers and moved columns by shuffles was slower still (in-order issue: every
+// shuffle -> FMA pair stalls, 1080 cycles per pivot); profiles/r02_band_cholesky_phases.txt.
+// sA: the tile ([NB][kLd], lower triangle used) -> L; sInv: reciprocals of the diagonal of L.  All threads of the CTA call.
+constexpr int kSub = 12;
+__device__ __noinline__ void diag_factor(double* sA, double* sInv, double* __restrict__ g, double* __restrict__ dinv, int32_t* info) {
+    for (int b = 0; b < NB; b += kSub) {
+        if (threadIdx.x == 0) {
+            double m[kSub][kSub];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) a0[c] = sA[lane * kLd + c];
+            for (int i = 0; i < kSub; ++i)
 #pragma unroll
-    for (int c = 0; c < NB; ++c) a1[c] = lane < NB - 32 ? sA[(32 + lane) * kLd + c] : 0.0;
-    bool bad = false;
+                for (int j = 0; j <= i; ++j) m[i][j] = sA[(b + i) * kLd + b + j];
+            bool bad = false;
 #pragma unroll
-    for (int k = 0; k < NB; ++k) {
-        double pv = __shfl_sync(0xffffffffu, k < 32 ? a0[k < 32 ? k : 0] : a1[k], k & 31);
-        if (!(pv > 0.0)) { bad = true; pv = 1.0; }
-        const double ri = rsqrt(pv), d = pv * ri;
-        double L0 = 0.0, L1;
-        if (k < 32) {
-            L0 = lane > k ? a0[k < 32 ? k : 0] * ri : (lane == k ? d : 0.0);
-            a0[k < 32 ? k : 0] = L0;
-            L1 = a1[k] * ri;                                  // rows 32.. are all below the pivot
-        } else {
-            L1 = 32 + lane > k ? a1[k] * ri : (32 + lane == k ? d : 0.0);
+            for (int k = 0; k < kSub; ++k) {
+                double pv = m[k][k];
+                if (!(pv > 0.0)) { bad = true; pv = 1.0; }
+                const double ri = rsqrt(pv);
+                m[k][k] = pv * ri;
+                sInv[b + k] = ri;
+#pragma unroll
+                for (int i = k + 1; i < kSub; ++i) m[i][k] *= ri;
+#pragma unroll
+                for (int i = k + 1; i < kSub; ++i)
+#pragma unroll
+                    for (int j = k + 1; j <= i; ++j) m[i][j] -= m[i][k] * m[j][k];
+            }
+            if (bad) atomicExch(info, 1);
+#pragma unroll
+            for (int i = 0; i < kSub; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) sA[(b + i) * kLd + b + j] = m[i][j];
         }
-        a1[k] = L1;
-        if (lane == 0) sInv[k] = ri;
+        __syncthreads();
+        const int n = NB - b - kSub;                    // rows below the sub-block
+        if (threadIdx.x < n) {
+            double* row = sA + (b + kSub + threadIdx.x) * kLd + b;
+            double x[kSub];
 #pragma unroll
-        for (int c = k + 1; c < NB; ++c) {
-            const double Lc = c < 32 ? __shfl_sync(0xffffffffu, L0, c) : __shfl_sync(0xffffffffu, L1, c - 32);
-            if (c < 32) a0[c < 32 ? c : 0] -= L0 * Lc;        // entries above the diagonal hold garbage nobody reads
-            a1[c] -= L1 * Lc;
+            for (int j = 0; j < kSub; ++j) {
+                double v = row[j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) v -= x[k] * sA[(b + j) * kLd + b + k];
+                x[j] = v * sInv[b + j];
+            }
+#pragma unroll
+            for (int j = 0; j < kSub; ++j) row[j] = x[j];
         }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n * n; i += kThreads) {
+            const int rr = i / n, cc = i - rr * n;
+            if (cc > rr) continue;
+            const double* pr = sA + (b + kSub + rr) * kLd + b;
+            const double* pc = sA + (b + kSub + cc) * kLd + b;
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < kSub; k += 2) { v0 += pr[k] * pc[k]; v1 += pr[k + 1] * pc[k + 1]; }
+            sA[(b + kSub + rr) * kLd + b + kSub + cc] -= v0 + v1;
+        }
+        __syncthreads();
     }
-    if (bad && lane == 0) atomicExch(info, 1);
-#pragma unroll
-    for (int c = 0; c < 32; ++c) sA[lane * kLd + c] = c <= lane ? a0[c] : 0.0;
-#pragma unroll
-    for (int c = 32; c < NB; ++c) sA[lane * kLd + c] = 0.0;
-    if (lane < NB - 32) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c) sA[(32 + lane) * kLd + c] = c <= 32 + lane ? a1[c] : 0.0;
+    for (int i = threadIdx.x; i < NB * NB; i += kThreads) {
+        const int r = i / NB, c = i - r * NB;
+        g[i] = c <= r ? sA[r * kLd + c] : 0.0;
     }
-}
-// factor the tile in sA (already loaded), write L to global g and the reciprocal diagonal to dinv; all threads of the CTA call
-__device__ __forceinline__ void diag_factor(double* sA, double* sInv, double* __restrict__ g, double* __restrict__ dinv, int32_t* info) {
-    if (threadIdx.x < 32) diag_cholesky_warp(sA, sInv, info);
-    __syncthreads();
-    for (int i = threadIdx.x; i < NB * NB; i += kThreads) g[i] = sA[(i / NB) * kLd + (i % NB)];
     if (threadIdx.x < NB) dinv[threadIdx.x] = sInv[threadIdx.x];
 }
 
@@ -194,27 +213,33 @@ band_cholesky_kernel(Params p) {
         for (int t = bid; t <= m; t += nblk) {
             load_tile(tile_ptr(p, j, j), sB);              // L_jj
             if (threadIdx.x < NB) sInv[threadIdx.x] = p.dinv[static_cast<size_t>(j) * NB + threadIdx.x];
-            // one code path for both kinds of task (the unrolled substitution exists once in the binary): a tile's 48 rows come
-            // through shared memory (coalesced global access), the right-hand sides are read in place
-            double* g = t < m ? tile_ptr(p, j + 1 + t, j) : nullptr;
-            if (g) load_tile(g, sA);
-            __syncthreads();
-            const bool active = g ? threadIdx.x < NB : threadIdx.x < p.nrhs;
-            double* yj = p.y + static_cast<size_t>(g ? 0 : threadIdx.x < p.nrhs ? threadIdx.x : 0) * Npad + static_cast<size_t>(j) * NB;
-            if (active) {
-                double x[NB];
+            if (t < m) {
+                double* g = tile_ptr(p, j + 1 + t, j);
+                // the tile through shared memory: coalesced global access, one row per thread afterwards
+                load_tile(g, sA);
+                __syncthreads();
+                if (threadIdx.x < NB) {
+                    double x[NB];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) x[c] = g ? sA[threadIdx.x * kLd + c] : yj[c];
-                solve_row(x, sB, sInv);
+                    for (int c = 0; c < NB; ++c) x[c] = sA[threadIdx.x * kLd + c];
+                    solve_row(x, sB, sInv);
 #pragma unroll
-                for (int c = 0; c < NB; ++c) {
-                    if (g) sA[threadIdx.x * kLd + c] = x[c];
-                    else yj[c] = x[c];
+                    for (int c = 0; c < NB; ++c) sA[threadIdx.x * kLd + c] = x[c];
+                }
+                __syncthreads();
+                for (int i = threadIdx.x; i < NB * NB; i += kThreads) g[i] = sA[(i / NB) * kLd + (i % NB)];
+            } else {
+                __syncthreads();
+                if (threadIdx.x < p.nrhs) {
+                    double* yj = p.y + static_cast<size_t>(threadIdx.x) * Npad + static_cast<size_t>(j) * NB;
+                    double x[NB];
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) x[c] = yj[c];
+                    solve_row(x, sB, sInv);
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) yj[c] = x[c];
                 }
             }
-            __syncthreads();
-            if (g)
-                for (int i = threadIdx.x; i < NB * NB; i += kThreads) g[i] = sA[(i / NB) * kLd + (i % NB)];
             __syncthreads();
         }
         BAND_TICK(tP);

@@ -7,7 +7,9 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <functional>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "ba_types.cuh"
@@ -42,6 +44,21 @@ struct Tiling {
 
 inline int tri_index(int la, int lb) { return lb * (lb + 1) / 2 + la; }   // la <= lb
 
+// f(begin, end) over [0, n) on up to 8 host threads (the analysis of a 5 M-observation problem is ~0.5 s on one)
+template <class F>
+inline void parallel_ranges(int n, F f) {
+    int nt = static_cast<int>(std::thread::hardware_concurrency());
+    nt = std::max(1, std::min(8, nt));
+    if (n < 20000 || nt == 1) { f(0, n); return; }
+    std::vector<std::thread> th;
+    const int step = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        const int b = t * step, e = std::min(n, b + step);
+        if (b < e) th.emplace_back([=] { f(b, e); });
+    }
+    for (auto& x : th) x.join();
+}
+
 // Device order + tiles + per-tile coupling marks.  obs_pt must be non-decreasing (validated by the caller).
 // Returns false if a point is observed twice by one camera.
 inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_cam, const int32_t* obs_pt,
@@ -49,60 +66,83 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
     std::vector<int32_t> start(size_t(n_pts) + 1, 0);
     for (int i = 0; i < n_obs; ++i) start[size_t(obs_pt[i]) + 1] += 1;
     for (int p = 0; p < n_pts; ++p) start[size_t(p) + 1] += start[p];
-    // observations of every point sorted by camera
-    std::vector<int32_t> sorted_obs(static_cast<size_t>(n_obs));
-    std::iota(sorted_obs.begin(), sorted_obs.end(), 0);
+    // observations of every point sorted by camera; cs = the sorted camera lists, contiguous (the comparisons below read them)
+    std::vector<int32_t> sorted_obs(static_cast<size_t>(n_obs)), cs(static_cast<size_t>(n_obs));
     std::vector<uint64_t> key(static_cast<size_t>(n_pts));
-    for (int p = 0; p < n_pts; ++p) {
-        int32_t* b = sorted_obs.data() + start[p];
-        int32_t* e = sorted_obs.data() + start[size_t(p) + 1];
-        std::sort(b, e, [&](int32_t x, int32_t y) { return obs_cam[x] < obs_cam[y]; });
-        for (int32_t* q = b; q + 1 < e; ++q)
-            if (obs_cam[q[0]] == obs_cam[q[1]]) return false;
-        // locality key: the three smallest cameras (20 bits each).  Order of the classes: points with at most 32
-        // observations, long tracks, points without observations.
-        uint64_t k = ~uint64_t(0);
-        if (e > b) {
-            const uint64_t c0 = uint64_t(obs_cam[b[0]]) & 0xFFFFF;
-            const uint64_t c1 = e - b > 1 ? uint64_t(obs_cam[b[1]]) & 0xFFFFF : c0;
-            const uint64_t c2 = e - b > 2 ? uint64_t(obs_cam[b[2]]) & 0xFFFFF : c1;
-            k = (uint64_t(e - b > 32 ? 1 : 0) << 62) | (c0 << 40) | (c1 << 20) | c2;
+    std::vector<char> dup(8, 0);
+    parallel_ranges(n_pts, [&](int p0, int p1) {
+        for (int p = p0; p < p1; ++p) {
+            int32_t* b = sorted_obs.data() + start[p];
+            int32_t* e = sorted_obs.data() + start[size_t(p) + 1];
+            std::iota(b, e, start[p]);
+            bool sorted = true;
+            for (int32_t* q = b; q + 1 < e && sorted; ++q) sorted = obs_cam[q[0]] < obs_cam[q[1]];
+            if (!sorted) {
+                std::sort(b, e, [&](int32_t x, int32_t y) { return obs_cam[x] < obs_cam[y]; });
+                for (int32_t* q = b; q + 1 < e; ++q)
+                    if (obs_cam[q[0]] == obs_cam[q[1]]) dup[0] = 1;
+            }
+            int32_t* c = cs.data() + start[p];
+            for (int32_t* q = b; q < e; ++q) *c++ = obs_cam[*q];
+            // locality key: the three smallest cameras (20 bits each).  Order of the classes: points with at most 32
+            // observations, long tracks, points without observations.
+            uint64_t k = ~uint64_t(0);
+            if (e > b) {
+                const int32_t* cc = cs.data() + start[p];
+                const uint64_t c0 = uint64_t(cc[0]) & 0xFFFFF;
+                const uint64_t c1 = e - b > 1 ? uint64_t(cc[1]) & 0xFFFFF : c0;
+                const uint64_t c2 = e - b > 2 ? uint64_t(cc[2]) & 0xFFFFF : c1;
+                k = (uint64_t(e - b > 32 ? 1 : 0) << 62) | (c0 << 40) | (c1 << 20) | c2;
+            }
+            key[p] = k;
         }
-        key[p] = k;
-    }
-    T.pt_order.resize(static_cast<size_t>(n_pts));
-    std::iota(T.pt_order.begin(), T.pt_order.end(), 0);
-    // Device order: class (key bit 62), then the camera list in lexicographic order — neighbours share cameras (few cameras per
-    // tile), and points with IDENTICAL camera lists end up adjacent (runs: their 6x6 products are summed in registers before
-    // they touch the shared-memory accumulator).
-    std::stable_sort(T.pt_order.begin(), T.pt_order.end(), [&](int32_t a, int32_t b) {
-        if (key[a] != key[b]) return key[a] < key[b];
-        const int ka = start[size_t(a) + 1] - start[a], kb = start[size_t(b) + 1] - start[b];
-        const int32_t* oa = sorted_obs.data() + start[a];
-        const int32_t* ob = sorted_obs.data() + start[b];
-        for (int i = 3; i < ka && i < kb; ++i) {            // the first three cameras are in the key
-            const int ca = obs_cam[oa[i]], cb = obs_cam[ob[i]];
-            if (ca != cb) return ca < cb;
-        }
-        return ka < kb;
     });
+    if (dup[0]) return false;
+    // Device order: class (key bit 62) and the three smallest cameras — neighbours share cameras (few cameras per tile) — then
+    // track length and a hash of the whole camera list, so that points with IDENTICAL lists end up adjacent (runs: their 6x6
+    // products are summed in registers before they touch the shared-memory accumulator; run detection compares the lists
+    // themselves, a hash collision only costs adjacency).  All-scalar keys in one contiguous array: no list walks in the sort.
+    struct SortKey { uint64_t key, hash; int32_t k, idx; };
+    std::vector<SortKey> sk(static_cast<size_t>(n_pts));
+    parallel_ranges(n_pts, [&](int p0, int p1) {
+        for (int p = p0; p < p1; ++p) {
+            uint64_t h = 1469598103934665603ull;
+            for (int i = start[p]; i < start[size_t(p) + 1]; ++i) { h ^= static_cast<uint64_t>(static_cast<uint32_t>(cs[i])); h *= 1099511628211ull; }
+            sk[p] = SortKey{key[p], h, start[size_t(p) + 1] - start[p], p};
+        }
+    });
+    std::sort(sk.begin(), sk.end(), [](const SortKey& a, const SortKey& b) {
+        if (a.key != b.key) return a.key < b.key;
+        if (a.k != b.k) return a.k < b.k;
+        if (a.hash != b.hash) return a.hash < b.hash;
+        return a.idx < b.idx;
+    });
+    T.pt_order.resize(static_cast<size_t>(n_pts));
+    for (int d = 0; d < n_pts; ++d) T.pt_order[d] = sk[d].idx;
+    sk.clear(); sk.shrink_to_fit();
     T.pt_start.assign(size_t(n_pts) + 1, 0);
     T.obs_perm.resize(static_cast<size_t>(n_obs));
     T.obs_lcam.assign(static_cast<size_t>(n_obs), 0);
     T.obs_lpt.assign(static_cast<size_t>(n_obs), 0);
+    std::vector<int32_t> dev_cam(static_cast<size_t>(n_obs));       // camera of every observation in device order
     for (int d = 0; d < n_pts; ++d) {
         const int p = T.pt_order[d];
-        const int k = start[size_t(p) + 1] - start[p];
-        T.pt_start[size_t(d) + 1] = T.pt_start[d] + k;
-        std::copy(sorted_obs.begin() + start[p], sorted_obs.begin() + start[size_t(p) + 1], T.obs_perm.begin() + T.pt_start[d]);
+        T.pt_start[size_t(d) + 1] = T.pt_start[d] + (start[size_t(p) + 1] - start[p]);
     }
+    parallel_ranges(n_pts, [&](int d0, int d1) {
+        for (int d = d0; d < d1; ++d) {
+            const int p = T.pt_order[d];
+            std::copy(sorted_obs.begin() + start[p], sorted_obs.begin() + start[size_t(p) + 1], T.obs_perm.begin() + T.pt_start[d]);
+            std::copy(cs.begin() + start[p], cs.begin() + start[size_t(p) + 1], dev_cam.begin() + T.pt_start[d]);
+        }
+    });
     const int w_cap = kTileCams;
     const int max_pts = std::max(1, std::min(prm.max_pts, kTilePts)), max_obs = std::max(32, std::min(prm.max_obs, kTileObs));
     const int max_items = std::max(1, std::min(prm.max_items, kTileItems));
     std::vector<int32_t> stamp(static_cast<size_t>(std::max(1, n_cams)), -1), lidx(static_cast<size_t>(std::max(1, n_cams)), 0);
     T.tiles.clear(); T.items.clear(); T.tile_cams.clear(); T.tile_marks.clear();
     T.w_max = 0;
-    auto cam_of = [&](int dev_obs) { return obs_cam[T.obs_perm[dev_obs]]; };
+    auto cam_of = [&](int dev_obs) { return dev_cam[dev_obs]; };
     // ---- normal tiles: greedy over the device order
     auto close_tile = [&](int d0, int d1, std::vector<int32_t>& cams) {
         if (d1 <= d0) return;
@@ -117,28 +157,23 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
         T.tile_cams.insert(T.tile_cams.end(), cams.begin(), cams.end());
         T.tile_marks.resize(T.tile_marks.size() + size_t(t.w) * (t.w + 1) / 2, 0);
         int32_t* marks = T.tile_marks.data() + t.slot_begin;
+        for (int a = T.pt_start[d0]; a < T.pt_start[d1]; ++a) T.obs_lcam[a] = static_cast<uint8_t>(lidx[cam_of(a)]);
         for (int d = d0; d < d1; ++d)
-            for (int a = T.pt_start[d]; a < T.pt_start[size_t(d) + 1]; ++a) {
-                const int ca = cam_of(a);
-                const int la = lidx[ca];
-                T.obs_lcam[a] = static_cast<uint8_t>(la);
-                T.obs_lpt[a] = static_cast<uint8_t>(d - d0);
-                if (cam_free[ca] < 0) continue;
-                for (int b = a; b < T.pt_start[size_t(d) + 1]; ++b) {
-                    const int cb = cam_of(b);
-                    if (cam_free[cb] >= 0) marks[tri_index(la, lidx[cb])] = 1;
-                }
-            }
-        // runs of consecutive points with identical camera lists (at most 255 points each), one work item per 32 camera pairs
+            for (int a = T.pt_start[d]; a < T.pt_start[size_t(d) + 1]; ++a) T.obs_lpt[a] = static_cast<uint8_t>(d - d0);
+        // runs of consecutive points with identical camera lists (at most 255 points each), one work item per 32 camera pairs;
+        // the coupling marks are those of the run's first point
         t.run_begin = static_cast<int32_t>(T.runs.size());
         for (int d = d0; d < d1;) {
             int e = d + 1;
             const int kd = T.pt_start[size_t(d) + 1] - T.pt_start[d];
-            while (e < d1 && e - d < 255 && T.pt_start[size_t(e) + 1] - T.pt_start[e] == kd) {
-                bool same = true;
-                for (int i = 0; i < kd && same; ++i) same = cam_of(T.pt_start[d] + i) == cam_of(T.pt_start[e] + i);
-                if (!same) break;
-                ++e;
+            const int32_t* cd = dev_cam.data() + T.pt_start[d];
+            while (e < d1 && e - d < 255 && T.pt_start[size_t(e) + 1] - T.pt_start[e] == kd &&
+                   std::equal(cd, cd + kd, dev_cam.data() + T.pt_start[e])) ++e;
+            for (int a = 0; a < kd; ++a) {
+                if (cam_free[cd[a]] < 0) continue;
+                const int la = lidx[cd[a]];
+                for (int b = a; b < kd; ++b)
+                    if (cam_free[cd[b]] >= 0) marks[tri_index(la, lidx[cd[b]])] = 1;
             }
             const int rounds = (kd * (kd - 1) / 2 + 31) / 32;
             for (int r = 0; r < rounds; ++r)
@@ -243,15 +278,23 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
                 if (gj != gi) { it.b0 = static_cast<uint16_t>(gj * 16); it.b1 = static_cast<uint16_t>(std::min(k, gj * 16 + 16)); }
                 const int na = it.a1 - it.a0, nb = it.b1 - it.b0;
                 Open& o = open[size_t(gi) * ng_max + gj];
-                int fresh = 0;
-                for (int l = 0; l < na + nb; ++l) {
-                    const int c = cam_of(beg + (l < na ? it.a0 + l : it.b0 + l - na));
-                    if (std::find(o.cams.begin(), o.cams.end(), c) == o.cams.end()) ++fresh;
-                }
-                if (!o.items.empty() && (int(o.cams.size()) + fresh > w_cap || int(o.items.size()) >= max_items)) close_items(o);
-                for (int l = 0; l < na + nb; ++l) {
-                    const int c = cam_of(beg + (l < na ? it.a0 + l : it.b0 + l - na));
-                    if (std::find(o.cams.begin(), o.cams.end(), c) == o.cams.end()) o.cams.push_back(c);
+                // the item's cameras are ascending (group A, then group B); the open tile keeps its list sorted: one merge walk
+                int32_t ic[32];
+                for (int l = 0; l < na + nb; ++l) ic[l] = cam_of(beg + (l < na ? it.a0 + l : it.b0 + l - na));
+                auto count_fresh = [&](const std::vector<int32_t>& have) {
+                    int fresh = 0;
+                    size_t h = 0;
+                    for (int l = 0; l < na + nb; ++l) {
+                        while (h < have.size() && have[h] < ic[l]) ++h;
+                        if (h == have.size() || have[h] != ic[l]) ++fresh;
+                    }
+                    return fresh;
+                };
+                if (!o.items.empty() && (int(o.cams.size()) + count_fresh(o.cams) > w_cap || int(o.items.size()) >= max_items)) close_items(o);
+                {
+                    std::vector<int32_t> merged(o.cams.size() + size_t(na + nb));
+                    merged.resize(static_cast<size_t>(std::set_union(o.cams.begin(), o.cams.end(), ic, ic + na + nb, merged.begin()) - merged.begin()));
+                    o.cams.swap(merged);
                 }
                 o.items.push_back(it);
             }
@@ -283,18 +326,27 @@ inline void assign_slots(Tiling& T, const int32_t* cam_free, int n_free, const s
         T.blk_rowptr[size_t(fa) + 1] = static_cast<int32_t>(T.blk_col.size());
     }
     T.tile_slots.assign(T.tile_marks.size(), -1);
-    for (const Tile& t : T.tiles) {
-        const int32_t* lc = T.tile_cams.data() + t.cam_begin;
-        for (int lb = 0; lb < t.w; ++lb)
-            for (int la = 0; la <= lb; ++la) {
-                const int i = t.slot_begin + tri_index(la, lb);
-                if (!T.tile_marks[i]) continue;
-                const int fa = cam_free[lc[la]], fb = cam_free[lc[lb]];
+    const int n_tiles = static_cast<int>(T.tiles.size());
+    parallel_ranges(n_tiles, [&](int t0, int t1) {
+        for (int ti = t0; ti < t1; ++ti) {
+            const Tile& t = T.tiles[ti];
+            const int32_t* lc = T.tile_cams.data() + t.cam_begin;
+            for (int la = 0; la < t.w; ++la) {
+                const int fa = cam_free[lc[la]];
+                if (fa < 0) continue;
+                // local cameras and the block row are both ascending in the free-camera index: one forward walk
                 const int32_t* b = T.blk_col.data() + T.blk_rowptr[fa];
                 const int32_t* e = T.blk_col.data() + T.blk_rowptr[size_t(fa) + 1];
-                T.tile_slots[i] = static_cast<int32_t>(std::lower_bound(b, e, fb) - T.blk_col.data());
+                for (int lb = la; lb < t.w; ++lb) {
+                    const int i = t.slot_begin + tri_index(la, lb);
+                    if (!T.tile_marks[i]) continue;
+                    const int fb = cam_free[lc[lb]];
+                    while (b < e && *b < fb) ++b;
+                    T.tile_slots[i] = static_cast<int32_t>(b - T.blk_col.data());
+                }
             }
-    }
+        }
+    });
 }
 
 }  // namespace ba

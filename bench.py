@@ -4,8 +4,12 @@
 A "step" is one pass of the matching hot path over one batch of synthetic input: ALL image pairs of
 BASELINE.json configs[1] (128 images x 8192 SIFT-like 128-D uint8 descriptors -> 8128 pairs, cross-checked 2-NN
 ratio matching).  Metric: descriptor-pairs/s, counting each unordered image pair's n1*n2 descriptor pairs once
-(SURVEY.md §8d).  Multi-GPU (torchrun, one rank per GPU): the pair list is sharded with no data-path
-collective; every rank processes a full configs[1]-sized pair list of its own image set (weak scaling).
+(SURVEY.md §8d).  Multi-GPU (torchrun, one rank per GPU): the workload is BASELINE configs[2] — 1329 images, ONE list
+of 882 456 pairs — sharded pairs[rank::world] with no data-path collective (descriptors replicated); the total work is the
+same for every N > 1 ("scaling": "strong"), `value` = all pairs / the slowest rank's time.  The BA section shards the points
+of ONE problem over the ranks (one fp32 + fp64 NCCL all-reduce of the block-sparse system per linearisation).
+Further keys: `distributions` (uniform / dense-overlap inputs), `target` (north_star's 1000-image pass), `geometric_verification`
+(batched F-matrix RANSAC vs cv2.findFundamentalMat), `ba` / `ba_large` (configs[3] / configs[4] shapes), `roofline.k2`.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -566,6 +570,12 @@ def run_ours(args, rank, world, local_rank):
         ctx.release_all()
         torch.cuda.empty_cache()
 
+    geo = None
+    if world == 1 and not args.no_extra:
+        try:
+            geo = bench_verify_geometric(ctx)
+        except Exception as ex:
+            geo = {"error": repr(ex)}
     peaks = load_peaks()
     ba_out = None
     ba_large = None
@@ -655,7 +665,8 @@ def run_ours(args, rank, world, local_rank):
                 "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
                 "roofline": roofline, "cpu_baseline": cpu, "verify": verify,
                 "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items() if v["launches"]},
-                "match_stats": stats, "distributions": dists_out, "target": target, "ba": ba_out, "ba_large": ba_large}
+                "match_stats": stats, "distributions": dists_out, "target": target,
+                "geometric_verification": geo, "ba": ba_out, "ba_large": ba_large}
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist:

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "ba_types.cuh"
+#include "ptx.cuh"
 
 namespace msfm {
 namespace band {
@@ -185,10 +186,60 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int& ta
     __syncthreads();
 }
 
+// ---- z += T^T x for one 48 x 48 row-major tile by one warp (back substitution).  The tile is walked flat, 32 consecutive
+// doubles per step (72 steps), so every load instruction of the warp reads 256 contiguous bytes; lane l meets the columns
+// l, (l + 32) % 48 and l + 16 — for steps 0, 1, 2 (mod 3) — and rows (32 i + l) / 48.  Lanes l and l + 16 hold the same three
+// columns in rotated order: one exchange finishes the sums.  (The first layout, three adjacent columns per lane, touched 24
+// sectors per load instruction instead of 8 and made the load/store unit the limit of the whole back substitution.)
+__device__ __forceinline__ int flat_row(int i, int lane) { return (32 * i + lane) / NB; }
+__device__ __forceinline__ void tile_fetch(const double* __restrict__ tile, int lane, double (&t)[72]) {
+#pragma unroll
+    for (int i = 0; i < 72; ++i) t[i] = tile[32 * i + lane];
+}
+__device__ __forceinline__ void tile_dot_regs(const double (&t)[72], const double* sx, int lane, double& a, double& b, double& c) {
+    a = b = c = 0.0;
+#pragma unroll
+    for (int i = 0; i < 72; i += 3) {
+        a += t[i] * sx[flat_row(i, lane)];
+        b += t[i + 1] * sx[flat_row(i + 1, lane)];
+        c += t[i + 2] * sx[flat_row(i + 2, lane)];
+    }
+}
+template <int kBatch>
+__device__ __forceinline__ void tile_dot_mem(const double* tile, const double* sx, int lane, double& a, double& b, double& c) {
+    a = b = c = 0.0;
+#pragma unroll 1
+    for (int i0 = 0; i0 < 72; i0 += kBatch) {
+        double u[kBatch];
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) u[i] = tile[32 * (i0 + i) + lane];
+#pragma unroll
+        for (int i = 0; i < kBatch; i += 3) {
+            a += u[i] * sx[(32 * (i0 + i) + lane) / NB];
+            b += u[i + 1] * sx[(32 * (i0 + i + 1) + lane) / NB];
+            c += u[i + 2] * sx[(32 * (i0 + i + 2) + lane) / NB];
+        }
+    }
+}
+// lanes < 16 add the finished sums of columns l, l + 16, l + 32 to zc
+__device__ __forceinline__ void tile_dot_commit(double a, double b, double c, int lane, double* zc) {
+    const double a2 = __shfl_xor_sync(0xffffffffu, a, 16), b2 = __shfl_xor_sync(0xffffffffu, b, 16), c2 = __shfl_xor_sync(0xffffffffu, c, 16);
+    if (lane < 16) {
+        zc[lane] += a + b2;
+        zc[lane + 16] += c + a2;
+        zc[lane + 32] += b + c2;
+    }
+}
+
+// dynamic shared memory, used by the back substitution only: kThreads/32 staged tiles, the ring of pending column sums (one
+// tile), two rows of pivot reciprocals and of right-hand sides, three mbarriers
+extern __shared__ __align__(128) unsigned char band_dyn[];
+constexpr size_t kDynSmem = (static_cast<size_t>(kThreads / 32) + 1) * NB * NB * sizeof(double) + 4 * NB * sizeof(double) + 64;
+
 __global__ void __launch_bounds__(kThreads, 1)
 band_cholesky_kernel(Params p) {
-    __shared__ double sA[NB * kLd];
-    __shared__ double sB[NB * kLd];
+    __shared__ __align__(16) double sA[NB * kLd];
+    __shared__ __align__(16) double sB[NB * kLd];
     __shared__ double sv[6 * NB];
     __shared__ double sInv[NB];
     const int R = p.R, nbk = p.nbk, Npad = R * NB;
@@ -292,41 +343,71 @@ band_cholesky_kernel(Params p) {
         BAND_TICK(tS);
     }
     // ---- back substitution by CTA 0: x_j = L_jj^-T (y_j - z_j),  z_j = sum_{I > j} L_Ij^T x_I
-    // Right-looking: the pending sums z of the next nbk columns live in a shared-memory ring, and a finished x_I is pushed
-    // into them tile by tile, so that the only work between two consecutive triangular solves is the product with the
-    // nearest tiles.  Per column: (a) every warp w issues the loads of tile (j, j-1-w) — they do not depend on x_j — and keeps
-    // them in registers (72 doubles a lane); (b) L_jj goes to shared memory; (c) warp 0 solves the 48 unknowns with shuffles
-    // while warps 1.. stream the tiles further than kWarps away against the PREVIOUS column's x (their columns are at least
-    // kWarps steps from being solved); (d) all warps multiply their prefetched tile with x_j.  The left-looking version read
-    // the nbk tiles of a column after x_{j+1} was known: 13.8k cycles per column, 2.3 M of the 9.0 M cycles of a solve.
+    // Right-looking: the pending sums z of the next nbk columns live in a shared-memory ring, and a finished x_j is pushed
+    // into them tile by tile, so that the only work between two consecutive triangular solves is one product per warp.
+    // None of the tiles depends on x, so all of them are on their way before x_j exists.  Per column:
+    //   (a) warp w issues the loads of tile (j, j-1-w) and keeps them in registers (72 doubles a lane); one thread starts the
+    //       bulk copies (TMA engine, completion on an mbarrier) of the tiles (j, j-9-w) and of the NEXT diagonal tile;
+    //   (c) warp 0 solves the 48 unknowns of L_jj^T x = y_j - z_j with shuffles (L_jj arrived by bulk copy a column ago);
+    //   (d) warp w multiplies its register tile and its shared-memory tile with x_j.
+    // Bands wider than 2 kWarps tiles: the remaining tiles are streamed by warps 1.. during (c) against the previous x.
+    // The left-looking first version read the nbk tiles of a column after x_{j+1} was known: 20.6k cycles per column, a
+    // third of the solve; this one: see profiles/r02_band_cholesky_phases.txt.
     if (bid != 0) return;
     {
+        using namespace ptx;
         constexpr int kWarps = kThreads / 32;
+        constexpr uint32_t kTileBytes = NB * NB * sizeof(double);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int cg3 = 3 * (lane & 15), rp = lane >> 4;          // a lane: columns cg3 .. cg3 + 2 of the rows of parity rp
         const int ring = nbk + 1;
-        double* z = sB;                                           // [ring][NB], ring <= NB (band_create keeps wider bands off this solver)
+        double* sFar = reinterpret_cast<double*>(band_dyn);       // [kWarps][NB * NB]
+        double* z = sFar + kWarps * NB * NB;                      // [ring][NB], ring <= NB (band_create)
+        double* sDinv = z + NB * NB;                              // [2][NB]
+        double* sY = sDinv + 2 * NB;                              // [2][NB] y_j, travelling with the diagonal tile
+        uint64_t* bars = reinterpret_cast<uint64_t*>(sY + 2 * NB);      // [0], [1]: diagonal tile buffers; [2]: far tiles
+        double* sDiag[2] = {sA, sB};                              // row-major [NB][NB] here (the factor phases use stride kLd)
+        uint32_t dphase = 0, fphase = 0;
+        if (threadIdx.x == 0) {
+            mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
         for (int q = 0; q < p.nrhs; ++q) {
             double* y = p.y + static_cast<size_t>(q) * Npad;
             for (int i = threadIdx.x; i < ring * NB; i += kThreads) z[i] = 0.0;
             __syncthreads();
+            if (threadIdx.x == 0) {
+                fence_proxy_async();
+                const int b = (R - 1) & 1;
+                mbar_arrive_expect_tx(&bars[b], kTileBytes + 2 * NB * sizeof(double));
+                bulk_g2s(sDiag[b], tile_ptr(p, R - 1, R - 1), kTileBytes, &bars[b]);
+                bulk_g2s(sDinv + b * NB, p.dinv + static_cast<size_t>(R - 1) * NB, NB * sizeof(double), &bars[b]);
+                bulk_g2s(sY + b * NB, y + static_cast<size_t>(R - 1) * NB, NB * sizeof(double), &bars[b]);
+            }
             for (int j = R - 1; j >= 0; --j) {
                 double* sx = sv + (j & 1) * NB;                   // x_j; the previous column's x stays in the other half
                 const double* sxp = sv + ((j + 1) & 1) * NB;
-                const int m_near = min(min(nbk, j), kWarps);
+                const int m_all = min(nbk, j);                    // tiles (j, j-1-w), w < m_all, take x_j
+                const int m_near = min(m_all, kWarps);
+                const int m_far = min(max(m_all - kWarps, 0), kWarps);
                 // (a)
-                double t[24][3];
-                if (warp < m_near) {
-                    const double* L = tile_ptr(p, j, j - 1 - warp) + cg3;
-#pragma unroll
-                    for (int k = 0; k < 24; ++k)
-#pragma unroll
-                        for (int u = 0; u < 3; ++u) t[k][u] = L[(rp + 2 * k) * NB + u];
+                double t[72];
+                if (warp < m_near) tile_fetch(tile_ptr(p, j, j - 1 - warp), lane, t);
+                if (threadIdx.x == 32) {                          // warp 1: idle during (c); warp 0 goes straight to the solve
+                    fence_proxy_async();
+                    if (j > 0) {
+                        const int b = (j - 1) & 1;
+                        mbar_arrive_expect_tx(&bars[b], kTileBytes + 2 * NB * sizeof(double));
+                        bulk_g2s(sDiag[b], tile_ptr(p, j - 1, j - 1), kTileBytes, &bars[b]);
+                        bulk_g2s(sDinv + b * NB, p.dinv + static_cast<size_t>(j - 1) * NB, NB * sizeof(double), &bars[b]);
+                        bulk_g2s(sY + b * NB, y + static_cast<size_t>(j - 1) * NB, NB * sizeof(double), &bars[b]);
+                    }
+                    if (m_far > 0) {
+                        mbar_arrive_expect_tx(&bars[2], m_far * kTileBytes);
+                        for (int f = 0; f < m_far; ++f)
+                            bulk_g2s(sFar + f * NB * NB, tile_ptr(p, j, j - 1 - kWarps - f), kTileBytes, &bars[2]);
+                    }
                 }
-                // (b)
-                load_tile(tile_ptr(p, j, j), sA);
-                if (threadIdx.x < NB) sInv[threadIdx.x] = p.dinv[static_cast<size_t>(j) * NB + threadIdx.x];
-                __syncthreads();
                 // (c)
                 if (warp == 0) {
                     // L_jj^T x = b from the last unknown up, b in registers (lane l: unknowns l and l + 32): x[cc] is final
@@ -335,14 +416,18 @@ band_cholesky_kernel(Params p) {
                     const int l = lane;
                     double* yj = y + static_cast<size_t>(j) * NB;
                     double* zj = z + (j % ring) * NB;
-                    double b0 = yj[l] - zj[l];
-                    double b1 = l < NB - 32 ? yj[32 + l] - zj[32 + l] : 0.0;
+                    mbar_wait(&bars[j & 1], (dphase >> (j & 1)) & 1u);
+                    const double* sYj = sY + (j & 1) * NB;
+                    double b0 = sYj[l] - zj[l];
+                    double b1 = l < NB - 32 ? sYj[32 + l] - zj[32 + l] : 0.0;
                     zj[l] = 0.0;                                   // the slot now collects for column j - ring
                     if (l < NB - 32) zj[32 + l] = 0.0;
-                    const double i0 = sInv[l], i1 = l < NB - 32 ? sInv[32 + l] : 0.0;
+                    const double* sL = sDiag[j & 1];
+                    const double* sI = sDinv + (j & 1) * NB;
+                    const double i0 = sI[l], i1 = l < NB - 32 ? sI[32 + l] : 0.0;
 #pragma unroll
                     for (int cc = NB - 1; cc >= 32; --cc) {
-                        const double lr0 = sA[cc * kLd + l], lr1 = l < cc - 32 ? sA[cc * kLd + 32 + l] : 0.0;
+                        const double lr0 = sL[cc * NB + l], lr1 = l < cc - 32 ? sL[cc * NB + 32 + l] : 0.0;
                         const double x = __shfl_sync(0xffffffffu, b1 * i1, cc - 32);
                         if (l == cc - 32) b1 = x;
                         else if (l < cc - 32) b1 -= lr1 * x;
@@ -350,7 +435,7 @@ band_cholesky_kernel(Params p) {
                     }
 #pragma unroll
                     for (int cc = 31; cc >= 0; --cc) {
-                        const double lr0 = l < cc ? sA[cc * kLd + l] : 0.0;
+                        const double lr0 = l < cc ? sL[cc * NB + l] : 0.0;
                         const double x = __shfl_sync(0xffffffffu, b0 * i0, cc);
                         if (l == cc) b0 = x;
                         else if (l < cc) b0 -= lr0 * x;
@@ -359,53 +444,34 @@ band_cholesky_kernel(Params p) {
                     if (l < NB - 32) sx[32 + l] = b1;
                     yj[l] = b0;
                     if (l < NB - 32) yj[32 + l] = b1;
-                } else if (j + 1 < R) {
-                    // tiles (j+1, j+1-d), d = kWarps+1 .. nbk, against x_{j+1}: streamed, eight row pairs at a time
-                    for (int d = kWarps + warp; d <= nbk; d += kWarps - 1) {
+                } else if (j + 1 < R && nbk > 2 * kWarps) {
+                    // tiles (j+1, j+1-d), d = 2 kWarps + 1 .. nbk, against x_{j+1}: streamed, eight row pairs at a time
+                    for (int d = 2 * kWarps + warp; d <= nbk; d += kWarps - 1) {
                         const int col = j + 1 - d;
                         if (col < 0) break;
-                        const double* L = tile_ptr(p, j + 1, col) + cg3;
-                        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll 1
-                        for (int k0 = 0; k0 < 24; k0 += 8) {
-                            double u[8][3];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k)
-#pragma unroll
-                                for (int e = 0; e < 3; ++e) u[k][e] = L[(rp + 2 * (k0 + k)) * NB + e];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const double xv = sxp[rp + 2 * (k0 + k)];
-                                s0 += u[k][0] * xv; s1 += u[k][1] * xv; s2 += u[k][2] * xv;
-                            }
-                        }
-                        s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-                        if (rp == 0) {
-                            double* zc = z + (col % ring) * NB + cg3;
-                            zc[0] += s0; zc[1] += s1; zc[2] += s2;
-                        }
+                        double a, b, c;
+                        tile_dot_mem<24>(tile_ptr(p, j + 1, col), sxp, lane, a, b, c);
+                        tile_dot_commit(a, b, c, lane, z + (col % ring) * NB);
                     }
                 }
+                dphase ^= 1u << (j & 1);
                 __syncthreads();
                 // (d)
                 if (warp < m_near) {
-                    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 24; ++k) {
-                        const double xv = sx[rp + 2 * k];
-                        s0 += t[k][0] * xv; s1 += t[k][1] * xv; s2 += t[k][2] * xv;
-                    }
-                    s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-                    if (rp == 0) {
-                        double* zc = z + ((j - 1 - warp) % ring) * NB + cg3;
-                        zc[0] += s0; zc[1] += s1; zc[2] += s2;
-                    }
+                    double a, b, c;
+                    tile_dot_regs(t, sx, lane, a, b, c);
+                    tile_dot_commit(a, b, c, lane, z + ((j - 1 - warp) % ring) * NB);
                 }
-                __syncthreads();                                  // z and sA are free for the next column
+                if (m_far > 0) {
+                    if (warp < m_far) {
+                        mbar_wait(&bars[2], fphase);
+                        double a, b, c;
+                        tile_dot_mem<72>(sFar + warp * NB * NB, sx, lane, a, b, c);
+                        tile_dot_commit(a, b, c, lane, z + ((j - 1 - kWarps - warp) % ring) * NB);
+                    }
+                    fphase ^= 1u;
+                }
+                __syncthreads();                                  // z, the far tiles and the diagonal buffer are free again
             }
         }
     }
@@ -498,7 +564,8 @@ BandSolver* band_create(int nf, const std::vector<int32_t>& blk_row, const std::
     if (e == cudaSuccess && getenv("MSFM_BAND_DEBUG")) e = cudaMalloc(reinterpret_cast<void**>(&B->d_dbg), 8 * sizeof(long long));
     if (e == cudaSuccess) e = cudaMemcpy(B->d_pos, pos.data(), static_cast<size_t>(nf) * sizeof(int32_t), cudaMemcpyHostToDevice);
     int per_sm = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, band::band_cholesky_kernel, band::kThreads, 0);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(band::band_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(band::kDynSmem));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, band::band_cholesky_kernel, band::kThreads, band::kDynSmem);
     if (e == cudaSuccess && per_sm < 1) e = cudaErrorLaunchOutOfResources;
     if (e != cudaSuccess) {
         *err = e;
@@ -543,7 +610,7 @@ cudaError_t band_factor_solve(BandSolver* B, const ba::Problem& P, double inv_ra
         band::permute_in_kernel<<<(N + 255) / 256, 256, 0, st>>>(rhs + static_cast<size_t>(c) * N, B->d_pos, B->nf, B->y + static_cast<size_t>(c) * Npad);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     void* args[] = {&p};
-    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(band::band_cholesky_kernel), dim3(B->grid), dim3(band::kThreads), args, 0, st);
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(band::band_cholesky_kernel), dim3(B->grid), dim3(band::kThreads), args, band::kDynSmem, st);
     if (e != cudaSuccess) return e;
     for (int c = 0; c < nrhs; ++c)
         band::permute_out_kernel<<<(N + 255) / 256, 256, 0, st>>>(B->y + static_cast<size_t>(c) * Npad, B->d_pos, B->nf, rhs + static_cast<size_t>(c) * N);

@@ -39,7 +39,7 @@ public:
         cv::Vec3d point3D;
         std::vector<Measurement> measurements;
     };
-    // world -> camera: x_cam = R(rvec) x + tvec, rvec an angle-axis vector (cv::Rodrigues); both 3x1 CV_64F
+    // world -> camera: x_cam = R(rvec) x + tvec, rvec an angle-axis vector (cv::Rodrigues); both CV_64F with 3 elements (3x1 or 1x3)
     struct CameraPose {
         CameraPose() {}
         CameraPose(const cv::Mat& rvec, const cv::Mat& tvec) : rvec(rvec), tvec(tvec) {}

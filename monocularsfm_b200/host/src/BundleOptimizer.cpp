@@ -3,6 +3,8 @@
 #include <cassert>
 #include <cmath>
 #include <iostream>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "DeviceContext.h"
@@ -25,6 +27,14 @@ struct Flat {
     double fx, fy, cx, cy;
 };
 
+// A pose vector as the reference hands it to Ceres: `rvec.data` taken as double[3] (CeresBundleOptimizer.cpp:230-233), which
+// holds for a 3x1 and for a 1x3 Mat alike.  Anything else is a caller error, reported instead of read out of bounds.
+double* PoseData(cv::Mat& v, const char* what) {
+    if (v.type() != CV_64F || v.rows * v.cols != 3 || !v.data)
+        throw std::runtime_error(std::string("CeresBundelOptimizer: ") + what + " must be a CV_64F Mat with 3 elements");
+    return reinterpret_cast<double*>(v.data);
+}
+
 Flat Flatten(BundleData& bd) {
     assert(bd.K.type() == CV_64F);                                           // :190
     Flat f;
@@ -38,9 +48,11 @@ Flat Flatten(BundleData& bd) {
     f.cam_const.assign(f.cam_ids.size(), 0);
     for (size_t i = 0; i < f.cam_ids.size(); ++i) {
         BundleData::CameraPose& cp = bd.camera_poses[f.cam_ids[i]];
+        const double* rv = PoseData(cp.rvec, "rvec");
+        const double* tv = PoseData(cp.tvec, "tvec");
         for (int k = 0; k < 3; ++k) {
-            f.cams[6 * i + k] = cp.rvec.at<double>(k, 0);
-            f.cams[6 * i + 3 + k] = cp.tvec.at<double>(k, 0);
+            f.cams[6 * i + k] = rv[k];
+            f.cams[6 * i + 3 + k] = tv[k];
         }
         if (bd.constant_camera_pose.count(f.cam_ids[i])) f.cam_const[i] = 1;   // :256-260
     }
@@ -118,9 +130,11 @@ bool CeresBundelOptimizer::Optimize(BundleData& bundle_data) {
     msfm_ba_destroy(ba);
     for (size_t i = 0; i < f.cam_ids.size(); ++i) {
         BundleData::CameraPose& cp = bundle_data.camera_poses[f.cam_ids[i]];
+        double* rv = PoseData(cp.rvec, "rvec");
+        double* tv = PoseData(cp.tvec, "tvec");
         for (int k = 0; k < 3; ++k) {
-            cp.rvec.at<double>(k, 0) = f.cams[6 * i + k];
-            cp.tvec.at<double>(k, 0) = f.cams[6 * i + 3 + k];
+            rv[k] = f.cams[6 * i + k];
+            tv[k] = f.cams[6 * i + 3 + k];
         }
     }
     for (size_t p = 0; p < f.pt_ids.size(); ++p)

@@ -157,8 +157,10 @@ static int run_ba(char** argv) {
     bd.K.at<double>(2, 2) = 1.0;
     const int id_off = 100;                                  // image ids need not be 0-based
     for (int c = 0; c < hdr[0]; ++c) {
-        cv::Mat r(3, 1, CV_64F), t(3, 1, CV_64F);
-        for (int j = 0; j < 3; ++j) { r.at<double>(j, 0) = cams[6 * c + j]; t.at<double>(j, 0) = cams[6 * c + 3 + j]; }
+        // every other pose as a 1x3 row: the reference hands `rvec.data` to Ceres as double[3], either shape works there
+        const bool row = (c & 1) != 0;
+        cv::Mat r(row ? 1 : 3, row ? 3 : 1, CV_64F), t(row ? 1 : 3, row ? 3 : 1, CV_64F);
+        for (int j = 0; j < 3; ++j) { reinterpret_cast<double*>(r.data)[j] = cams[6 * c + j]; reinterpret_cast<double*>(t.data)[j] = cams[6 * c + 3 + j]; }
         bd.camera_poses[id_off + c] = BundleData::CameraPose(r, t);
     }
     for (int p = 0; p < hdr[1]; ++p) bd.landmarks[7 * p + 3].point3D = cv::Vec3d(pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]);
@@ -171,7 +173,10 @@ static int run_ba(char** argv) {
     const bool ok = opt.Optimize(bd);
     const double after = bd.Debug();
     for (int c = 0; c < hdr[0]; ++c)
-        for (int j = 0; j < 3; ++j) { cams[6 * c + j] = bd.camera_poses[id_off + c].rvec.at<double>(j, 0); cams[6 * c + 3 + j] = bd.camera_poses[id_off + c].tvec.at<double>(j, 0); }
+        for (int j = 0; j < 3; ++j) {
+            cams[6 * c + j] = reinterpret_cast<const double*>(bd.camera_poses[id_off + c].rvec.data)[j];
+            cams[6 * c + 3 + j] = reinterpret_cast<const double*>(bd.camera_poses[id_off + c].tvec.data)[j];
+        }
     for (int p = 0; p < hdr[1]; ++p)
         for (int j = 0; j < 3; ++j) pts[3 * p + j] = bd.landmarks[7 * p + 3].point3D(j);
     std::ofstream out(argv[3], std::ios::binary);

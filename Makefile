@@ -53,3 +53,8 @@ microbench_alu: build/microbench_alu
 build/microbench_alu: tools/microbench_alu.cu
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ $<
+
+microbench_f64: build/microbench_f64
+build/microbench_f64: tools/microbench_f64.cu
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ $<

@@ -39,7 +39,9 @@ struct Params {
     double* dinv;      // [R * NB] reciprocals of the diagonal of L (the substitutions multiply instead of dividing)
     unsigned int* bar; // grid barrier counter (zeroed before the launch)
     int32_t* info;     // != 0: a pivot was not positive
-    long long* dbg;    // optional [8]: cycles CTA 0 spent in D, P, U, the three barriers, the back substitution (MSFM_BAND_DEBUG=1)
+    double* zfar;      // [nrhs][R * NB] back substitution: sums of the tiles further than 4 from the diagonal, added by the helper CTAs
+    unsigned int* flags;   // [nrhs][R + 1]: done[col] = helper sums that have reached zfar[col]; [R] = columns solved so far
+    long long* dbg;    // optional [16]: cycles CTA 0 spent in D, P, U, the grid barriers, the back substitution (+ three parts of it) (MSFM_BAND_DEBUG=1)
     int32_t R, nbk, nrhs;
 };
 
@@ -127,24 +129,24 @@ __device__ __noinline__ void diag_factor(double* sA, double* sInv, double* __res
     if (threadIdx.x < NB) dinv[threadIdx.x] = sInv[threadIdx.x];
 }
 
-// ---- P: rows x of a tile solved against L (shared memory sL, reciprocal diagonal sInv): x <- x L^-T, i.e.
-// x[c] = (x[c] - sum_{k<c} x[k] L[c][k]) / L[c][c].
-// One thread per row, the row in registers, no communication.
-__device__ __forceinline__ void solve_row(double x[NB], const double* sL, const double* sInv) {
+// ---- P: rows x of a tile solved against L: x <- x L^-T, i.e. x[c] = (x[c] - sum_{k<c} x[k] L[c][k]) / L[c][c].
+// One thread per row, the row in registers, no communication.  sLs holds L with row c SCALED by 1 / L[c][c] (load_tile_scaled),
+// so that x[c] = x[c] / L[c][c] - sum_k x[k] Ls[c][k], and the loop runs column by column (right-looking): as soon as x[k] is
+// final it is removed from all later unknowns, the first of which is the next one to become final — ONE dependent FMA per
+// unknown (8.8 cycles, tools/microbench_f64.cu) with the other 46 - k FMAs of the column issued in its shadow.  The row-by-row
+// form with four partial sums had the last FMA, two adds and the multiply by 1 / L[c][c] on the chain of every unknown.
+__device__ __forceinline__ void solve_row(double x[NB], const double* sLs, const double* sInv) {
 #pragma unroll
-    for (int c = 0; c < NB; ++c) {
-        double s0 = x[c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int c = 0; c < NB; ++c) x[c] *= sInv[c];
 #pragma unroll
-        for (int k = 0; k + 3 < c; k += 4) {
-            s0 -= x[k] * sL[c * kLd + k];
-            s1 -= x[k + 1] * sL[c * kLd + k + 1];
-            s2 -= x[k + 2] * sL[c * kLd + k + 2];
-            s3 -= x[k + 3] * sL[c * kLd + k + 3];
-        }
+    for (int k = 0; k < NB - 1; ++k) {
+        const double xk = x[k];
 #pragma unroll
-        for (int k = c & ~3; k < c; ++k) s0 -= x[k] * sL[c * kLd + k];
-        x[c] = ((s0 + s1) + (s2 + s3)) * sInv[c];
+        for (int c = k + 1; c < NB; ++c) x[c] = fma(-xk, sLs[c * kLd + k], x[c]);
     }
+}
+__device__ __forceinline__ void load_tile_scaled(const double* __restrict__ g, const double* __restrict__ dinv, double* s) {
+    for (int i = threadIdx.x; i < NB * NB; i += kThreads) s[(i / NB) * kLd + (i % NB)] = g[i] * dinv[i / NB];
 }
 
 // ---- U: C -= A B^T for 48 x 48 tiles; A, B staged in shared memory TRANSPOSED ([k][row]); 16 x 16 threads, 3 x 3 outputs each
@@ -196,28 +198,103 @@ __device__ __forceinline__ void tile_fetch(const double* __restrict__ tile, int 
 #pragma unroll
     for (int i = 0; i < 72; ++i) t[i] = tile[32 * i + lane];
 }
+// four partial sums per column: dependent chains of 6 FMAs instead of 24
 __device__ __forceinline__ void tile_dot_regs(const double (&t)[72], const double* sx, int lane, double& a, double& b, double& c) {
-    a = b = c = 0.0;
+    double pa[4] = {0.0, 0.0, 0.0, 0.0}, pb[4] = {0.0, 0.0, 0.0, 0.0}, pc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int i = 0; i < 72; i += 3) {
-        a += t[i] * sx[flat_row(i, lane)];
-        b += t[i + 1] * sx[flat_row(i + 1, lane)];
-        c += t[i + 2] * sx[flat_row(i + 2, lane)];
+        pa[(i / 3) & 3] += t[i] * sx[flat_row(i, lane)];
+        pb[(i / 3) & 3] += t[i + 1] * sx[flat_row(i + 1, lane)];
+        pc[(i / 3) & 3] += t[i + 2] * sx[flat_row(i + 2, lane)];
+    }
+    a = (pa[0] + pa[1]) + (pa[2] + pa[3]);
+    b = (pb[0] + pb[1]) + (pb[2] + pb[3]);
+    c = (pc[0] + pc[1]) + (pc[2] + pc[3]);
+}
+// ---- the diagonal tile of the back substitution, solved four unknowns at a time.
+// invert_diag_blocks: lane bk < 12 inverts the 4 x 4 diagonal block bk of L (row-major tile sL, reciprocals of the diagonal sI)
+// into W[bk][16] (row-major, lower triangle).  Off the critical path: done by an idle warp a column ahead.
+__device__ __forceinline__ void invert_diag_blocks(const double* sL, const double* sI, double* W, int lane) {
+    if (lane >= NB / 4) return;
+    const int u0 = 4 * lane;
+    double w[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double di = sI[u0 + i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k > i) { w[i][k] = 0.0; continue; }
+            if (k == i) { w[i][k] = di; continue; }
+            double acc = 0.0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+                if (m >= k && m < i) acc += sL[(u0 + i) * NB + u0 + m] * w[m][k];
+            w[i][k] = -di * acc;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) W[lane * 16 + 4 * i + k] = w[i][k];
+}
+// solve_diag_blocked: L^T x = b by one warp; lane l holds unknowns l (b0) and l + 32 (b1, lanes < 16).  Per block of four
+// unknowns, from the last: four shuffles fetch the block's b, every lane forms x_blk = W_blk^T b_blk (10 FMAs, three levels
+// deep), the owners keep their x, the lanes below eliminate the four unknowns from their own (rows of L read ahead of the
+// chain).  12 steps of shuffle + ~6 dependent operations instead of 48 steps of multiply -> shuffle -> FMA (55 cycles each,
+// tools/microbench_f64.cu).
+__device__ __forceinline__ void solve_diag_blocked(const double* sL, const double* W, int l, double& b0, double& b1) {
+#pragma unroll
+    for (int bk = NB / 4 - 1; bk >= 0; --bk) {
+        const int u0 = 4 * bk;
+        const bool hi = u0 >= 32;                                  // compile-time: the loop is unrolled
+        double bb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bb[i] = __shfl_sync(0xffffffffu, hi ? b1 : b0, (u0 + i) & 31);
+        const double* w = W + bk * 16;
+        const double x3 = w[15] * bb[3];
+        const double x2 = w[10] * bb[2] + w[14] * bb[3];
+        const double x1 = (w[5] * bb[1] + w[9] * bb[2]) + w[13] * bb[3];
+        const double x0 = (w[0] * bb[0] + w[4] * bb[1]) + (w[8] * bb[2] + w[12] * bb[3]);
+        // branch-free: every lane forms the update, selects decide who keeps what (a five-way divergent branch per block cost
+        // more than the arithmetic)
+        const double l0 = sL[(u0 + 0) * NB + l], l1 = sL[(u0 + 1) * NB + l], l2 = sL[(u0 + 2) * NB + l], l3 = sL[(u0 + 3) * NB + l];
+        const double upd0 = (b0 - (l0 * x0 + l1 * x1)) - (l2 * x2 + l3 * x3);
+        if (hi) {
+            // unknowns 32 + l of lanes l < u0 - 32 are below the block; unknowns l (all lanes) too
+            const int r = l - (u0 - 32);
+            const int lc = 32 + (l & 15);                          // a valid column for every lane; lanes >= 16 hold no second unknown
+            const double h0 = sL[(u0 + 0) * NB + lc], h1 = sL[(u0 + 1) * NB + lc], h2 = sL[(u0 + 2) * NB + lc], h3 = sL[(u0 + 3) * NB + lc];
+            const double upd1 = (b1 - (h0 * x0 + h1 * x1)) - (h2 * x2 + h3 * x3);
+            const double xs = r == 0 ? x0 : (r == 1 ? x1 : (r == 2 ? x2 : x3));
+            b1 = r < 0 ? upd1 : (r < 4 ? xs : b1);
+            b0 = upd0;
+        } else {
+            const int r = l - u0;
+            const double xs = r == 0 ? x0 : (r == 1 ? x1 : (r == 2 ? x2 : x3));
+            b0 = r < 0 ? upd0 : (r < 4 ? xs : b0);
+        }
     }
 }
-template <int kBatch>
-__device__ __forceinline__ void tile_dot_mem(const double* tile, const double* sx, int lane, double& a, double& b, double& c) {
-    a = b = c = 0.0;
-#pragma unroll 1
-    for (int i0 = 0; i0 < 72; i0 += kBatch) {
-        double u[kBatch];
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) u[i] = tile[32 * (i0 + i) + lane];
-#pragma unroll
-        for (int i = 0; i < kBatch; i += 3) {
-            a += u[i] * sx[(32 * (i0 + i) + lane) / NB];
-            b += u[i + 1] * sx[(32 * (i0 + i + 1) + lane) / NB];
-            c += u[i + 2] * sx[(32 * (i0 + i + 2) + lane) / NB];
+// ---- flags between the CTAs of the back substitution (all resident: cooperative launch).  Waits are bounded: a protocol bug
+// must become a trapped kernel, never a hang.
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_at_least(const unsigned int* p, unsigned int want) {
+    if (ld_acquire(p) >= want) return;
+    const long long t0 = clock64();
+    while (ld_acquire(p) < want) {
+        if (clock64() - t0 > 4000000000LL) {           // ~2 s
+            printf("msfm: band back substitution flag wait timed out (block %d thread %d want %u have %u)\n", blockIdx.x, threadIdx.x, want, ld_acquire(p));
+            __trap();
         }
     }
 }
@@ -231,10 +308,11 @@ __device__ __forceinline__ void tile_dot_commit(double a, double b, double c, in
     }
 }
 
-// dynamic shared memory, used by the back substitution only: kThreads/32 staged tiles, the ring of pending column sums (one
-// tile), two rows of pivot reciprocals and of right-hand sides, three mbarriers
+// dynamic shared memory, used by the back substitution only (CTA 0: a third diagonal tile buffer, ring of pending column
+// sums, three sets of pivots / right-hand sides / inverted diagonal blocks, two of helper sums, three mbarriers; helpers: one
+// copy of x_j per warp)
 extern __shared__ __align__(128) unsigned char band_dyn[];
-constexpr size_t kDynSmem = (static_cast<size_t>(kThreads / 32) + 1) * NB * NB * sizeof(double) + 4 * NB * sizeof(double) + 64;
+constexpr size_t kDynSmem = NB * NB * sizeof(double) + 16 * NB * sizeof(double) + 3 * (NB / 4) * 16 * sizeof(double) + 64;
 
 __global__ void __launch_bounds__(kThreads, 1)
 band_cholesky_kernel(Params p) {
@@ -262,7 +340,7 @@ band_cholesky_kernel(Params p) {
         const int m = min(nbk, R - 1 - j);                 // tile rows below the diagonal in this column
         // ---- P: tasks 0 .. m-1 = tiles (j + 1 + t, j); task m = the right-hand sides
         for (int t = bid; t <= m; t += nblk) {
-            load_tile(tile_ptr(p, j, j), sB);              // L_jj
+            load_tile_scaled(tile_ptr(p, j, j), p.dinv + static_cast<size_t>(j) * NB, sB);     // L_jj, row c scaled by 1 / L_cc
             if (threadIdx.x < NB) sInv[threadIdx.x] = p.dinv[static_cast<size_t>(j) * NB + threadIdx.x];
             if (t < m) {
                 double* g = tile_ptr(p, j + 1 + t, j);
@@ -342,31 +420,78 @@ band_cholesky_kernel(Params p) {
         grid_barrier(p.bar, bar_target, nblk);
         BAND_TICK(tS);
     }
-    // ---- back substitution by CTA 0: x_j = L_jj^-T (y_j - z_j),  z_j = sum_{I > j} L_Ij^T x_I
-    // Right-looking: the pending sums z of the next nbk columns live in a shared-memory ring, and a finished x_j is pushed
-    // into them tile by tile, so that the only work between two consecutive triangular solves is one product per warp.
-    // None of the tiles depends on x, so all of them are on their way before x_j exists.  Per column:
-    //   (a) warp w issues the loads of tile (j, j-1-w) and keeps them in registers (72 doubles a lane); one thread starts the
-    //       bulk copies (TMA engine, completion on an mbarrier) of the tiles (j, j-9-w) and of the NEXT diagonal tile;
-    //   (c) warp 0 solves the 48 unknowns of L_jj^T x = y_j - z_j with shuffles (L_jj arrived by bulk copy a column ago);
-    //   (d) warp w multiplies its register tile and its shared-memory tile with x_j.
-    // Bands wider than 2 kWarps tiles: the remaining tiles are streamed by warps 1.. during (c) against the previous x.
-    // The left-looking first version read the nbk tiles of a column after x_{j+1} was known: 20.6k cycles per column, a
-    // third of the solve; this one: see profiles/r02_band_cholesky_phases.txt.
-    if (bid != 0) return;
+    // ---- back substitution: x_j = L_jj^-T (y_j - z_j),  z_j = sum_{I > j} L_Ij^T x_I, columns from the last.
+    // The chain x_{j+1} -> x_j is sequential, but only through the diagonal solve and the NEAREST tiles; everything else is
+    // bandwidth: 17 tiles of 18 KB per column, and one SM draws ~42 B/clk from L2 (7.4k cycles per column — the single-CTA
+    // versions sat at 9.3-10k whatever the prefetching, profiles/r02_band_cholesky_phases.txt).  So the tiles are spread:
+    //   CTA 0  solves.  Warp 0: the 48 unknowns of a column, four at a time against inverted 4 x 4 diagonal blocks (the diagonal
+    //          tile, its pivots and y_j arrive by bulk copy a column ahead; warp 1 inverts the blocks).  Warps 1..4: the tiles
+    //          at distance 1..4 (tile (j, j - w)), loaded into registers BEFORE x_j exists, multiplied right after, summed into a
+    //          shared-memory ring of pending column sums.  Warp 5 collects the helpers' sums of the NEXT column; warp 6
+    //          publishes the previous x (global store + release of a monotonic counter) under the current solve; warp 7
+    //          starts the bulk copies two columns ahead and inverts the diagonal blocks one column ahead.
+    //   CTA h  (helper, one per distance d = 4 + h <= nbk): each of its warps takes every 8th column j, loads tile (j, j - d)
+    //          ahead of time, waits for x_j, multiplies, adds into zfar[j - d] with fp64 reductions and releases done[j - d].
+    //          A column's last helper sum comes from x_{j+5}: it has more than three column times to arrive.
+    // Right-looking, so no tile ever waits for an x on the critical path except the four of CTA 0.
     {
         using namespace ptx;
         constexpr int kWarps = kThreads / 32;
+        constexpr int kNear = 4;
         constexpr uint32_t kTileBytes = NB * NB * sizeof(double);
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int ring = nbk + 1;
-        double* sFar = reinterpret_cast<double*>(band_dyn);       // [kWarps][NB * NB]
-        double* z = sFar + kWarps * NB * NB;                      // [ring][NB], ring <= NB (band_create)
-        double* sDinv = z + NB * NB;                              // [2][NB]
-        double* sY = sDinv + 2 * NB;                              // [2][NB] y_j, travelling with the diagonal tile
-        uint64_t* bars = reinterpret_cast<uint64_t*>(sY + 2 * NB);      // [0], [1]: diagonal tile buffers; [2]: far tiles
-        double* sDiag[2] = {sA, sB};                              // row-major [NB][NB] here (the factor phases use stride kLd)
-        uint32_t dphase = 0, fphase = 0;
+        // the warp index through a shuffle: the compiler then knows it is uniform across the warp and compiles the shuffles of the
+        // warp-specialised branches below as plain SHFL; with `threadIdx.x >> 5` every one of them was wrapped in a convergence
+        // barrier (WARPSYNC.COLLECTIVE ... ENDCOLLECTIVE) and completed before the next could start — 96 of them, 5.1k cycles per
+        // column in the diagonal solve alone
+        const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+        const int n_helpers = max(nbk - kNear, 0);
+        if (bid > n_helpers) return;
+        double* dyn = reinterpret_cast<double*>(band_dyn);
+        if (bid > 0) {
+            // ------------------------------------------------------------------ helper of distance d
+            const int d = kNear + bid;
+            double* xs = dyn + warp * NB;                          // this warp's copy of x_j
+            for (int q = 0; q < p.nrhs; ++q) {
+                const double* y = p.y + static_cast<size_t>(q) * Npad;
+                double* zfar = p.zfar + static_cast<size_t>(q) * Npad;
+                unsigned int* flags = p.flags + static_cast<size_t>(q) * (R + 1);     // [0..R): done[col], [R]: columns solved
+                for (int j = R - 1 - warp; j >= d; j -= kWarps) {
+                    double t[72];
+                    tile_fetch(tile_ptr(p, j, j - d), lane, t);
+                    if (lane == 0) wait_at_least(flags + R, static_cast<unsigned int>(R - j));
+                    __syncwarp();
+                    xs[lane] = __ldcg(y + static_cast<size_t>(j) * NB + lane);
+                    if (lane < NB - 32) xs[32 + lane] = __ldcg(y + static_cast<size_t>(j) * NB + 32 + lane);
+                    __syncwarp();
+                    double a, b, c;
+                    tile_dot_regs(t, xs, lane, a, b, c);
+                    const double a2 = __shfl_xor_sync(0xffffffffu, a, 16), b2 = __shfl_xor_sync(0xffffffffu, b, 16), c2 = __shfl_xor_sync(0xffffffffu, c, 16);
+                    if (lane < 16) {
+                        double* zc = zfar + static_cast<size_t>(j - d) * NB;
+                        atomicAdd(zc + lane, a + b2);
+                        atomicAdd(zc + lane + 16, c + a2);
+                        atomicAdd(zc + lane + 32, b + c2);
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) red_release_add(flags + (j - d), 1u);
+                }
+            }
+            return;
+        }
+        // ---------------------------------------------------------------------- CTA 0
+        const int ring = kNear + 1;
+        double* sD2 = dyn;                                        // third diagonal tile buffer (row-major [NB][NB])
+        double* z = sD2 + NB * NB;                                // [ring][NB] pending sums of the near tiles
+        double* sDinv = z + ring * NB;                            // [3][NB]
+        double* sY = sDinv + 3 * NB;                              // [3][NB] y_j, travelling with the diagonal tile
+        double* sW = sY + 3 * NB;                                 // [3][NB / 4][16] inverted diagonal blocks
+        double* sZf = sW + 3 * (NB / 4) * 16;                     // [2][NB] the helpers' sums of a column
+        uint64_t* bars = reinterpret_cast<uint64_t*>(sZf + 2 * NB);      // [3]: diagonal tile buffers
+        double* sDiag[3] = {sA, sB, sD2};                         // sA / sB: row-major [NB][NB] here (the factor phases use stride kLd)
+        uint32_t dphase = 0;
+        long long bA = 0, bC = 0, bD = 0, bE = 0, bt = timing ? clock64() : 0;      // MSFM_BAND_DEBUG: phases of the loop below
+#define BACK_TICK(acc) do { if (timing) { const long long t1 = clock64(); acc += t1 - bt; bt = t1; } } while (0)
         if (threadIdx.x == 0) {
             mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
             fence_mbar_init();
@@ -374,106 +499,109 @@ band_cholesky_kernel(Params p) {
         __syncthreads();
         for (int q = 0; q < p.nrhs; ++q) {
             double* y = p.y + static_cast<size_t>(q) * Npad;
-            for (int i = threadIdx.x; i < ring * NB; i += kThreads) z[i] = 0.0;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                fence_proxy_async();
-                const int b = (R - 1) & 1;
+            const double* zfar = p.zfar + static_cast<size_t>(q) * Npad;
+            unsigned int* flags = p.flags + static_cast<size_t>(q) * (R + 1);
+            // diagonal tile of column c with its pivots and y_c -> buffer c % 3 (one thread)
+            auto fetch_diag = [&](int c) {
+                const int b = c % 3;
                 mbar_arrive_expect_tx(&bars[b], kTileBytes + 2 * NB * sizeof(double));
-                bulk_g2s(sDiag[b], tile_ptr(p, R - 1, R - 1), kTileBytes, &bars[b]);
-                bulk_g2s(sDinv + b * NB, p.dinv + static_cast<size_t>(R - 1) * NB, NB * sizeof(double), &bars[b]);
-                bulk_g2s(sY + b * NB, y + static_cast<size_t>(R - 1) * NB, NB * sizeof(double), &bars[b]);
-            }
-            for (int j = R - 1; j >= 0; --j) {
-                double* sx = sv + (j & 1) * NB;                   // x_j; the previous column's x stays in the other half
-                const double* sxp = sv + ((j + 1) & 1) * NB;
-                const int m_all = min(nbk, j);                    // tiles (j, j-1-w), w < m_all, take x_j
-                const int m_near = min(m_all, kWarps);
-                const int m_far = min(max(m_all - kWarps, 0), kWarps);
-                // (a)
-                double t[72];
-                if (warp < m_near) tile_fetch(tile_ptr(p, j, j - 1 - warp), lane, t);
-                if (threadIdx.x == 32) {                          // warp 1: idle during (c); warp 0 goes straight to the solve
+                bulk_g2s(sDiag[b], tile_ptr(p, c, c), kTileBytes, &bars[b]);
+                bulk_g2s(sDinv + b * NB, p.dinv + static_cast<size_t>(c) * NB, NB * sizeof(double), &bars[b]);
+                bulk_g2s(sY + b * NB, y + static_cast<size_t>(c) * NB, NB * sizeof(double), &bars[b]);
+            };
+            for (int i = threadIdx.x; i < ring * NB; i += kThreads) z[i] = 0.0;
+            for (int i = threadIdx.x; i < 2 * NB; i += kThreads) sZf[i] = 0.0;        // the last column has no helper sums
+            __syncthreads();
+            if (warp == 1) {
+                if (lane == 0) {
                     fence_proxy_async();
-                    if (j > 0) {
-                        const int b = (j - 1) & 1;
-                        mbar_arrive_expect_tx(&bars[b], kTileBytes + 2 * NB * sizeof(double));
-                        bulk_g2s(sDiag[b], tile_ptr(p, j - 1, j - 1), kTileBytes, &bars[b]);
-                        bulk_g2s(sDinv + b * NB, p.dinv + static_cast<size_t>(j - 1) * NB, NB * sizeof(double), &bars[b]);
-                        bulk_g2s(sY + b * NB, y + static_cast<size_t>(j - 1) * NB, NB * sizeof(double), &bars[b]);
-                    }
-                    if (m_far > 0) {
-                        mbar_arrive_expect_tx(&bars[2], m_far * kTileBytes);
-                        for (int f = 0; f < m_far; ++f)
-                            bulk_g2s(sFar + f * NB * NB, tile_ptr(p, j, j - 1 - kWarps - f), kTileBytes, &bars[2]);
-                    }
+                    fetch_diag(R - 1);
+                    if (R >= 2) fetch_diag(R - 2);
+                }
+                __syncwarp();
+                const int b = (R - 1) % 3;
+                mbar_wait(&bars[b], (dphase >> b) & 1u);          // the phase is consumed (toggled) when column R-1 is solved
+                invert_diag_blocks(sDiag[b], sDinv + b * NB, sW + b * (NB / 4) * 16, lane);
+            }
+            __syncthreads();
+            for (int j = R - 1; j >= 0; --j) {
+                const int jb = j % 3;
+                double* sx = sv + (j & 1) * NB;                   // x_j
+                const double* sxp = sv + ((j + 1) & 1) * NB;      // x_{j+1}
+                const int m_near = min(min(nbk, j), kNear);       // tiles (j, j - w), w = 1 .. m_near, take x_j here
+                // (a) loads that do not depend on x_j
+                double t[72];
+                if (warp >= 1 && warp <= m_near) tile_fetch(tile_ptr(p, j, j - warp), lane, t);
+                if (threadIdx.x == 7 * 32 && j >= 2) {
+                    fence_proxy_async();
+                    fetch_diag(j - 2);                             // two columns ahead: landed long before warp 1 inverts its blocks
                 }
                 // (c)
                 if (warp == 0) {
-                    // L_jj^T x = b from the last unknown up, b in registers (lane l: unknowns l and l + 32): x[cc] is final
-                    // once every later unknown has been eliminated from it; it travels by one shuffle, every lane removes it
-                    // from its own unknowns (row cc of L, read ahead of the chain)
                     const int l = lane;
-                    double* yj = y + static_cast<size_t>(j) * NB;
                     double* zj = z + (j % ring) * NB;
-                    mbar_wait(&bars[j & 1], (dphase >> (j & 1)) & 1u);
-                    const double* sYj = sY + (j & 1) * NB;
-                    double b0 = sYj[l] - zj[l];
-                    double b1 = l < NB - 32 ? sYj[32 + l] - zj[32 + l] : 0.0;
+                    const double* zf = sZf + (j & 1) * NB;
+                    BACK_TICK(bE);
+                    mbar_wait(&bars[jb], (dphase >> jb) & 1u);
+                    BACK_TICK(bA);
+                    const double* sYj = sY + jb * NB;
+                    double b0 = sYj[l] - (zj[l] + zf[l]);
+                    double b1 = l < NB - 32 ? sYj[32 + l] - (zj[32 + l] + zf[32 + l]) : 0.0;
                     zj[l] = 0.0;                                   // the slot now collects for column j - ring
                     if (l < NB - 32) zj[32 + l] = 0.0;
-                    const double* sL = sDiag[j & 1];
-                    const double* sI = sDinv + (j & 1) * NB;
-                    const double i0 = sI[l], i1 = l < NB - 32 ? sI[32 + l] : 0.0;
-#pragma unroll
-                    for (int cc = NB - 1; cc >= 32; --cc) {
-                        const double lr0 = sL[cc * NB + l], lr1 = l < cc - 32 ? sL[cc * NB + 32 + l] : 0.0;
-                        const double x = __shfl_sync(0xffffffffu, b1 * i1, cc - 32);
-                        if (l == cc - 32) b1 = x;
-                        else if (l < cc - 32) b1 -= lr1 * x;
-                        b0 -= lr0 * x;
-                    }
-#pragma unroll
-                    for (int cc = 31; cc >= 0; --cc) {
-                        const double lr0 = l < cc ? sL[cc * NB + l] : 0.0;
-                        const double x = __shfl_sync(0xffffffffu, b0 * i0, cc);
-                        if (l == cc) b0 = x;
-                        else if (l < cc) b0 -= lr0 * x;
-                    }
+                    solve_diag_blocked(sDiag[jb], sW + jb * (NB / 4) * 16, l, b0, b1);
                     sx[l] = b0;
                     if (l < NB - 32) sx[32 + l] = b1;
-                    yj[l] = b0;
-                    if (l < NB - 32) yj[32 + l] = b1;
-                } else if (j + 1 < R && nbk > 2 * kWarps) {
-                    // tiles (j+1, j+1-d), d = 2 kWarps + 1 .. nbk, against x_{j+1}: streamed, eight row pairs at a time
-                    for (int d = 2 * kWarps + warp; d <= nbk; d += kWarps - 1) {
-                        const int col = j + 1 - d;
-                        if (col < 0) break;
-                        double a, b, c;
-                        tile_dot_mem<24>(tile_ptr(p, j + 1, col), sxp, lane, a, b, c);
-                        tile_dot_commit(a, b, c, lane, z + (col % ring) * NB);
+                    BACK_TICK(bC);
+                } else if (warp == 5 && j > 0) {
+                    // the helpers' sums of column j - 1: complete when done[j-1] has counted every distance that reaches it
+                    const int c = j - 1;
+                    const int expect = max(min(nbk, R - 1 - c) - kNear, 0);
+                    double* zf = sZf + (c & 1) * NB;
+                    if (expect > 0) {
+                        if (lane == 0) wait_at_least(flags + c, static_cast<unsigned int>(expect));
+                        __syncwarp();
+                        zf[lane] = __ldcg(zfar + static_cast<size_t>(c) * NB + lane);
+                        if (lane < NB - 32) zf[32 + lane] = __ldcg(zfar + static_cast<size_t>(c) * NB + 32 + lane);
+                    } else {
+                        zf[lane] = 0.0;
+                        if (lane < NB - 32) zf[32 + lane] = 0.0;
                     }
+                } else if (warp == 6 && j + 1 < R) {
+                    // publish x_{j+1} (solved a column ago) under this column's solve: the helpers and the caller read it from
+                    // global memory; the fence and the release stay off the solver's path
+                    double* yp = y + static_cast<size_t>(j + 1) * NB;
+                    yp[lane] = sxp[lane];
+                    if (lane < NB - 32) yp[32 + lane] = sxp[32 + lane];
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) st_release(flags + R, static_cast<unsigned int>(R - 1 - j));
                 }
-                dphase ^= 1u << (j & 1);
                 __syncthreads();
                 // (d)
-                if (warp < m_near) {
+                if (warp >= 1 && warp <= m_near) {
                     double a, b, c;
                     tile_dot_regs(t, sx, lane, a, b, c);
-                    tile_dot_commit(a, b, c, lane, z + ((j - 1 - warp) % ring) * NB);
+                    tile_dot_commit(a, b, c, lane, z + ((j - warp) % ring) * NB);
                 }
-                if (m_far > 0) {
-                    if (warp < m_far) {
-                        mbar_wait(&bars[2], fphase);
-                        double a, b, c;
-                        tile_dot_mem<72>(sFar + warp * NB * NB, sx, lane, a, b, c);
-                        tile_dot_commit(a, b, c, lane, z + ((j - 1 - kWarps - warp) % ring) * NB);
-                    }
-                    fphase ^= 1u;
+                if (warp == 7 && j > 0) {
+                    // the next column's diagonal tile landed a column ago: invert its 4 x 4 blocks
+                    const int b = (j - 1) % 3;
+                    mbar_wait(&bars[b], (dphase >> b) & 1u);
+                    invert_diag_blocks(sDiag[b], sDinv + b * NB, sW + b * (NB / 4) * 16, lane);
                 }
-                __syncthreads();                                  // z, the far tiles and the diagonal buffer are free again
+                dphase ^= 1u << jb;                               // this column's diagonal buffer: phase consumed
+                __syncthreads();                                  // z, sZf, sx and the diagonal buffer are free again
+                if (warp == 0) BACK_TICK(bD);
             }
+            if (warp == 6) {                                      // x_0
+                y[lane] = sv[lane];
+                if (lane < NB - 32) y[32 + lane] = sv[32 + lane];
+            }
+            __syncthreads();
         }
+        if (timing) { p.dbg[5] = bA; p.dbg[6] = bC; p.dbg[7] = bD; p.dbg[8] = bE; }
+#undef BACK_TICK
     }
     if (timing) {
         const long long t1 = clock64();
@@ -524,6 +652,8 @@ struct BandSolver {
     int nf = 0, bw = 0, R = 0, nbk = 0, grid = 0;
     int32_t* d_pos = nullptr;
     double *tiles = nullptr, *y = nullptr, *dinv = nullptr;
+    double* zfar = nullptr;         // [3][R * NB] doubles, then the back substitution's flags [3][R + 1] u32 (one allocation, one memset)
+    size_t zfar_bytes = 0;
     int32_t* d_info = nullptr;      // [0] status, [2] the grid barrier counter
     long long* d_dbg = nullptr;
     size_t tile_bytes = 0;
@@ -551,17 +681,15 @@ BandSolver* band_create(int nf, const std::vector<int32_t>& blk_row, const std::
         const int hi = std::max(pa, pb) * 6 + 5, lo = std::min(pa, pb) * 6;
         B->nbk = std::max(B->nbk, hi / band::NB - lo / band::NB);
     }
-    if (B->nbk + 1 > band::NB) {          // the back substitution keeps nbk + 1 pending column sums in one tile of shared memory
-        delete B;
-        return nullptr;
-    }
     B->tile_bytes = static_cast<size_t>(B->R) * (B->nbk + 1) * band::NB * band::NB * sizeof(double);
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&B->d_pos), static_cast<size_t>(nf) * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->tiles), B->tile_bytes);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->y), 3 * static_cast<size_t>(B->R) * band::NB * sizeof(double));
+    B->zfar_bytes = 3 * static_cast<size_t>(B->R) * band::NB * sizeof(double) + 3 * static_cast<size_t>(B->R + 1) * sizeof(unsigned int);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->zfar), B->zfar_bytes);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->dinv), static_cast<size_t>(B->R) * band::NB * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&B->d_info), 4 * sizeof(int32_t));
-    if (e == cudaSuccess && getenv("MSFM_BAND_DEBUG")) e = cudaMalloc(reinterpret_cast<void**>(&B->d_dbg), 8 * sizeof(long long));
+    if (e == cudaSuccess && getenv("MSFM_BAND_DEBUG")) e = cudaMalloc(reinterpret_cast<void**>(&B->d_dbg), 16 * sizeof(long long));
     if (e == cudaSuccess) e = cudaMemcpy(B->d_pos, pos.data(), static_cast<size_t>(nf) * sizeof(int32_t), cudaMemcpyHostToDevice);
     int per_sm = 0;
     if (e == cudaSuccess) e = cudaFuncSetAttribute(band::band_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(band::kDynSmem));
@@ -569,7 +697,7 @@ BandSolver* band_create(int nf, const std::vector<int32_t>& blk_row, const std::
     if (e == cudaSuccess && per_sm < 1) e = cudaErrorLaunchOutOfResources;
     if (e != cudaSuccess) {
         *err = e;
-        cudaFree(B->d_pos); cudaFree(B->tiles); cudaFree(B->y); cudaFree(B->dinv); cudaFree(B->d_info);
+        cudaFree(B->d_pos); cudaFree(B->tiles); cudaFree(B->y); cudaFree(B->dinv); cudaFree(B->zfar); cudaFree(B->d_info);
         delete B;
         return nullptr;
     }
@@ -581,13 +709,14 @@ BandSolver* band_create(int nf, const std::vector<int32_t>& blk_row, const std::
 void band_destroy(BandSolver* B) {
     if (!B) return;
     if (B->d_dbg) {
-        long long h[8] = {0};
+        long long h[16] = {0};
         cudaMemcpy(h, B->d_dbg, sizeof h, cudaMemcpyDeviceToHost);
         fprintf(stderr, "band Cholesky, last solve, CTA 0 cycles: D %lld  P %lld  U %lld  barriers %lld  back substitution %lld  (%d tile columns)\n",
                 h[0], h[1], h[2], h[3], h[4], B->R);
+        fprintf(stderr, "  back substitution, thread 0: wait for the diagonal tile %lld  solve %lld  barrier + products + barrier %lld  loop head %lld\n", h[5], h[6], h[7], h[8]);
         cudaFree(B->d_dbg);
     }
-    cudaFree(B->d_pos); cudaFree(B->tiles); cudaFree(B->y); cudaFree(B->dinv); cudaFree(B->d_info);
+    cudaFree(B->d_pos); cudaFree(B->tiles); cudaFree(B->y); cudaFree(B->dinv); cudaFree(B->zfar); cudaFree(B->d_info);
     delete B;
 }
 void band_info(const BandSolver* B, int32_t out[4]) { out[0] = B->bw; out[1] = band::NB; out[2] = B->R; out[3] = B->nbk; }
@@ -597,10 +726,11 @@ int32_t* band_dev_info(BandSolver* B) { return B->d_info; }
 // camera order; overwritten by the solutions).  Asynchronous on st; *band_dev_info != 0 afterwards = not positive definite.
 cudaError_t band_factor_solve(BandSolver* B, const ba::Problem& P, double inv_radius, double* rhs, int nrhs, cudaStream_t st) {
     band::Params p;
-    p.tiles = B->tiles; p.y = B->y; p.dinv = B->dinv; p.info = B->d_info; p.bar = reinterpret_cast<unsigned int*>(B->d_info + 2); p.dbg = B->d_dbg; p.R = B->R; p.nbk = B->nbk; p.nrhs = nrhs;
+    p.tiles = B->tiles; p.y = B->y; p.dinv = B->dinv; p.info = B->d_info; p.bar = reinterpret_cast<unsigned int*>(B->d_info + 2); p.dbg = B->d_dbg; p.zfar = B->zfar; p.flags = reinterpret_cast<unsigned int*>(B->zfar + 3 * static_cast<size_t>(B->R) * band::NB); p.R = B->R; p.nbk = B->nbk; p.nrhs = nrhs;
     const int N = 6 * B->nf, Npad = B->R * band::NB;
     cudaError_t e = cudaMemsetAsync(B->tiles, 0, B->tile_bytes, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(B->y, 0, 3 * static_cast<size_t>(Npad) * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(B->zfar, 0, B->zfar_bytes, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(B->d_info, 0, 4 * sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
     const int tot = P.n_blocks * 36;

@@ -456,14 +456,15 @@ __host__ __device__ inline FusedSmem fused_smem_layout(bool focal) {
 template <bool kFocal>
 __global__ void __launch_bounds__(256)
 long_track_prepass_kernel(Problem P, double inv_radius) {
-    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    // warp index / track bounds through a shuffle: provably warp-uniform, so the reductions' shuffles stay plain SHFL (backsub_kernel)
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
     constexpr int kRec = kFocal ? 15 : 9;
     double cost_local = 0.0, gpmax_local = 0.0;
     double ff[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int li = blockIdx.x * wpb + warp; li < P.n_long; li += gridDim.x * wpb) {
         const int d = P.first_long + li;
         const int p = __ldg(P.pt_order + d);
-        const int beg = __ldg(P.pt_start + d), end = __ldg(P.pt_start + d + 1);
+        const int beg = __shfl_sync(0xffffffffu, __ldg(P.pt_start + d), 0), end = __shfl_sync(0xffffffffu, __ldg(P.pt_start + d + 1), 0);
         const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
         double Vinv[6], gp[3], Wf[6], fs[4], cl = 0.0;
         LaneObs A;
@@ -921,9 +922,12 @@ backsub_kernel(Problem P, int first_point, double inv_radius, const double* __re
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     double acc_model = 0.0, acc_dp = 0.0, acc_x = 0.0;
-    for (int d = first_point + blockIdx.x * wpb + (threadIdx.x >> 5); d < P.n_pts; d += gridDim.x * wpb) {
+    // warp index and track bounds go through a shuffle so that the compiler knows they are uniform across the warp: otherwise every
+    // shuffle of the reductions below is compiled as a convergence barrier (WARPSYNC.COLLECTIVE), one at a time
+    const int wid = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    for (int d = first_point + blockIdx.x * wpb + wid; d < P.n_pts; d += gridDim.x * wpb) {
         const int p = P.pt_order[d];
-        const int beg = P.pt_start[d], end = P.pt_start[d + 1];
+        const int beg = __shfl_sync(0xffffffffu, P.pt_start[d], 0), end = __shfl_sync(0xffffffffu, P.pt_start[d + 1], 0);
         const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
         if (beg == end) {
             if (lane == 0) { pts_new[3 * p] = X[0]; pts_new[3 * p + 1] = X[1]; pts_new[3 * p + 2] = X[2]; }

@@ -199,7 +199,7 @@ def bench_ba(ctx, args, rank, world, dist, dev, peaks, n_cams=None, n_pts=None, 
         with open(tpath) as f:
             tj = json.load(f)
         ent = tj.get(f"{n_cams}x{n_pts}")
-        if ent:
+        if ent and world == 1:          # the capture is of one GPU holding the whole problem
             traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
     ach = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None
     out = {"workload": f"BA {len(P['cams'])} cams / {len(P['pts'])} points / {n_obs_total} observations, points sharded over {world} GPU(s)",
@@ -378,6 +378,82 @@ def run_reference_arm(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------- our arm
+def _two_view(rng, n_in, n_out, noise=0.4):
+    """Keypoints of two pinhole views (NEU intrinsics) of random 3-D points: n_in true correspondences with pixel noise, n_out
+    random wrong ones; matches (queryIdx, trainIdx) in random order (same generator as tests/test_verify_gpu.py)."""
+    K = np.array([[1449.2752980237, 0, 1080.0], [0, 1449.2752980237, 720.0], [0, 0, 1]])
+    X = np.c_[rng.uniform(-4, 4, n_in), rng.uniform(-3, 3, n_in), rng.uniform(6, 14, n_in)]
+    ang = rng.uniform(0.1, 0.25)
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    t = np.array([-1.5, 0.1, 0.3]) * rng.uniform(0.7, 1.3)
+    x1 = (K @ X.T).T
+    x1 = x1[:, :2] / x1[:, 2:]
+    x2 = (K @ (R @ X.T + t[:, None])).T
+    x2 = x2[:, :2] / x2[:, 2:]
+    x1 = x1 + rng.normal(0, noise, x1.shape)
+    x2 = x2 + rng.normal(0, noise, x2.shape)
+    o1 = np.c_[rng.uniform(0, 2160, n_out), rng.uniform(0, 1440, n_out)]
+    o2 = np.c_[rng.uniform(0, 2160, n_out), rng.uniform(0, 1440, n_out)]
+    n = n_in + n_out
+    perm1, perm2 = rng.permutation(n), rng.permutation(n)
+    kp1 = np.zeros((n, 2), np.float32)
+    kp2 = np.zeros((n, 2), np.float32)
+    kp1[perm1] = np.r_[x1, o1]
+    kp2[perm2] = np.r_[x2, o2]
+    order = rng.permutation(n)
+    return kp1, kp2, np.c_[perm1[order], perm2[order]].astype(np.int32), order < n_in
+
+
+def bench_verify_geometric(ctx, n_pairs=8128, n_scenes=64, n_in=534, n_out=229, cpu_pairs=64):
+    """SURVEY 8f-1: FeatureUtils::FilterMatches (cv::findFundamentalMat FM_RANSAC 3.0 / 0.99, FeatureUtils.cpp:176-206) over the
+    matches of every pair of the headline workload's size (8128 pairs x ~763 matches, 70 % true correspondences), batched on
+    the device through the host-pointer C-ABI call vs cv2.findFundamentalMat per pair on the host cores."""
+    import cv2
+    rng = np.random.default_rng(99)
+    scenes = [_two_view(rng, n_in, n_out) for _ in range(n_scenes)]
+    for k, (kp1, kp2, _m, _t) in enumerate(scenes):
+        ctx.upload_keypoints(200000 + 2 * k, kp1)
+        ctx.upload_keypoints(200001 + 2 * k, kp2)
+    pairs = [(200000 + 2 * (i % n_scenes), 200001 + 2 * (i % n_scenes)) for i in range(n_pairs)]
+    per = n_in + n_out
+    offs = np.arange(n_pairs + 1, dtype=np.int64) * per
+    matches = np.concatenate([scenes[i % n_scenes][2] for i in range(n_pairs)])
+    ctx.verify_pairs(pairs[:64], offs[:65], matches[:64 * per])                      # warm-up
+    ctx.prof_enable(True)
+    ctx.prof_reset()
+    t0 = time.perf_counter()
+    mask, counts = ctx.verify_pairs(pairs, offs, matches)
+    wall = time.perf_counter() - t0
+    prof = ctx.prof_read()
+    ctx.prof_enable(False)
+    kern_ms = prof.get("verify", {}).get("ms", 0.0)
+    # host reference on a sample: the call the reference makes, all cv2 threads
+    t0 = time.perf_counter()
+    agree, kept_of_cv, cv_in = [], 0, 0
+    n_cpu = min(cpu_pairs, n_scenes)
+    for k in range(n_cpu):
+        kp1, kp2, m, _truth = scenes[k]
+        _F, cm = cv2.findFundamentalMat(kp1[m[:, 0]], kp2[m[:, 1]], cv2.FM_RANSAC, 3.0, 0.99)
+        cm = cm.ravel().astype(bool) if cm is not None else np.zeros(per, bool)
+        got = mask[k * per:(k + 1) * per]
+        agree.append(float((got == cm).mean()))
+        kept_of_cv += int((got & cm).sum())
+        cv_in += int(cm.sum())
+    cpu_wall = time.perf_counter() - t0
+    truth_all = np.concatenate([scenes[i % n_scenes][3] for i in range(n_pairs)])
+    return {"workload": f"F-matrix RANSAC (3.0 px, 0.99) over {n_pairs} pairs x {per} matches ({n_in} true + {n_out} wrong), "
+                        f"{n_scenes} distinct two-view scenes",
+            "pairs_per_s": n_pairs / wall, "wall_s": wall, "kernel_ms": kern_ms,
+            "what": "msfm_verify_pairs with HOST match lists: H2D of the matches, one CTA per pair, D2H of the masks",
+            "h2d_bytes": int(matches.nbytes + offs.nbytes), "d2h_bytes": int(mask.size + counts.nbytes),
+            "cpu": {"pairs_per_s": n_cpu / cpu_wall, "sample_pairs": n_cpu, "cores": os.cpu_count() or 1,
+                    "kind": "reference (cv2.findFundamentalMat per pair)"},
+            "parity": {"min_agreement_with_cv2": min(agree), "mean_agreement_with_cv2": sum(agree) / len(agree),
+                       "cv2_inliers_kept": kept_of_cv / max(1, cv_in),
+                       "true_correspondences_kept": float(mask[truth_all].mean()),
+                       "wrong_matches_kept": float(mask[~truth_all].mean())}}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):

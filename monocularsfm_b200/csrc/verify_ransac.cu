@@ -325,6 +325,7 @@ ransac_pairs_kernel(const KpDev* __restrict__ kps, const int32_t* __restrict__ p
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                __syncwarp();                                          // every lane has read S.cnt[h] (loop head) before lane 0 overwrites it
                 if (lane == 0) S.cnt[h] = c;
             }
             __syncthreads();

@@ -28,3 +28,29 @@ def test_final_bench_line_carries_the_contract_keys():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
+
+
+def test_round2_evidence_is_consistent():
+    """k2_traffic.json is the sum the committed ncu raw page of the final K2 holds; the round-2 bench lines carry the contract keys,
+    the K2 roofline object and the sharded runs' per-rank times."""
+    import csv
+    rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r02_k2_final_ncu_raw.csv"), newline="")))
+    hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr, units, vals = rows[hi], rows[hi + 1], rows[hi + 2]
+    d = dict(zip(hdr, vals))
+    u = dict(zip(hdr, units))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = sum(float(d[k]) * scale[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    want = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))["1329x542000"]
+    assert "fused_linearize_kernel" in d["Kernel Name"]
+    assert abs(total - want["dram_bytes_per_launch"]) <= 1e-6 * total and total < 2 * 133405246        # <= 2x the algorithmic bytes
+    line = json.loads([l for l in open(os.path.join(ROOT, "profiles", "r02_bench_final.json")) if l.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in line, k
+    k2 = line["roofline"]["k2"]
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(k2) and k2["unit"] == "GB/s"
+    assert line["verify"]["bit_exact"] is True and line["ba_large"]["lm"]["termination"] == 0
+    for n in (2, 4, 8):
+        ln = json.loads([l for l in open(os.path.join(ROOT, "profiles", f"r02_bench_n{n}_sharded_configs2.json")) if l.startswith("{")][-1])
+        assert ln["n_gpus"] == n and len(ln["config"]["per_rank_ms_per_step"]) == n and "1329 images" in ln["config"]["workload"]
+        assert ln["ba_large"]["allreduce_ms"] > 0 and ln["ba_large"]["allreduce_message_bytes"] < 13e6

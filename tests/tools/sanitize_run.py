@@ -51,6 +51,26 @@ def main():
     s3 = ba.solve()
     assert s3["termination"] == 0 and ba.solver_info()["kind"].startswith("band"), (s3, ba.solver_info())
     ba.close()
+    # a WIDE band (ring with tracks spanning up to 64 cameras, the generator of bench.py): 16 tiles below the diagonal, so the
+    # back substitution runs on CTA 0 plus 12 helper CTAs (flags, fp64 reductions into zfar)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+    import bench
+    P = bench.make_ba_problem(400, 3000, 9.2, 7)
+    ba = ctx.ba_create(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"])
+    S, rhs, _, _ = ba.linearize(1e-4)
+    dc, st = ba.solve_system(1e-4)
+    info = ba.solver_info()
+    assert st == 0 and info["kind"].startswith("band") and info["band_tiles"] > 4, info
+    assert np.abs(S @ dc - rhs).max() <= 1e-6 * np.abs(rhs).max()
+    ba.close()
+    # batched geometric verification
+    k1 = rng.uniform(0, 1000, (300, 2)).astype(np.float32)
+    k2 = (k1 + np.float32(5.0)).astype(np.float32)
+    ctx.upload_keypoints(900, k1)
+    ctx.upload_keypoints(901, k2)
+    mm = np.c_[np.arange(300), np.arange(300)].astype(np.int32)
+    mask, counts = ctx.verify_pairs([(900, 901)], [0, 300], mm)
+    assert counts[0] == mask.sum()
     ctx.close()
     print("sanitize workload ok", len(mt), "matches, BA", s["iterations"], "iterations")
 

@@ -187,6 +187,23 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int& ta
     }
     __syncthreads();
 }
+// The two halves of the same barrier, for a CTA that has work between its arrival and the point where it needs the others
+// (CTA 0: the diagonal chain).  target counts as in grid_barrier.
+__device__ __forceinline__ void grid_arrive(unsigned int* ctr, unsigned int& target, unsigned int nblk) {
+    target += nblk;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+    }
+}
+__device__ __forceinline__ void grid_wait(unsigned int* ctr, unsigned int target) {
+    if (threadIdx.x == 0) {
+        while (*reinterpret_cast<volatile unsigned int*>(ctr) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
 
 // ---- z += T^T x for one 48 x 48 row-major tile by one warp (back substitution).  The tile is walked flat, 32 consecutive
 // doubles per step (72 steps), so every load instruction of the warp reads 256 contiguous bytes; lane l meets the columns
@@ -372,13 +389,29 @@ band_cholesky_kernel(Params p) {
             __syncthreads();
         }
         BAND_TICK(tP);
-        grid_barrier(p.bar, bar_target, nblk);
-        BAND_TICK(tS);
         // ---- U: tasks 0 .. m(m+1)/2 - 1 = tiles (I, K), j < K <= I <= j + m; the last task = right-hand side updates.
-        //      Task 0 is the next diagonal tile (j+1, j+1): CTA 0 factors it right after updating it (D of the next column runs
-        //      under the other CTAs' updates).
+        //      Task 0 is the next diagonal tile (j+1, j+1) -= L_{j+1,j} L_{j+1,j}^T: it needs only the panel tile CTA 0 has just
+        //      solved itself, so CTA 0 arrives at the barrier between P and U without waiting, updates and factors the next
+        //      diagonal tile (D of column j+1) while the other CTAs are still in P, the barrier and their updates, and only then
+        //      waits for the others' panel tiles (for its further update tasks, when the grid is smaller than the task list).
         const int ntile = m * (m + 1) / 2;
-        for (int t = bid; t <= ntile; t += nblk) {
+        if (bid == 0) {
+            grid_arrive(p.bar, bar_target, nblk);
+            if (m > 0) {
+                tile_update(tile_ptr(p, j + 1, j), tile_ptr(p, j + 1, j), tile_ptr(p, j + 1, j + 1), sA, sB);
+                BAND_TICK(tU);
+                load_tile(tile_ptr(p, j + 1, j + 1), sA);            // written by this CTA just above
+                __syncthreads();
+                diag_factor(sA, sInv, tile_ptr(p, j + 1, j + 1), p.dinv + static_cast<size_t>(j + 1) * NB, p.info);
+                __syncthreads();
+                BAND_TICK(tD);
+            }
+            grid_wait(p.bar, bar_target);
+        } else {
+            grid_barrier(p.bar, bar_target, nblk);
+        }
+        BAND_TICK(tS);
+        for (int t = bid == 0 ? nblk : bid; t <= ntile; t += nblk) {
             if (t < ntile) {
                 int a = static_cast<int>((sqrtf(8.0f * static_cast<float>(t) + 1.0f) - 1.0f) * 0.5f);
                 while (a * (a + 1) / 2 > t) --a;
@@ -386,14 +419,6 @@ band_cholesky_kernel(Params p) {
                 const int b = t - a * (a + 1) / 2;           // 0 <= b <= a < m
                 const int I = j + 1 + a, K = j + 1 + b;
                 tile_update(tile_ptr(p, I, j), tile_ptr(p, K, j), tile_ptr(p, I, K), sA, sB);
-                if (t == 0) {
-                    BAND_TICK(tU);
-                    load_tile(tile_ptr(p, j + 1, j + 1), sA);        // written by this CTA just above
-                    __syncthreads();
-                    diag_factor(sA, sInv, tile_ptr(p, j + 1, j + 1), p.dinv + static_cast<size_t>(j + 1) * NB, p.info);
-                    __syncthreads();
-                    BAND_TICK(tD);
-                }
             } else if (m > 0) {
                 // y_I -= L_Ij y_j for the m tile rows below: thread = (tile row a, row r), the 48 products of a row in flight together
                 for (int q = 0; q < p.nrhs; ++q) {

@@ -345,10 +345,13 @@ band_cholesky_kernel(Params p) {
 #define BAND_TICK(acc) do { if (timing) { const long long t1 = clock64(); acc += t1 - t0; t0 = t1; } } while (0)
     if (timing) t0 = clock64();
 
+    bool sA_has_L = false;                                  // CTA 0: sA / sInv still hold the factor of the current diagonal tile
     if (bid == 0) {
         load_tile(tile_ptr(p, 0, 0), sA);
         __syncthreads();
         diag_factor(sA, sInv, tile_ptr(p, 0, 0), p.dinv, p.info);
+        __syncthreads();
+        sA_has_L = true;
     }
     BAND_TICK(tD);
     grid_barrier(p.bar, bar_target, nblk);
@@ -356,9 +359,38 @@ band_cholesky_kernel(Params p) {
     for (int j = 0; j < R; ++j) {
         const int m = min(nbk, R - 1 - j);                 // tile rows below the diagonal in this column
         // ---- P: tasks 0 .. m-1 = tiles (j + 1 + t, j); task m = the right-hand sides
+        // CTA 0's chain P(j+1, j) -> update of (j+1, j+1) -> D(j+1) is the critical path of the whole factorisation (every other
+        // CTA waits for it at the next barrier), so it keeps its data on chip: L_jj is still in sA from D(j) (no reload), the next
+        // diagonal tile is fetched into registers before the solve, the update reads the freshly solved panel tile from shared
+        // memory and hands its result to D(j+1) in shared memory (round 2's first version went through global memory three
+        // times here: ~4k of the 37k cycles of a column).  Only when the grid is at least as large as the task lists.
+        const bool chain = bid == 0 && m > 0 && nblk > m * (m + 1) / 2;
+        double cnext[3][3];                                          // thread (ty, tx): its 3 x 3 block of tile (j+1, j+1)
         for (int t = bid; t <= m; t += nblk) {
-            load_tile_scaled(tile_ptr(p, j, j), p.dinv + static_cast<size_t>(j) * NB, sB);     // L_jj, row c scaled by 1 / L_cc
-            if (threadIdx.x < NB) sInv[threadIdx.x] = p.dinv[static_cast<size_t>(j) * NB + threadIdx.x];
+            if (chain && t == 0 && sA_has_L) {
+                for (int i = threadIdx.x; i < NB * NB; i += kThreads) {
+                    const int r = i / NB, c = i - r * NB;
+                    sB[r * kLd + c] = sA[r * kLd + c] * sInv[r];
+                }
+                const double* gC = tile_ptr(p, j + 1, j + 1);
+                const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 3; ++jj) cnext[i][jj] = gC[(3 * ty + i) * NB + 3 * tx + jj];
+                __syncthreads();                                     // sA (L_jj) has been read: the panel tile may replace it
+            } else {
+                load_tile_scaled(tile_ptr(p, j, j), p.dinv + static_cast<size_t>(j) * NB, sB);     // L_jj, row c scaled by 1 / L_cc
+                if (threadIdx.x < NB) sInv[threadIdx.x] = p.dinv[static_cast<size_t>(j) * NB + threadIdx.x];
+                if (chain && t == 0) {
+                    const double* gC = tile_ptr(p, j + 1, j + 1);
+                    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int jj = 0; jj < 3; ++jj) cnext[i][jj] = gC[(3 * ty + i) * NB + 3 * tx + jj];
+                }
+            }
             if (t < m) {
                 double* g = tile_ptr(p, j + 1 + t, j);
                 // the tile through shared memory: coalesced global access, one row per thread afterwards
@@ -397,13 +429,37 @@ band_cholesky_kernel(Params p) {
         const int ntile = m * (m + 1) / 2;
         if (bid == 0) {
             grid_arrive(p.bar, bar_target, nblk);
-            if (m > 0) {
+            if (chain) {
+                // sA still holds the panel tile X = L_{j+1,j} this CTA has just solved (row-major, stride kLd): C -= X X^T
+                const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+                double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll 4
+                for (int k = 0; k < NB; ++k) {
+                    const double a0 = sA[(3 * ty) * kLd + k], a1 = sA[(3 * ty + 1) * kLd + k], a2 = sA[(3 * ty + 2) * kLd + k];
+                    const double b0 = sA[(3 * tx) * kLd + k], b1 = sA[(3 * tx + 1) * kLd + k], b2 = sA[(3 * tx + 2) * kLd + k];
+                    acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[0][2] += a0 * b2;
+                    acc[1][0] += a1 * b0; acc[1][1] += a1 * b1; acc[1][2] += a1 * b2;
+                    acc[2][0] += a2 * b0; acc[2][1] += a2 * b1; acc[2][2] += a2 * b2;
+                }
+                __syncthreads();                                     // every thread has read X
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 3; ++jj) sA[(3 * ty + i) * kLd + 3 * tx + jj] = cnext[i][jj] - acc[i][jj];
+                __syncthreads();
+                BAND_TICK(tU);
+                diag_factor(sA, sInv, tile_ptr(p, j + 1, j + 1), p.dinv + static_cast<size_t>(j + 1) * NB, p.info);
+                __syncthreads();
+                sA_has_L = true;
+                BAND_TICK(tD);
+            } else if (m > 0) {
                 tile_update(tile_ptr(p, j + 1, j), tile_ptr(p, j + 1, j), tile_ptr(p, j + 1, j + 1), sA, sB);
                 BAND_TICK(tU);
                 load_tile(tile_ptr(p, j + 1, j + 1), sA);            // written by this CTA just above
                 __syncthreads();
                 diag_factor(sA, sInv, tile_ptr(p, j + 1, j + 1), p.dinv + static_cast<size_t>(j + 1) * NB, p.info);
                 __syncthreads();
+                sA_has_L = true;
                 BAND_TICK(tD);
             }
             grid_wait(p.bar, bar_target);
@@ -419,6 +475,7 @@ band_cholesky_kernel(Params p) {
                 const int b = t - a * (a + 1) / 2;           // 0 <= b <= a < m
                 const int I = j + 1 + a, K = j + 1 + b;
                 tile_update(tile_ptr(p, I, j), tile_ptr(p, K, j), tile_ptr(p, I, K), sA, sB);
+                sA_has_L = false;
             } else if (m > 0) {
                 // y_I -= L_Ij y_j for the m tile rows below: thread = (tile row a, row r), the 48 products of a row in flight together
                 for (int q = 0; q < p.nrhs; ++q) {

@@ -233,14 +233,43 @@ def bench_ba(ctx, args, rank, world, dist, dev, peaks, n_cams=None, n_pts=None, 
     # problem, LM solve, D2H of the parameters
     t0 = time.perf_counter()
     ba2 = ctx.ba_create(L["cams"], L["pts"], L["obs_uv"], L["obs_cam"], L["obs_pt"], L["cam_const"], L["fx"], L["fy"])
+    create_s = time.perf_counter() - t0
+    up0 = ba2.last_upload()
     s2 = ba2.solve()
     ba2.get_params()
     e2e_s = time.perf_counter() - t0
-    ba2.close()
     out["e2e"] = {"wall_s": e2e_s, "observations_per_s_per_iteration": n_obs_total * s2["iterations"] / e2e_s,
-                  "h2d_bytes": int(L["cams"].nbytes + L["pts"].nbytes + L["obs_uv"].nbytes + 2 * L["obs_cam"].nbytes),
+                  "create_s": create_s, "h2d_bytes": up0["h2d_bytes"],
                   "d2h_bytes": int(L["cams"].nbytes + L["pts"].nbytes),
                   "what": "msfm_ba_create (host structure analysis + upload) + msfm_ba_solve + msfm_ba_get_params"}
+    # the next Optimize calls on the SAME object (msfm_ba_update; MapBuilder keeps one optimizer, MapBuilder.cpp:92):
+    # (a) the same map with the start values again — structure kept, only values travel; (b) a changed map (the last 2 % of the
+    # points dropped) — analysed again into the same device arena
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    reused = ba2.update(L["cams"], L["pts"], L["obs_uv"], L["obs_cam"], L["obs_pt"], L["cam_const"], L["fx"], L["fy"])
+    upd_s = time.perf_counter() - t0
+    up1 = ba2.last_upload()
+    s3 = ba2.solve()
+    ba2.get_params()
+    same_s = time.perf_counter() - t0
+    out["e2e"]["next_call_same_map"] = {"wall_s": same_s, "update_s": upd_s, "structure_reused": bool(reused), "h2d_bytes": up1["h2d_bytes"],
+                                        "iterations": s3["iterations"], "final_cost_rel_diff": abs(s3["final_cost"] - s2["final_cost"]) / s2["final_cost"]}
+    keep_pts = max(1, int(len(L["pts"]) * 0.98))
+    keep_obs = int(np.searchsorted(L["obs_pt"], keep_pts, side="left"))
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    reused = ba2.update(L["cams"], L["pts"][:keep_pts], L["obs_uv"][:keep_obs], L["obs_cam"][:keep_obs], L["obs_pt"][:keep_obs], L["cam_const"],
+                        L["fx"], L["fy"])
+    upd_s = time.perf_counter() - t0
+    up2 = ba2.last_upload()
+    s4 = ba2.solve()
+    ba2.get_params()
+    out["e2e"]["next_call_changed_map"] = {"wall_s": time.perf_counter() - t0, "update_s": upd_s, "structure_reused": bool(reused),
+                                           "h2d_bytes": up2["h2d_bytes"], "iterations": s4["iterations"], "termination": s4["termination"]}
+    ba2.close()
     if rank == 0 and world == 1 and args.cpu_pairs != 0:
         from oracle import ba_oracle as bo
         lib = bo.c_oracle()

@@ -257,6 +257,22 @@ void msfm_ba_default_options(msfm_ba_options* opt, int32_t n_cams);
  * (msfm_comm_init) every rank passes ALL cameras and its own share of the points/observations. */
 int  msfm_ba_create(msfm_ctx* ctx, const msfm_ba_problem* prob, msfm_ba** out);
 void msfm_ba_destroy(msfm_ba* ba);
+/* The next problem on the same object.  MapBuilder calls Optimize again and again on a map that changes a little between
+ * the calls (LocalBA after almost every registered image, GlobalBA in rounds: src/Reconstruction/MapBuilder.cpp:189-215,
+ * 576-625), and the reference rebuilds the whole ceres::Problem every time (CeresBundleOptimizer.cpp:206-260).  Here the
+ * device problem persists:
+ *   - same sparsity pattern (n_cams, n_pts, n_obs, flags, cam_const, obs_cam, obs_pt all equal — compared exactly): only
+ *     the VALUES travel (cams, pts, obs_uv, fx, fy); device order, tiles, block structure, solver set-up and every
+ *     allocation are kept.  *reused = 1.
+ *   - anything else: the structure is analysed again INTO the same object; its device arena is re-used when it is large
+ *     enough (grown by 25 % otherwise), so a map that grows does not pay cudaMalloc / cudaFree per call.  *reused = 0.
+ * With a communicator attached every rank must call it; the ranks agree on the path with one 8-byte all-reduce.
+ * After an error other than MSFM_E_INVALID the object can only be destroyed.  reused may be NULL. */
+int  msfm_ba_update(msfm_ba* ba, const msfm_ba_problem* prob, int32_t* reused);
+/* sizes[0..2] = n_cams, n_pts, n_obs of the resident problem (the array lengths msfm_ba_get_params / _filter_stats expect). */
+int  msfm_ba_sizes(msfm_ba* ba, int64_t sizes[3]);
+/* Host -> device traffic of the last msfm_ba_create / msfm_ba_update: info[0] bytes, info[1] = 1 if the structure was kept. */
+int  msfm_ba_last_upload(msfm_ba* ba, int64_t info[2]);
 /* Structure of the problem as the device sees it: info[0] free cameras F, [1] non-empty 6x6 blocks of the upper block
  * triangle of the reduced camera system (the fp32 part of the all-reduce message), [2] point tiles, [3] max cameras per
  * tile, [4] bytes of the system buffer (= the all-reduce message + 16), [5] shared memory per CTA of the linearisation

@@ -119,6 +119,9 @@ def load_library():
         "msfm_ba_default_options": (None, [P(BAOptions), i32]),
         "msfm_ba_create": (C.c_int, [vp, P(BAProblemC), P(vp)]),
         "msfm_ba_destroy": (None, [vp]),
+        "msfm_ba_update": (C.c_int, [vp, P(BAProblemC), P(i32)]),
+        "msfm_ba_last_upload": (C.c_int, [vp, P(i64)]),
+        "msfm_ba_sizes": (C.c_int, [vp, P(i64)]),
         "msfm_ba_structure": (C.c_int, [vp, P(i32)]),
         "msfm_ba_get_params": (C.c_int, [vp, vp, vp]),
         "msfm_ba_set_params": (C.c_int, [vp, vp, vp]),
@@ -328,6 +331,12 @@ class BAProblem:
     def __init__(self, ctx: Context, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, refine_focal=False):
         self.ctx = ctx
         self.lib = ctx.lib
+        pr, keep = self._describe(cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, refine_focal)
+        h = C.c_void_p()
+        ctx._check(self.lib.msfm_ba_create(ctx.h, C.byref(pr), C.byref(h)))
+        self.h = h
+
+    def _describe(self, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, refine_focal):
         cams = np.ascontiguousarray(cams, np.float64).reshape(-1, 6)
         pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
         obs_uv = np.ascontiguousarray(obs_uv, np.float64).reshape(-1, 2)
@@ -339,9 +348,20 @@ class BAProblem:
         self.refine_focal = bool(refine_focal)
         pr = BAProblemC(self.n_cams, self.n_pts, self.n_obs, 1 if refine_focal else 0, float(fx), float(fy), _ptr(cams), _ptr(pts),
                         _ptr(obs_uv), _ptr(obs_cam), _ptr(obs_pt), _ptr(cam_const))
-        h = C.c_void_p()
-        ctx._check(self.lib.msfm_ba_create(ctx.h, C.byref(pr), C.byref(h)))
-        self.h = h
+        return pr, (cams, pts, obs_uv, obs_cam, obs_pt, cam_const)
+
+    def update(self, cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, refine_focal=False) -> bool:
+        """msfm_ba_update: the next problem on this object.  True if the structure was kept (same sparsity pattern: only
+        the values travelled)."""
+        pr, keep = self._describe(cams, pts, obs_uv, obs_cam, obs_pt, cam_const, fx, fy, refine_focal)
+        reused = C.c_int32(0)
+        self.ctx._check(self.lib.msfm_ba_update(self.h, C.byref(pr), C.byref(reused)))
+        return bool(reused.value)
+
+    def last_upload(self):
+        info = (C.c_int64 * 2)()
+        self.ctx._check(self.lib.msfm_ba_last_upload(self.h, info))
+        return {"h2d_bytes": int(info[0]), "reused": bool(info[1])}
 
     def close(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):

@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -29,6 +30,8 @@ cudaError_t ba_launch_track_errors(const Problem&, double*, int, cudaStream_t);
 cudaError_t ba_launch_backsub(const Problem&, double, const double*, double*, double*, int, cudaStream_t);
 cudaError_t ba_launch_update_cams(const double*, const int32_t*, int, const double*, double*, cudaStream_t);
 cudaError_t ba_launch_copy(const double*, double*, int, cudaStream_t);
+cudaError_t ba_launch_permute_obs(int, const int32_t*, const double*, const int32_t*, double*, int32_t*, cudaStream_t);
+cudaError_t ba_launch_fill_obs_pt(int, const int32_t*, const int32_t*, int32_t*, cudaStream_t);
 cudaError_t ba_launch_lm_record(const Problem&, const double*, const double*, const double*, const int*, int, int, double*, cudaStream_t);
 cudaError_t ba_launch_filter_stats(const Problem&, double, uint8_t*, double*, int32_t*, double*, int, cudaStream_t);
 size_t ba_fused_smem_bytes(bool);
@@ -129,6 +132,16 @@ struct msfm_ba {
     int cur = 0;
     std::vector<double> h_cams;   // host mirror of the current cameras
     std::vector<int32_t> h_cam_free;
+    // Everything above that is sized by the problem lives in ONE device allocation (the arena), carved up by build_problem;
+    // msfm_ba_update re-uses it for the next problem when it is large enough (no cudaMalloc / cudaFree on the steady path).
+    unsigned char* arena = nullptr;
+    size_t arena_cap = 0;
+    // host copy of the sparsity pattern the structure was analysed for (msfm_ba_update compares the next problem with it)
+    int32_t flags = 0;
+    std::vector<int32_t> h_obs_cam, h_obs_pt;
+    std::vector<uint8_t> h_cam_const;
+    int64_t last_h2d_bytes = 0;   // host -> device bytes of the last create / update
+    int32_t last_reused = 0;      // 1: the last update kept the structure
     double* tail() const { return reinterpret_cast<double*>(sysbuf); }
     Problem view(int which) const {
         Problem P{};
@@ -188,40 +201,87 @@ void msfm_ba_default_options(msfm_ba_options* o, int32_t n_cams) {
     }
 }
 
+// solver objects and buffers that depend on the block structure (allocated lazily by the first solve)
+static void release_solver_state(msfm_ba* b) {
+    if (b->tri) tridiag_destroy(b->tri);
+    if (b->bands) band_destroy(b->bands);
+    b->tri = nullptr; b->bands = nullptr; b->tri_tried = false;
+    if (b->dense) cudaFree(b->dense);
+    b->dense = nullptr;
+}
+
 void msfm_ba_destroy(msfm_ba* b) {
     if (!b) return;
     msfm_ctx* c = b->ctx;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    void* ptrs[] = {b->cams[0], b->cams[1], b->pts[0], b->pts[1], b->pre[0], b->pre[1], b->obs_uv, b->obs_cam, b->obs_pt, b->obs_orig,
-                    b->obs_lcam, b->obs_lpt, b->long_V, b->pt_start, b->pt_order, b->cam_free, b->tiles, b->items, b->runs, b->tile_cams, b->tile_slots, b->blk_row, b->blk_col,
-                    b->sysbuf, b->dense, b->xsol, b->small, b->work, b->dev_info, b->pt_Wf};
+    release_solver_state(b);
+    void* ptrs[] = {b->arena, b->work, b->rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    if (b->rec) cudaFree(b->rec);
-    if (b->tri) tridiag_destroy(b->tri);
-    if (b->bands) band_destroy(b->bands);
     for (cudaEvent_t e : b->ev)
         if (e) cudaEventDestroy(e);
     delete b;
 }
 
-int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
-    if (!c) return MSFM_E_INVALID;
-    if (!pr || !out) return c->fail(MSFM_E_INVALID, "msfm_ba_create: null argument");
-    *out = nullptr;
+static int check_problem(msfm_ctx* c, const msfm_ba_problem* pr, const char* who) {
+    if (!pr) return c->fail(MSFM_E_INVALID, "%s: null argument", who);
     if (pr->n_cams <= 0 || pr->n_pts < 0 || pr->n_obs < 0 || (pr->flags & ~MSFM_BA_REFINE_FOCAL) != 0 || !pr->cams || !pr->cam_const ||
         (pr->n_pts > 0 && !pr->pts) || (pr->n_obs > 0 && (!pr->obs_uv || !pr->obs_cam || !pr->obs_pt)))
-        return c->fail(MSFM_E_INVALID, "msfm_ba_create: bad problem description");
-    BA_CUDA(cudaSetDevice(c->device));
+        return c->fail(MSFM_E_INVALID, "%s: bad problem description", who);
+    return MSFM_OK;
+}
+
+// Parameters and measurements of `pr` -> device (the structure of b must be the one of pr): cameras and points into the
+// current parameter set, the measurements in the caller's order into a staging buffer and from there into device order with
+// one kernel (obs_orig), and, with `with_cams`, the camera index of every observation the same way.
+static int upload_values(msfm_ba* b, const msfm_ba_problem* pr, bool with_cams) {
+    msfm_ctx* c = b->ctx;
+    const size_t no = size_t(b->n_obs);
+    BA_CUDA(cudaMemcpyAsync(b->cams[b->cur], pr->cams, size_t(b->n_cams) * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    b->last_h2d_bytes += int64_t(b->n_cams) * 6 * sizeof(double);
+    if (b->n_pts) {
+        BA_CUDA(cudaMemcpyAsync(b->pts[b->cur], pr->pts, size_t(b->n_pts) * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        b->last_h2d_bytes += int64_t(b->n_pts) * 3 * sizeof(double);
+    }
+    if (no) {
+        BA_CUDA(c->d_ba_J.reserve(no * (2 * sizeof(double) + sizeof(int32_t))));
+        double* st_uv = c->d_ba_J.as<double>();
+        int32_t* st_cam = reinterpret_cast<int32_t*>(st_uv + 2 * no);
+        BA_CUDA(cudaMemcpyAsync(st_uv, pr->obs_uv, no * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        b->last_h2d_bytes += int64_t(no) * 2 * sizeof(double);
+        if (with_cams) {
+            BA_CUDA(cudaMemcpyAsync(st_cam, pr->obs_cam, no * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            b->last_h2d_bytes += int64_t(no) * sizeof(int32_t);
+        }
+        BA_CUDA(ba_launch_permute_obs(b->n_obs, b->obs_orig, st_uv, with_cams ? st_cam : nullptr, b->obs_uv, b->obs_cam, c->stream));
+        c->launches += 1;
+    }
+    b->focal[0][0] = b->focal[1][0] = pr->fx; b->focal[0][1] = b->focal[1][1] = pr->fy;
+    b->h_cams.assign(pr->cams, pr->cams + size_t(pr->n_cams) * 6);
+    return MSFM_OK;
+}
+
+// Structure analysis of `pr` on the host threads, carve-up of the arena, upload.  Used by msfm_ba_create and by
+// msfm_ba_update when the sparsity pattern has changed.
+static int build_problem(msfm_ba* b, const msfm_ba_problem* pr) {
+    msfm_ctx* c = b->ctx;
+    b->last_h2d_bytes = 0;
+    b->last_reused = 0;
     // validate indices, free-camera map
     std::vector<int32_t> cam_free(pr->n_cams, -1);
-    int prev = 0;
-    for (int i = 0; i < pr->n_obs; ++i) {
-        const int p = pr->obs_pt[i], cam = pr->obs_cam[i];
-        if (p < prev || p >= pr->n_pts || cam < 0 || cam >= pr->n_cams)
-            return c->fail(MSFM_E_INVALID, "msfm_ba_create: observation %d has bad indices (obs_pt must be non-decreasing)", i);
-        prev = p;
+    {
+        std::atomic<int> bad{-1};
+        ba::parallel_ranges(pr->n_obs, [&](int i0, int i1) {
+            int prev = i0 > 0 ? pr->obs_pt[i0 - 1] : 0;
+            for (int i = i0; i < i1; ++i) {
+                const int p = pr->obs_pt[i], cam = pr->obs_cam[i];
+                if (p < prev || p >= pr->n_pts || cam < 0 || cam >= pr->n_cams) { bad.store(i); return; }
+                prev = p;
+            }
+        });
+        if (bad.load() >= 0)
+            return c->fail(MSFM_E_INVALID, "msfm_ba_create: observation %d has bad indices (obs_pt must be non-decreasing)", bad.load());
     }
     int nf = 0;
     for (int i = 0; i < pr->n_cams; ++i)
@@ -257,19 +317,20 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
     ba::assign_slots(T, cam_free.data(), nf, present);
     present.clear(); present.shrink_to_fit();
 
-    msfm_ba* b = new (std::nothrow) msfm_ba();
-    if (!b) return c->fail(MSFM_E_CUDA, "out of host memory");
-    b->ctx = c;
+    release_solver_state(b);                     // the band / dense solvers were set up for the previous block structure
     b->n_cams = pr->n_cams; b->n_pts = pr->n_pts; b->n_obs = pr->n_obs; b->n_free = nf;
+    b->flags = pr->flags;
     b->refine_focal = (pr->flags & MSFM_BA_REFINE_FOCAL) ? 1 : 0;
-    b->focal[0][0] = b->focal[1][0] = pr->fx; b->focal[0][1] = b->focal[1][1] = pr->fy;
-    b->h_cams.assign(pr->cams, pr->cams + size_t(pr->n_cams) * 6);
+    b->cur = 0;
     b->h_cam_free = cam_free;
     b->n_tiles = static_cast<int32_t>(T.tiles.size());
     b->w_max = T.w_max;
     b->first_long = T.first_long; b->n_long = T.n_long;
     b->n_blocks = static_cast<int32_t>(T.blk_col.size());
     b->h_blk_row = T.blk_row; b->h_blk_col = T.blk_col;
+    b->h_obs_cam.assign(pr->obs_cam, pr->obs_cam + pr->n_obs);
+    b->h_obs_pt.assign(pr->obs_pt, pr->obs_pt + pr->n_obs);
+    b->h_cam_const.assign(pr->cam_const, pr->cam_const + pr->n_cams);
     const size_t n6 = size_t(nf) * 6;
     {
         const int R = c->comm ? c->comm_ranks : 1;
@@ -279,75 +340,146 @@ int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
         tl.total = tl.ff + (b->refine_focal ? 16 : 0);
         tl.total = (tl.total + 1) & ~1;          // sblk stays 16-byte aligned behind the 16-byte counter slot
     }
-    // device-order copies of the observation arrays
-    std::vector<double> uv(size_t(pr->n_obs) * 2);
-    std::vector<int32_t> ocam(pr->n_obs), opt(pr->n_obs);
-    for (int i = 0; i < pr->n_obs; ++i) {
-        const int o = T.obs_perm[i];
-        uv[2 * size_t(i)] = pr->obs_uv[2 * size_t(o)]; uv[2 * size_t(i) + 1] = pr->obs_uv[2 * size_t(o) + 1];
-        ocam[i] = pr->obs_cam[o]; opt[i] = pr->obs_pt[o];
-    }
-    auto fail_free = [&](int rc) { msfm_ba_destroy(b); return rc; };
-#define BA_ALLOC(ptr, bytes)                                                         \
-    do {                                                                             \
-        cudaError_t e__ = cudaMalloc(reinterpret_cast<void**>(&(ptr)), std::max<size_t>(16, (bytes))); \
-        if (e__ != cudaSuccess) return fail_free(c->cuda_fail(e__, "cudaMalloc(" #ptr ")")); \
-    } while (0)
-    for (int k = 0; k < 2; ++k) {
-        BA_ALLOC(b->cams[k], size_t(pr->n_cams) * 6 * sizeof(double));
-        BA_ALLOC(b->pts[k], size_t(pr->n_pts) * 3 * sizeof(double));
-        BA_ALLOC(b->pre[k], size_t(pr->n_cams) * sizeof(CamPre));
-    }
-    BA_ALLOC(b->obs_uv, size_t(pr->n_obs) * 2 * sizeof(double));
-    BA_ALLOC(b->obs_cam, size_t(pr->n_obs) * sizeof(int32_t));
-    BA_ALLOC(b->obs_pt, size_t(pr->n_obs) * sizeof(int32_t));
-    BA_ALLOC(b->obs_orig, size_t(pr->n_obs) * sizeof(int32_t));
-    BA_ALLOC(b->obs_lcam, size_t(pr->n_obs));
-    BA_ALLOC(b->obs_lpt, size_t(pr->n_obs));
-    BA_ALLOC(b->long_V, size_t(std::max(1, T.n_long)) * 15 * sizeof(double));
-    BA_ALLOC(b->pt_start, (size_t(pr->n_pts) + 1) * sizeof(int32_t));
-    BA_ALLOC(b->pt_order, size_t(pr->n_pts) * sizeof(int32_t));
-    BA_ALLOC(b->cam_free, size_t(pr->n_cams) * sizeof(int32_t));
-    BA_ALLOC(b->tiles, T.tiles.size() * sizeof(Tile));
-    BA_ALLOC(b->items, T.items.size() * sizeof(Item));
-    BA_ALLOC(b->runs, T.runs.size() * sizeof(uint32_t));
-    BA_ALLOC(b->tile_cams, T.tile_cams.size() * sizeof(int32_t));
-    BA_ALLOC(b->tile_slots, T.tile_slots.size() * sizeof(int32_t));
-    BA_ALLOC(b->blk_row, T.blk_row.size() * sizeof(int32_t));
-    BA_ALLOC(b->blk_col, T.blk_col.size() * sizeof(int32_t));
     b->sys_bytes = size_t(b->tl.total) * sizeof(double) + 16 + size_t(b->n_blocks) * 36 * sizeof(float);
-    BA_ALLOC(b->sysbuf, b->sys_bytes);
+    // ---- carve-up of the arena (256-byte aligned parts)
+    struct Part { void** ptr; size_t bytes; };
+    const size_t np = size_t(pr->n_pts), no = size_t(pr->n_obs), nc = size_t(pr->n_cams);
+    std::vector<Part> parts = {
+        {reinterpret_cast<void**>(&b->cams[0]), nc * 6 * sizeof(double)}, {reinterpret_cast<void**>(&b->cams[1]), nc * 6 * sizeof(double)},
+        {reinterpret_cast<void**>(&b->pts[0]), np * 3 * sizeof(double)},  {reinterpret_cast<void**>(&b->pts[1]), np * 3 * sizeof(double)},
+        {reinterpret_cast<void**>(&b->pre[0]), nc * sizeof(CamPre)},      {reinterpret_cast<void**>(&b->pre[1]), nc * sizeof(CamPre)},
+        {reinterpret_cast<void**>(&b->obs_uv), no * 2 * sizeof(double)},  {reinterpret_cast<void**>(&b->obs_cam), no * sizeof(int32_t)},
+        {reinterpret_cast<void**>(&b->obs_pt), no * sizeof(int32_t)},     {reinterpret_cast<void**>(&b->obs_orig), no * sizeof(int32_t)},
+        {reinterpret_cast<void**>(&b->obs_lcam), no},                     {reinterpret_cast<void**>(&b->obs_lpt), no},
+        {reinterpret_cast<void**>(&b->long_V), size_t(std::max(1, T.n_long)) * 15 * sizeof(double)},
+        {reinterpret_cast<void**>(&b->pt_start), (np + 1) * sizeof(int32_t)}, {reinterpret_cast<void**>(&b->pt_order), np * sizeof(int32_t)},
+        {reinterpret_cast<void**>(&b->cam_free), nc * sizeof(int32_t)},
+        {reinterpret_cast<void**>(&b->tiles), T.tiles.size() * sizeof(Tile)}, {reinterpret_cast<void**>(&b->items), T.items.size() * sizeof(Item)},
+        {reinterpret_cast<void**>(&b->runs), T.runs.size() * sizeof(uint32_t)},
+        {reinterpret_cast<void**>(&b->tile_cams), T.tile_cams.size() * sizeof(int32_t)},
+        {reinterpret_cast<void**>(&b->tile_slots), T.tile_slots.size() * sizeof(int32_t)},
+        {reinterpret_cast<void**>(&b->blk_row), T.blk_row.size() * sizeof(int32_t)}, {reinterpret_cast<void**>(&b->blk_col), T.blk_col.size() * sizeof(int32_t)},
+        {reinterpret_cast<void**>(&b->sysbuf), b->sys_bytes},
+        {reinterpret_cast<void**>(&b->xsol), (3 * std::max<size_t>(1, n6) + 2) * sizeof(double)},     // up to 3 right-hand sides + (d fx, d fy)
+        {reinterpret_cast<void**>(&b->pt_Wf), b->refine_focal ? std::max<size_t>(1, np) * 6 * sizeof(double) : 0},
+        {reinterpret_cast<void**>(&b->small), 8 * sizeof(double)},        {reinterpret_cast<void**>(&b->dev_info), 4 * sizeof(int)},
+    };
+    size_t total = 0;
+    for (const Part& q : parts) total += (std::max<size_t>(16, q.bytes) + 255) / 256 * 256;
+    if (total > b->arena_cap) {
+        BA_CUDA(cudaStreamSynchronize(c->stream));
+        if (b->arena) cudaFree(b->arena);
+        b->arena = nullptr;
+        const size_t want = b->arena_cap ? total + total / 4 : total;      // a problem that grew will grow again
+        b->arena_cap = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&b->arena), want);
+        if (e != cudaSuccess) return c->cuda_fail(e, "cudaMalloc(problem arena)");
+        b->arena_cap = want;
+    }
+    {
+        size_t off = 0;
+        for (const Part& q : parts) {
+            *q.ptr = q.bytes || q.ptr != reinterpret_cast<void**>(&b->pt_Wf) ? b->arena + off : nullptr;
+            off += (std::max<size_t>(16, q.bytes) + 255) / 256 * 256;
+        }
+    }
     b->tile_counter = reinterpret_cast<int32_t*>(b->sysbuf + size_t(b->tl.total) * sizeof(double));
     b->sblk = reinterpret_cast<float*>(b->sysbuf + size_t(b->tl.total) * sizeof(double) + 16);
-    BA_ALLOC(b->xsol, (3 * std::max<size_t>(1, n6) + 2) * sizeof(double));      // up to 3 right-hand sides + (d fx, d fy)
-    if (b->refine_focal) BA_ALLOC(b->pt_Wf, std::max<size_t>(1, size_t(pr->n_pts)) * 6 * sizeof(double));
-    BA_ALLOC(b->small, 8 * sizeof(double));
-    BA_ALLOC(b->dev_info, 4 * sizeof(int));
-#undef BA_ALLOC
-    auto H2D = [&](void* dst, const void* src, size_t bytes) {
-        return bytes ? cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
-    };
+    // ---- upload: structure tables, then the values (measurements and camera indices are permuted on the device)
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = H2D(b->cams[0], pr->cams, size_t(pr->n_cams) * 6 * sizeof(double));
-    if (e == cudaSuccess) e = H2D(b->pts[0], pr->pts, size_t(pr->n_pts) * 3 * sizeof(double));
-    if (e == cudaSuccess) e = H2D(b->obs_uv, uv.data(), uv.size() * sizeof(double));
-    if (e == cudaSuccess) e = H2D(b->obs_cam, ocam.data(), ocam.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->obs_pt, opt.data(), opt.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->obs_orig, T.obs_perm.data(), T.obs_perm.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->obs_lcam, T.obs_lcam.data(), T.obs_lcam.size());
-    if (e == cudaSuccess) e = H2D(b->obs_lpt, T.obs_lpt.data(), T.obs_lpt.size());
-    if (e == cudaSuccess) e = H2D(b->pt_start, T.pt_start.data(), T.pt_start.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->pt_order, T.pt_order.data(), T.pt_order.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->cam_free, cam_free.data(), cam_free.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->tiles, T.tiles.data(), T.tiles.size() * sizeof(Tile));
-    if (e == cudaSuccess) e = H2D(b->items, T.items.data(), T.items.size() * sizeof(Item));
-    if (e == cudaSuccess) e = H2D(b->runs, T.runs.data(), T.runs.size() * sizeof(uint32_t));
-    if (e == cudaSuccess) e = H2D(b->tile_cams, T.tile_cams.data(), T.tile_cams.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->tile_slots, T.tile_slots.data(), T.tile_slots.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->blk_row, T.blk_row.data(), T.blk_row.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = H2D(b->blk_col, T.blk_col.data(), T.blk_col.size() * sizeof(int32_t));
-    if (e != cudaSuccess) return fail_free(c->cuda_fail(e, "msfm_ba_create H2D"));
+    auto H2D = [&](void* dst, const void* src, size_t bytes) {
+        if (e != cudaSuccess || bytes == 0) return;
+        e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+        b->last_h2d_bytes += int64_t(bytes);
+    };
+    H2D(b->obs_orig, T.obs_perm.data(), T.obs_perm.size() * sizeof(int32_t));
+    H2D(b->obs_lcam, T.obs_lcam.data(), T.obs_lcam.size());
+    H2D(b->obs_lpt, T.obs_lpt.data(), T.obs_lpt.size());
+    H2D(b->pt_start, T.pt_start.data(), T.pt_start.size() * sizeof(int32_t));
+    H2D(b->pt_order, T.pt_order.data(), T.pt_order.size() * sizeof(int32_t));
+    H2D(b->cam_free, cam_free.data(), cam_free.size() * sizeof(int32_t));
+    H2D(b->tiles, T.tiles.data(), T.tiles.size() * sizeof(Tile));
+    H2D(b->items, T.items.data(), T.items.size() * sizeof(Item));
+    H2D(b->runs, T.runs.data(), T.runs.size() * sizeof(uint32_t));
+    H2D(b->tile_cams, T.tile_cams.data(), T.tile_cams.size() * sizeof(int32_t));
+    H2D(b->tile_slots, T.tile_slots.data(), T.tile_slots.size() * sizeof(int32_t));
+    H2D(b->blk_row, T.blk_row.data(), T.blk_row.size() * sizeof(int32_t));
+    H2D(b->blk_col, T.blk_col.data(), T.blk_col.size() * sizeof(int32_t));
+    if (e != cudaSuccess) return c->cuda_fail(e, "msfm_ba_create H2D");
+    if (pr->n_pts > 0) {
+        BA_CUDA(ba_launch_fill_obs_pt(pr->n_pts, b->pt_start, b->pt_order, b->obs_pt, c->stream));
+        c->launches += 1;
+    }
+    int rc = upload_values(b, pr, true);
+    if (rc) return rc;
+    BA_CUDA(cudaStreamSynchronize(c->stream));       // the host tables of T go out of scope
+    return MSFM_OK;
+}
+
+int msfm_ba_create(msfm_ctx* c, const msfm_ba_problem* pr, msfm_ba** out) {
+    if (!c) return MSFM_E_INVALID;
+    if (!out) return c->fail(MSFM_E_INVALID, "msfm_ba_create: null argument");
+    *out = nullptr;
+    int rc = check_problem(c, pr, "msfm_ba_create");
+    if (rc) return rc;
+    BA_CUDA(cudaSetDevice(c->device));
+    msfm_ba* b = new (std::nothrow) msfm_ba();
+    if (!b) return c->fail(MSFM_E_CUDA, "out of host memory");
+    b->ctx = c;
+    if ((rc = build_problem(b, pr))) { msfm_ba_destroy(b); return rc; }
     *out = b;
+    return MSFM_OK;
+}
+
+int msfm_ba_update(msfm_ba* b, const msfm_ba_problem* pr, int32_t* reused) {
+    if (!b) return MSFM_E_INVALID;
+    msfm_ctx* c = b->ctx;
+    int rc = check_problem(c, pr, "msfm_ba_update");
+    if (rc) return rc;
+    BA_CUDA(cudaSetDevice(c->device));
+    // same sparsity pattern?  sizes, flags, constant cameras and the two index arrays, compared exactly
+    int differs = pr->n_cams != b->n_cams || pr->n_pts != b->n_pts || pr->n_obs != b->n_obs || pr->flags != b->flags;
+    if (!differs) differs = std::memcmp(pr->cam_const, b->h_cam_const.data(), size_t(pr->n_cams)) != 0;
+    if (!differs && pr->n_obs > 0) {
+        std::atomic<int> d{0};
+        ba::parallel_ranges(pr->n_obs, [&](int i0, int i1) {
+            if (std::memcmp(pr->obs_cam + i0, b->h_obs_cam.data() + i0, size_t(i1 - i0) * sizeof(int32_t)) != 0 ||
+                std::memcmp(pr->obs_pt + i0, b->h_obs_pt.data() + i0, size_t(i1 - i0) * sizeof(int32_t)) != 0) d.store(1);
+        });
+        differs = d.load();
+    }
+    if (c->comm && c->comm_ranks > 1) {
+        // every rank has to take the same path (a rebuild merges the block structure with a collective)
+        double v = differs ? 1.0 : 0.0;
+        BA_CUDA(cudaMemcpyAsync(b->small, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        if ((rc = msfm_comm_allreduce_f64(c, b->small, 1, 1))) return rc;
+        BA_CUDA(cudaMemcpyAsync(&v, b->small, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        BA_CUDA(cudaStreamSynchronize(c->stream));
+        differs = v != 0.0;
+    }
+    if (differs) {
+        BA_CUDA(cudaStreamSynchronize(c->stream));
+        rc = build_problem(b, pr);
+    } else {
+        b->last_h2d_bytes = 0;
+        b->last_reused = 1;
+        rc = upload_values(b, pr, false);
+        if (rc == MSFM_OK) BA_CUDA(cudaStreamSynchronize(c->stream));       // the caller's arrays may go away
+    }
+    if (reused) *reused = b->last_reused;
+    return rc;
+}
+
+int msfm_ba_sizes(msfm_ba* b, int64_t sizes[3]) {
+    if (!b || !sizes) return MSFM_E_INVALID;
+    sizes[0] = b->n_cams; sizes[1] = b->n_pts; sizes[2] = b->n_obs;
+    return MSFM_OK;
+}
+
+int msfm_ba_last_upload(msfm_ba* b, int64_t info[2]) {
+    if (!b || !info) return MSFM_E_INVALID;
+    info[0] = b->last_h2d_bytes;
+    info[1] = b->last_reused;
     return MSFM_OK;
 }
 

@@ -1132,6 +1132,26 @@ __global__ void copy_kernel(const double* __restrict__ src, double* __restrict__
     if (i < n) dst[i] = src[i];
 }
 
+
+// Measurements (and camera indices) from the caller's observation order into device order: out[i] = in[obs_orig[i]].
+// msfm_ba_create / msfm_ba_update upload the caller's arrays as they are; the gather runs here at HBM speed instead of on
+// one host thread.
+__global__ void permute_obs_kernel(int n_obs, const int32_t* __restrict__ obs_orig, const double2* __restrict__ uv_in,
+                                   const int32_t* __restrict__ cam_in, double2* __restrict__ uv_out, int32_t* __restrict__ cam_out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_obs; i += gridDim.x * blockDim.x) {
+        const int o = __ldg(obs_orig + i);
+        uv_out[i] = __ldg(uv_in + o);
+        if (cam_in) cam_out[i] = __ldg(cam_in + o);
+    }
+}
+// obs_pt in device order (the caller's point index of every device observation) from the point tables
+__global__ void fill_obs_pt_kernel(int n_pts, const int32_t* __restrict__ pt_start, const int32_t* __restrict__ pt_order,
+                                   int32_t* __restrict__ obs_pt) {
+    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n_pts; d += gridDim.x * blockDim.x) {
+        const int p = __ldg(pt_order + d);
+        for (int a = __ldg(pt_start + d); a < __ldg(pt_start + d + 1); ++a) obs_pt[a] = p;
+    }
+}
 }  // namespace ba
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -1219,6 +1239,21 @@ cudaError_t ba_launch_lm_record(const Problem& P, const double* cams, const doub
 cudaError_t ba_launch_copy(const double* src, double* dst, int n, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n);
+    return cudaGetLastError();
+}
+
+cudaError_t ba_launch_permute_obs(int n_obs, const int32_t* obs_orig, const double* uv_in, const int32_t* cam_in, double* uv_out,
+                                  int32_t* cam_out, cudaStream_t st) {
+    if (n_obs <= 0) return cudaSuccess;
+    const int grid = std::min((n_obs + 255) / 256, 148 * 16);
+    permute_obs_kernel<<<grid, 256, 0, st>>>(n_obs, obs_orig, reinterpret_cast<const double2*>(uv_in), cam_in,
+                                             reinterpret_cast<double2*>(uv_out), cam_out);
+    return cudaGetLastError();
+}
+cudaError_t ba_launch_fill_obs_pt(int n_pts, const int32_t* pt_start, const int32_t* pt_order, int32_t* obs_pt, cudaStream_t st) {
+    if (n_pts <= 0) return cudaSuccess;
+    const int grid = std::min((n_pts + 255) / 256, 148 * 16);
+    fill_obs_pt_kernel<<<grid, 256, 0, st>>>(n_pts, pt_start, pt_order, obs_pt);
     return cudaGetLastError();
 }
 

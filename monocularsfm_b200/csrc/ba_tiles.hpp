@@ -6,6 +6,7 @@
 // ceres::Solve (src/Optimizer/CeresBundleOptimizer.cpp:293) — e-blocks = points, f-blocks = cameras.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <functional>
 #include <numeric>
@@ -59,6 +60,57 @@ inline void parallel_ranges(int n, F f) {
     for (auto& x : th) x.join();
 }
 
+// Stable order of v under a strict total order `less`, on the host threads: sorted chunks, then rounds of pairwise merges.
+template <class T, class Less>
+inline void parallel_sort(std::vector<T>& v, Less less) {
+    int nt = static_cast<int>(std::thread::hardware_concurrency());
+    nt = std::max(1, std::min(8, nt));
+    const size_t n = v.size();
+    if (n < 50000 || nt == 1) { std::sort(v.begin(), v.end(), less); return; }
+    int parts = 1;
+    while (parts * 2 <= nt) parts *= 2;
+    std::vector<size_t> cut(size_t(parts) + 1);
+    for (int i = 0; i <= parts; ++i) cut[i] = n * size_t(i) / size_t(parts);
+    {
+        std::vector<std::thread> th;
+        for (int i = 0; i < parts; ++i) th.emplace_back([&, i] { std::sort(v.begin() + cut[i], v.begin() + cut[i + 1], less); });
+        for (auto& x : th) x.join();
+    }
+    for (int width = 1; width < parts; width *= 2) {
+        std::vector<std::thread> th;
+        for (int i = 0; i + width < parts; i += 2 * width)
+            th.emplace_back([&, i, width] {
+                std::inplace_merge(v.begin() + cut[i], v.begin() + cut[i + width], v.begin() + cut[std::min(parts, i + 2 * width)], less);
+            });
+        for (auto& x : th) x.join();
+    }
+}
+
+// f(chunk) for chunk in [0, n_chunks), chunks handed out dynamically to up to 8 host threads
+template <class F>
+inline void parallel_chunks(int n_chunks, F f) {
+    int nt = static_cast<int>(std::thread::hardware_concurrency());
+    nt = std::max(1, std::min(std::min(8, nt), n_chunks));
+    if (nt <= 1) { for (int c = 0; c < n_chunks; ++c) f(c); return; }
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([&] { for (int c = next.fetch_add(1); c < n_chunks; c = next.fetch_add(1)) f(c); });
+    for (auto& x : th) x.join();
+}
+
+// Tiles of one chunk of the device order (the chunks are tiled independently on the host threads and concatenated in order;
+// the chunk size is a constant, so the result does not depend on the number of threads).  Offsets are chunk-local.
+struct TileChunk {
+    std::vector<Tile> tiles;
+    std::vector<Item> items;
+    std::vector<uint32_t> runs;
+    std::vector<int32_t> tile_cams, tile_marks;
+    int w_max = 0;
+};
+constexpr int kChunkPoints = 16384;      // device points per chunk of normal tiles
+constexpr int kChunkLong = 1024;         // long tracks per chunk of item tiles (their open tiles are closed at the chunk's end)
+
 // Device order + tiles + per-tile coupling marks.  obs_pt must be non-decreasing (validated by the caller).
 // Returns false if a point is observed twice by one camera.
 inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_cam, const int32_t* obs_pt,
@@ -66,10 +118,16 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
     std::vector<int32_t> start(size_t(n_pts) + 1, 0);
     for (int i = 0; i < n_obs; ++i) start[size_t(obs_pt[i]) + 1] += 1;
     for (int p = 0; p < n_pts; ++p) start[size_t(p) + 1] += start[p];
-    // observations of every point sorted by camera; cs = the sorted camera lists, contiguous (the comparisons below read them)
+    // observations of every point sorted by camera; cs = the sorted camera lists, contiguous (the comparisons below read them).
+    // Device order: class (key bit 62: long tracks behind the others, points without observations last) and the three smallest
+    // cameras — neighbours share cameras (few cameras per tile) — then track length and a hash of the whole camera list, so
+    // that points with IDENTICAL lists end up adjacent (runs: their 6x6 products are summed in registers before they touch the
+    // shared-memory accumulator; run detection compares the lists themselves, a hash collision only costs adjacency).
+    // All-scalar keys in one contiguous array: no list walks in the sort.
+    struct SortKey { uint64_t key, hash; int32_t k, idx; };
     std::vector<int32_t> sorted_obs(static_cast<size_t>(n_obs)), cs(static_cast<size_t>(n_obs));
-    std::vector<uint64_t> key(static_cast<size_t>(n_pts));
-    std::vector<char> dup(8, 0);
+    std::vector<SortKey> sk(static_cast<size_t>(n_pts));
+    std::atomic<int> dup{0};
     parallel_ranges(n_pts, [&](int p0, int p1) {
         for (int p = p0; p < p1; ++p) {
             int32_t* b = sorted_obs.data() + start[p];
@@ -80,12 +138,15 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
             if (!sorted) {
                 std::sort(b, e, [&](int32_t x, int32_t y) { return obs_cam[x] < obs_cam[y]; });
                 for (int32_t* q = b; q + 1 < e; ++q)
-                    if (obs_cam[q[0]] == obs_cam[q[1]]) dup[0] = 1;
+                    if (obs_cam[q[0]] == obs_cam[q[1]]) dup.store(1, std::memory_order_relaxed);
             }
             int32_t* c = cs.data() + start[p];
-            for (int32_t* q = b; q < e; ++q) *c++ = obs_cam[*q];
-            // locality key: the three smallest cameras (20 bits each).  Order of the classes: points with at most 32
-            // observations, long tracks, points without observations.
+            uint64_t h = 1469598103934665603ull;
+            for (int32_t* q = b; q < e; ++q) {
+                const int32_t cam = obs_cam[*q];
+                *c++ = cam;
+                h ^= static_cast<uint64_t>(static_cast<uint32_t>(cam)); h *= 1099511628211ull;
+            }
             uint64_t k = ~uint64_t(0);
             if (e > b) {
                 const int32_t* cc = cs.data() + start[p];
@@ -94,41 +155,30 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
                 const uint64_t c2 = e - b > 2 ? uint64_t(cc[2]) & 0xFFFFF : c1;
                 k = (uint64_t(e - b > 32 ? 1 : 0) << 62) | (c0 << 40) | (c1 << 20) | c2;
             }
-            key[p] = k;
+            sk[p] = SortKey{k, h, static_cast<int32_t>(e - b), p};
         }
     });
-    if (dup[0]) return false;
-    // Device order: class (key bit 62) and the three smallest cameras — neighbours share cameras (few cameras per tile) — then
-    // track length and a hash of the whole camera list, so that points with IDENTICAL lists end up adjacent (runs: their 6x6
-    // products are summed in registers before they touch the shared-memory accumulator; run detection compares the lists
-    // themselves, a hash collision only costs adjacency).  All-scalar keys in one contiguous array: no list walks in the sort.
-    struct SortKey { uint64_t key, hash; int32_t k, idx; };
-    std::vector<SortKey> sk(static_cast<size_t>(n_pts));
-    parallel_ranges(n_pts, [&](int p0, int p1) {
-        for (int p = p0; p < p1; ++p) {
-            uint64_t h = 1469598103934665603ull;
-            for (int i = start[p]; i < start[size_t(p) + 1]; ++i) { h ^= static_cast<uint64_t>(static_cast<uint32_t>(cs[i])); h *= 1099511628211ull; }
-            sk[p] = SortKey{key[p], h, start[size_t(p) + 1] - start[p], p};
-        }
-    });
-    std::sort(sk.begin(), sk.end(), [](const SortKey& a, const SortKey& b) {
+    if (dup.load()) return false;
+    parallel_sort(sk, [](const SortKey& a, const SortKey& b) {
         if (a.key != b.key) return a.key < b.key;
         if (a.k != b.k) return a.k < b.k;
         if (a.hash != b.hash) return a.hash < b.hash;
         return a.idx < b.idx;
     });
     T.pt_order.resize(static_cast<size_t>(n_pts));
-    for (int d = 0; d < n_pts; ++d) T.pt_order[d] = sk[d].idx;
-    sk.clear(); sk.shrink_to_fit();
     T.pt_start.assign(size_t(n_pts) + 1, 0);
+    int first_long = n_pts, end_long = n_pts;          // classes are sorted: normal | long | unobserved
+    for (int d = 0; d < n_pts; ++d) {
+        T.pt_order[d] = sk[d].idx;
+        T.pt_start[size_t(d) + 1] = T.pt_start[d] + sk[d].k;
+        if (first_long == n_pts && (sk[d].k == 0 || sk[d].k > 32)) first_long = d;
+        if (end_long == n_pts && sk[d].k == 0) end_long = d;
+    }
+    sk.clear(); sk.shrink_to_fit();
     T.obs_perm.resize(static_cast<size_t>(n_obs));
     T.obs_lcam.assign(static_cast<size_t>(n_obs), 0);
     T.obs_lpt.assign(static_cast<size_t>(n_obs), 0);
     std::vector<int32_t> dev_cam(static_cast<size_t>(n_obs));       // camera of every observation in device order
-    for (int d = 0; d < n_pts; ++d) {
-        const int p = T.pt_order[d];
-        T.pt_start[size_t(d) + 1] = T.pt_start[d] + (start[size_t(p) + 1] - start[p]);
-    }
     parallel_ranges(n_pts, [&](int d0, int d1) {
         for (int d = d0; d < d1; ++d) {
             const int p = T.pt_order[d];
@@ -139,167 +189,201 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
     const int w_cap = kTileCams;
     const int max_pts = std::max(1, std::min(prm.max_pts, kTilePts)), max_obs = std::max(32, std::min(prm.max_obs, kTileObs));
     const int max_items = std::max(1, std::min(prm.max_items, kTileItems));
-    std::vector<int32_t> stamp(static_cast<size_t>(std::max(1, n_cams)), -1), lidx(static_cast<size_t>(std::max(1, n_cams)), 0);
-    T.tiles.clear(); T.items.clear(); T.tile_cams.clear(); T.tile_marks.clear();
-    T.w_max = 0;
+    const int n_cam_slots = std::max(1, n_cams);
     auto cam_of = [&](int dev_obs) { return dev_cam[dev_obs]; };
-    // ---- normal tiles: greedy over the device order
-    auto close_tile = [&](int d0, int d1, std::vector<int32_t>& cams) {
-        if (d1 <= d0) return;
-        std::sort(cams.begin(), cams.end());
-        Tile t{};
-        t.begin = d0; t.end = d1;
-        t.obs_begin = T.pt_start[d0]; t.n_obs = T.pt_start[d1] - T.pt_start[d0];
-        t.cam_begin = static_cast<int32_t>(T.tile_cams.size());
-        t.w = static_cast<int32_t>(cams.size());
-        t.slot_begin = static_cast<int32_t>(T.tile_marks.size());
-        for (size_t i = 0; i < cams.size(); ++i) lidx[cams[i]] = static_cast<int32_t>(i);
-        T.tile_cams.insert(T.tile_cams.end(), cams.begin(), cams.end());
-        T.tile_marks.resize(T.tile_marks.size() + size_t(t.w) * (t.w + 1) / 2, 0);
-        int32_t* marks = T.tile_marks.data() + t.slot_begin;
-        for (int a = T.pt_start[d0]; a < T.pt_start[d1]; ++a) T.obs_lcam[a] = static_cast<uint8_t>(lidx[cam_of(a)]);
-        for (int d = d0; d < d1; ++d)
-            for (int a = T.pt_start[d]; a < T.pt_start[size_t(d) + 1]; ++a) T.obs_lpt[a] = static_cast<uint8_t>(d - d0);
-        // runs of consecutive points with identical camera lists (at most 255 points each), one work item per 32 camera pairs;
-        // the coupling marks are those of the run's first point
-        t.run_begin = static_cast<int32_t>(T.runs.size());
-        for (int d = d0; d < d1;) {
-            int e = d + 1;
-            const int kd = T.pt_start[size_t(d) + 1] - T.pt_start[d];
-            const int32_t* cd = dev_cam.data() + T.pt_start[d];
-            while (e < d1 && e - d < 255 && T.pt_start[size_t(e) + 1] - T.pt_start[e] == kd &&
-                   std::equal(cd, cd + kd, dev_cam.data() + T.pt_start[e])) ++e;
-            for (int a = 0; a < kd; ++a) {
-                if (cam_free[cd[a]] < 0) continue;
-                const int la = lidx[cd[a]];
-                for (int b = a; b < kd; ++b)
-                    if (cam_free[cd[b]] >= 0) marks[tri_index(la, lidx[cd[b]])] = 1;
+
+    // ---- normal tiles: greedy over the device order, chunk by chunk
+    const int n_chunks_a = (first_long + kChunkPoints - 1) / kChunkPoints;
+    std::vector<TileChunk> chunk_a(static_cast<size_t>(n_chunks_a));
+    parallel_chunks(n_chunks_a, [&](int ci) {
+        TileChunk& C = chunk_a[ci];
+        std::vector<int32_t> stamp(static_cast<size_t>(n_cam_slots), -1), lidx(static_cast<size_t>(n_cam_slots), 0);
+        std::vector<int32_t> cams;
+        auto close_tile = [&](int d0, int d1) {
+            if (d1 <= d0) return;
+            std::sort(cams.begin(), cams.end());
+            Tile t{};
+            t.begin = d0; t.end = d1;
+            t.obs_begin = T.pt_start[d0]; t.n_obs = T.pt_start[d1] - T.pt_start[d0];
+            t.cam_begin = static_cast<int32_t>(C.tile_cams.size());
+            t.w = static_cast<int32_t>(cams.size());
+            t.slot_begin = static_cast<int32_t>(C.tile_marks.size());
+            for (size_t i = 0; i < cams.size(); ++i) lidx[cams[i]] = static_cast<int32_t>(i);
+            C.tile_cams.insert(C.tile_cams.end(), cams.begin(), cams.end());
+            C.tile_marks.resize(C.tile_marks.size() + size_t(t.w) * (t.w + 1) / 2, 0);
+            int32_t* marks = C.tile_marks.data() + t.slot_begin;
+            for (int a = T.pt_start[d0]; a < T.pt_start[d1]; ++a) T.obs_lcam[a] = static_cast<uint8_t>(lidx[cam_of(a)]);
+            for (int d = d0; d < d1; ++d)
+                for (int a = T.pt_start[d]; a < T.pt_start[size_t(d) + 1]; ++a) T.obs_lpt[a] = static_cast<uint8_t>(d - d0);
+            // runs of consecutive points with identical camera lists (at most 255 points each), one work item per 32 camera
+            // pairs; the coupling marks are those of the run's first point
+            t.run_begin = static_cast<int32_t>(C.runs.size());
+            for (int d = d0; d < d1;) {
+                int e = d + 1;
+                const int kd = T.pt_start[size_t(d) + 1] - T.pt_start[d];
+                const int32_t* cd = dev_cam.data() + T.pt_start[d];
+                while (e < d1 && e - d < 255 && T.pt_start[size_t(e) + 1] - T.pt_start[e] == kd &&
+                       std::equal(cd, cd + kd, dev_cam.data() + T.pt_start[e])) ++e;
+                for (int a = 0; a < kd; ++a) {
+                    if (cam_free[cd[a]] < 0) continue;
+                    const int la = lidx[cd[a]];
+                    for (int b = a; b < kd; ++b)
+                        if (cam_free[cd[b]] >= 0) marks[tri_index(la, lidx[cd[b]])] = 1;
+                }
+                const int rounds = (kd * (kd - 1) / 2 + 31) / 32;
+                for (int r = 0; r < rounds; ++r)
+                    C.runs.push_back(static_cast<uint32_t>(d - d0) | (static_cast<uint32_t>(e - d) << 16) | (static_cast<uint32_t>(r) << 24));
+                d = e;
             }
-            const int rounds = (kd * (kd - 1) / 2 + 31) / 32;
-            for (int r = 0; r < rounds; ++r)
-                T.runs.push_back(static_cast<uint32_t>(d - d0) | (static_cast<uint32_t>(e - d) << 16) | (static_cast<uint32_t>(r) << 24));
-            d = e;
+            t.n_runs = static_cast<int32_t>(C.runs.size()) - t.run_begin;
+            C.w_max = std::max(C.w_max, int(t.w));
+            C.tiles.push_back(t);
+            cams.clear();
+        };
+        const int c0 = ci * kChunkPoints, c1 = std::min(first_long, c0 + kChunkPoints);
+        int d0 = c0, tile_id = 0, tile_obs = 0;
+        for (int d = c0; d < c1; ++d) {
+            const int beg = T.pt_start[d], k = T.pt_start[size_t(d) + 1] - beg;
+            int fresh = 0;
+            for (int a = beg; a < beg + k; ++a)
+                if (stamp[cam_of(a)] != tile_id) ++fresh;
+            if (d > d0 && (int(cams.size()) + fresh > w_cap || d - d0 >= max_pts || tile_obs + k > max_obs)) {
+                close_tile(d0, d);
+                ++tile_id; tile_obs = 0; d0 = d;
+            }
+            for (int a = beg; a < beg + k; ++a) {
+                const int c = cam_of(a);
+                if (stamp[c] != tile_id) { stamp[c] = tile_id; cams.push_back(c); }
+            }
+            tile_obs += k;
         }
-        t.n_runs = static_cast<int32_t>(T.runs.size()) - t.run_begin;
-        T.w_max = std::max(T.w_max, int(t.w));
-        T.tiles.push_back(t);
-        cams.clear();
-    };
-    std::vector<int32_t> cams;
-    int d0 = 0, tile_id = 0, first_long = n_pts;
-    int tile_obs = 0;
-    for (int d = 0; d < n_pts; ++d) {
-        const int beg = T.pt_start[d], k = T.pt_start[size_t(d) + 1] - beg;
-        if (k == 0 || k > 32) { first_long = d; break; }                 // classes are sorted: normal | long | unobserved
-        int fresh = 0;
-        for (int a = beg; a < beg + k; ++a)
-            if (stamp[cam_of(a)] != tile_id) ++fresh;
-        if (d > d0 && (int(cams.size()) + fresh > w_cap || d - d0 >= max_pts || tile_obs + k > max_obs)) {
-            close_tile(d0, d, cams);
-            ++tile_id; tile_obs = 0; d0 = d;
-        }
-        for (int a = beg; a < beg + k; ++a) {
-            const int c = cam_of(a);
-            if (stamp[c] != tile_id) { stamp[c] = tile_id; cams.push_back(c); }
-        }
-        tile_obs += k;
-    }
-    close_tile(d0, first_long, cams);
-    T.first_long = first_long;
-    T.n_long = 0;
+        close_tile(d0, c1);
+    });
+
     // ---- item tiles: long tracks cut into groups of 16 observations; one open tile per (group A, group B) index pair, so
     //      that the items of neighbouring long points (nearly the same cameras) are packed together
-    struct Open { std::vector<int32_t> cams; std::vector<Item> items; };
-    std::vector<Open> open;                    // index gi * ng_max + gj, grown on demand
-    int ng_max = 0;
-    auto close_items = [&](Open& o) {
-        if (o.items.empty()) return;
-        std::sort(o.cams.begin(), o.cams.end());
-        Tile t{};
-        t.flags = kTileSplit;
-        t.begin = static_cast<int32_t>(T.items.size());
-        t.end = t.begin + static_cast<int32_t>(o.items.size());
-        t.cam_begin = static_cast<int32_t>(T.tile_cams.size());
-        t.w = static_cast<int32_t>(o.cams.size());
-        t.slot_begin = static_cast<int32_t>(T.tile_marks.size());
-        for (size_t i = 0; i < o.cams.size(); ++i) lidx[o.cams[i]] = static_cast<int32_t>(i);
-        T.tile_cams.insert(T.tile_cams.end(), o.cams.begin(), o.cams.end());
-        T.tile_marks.resize(T.tile_marks.size() + size_t(t.w) * (t.w + 1) / 2, 0);
-        int32_t* marks = T.tile_marks.data() + t.slot_begin;
-        for (Item& it : o.items) {
-            const int beg = T.pt_start[it.d];
-            const int na = it.a1 - it.a0, nb = it.b1 - it.b0;
-            int cam_l[32];
-            for (int l = 0; l < na + nb; ++l) {
-                cam_l[l] = cam_of(beg + (l < na ? it.a0 + l : it.b0 + l - na));
-                it.lc[l] = static_cast<uint8_t>(lidx[cam_l[l]]);
-            }
-            for (int x = 0; x < na; ++x) {
-                if (cam_free[cam_l[x]] < 0) continue;
-                if (nb == 0) {
-                    for (int y = x; y < na; ++y)
-                        if (cam_free[cam_l[y]] >= 0) marks[tri_index(it.lc[x], it.lc[y])] = 1;
-                } else {
-                    for (int y = na; y < na + nb; ++y)
-                        if (cam_free[cam_l[y]] >= 0) marks[tri_index(it.lc[x], it.lc[y])] = 1;
-                }
-            }
-            T.items.push_back(it);
-        }
-        t.run_begin = static_cast<int32_t>(T.runs.size());
-        for (int u = 0; u < t.end - t.begin; ++u) {                          // an item is a run of one; a work item per 32 pairs
-            const Item& it = T.items[size_t(t.begin) + u];
-            const int na = it.a1 - it.a0, nb = it.b1 - it.b0;
-            const int rounds = ((nb ? na * nb : na * (na - 1) / 2) + 31) / 32;
-            for (int r = 0; r < rounds; ++r) T.runs.push_back(static_cast<uint32_t>(u) | (1u << 16) | (static_cast<uint32_t>(r) << 24));
-        }
-        t.n_runs = static_cast<int32_t>(T.runs.size()) - t.run_begin;
-        T.w_max = std::max(T.w_max, int(t.w));
-        T.tiles.push_back(t);
-        o = Open();
-    };
-    for (int d = first_long; d < n_pts; ++d) {
-        const int beg = T.pt_start[d], k = T.pt_start[size_t(d) + 1] - beg;
-        if (k == 0) break;
-        T.n_long += 1;
-        const int ng = (k + 15) / 16;
-        if (ng > ng_max) {                         // re-index the open tiles for the larger group count
-            std::vector<Open> grown(size_t(ng) * ng);
-            for (int gi = 0; gi < ng_max; ++gi)
-                for (int gj = gi; gj < ng_max; ++gj) grown[size_t(gi) * ng + gj] = std::move(open[size_t(gi) * ng_max + gj]);
-            open.swap(grown);
-            ng_max = ng;
-        }
-        for (int gi = 0; gi < ng; ++gi)
-            for (int gj = gi; gj < ng; ++gj) {
-                Item it{};
-                it.d = d;
-                it.a0 = static_cast<uint16_t>(gi * 16); it.a1 = static_cast<uint16_t>(std::min(k, gi * 16 + 16));
-                if (gj != gi) { it.b0 = static_cast<uint16_t>(gj * 16); it.b1 = static_cast<uint16_t>(std::min(k, gj * 16 + 16)); }
+    T.first_long = first_long;
+    T.n_long = end_long - first_long;
+    const int n_chunks_b = (T.n_long + kChunkLong - 1) / kChunkLong;
+    std::vector<TileChunk> chunk_b(static_cast<size_t>(n_chunks_b));
+    parallel_chunks(n_chunks_b, [&](int ci) {
+        TileChunk& C = chunk_b[ci];
+        std::vector<int32_t> lidx(static_cast<size_t>(n_cam_slots), 0);
+        struct Open { std::vector<int32_t> cams; std::vector<Item> items; };
+        std::vector<Open> open;                    // index gi * ng_max + gj, grown on demand
+        int ng_max = 0;
+        auto close_items = [&](Open& o) {
+            if (o.items.empty()) return;
+            Tile t{};
+            t.flags = kTileSplit;
+            t.begin = static_cast<int32_t>(C.items.size());
+            t.end = t.begin + static_cast<int32_t>(o.items.size());
+            t.cam_begin = static_cast<int32_t>(C.tile_cams.size());
+            t.w = static_cast<int32_t>(o.cams.size());
+            t.slot_begin = static_cast<int32_t>(C.tile_marks.size());
+            for (size_t i = 0; i < o.cams.size(); ++i) lidx[o.cams[i]] = static_cast<int32_t>(i);       // o.cams is kept sorted
+            C.tile_cams.insert(C.tile_cams.end(), o.cams.begin(), o.cams.end());
+            C.tile_marks.resize(C.tile_marks.size() + size_t(t.w) * (t.w + 1) / 2, 0);
+            int32_t* marks = C.tile_marks.data() + t.slot_begin;
+            for (Item& it : o.items) {
+                const int beg = T.pt_start[it.d];
                 const int na = it.a1 - it.a0, nb = it.b1 - it.b0;
-                Open& o = open[size_t(gi) * ng_max + gj];
-                // the item's cameras are ascending (group A, then group B); the open tile keeps its list sorted: one merge walk
-                int32_t ic[32];
-                for (int l = 0; l < na + nb; ++l) ic[l] = cam_of(beg + (l < na ? it.a0 + l : it.b0 + l - na));
-                auto count_fresh = [&](const std::vector<int32_t>& have) {
-                    int fresh = 0;
-                    size_t h = 0;
-                    for (int l = 0; l < na + nb; ++l) {
-                        while (h < have.size() && have[h] < ic[l]) ++h;
-                        if (h == have.size() || have[h] != ic[l]) ++fresh;
+                int cam_l[32];
+                for (int l = 0; l < na + nb; ++l) {
+                    cam_l[l] = cam_of(beg + (l < na ? it.a0 + l : it.b0 + l - na));
+                    it.lc[l] = static_cast<uint8_t>(lidx[cam_l[l]]);
+                }
+                for (int x = 0; x < na; ++x) {
+                    if (cam_free[cam_l[x]] < 0) continue;
+                    if (nb == 0) {
+                        for (int y = x; y < na; ++y)
+                            if (cam_free[cam_l[y]] >= 0) marks[tri_index(it.lc[x], it.lc[y])] = 1;
+                    } else {
+                        for (int y = na; y < na + nb; ++y)
+                            if (cam_free[cam_l[y]] >= 0) marks[tri_index(it.lc[x], it.lc[y])] = 1;
                     }
-                    return fresh;
-                };
-                if (!o.items.empty() && (int(o.cams.size()) + count_fresh(o.cams) > w_cap || int(o.items.size()) >= max_items)) close_items(o);
-                {
-                    std::vector<int32_t> merged(o.cams.size() + size_t(na + nb));
+                }
+                C.items.push_back(it);
+            }
+            t.run_begin = static_cast<int32_t>(C.runs.size());
+            for (int u = 0; u < t.end - t.begin; ++u) {                          // an item is a run of one; a work item per 32 pairs
+                const Item& it = C.items[size_t(t.begin) + u];
+                const int na = it.a1 - it.a0, nb = it.b1 - it.b0;
+                const int rounds = ((nb ? na * nb : na * (na - 1) / 2) + 31) / 32;
+                for (int r = 0; r < rounds; ++r) C.runs.push_back(static_cast<uint32_t>(u) | (1u << 16) | (static_cast<uint32_t>(r) << 24));
+            }
+            t.n_runs = static_cast<int32_t>(C.runs.size()) - t.run_begin;
+            C.w_max = std::max(C.w_max, int(t.w));
+            C.tiles.push_back(t);
+            o = Open();
+        };
+        const int c0 = first_long + ci * kChunkLong, c1 = std::min(end_long, c0 + kChunkLong);
+        std::vector<int32_t> merged;
+        for (int d = c0; d < c1; ++d) {
+            const int beg = T.pt_start[d], k = T.pt_start[size_t(d) + 1] - beg;
+            const int ng = (k + 15) / 16;
+            if (ng > ng_max) {                         // re-index the open tiles for the larger group count
+                std::vector<Open> grown(size_t(ng) * ng);
+                for (int gi = 0; gi < ng_max; ++gi)
+                    for (int gj = gi; gj < ng_max; ++gj) grown[size_t(gi) * ng + gj] = std::move(open[size_t(gi) * ng_max + gj]);
+                open.swap(grown);
+                ng_max = ng;
+            }
+            for (int gi = 0; gi < ng; ++gi)
+                for (int gj = gi; gj < ng; ++gj) {
+                    Item it{};
+                    it.d = d;
+                    it.a0 = static_cast<uint16_t>(gi * 16); it.a1 = static_cast<uint16_t>(std::min(k, gi * 16 + 16));
+                    if (gj != gi) { it.b0 = static_cast<uint16_t>(gj * 16); it.b1 = static_cast<uint16_t>(std::min(k, gj * 16 + 16)); }
+                    const int na = it.a1 - it.a0, nb = it.b1 - it.b0;
+                    Open& o = open[size_t(gi) * ng_max + gj];
+                    // the item's cameras are ascending (group A, then group B); the open tile keeps its list sorted: one merge walk
+                    int32_t ic[32];
+                    for (int l = 0; l < na + nb; ++l) ic[l] = cam_of(beg + (l < na ? it.a0 + l : it.b0 + l - na));
+                    auto count_fresh = [&](const std::vector<int32_t>& have) {
+                        int fresh = 0;
+                        size_t h = 0;
+                        for (int l = 0; l < na + nb; ++l) {
+                            while (h < have.size() && have[h] < ic[l]) ++h;
+                            if (h == have.size() || have[h] != ic[l]) ++fresh;
+                        }
+                        return fresh;
+                    };
+                    if (!o.items.empty() && (int(o.cams.size()) + count_fresh(o.cams) > w_cap || int(o.items.size()) >= max_items)) close_items(o);
+                    merged.resize(o.cams.size() + size_t(na + nb));
                     merged.resize(static_cast<size_t>(std::set_union(o.cams.begin(), o.cams.end(), ic, ic + na + nb, merged.begin()) - merged.begin()));
                     o.cams.swap(merged);
+                    o.items.push_back(it);
                 }
-                o.items.push_back(it);
+        }
+        for (Open& o : open) close_items(o);
+    });
+
+    // ---- concatenate the chunks in order (normal tiles, then item tiles); chunk-local offsets become global
+    size_t n_tiles = 0, n_items = 0, n_runs = 0, n_tc = 0, n_marks = 0;
+    for (const std::vector<TileChunk>* cv : {&chunk_a, &chunk_b})
+        for (const TileChunk& C : *cv) {
+            n_tiles += C.tiles.size(); n_items += C.items.size(); n_runs += C.runs.size(); n_tc += C.tile_cams.size(); n_marks += C.tile_marks.size();
+        }
+    T.tiles.clear(); T.items.clear(); T.runs.clear(); T.tile_cams.clear(); T.tile_marks.clear();
+    T.tiles.reserve(n_tiles); T.items.reserve(n_items); T.runs.reserve(n_runs); T.tile_cams.reserve(n_tc); T.tile_marks.reserve(n_marks);
+    T.w_max = 0;
+    for (std::vector<TileChunk>* cv : {&chunk_a, &chunk_b})
+        for (TileChunk& C : *cv) {
+            const int32_t item0 = static_cast<int32_t>(T.items.size()), run0 = static_cast<int32_t>(T.runs.size());
+            const int32_t cam0 = static_cast<int32_t>(T.tile_cams.size()), mark0 = static_cast<int32_t>(T.tile_marks.size());
+            for (Tile t : C.tiles) {
+                if (t.flags & kTileSplit) { t.begin += item0; t.end += item0; }
+                t.cam_begin += cam0; t.slot_begin += mark0; t.run_begin += run0;
+                T.tiles.push_back(t);
             }
-    }
-    for (Open& o : open) close_items(o);
+            T.items.insert(T.items.end(), C.items.begin(), C.items.end());
+            T.runs.insert(T.runs.end(), C.runs.begin(), C.runs.end());
+            T.tile_cams.insert(T.tile_cams.end(), C.tile_cams.begin(), C.tile_cams.end());
+            T.tile_marks.insert(T.tile_marks.end(), C.tile_marks.begin(), C.tile_marks.end());
+            T.w_max = std::max(T.w_max, C.w_max);
+            C = TileChunk();
+        }
     return true;
 }
 

@@ -72,7 +72,7 @@ Flat Flatten(BundleData& bd) {
     return f;
 }
 
-msfm_ba* CreateOnDevice(const Flat& f, bool refine_focal_length) {
+msfm_ba_problem Describe(const Flat& f, bool refine_focal_length) {
     msfm_ba_problem pr;
     pr.n_cams = static_cast<int32_t>(f.cam_ids.size());
     pr.n_pts = static_cast<int32_t>(f.pt_ids.size());
@@ -81,6 +81,11 @@ msfm_ba* CreateOnDevice(const Flat& f, bool refine_focal_length) {
     pr.fx = f.fx; pr.fy = f.fy;
     pr.cams = f.cams.data(); pr.pts = f.pts.data(); pr.obs_uv = f.uv.data();
     pr.obs_cam = f.obs_cam.data(); pr.obs_pt = f.obs_pt.data(); pr.cam_const = f.cam_const.data();
+    return pr;
+}
+
+msfm_ba* CreateOnDevice(const Flat& f, bool refine_focal_length) {
+    const msfm_ba_problem pr = Describe(f, refine_focal_length);
     msfm_ba* ba = nullptr;
     device::Check(msfm_ba_create(device::Context(), &pr, &ba), "msfm_ba_create");
     return ba;
@@ -112,13 +117,50 @@ double BundleData::Debug() {
 
 CeresBundelOptimizer::CeresBundelOptimizer(const Parameters& params) : params_(params) {}
 
+CeresBundelOptimizer::~CeresBundelOptimizer() {
+    if (problem_ && device::Alive()) msfm_ba_destroy(problem_);      // the context's shutdown releases the device anyway
+}
+
+bool CeresBundelOptimizer::FilterStatistics(double max_reproj_error, std::vector<unsigned char>* obs_keep, std::vector<double>* pt_mean_error,
+                                            std::vector<int>* pt_kept, std::vector<double>* pt_max_parallax_deg) {
+    if (!problem_) return false;
+    int64_t sizes[3];
+    device::Check(msfm_ba_sizes(problem_, sizes), "msfm_ba_sizes");
+    if (obs_keep) obs_keep->assign(static_cast<size_t>(sizes[2]), 0);
+    if (pt_mean_error) pt_mean_error->assign(static_cast<size_t>(sizes[1]), 0.0);
+    if (pt_kept) pt_kept->assign(static_cast<size_t>(sizes[1]), 0);
+    if (pt_max_parallax_deg) pt_max_parallax_deg->assign(static_cast<size_t>(sizes[1]), 0.0);
+    static_assert(sizeof(int) == sizeof(int32_t), "int32_t outputs are handed out as int");
+    device::Check(msfm_ba_filter_stats(problem_, max_reproj_error, obs_keep ? obs_keep->data() : nullptr,
+                                       pt_mean_error ? pt_mean_error->data() : nullptr,
+                                       pt_kept ? reinterpret_cast<int32_t*>(pt_kept->data()) : nullptr,
+                                       pt_max_parallax_deg ? pt_max_parallax_deg->data() : nullptr), "msfm_ba_filter_stats");
+    return true;
+}
+
 bool CeresBundelOptimizer::Optimize(BundleData& bundle_data) {
     Flat f = Flatten(bundle_data);
     if (f.obs_cam.empty() || f.cam_ids.empty()) {
         std::cout << "Bundle Adjustment failed." << std::endl;
         return false;
     }
-    msfm_ba* ba = CreateOnDevice(f, params_.refine_focal_length);
+    // the device problem persists across calls: same sparsity pattern -> only the values travel; a changed map is analysed
+    // again into the same device arena (msfm_ba_update)
+    if (!problem_) {
+        problem_ = CreateOnDevice(f, params_.refine_focal_length);
+        last_reused_ = false;
+    } else {
+        const msfm_ba_problem pr = Describe(f, params_.refine_focal_length);
+        int32_t reused = 0;
+        device::Check(msfm_ba_update(problem_, &pr, &reused), "msfm_ba_update");
+        last_reused_ = reused != 0;
+    }
+    msfm_ba* ba = problem_;
+    {
+        int64_t up[2] = {0, 0};
+        device::Check(msfm_ba_last_upload(ba, up), "msfm_ba_last_upload");
+        last_h2d_bytes_ = up[0];
+    }
     msfm_ba_options opt;
     msfm_ba_default_options(&opt, static_cast<int32_t>(bundle_data.camera_poses.size()));   // :262-291
     msfm_ba_summary s;
@@ -127,7 +169,6 @@ bool CeresBundelOptimizer::Optimize(BundleData& bundle_data) {
     device::Check(msfm_ba_get_params(ba, f.cams.data(), f.pts.data()), "msfm_ba_get_params");
     double focal[2] = {f.fx, f.fy};
     device::Check(msfm_ba_get_focal(ba, focal), "msfm_ba_get_focal");
-    msfm_ba_destroy(ba);
     for (size_t i = 0; i < f.cam_ids.size(); ++i) {
         BundleData::CameraPose& cp = bundle_data.camera_poses[f.cam_ids[i]];
         double* rv = PoseData(cp.rvec, "rvec");

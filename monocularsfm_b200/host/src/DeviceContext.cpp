@@ -27,6 +27,8 @@ void Check(int rc, const char* what) {
     std::exit(EXIT_FAILURE);
 }
 
+bool Alive() { return g_ctx != nullptr; }
+
 void Shutdown() {
     if (g_ctx) msfm_destroy(g_ctx);
     g_ctx = nullptr;

@@ -10,6 +10,7 @@ namespace device {
 msfm_ctx* Context();
 void Check(int rc, const char* what);
 void Shutdown();
+bool Alive();      // false before the first Context() and after Shutdown()
 }  // namespace device
 }  // namespace MonocularSfM
 #endif

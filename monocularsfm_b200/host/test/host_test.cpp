@@ -5,9 +5,11 @@
 //   (noverify = the explicit opt-out of the geometric verification, for tests of the exact match lists)
 //   host_test two <a.u8> <na> <b.u8> <nb> <out.txt>   FeatureUtils::ComputeMatches / ComputeCrossMatches on raw files
 //   host_test ba <in.bin> <out.bin>    CeresBundelOptimizer::Optimize on a BundleData read from a flat binary file
+//   host_test ba_persist <in.bin> <out.bin>   three Optimize calls on ONE optimizer (same map, perturbed values, changed map) vs fresh ones
 //   host_test ransac <in.bin> <out.bin>  FeatureUtils::FilterMatches on float32 point pairs (no GPU)
 //   host_test scenegraph <script.txt> <out.txt>  SceneGraph driven by a script of I / M / F / Q lines (no GPU)
 //   host_test scenegraph_db <db> <min_matches> <out.txt>  SceneGraph::Load on a database + the same dump (no GPU)
+#include <cmath>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -200,6 +202,79 @@ static int run_ba(char** argv) {
     return 0;
 }
 
+// The optimizer object persists across Optimize calls like MapBuilder's bundle_optimizer_ (MapBuilder.cpp:92,582,618):
+//   call 1  the scene as read;  call 2  the same map with perturbed values (structure kept: only values travel);
+//   call 3  a changed map (every 7th landmark removed, one camera released from the constant set): analysed again into the same
+//   device object.  Every call is repeated by a FRESH optimizer on a copy of the same input; the costs must agree.
+// out: f64 [3][6] = reused, h2d bytes, final cost, fresh final cost, fresh h2d bytes, iterations
+static int run_ba_persist(char** argv) {
+    std::ifstream in(argv[2], std::ios::binary);
+    int32_t hdr[4];
+    in.read(reinterpret_cast<char*>(hdr), sizeof hdr);
+    double k[4];
+    in.read(reinterpret_cast<char*>(k), sizeof k);
+    std::vector<double> cams(hdr[0] * 6), pts(hdr[1] * 3), xy(hdr[2] * 2);
+    std::vector<int32_t> oc(hdr[2]), op(hdr[2]), cst(hdr[3]);
+    in.read(reinterpret_cast<char*>(cams.data()), cams.size() * 8);
+    in.read(reinterpret_cast<char*>(pts.data()), pts.size() * 8);
+    in.read(reinterpret_cast<char*>(xy.data()), xy.size() * 8);
+    in.read(reinterpret_cast<char*>(oc.data()), oc.size() * 4);
+    in.read(reinterpret_cast<char*>(op.data()), op.size() * 4);
+    in.read(reinterpret_cast<char*>(cst.data()), cst.size() * 4);
+    auto make = [&](double shift, bool changed) {
+        BundleData bd;
+        bd.K = cv::Mat(3, 3, CV_64F);
+        bd.K.at<double>(0, 0) = k[0]; bd.K.at<double>(1, 1) = k[1]; bd.K.at<double>(0, 2) = k[2]; bd.K.at<double>(1, 2) = k[3];
+        bd.K.at<double>(2, 2) = 1.0;
+        for (int c = 0; c < hdr[0]; ++c) {
+            cv::Mat r(3, 1, CV_64F), t(3, 1, CV_64F);
+            for (int j = 0; j < 3; ++j) { r.at<double>(j, 0) = cams[6 * c + j]; t.at<double>(j, 0) = cams[6 * c + 3 + j] + shift * ((c + j) % 3 - 1); }
+            bd.camera_poses[c] = BundleData::CameraPose(r, t);
+        }
+        for (int p = 0; p < hdr[1]; ++p) {
+            if (changed && p % 7 == 0) continue;
+            bd.landmarks[p].point3D = cv::Vec3d(pts[3 * p] + shift, pts[3 * p + 1] - shift, pts[3 * p + 2] + 0.5 * shift);
+        }
+        for (int i = 0; i < hdr[2]; ++i) {
+            if (changed && op[i] % 7 == 0) continue;
+            bd.landmarks[op[i]].measurements.push_back(BundleData::Measurement(oc[i], cv::Vec2d(xy[2 * i], xy[2 * i + 1])));
+        }
+        for (size_t i = 0; i < cst.size(); ++i)
+            if (!changed || i + 1 < cst.size() || cst.size() == 1) bd.constant_camera_pose.insert(cst[i]);
+        return bd;
+    };
+    CeresBundelOptimizer::Parameters params;
+    CeresBundelOptimizer persistent(params);
+    std::ofstream out(argv[3], std::ios::binary);
+    const double shifts[3] = {0.0, 0.01, 0.005};
+    for (int call = 0; call < 3; ++call) {
+        BundleData a = make(shifts[call], call == 2), b = make(shifts[call], call == 2);
+        if (!persistent.Optimize(a)) return 4;
+        CeresBundelOptimizer fresh(params);
+        if (!fresh.Optimize(b)) return 5;
+        const double rec[6] = {persistent.last_structure_reused() ? 1.0 : 0.0, static_cast<double>(persistent.last_h2d_bytes()), persistent.last_final_cost(),
+                               fresh.last_final_cost(), static_cast<double>(fresh.last_h2d_bytes()), static_cast<double>(persistent.last_iterations())};
+        out.write(reinterpret_cast<const char*>(rec), sizeof rec);
+        // both optimizers must have written the same parameters back
+        double worst = 0;
+        for (auto& el : a.landmarks)
+            for (int j = 0; j < 3; ++j) worst = std::max(worst, std::fabs(el.second.point3D(j) - b.landmarks[el.first].point3D(j)));
+        out.write(reinterpret_cast<const char*>(&worst), sizeof worst);
+        if (call == 2) {
+            // Map::FilterAllPoints3D's statistics from the resident problem
+            std::vector<unsigned char> keep;
+            std::vector<double> err, ang;
+            std::vector<int> kept;
+            if (!persistent.FilterStatistics(4.0, &keep, &err, &kept, &ang)) return 6;
+            double s[4] = {static_cast<double>(keep.size()), static_cast<double>(err.size()), 0, 0};
+            for (unsigned char v : keep) s[2] += v;
+            for (double v : err) s[3] += v;
+            out.write(reinterpret_cast<const char*>(s), sizeof s);
+        }
+    }
+    return 0;
+}
+
 // in: int32 n | float32 [n][2] pts1 | float32 [n][2] pts2 ; matches are (i, i).  out: uint8 [n] kept-mask
 static int run_ransac(char** argv) {
     std::ifstream in(argv[2], std::ios::binary);
@@ -302,6 +377,7 @@ int main(int argc, char** argv) {
     }
     if (mode == "two" && argc >= 7) return run_two(argv);
     if (mode == "ba" && argc >= 4) return run_ba(argv);
+    if (mode == "ba_persist" && argc >= 4) return run_ba_persist(argv);
     if (mode == "ransac" && argc >= 4) return run_ransac(argv);
     if (mode == "scenegraph" && argc >= 4) return run_scenegraph(argv);
     if (mode == "scenegraph_db" && argc >= 5) return run_scenegraph_db(argv);

@@ -372,3 +372,53 @@ def test_lm_solve_with_shared_focal_matches_oracle(ctx, golden_ba, name):
         ba0.linearize_focal(0.0)
     ba0.close()
     ba.close()
+
+
+def test_update_keeps_the_structure_for_the_same_pattern_and_rebuilds_for_another(ctx):
+    """msfm_ba_update: the device problem persists across Optimize calls.  (1) same sparsity pattern, other values: only values
+    are uploaded and the results equal those of a freshly created problem; (2) a grown map (more cameras, points, long tracks),
+    then a shrunk one: analysed again into the same object, again equal to a fresh problem and to the oracle."""
+    A = bo.make_problem(24, 900, 6, 3)
+    ba = _create(ctx, A)
+    first = ba.last_upload()
+    assert not first["reused"] and first["h2d_bytes"] > 0
+    ba.solve()
+    # (1) same pattern, perturbed values (what LocalBA / GlobalBA see when only poses and points moved)
+    rng = np.random.default_rng(7)
+    A2 = dict(A, cams=A["cams"] + rng.normal(0, 1e-3, A["cams"].shape), pts=A["pts"] + rng.normal(0, 1e-2, A["pts"].shape),
+              obs_uv=A["obs_uv"] + rng.normal(0, 0.1, A["obs_uv"].shape))
+    A2["cams"][A["cam_const"].astype(bool)] = A["cams"][A["cam_const"].astype(bool)]
+    assert ba.update(A2["cams"], A2["pts"], A2["obs_uv"], A2["obs_cam"], A2["obs_pt"], A2["cam_const"], A2["fx"], A2["fy"]) is True
+    up = ba.last_upload()
+    assert up["reused"] and up["h2d_bytes"] == 8 * (A["cams"].size + A["pts"].size + A["obs_uv"].size) < first["h2d_bytes"]
+    fresh = _create(ctx, A2)
+    r1, J1, c1 = ba.evaluate()
+    r2, J2, c2 = fresh.evaluate()
+    assert np.array_equal(r1, r2) and np.array_equal(J1, J2) and c1 == c2            # fp64 / fp32 per observation: deterministic
+    S1, rhs1, _, _ = ba.linearize(1e-4)
+    S2, rhs2, _, _ = fresh.linearize(1e-4)
+    assert np.abs(S1 - S2).max() <= 1e-6 * np.abs(S2).max() and np.abs(rhs1 - rhs2).max() <= 1e-9 * np.abs(rhs2).max()
+    s1, s2 = ba.solve(), fresh.solve()
+    assert s1["termination"] == 0 and abs(s1["final_cost"] - s2["final_cost"]) <= 1e-6 * s2["final_cost"]
+    fresh.close()
+    # (2) another pattern: larger with long tracks, then smaller; a different constant set counts as another pattern too
+    B = bo.make_long_track_problem()
+    C = bo.make_problem(9, 150, 4, 11)
+    Aconst = dict(A, cam_const=np.roll(A["cam_const"], 1))
+    for Q in (B, C, Aconst):
+        assert ba.update(Q["cams"], Q["pts"], Q["obs_uv"], Q["obs_cam"], Q["obs_pt"], Q["cam_const"], Q["fx"], Q["fy"]) is False
+        assert not ba.last_upload()["reused"]
+        fresh = _create(ctx, Q)
+        assert ba.structure() == fresh.structure()
+        r1, J1, c1 = ba.evaluate()
+        r2, J2, c2 = fresh.evaluate()
+        assert np.array_equal(r1, r2) and np.array_equal(J1, J2) and c1 == c2
+        r, J = bo.residual_jacobian_jets(Q["cams"], Q["pts"], Q["obs_uv"], Q["obs_cam"], Q["obs_pt"], Q["fx"], Q["fy"])
+        U, gc, V, gp, W = bo.build_normal_equations(r, J, Q["obs_cam"], Q["obs_pt"], len(Q["cams"]), len(Q["pts"]), Q["cam_const"])
+        So, rhso, _, _ = bo.schur_reduce(U, gc, V, gp, W, Q["obs_cam"], Q["obs_pt"], Q["cam_const"], 1e-4)
+        S1, rhs1, _, _ = ba.linearize(1e-4)
+        assert np.abs(S1 - So).max() <= 1e-5 * np.abs(So).max() and np.abs(rhs1 - rhso).max() <= 1e-5 * np.abs(rhso).max()
+        s1, s2 = ba.solve(), fresh.solve()
+        assert s1["termination"] == s2["termination"] and abs(s1["final_cost"] - s2["final_cost"]) <= 1e-6 * s2["final_cost"]
+        fresh.close()
+    ba.close()

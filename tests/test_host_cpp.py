@@ -268,6 +268,44 @@ def test_ceres_bundel_optimizer_dropin(tmp_path):
     assert abs(per_pt.mean() - after) < 1e-9
 
 
+@pytest.mark.gpu
+def test_optimizer_keeps_the_device_problem_across_calls(tmp_path):
+    """MapBuilder owns ONE CeresBundelOptimizer (MapBuilder.cpp:92) and calls Optimize on a map that changes between the calls.
+    The device problem persists (msfm_ba_update): same sparsity pattern -> only values are uploaded; a changed map is analysed
+    again into the same object.  Every call must give what a fresh optimizer gives on the same input."""
+    _need_exe()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ba_golden.npz"))
+    name = "ring16"
+    cams, pts = g[f"{name}/cams"], g[f"{name}/pts"]
+    cx, cy = 1080.0, 720.0
+    xy = g[f"{name}/obs_uv"] + [cx, cy]
+    oc, op = g[f"{name}/obs_cam"].astype(np.int32), g[f"{name}/obs_pt"].astype(np.int32)
+    const = np.nonzero(g[f"{name}/cam_const"])[0].astype(np.int32)
+    fin = tmp_path / "in.bin"
+    with open(fin, "wb") as f:
+        f.write(struct.pack("4i", len(cams), len(pts), len(oc), len(const)))
+        f.write(struct.pack("4d", float(g[f"{name}/fx"]), float(g[f"{name}/fy"]), cx, cy))
+        for arr in (cams, pts, xy):
+            f.write(np.ascontiguousarray(arr, np.float64).tobytes())
+        for arr in (oc, op, const):
+            f.write(arr.tobytes())
+    out = subprocess.run([EXE, "ba_persist", str(fin), str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr + out.stdout
+    raw = np.fromfile(tmp_path / "out.bin", np.float64)
+    calls = raw[:21].reshape(3, 7)
+    reused, h2d, cost, fresh_cost, fresh_h2d, iters, worst = calls.T
+    assert reused.tolist() == [0.0, 1.0, 0.0]
+    # the fp32 block sums are accumulated with atomics (order varies from launch to launch): same optimum, not the same bits
+    assert (np.abs(cost - fresh_cost) <= 1e-6 * fresh_cost).all(), (cost, fresh_cost)
+    assert (worst < 1e-5).all(), worst
+    values_only = (cams.size + pts.size + xy.size) * 8
+    assert h2d[1] == values_only and h2d[1] < 0.75 * h2d[0] and h2d[0] == fresh_h2d[0]
+    assert h2d[2] == fresh_h2d[2] < h2d[0]
+    n_keep, n_pts_now, kept_sum, err_sum = raw[21:25]
+    assert n_pts_now == len(pts) - len(range(0, len(pts), 7)) and n_keep == (op % 7 != 0).sum()
+    assert kept_sum >= 0.95 * n_keep and 0 < err_sum / n_pts_now < 2.0
+
+
 def _two_view_scene(seed, n_in, n_out, noise_px):
     """3-D points seen by two cameras (NEU intrinsics), `n_out` mismatched pairs appended; float32 pixel coordinates."""
     rng = np.random.default_rng(seed)

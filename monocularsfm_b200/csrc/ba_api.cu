@@ -106,7 +106,7 @@ struct msfm_ba {
     Tile* tiles = nullptr;
     Item* items = nullptr;
     uint32_t* runs = nullptr;
-    int32_t *tile_cams = nullptr, *tile_slots = nullptr, *blk_row = nullptr, *blk_col = nullptr;
+    int32_t *tile_cams = nullptr, *tile_free = nullptr, *tile_slots = nullptr, *blk_row = nullptr, *blk_col = nullptr;
     int32_t n_tiles = 0, w_max = 0, n_blocks = 0, first_long = 0, n_long = 0;
     uint8_t* obs_lpt = nullptr;
     double* long_V = nullptr;      // per long track: V^-1 | g_p (| Wf), written by the pre-pass of every linearisation
@@ -150,7 +150,7 @@ struct msfm_ba {
         P.refine_focal = refine_focal; P.pt_Wf = pt_Wf;
         P.pre = pre[which]; P.pts = pts[which]; P.obs_uv = obs_uv; P.obs_cam = obs_cam; P.obs_pt = obs_pt; P.obs_orig = obs_orig;
         P.obs_lcam = obs_lcam; P.pt_start = pt_start; P.pt_order = pt_order; P.cam_free = cam_free;
-        P.tiles = tiles; P.items = items; P.runs = runs; P.n_tiles = n_tiles; P.tile_cams = tile_cams; P.tile_slots = tile_slots;
+        P.tiles = tiles; P.items = items; P.runs = runs; P.n_tiles = n_tiles; P.tile_cams = tile_cams; P.tile_free = tile_free; P.tile_slots = tile_slots;
         P.obs_lpt = obs_lpt; P.first_long = first_long; P.n_long = n_long; P.long_V = long_V;
         P.n_blocks = n_blocks; P.blk_row = blk_row; P.blk_col = blk_col;
         P.sblk = sblk; P.tail = tail(); P.tl = tl; P.gpm_slot = ctx->comm ? ctx->comm_rank : 0; P.tile_counter = tile_counter;
@@ -294,6 +294,8 @@ static int build_problem(msfm_ba* b, const msfm_ba_problem* pr) {
         const char* e2 = getenv("MSFM_BA_TILE_PTS");
         if (e1 && atoi(e1) > 0) tp.max_obs = atoi(e1);
         if (e2 && atoi(e2) > 0) tp.max_pts = atoi(e2);
+        const char* e3 = getenv("MSFM_BA_MAX_RUN");
+        if (e3 && atoi(e3) > 0) tp.max_run = atoi(e3);
     }
     ba::Tiling T;
     // a landmark holds at most one measurement per image (tracks in Map.cpp are keyed by image): the pair products rely on it
@@ -357,6 +359,7 @@ static int build_problem(msfm_ba* b, const msfm_ba_problem* pr) {
         {reinterpret_cast<void**>(&b->tiles), T.tiles.size() * sizeof(Tile)}, {reinterpret_cast<void**>(&b->items), T.items.size() * sizeof(Item)},
         {reinterpret_cast<void**>(&b->runs), T.runs.size() * sizeof(uint32_t)},
         {reinterpret_cast<void**>(&b->tile_cams), T.tile_cams.size() * sizeof(int32_t)},
+        {reinterpret_cast<void**>(&b->tile_free), T.tile_free.size() * sizeof(int32_t)},
         {reinterpret_cast<void**>(&b->tile_slots), T.tile_slots.size() * sizeof(int32_t)},
         {reinterpret_cast<void**>(&b->blk_row), T.blk_row.size() * sizeof(int32_t)}, {reinterpret_cast<void**>(&b->blk_col), T.blk_col.size() * sizeof(int32_t)},
         {reinterpret_cast<void**>(&b->sysbuf), b->sys_bytes},
@@ -402,6 +405,7 @@ static int build_problem(msfm_ba* b, const msfm_ba_problem* pr) {
     H2D(b->items, T.items.data(), T.items.size() * sizeof(Item));
     H2D(b->runs, T.runs.data(), T.runs.size() * sizeof(uint32_t));
     H2D(b->tile_cams, T.tile_cams.data(), T.tile_cams.size() * sizeof(int32_t));
+    H2D(b->tile_free, T.tile_free.data(), T.tile_free.size() * sizeof(int32_t));
     H2D(b->tile_slots, T.tile_slots.data(), T.tile_slots.size() * sizeof(int32_t));
     H2D(b->blk_row, T.blk_row.data(), T.blk_row.size() * sizeof(int32_t));
     H2D(b->blk_col, T.blk_col.data(), T.blk_col.size() * sizeof(int32_t));

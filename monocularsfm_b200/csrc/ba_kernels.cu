@@ -424,9 +424,27 @@ __device__ __forceinline__ void diag_row_pair(const float* __restrict__ stage, c
     }
 }
 
+// Everything a CTA needs to know about a tile before it touches an observation, staged in shared memory one tile AHEAD (two
+// buffers): the Tile record, its local cameras, their free-camera indices and the block slots of its local camera pairs.
+// (Read from global memory at the point of use these were a chain of dependent L2 round trips at the top of every tile and one
+// exposed load per flushed block row: 12 % of the kernel's stall samples at `if (slot < 0)` alone, profiles/r02_k2_v6_source_lines.txt.)
+struct alignas(16) TileHdr {
+    Tile T;
+    int32_t cams[kTileCams];
+    int32_t free_[kTileCams];
+    int32_t slots[kTileCams * (kTileCams + 1) / 2];
+};
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // Shared-memory carve-up of the linearisation kernel
 struct FusedSmem {
-    size_t camacc, acc, stage, rbuf, qbuf, xybuf, ptV, ptg, ptWf, cam_start, cam_cursor, cam_obs, unit_info, run_items, lfree, misc, total;
+    size_t camacc, acc, stage, rbuf, qbuf, xybuf, ptV, ptg, ptWf, cam_start, cam_cursor, cam_obs, unit_info, run_items, hdr, misc, total;
 };
 __host__ __device__ inline FusedSmem fused_smem_layout(bool focal) {
     FusedSmem L;
@@ -445,7 +463,8 @@ __host__ __device__ inline FusedSmem fused_smem_layout(bool focal) {
     L.cam_obs = o; o += static_cast<size_t>(kTileObs) * sizeof(uint16_t);
     L.unit_info = o; o += static_cast<size_t>(kTilePts) * sizeof(uint32_t);
     L.run_items = o; o += static_cast<size_t>(kTileRunItems) * sizeof(uint32_t);
-    L.lfree = o; o += static_cast<size_t>(kTileCams) * sizeof(int32_t);
+    o = (o + 15) / 16 * 16;
+    L.hdr = o; o += 2 * sizeof(TileHdr);
     L.misc = o; o += 64;
     L.total = (o + 15) / 16 * 16;
     return L;
@@ -545,20 +564,40 @@ fused_linearize_kernel(Problem P, double inv_radius) {
     uint16_t* cam_obs = reinterpret_cast<uint16_t*>(smem_raw + L.cam_obs);        // observation rows bucketed by local camera
     uint32_t* unit_info = reinterpret_cast<uint32_t*>(smem_raw + L.unit_info);       // obs base (16) | nA (8) | nB (8)
     uint32_t* run_items = reinterpret_cast<uint32_t*>(smem_raw + L.run_items);
-    int32_t* lfree = reinterpret_cast<int32_t*>(smem_raw + L.lfree);
-    int32_t* misc = reinterpret_cast<int32_t*>(smem_raw + L.misc);                   // [0] tile, [1] work-queue cursor
+    TileHdr* hdr = reinterpret_cast<TileHdr*>(smem_raw + L.hdr);
+    int32_t* misc = reinterpret_cast<int32_t*>(smem_raw + L.misc);                   // [1] work-queue cursor, [4], [5] tile index of header 0 / 1
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* tail = P.tail;
     double cost_local = 0.0, gpmax_local = 0.0;
     double ff[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};        // focal block sums of this thread's points
     if (tid <= kTileCams) cam_start[tid] = 0;
+    // ---- tile pipeline: header `cur` is complete when a tile starts; the Tile record of the next tile is copied while phases
+    //      A - C run, its camera / slot tables while phase E runs; the index of the tile after next comes from an atomic whose
+    //      latency hides behind phase A
+    if (tid == 0) { misc[4] = atomicAdd(P.tile_counter, 1); misc[5] = atomicAdd(P.tile_counter, 1); }
+    __syncthreads();
+    {
+        const int t0 = misc[4];
+        if (t0 < P.n_tiles) {
+            const Tile T0 = P.tiles[t0];
+            if (tid == 0) hdr[0].T = T0;
+            if (tid < T0.w) { hdr[0].cams[tid] = __ldg(P.tile_cams + T0.cam_begin + tid); hdr[0].free_[tid] = __ldg(P.tile_free + T0.cam_begin + tid); }
+            for (int i = tid; i < T0.w * (T0.w + 1) / 2; i += kFusedThreads) hdr[0].slots[i] = __ldg(P.tile_slots + T0.slot_begin + i);
+        }
+    }
+    __syncthreads();
+    int cur = 0;
 
     for (;;) {
-        if (tid == 0) { misc[0] = atomicAdd(P.tile_counter, 1); misc[1] = 0; }
-        __syncthreads();
-        const int ti = misc[0];
+        const int ti = misc[4 + cur];
         if (ti >= P.n_tiles) break;
-        const Tile T = P.tiles[ti];
+        const TileHdr& H = hdr[cur];
+        const Tile T = H.T;
+        const int ti_next = misc[4 + (cur ^ 1)];
+        int ti_after = 0;
+        if (tid == 0) { ti_after = atomicAdd(P.tile_counter, 1); misc[1] = 0; }
+        if (tid < 3 && ti_next < P.n_tiles)
+            cp_async16(reinterpret_cast<unsigned char*>(&hdr[cur ^ 1].T) + 16 * tid, reinterpret_cast<const unsigned char*>(P.tiles + ti_next) + 16 * tid);
         const bool split = (T.flags & kTileSplit) != 0;
         const int n_units = T.end - T.begin;
         const int nb = T.w * (T.w + 1) / 2;
@@ -567,7 +606,6 @@ fused_linearize_kernel(Problem P, double inv_radius) {
             for (int i = tid; i < nb * (kBlkStride / 4); i += kFusedThreads) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int i = tid; i < T.w * CV; i += kFusedThreads) camacc[i] = 0.0;
             for (int i = tid; i < T.n_runs && i < kTileRunItems; i += kFusedThreads) run_items[i] = __ldg(P.runs + T.run_begin + i);
-            if (tid < T.w) lfree[tid] = __ldg(P.cam_free + __ldg(P.tile_cams + T.cam_begin + tid));
         }
         // ---- A: this thread's observation
         int unit = 0, f_mine = -1, lcam = 0;
@@ -600,9 +638,9 @@ fused_linearize_kernel(Problem P, double inv_radius) {
             }
             float* srow = stage + tid * kStageStride;
             if (valid) {
-                const int cam = __ldg(P.obs_cam + o);
-                f_mine = __ldg(P.cam_free + cam);
-                const int p = __ldg(P.pt_order + d);
+                const int cam = H.cams[lcam];
+                f_mine = H.free_[lcam];
+                const int p = split ? __ldg(P.pt_order + d) : __ldg(P.obs_pt + o);      // the caller's point index
                 const double X[3] = {P.pts[3 * p], P.pts[3 * p + 1], P.pts[3 * p + 2]};
                 const double2 uv = __ldg(reinterpret_cast<const double2*>(P.obs_uv) + o);
                 double r[2], Jc[12], Jp[6], xy[2];
@@ -623,16 +661,26 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                 if (kFocal) { xybuf[2 * tid] = xy[0]; xybuf[2 * tid + 1] = xy[1]; }
             }
         }
+        if (tid < 3) cp_async_wait_all();                       // the next tile's record has landed (visible after the barrier)
         __syncthreads();
+        if (tid == 0) misc[4 + cur] = ti_after;                 // this header slot serves the tile after next
         // ---- B: this thread's point: V^-1, g_p
         {
-            if (tid < n_units) {
-                const uint32_t ui = unit_info[tid];
-                double Vinv[6], gp[3], Wf[6] = {0, 0, 0, 0, 0, 0};
-                if (!split) {
+            // sB threads per point (a power of two <= 8 that keeps all points of the tile inside the CTA): each sums every sB-th
+            // observation, the partial sums meet through shuffles.  (One thread per point left 50 - 250 of the 512 threads with a
+            // serial loop over the whole track while the others waited at the barrier: 9 % of the stall samples.)
+            int sB = 1, lgB = 0;
+            if (!split)
+                while (sB < 8 && n_units * sB * 2 <= kFusedThreads) { sB *= 2; ++lgB; }
+            const int u = tid >> lgB, sub = tid & (sB - 1);
+            const bool mine = u < n_units;
+            double Vinv[6], gp[3], Wf[6] = {0, 0, 0, 0, 0, 0};
+            if (!split) {
+                double v[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, f4[4] = {0, 0, 0, 0}, cl = 0.0;
+                if (mine) {
+                    const uint32_t ui = unit_info[u];
                     const int ob = static_cast<int>(ui & 0xFFFFu), k = static_cast<int>(ui >> 16);
-                    double v[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, f4[4] = {0, 0, 0, 0}, cl = 0.0;
-                    for (int j = 0; j < k; ++j) {
+                    for (int j = sub; j < k; j += sB) {
                         const float* sr = stage + (ob + j) * kStageStride;
                         const double j0 = sr[18], j1 = sr[19], j2 = sr[20], j3 = sr[21], j4 = sr[22], j5 = sr[23];
                         const double r0 = rbuf[2 * (ob + j)], r1 = rbuf[2 * (ob + j) + 1];
@@ -646,17 +694,31 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                             f4[0] += xp * xp; f4[1] += yp * yp; f4[2] += xp * r0; f4[3] += yp * r1;
                         }
                     }
+                }
+                cost_local += cl;
+                for (int off = 1; off < sB; off <<= 1) {               // all 32 lanes take part (sB divides 32: groups do not straddle warps)
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) g[q] += __shfl_xor_sync(0xffffffffu, g[q], off);
+                    if (kFocal) {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) Wf[q] += __shfl_xor_sync(0xffffffffu, Wf[q], off);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) f4[q] += __shfl_xor_sync(0xffffffffu, f4[q], off);
+                    }
+                }
+                if (mine && sub == 0) {
                     // Marquardt damping D^2 = max(diag, 1e-6) / radius  (Ceres LM strategy with Jacobi scaling, min_lm_diagonal)
                     v[0] += fmax(v[0], 1e-6) * inv_radius;
                     v[3] += fmax(v[3], 1e-6) * inv_radius;
                     v[5] += fmax(v[5], 1e-6) * inv_radius;
                     sym3_inverse(v, Vinv);
                     gp[0] = g[0]; gp[1] = g[1]; gp[2] = g[2];
-                    cost_local += cl;
                     gpmax_local = fmax(gpmax_local, fmax(fabs(gp[0]), fmax(fabs(gp[1]), fabs(gp[2]))));
                     if (kFocal) {
                         // T = Wf V^-1 (2x3);  F -= T Wf^T,  rhs_f += T g_p - g_f   (the point is eliminated from the focal block too)
-                        double* gw = P.pt_Wf + 6 * static_cast<size_t>(T.begin + tid);
+                        double* gw = P.pt_Wf + 6 * static_cast<size_t>(T.begin + u);
 #pragma unroll
                         for (int q = 0; q < 6; ++q) gw[q] = Wf[q];
                         const double T0[3] = {Wf[0] * Vinv[0] + Wf[1] * Vinv[1] + Wf[2] * Vinv[2], Wf[0] * Vinv[1] + Wf[1] * Vinv[3] + Wf[2] * Vinv[4],
@@ -670,24 +732,26 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                         ff[4] += (T1[0] * gp[0] + T1[1] * gp[1] + T1[2] * gp[2]) - f4[3];
                         ff[5] += f4[2]; ff[6] += f4[3]; ff[7] += f4[0]; ff[8] += f4[1];
                     }
-                } else {
-                    // a long track: the pre-pass reduced over the whole track
-                    const int d = P.items[T.begin + tid].d;
-                    const double* rec = P.long_V + static_cast<size_t>(d - P.first_long) * (kFocal ? 15 : 9);
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) Vinv[q] = rec[q];
-                    gp[0] = rec[6]; gp[1] = rec[7]; gp[2] = rec[8];
-                    if (kFocal) {
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) Wf[q] = rec[9 + q];
-                    }
                 }
+            } else if (mine) {
+                // a long track: the pre-pass reduced over the whole track
+                const int d = P.items[T.begin + u].d;
+                const double* rec = P.long_V + static_cast<size_t>(d - P.first_long) * (kFocal ? 15 : 9);
 #pragma unroll
-                for (int q = 0; q < 6; ++q) ptV[6 * tid + q] = static_cast<float>(Vinv[q]);
-                ptg[3 * tid] = gp[0]; ptg[3 * tid + 1] = gp[1]; ptg[3 * tid + 2] = gp[2];
+                for (int q = 0; q < 6; ++q) Vinv[q] = rec[q];
+                gp[0] = rec[6]; gp[1] = rec[7]; gp[2] = rec[8];
                 if (kFocal) {
 #pragma unroll
-                    for (int q = 0; q < 6; ++q) ptWf[6 * tid + q] = Wf[q];
+                    for (int q = 0; q < 6; ++q) Wf[q] = rec[9 + q];
+                }
+            }
+            if (mine && sub == 0) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) ptV[6 * u + q] = static_cast<float>(Vinv[q]);
+                ptg[3 * u] = gp[0]; ptg[3 * u + 1] = gp[1]; ptg[3 * u + 2] = gp[2];
+                if (kFocal) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) ptWf[6 * u + q] = Wf[q];
                 }
             }
             // bucket starts of the per-camera observation lists (the histogram of phase A, scanned in place)
@@ -719,6 +783,14 @@ fused_linearize_kernel(Problem P, double inv_radius) {
             }
         }
         __syncthreads();
+        // the next tile's camera / free-index / slot tables, copied asynchronously under phase E
+        if (ti_next < P.n_tiles) {
+            TileHdr& N = hdr[cur ^ 1];
+            const int wn = N.T.w, cbn = N.T.cam_begin, sbn = N.T.slot_begin;
+            if (tid < wn) cp_async4(N.cams + tid, P.tile_cams + cbn + tid);
+            else if (tid >= 32 && tid - 32 < wn) cp_async4(N.free_ + (tid - 32), P.tile_free + cbn + (tid - 32));
+            for (int i = tid; i < wn * (wn + 1) / 2; i += kFusedThreads) cp_async4(N.slots + i, P.tile_slots + sbn + i);
+        }
         // ---- E: work queue: camera items first, then one item per unit
         {
             constexpr int kCamSplit = 4;                    // every camera part is summed by four items (a quarter of the list each)
@@ -844,19 +916,19 @@ fused_linearize_kernel(Problem P, double inv_radius) {
                 }
             }
         }
+        cp_async_wait_all();
         __syncthreads();
         // ---- flush the tile: 6x6 blocks with vector reductions, camera vectors with fp64 reductions
-        const int32_t* slots = P.tile_slots + T.slot_begin;
         for (int u = tid; u < nb * 9; u += kFusedThreads) {
             const int b = u / 9, q4 = u - 9 * b;
-            const int slot = __ldg(slots + b);
+            const int slot = H.slots[b];
             if (slot < 0) continue;
             const float4 v4 = reinterpret_cast<const float4*>(acc + b * kBlkStride)[q4];
             atomicAdd(reinterpret_cast<float4*>(P.sblk + static_cast<size_t>(slot) * 36) + q4, v4);
         }
         for (int u = tid; u < T.w * CV; u += kFusedThreads) {
             const int l = u / CV, e = u - l * CV;
-            const int f = lfree[l];
+            const int f = H.free_[l];
             if (f < 0) continue;
             double* dst;
             if (e < 6) dst = tail + P.tl.rhs + f * 6 + e;
@@ -867,6 +939,7 @@ fused_linearize_kernel(Problem P, double inv_radius) {
         }
         if (tid <= kTileCams) cam_start[tid] = 0;               // the histogram of the next tile
         __syncthreads();
+        cur ^= 1;
     }
     // ---- scalars: one fp64 atomic per CTA
     __shared__ double sh_c[kFusedThreads / 32], sh_g[kFusedThreads / 32];

@@ -22,6 +22,8 @@ struct TilingParams {
     int max_pts = kTilePts;    // max points per normal tile (<= kTilePts)
     int max_obs = kTileObs;    // max observations per normal tile (<= kTileObs)
     int max_items = kTileItems;
+    int max_run = 16;          // units per run (<= 255).  A run is ONE work item per 32 camera pairs, i.e. the load-balance grain of
+                               // the pair phase: 255 -> 16 took 4.5 % off the kernel at configs[4] (profiles/r02_k2_v7_ab.txt)
 };
 
 struct Tiling {
@@ -36,6 +38,7 @@ struct Tiling {
     std::vector<uint32_t> runs;         // per tile, the work items of the pair phase: first unit of a run of units with identical
                                         // camera lists (16 bits) | units in the run (8 bits) | round of 32 camera pairs (8 bits)
     std::vector<int32_t> tile_cams;
+    std::vector<int32_t> tile_free;     // parallel to tile_cams: cam_free of the local camera (assign_slots)
     std::vector<int32_t> tile_marks;    // per tile, tri(w) entries: 1 if some point of the tile couples the two local cameras
     std::vector<int32_t> tile_slots;    // same shape: global block slot or -1 (assign_slots)
     int w_max = 0;
@@ -189,6 +192,7 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
     const int w_cap = kTileCams;
     const int max_pts = std::max(1, std::min(prm.max_pts, kTilePts)), max_obs = std::max(32, std::min(prm.max_obs, kTileObs));
     const int max_items = std::max(1, std::min(prm.max_items, kTileItems));
+    const int max_run = std::max(1, std::min(prm.max_run, 255));
     const int n_cam_slots = std::max(1, n_cams);
     auto cam_of = [&](int dev_obs) { return dev_cam[dev_obs]; };
 
@@ -215,14 +219,14 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
             for (int a = T.pt_start[d0]; a < T.pt_start[d1]; ++a) T.obs_lcam[a] = static_cast<uint8_t>(lidx[cam_of(a)]);
             for (int d = d0; d < d1; ++d)
                 for (int a = T.pt_start[d]; a < T.pt_start[size_t(d) + 1]; ++a) T.obs_lpt[a] = static_cast<uint8_t>(d - d0);
-            // runs of consecutive points with identical camera lists (at most 255 points each), one work item per 32 camera
+            // runs of consecutive points with identical camera lists (at most max_run points each), one work item per 32 camera
             // pairs; the coupling marks are those of the run's first point
             t.run_begin = static_cast<int32_t>(C.runs.size());
             for (int d = d0; d < d1;) {
                 int e = d + 1;
                 const int kd = T.pt_start[size_t(d) + 1] - T.pt_start[d];
                 const int32_t* cd = dev_cam.data() + T.pt_start[d];
-                while (e < d1 && e - d < 255 && T.pt_start[size_t(e) + 1] - T.pt_start[e] == kd &&
+                while (e < d1 && e - d < max_run && T.pt_start[size_t(e) + 1] - T.pt_start[e] == kd &&
                        std::equal(cd, cd + kd, dev_cam.data() + T.pt_start[e])) ++e;
                 for (int a = 0; a < kd; ++a) {
                     if (cam_free[cd[a]] < 0) continue;
@@ -410,6 +414,8 @@ inline void assign_slots(Tiling& T, const int32_t* cam_free, int n_free, const s
         T.blk_rowptr[size_t(fa) + 1] = static_cast<int32_t>(T.blk_col.size());
     }
     T.tile_slots.assign(T.tile_marks.size(), -1);
+    T.tile_free.resize(T.tile_cams.size());
+    for (size_t i = 0; i < T.tile_cams.size(); ++i) T.tile_free[i] = cam_free[T.tile_cams[i]];
     const int n_tiles = static_cast<int>(T.tiles.size());
     parallel_ranges(n_tiles, [&](int t0, int t1) {
         for (int ti = t0; ti < t1; ++ti) {

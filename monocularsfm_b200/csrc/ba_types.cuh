@@ -78,6 +78,7 @@ struct Problem {
     const uint32_t* runs;           // first unit of the run inside its tile (16 bits) | units (8 bits) | round of 32 pairs (8 bits)
     int32_t n_tiles;
     const int32_t* tile_cams;
+    const int32_t* tile_free;       // parallel to tile_cams: cam_free of the local camera (-1: constant pose)
     const int32_t* tile_slots;
     int32_t first_long, n_long;     // device points [first_long, first_long + n_long) are long tracks (more than 32 observations)
     double* long_V;                 // [n_long][9 (+6)]  per long track: V^-1 (6) | g_p (3) (| Wf (6)), written by the pre-pass

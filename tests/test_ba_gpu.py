@@ -394,7 +394,8 @@ def test_update_keeps_the_structure_for_the_same_pattern_and_rebuilds_for_anothe
     fresh = _create(ctx, A2)
     r1, J1, c1 = ba.evaluate()
     r2, J2, c2 = fresh.evaluate()
-    assert np.array_equal(r1, r2) and np.array_equal(J1, J2) and c1 == c2            # fp64 / fp32 per observation: deterministic
+    # residuals and Jacobians are computed per observation (deterministic); the cost is summed with atomics
+    assert np.array_equal(r1, r2) and np.array_equal(J1, J2) and abs(c1 - c2) <= 1e-12 * c2
     S1, rhs1, _, _ = ba.linearize(1e-4)
     S2, rhs2, _, _ = fresh.linearize(1e-4)
     assert np.abs(S1 - S2).max() <= 1e-6 * np.abs(S2).max() and np.abs(rhs1 - rhs2).max() <= 1e-9 * np.abs(rhs2).max()
@@ -412,7 +413,7 @@ def test_update_keeps_the_structure_for_the_same_pattern_and_rebuilds_for_anothe
         assert ba.structure() == fresh.structure()
         r1, J1, c1 = ba.evaluate()
         r2, J2, c2 = fresh.evaluate()
-        assert np.array_equal(r1, r2) and np.array_equal(J1, J2) and c1 == c2
+        assert np.array_equal(r1, r2) and np.array_equal(J1, J2) and abs(c1 - c2) <= 1e-12 * c2
         r, J = bo.residual_jacobian_jets(Q["cams"], Q["pts"], Q["obs_uv"], Q["obs_cam"], Q["obs_pt"], Q["fx"], Q["fy"])
         U, gc, V, gp, W = bo.build_normal_equations(r, J, Q["obs_cam"], Q["obs_pt"], len(Q["cams"]), len(Q["pts"]), Q["cam_const"])
         So, rhso, _, _ = bo.schur_reduce(U, gc, V, gp, W, Q["obs_cam"], Q["obs_pt"], Q["cam_const"], 1e-4)

@@ -50,6 +50,15 @@ def main():
     ba = ctx.ba_create(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"])
     s3 = ba.solve()
     assert s3["termination"] == 0 and ba.solver_info()["kind"].startswith("band"), (s3, ba.solver_info())
+    # the same object serves the next problems (msfm_ba_update): same pattern (values only), a larger one (the arena grows),
+    # a smaller one (the arena is re-used)
+    assert ba.update(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["cam_const"], P["fx"], P["fy"]) is True
+    assert ba.solve()["termination"] == 0
+    for Q in (bo.make_long_track_problem(n_cams=130, n_pts=700), bo.make_problem(9, 60, 4, 2)):
+        assert ba.update(Q["cams"], Q["pts"], Q["obs_uv"], Q["obs_cam"], Q["obs_pt"], Q["cam_const"], Q["fx"], Q["fy"]) is False
+        ba.linearize(1e-4)
+        assert ba.solve()["termination"] == 0
+        ba.filter_stats(4.0)
     ba.close()
     # a WIDE band (ring with tracks spanning up to 64 cameras, the generator of bench.py): 16 tiles below the diagonal, so the
     # back substitution runs on CTA 0 plus 12 helper CTAs (flags, fp64 reductions into zfar)

@@ -61,7 +61,8 @@ class BASummary(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libmsfm_b200.so")
+    # MSFM_B200_LIB: another build of the same library (A/B measurements of kernel variants, tools/dev/build_variants.sh)
+    return os.environ.get("MSFM_B200_LIB") or os.path.join(_HERE, "libmsfm_b200.so")
 
 
 def header_path() -> str:

@@ -323,7 +323,7 @@ __device__ __forceinline__ void point_pass1(const Problem& P, int beg, int end, 
 // 28 floats = 7 x 16 bytes: 128-bit loads; rows r and r' collide on a bank group only when r = r' mod 8.
 constexpr int kStageStride = 28;
 constexpr int kFusedThreads = kTileObs;       // one thread per observation of a tile
-constexpr int kTileRunItems = 1024;           // work items of the pair phase staged in shared memory (more: read from global)
+constexpr int kTileRunItems = 2 * kTileObs;           // work items of the pair phase staged in shared memory (more: read from global)
 
 // acc[0..5] += v[0..5] on shared memory, 8-byte aligned.  sm_100 has no native fp32 shared-memory atomic add (atomicAdd
 // compiles to an LDS / FADD / ATOMS.CAST.SPIN loop per element, one after the other); here a row of a block is three 64-bit
@@ -545,7 +545,7 @@ long_track_prepass_kernel(Problem P, double inv_radius) {
 // (v4 of this kernel let every observation thread add its diagonal contribution itself: 512 threads into 32 cameras' accumulators
 // at the same instant, 16-way compare-and-swap contention, 86k cycles per tile — profiles/r02_k2_history.txt.)
 template <bool kFocal>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+__global__ void __launch_bounds__(kFusedThreads, kCtasPerSm)
 fused_linearize_kernel(Problem P, double inv_radius) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CV = kFocal ? 30 : 18;         // per local camera: rhs[6] | gc[6] | udiag[6] (| border B [6][2])
@@ -1271,7 +1271,12 @@ cudaError_t ba_launch_linearize(const Problem& P, double inv_radius, int num_sms
     if (P.refine_focal) e = cudaFuncSetAttribute(fused_linearize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     else e = cudaFuncSetAttribute(fused_linearize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
+    if (kCtasPerSm > 1) {      // two CTAs per SM need (nearly) the whole shared memory of the SM
+        if (P.refine_focal) e = cudaFuncSetAttribute(fused_linearize_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        else e = cudaFuncSetAttribute(fused_linearize_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return e;
+    }
+    const int grid = P.n_tiles < num_sms * kCtasPerSm ? P.n_tiles : num_sms * kCtasPerSm;
     if (P.refine_focal) fused_linearize_kernel<true><<<grid, kFusedThreads, smem, st>>>(P, inv_radius);
     else fused_linearize_kernel<false><<<grid, kFusedThreads, smem, st>>>(P, inv_radius);
     return cudaGetLastError();
@@ -1287,7 +1292,7 @@ cudaError_t ba_launch_backsub(const Problem& P, double inv_radius, const double*
     if (P.n_pts <= 0) return cudaSuccess;
     // normal tiles: thread-per-observation kernel; long tracks + unobserved points (device points >= first_long): warp per point
     if (P.first_long > 0 && P.n_tiles > 0) {
-        const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
+        const int grid = P.n_tiles < num_sms * kCtasPerSm ? P.n_tiles : num_sms * kCtasPerSm;
         backsub_tile_kernel<<<grid, kTileObs, 0, st>>>(P, inv_radius, dc, pts_new, out);
     }
     const int rest = P.n_pts - P.first_long;

@@ -156,7 +156,7 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
                 const uint64_t c0 = uint64_t(cc[0]) & 0xFFFFF;
                 const uint64_t c1 = e - b > 1 ? uint64_t(cc[1]) & 0xFFFFF : c0;
                 const uint64_t c2 = e - b > 2 ? uint64_t(cc[2]) & 0xFFFFF : c1;
-                k = (uint64_t(e - b > 32 ? 1 : 0) << 62) | (c0 << 40) | (c1 << 20) | c2;
+                k = (uint64_t(e - b > kLongTrack ? 1 : 0) << 62) | (c0 << 40) | (c1 << 20) | c2;
             }
             sk[p] = SortKey{k, h, static_cast<int32_t>(e - b), p};
         }
@@ -174,7 +174,7 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
     for (int d = 0; d < n_pts; ++d) {
         T.pt_order[d] = sk[d].idx;
         T.pt_start[size_t(d) + 1] = T.pt_start[d] + sk[d].k;
-        if (first_long == n_pts && (sk[d].k == 0 || sk[d].k > 32)) first_long = d;
+        if (first_long == n_pts && (sk[d].k == 0 || sk[d].k > kLongTrack)) first_long = d;
         if (end_long == n_pts && sk[d].k == 0) end_long = d;
     }
     sk.clear(); sk.shrink_to_fit();
@@ -325,7 +325,7 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
         std::vector<int32_t> merged;
         for (int d = c0; d < c1; ++d) {
             const int beg = T.pt_start[d], k = T.pt_start[size_t(d) + 1] - beg;
-            const int ng = (k + 15) / 16;
+            const int ng = (k + kItemGroup - 1) / kItemGroup;
             if (ng > ng_max) {                         // re-index the open tiles for the larger group count
                 std::vector<Open> grown(size_t(ng) * ng);
                 for (int gi = 0; gi < ng_max; ++gi)
@@ -337,8 +337,8 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
                 for (int gj = gi; gj < ng; ++gj) {
                     Item it{};
                     it.d = d;
-                    it.a0 = static_cast<uint16_t>(gi * 16); it.a1 = static_cast<uint16_t>(std::min(k, gi * 16 + 16));
-                    if (gj != gi) { it.b0 = static_cast<uint16_t>(gj * 16); it.b1 = static_cast<uint16_t>(std::min(k, gj * 16 + 16)); }
+                    it.a0 = static_cast<uint16_t>(gi * kItemGroup); it.a1 = static_cast<uint16_t>(std::min(k, gi * kItemGroup + kItemGroup));
+                    if (gj != gi) { it.b0 = static_cast<uint16_t>(gj * kItemGroup); it.b1 = static_cast<uint16_t>(std::min(k, gj * kItemGroup + kItemGroup)); }
                     const int na = it.a1 - it.a0, nb = it.b1 - it.b0;
                     Open& o = open[size_t(gi) * ng_max + gj];
                     // the item's cameras are ascending (group A, then group B); the open tile keeps its list sorted: one merge walk

@@ -40,10 +40,25 @@ struct Item {
     uint8_t lc[32];               // local camera of lane l: lanes 0 .. nA-1 hold group A, nA .. nA+nB-1 group B
 };
 constexpr int32_t kTileSplit = 1;
+// Tile shape.  MSFM_K2_SMALL_TILES=1 (a build-time experiment): half-size tiles with 24 local cameras so that
+// TWO 256-thread CTAs of the linearisation kernel fit one SM (102 KB of shared memory each) and overlap each other's barriers.
+#ifndef MSFM_K2_SMALL_TILES
+#define MSFM_K2_SMALL_TILES 0
+#endif
+#if MSFM_K2_SMALL_TILES
+constexpr int kTileCams = 24;
+constexpr int kTileObs = 256;
+constexpr int kTilePts = 128;
+constexpr int kCtasPerSm = 2;
+#else
 constexpr int kTileCams = 32;          // local cameras per tile (shared-memory accumulator = 528 blocks)
 constexpr int kTileObs = 512;          // observations per tile = threads of the linearisation kernel
 constexpr int kTilePts = 256;          // points per normal tile
-constexpr int kTileItems = 16;         // items per item tile (32 observation lanes each)
+constexpr int kCtasPerSm = 1;
+#endif
+constexpr int kLongTrack = kTileCams;  // a point with more observations than this is a long track (cut into item groups)
+constexpr int kItemGroup = kTileCams / 2;   // observations per group of a long track: an item couples two groups = at most kTileCams lanes
+constexpr int kTileItems = kTileObs / 32;   // items per item tile (one warp of observation lanes each)
 constexpr int kBlkStride = 36;         // floats per 6x6 block in the shared-memory accumulator (16-byte aligned rows of 4)
 
 // Offsets (in doubles) into the fp64 "tail" of the system: everything of the reduced system that is not a 6x6 block.

@@ -48,11 +48,13 @@ struct Tiling {
 
 inline int tri_index(int la, int lb) { return lb * (lb + 1) / 2 + la; }   // la <= lb
 
-// f(begin, end) over [0, n) on up to 8 host threads (the analysis of a 5 M-observation problem is ~0.5 s on one)
+constexpr int kMaxHostThreads = 16;
+
+// f(begin, end) over [0, n) on up to kMaxHostThreads host threads (the analysis of a 5 M-observation problem is ~0.5 s on one)
 template <class F>
 inline void parallel_ranges(int n, F f) {
     int nt = static_cast<int>(std::thread::hardware_concurrency());
-    nt = std::max(1, std::min(8, nt));
+    nt = std::max(1, std::min(kMaxHostThreads, nt));
     if (n < 20000 || nt == 1) { f(0, n); return; }
     std::vector<std::thread> th;
     const int step = (n + nt - 1) / nt;
@@ -67,7 +69,7 @@ inline void parallel_ranges(int n, F f) {
 template <class T, class Less>
 inline void parallel_sort(std::vector<T>& v, Less less) {
     int nt = static_cast<int>(std::thread::hardware_concurrency());
-    nt = std::max(1, std::min(8, nt));
+    nt = std::max(1, std::min(kMaxHostThreads, nt));
     const size_t n = v.size();
     if (n < 50000 || nt == 1) { std::sort(v.begin(), v.end(), less); return; }
     int parts = 1;
@@ -93,7 +95,7 @@ inline void parallel_sort(std::vector<T>& v, Less less) {
 template <class F>
 inline void parallel_chunks(int n_chunks, F f) {
     int nt = static_cast<int>(std::thread::hardware_concurrency());
-    nt = std::max(1, std::min(std::min(8, nt), n_chunks));
+    nt = std::max(1, std::min(std::min(kMaxHostThreads, nt), n_chunks));
     if (nt <= 1) { for (int c = 0; c < n_chunks; ++c) f(c); return; }
     std::atomic<int> next{0};
     std::vector<std::thread> th;

@@ -34,14 +34,14 @@ def test_round2_evidence_is_consistent():
     """k2_traffic.json is the sum the committed ncu raw page of the final K2 holds; the round-2 bench lines carry the contract keys,
     the K2 roofline object and the sharded runs' per-rank times."""
     import csv
-    rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r02_k2_final_ncu_raw.csv"), newline="")))
+    want = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))["1329x542000"]
+    rows = list(csv.reader(open(os.path.join(ROOT, want["source"].split(" ")[0]), newline="")))      # the capture the figure quotes
     hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr, units, vals = rows[hi], rows[hi + 1], rows[hi + 2]
     d = dict(zip(hdr, vals))
     u = dict(zip(hdr, units))
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     total = sum(float(d[k]) * scale[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    want = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))["1329x542000"]
     assert "fused_linearize_kernel" in d["Kernel Name"]
     assert abs(total - want["dram_bytes_per_launch"]) <= 1e-6 * total and total < 2 * 133405246        # <= 2x the algorithmic bytes
     line = json.loads([l for l in open(os.path.join(ROOT, "profiles", "r02_bench_final.json")) if l.startswith("{")][-1])

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #include <functional>
 #include <numeric>
 #include <thread>
@@ -49,12 +50,22 @@ struct Tiling {
 inline int tri_index(int la, int lb) { return lb * (lb + 1) / 2 + la; }   // la <= lb
 
 constexpr int kMaxHostThreads = 16;
+// host threads of the structure analysis: hardware_concurrency, at most kMaxHostThreads; MSFM_HOST_THREADS=<n> lowers it
+// (the result does not depend on it: tests/test_ba_tiles.py::test_analysis_does_not_depend_on_the_thread_count)
+inline int host_threads() {
+    int nt = static_cast<int>(std::thread::hardware_concurrency());
+    nt = std::max(1, std::min(kMaxHostThreads, nt));
+    if (const char* e = std::getenv("MSFM_HOST_THREADS")) {
+        const int v = std::atoi(e);
+        if (v > 0) nt = std::min(nt, v);
+    }
+    return nt;
+}
 
 // f(begin, end) over [0, n) on up to kMaxHostThreads host threads (the analysis of a 5 M-observation problem is ~0.5 s on one)
 template <class F>
 inline void parallel_ranges(int n, F f) {
-    int nt = static_cast<int>(std::thread::hardware_concurrency());
-    nt = std::max(1, std::min(kMaxHostThreads, nt));
+    const int nt = host_threads();
     if (n < 20000 || nt == 1) { f(0, n); return; }
     std::vector<std::thread> th;
     const int step = (n + nt - 1) / nt;
@@ -68,8 +79,7 @@ inline void parallel_ranges(int n, F f) {
 // Stable order of v under a strict total order `less`, on the host threads: sorted chunks, then rounds of pairwise merges.
 template <class T, class Less>
 inline void parallel_sort(std::vector<T>& v, Less less) {
-    int nt = static_cast<int>(std::thread::hardware_concurrency());
-    nt = std::max(1, std::min(kMaxHostThreads, nt));
+    const int nt = host_threads();
     const size_t n = v.size();
     if (n < 50000 || nt == 1) { std::sort(v.begin(), v.end(), less); return; }
     int parts = 1;
@@ -94,8 +104,7 @@ inline void parallel_sort(std::vector<T>& v, Less less) {
 // f(chunk) for chunk in [0, n_chunks), chunks handed out dynamically to up to 8 host threads
 template <class F>
 inline void parallel_chunks(int n_chunks, F f) {
-    int nt = static_cast<int>(std::thread::hardware_concurrency());
-    nt = std::max(1, std::min(std::min(kMaxHostThreads, nt), n_chunks));
+    const int nt = std::max(1, std::min(host_threads(), n_chunks));
     if (nt <= 1) { for (int c = 0; c < n_chunks; ++c) f(c); return; }
     std::atomic<int> next{0};
     std::vector<std::thread> th;

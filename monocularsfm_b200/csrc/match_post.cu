@@ -163,6 +163,34 @@ __device__ __forceinline__ int32_t sqdist_rows(const uint8_t* __restrict__ qsw, 
     return static_cast<int32_t>(acc);
 }
 
+// The same, but a caller that only needs min(limit, distance) lets the row stop early: after 64 and after 96 of the 128 bytes
+// the partial sum is compared with `limit` and returned as it is once it has reached it (partial >= limit implies distance >=
+// limit, so min(limit, .) is unchanged — the results stay bit-exact).  The rescan of resolve_rows_kernel is bound by L2
+// bandwidth (74 % of the L2's peak, profiles/r02_resolve_ncu_summary.txt); a column that is not a neighbour usually passes the
+// best distance outside its group well before its last bytes.
+__device__ __forceinline__ int32_t sqdist_rows_bounded(const uint8_t* __restrict__ qsw, int qi, const uint8_t* __restrict__ tsw,
+                                                       int tj, int32_t limit) {
+    const uint4* qa = reinterpret_cast<const uint4*>(qsw + static_cast<size_t>(qi) * 128);
+    const uint4* tb = reinterpret_cast<const uint4*>(tsw + static_cast<size_t>(tj) * 128);
+    const int qx = qi & 7, tx = tj & 7;
+    uint32_t acc = 0;
+    auto chunk = [&](int c) {
+        const uint4 a = __ldg(qa + (c ^ qx));
+        const uint4 b = __ldg(tb + (c ^ tx));
+        uint32_t d;
+        d = __vabsdiffu4(a.x, b.x); acc = __dp4a(d, d, acc);
+        d = __vabsdiffu4(a.y, b.y); acc = __dp4a(d, d, acc);
+        d = __vabsdiffu4(a.z, b.z); acc = __dp4a(d, d, acc);
+        d = __vabsdiffu4(a.w, b.w); acc = __dp4a(d, d, acc);
+    };
+    chunk(0); chunk(1); chunk(2); chunk(3);
+    if (static_cast<int32_t>(acc) >= limit) return static_cast<int32_t>(acc);
+    chunk(4); chunk(5);
+    if (static_cast<int32_t>(acc) >= limit) return static_cast<int32_t>(acc);
+    chunk(6); chunk(7);
+    return static_cast<int32_t>(acc);
+}
+
 __device__ __forceinline__ float dist_of(int32_t d2) { return __fsqrt_rn(static_cast<float>(d2)); }
 __device__ __forceinline__ bool ratio_pass(int32_t d1, int32_t d2, float ratio) {
     return dist_of(d1) < __fmul_rn(ratio, dist_of(d2));
@@ -217,18 +245,16 @@ resolve_rows_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__
         todo &= todo - 1;
         const int sg1 = __shfl_sync(0xffffffffu, g1, src);
         const int sqp = __shfl_sync(0xffffffffu, qp, src);
+        // a column at or beyond the best distance outside the group (uu) changes neither the winner (its distance d1 < uu) nor
+        // d2 = min(uu, in-group runner-up): it may stop early — unless the caller wants the exact second distance (knn2)
+        const int32_t lim = opt.exact_second ? kIntInf : __shfl_sync(0xffffffffu, uu, src);
         const int col = sg1 * 32 + lane;                     // sorted-space column (< t.n_pad)
         const int corig = t.perm[col];
         int32_t dd = kIntInf;
-        if (corig >= 0) dd = sqdist_rows(q.sw, sqp, t.sw, col);
-        // (dd, corig) lexicographic minimum over the warp
-        int32_t bd = dd, bj = corig >= 0 ? corig : kIntInf;
-#pragma unroll
-        for (int ofs = 16; ofs > 0; ofs >>= 1) {
-            const int32_t od = __shfl_xor_sync(0xffffffffu, bd, ofs);
-            const int32_t oj = __shfl_xor_sync(0xffffffffu, bj, ofs);
-            if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
-        }
+        if (corig >= 0) dd = sqdist_rows_bounded(q.sw, sqp, t.sw, col, lim);
+        // (dd, corig) lexicographic minimum over the warp: two REDUX instead of five shuffle / compare rounds
+        const int32_t bd = __reduce_min_sync(0xffffffffu, dd);
+        const int32_t bj = __reduce_min_sync(0xffffffffu, (corig >= 0 && dd == bd) ? corig : kIntInf);
         // runner-up inside the group: minimum over the lanes that are not the winner
         const int32_t second = __reduce_min_sync(0xffffffffu, (corig >= 0 && corig != bj) ? dd : kIntInf);
         if (lane == src) {

@@ -257,3 +257,19 @@ def test_tile_accumulation_emulation_matches_dense_schur(harness, which):
     S[np.arange(6 * nf), np.arange(6 * nf)] += np.maximum(udiag.ravel(), 1e-6) * inv_radius
     assert np.abs(S - So).max() <= 1e-10 * np.abs(So).max()
     assert np.abs(rhs.ravel() - rhso).max() <= 1e-9 * np.abs(rhso).max()
+
+
+def test_analysis_does_not_depend_on_the_thread_count(harness, monkeypatch):
+    """The structure analysis runs on the host threads (parallel merge sort of the point keys, tiling in chunks of a constant
+    size); one thread and many must give the same tables."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    P = bench.make_ba_problem(200, 60000, 9.2, 99)          # above the thresholds of the parallel paths, several chunks
+    monkeypatch.setenv("MSFM_HOST_THREADS", "1")
+    A = run_tiling(harness, P, 512, 256)
+    monkeypatch.delenv("MSFM_HOST_THREADS")
+    B = run_tiling(harness, P, 512, 256)
+    for k in ("pt_order", "pt_start", "obs_perm", "obs_lcam", "obs_lpt", "tiles", "runs", "tile_cams", "tile_slots", "blk_row", "blk_col", "items_raw"):
+        assert np.array_equal(A[k], B[k]), k
+    assert len(A["tiles"]) > 200 and A["n_long"] > 0

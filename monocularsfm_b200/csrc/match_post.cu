@@ -206,7 +206,10 @@ __device__ __forceinline__ bool dist_filter_ok(int32_t d1, double max_distance) 
 //   m_j   original train index of the accepted match or -1     m_d1  exact d2 of the best column (kIntInf = none)
 //   m_d2  exact d2 of the runner-up when it was computed, else an upper bound (kIntInf = none)
 //   m_j0  [2o] best column regardless of the ratio test (knn2 API), [2o+1] runner-up column (exact path only) or -1
-__global__ void __launch_bounds__(kUnitRows)
+#ifndef MSFM_RESOLVE_MIN_CTAS
+#define MSFM_RESOLVE_MIN_CTAS 12
+#endif
+__global__ void __launch_bounds__(kUnitRows, MSFM_RESOLVE_MIN_CTAS)
 resolve_rows_kernel(const ImgDev* __restrict__ imgs, const UnitDev* __restrict__ units, int unit0, int num_units,
                     const int32_t* __restrict__ res_g, const int32_t* __restrict__ res_d1,
                     const int32_t* __restrict__ res_u, MatchOpts opt, int32_t* __restrict__ m_j,

@@ -2,6 +2,7 @@
 """2..8-GPU functional check (launch with torchrun, one rank per GPU):
    - the library's NCCL communicator (dlopen'ed ncclAllReduce) sums / maxes correctly,
    - a point-sharded BA solve with the all-reduced reduced camera system reproduces the single-GPU solve,
+   - msfm_ba_update takes the same path on every rank (values only / re-analysis) and reproduces a fresh problem,
    - pair-sharded matching reproduces the single-GPU match lists.
 """
 import os
@@ -47,6 +48,23 @@ def main():
     S, rhs, gc, cost = ba.linearize(1e-4)
     s = ba.solve()
     cams_multi, _ = ba.get_params()
+    # msfm_ba_update is collective: (a) same pattern on every rank -> values only; (b) ONE rank's shard changes -> every rank
+    # re-analyses (the block structure is merged across ranks); the result must equal a freshly created sharded problem
+    reused_a = ba.update(L["cams"], L["pts"], L["obs_uv"], L["obs_cam"], L["obs_pt"], L["cam_const"], L["fx"], L["fy"])
+    s_a = ba.solve()
+    P2 = bench.make_ba_problem(64, 20000, 8.0, 78)
+    L2 = dict(shard_ba_problem(P2, rank, world), cams=L["cams"], cam_const=L["cam_const"]) if rank == 0 else L      # only rank 0's points differ
+    reused_b = ba.update(L2["cams"], L2["pts"], L2["obs_uv"], L2["obs_cam"], L2["obs_pt"], L2["cam_const"], L2["fx"], L2["fy"])
+    S_b, rhs_b, _, _ = ba.linearize(1e-4)
+    fresh = ctx.ba_create(L2["cams"], L2["pts"], L2["obs_uv"], L2["obs_cam"], L2["obs_pt"], L2["cam_const"], L2["fx"], L2["fy"])
+    S_f, rhs_f, _, _ = fresh.linearize(1e-4)
+    fresh.close()
+    e_upd = max(np.abs(S_b - S_f).max() / np.abs(S_f).max(), np.abs(rhs_b - rhs_f).max() / np.abs(rhs_f).max())
+    ok_upd = bool(reused_a) and not reused_b and abs(s_a["final_cost"] - s["final_cost"]) <= 1e-7 * s["final_cost"] and e_upd < 1e-6
+    if rank == 0:
+        print(f"BA update (collective): same pattern reused {reused_a}, changed on one rank reused {reused_b}, "
+              f"re-analysed vs fresh {e_upd:.2e}: {ok_upd}", flush=True)
+    ok &= ok_upd
     ba.close()
     if rank == 0:
         solo = m.Context(local)                       # no communicator: the whole problem on one GPU

@@ -23,6 +23,8 @@ struct TilingParams {
     int max_pts = kTilePts;    // max points per normal tile (<= kTilePts)
     int max_obs = kTileObs;    // max observations per normal tile (<= kTileObs)
     int max_items = kTileItems;
+    int chunk_pts = 16384;     // device points per independently tiled chunk of normal tiles (a constant of the analysis, not
+    int chunk_long = 1024;     // of the machine: the result does not depend on the thread count); long tracks per chunk of item tiles
     int max_run = 16;          // units per run (<= 255).  A run is ONE work item per 32 camera pairs, i.e. the load-balance grain of
                                // the pair phase: 255 -> 16 took 4.5 % off the kernel at configs[4] (profiles/r02_k2_v7_ab.txt)
 };
@@ -122,8 +124,6 @@ struct TileChunk {
     std::vector<int32_t> tile_cams, tile_marks;
     int w_max = 0;
 };
-constexpr int kChunkPoints = 16384;      // device points per chunk of normal tiles
-constexpr int kChunkLong = 1024;         // long tracks per chunk of item tiles (their open tiles are closed at the chunk's end)
 
 // Device order + tiles + per-tile coupling marks.  obs_pt must be non-decreasing (validated by the caller).
 // Returns false if a point is observed twice by one camera.
@@ -204,6 +204,7 @@ inline bool build_tiling(int n_cams, int n_pts, int n_obs, const int32_t* obs_ca
     const int max_pts = std::max(1, std::min(prm.max_pts, kTilePts)), max_obs = std::max(32, std::min(prm.max_obs, kTileObs));
     const int max_items = std::max(1, std::min(prm.max_items, kTileItems));
     const int max_run = std::max(1, std::min(prm.max_run, 255));
+    const int kChunkPoints = std::max(1, prm.chunk_pts), kChunkLong = std::max(1, prm.chunk_long);
     const int n_cam_slots = std::max(1, n_cams);
     auto cam_of = [&](int dev_obs) { return dev_cam[dev_obs]; };
 

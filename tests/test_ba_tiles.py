@@ -81,9 +81,12 @@ def tri(la, lb):
     return lb * (lb + 1) // 2 + la
 
 
-@pytest.mark.parametrize("which", ["ring", "long"])
-def test_tiling_invariants(harness, which):
+@pytest.mark.parametrize("which", ["ring", "long", "long-tiny-chunks"])
+def test_tiling_invariants(harness, which, monkeypatch):
     P = bo.make_problem(40, 500, 8, 1) if which == "ring" else long_track_problem()
+    if which == "long-tiny-chunks":
+        monkeypatch.setenv("TILING_TEST_CHUNK_PTS", "37")
+        monkeypatch.setenv("TILING_TEST_CHUNK_LONG", "2")
     T = run_tiling(harness, P)
     n_pts, n_obs = len(P["pts"]), len(P["obs_cam"])
     assert sorted(T["pt_order"].tolist()) == list(range(n_pts))
@@ -192,13 +195,20 @@ def test_duplicate_camera_rejected(harness):
     assert run_tiling(harness, dict(P, obs_cam=oc)) is None
 
 
-@pytest.mark.parametrize("which", ["ring", "long"])
-def test_tile_accumulation_emulation_matches_dense_schur(harness, which):
+@pytest.mark.parametrize("which", ["ring", "long", "long-tiny-chunks"])
+def test_tile_accumulation_emulation_matches_dense_schur(harness, which, monkeypatch):
     """What fused_linearize_kernel computes, restated in numpy from the tiling tables: per tile a local block triangle over
     the local cameras, block (x, y) -= Jc_x^T (Jp_x V^-1 Jp_y^T) Jc_y, diagonal += Jc^T (I - Jp V^-1 Jp^T) Jc, flushed to
     the global block list through tile_slots.  Must equal the oracle's S, rhs."""
     P = bo.make_problem(40, 500, 8, 1) if which == "ring" else long_track_problem()
+    if which == "long-tiny-chunks":
+        # the tiling runs in independent chunks of the device order that are concatenated afterwards (16 384 points / 1 024 long
+        # tracks in production): chunks of 37 points / 2 long tracks put many chunk boundaries into this small problem
+        monkeypatch.setenv("TILING_TEST_CHUNK_PTS", "37")
+        monkeypatch.setenv("TILING_TEST_CHUNK_LONG", "2")
     T = run_tiling(harness, P)
+    if which == "long-tiny-chunks":
+        assert len(T["tiles"]) >= 8 + 4
     inv_radius = 1e-4
     r, J = bo.residual_jacobian_jets(P["cams"], P["pts"], P["obs_uv"], P["obs_cam"], P["obs_pt"], P["fx"], P["fy"])
     U, gc, V, gp, W = bo.build_normal_equations(r, J, P["obs_cam"], P["obs_pt"], len(P["cams"]), len(P["pts"]), P["cam_const"])

@@ -1,5 +1,6 @@
 // Test harness (CPU): exposes monocularsfm_b200/csrc/ba_tiles.hpp through a tiny C interface so that
 // tests/test_ba_tiles.py can check the structure analysis without a GPU.
+#include <cstdlib>
 #include <cstring>
 #include "../../monocularsfm_b200/csrc/ba_tiles.hpp"
 
@@ -11,6 +12,8 @@ extern "C" {
 int tiling_build(int n_cams, int n_pts, int n_obs, const int32_t* obs_cam, const int32_t* obs_pt, const int32_t* cam_free,
                  int n_free, int max_obs, int max_pts, int max_items, int32_t sizes[9]) {
     TilingParams p; p.max_obs = max_obs; p.max_pts = max_pts; p.max_items = max_items;
+    if (const char* e = std::getenv("TILING_TEST_CHUNK_PTS")) p.chunk_pts = std::atoi(e);      // tests: tiny chunks exercise the concatenation
+    if (const char* e = std::getenv("TILING_TEST_CHUNK_LONG")) p.chunk_long = std::atoi(e);
     g_T = Tiling();
     if (!build_tiling(n_cams, n_pts, n_obs, obs_cam, obs_pt, cam_free, p, g_T)) return 1;
     std::vector<uint8_t> present;

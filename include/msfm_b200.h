@@ -51,7 +51,9 @@ const char* msfm_version(void);
 int  msfm_sync(msfm_ctx* ctx);
 /* The cudaStream_t (as void*) the ctx launches on — for callers that time with CUDA events. */
 void* msfm_stream(msfm_ctx* ctx);
-/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+/* Kernels the library has launched since the ctx was created (bench.py's gpu_launches): a counter incremented AT every launch
+ * site of the library's own kernels (csrc/launch_count.hpp), process-wide — one ctx per process is the intended use.  Library
+ * routines of the fallback solvers (cuSOLVER / cuBLAS) are not counted. */
 int64_t msfm_launch_count(const msfm_ctx* ctx);
 
 /* Optional per-kernel-class device timing (CUDA events on the ctx stream, recorded around every launch

@@ -255,7 +255,6 @@ static int upload_values(msfm_ba* b, const msfm_ba_problem* pr, bool with_cams) 
             b->last_h2d_bytes += int64_t(no) * sizeof(int32_t);
         }
         BA_CUDA(ba_launch_permute_obs(b->n_obs, b->obs_orig, st_uv, with_cams ? st_cam : nullptr, b->obs_uv, b->obs_cam, c->stream));
-        c->launches += 1;
     }
     b->focal[0][0] = b->focal[1][0] = pr->fx; b->focal[0][1] = b->focal[1][1] = pr->fy;
     b->h_cams.assign(pr->cams, pr->cams + size_t(pr->n_cams) * 6);
@@ -412,7 +411,6 @@ static int build_problem(msfm_ba* b, const msfm_ba_problem* pr) {
     if (e != cudaSuccess) return c->cuda_fail(e, "msfm_ba_create H2D");
     if (pr->n_pts > 0) {
         BA_CUDA(ba_launch_fill_obs_pt(pr->n_pts, b->pt_start, b->pt_order, b->obs_pt, c->stream));
-        c->launches += 1;
     }
     int rc = upload_values(b, pr, true);
     if (rc) return rc;
@@ -523,7 +521,6 @@ static int prep(msfm_ba* b, int which) {
     c->prof_begin(MSFM_PROF_BA_OTHER);
     BA_CUDA(ba_launch_cam_prep(b->cams[which], b->n_cams, b->pre[which], c->stream));
     c->prof_end();
-    c->launches += 1;
     return MSFM_OK;
 }
 
@@ -548,7 +545,6 @@ int msfm_ba_evaluate(msfm_ba* b, double* r, float* J, double* cost) {
     c->prof_begin(MSFM_PROF_BA_EVAL);
     BA_CUDA(ba_launch_evaluate(b->view(b->cur), d_r, d_J, b->small, c->num_sms, c->stream));
     c->prof_end();
-    c->launches += 1;
     double h = 0;
     BA_CUDA(cudaMemcpyAsync(&h, b->small, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (d_r) BA_CUDA(cudaMemcpyAsync(r, d_r, size_t(b->n_obs) * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -570,7 +566,6 @@ int msfm_ba_track_errors(msfm_ba* b, double* err) {
     c->prof_begin(MSFM_PROF_BA_EVAL);
     BA_CUDA(ba_launch_track_errors(b->view(b->cur), c->d_ba_r.as<double>(), c->num_sms, c->stream));
     c->prof_end();
-    c->launches += 1;
     BA_CUDA(cudaMemcpyAsync(err, c->d_ba_r.p, size_t(b->n_pts) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     BA_CUDA(cudaStreamSynchronize(c->stream));
     return MSFM_OK;
@@ -593,7 +588,6 @@ int msfm_ba_filter_stats(msfm_ba* b, double max_reproj_error, uint8_t* obs_keep,
     c->prof_begin(MSFM_PROF_BA_EVAL);
     BA_CUDA(ba_launch_filter_stats(b->view(b->cur), max_reproj_error, d_keep, d_err, d_kept, d_ang, c->num_sms, c->stream));
     c->prof_end();
-    c->launches += 1;
     if (obs_keep && no) BA_CUDA(cudaMemcpyAsync(obs_keep, d_keep, no, cudaMemcpyDeviceToHost, c->stream));
     if (pt_mean_error) BA_CUDA(cudaMemcpyAsync(pt_mean_error, d_err, np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (pt_kept) BA_CUDA(cudaMemcpyAsync(pt_kept, d_kept, np * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -613,7 +607,6 @@ static int linearize(msfm_ba* b, int which, double inv_radius) {
     c->prof_begin(MSFM_PROF_BA_SCHUR);
     BA_CUDA(ba_launch_linearize(b->view(which), inv_radius, c->num_sms, c->stream));
     c->prof_end();
-    c->launches += (b->n_tiles > 0 ? 1 : 0) + (b->n_long > 0 ? 1 : 0);
     if (c->comm && c->comm_ranks > 1) {
         c->prof_begin(MSFM_PROF_BA_COMM);
         if (g_nccl.GroupStart() != 0) return c->fail(MSFM_E_CUDA, "ncclGroupStart failed");
@@ -761,7 +754,6 @@ static int solver_queue(msfm_ba* b, double inv_radius, int nrhs, const int** inf
         *n_info = 1;
     }
     c->prof_end();
-    c->launches += 3;
     return MSFM_OK;
 }
 
@@ -882,18 +874,15 @@ int msfm_ba_solve(msfm_ba* b, const msfm_ba_options* uopt, msfm_ba_summary* sum)
             BA_CUDA(ba_launch_backsub(b->view(b->cur), inv_radius, b->xsol, b->pts[nxt], b->small, c->num_sms, c->stream));
             BA_CUDA(ba_launch_update_cams(b->cams[b->cur], b->cam_free, b->n_cams, b->xsol, b->cams[nxt], c->stream));
             c->prof_end();
-            c->launches += 2;
             b->focal[nxt][0] = b->focal[b->cur][0] + df[0];
             b->focal[nxt][1] = b->focal[b->cur][1] + df[1];
             if ((rc = prep(b, nxt))) return rc;
             c->prof_begin(MSFM_PROF_BA_EVAL);
             BA_CUDA(ba_launch_evaluate(b->view(nxt), nullptr, nullptr, b->small + 3, c->num_sms, c->stream));
             c->prof_end();
-            c->launches += 1;
             if (multi && (rc = msfm_comm_allreduce_f64(c, b->small, 4, 0))) return rc;
         }
         BA_CUDA(ba_launch_lm_record(b->view(b->cur), b->cams[b->cur], b->xsol, b->small, info_ptr, n_info, n_ranks, b->rec, c->stream));
-        c->launches += 1;
         BA_CUDA(cudaMemcpyAsync(h_rec, b->rec, 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         BA_CUDA(cudaStreamSynchronize(c->stream));                  // the iteration's one synchronisation
         {

@@ -25,6 +25,7 @@
 
 #include "ba_types.cuh"
 #include "ptx.cuh"
+#include "launch_count.hpp"
 
 namespace msfm {
 namespace band {
@@ -816,16 +817,17 @@ cudaError_t band_factor_solve(BandSolver* B, const ba::Problem& P, double inv_ra
     if (e == cudaSuccess) e = cudaMemsetAsync(B->d_info, 0, 4 * sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
     const int tot = P.n_blocks * 36;
-    band::expand_band_kernel<<<(tot + 255) / 256, 256, 0, st>>>(P, B->d_pos, p, inv_radius);
-    if (Npad > N) band::pad_band_kernel<<<(Npad - N + 63) / 64, 64, 0, st>>>(p, N);
+    { band::expand_band_kernel<<<(tot + 255) / 256, 256, 0, st>>>(P, B->d_pos, p, inv_radius); MSFM_COUNT_LAUNCH(); }
+    if (Npad > N) { band::pad_band_kernel<<<(Npad - N + 63) / 64, 64, 0, st>>>(p, N); MSFM_COUNT_LAUNCH(); }
     for (int c = 0; c < nrhs; ++c)
-        band::permute_in_kernel<<<(N + 255) / 256, 256, 0, st>>>(rhs + static_cast<size_t>(c) * N, B->d_pos, B->nf, B->y + static_cast<size_t>(c) * Npad);
+        { band::permute_in_kernel<<<(N + 255) / 256, 256, 0, st>>>(rhs + static_cast<size_t>(c) * N, B->d_pos, B->nf, B->y + static_cast<size_t>(c) * Npad); MSFM_COUNT_LAUNCH(); }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     void* args[] = {&p};
     e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(band::band_cholesky_kernel), dim3(B->grid), dim3(band::kThreads), args, band::kDynSmem, st);
     if (e != cudaSuccess) return e;
+    MSFM_COUNT_LAUNCH();
     for (int c = 0; c < nrhs; ++c)
-        band::permute_out_kernel<<<(N + 255) / 256, 256, 0, st>>>(B->y + static_cast<size_t>(c) * Npad, B->d_pos, B->nf, rhs + static_cast<size_t>(c) * N);
+        { band::permute_out_kernel<<<(N + 255) / 256, 256, 0, st>>>(B->y + static_cast<size_t>(c) * Npad, B->d_pos, B->nf, rhs + static_cast<size_t>(c) * N); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 

@@ -23,6 +23,7 @@
 #include <cstdint>
 
 #include "ba_types.cuh"
+#include "launch_count.hpp"
 
 namespace msfm {
 namespace ba {
@@ -1231,21 +1232,21 @@ __global__ void fill_obs_pt_kernel(int n_pts, const int32_t* __restrict__ pt_sta
 using namespace ba;
 cudaError_t ba_launch_cam_prep(const double* cams, int n_cams, CamPre* pre, cudaStream_t st) {
     if (n_cams <= 0) return cudaSuccess;
-    cam_prep_kernel<<<(n_cams + 127) / 128, 128, 0, st>>>(cams, n_cams, pre);
+    { cam_prep_kernel<<<(n_cams + 127) / 128, 128, 0, st>>>(cams, n_cams, pre); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t ba_launch_evaluate(const Problem& P, double* r_out, float* J_out, double* cost, int num_sms, cudaStream_t st) {
     if (P.n_obs <= 0) return cudaSuccess;
     int grid = (P.n_obs + 255) / 256;
     if (grid > num_sms * 8) grid = num_sms * 8;
-    evaluate_kernel<<<grid, 256, 0, st>>>(P, r_out, J_out, cost);
+    { evaluate_kernel<<<grid, 256, 0, st>>>(P, r_out, J_out, cost); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t ba_launch_track_errors(const Problem& P, double* err, int num_sms, cudaStream_t st) {
     if (P.n_pts <= 0) return cudaSuccess;
     int grid = (P.n_pts + 7) / 8;
     if (grid > num_sms * 8) grid = num_sms * 8;
-    track_error_kernel<<<grid, 256, 0, st>>>(P, err);
+    { track_error_kernel<<<grid, 256, 0, st>>>(P, err); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t ba_launch_filter_stats(const Problem& P, double max_err, uint8_t* keep, double* err, int32_t* kept, double* angle, int num_sms,
@@ -1253,7 +1254,7 @@ cudaError_t ba_launch_filter_stats(const Problem& P, double max_err, uint8_t* ke
     if (P.n_pts <= 0) return cudaSuccess;
     int grid = (P.n_pts + 7) / 8;
     if (grid > num_sms * 8) grid = num_sms * 8;
-    filter_stats_kernel<<<grid, 256, 0, st>>>(P, max_err, keep, err, kept, angle);
+    { filter_stats_kernel<<<grid, 256, 0, st>>>(P, max_err, keep, err, kept, angle); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 size_t ba_fused_smem_bytes(bool focal) { return fused_smem_layout(focal).total; }
@@ -1263,8 +1264,8 @@ cudaError_t ba_launch_linearize(const Problem& P, double inv_radius, int num_sms
     if (P.n_long > 0) {
         int g = (P.n_long + 7) / 8;
         if (g > num_sms * 4) g = num_sms * 4;
-        if (P.refine_focal) long_track_prepass_kernel<true><<<g, 256, 0, st>>>(P, inv_radius);
-        else long_track_prepass_kernel<false><<<g, 256, 0, st>>>(P, inv_radius);
+        if (P.refine_focal) { long_track_prepass_kernel<true><<<g, 256, 0, st>>>(P, inv_radius); MSFM_COUNT_LAUNCH(); }
+        else { long_track_prepass_kernel<false><<<g, 256, 0, st>>>(P, inv_radius); MSFM_COUNT_LAUNCH(); }
     }
     const size_t smem = fused_smem_layout(P.refine_focal != 0).total;
     cudaError_t e;
@@ -1277,14 +1278,14 @@ cudaError_t ba_launch_linearize(const Problem& P, double inv_radius, int num_sms
         if (e != cudaSuccess) return e;
     }
     const int grid = P.n_tiles < num_sms * kCtasPerSm ? P.n_tiles : num_sms * kCtasPerSm;
-    if (P.refine_focal) fused_linearize_kernel<true><<<grid, kFusedThreads, smem, st>>>(P, inv_radius);
-    else fused_linearize_kernel<false><<<grid, kFusedThreads, smem, st>>>(P, inv_radius);
+    if (P.refine_focal) { fused_linearize_kernel<true><<<grid, kFusedThreads, smem, st>>>(P, inv_radius); MSFM_COUNT_LAUNCH(); }
+    else { fused_linearize_kernel<false><<<grid, kFusedThreads, smem, st>>>(P, inv_radius); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t ba_launch_expand_dense(const Problem& P, double inv_radius, double* S, cudaStream_t st) {
     if (P.n_blocks <= 0) return cudaSuccess;
     const int n = P.n_blocks * 36;
-    expand_dense_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, inv_radius, S);
+    { expand_dense_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, inv_radius, S); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t ba_launch_backsub(const Problem& P, double inv_radius, const double* dc, double* pts_new, double* out,
@@ -1293,30 +1294,30 @@ cudaError_t ba_launch_backsub(const Problem& P, double inv_radius, const double*
     // normal tiles: thread-per-observation kernel; long tracks + unobserved points (device points >= first_long): warp per point
     if (P.first_long > 0 && P.n_tiles > 0) {
         const int grid = P.n_tiles < num_sms * kCtasPerSm ? P.n_tiles : num_sms * kCtasPerSm;
-        backsub_tile_kernel<<<grid, kTileObs, 0, st>>>(P, inv_radius, dc, pts_new, out);
+        { backsub_tile_kernel<<<grid, kTileObs, 0, st>>>(P, inv_radius, dc, pts_new, out); MSFM_COUNT_LAUNCH(); }
     }
     const int rest = P.n_pts - P.first_long;
     if (rest > 0) {
         int grid = (rest + 7) / 8;
         if (grid > num_sms * 8) grid = num_sms * 8;
-        backsub_kernel<<<grid, 256, 0, st>>>(P, P.first_long, inv_radius, dc, pts_new, out);
+        { backsub_kernel<<<grid, 256, 0, st>>>(P, P.first_long, inv_radius, dc, pts_new, out); MSFM_COUNT_LAUNCH(); }
     }
     return cudaGetLastError();
 }
 cudaError_t ba_launch_update_cams(const double* cams, const int32_t* cam_free, int n_cams, const double* dc,
                                   double* cams_new, cudaStream_t st) {
     if (n_cams <= 0) return cudaSuccess;
-    update_cams_kernel<<<(n_cams * 6 + 127) / 128, 128, 0, st>>>(cams, cam_free, n_cams, dc, cams_new);
+    { update_cams_kernel<<<(n_cams * 6 + 127) / 128, 128, 0, st>>>(cams, cam_free, n_cams, dc, cams_new); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t ba_launch_lm_record(const Problem& P, const double* cams, const double* dc, const double* small, const int* info, int n_info,
                                 int n_ranks, double* rec, cudaStream_t st) {
-    lm_record_kernel<<<1, 256, 0, st>>>(P, cams, dc, small, info, n_info, n_ranks, rec);
+    { lm_record_kernel<<<1, 256, 0, st>>>(P, cams, dc, small, info, n_info, n_ranks, rec); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t ba_launch_copy(const double* src, double* dst, int n, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n);
+    { copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 
@@ -1324,14 +1325,14 @@ cudaError_t ba_launch_permute_obs(int n_obs, const int32_t* obs_orig, const doub
                                   int32_t* cam_out, cudaStream_t st) {
     if (n_obs <= 0) return cudaSuccess;
     const int grid = std::min((n_obs + 255) / 256, 148 * 16);
-    permute_obs_kernel<<<grid, 256, 0, st>>>(n_obs, obs_orig, reinterpret_cast<const double2*>(uv_in), cam_in,
-                                             reinterpret_cast<double2*>(uv_out), cam_out);
+    { permute_obs_kernel<<<grid, 256, 0, st>>>(n_obs, obs_orig, reinterpret_cast<const double2*>(uv_in), cam_in,
+                                             reinterpret_cast<double2*>(uv_out), cam_out); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t ba_launch_fill_obs_pt(int n_pts, const int32_t* pt_start, const int32_t* pt_order, int32_t* obs_pt, cudaStream_t st) {
     if (n_pts <= 0) return cudaSuccess;
     const int grid = std::min((n_pts + 255) / 256, 148 * 16);
-    fill_obs_pt_kernel<<<grid, 256, 0, st>>>(n_pts, pt_start, pt_order, obs_pt);
+    { fill_obs_pt_kernel<<<grid, 256, 0, st>>>(n_pts, pt_start, pt_order, obs_pt); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "ba_types.cuh"
+#include "launch_count.hpp"
 
 namespace msfm {
 namespace ba {
@@ -191,9 +192,9 @@ cudaError_t tridiag_factor_solve(TridiagSolver* T, const ba::Problem& P, double 
     cudaError_t e = cudaMemsetAsync(T->D, 0, 2 * static_cast<size_t>(n) * MM * sizeof(double), st);
     if (e != cudaSuccess) return e;
     const int tot = P.n_blocks * 36;
-    ba::expand_tridiag_kernel<<<(tot + 255) / 256, 256, 0, st>>>(P, T->d_pos, T->m, M, inv_radius, T->D, T->E);
+    { ba::expand_tridiag_kernel<<<(tot + 255) / 256, 256, 0, st>>>(P, T->d_pos, T->m, M, inv_radius, T->D, T->E); MSFM_COUNT_LAUNCH(); }
     for (int c = 0; c < nrhs; ++c)
-        ba::permute_rhs_kernel<<<(T->N + 255) / 256, 256, 0, st>>>(rhs + static_cast<size_t>(c) * T->N, T->d_pos, T->nf, T->N, T->X + static_cast<size_t>(c) * T->N);
+        { ba::permute_rhs_kernel<<<(T->N + 255) / 256, 256, 0, st>>>(rhs + static_cast<size_t>(c) * T->N, T->d_pos, T->nf, T->N, T->X + static_cast<size_t>(c) * T->N); MSFM_COUNT_LAUNCH(); }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     const double one = 1.0, minus = -1.0;
     for (int s = 0; s < n; ++s) {
@@ -233,7 +234,7 @@ cudaError_t tridiag_factor_solve(TridiagSolver* T, const ba::Problem& P, double 
             return cudaErrorUnknown;
     }
     for (int c = 0; c < nrhs; ++c)
-        ba::unpermute_kernel<<<(T->N + 255) / 256, 256, 0, st>>>(T->X + static_cast<size_t>(c) * T->N, T->d_pos, T->nf, rhs + static_cast<size_t>(c) * T->N);
+        { ba::unpermute_kernel<<<(T->N + 255) / 256, 256, 0, st>>>(T->X + static_cast<size_t>(c) * T->N, T->d_pos, T->nf, rhs + static_cast<size_t>(c) * T->N); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 

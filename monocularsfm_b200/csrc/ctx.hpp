@@ -51,7 +51,7 @@ struct msfm_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    int64_t launches = 0;
+    int64_t launches = 0;          // value of the library's launch counter (launch_count.hpp) when the ctx was created
 
     // ---- M-path
     std::unordered_map<int32_t, int> slot_of;      // image_id -> slot

@@ -46,6 +46,7 @@
 // (d1 >= 2^22) with the exact scan.
 #include "match_types.cuh"
 #include "ptx.cuh"
+#include "launch_count.hpp"
 #include <cstdlib>
 
 namespace msfm {
@@ -557,7 +558,7 @@ cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, i
     const int clusters = num_items < num_sms / 2 ? num_items : num_sms / 2;
     if (clusters <= 0) return cudaErrorInvalidConfiguration;
     k1::Item* items = static_cast<k1::Item*>(item_scratch);
-    k1::build_items_kernel<<<(num_items + 255) / 256, 256, 0, stream>>>(imgs, units, unit0, num_items, items);
+    { k1::build_items_kernel<<<(num_items + 255) / 256, 256, 0, stream>>>(imgs, units, unit0, num_items, items); MSFM_COUNT_LAUNCH(); }
     long long* dbg = nullptr;
     if (debug) {
         static long long* d_dbg = nullptr;
@@ -565,7 +566,7 @@ cudaError_t launch_match_tile_kernel(const ImgDev* imgs, const UnitDev* units, i
         dbg = d_dbg;
         cudaMemsetAsync(dbg, 0, (4 * 128 + 64 * 8 + 128) * sizeof(long long), stream);
     }
-    kernel<<<2 * clusters, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(items, num_items, res_g, res_d1, res_u, dbg, debug > 10 ? debug - 10 : 0);
+    { kernel<<<2 * clusters, k1::NUM_THREADS, k1::SMEM_BYTES, stream>>>(items, num_items, res_g, res_d1, res_u, dbg, debug > 10 ? debug - 10 : 0); MSFM_COUNT_LAUNCH(); }
     if (debug) {
         long long h[4 * 128 + 64 * 8 + 128];
         cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, stream);

@@ -12,6 +12,7 @@
 // All integer arithmetic is exact; the float steps reproduce the reference's: distance = sqrtf((float)d2)
 // (OpenCV batchDistL2_), ratio test `d0 < ratio * d1` in float (FeatureUtils.cpp:152).
 #include "match_types.cuh"
+#include "launch_count.hpp"
 #include <cuda_runtime.h>
 
 namespace msfm {
@@ -626,13 +627,13 @@ gather_candidates_kernel(const ImgDev* __restrict__ imgs, const SegDev* __restri
 // ------------------------------------------------------------------------------------------------ launchers
 cudaError_t launch_setup_temp_imgs(ImgDev* imgs, int first_temp_slot, const SegDev* segs, int npairs, TempImgs T, cudaStream_t st) {
     if (npairs <= 0) return cudaSuccess;
-    setup_temp_imgs_kernel<<<(npairs + 127) / 128, 128, 0, st>>>(imgs, first_temp_slot, segs, npairs, T);
+    { setup_temp_imgs_kernel<<<(npairs + 127) / 128, 128, 0, st>>>(imgs, first_temp_slot, segs, npairs, T); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t launch_gather_candidates(const ImgDev* imgs, const SegDev* segs, int npairs, const int32_t* m_j, TempImgs T,
                                      cudaStream_t st) {
     if (npairs <= 0) return cudaSuccess;
-    gather_candidates_kernel<<<npairs, kGatherThreads, 0, st>>>(imgs, segs, npairs, m_j, T);
+    { gather_candidates_kernel<<<npairs, kGatherThreads, 0, st>>>(imgs, segs, npairs, m_j, T); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 // ---- float32 descriptors (what the reference's Database stores, src/Database/Database.cpp:174-199) -> uint8.
@@ -688,7 +689,7 @@ cudaError_t launch_desc_normalize(float* data, int n, int kind, cudaStream_t st)
     if (n <= 0) return cudaSuccess;
     int grid = (n + 7) / 8;
     if (grid > 148 * 8) grid = 148 * 8;
-    desc_f32_normalize_kernel<<<grid, 256, 0, st>>>(data, n, kind);
+    { desc_f32_normalize_kernel<<<grid, 256, 0, st>>>(data, n, kind); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 
@@ -700,8 +701,8 @@ cudaError_t launch_desc_quantize(const float* src, int n, int mode, int32_t* fla
     if ((e = cudaMemcpyAsync(flag, &one, sizeof(one), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     int grid = static_cast<int>((count / 4 + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
-    if (mode == 0) desc_f32_check_kernel<<<grid, 256, 0, st>>>(src, count, flag);
-    desc_f32_quantize_kernel<<<grid, 256, 0, st>>>(src, count / 4, mode, flag, reinterpret_cast<uint32_t*>(dst));
+    if (mode == 0) { desc_f32_check_kernel<<<grid, 256, 0, st>>>(src, count, flag); MSFM_COUNT_LAUNCH(); }
+    { desc_f32_quantize_kernel<<<grid, 256, 0, st>>>(src, count / 4, mode, flag, reinterpret_cast<uint32_t*>(dst)); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 
@@ -723,19 +724,19 @@ cudaError_t launch_desc_format(const uint8_t* raw, int n, int n_pad, uint8_t* sw
         const int wpb = 8;
         int grid = (n + wpb - 1) / wpb;
         if (grid > 148 * 8) grid = 148 * 8;
-        desc_norm_key_kernel<<<grid, wpb * 32, 0, st>>>(raw, n, nrm_orig, keys, bucket_cnt);
+        { desc_norm_key_kernel<<<grid, wpb * 32, 0, st>>>(raw, n, nrm_orig, keys, bucket_cnt); MSFM_COUNT_LAUNCH(); }
         if ((e = cudaMemsetAsync(pos_of, 0, static_cast<size_t>(n) * 4, st)) != cudaSuccess) return e;
         const int slices = n >= 2048 ? 8 : 1;
-        desc_rank_kernel<<<dim3((n + 255) / 256, slices), 256, 0, st>>>(keys, n, bucket_cnt, pos_of, used);
-        desc_scatter_kernel<<<grid, wpb * 32, 0, st>>>(raw, n, pos_of, nrm_orig, bucket_cnt, sw, nrm, perm, inv);
+        { desc_rank_kernel<<<dim3((n + 255) / 256, slices), 256, 0, st>>>(keys, n, bucket_cnt, pos_of, used); MSFM_COUNT_LAUNCH(); }
+        { desc_scatter_kernel<<<grid, wpb * 32, 0, st>>>(raw, n, pos_of, nrm_orig, bucket_cnt, sw, nrm, perm, inv); MSFM_COUNT_LAUNCH(); }
     }
     int ggrid = (n_pad / 32 + 7) / 8;
-    desc_groups_kernel<<<ggrid, 256, 0, st>>>(nrm, n_pad, cg, ext);
+    { desc_groups_kernel<<<ggrid, 256, 0, st>>>(nrm, n_pad, cg, ext); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t launch_build_units(const SegDev* segs, int nseg, int num_units, UnitDev* units, cudaStream_t st) {
     if (num_units <= 0) return cudaSuccess;
-    build_units_kernel<<<(num_units + 255) / 256, 256, 0, st>>>(segs, nseg, num_units, units);
+    { build_units_kernel<<<(num_units + 255) / 256, 256, 0, st>>>(segs, nseg, num_units, units); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t launch_resolve_rows(const ImgDev* imgs, const UnitDev* units, int unit0, int num_units, const int32_t* res_g,
@@ -743,15 +744,15 @@ cudaError_t launch_resolve_rows(const ImgDev* imgs, const UnitDev* units, int un
                                 int32_t* m_d2, int32_t* m_j0, int32_t* exact_list, unsigned int* counters,
                                 cudaStream_t st) {
     if (num_units <= 0) return cudaSuccess;
-    resolve_rows_kernel<<<num_units, kUnitRows, 0, st>>>(imgs, units, unit0, num_units, res_g, res_d1, res_u, opt, m_j, m_d1, m_d2,
-                                                   m_j0, exact_list, counters);
+    { resolve_rows_kernel<<<num_units, kUnitRows, 0, st>>>(imgs, units, unit0, num_units, res_g, res_d1, res_u, opt, m_j, m_d1, m_d2,
+                                                   m_j0, exact_list, counters); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t launch_exact_rows(const ImgDev* imgs, const UnitDev* units, const int32_t* row_list,
                               const unsigned int* row_count_dev, int row_count_host, MatchOpts opt, int32_t* m_j,
                               int32_t* m_d1, int32_t* m_d2, int32_t* m_j0, int num_sms, cudaStream_t st) {
-    exact_rows_kernel<<<num_sms * 8, 256, 0, st>>>(imgs, units, row_list, row_count_dev, row_count_host, opt, m_j, m_d1,
-                                                   m_d2, m_j0);
+    { exact_rows_kernel<<<num_sms * 8, 256, 0, st>>>(imgs, units, row_list, row_count_dev, row_count_host, opt, m_j, m_d1,
+                                                   m_d2, m_j0); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 cudaError_t launch_count_scan_write(const ImgDev* imgs, const SegDev* segs, int npairs, MatchOpts opt,
@@ -759,10 +760,10 @@ cudaError_t launch_count_scan_write(const ImgDev* imgs, const SegDev* segs, int 
                                     long long* running_total, long long capacity, int32_t* out_matches, float* out_dist,
                                     cudaStream_t st) {
     if (npairs <= 0) return cudaSuccess;
-    count_matches_kernel<<<npairs, 256, 0, st>>>(imgs, segs, npairs, opt, m_j, m_d1, counts);
-    scan_counts_kernel<<<1, 1024, 0, st>>>(counts, npairs, offsets, running_total);
-    write_matches_kernel<<<npairs, 256, 0, st>>>(imgs, segs, npairs, opt, m_j, m_d1, offsets, capacity, out_matches,
-                                                 out_dist);
+    { count_matches_kernel<<<npairs, 256, 0, st>>>(imgs, segs, npairs, opt, m_j, m_d1, counts); MSFM_COUNT_LAUNCH(); }
+    { scan_counts_kernel<<<1, 1024, 0, st>>>(counts, npairs, offsets, running_total); MSFM_COUNT_LAUNCH(); }
+    { write_matches_kernel<<<npairs, 256, 0, st>>>(imgs, segs, npairs, opt, m_j, m_d1, offsets, capacity, out_matches,
+                                                 out_dist); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 

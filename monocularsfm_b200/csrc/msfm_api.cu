@@ -6,6 +6,7 @@
 #include <new>
 
 #include "ctx.hpp"
+#include "launch_count.hpp"
 
 namespace msfm {
 struct TempImgs {
@@ -34,6 +35,10 @@ using namespace msfm;
 static thread_local std::string g_init_error;
 static constexpr int kMaxUnitsPerBatch = 1 << 17;     // 131072 units = 16.7 M rows of scratch per batch
 static constexpr int32_t kTmpIdA = -1000001, kTmpIdB = -1000002;
+
+namespace msfm {
+std::atomic<long long> g_kernel_launches{0};      // launch_count.hpp: incremented at every launch site of the library
+}
 
 extern "C" {
 
@@ -67,6 +72,7 @@ int msfm_init(msfm_ctx** out, int device_id) {
         return MSFM_E_CUDA;
     }
     msfm_ctx* c = new (std::nothrow) msfm_ctx();
+    if (c) c->launches = static_cast<int64_t>(msfm::g_kernel_launches.load());      // msfm_launch_count reports launches since creation
     if (!c) return MSFM_E_CUDA;
     c->device = device_id;
     c->num_sms = prop.multiProcessorCount;
@@ -120,7 +126,7 @@ int msfm_sync(msfm_ctx* c) {
     return MSFM_OK;
 }
 void* msfm_stream(msfm_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
-int64_t msfm_launch_count(const msfm_ctx* c) { return c ? c->launches : 0; }
+int64_t msfm_launch_count(const msfm_ctx* c) { return c ? static_cast<int64_t>(msfm::g_kernel_launches.load()) - c->launches : 0; }
 
 int msfm_prof_enable(msfm_ctx* c, int on) {
     if (!c) return MSFM_E_INVALID;
@@ -213,14 +219,12 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
             c->prof_begin(MSFM_PROF_DESC_FORMAT);
             MSFM_CUDA(c, launch_desc_normalize(stage, n, normalize, c->stream));
             c->prof_end();
-            c->launches += 1;
             if (normalized_out) MSFM_CUDA(c, cudaMemcpyAsync(normalized_out, stage, f32_bytes, cudaMemcpyDeviceToHost, c->stream));
         }
         c->prof_begin(MSFM_PROF_DESC_FORMAT);
         MSFM_CUDA(c, launch_desc_quantize(stage, n, f32_mode, reinterpret_cast<int32_t*>(c->d_raw.as<uint8_t>() + u8_bytes + f32_bytes),
                                           c->d_raw.as<uint8_t>(), c->stream));
         c->prof_end();
-        c->launches += f32_mode == 0 ? 2 : 1;
         raw = c->d_raw.as<uint8_t>();
     } else if (!src_on_device) {
         // double-buffered staging on the copy stream: this copy runs under the formatting kernels of the previous upload
@@ -248,7 +252,6 @@ static int upload_common(msfm_ctx* c, int32_t image_id, const uint8_t* src, int3
                                     reinterpret_cast<int32_t*>(sw + L.off_nrm), reinterpret_cast<int32_t*>(sw + L.off_perm),
                                     reinterpret_cast<int32_t*>(sw + L.off_inv), reinterpret_cast<int32_t*>(sw + L.off_used), keys, nrm_orig, pos_of, bucket_cnt, c->stream));
     c->prof_end();
-    c->launches += 4;
     if (raw_q >= 0) {
         MSFM_CUDA(c, cudaEventRecord(c->raw_free[raw_q], c->stream));
         c->raw_free_set[raw_q] = true;
@@ -500,7 +503,6 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
             MSFM_CUDA(c, launch_setup_temp_imgs(d_imgs, first_temp_slot, bsegs, b.npairs, T, c->stream));
             // reverse rows that are never computed (train rows nobody matched) must read as "no match"
             MSFM_CUDA(c, cudaMemsetAsync(m_j, 0xFF, static_cast<size_t>(nunits) * kUnitRows * sizeof(int32_t), c->stream));
-            c->launches += 1;
         }
         c->prof_begin(MSFM_PROF_BUILD_UNITS);
         MSFM_CUDA(c, launch_build_units(bsegs, b.npairs * spp, nunits, units, c->stream));
@@ -513,7 +515,6 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
                     c->prof_begin(MSFM_PROF_COMPACT);
                     MSFM_CUDA(c, launch_gather_candidates(d_imgs, bsegs, b.npairs, m_j, T, c->stream));
                     c->prof_end();
-                    c->launches += 1;
                 }
                 c->prof_begin(MSFM_PROF_MATCH_TILE);
                 MSFM_CUDA(c, launch_match_tile_kernel(d_imgs, units, u0, nu, res_j, res_d1, res_u, c->d_items.p, c->num_sms, c->stream));
@@ -526,7 +527,6 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
                 MSFM_CUDA(c, launch_exact_rows(d_imgs, units, c->d_exact.as<int32_t>(), bcnt + 2 * pass, -1, opt, m_j, m_d1,
                                                m_d2, m_j0, c->num_sms, c->stream));
                 c->prof_end();
-                c->launches += (nu > 0 ? 3 : 1);
             }
         } else {
             // exact CUDA-core scan of every row (knn2 parity API; never combined with cross-check)
@@ -534,15 +534,12 @@ static int match_core(msfm_ctx* c, const int32_t* pairs, int32_t P, const msfm_m
             MSFM_CUDA(c, launch_exact_rows(d_imgs, units, nullptr, nullptr, nunits * kUnitRows, opt, m_j, m_d1, m_d2, m_j0,
                                            c->num_sms, c->stream));
             c->prof_end();
-            c->launches += 1;
         }
-        c->launches += 1;
         c->prof_begin(MSFM_PROF_COMPACT);
         MSFM_CUDA(c, launch_count_scan_write(d_imgs, bsegs, b.npairs, opt, m_j, m_d1, c->d_counts.as<int32_t>(),
                                              out_offsets_dev + b.first_pair, running_total, capacity, out_matches_dev,
                                              out_dist_dev, c->stream));
         c->prof_end();
-        c->launches += 3;
         total_units += nunits;
         total_rows += static_cast<int64_t>(nunits) * kUnitRows;
         if (dump && bi == 0 && dump->n > 0) {

@@ -102,7 +102,6 @@ int msfm_verify_pairs_dev(msfm_ctx* c, const int32_t* pairs_host, int32_t P, con
     MSFM_CUDA(c, launch_ransac_pairs(c->d_kp_tab.p, c->d_kp_slots.as<int32_t>(), reinterpret_cast<const long long*>(offsets_dev), matches_dev, P,
                                      opt->threshold, opt->confidence, opt->max_iters, mask_dev, counts_dev, c->num_sms, c->stream));
     c->prof_end();
-    c->launches += 1;
     return MSFM_OK;
 }
 

@@ -15,6 +15,7 @@
 // criterion is the agreement of the inlier sets (tests/test_verify_gpu.py).
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "launch_count.hpp"
 
 namespace msfm {
 namespace verify {
@@ -468,8 +469,8 @@ cudaError_t launch_ransac_pairs(const void* kps, const int32_t* pair_slots, cons
     cudaError_t e = cudaFuncSetAttribute(verify::ransac_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const int grid = P < num_sms * 2 ? P : num_sms * 2;
-    verify::ransac_pairs_kernel<<<grid, verify::kThreads, smem, st>>>(static_cast<const verify::KpDev*>(kps), pair_slots, offsets, matches, P,
-                                                                      threshold, confidence, max_iters, mask, counts);
+    { verify::ransac_pairs_kernel<<<grid, verify::kThreads, smem, st>>>(static_cast<const verify::KpDev*>(kps), pair_slots, offsets, matches, P,
+                                                                      threshold, confidence, max_iters, mask, counts); MSFM_COUNT_LAUNCH(); }
     return cudaGetLastError();
 }
 

@@ -423,3 +423,23 @@ def test_update_keeps_the_structure_for_the_same_pattern_and_rebuilds_for_anothe
         assert s1["termination"] == s2["termination"] and abs(s1["final_cost"] - s2["final_cost"]) <= 1e-6 * s2["final_cost"]
         fresh.close()
     ba.close()
+
+
+def test_launch_counter_counts_launch_sites(ctx):
+    """msfm_launch_count is incremented at the launch sites (csrc/launch_count.hpp), so known calls add known numbers:
+    evaluate = pose preparation + residual kernel; linearize = pose preparation + (long-track pre-pass) + fused kernel."""
+    P = bo.make_problem(12, 300, 5, 2)                     # no track longer than 32 views
+    ba = _create(ctx, P)
+    n0 = ctx.launch_count
+    ba.evaluate()
+    assert ctx.launch_count - n0 == 2
+    n0 = ctx.launch_count
+    ba.linearize(1e-4, want_S=False)
+    assert ctx.launch_count - n0 == 2 and ba.structure()["n_long_tracks"] == 0
+    ba.close()
+    Q = bo.make_long_track_problem()
+    ba = _create(ctx, Q)
+    n0 = ctx.launch_count
+    ba.linearize(1e-4, want_S=False)
+    assert ctx.launch_count - n0 == 3 and ba.structure()["n_long_tracks"] > 0
+    ba.close()

@@ -596,11 +596,14 @@ def c_oracle():
     lib.ba_oracle_linearize.restype = C.c_double
     lib.ba_oracle_linearize.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, ip, ip, ip, C.c_int, C.c_double,
                                         C.c_double, C.c_double, dp, dp]
+    lib.ba_oracle_linearize_mt.restype = C.c_double
+    lib.ba_oracle_linearize_mt.argtypes = [C.c_int] + lib.ba_oracle_linearize.argtypes
     return lib
 
 
-def c_linearize(P, inv_radius, lib=None):
-    """One evaluate + Schur-eliminate pass of the C oracle.  Returns (S, rhs, cost, seconds)."""
+def c_linearize(P, inv_radius, lib=None, threads=1):
+    """One evaluate + Schur-eliminate pass of the C oracle (threads > 1: the multi-threaded variant, an all-cores bound the reference
+    itself does not reach — it never sets Ceres' num_threads).  Returns (S, rhs, cost, seconds)."""
     import ctypes as C
     import time
     lib = lib or c_oracle()
@@ -617,8 +620,10 @@ def c_linearize(P, inv_radius, lib=None):
     rhs = np.zeros(6 * nf)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
     t0 = time.perf_counter()
-    cost = lib.ba_oracle_linearize(len(cams), len(pts), len(oc), cams.ctypes.data_as(dp), pts.ctypes.data_as(dp),
-                                   uv.ctypes.data_as(dp), oc.ctypes.data_as(ip), op.ctypes.data_as(ip),
-                                   cam_free.ctypes.data_as(ip), nf, float(P["fx"]), float(P["fy"]), float(inv_radius),
-                                   S.ctypes.data_as(dp), rhs.ctypes.data_as(dp))
+    args = (len(cams), len(pts), len(oc), cams.ctypes.data_as(dp), pts.ctypes.data_as(dp),
+            uv.ctypes.data_as(dp), oc.ctypes.data_as(ip), op.ctypes.data_as(ip),
+            cam_free.ctypes.data_as(ip), nf, float(P["fx"]), float(P["fy"]), float(inv_radius),
+            S.ctypes.data_as(dp), rhs.ctypes.data_as(dp))
+    # threads < 0: |threads| threads on one shared S with atomic updates (what large systems use; tests force it)
+    cost = lib.ba_oracle_linearize(*args) if threads in (0, 1) else lib.ba_oracle_linearize_mt(int(threads), *args)
     return S, rhs, cost, time.perf_counter() - t0

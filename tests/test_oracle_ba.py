@@ -158,6 +158,12 @@ def test_c_oracle_matches_python(golden_ba, name):
     np.testing.assert_allclose(S, g[f"{name}/S"], rtol=1e-9, atol=1e-7)
     np.testing.assert_allclose(rhs, g[f"{name}/rhs"], rtol=1e-9, atol=1e-7)
     assert abs(cost - float(g[f"{name}/cost"])) < 1e-9 * cost
+    # the multi-threaded variant (bench.py's all-cores figure): same sums in another order; both accumulation modes
+    for threads in (3, 8, -4):
+        S2, rhs2, cost2, _ = bo.c_linearize(P, 1e-4, lib, threads=threads)
+        np.testing.assert_allclose(S2, S, rtol=1e-11, atol=1e-9 * np.abs(S).max())
+        np.testing.assert_allclose(rhs2, rhs, rtol=1e-11, atol=1e-9 * np.abs(rhs).max())
+        assert abs(cost2 - cost) < 1e-12 * cost
 
 
 @pytest.mark.parametrize("name", NAMES)

@@ -45,7 +45,8 @@ def env_int(name, default):
 def make_descriptors_torch(n_img, n_desc, seed, device, distribution="S"):
     """Synthetic descriptor sets of SURVEY 8d, generated on the device.
     "S" SIFT-like: |N(0,1)| vectors, L2-normalised to 512, clipped to 255, rounded; image k>0 shares a planted 30 % of
-        image 0's descriptors (random slots, +-2 noise) so that the ratio / cross-check lists are non-trivial;
+        image 0's descriptors (random slots, +-2 noise) so that the ratio / cross-check lists are non-trivial; plus planted
+        duplicates and rows in the float-sqrt collapse range (plant_ties) so that the tie paths run in every pass;
     "D" dense overlap: the same with 90 % planted (most rows pass the ratio test: the worst case of the reverse pass);
     "U" i.i.d. uniform bytes (almost nothing passes the ratio test)."""
     import torch
@@ -70,8 +71,26 @@ def make_descriptors_torch(n_img, n_desc, seed, device, distribution="S"):
             src = torch.randperm(n_desc, generator=g, device=device)[:m]
             noise = torch.randint(-2, 3, (m, 128), generator=g, device=device).float()
             x[dst] = (base[src] + noise).clamp_(0, 255)
+        plant_ties(x, base, k)
         out[k] = x.to(torch.uint8)
     return out
+
+
+def plant_ties(x, base, k):
+    """Tie coverage of SURVEY 8d in every S / D image: rows 0-3 are image 0's rows 0-3 and rows 4-7 duplicate them, so a query
+    that matches one of them finds TWO columns at the best distance (OpenCV keeps the lower index, the ratio test then fails: the
+    exact path).  In every second image row 8 is all 255 and rows 9-11 differ from it in one component: matched against an
+    image without such rows all their distances are >= 2^22, where distinct integers share one float sqrt (the collapse range);
+    against an image that has them they are ties and near-ties at distance 0 / 1 / 2."""
+    if len(x) < 16:
+        return
+    x[0:4] = base[0:4]
+    x[4:8] = x[0:4]
+    if k % 2 == 0:
+        x[8:12] = 255
+        x[9, 0] = 254
+        x[10, 1] = 254
+        x[11, 0] = 253
 
 
 def make_descriptors_numpy(n_img, n_desc, seed):
@@ -88,6 +107,7 @@ def make_descriptors_numpy(n_img, n_desc, seed):
             dst = rng.permutation(n_desc)[:m]
             src = rng.permutation(n_desc)[:m]
             x[dst] = np.clip(base[src] + rng.integers(-2, 3, (m, 128)), 0, 255)
+        plant_ties(x, base, k)
         out[k] = x.astype(np.uint8)
     return out
 
@@ -739,7 +759,14 @@ def run_ours(args, rank, world, local_rank):
                                     "(profiles/r01_microbench.log); achieved/4770 = %.3f" % (achieved / 4770.0),
                     "avg_launch_ms": k1_avg_s * 1e3, "launches_timed": k1["launches"],
                     "kernel_share_of_step": k1["ms"] / ms_total if ms_total else None,
-                    "step_level_frac": step_frac}
+                    "step_level_frac": step_frac,
+                    # the INT32-ALU bound of the epilogue: per 128 x 256 accumulator tile of a CTA one VIMNMX3 per
+                    # two elements = 512 warp instructions, 3.7 cycles each per sub-partition with fresh operands
+                    # (profiles/r01b_microbench_pair.log) over 4 sub-partitions, against the 640 tensor cycles of the tile's
+                    # five MMAs: the reduction fits under the tensor work only because each warpgroup has two tile times per tile
+                    "epilogue_alu_bound": {"vimnmx3_warp_instructions_per_tile": 512, "cycles_per_instruction_per_subpartition": 3.7,
+                                           "alu_cycles_per_tile": 512 / 4 * 3.7, "tensor_cycles_per_tile": 640,
+                                           "alu_over_tensor": 512 / 4 * 3.7 / 640}}
         if ba_large and "roofline" in ba_large:
             roofline["k2"] = dict(ba_large["roofline"], workload=ba_large["workload"], observations_per_s=ba_large["value"],
                                   ms_per_iteration=ba_large["ms_per_iteration"], allreduce_ms=ba_large["allreduce_ms"])

@@ -464,6 +464,105 @@ def _two_view(rng, n_in, n_out, noise=0.4):
     return kp1, kp2, np.c_[perm1[order], perm2[order]].astype(np.int32), order < n_in
 
 
+def bench_dropin_database(n_img=32, n_desc=8192, cpu_pairs=6):
+    """SURVEY 8f-1, end to end as a user of the reference runs it: BruteFeatureMatcher(db).RunMatching() of the drop-in C++
+    classes (build/host_test) on a SQLite database in the reference's schema — float32 unit-norm descriptor blobs and keypoints
+    read from the database, one upload per image, all pairs matched (ratio 0.8, cross-check, max_distance 0.7), F-matrix
+    verification of every pair on the device, one matches row per pair written back (FeatureMatching.cpp:10-145).  The wall time is
+    that of the whole PROCESS (CUDA context creation and the SQLite I/O included).  Beside it the reference's per-pair CPU cost:
+    cv2 BFMatcher both directions on the float32 rows + cv2.findFundamentalMat, on a sample of pairs."""
+    import sqlite3
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "build", "host_test")
+    if not os.path.exists(exe):
+        return {"skipped": "build/host_test is missing (make)"}
+    rng = np.random.default_rng(2024)
+    K = np.array([[1449.2752980237, 0, 1080.0], [0, 1449.2752980237, 720.0], [0, 0, 1]])
+    X = np.c_[rng.uniform(-4, 4, n_desc), rng.uniform(-3, 3, n_desc), rng.uniform(6, 14, n_desc)]      # one 3-D point per base row
+
+    def sift_like(n):
+        x = np.abs(rng.standard_normal((n, 128), dtype=np.float32))
+        return np.clip(np.rint(x / np.linalg.norm(x, axis=1, keepdims=True) * 512.0), 0, 255)
+    base = sift_like(n_desc)
+    tmp = tempfile.mkdtemp(prefix="msfm_dropin_")
+    db = os.path.join(tmp, "bench.db")
+    con = sqlite3.connect(db)
+    con.executescript("""
+        CREATE TABLE images(image_id INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, name TEXT NOT NULL UNIQUE);
+        CREATE TABLE keypoints(image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+        CREATE TABLE colors(image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+        CREATE TABLE descriptors(image_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+        CREATE TABLE matches(pair_id INTEGER PRIMARY KEY NOT NULL, rows INTEGER NOT NULL, cols INTEGER NOT NULL, data BLOB);
+    """)
+    descs, kps = [], []
+    for k in range(n_img):
+        ang = 0.02 * k
+        R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+        t = np.array([-0.25 * k, 0.02 * k, 0.03 * k])
+        d = sift_like(n_desc)
+        kp = np.zeros((n_desc, 4), np.float32)
+        kp[:, 0] = rng.uniform(0, 2160, n_desc)
+        kp[:, 1] = rng.uniform(0, 1440, n_desc)
+        kp[:, 2] = rng.permutation(n_desc).astype(np.float32) + 1.0
+        m = int(0.3 * n_desc)
+        dst, src = rng.permutation(n_desc)[:m], rng.permutation(n_desc)[:m]
+        d[dst] = np.clip(base[src] + rng.integers(-2, 3, (m, 128)), 0, 255)
+        x = (K @ (R @ X[src].T + t[:, None])).T
+        kp[dst, :2] = (x[:, :2] / x[:, 2:] + rng.normal(0, 0.4, (m, 2))).astype(np.float32)      # planted rows see their 3-D point
+        con.execute("insert into images(image_id, name) values(?, ?)", (k, f"img{k}.jpg"))
+        con.execute("insert into keypoints values(?,?,?,?)", (k, n_desc, 4, kp.tobytes()))
+        con.execute("insert into descriptors values(?,?,?,?)", (k, n_desc, 128, (d / 512.0).astype(np.float32).tobytes()))
+        descs.append((d / 512.0).astype(np.float32))
+        kps.append(kp[:, :2].copy())
+    con.commit()
+    con.close()
+    n_pairs = n_img * (n_img - 1) // 2
+    t0 = time.perf_counter()
+    run = subprocess.run([exe, "match", db, "0"], capture_output=True, text=True, timeout=600)
+    wall = time.perf_counter() - t0
+    out = {"workload": f"BruteFeatureMatcher::RunMatching on a reference-schema SQLite database: {n_img} images x {n_desc} float32 descriptors, "
+                       f"all {n_pairs} pairs, geometric verification on",
+           "wall_s": wall, "returncode": run.returncode, "pairs_per_s": n_pairs / wall,
+           "descriptor_pairs_per_s": float(n_pairs) * n_desc * n_desc / wall,
+           "what": "whole process: CUDA context, SQLite reads of descriptors / keypoints, uploads, matching, verification, SQLite writes"}
+    if run.returncode != 0:
+        out["error"] = (run.stderr + run.stdout)[-500:]
+        return out
+    con = sqlite3.connect(db)
+    rows = con.execute("select count(*), sum(rows) from matches").fetchone()
+    con.close()
+    out["match_rows_written"], out["verified_matches"] = int(rows[0]), int(rows[1] or 0)
+    # the reference's cost per pair on this box's host cores, on a sample
+    try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count() or 1)
+        bf = cv2.BFMatcher(cv2.NORM_L2)
+        t0 = time.perf_counter()
+        for q in range(cpu_pairs):
+            i, j = q + 1, q
+            m12 = bf.knnMatch(descs[i], descs[j], k=2)
+            m21 = bf.knnMatch(descs[j], descs[i], k=2)
+            good = [a for a, b in m12 if a.distance < 0.8 * b.distance]
+            back = {a.queryIdx: a.trainIdx for a, b in m21 if a.distance < 0.8 * b.distance}
+            cross = [a for a in good if back.get(a.trainIdx, 0) == a.queryIdx and a.distance <= 0.7]
+            if len(cross) >= 8:
+                cv2.findFundamentalMat(kps[i][[a.queryIdx for a in cross]], kps[j][[a.trainIdx for a in cross]], cv2.FM_RANSAC, 3.0, 0.99)
+        per_pair = (time.perf_counter() - t0) / max(1, cpu_pairs)
+        out["cpu"] = {"s_per_pair": per_pair, "extrapolated_wall_s": per_pair * n_pairs, "sample_pairs": cpu_pairs, "cores": os.cpu_count(),
+                      "kind": "reference (cv2 BFMatcher on the float32 rows, both directions + ratio + cross-check + distance filter, "
+                              "cv2.findFundamentalMat), without its SQLite I/O"}
+        out["speedup_vs_cpu_extrapolated"] = per_pair * n_pairs / wall
+    except Exception as ex:      # cv2 missing: the GPU figure stands alone
+        out["cpu"] = {"error": repr(ex)}
+    try:
+        os.remove(db)
+        os.rmdir(tmp)
+    except OSError:
+        pass
+    return out
+
+
 def bench_verify_geometric(ctx, n_pairs=8128, n_scenes=64, n_in=534, n_out=229, cpu_pairs=64):
     """SURVEY 8f-1: FeatureUtils::FilterMatches (cv::findFundamentalMat FM_RANSAC 3.0 / 0.99, FeatureUtils.cpp:176-206) over the
     matches of every pair of the headline workload's size (8128 pairs x ~763 matches, 70 % true correspondences), batched on
@@ -712,6 +811,12 @@ def run_ours(args, rank, world, local_rank):
             geo = bench_verify_geometric(ctx)
         except Exception as ex:
             geo = {"error": repr(ex)}
+    dropin = None
+    if world == 1 and not args.no_extra:
+        try:
+            dropin = bench_dropin_database()
+        except Exception as ex:
+            dropin = {"error": repr(ex)}
     peaks = load_peaks()
     ba_out = None
     ba_large = None
@@ -809,7 +914,7 @@ def run_ours(args, rank, world, local_rank):
                 "roofline": roofline, "cpu_baseline": cpu, "verify": verify,
                 "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items() if v["launches"]},
                 "match_stats": stats, "distributions": dists_out, "target": target,
-                "geometric_verification": geo, "ba": ba_out, "ba_large": ba_large}
+                "geometric_verification": geo, "dropin_database": dropin, "ba": ba_out, "ba_large": ba_large}
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist:

@@ -151,21 +151,23 @@ void BruteFeatureMatcher::RunMatching() {
     database_ = cv::Ptr<Database>(new Database());
     database_->Open(database_path_);
     std::vector<Database::Image> images = database_->ReadAllImages();
-    for (size_t i = 0; i < images.size(); ++i) {                              // FeatureMatching.cpp:110-142
-        std::vector<std::pair<image_t, image_t>> image_pairs;
+    // The pair order is the reference's (FeatureMatching.cpp:110-142: for i, for j < i).  The reference also flushes at the end
+    // of every i because its batch is a list of descriptor Mats loaded for that image; here the descriptors are resident on the
+    // device and a batch is ONE device call (matching + verification) and one transaction, so batches are filled up to
+    // max_pairs_size across images: 32 images give 5 batches of <= 100 pairs instead of 31 batches of 1..31.
+    std::vector<std::pair<image_t, image_t>> image_pairs;
+    auto flush = [&]() {
+        if (image_pairs.empty()) return;
+        if (is_preemtive_) image_pairs = PreemptivelyFilterImagePairs(image_pairs);
+        MatchImagePairs(image_pairs);
+        image_pairs.clear();
+    };
+    for (size_t i = 0; i < images.size(); ++i)
         for (size_t j = 0; j < i; ++j) {
             image_pairs.push_back(std::make_pair(static_cast<image_t>(i), static_cast<image_t>(j)));
-            if (static_cast<int>(image_pairs.size()) == max_pairs_size_) {
-                if (is_preemtive_) image_pairs = PreemptivelyFilterImagePairs(image_pairs);
-                MatchImagePairs(image_pairs);
-                image_pairs.clear();
-            }
+            if (static_cast<int>(image_pairs.size()) >= std::max(1, max_pairs_size_)) flush();
         }
-        if (!image_pairs.empty()) {
-            if (is_preemtive_) image_pairs = PreemptivelyFilterImagePairs(image_pairs);
-            MatchImagePairs(image_pairs);
-        }
-    }
+    flush();
     database_->Close();
 }
 

@@ -1,6 +1,7 @@
 // Test driver of the drop-in C++ classes (run by tests/test_host_cpp.py).
 //   host_test cpu <tmp.db>             Database round trip, pair ids, CrossCheck quirk, distance filter  (no GPU)
-//   host_test match <db> <preempt 0|1> [noverify]  BruteFeatureMatcher(db).RunMatching() on a database made by the Python test
+//   host_test match <db> <preempt 0|1> [noverify] [quiet] [max_pairs_size]  BruteFeatureMatcher(db).RunMatching() on a database made by the
+//                                      Python test; prints the time of RunMatching (bench.py: dropin_database)
 //   host_test seq <db> [noverify]                  SequentialFeatureMatcher(db).RunMatching()
 //   (noverify = the explicit opt-out of the geometric verification, for tests of the exact match lists)
 //   host_test two <a.u8> <na> <b.u8> <nb> <out.txt>   FeatureUtils::ComputeMatches / ComputeCrossMatches on raw files
@@ -13,6 +14,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -364,9 +366,21 @@ int main(int argc, char** argv) {
     const std::string mode = argv[1];
     if (mode == "cpu" && argc >= 3) return test_cpu(argv[2]);
     if (mode == "match" && argc >= 4) {
-        BruteFeatureMatcher matcher(argv[2], 100, std::atoi(argv[3]) != 0);
-        if (argc >= 5 && std::string(argv[4]) == "noverify") matcher.SetGeometricFilter(FeatureMatcher::GeometricFilter());
+        // optional arguments in any order: "noverify", "quiet", a number = max_pairs_size (default 100 like the reference)
+        int max_pairs = 100;
+        bool noverify = false, quiet = false;
+        for (int a = 4; a < argc; ++a) {
+            const std::string arg = argv[a];
+            if (arg == "noverify") noverify = true;
+            else if (arg == "quiet") quiet = true;
+            else if (std::atoi(argv[a]) > 0) max_pairs = std::atoi(argv[a]);
+        }
+        BruteFeatureMatcher matcher(argv[2], max_pairs, std::atoi(argv[3]) != 0);
+        if (noverify) matcher.SetGeometricFilter(FeatureMatcher::GeometricFilter());
+        if (quiet) matcher.SetVerbose(false);
+        const auto t0 = std::chrono::steady_clock::now();
         matcher.RunMatching();
+        std::printf("RunMatching: %.6f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
         return 0;
     }
     if (mode == "seq" && argc >= 3) {

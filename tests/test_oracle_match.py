@@ -63,6 +63,28 @@ def test_against_cv2_fresh_inputs():
         np.testing.assert_array_equal(d1, d2)
 
 
+def test_bench_workload_with_planted_ties_is_pinned_to_cv2():
+    """The benchmark's S images (bench.py: make_descriptors_numpy + plant_ties: duplicated rows = two columns at the best
+    distance; all-255 rows = every distance in the float-sqrt collapse range when the other image has none) through the oracle
+    and through cv2 itself: same neighbours, same distances, and the planted cases really occur."""
+    cv2 = pytest.importorskip("cv2")
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    d = bench.make_descriptors_numpy(3, 1500, 9)
+    for (i, j) in ((2, 1), (1, 2), (2, 0)):
+        i1, d1, dd1 = mo.knn2(d[i], d[j])
+        i2, d2 = mo.cv2_knn2(d[i], d[j])
+        np.testing.assert_array_equal(i1, i2)
+        np.testing.assert_array_equal(d1, d2)
+    idx, dist, d2sq = mo.knn2(d[2], d[1])
+    assert (dist[:8, 0] == dist[:8, 1]).all() and (idx[:4, 0] == np.arange(4)).all() and (idx[:4, 1] == np.arange(4, 8)).all()   # ties: lowest index first
+    assert (d2sq[8:12, 0] >= 1 << 22).all()                                   # even image vs odd image: collapse range
+    m, _ = mo.match_image_pair(d[2], d[1], 0.8, -1.0, True, True)
+    assert not (m[:, 0] < 12).any()                                           # neither the tied nor the far rows give a match
+
+
 def test_filter_by_distance():
     m = np.array([[0, 1], [1, 2], [2, 3]], np.int32)
     d = np.array([0.5, 0.7, 0.70001], np.float32)

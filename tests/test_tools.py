@@ -54,3 +54,22 @@ def test_round2_evidence_is_consistent():
         ln = json.loads([l for l in open(os.path.join(ROOT, "profiles", f"r02_bench_n{n}_sharded_configs2.json")) if l.startswith("{")][-1])
         assert ln["n_gpus"] == n and len(ln["config"]["per_rank_ms_per_step"]) == n and "1329 images" in ln["config"]["workload"]
         assert ln["ba_large"]["allreduce_ms"] > 0 and ln["ba_large"]["allreduce_message_bytes"] < 13e6
+
+
+def test_launch_shares_tool_on_the_committed_launch_lists():
+    """tools/launch_shares.py on the committed ncu launch lists: K1 dominates the matching pass, the band Cholesky and the fused
+    linearisation kernel the BA solve (the shares DESIGN.md / profiles/README.md quote)."""
+    import subprocess
+    import sys
+    def shares(name):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_shares.py"), os.path.join(ROOT, "profiles", name)],
+                             capture_output=True, text=True, check=True).stdout
+        rows = {}
+        for line in out.splitlines():
+            if " share " in line:
+                rows[line.split()[0]] = float(line.split("share")[1].replace("%", ""))
+        return rows
+    m = shares("r02_launches_match.csv")
+    assert 75.0 < m["k1::match_pair_kernel<0>"] < 90.0 and m["resolve_rows_kernel"] < 15.0
+    b = shares("r02_launches_ba_band.csv")
+    assert b["band::band_cholesky_kernel"] + b["ba::fused_linearize_kernel<0>"] > 80.0
